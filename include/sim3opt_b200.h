@@ -1,0 +1,149 @@
+/*
+ * sim3opt_b200.h -- C ABI of the B200-native Sim3 / SE3 nonlinear least-squares back-end.
+ *
+ * This is the drop-in boundary: everything the reference does through
+ * g2o between "graph is built" and "estimates are read back" goes through these calls.
+ *
+ *   reference call site (kitti_surf.cpp)                         replacement
+ *   ------------------------------------------------------------ ---------------------------
+ *   new OptimizationAlgorithmLevenberg(BlockSolverX(LinearSolverEigen))  :552-558,:726-735
+ *                                                                 s3o_create / s3o_set_lm / s3o_set_pcg
+ *   optimizer.addVertex(VertexSim3Expmap: setEstimate,setFixed)  :597-622   s3o_set_vertices
+ *   optimizer.addEdge(EdgeSim3: setVertex,setMeasurement,information) :624-670  s3o_set_edges
+ *   optimizer.initializeOptimization()                           :674       s3o_build_structure
+ *   optimizer.optimize(100)                                      :675       s3o_optimize
+ *   vSim3->estimate()                                            :688-689   s3o_get_vertices
+ *   G2oVertexScaleTrans / G2oEdgeScaleTrans graph                :779-884   kind S3O_KIND_SCALE_TRANS
+ *   edge->setRobustKernel(RobustKernelHuber, delta)   bal_example.cpp:149-153   s3o_set_robust
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all array arguments are HOST pointers borrowed for the
+ *     duration of the call (copied to the device inside); results are copied into caller buffers.
+ *   - every function returns 0 on success or a negative s3o_status; s3o_last_error() gives text.
+ *     Nothing throws across this boundary.  There is no CPU fallback: without a CUDA device
+ *     s3o_create fails with S3O_ERR_CUDA.
+ *   - Sim3 state   : 8 doubles [qx qy qz qw tx ty tz s] (g2o::Sim3: x -> s*(R x) + t)
+ *     tangent      : 7 doubles [omega upsilon sigma] (g2o order)
+ *     scale-trans  : 4 doubles [s tx ty tz], aux = fixed rotation quaternion [qx qy qz qw]
+ *     matrices     : row-major
+ *   - one host thread per problem; distinct problems are independent (SURVEY.md 8b "Threading").
+ */
+#ifndef SIM3OPT_B200_H
+#define SIM3OPT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct s3o_problem s3o_problem;
+
+enum s3o_status {
+    S3O_OK = 0,
+    S3O_ERR_INVALID = -1,   /* bad argument / call order */
+    S3O_ERR_CUDA = -2,      /* CUDA runtime failure (no device, OOM, launch error) */
+    S3O_ERR_NCCL = -3,
+    S3O_ERR_IO = -4,
+    S3O_ERR_UNSUPPORTED = -5
+};
+
+enum s3o_kind { S3O_KIND_SIM3 = 0, S3O_KIND_SCALE_TRANS = 1, S3O_KIND_SCALE = 2, S3O_KIND_BA = 3 };
+enum s3o_jacobian { S3O_JAC_NUMERIC = 0, S3O_JAC_ANALYTIC = 1 };
+/* robust kernels: g2o RobustKernelHuber (param = delta) and the PTAM M-estimators of
+ * MEstimator.h:54-198 (param = sigma squared) */
+enum s3o_robust { S3O_ROBUST_NONE = 0, S3O_ROBUST_HUBER = 1, S3O_ROBUST_PTAM_TUKEY = 2,
+                  S3O_ROBUST_PTAM_CAUCHY = 3, S3O_ROBUST_PTAM_HUBER = 4, S3O_ROBUST_PTAM_LS = 5 };
+/* Sim3 exp/log small-angle coefficients.  REFERENCE (default): exactly as written at
+ * sim3_rv.h:143-181,:261-303 -- including B = ((sigma^2/2 - sigma + 1) s)/sigma^3 (no "-1") in the
+ * theta<eps, |sigma|>=eps branch and R = I + Om + Om^2 -- which is what the reference's pinned g2o
+ * computes.  CORRECTED: the consistent Taylor limits (B with "-1", R = I + Om + Om^2/2).  The
+ * as-written B is O(1/sigma^3) off, which makes the objective discontinuous whenever a residual
+ * rotation drops below 4.5e-3 rad while sigma != 0; graphs that must converge to a minimum
+ * (the synthetic configs) are run in CORRECTED mode on both the CPU and the GPU side. */
+enum s3o_math_mode { S3O_MATH_REFERENCE = 0, S3O_MATH_CORRECTED = 1 };
+/* g2o OptimizationAlgorithm::SolverResult */
+enum s3o_solver_result { S3O_RESULT_TERMINATE = 2, S3O_RESULT_OK = 1, S3O_RESULT_FAIL = -1 };
+
+const char *s3o_last_error(void);
+int s3o_version(void);
+int s3o_device_count(void);
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+int s3o_create(int kind, int device, s3o_problem **out);
+int s3o_destroy(s3o_problem *p);
+/* run all work of this problem on an existing CUDA stream (cudaStream_t passed as void*);
+ * NULL = a private non-blocking stream created by s3o_create */
+int s3o_set_stream(s3o_problem *p, void *cuda_stream);
+
+/* ---- graph (replaces addVertex / addEdge) --------------------------------------------- */
+/* est: n x est_dim (SIM3 8, SCALE_TRANS 4, SCALE 1); fixed: n bytes or NULL;
+ * aux: n x 4 rotation quaternions (SCALE_TRANS only, vST->Rw2i at kitti_surf.cpp:792-793) */
+int s3o_set_vertices(s3o_problem *p, int n, const double *est, const uint8_t *fixed, const double *aux);
+/* v0/v1: vertex indices (EdgeSim3 setVertex(0,.) / setVertex(1,.)); meas: n x est_dim;
+ * info: n x d x d row-major symmetric, or NULL for identity (matLambdasim at kitti_surf.cpp:592) */
+int s3o_set_edges(s3o_problem *p, int n, const int32_t *v0, const int32_t *v1, const double *meas,
+                  const double *info);
+/* overwrite the current estimates only (same n as s3o_set_vertices); structure is kept */
+int s3o_set_estimates(s3o_problem *p, const double *est);
+int s3o_set_robust(s3o_problem *p, int kind, double param);
+int s3o_set_jacobian_mode(s3o_problem *p, int mode, double h /* numeric step, g2o: 1e-9 */);
+int s3o_set_math_mode(s3o_problem *p, int mode);
+/* tau (g2o 1e-5), user lambda init (<=0: tau*max diag), maxTrialsAfterFailure (g2o 10) */
+int s3o_set_lm(s3o_problem *p, double tau, double user_lambda_init, int max_trials);
+/* block-Jacobi PCG: relative residual tolerance |r|/|b| and iteration cap */
+int s3o_set_pcg(s3o_problem *p, double rel_tol, int max_iter);
+
+/* ---- structure (replaces initializeOptimization + BlockSolver::buildStructure) -------- */
+int s3o_build_structure(s3o_problem *p, int *n_free, int *n_blocks);
+/* g2o-order upper block-CCS of Hpp: colptr[n_free+1], rowidx[n_blocks] (rows <= col, ascending) */
+int s3o_get_structure(s3o_problem *p, int32_t *colptr, int32_t *rowidx);
+/* Hessian index of every vertex (fixed -> -1) */
+int s3o_get_hessian_index(s3o_problem *p, int32_t *hidx);
+
+/* Host-only twin of the structure build (no device needed): fills the g2o-order upper block-CCS
+ * for a graph given as plain arrays.  colptr must hold n_vertices+1 ints, rowidx n_vertices+n_edges
+ * ints (upper bounds); hidx (may be NULL) n_vertices ints. */
+int s3o_host_structure(int n_vertices, const uint8_t *fixed, int n_edges, const int32_t *v0, const int32_t *v1,
+                       int *n_free, int *n_blocks, int32_t *colptr, int32_t *rowidx, int32_t *hidx);
+
+/* ---- lock-step pieces (each mirrors one g2o step; used by the parity tests) ------------ */
+int s3o_chi2(s3o_problem *p, double *chi2);                 /* computeActiveErrors + activeRobustChi2 */
+int s3o_edge_errors(s3o_problem *p, double *err /* n_edges x d, caller's edge order */);
+int s3o_linearize(s3o_problem *p);                          /* BlockSolver::buildSystem */
+/* blocks in the g2o CCS order of s3o_get_structure, each d x d row-major; b: n_free*d */
+int s3o_get_hessian(s3o_problem *p, double *blocks, double *b);
+int s3o_max_diag(s3o_problem *p, double *max_diag);
+/* solve (H + lambda I) x = b by block-Jacobi PCG; x: n_free*d (may be NULL) */
+int s3o_solve(s3o_problem *p, double lambda, double *x, int *pcg_iters, double *rel_residual);
+/* y = (H + lambda I) x on the device (x, y: n_free*d host arrays) -- for backward-error checks */
+int s3o_hessian_multiply(s3o_problem *p, double lambda, const double *x, double *y);
+int s3o_update(s3o_problem *p, const double *x);            /* oplus on every free vertex */
+
+/* ---- the hot call (replaces optimizer.optimize(n)) ------------------------------------- */
+/* hist (may be NULL): per LM iteration [chi2, lambda, trials, rho, pcg_iters]; returns via
+ * out-params the number of iterations run (g2o's return value), final chi2 and lambda.
+ * stop_rel_gain > 0 adds g2o's optional gain rule 0 <= (chi2_prev-chi2)/chi2 < gain. */
+int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterations,
+                 double *final_chi2, double *final_lambda, double *hist, int hist_cap);
+int s3o_get_vertices(s3o_problem *p, double *est);
+
+/* ---- statistics ------------------------------------------------------------------------ */
+typedef struct s3o_stats {
+    double ms_linearize, ms_solve, ms_chi2, ms_update, ms_total; /* CUDA-event time, last optimize */
+    int64_t kernel_launches;   /* kernels launched by this problem since create / reset */
+    int64_t pcg_iterations;    /* PCG iterations since create / reset */
+    int64_t lm_iterations, lm_trials;
+    int64_t h2d_bytes, d2h_bytes;
+    int32_t n_vertices, n_free, n_edges, n_blocks, dim;
+} s3o_stats;
+int s3o_get_stats(s3o_problem *p, s3o_stats *out);
+int s3o_reset_stats(s3o_problem *p);
+
+/* ---- PTAM sigma estimate (MEstimator.h FindSigmaSquared) on the current edge chi2 values - */
+int s3o_estimate_sigma_squared(s3o_problem *p, int robust_kind, double *sigma_squared);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIM3OPT_B200_H */

@@ -17,6 +17,15 @@
 
 static const double SIM3_EPS = 0.00001; /* sim3_rv.h:133, :258 */
 
+/* ORC_MATH_REFERENCE (default): coefficients exactly as written in the reference, including the
+ * small-angle / non-zero-sigma B of sim3_rv.h:165,:291 (no "-1") and R = I + Om + Om^2.
+ * ORC_MATH_CORRECTED: B = ((sigma^2/2 - sigma + 1) s - 1)/sigma^3 and R = I + Om + Om^2/2, i.e. the
+ * consistent Taylor limits (what later g2o releases ship); needed wherever LM must converge on
+ * graphs whose residuals enter the small-angle branch with sigma != 0. */
+static int g_math_mode = ORC_MATH_REFERENCE;
+void orc_set_math_mode(int mode) { g_math_mode = mode; }
+int orc_get_math_mode(void) { return g_math_mode; }
+
 void orc_quat_to_rot(const double q[4], double R[9]) {
     const double x = q[0], y = q[1], z = q[2], w = q[3];
     const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
@@ -104,7 +113,10 @@ static void sim3_abc(double sigma, double s, double theta, int small_angle, doub
         if (small_angle) {
             const double sigma2 = sigma * sigma;
             *A = ((sigma - 1) * s + 1) / sigma2;
-            *B = ((0.5 * sigma2 - sigma + 1) * s) / (sigma2 * sigma); /* as written at sim3_rv.h:165 */
+            if (g_math_mode == ORC_MATH_CORRECTED)
+                *B = ((0.5 * sigma2 - sigma + 1) * s - 1) / (sigma2 * sigma);
+            else
+                *B = ((0.5 * sigma2 - sigma + 1) * s) / (sigma2 * sigma); /* as written at sim3_rv.h:165 */
         } else {
             const double a = s * sin(theta);
             const double b = s * cos(theta);
@@ -129,7 +141,8 @@ void orc_sim3_exp(const double v[7], double S[8]) {
     const int small_angle = theta < SIM3_EPS;
     sim3_abc(sigma, s, theta, small_angle, &A, &B, &C);
     if (small_angle) {
-        for (int i = 0; i < 9; ++i) R[i] = Omega[i] + Omega2[i];
+        const double k2 = g_math_mode == ORC_MATH_CORRECTED ? 0.5 : 1.0;
+        for (int i = 0; i < 9; ++i) R[i] = Omega[i] + k2 * Omega2[i];
         R[0] += 1; R[4] += 1; R[8] += 1;
     } else {
         const double k1 = sin(theta) / theta, k2 = (1 - cos(theta)) / (theta * theta);

@@ -38,6 +38,9 @@ extern "C" {
 #endif
 
 /* ---- Lie-group math (sim3_rv.h conventions, g2o tangent order) ---------- */
+enum { ORC_MATH_REFERENCE = 0, ORC_MATH_CORRECTED = 1 };
+void orc_set_math_mode(int mode); /* process-wide; see lie.c */
+int orc_get_math_mode(void);
 void orc_quat_to_rot(const double q[4], double R[9]);
 void orc_rot_to_quat(const double R[9], double q[4]);
 void orc_sim3_exp(const double v[7], double S[8]);

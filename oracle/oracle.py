@@ -146,6 +146,13 @@ def sim3_edge_jac_analytic(Cm, Si, Sj):
     return Ji.reshape(7, 7), Jj.reshape(7, 7)
 
 
+MATH_REFERENCE, MATH_CORRECTED = 0, 1
+
+
+def set_math_mode(mode):
+    lib().orc_set_math_mode(int(mode))
+
+
 def robustify(kind, param, e2):
     rho = np.zeros(3)
     lib().orc_robustify(kind, param, e2, _d(rho))

@@ -1,0 +1,10 @@
+"""sim3opt_b200 -- B200-native Sim3/SE3 nonlinear least-squares back-end (host-side Python mirror).
+
+The product is the C-ABI shared library sim3opt_b200/lib/libsim3opt_b200.so (include/sim3opt_b200.h);
+this package only binds it for tests and bench.py.
+"""
+from .api import (Problem, S3OError, KIND_SIM3, KIND_SCALE_TRANS, KIND_SCALE, JAC_NUMERIC, JAC_ANALYTIC,
+                  ROBUST_NONE, ROBUST_HUBER, ROBUST_PTAM_TUKEY, ROBUST_PTAM_CAUCHY, ROBUST_PTAM_HUBER,
+                  ROBUST_PTAM_LS)
+
+__all__ = ["Problem", "S3OError"]

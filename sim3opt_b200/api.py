@@ -1,0 +1,204 @@
+"""Thin Python mirror of the C ABI (include/sim3opt_b200.h) used by tests and bench.py.
+
+Every method is one C call; no arithmetic happens in Python.  The object plays the role of
+g2o::SparseOptimizer + OptimizationAlgorithmLevenberg for one graph (kitti_surf.cpp:552-558).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+KIND_SIM3, KIND_SCALE_TRANS, KIND_SCALE, KIND_BA = 0, 1, 2, 3
+JAC_NUMERIC, JAC_ANALYTIC = 0, 1
+MATH_REFERENCE, MATH_CORRECTED = 0, 1
+ROBUST_NONE, ROBUST_HUBER, ROBUST_PTAM_TUKEY, ROBUST_PTAM_CAUCHY, ROBUST_PTAM_HUBER, ROBUST_PTAM_LS = range(6)
+
+_EST_DIM = {KIND_SIM3: 8, KIND_SCALE_TRANS: 4, KIND_SCALE: 1}
+_DIM = {KIND_SIM3: 7, KIND_SCALE_TRANS: 4, KIND_SCALE: 1}
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_up = C.POINTER(C.c_uint8)
+
+
+class S3OError(RuntimeError):
+    pass
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Problem:
+    def __init__(self, kind=KIND_SIM3, device=0, stream=None):
+        self.L = _lib.load()
+        self.kind = kind
+        if kind not in _DIM:
+            raise S3OError(f"unsupported kind {kind}")
+        self.d = _DIM[kind]
+        self.est_dim = _EST_DIM[kind]
+        h = C.c_void_p()
+        self._check(self.L.s3o_create(kind, device, C.byref(h)))
+        self.h = h
+        self.nv = self.ne = 0
+        if stream is not None:
+            self.set_stream(stream)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise S3OError(f"s3o error {rc}: {self.L.s3o_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.s3o_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_handle):
+        self._check(self.L.s3o_set_stream(self.h, C.c_void_p(int(cuda_stream_handle) if cuda_stream_handle else None)))
+
+    # ---- graph -------------------------------------------------------------------
+    def set_vertices(self, est, fixed=None, aux=None):
+        est = _f64(est).reshape(-1, self.est_dim)
+        self.nv = est.shape[0]
+        fx = np.zeros(self.nv, np.uint8) if fixed is None else np.ascontiguousarray(fixed, np.uint8)
+        auxp = None
+        if aux is not None:
+            aux = _f64(aux).reshape(self.nv, 4)
+            auxp = _d(aux)
+        self._check(self.L.s3o_set_vertices(self.h, self.nv, _d(est), fx.ctypes.data_as(_up), auxp))
+
+    def set_edges(self, v0, v1, meas, info=None):
+        v0 = np.ascontiguousarray(v0, np.int32)
+        v1 = np.ascontiguousarray(v1, np.int32)
+        meas = _f64(meas).reshape(-1, self.est_dim)
+        self.ne = len(v0)
+        infop = None
+        if info is not None:
+            info = _f64(info).reshape(self.ne, self.d, self.d)
+            infop = _d(info)
+        self._check(self.L.s3o_set_edges(self.h, self.ne, v0.ctypes.data_as(_ip), v1.ctypes.data_as(_ip), _d(meas), infop))
+
+    def set_estimates(self, est):
+        est = _f64(est).reshape(self.nv, self.est_dim)
+        self._check(self.L.s3o_set_estimates(self.h, _d(est)))
+
+    def set_robust(self, kind, param=0.0): self._check(self.L.s3o_set_robust(self.h, kind, float(param)))
+    def set_jacobian_mode(self, mode, h=0.0): self._check(self.L.s3o_set_jacobian_mode(self.h, mode, float(h)))
+    def set_math_mode(self, mode): self._check(self.L.s3o_set_math_mode(self.h, int(mode)))
+    def set_lm(self, tau=0.0, lambda_init=0.0, max_trials=0): self._check(self.L.s3o_set_lm(self.h, tau, lambda_init, max_trials))
+    def set_pcg(self, rel_tol=0.0, max_iter=0): self._check(self.L.s3o_set_pcg(self.h, rel_tol, max_iter))
+
+    # ---- structure ---------------------------------------------------------------
+    def build_structure(self):
+        nf, nb = C.c_int(0), C.c_int(0)
+        self._check(self.L.s3o_build_structure(self.h, C.byref(nf), C.byref(nb)))
+        self.num_free, self.num_blocks = nf.value, nb.value
+        colptr = np.zeros(nf.value + 1, np.int32)
+        rowidx = np.zeros(max(nb.value, 1), np.int32)
+        self._check(self.L.s3o_get_structure(self.h, colptr.ctypes.data_as(_ip), rowidx.ctypes.data_as(_ip)))
+        return colptr, rowidx[:nb.value]
+
+    def hessian_index(self):
+        h = np.zeros(self.nv, np.int32)
+        self._check(self.L.s3o_get_hessian_index(self.h, h.ctypes.data_as(_ip)))
+        return h
+
+    # ---- lock-step pieces --------------------------------------------------------
+    def chi2(self):
+        out = C.c_double(0)
+        self._check(self.L.s3o_chi2(self.h, C.byref(out)))
+        return out.value
+
+    def edge_errors(self):
+        e = np.zeros((self.ne, self.d))
+        self._check(self.L.s3o_edge_errors(self.h, _d(e)))
+        return e
+
+    def linearize(self):
+        self._check(self.L.s3o_linearize(self.h))
+        st = self.stats()
+        H = np.zeros((st["n_blocks"], self.d, self.d))
+        b = np.zeros(st["n_free"] * self.d)
+        self._check(self.L.s3o_get_hessian(self.h, _d(H), _d(b)))
+        return H, b
+
+    def linearize_only(self):
+        self._check(self.L.s3o_linearize(self.h))
+
+    def max_diag(self):
+        out = C.c_double(0)
+        self._check(self.L.s3o_max_diag(self.h, C.byref(out)))
+        return out.value
+
+    def solve(self, lam):
+        st = self.stats()
+        x = np.zeros(st["n_free"] * self.d)
+        it, rel = C.c_int(0), C.c_double(0)
+        rc = self.L.s3o_solve(self.h, float(lam), _d(x), C.byref(it), C.byref(rel))
+        if rc not in (0, -1) or (rc == -1 and self.L.s3o_last_error()):
+            pass
+        return rc, x, it.value, rel.value
+
+    def hessian_multiply(self, lam, x):
+        x = _f64(x)
+        y = np.zeros_like(x)
+        self._check(self.L.s3o_hessian_multiply(self.h, float(lam), _d(x), _d(y)))
+        return y
+
+    def update(self, x):
+        x = _f64(x)
+        self._check(self.L.s3o_update(self.h, _d(x)))
+
+    # ---- the hot call ------------------------------------------------------------
+    def optimize(self, max_iter, stop_rel_gain=0.0):
+        hist = np.zeros((max(max_iter, 1), 5))
+        n, chi2, lam = C.c_int(0), C.c_double(0), C.c_double(0)
+        self._check(self.L.s3o_optimize(self.h, max_iter, stop_rel_gain, C.byref(n), C.byref(chi2), C.byref(lam),
+                                        _d(hist), max_iter))
+        return n.value, chi2.value, lam.value, hist[:max(n.value, 0)]
+
+    def vertices(self):
+        est = np.zeros((self.nv, self.est_dim))
+        self._check(self.L.s3o_get_vertices(self.h, _d(est)))
+        return est
+
+    def stats(self):
+        st = _lib.Stats()
+        self._check(self.L.s3o_get_stats(self.h, C.byref(st)))
+        return {name: getattr(st, name) for name, _ in _lib.Stats._fields_}
+
+    def reset_stats(self): self._check(self.L.s3o_reset_stats(self.h))
+
+    def estimate_sigma_squared(self, robust_kind):
+        out = C.c_double(0)
+        self._check(self.L.s3o_estimate_sigma_squared(self.h, robust_kind, C.byref(out)))
+        return out.value
+
+
+def host_structure(n_vertices, fixed, v0, v1):
+    """g2o-order upper block-CCS from plain arrays, computed on the host (no device needed)."""
+    L = _lib.load()
+    v0 = np.ascontiguousarray(v0, np.int32)
+    v1 = np.ascontiguousarray(v1, np.int32)
+    fx = np.zeros(n_vertices, np.uint8) if fixed is None else np.ascontiguousarray(fixed, np.uint8)
+    nf, nb = C.c_int(0), C.c_int(0)
+    colptr = np.zeros(n_vertices + 1, np.int32)
+    rowidx = np.zeros(n_vertices + len(v0) + 1, np.int32)
+    hidx = np.zeros(max(n_vertices, 1), np.int32)
+    rc = L.s3o_host_structure(n_vertices, fx.ctypes.data_as(_up), len(v0), v0.ctypes.data_as(_ip),
+                              v1.ctypes.data_as(_ip), C.byref(nf), C.byref(nb), colptr.ctypes.data_as(_ip),
+                              rowidx.ctypes.data_as(_ip), hidx.ctypes.data_as(_ip))
+    if rc != 0:
+        raise S3OError(f"s3o error {rc}: {L.s3o_last_error().decode()}")
+    return colptr[:nf.value + 1].copy(), rowidx[:nb.value].copy(), hidx[:n_vertices].copy()

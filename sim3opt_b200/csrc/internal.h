@@ -1,0 +1,48 @@
+// internal.h -- shared declarations of the sim3opt_b200 library (host side).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/sim3opt_b200.h"
+
+namespace s3o {
+
+void set_error(const char *fmt, ...);
+
+#define S3O_CUDA(call)                                                                      \
+    do {                                                                                    \
+        cudaError_t _e = (call);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            s3o::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call,               \
+                           cudaGetErrorString(_e));                                         \
+            return S3O_ERR_CUDA;                                                            \
+        }                                                                                   \
+    } while (0)
+
+inline int pad32(int n) { return (n + 31) & ~31; }
+
+// Host-side result of the structure build.
+struct HostStructure {
+    int nv = 0, ne = 0;          // vertices, user edges
+    int nf = 0, nb = 0;          // free vertices, upper blocks
+    int ne_act = 0;              // active edges (at least one free end), in sorted order
+    std::vector<int32_t> hidx;   // [nv] Hessian index or -1
+    std::vector<int32_t> free2v; // [nf]
+    std::vector<int32_t> perm;   // [ne_act] sorted position -> user edge index
+    std::vector<int32_t> sv0, sv1;      // [ne_act] vertex ids in sorted order
+    std::vector<int32_t> e_blk;         // [ne_act] off-diagonal block (BSR index) or -1
+    std::vector<int32_t> rowptr, colidx;        // BSR upper, diagonal first in each row
+    std::vector<int32_t> blk_ebeg, blk_eend;    // [nb] sorted-edge range feeding each off-diag block
+                                                //      (diag blocks: empty range)
+    std::vector<int32_t> colT_ptr, colT_blk;    // [nf+1], [nb-nf]: off-diag blocks by column (rows ascending)
+    std::vector<int32_t> inc_ptr, inc_ent;      // [nf+1], incidences: (sorted edge << 1) | side
+    std::vector<int32_t> ccs_colptr, ccs_rowidx; // g2o-order upper block-CCS
+    std::vector<int32_t> ccs2bsr;               // [nb] CCS position -> BSR block index
+};
+
+void build_structure_host(int nv, const uint8_t *fixed, int ne, const int32_t *v0, const int32_t *v1,
+                          HostStructure &S);
+
+}  // namespace s3o

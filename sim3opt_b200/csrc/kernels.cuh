@@ -1,0 +1,83 @@
+// kernels.cuh -- device data layout and launcher declarations.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace s3o {
+
+// Device scalars of the PCG / LM bookkeeping.  Everything the inner loop needs stays on the
+// device; the host reads this struct back once per LM trial (and per PCG batch).
+struct DevScalars {
+    double rz;        // r.z of the current iterate
+    double pq;        // p.(H+lambda I)p
+    double alpha, beta;
+    double rr, rr0;   // |r|^2, |b|^2
+    double tol2;      // (rel_tol)^2
+    double chi2;      // last chi2 reduction
+    double scale;     // sum x_j (lambda x_j + b_j)   (computeScale)
+    double maxdiag;   // max |H_jj|                  (computeLambdaInit)
+    int done;         // 0 running, 1 converged, 2 iteration cap, 3 breakdown
+    int iters, max_iter;
+    int precond_fail;
+    unsigned counters[8];
+};
+
+struct GraphDev {
+    int kind, d, est_dim, ninfo;
+    int nv, nv_pad, ne, ne_pad, nf, nb;
+    const double *est;       // [est_dim][nv_pad]
+    const double *aux;       // [4][nv_pad] or null
+    const int32_t *hidx;     // [nv]
+    const int32_t *sv0, *sv1; // [ne]
+    const double *meas;      // [est_dim][ne_pad]
+    const double *info;      // [ninfo][ne_pad] or null (identity)
+    int robust_kind;
+    double robust_param;
+    bool math_corrected;     // s3o_set_math_mode
+};
+
+struct StructDev {
+    const int32_t *rowptr, *colidx, *blk_row;
+    const int32_t *blk_ebeg, *blk_eend;
+    const int32_t *colT_ptr, *colT_blk;
+    const int32_t *inc_ptr, *inc_ent;
+    const int32_t *e_blk;
+};
+
+constexpr int kMaxPartials = 4096;
+
+// ---- packing ---------------------------------------------------------------------------
+void launch_pack_vertices(const double *aos, int n, int n_pad, int dim, double *soa, cudaStream_t st);
+void launch_unpack_vertices(const double *soa, int n, int n_pad, int dim, double *aos, cudaStream_t st);
+void launch_pack_edges(const double *meas_aos, const double *info_aos, const int32_t *perm, int ne, int ne_pad,
+                       int est_dim, int d, double *meas, double *info, cudaStream_t st);
+
+// ---- per-edge --------------------------------------------------------------------------
+void launch_chi2(const GraphDev &g, double *partials, DevScalars *sc, cudaStream_t st);
+void launch_edge_errors(const GraphDev &g, double *err_sorted /* [ne][d] */, double *chi2_sorted /* [ne] or null */,
+                        cudaStream_t st);
+void launch_linearize(const GraphDev &g, int jac_mode, double h, double *scratch /* [ne][scr] */, cudaStream_t st);
+int scratch_stride(int d);
+void launch_assemble(const GraphDev &g, const StructDev &s, const double *scratch, double *H, double *b,
+                     cudaStream_t st);
+void launch_retract(const GraphDev &g, const double *x, double *est_out, cudaStream_t st);
+
+// ---- linear algebra on the BSR-upper Hessian --------------------------------------------
+void launch_maxdiag(int d, const double *H, const int32_t *rowptr, int nf, double *partials, DevScalars *sc,
+                    cudaStream_t st);
+void launch_precond(int d, const double *H, const int32_t *rowptr, int nf, double lambda, double *Minv,
+                    DevScalars *sc, cudaStream_t st);
+void launch_spmv(int d, const double *H, const StructDev &s, int nf, double lambda, const double *p, double *q1,
+                 double *T, double *partials, DevScalars *sc, int pcg_mode, cudaStream_t st);
+void launch_finish_q(int d, const StructDev &s, int nf, const double *q1, const double *T, double *q, cudaStream_t st);
+void launch_pcg_init(int d, int nf, const double *b, const double *Minv, double *x, double *r, double *z, double *p,
+                     double *partials, DevScalars *sc, double tol, int max_iter, cudaStream_t st);
+void launch_pcg_update(int d, const StructDev &s, int nf, const double *q1, const double *T, const double *Minv,
+                       const double *p, double *x, double *r, double *z, double *partials, DevScalars *sc,
+                       cudaStream_t st);
+void launch_pcg_pupdate(int d, int nf, const double *z, double *p, const DevScalars *sc, cudaStream_t st);
+void launch_scale(int n, const double *x, const double *b, double lambda, double *partials, DevScalars *sc,
+                  cudaStream_t st);
+int launches_per_pcg_iter();
+
+}  // namespace s3o

@@ -1,0 +1,796 @@
+// problem.cu -- the s3o_problem object, the Levenberg-Marquardt driver and the C ABI.
+//
+// The driver restates OptimizationAlgorithmLevenberg::solve inside SparseOptimizer::optimize
+// [EXT g2o] (reference call sites kitti_surf.cpp:674-675, :1021-1022,
+// :1044-1045) with every numeric step on the device:
+//   computeActiveErrors/activeRobustChi2 -> chi2 kernel      buildSystem -> linearize + assemble
+//   setLambda/solve/restoreDiagonal      -> precond + PCG (lambda added inside the SpMV)
+//   push / update / pop / discardTop     -> retract into the alternate estimate buffer + swap
+//   computeScale, computeLambdaInit      -> device reductions
+// The host only sees three scalars per trial (chi2, scale, PCG status).
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "internal.h"
+#include "kernels.cuh"
+
+namespace s3o {
+
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+template <class T>
+static int dev_alloc(T **ptr, size_t count) {
+    *ptr = nullptr;
+    if (count == 0) count = 1;
+    S3O_CUDA(cudaMalloc((void **)ptr, count * sizeof(T)));
+    return S3O_OK;
+}
+template <class T>
+static void dev_free(T *&ptr) {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+}
+
+}  // namespace s3o
+
+using namespace s3o;
+
+struct s3o_problem {
+    int kind = 0, d = 0, est_dim = 0, ninfo = 0, device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // host-side graph description
+    int nv = 0, ne = 0;
+    std::vector<uint8_t> fixed;
+    std::vector<int32_t> v0, v1;
+    bool has_info = false, has_aux = false;
+    double *d_meas_aos = nullptr, *d_info_aos = nullptr;  // caller-ordered staging until the structure is built
+    // device graph
+    int nv_pad = 0, ne_pad = 0;
+    double *d_est[2] = { nullptr, nullptr };
+    int cur = 0;
+    double *d_aux = nullptr;
+    int32_t *d_hidx = nullptr, *d_sv0 = nullptr, *d_sv1 = nullptr;
+    double *d_meas = nullptr, *d_info = nullptr;
+    // structure
+    HostStructure S;
+    bool built = false;
+    int32_t *d_rowptr = nullptr, *d_colidx = nullptr, *d_blk_row = nullptr, *d_blk_ebeg = nullptr, *d_blk_eend = nullptr;
+    int32_t *d_colT_ptr = nullptr, *d_colT_blk = nullptr, *d_inc_ptr = nullptr, *d_inc_ent = nullptr, *d_e_blk = nullptr;
+    // linear system
+    double *d_H = nullptr, *d_b = nullptr, *d_x = nullptr, *d_r = nullptr, *d_z = nullptr, *d_p = nullptr;
+    double *d_q1 = nullptr, *d_T = nullptr, *d_Minv = nullptr, *d_scratch = nullptr, *d_partials = nullptr;
+    DevScalars *d_sc = nullptr, *h_sc = nullptr;
+    // parameters
+    int robust_kind = S3O_ROBUST_NONE;
+    double robust_param = 0;
+    int math_mode = S3O_MATH_REFERENCE;
+    int jac_mode = S3O_JAC_ANALYTIC;
+    double jac_h = 1e-9;
+    double tau = 1e-5, user_lambda = 0;
+    int max_trials = 10;
+    double pcg_tol = 1e-8;
+    int pcg_max_iter = 1000;
+    bool linearized = false;
+    // statistics
+    s3o_stats stats{};
+    cudaEvent_t ev[6] = {};
+};
+
+namespace {
+
+GraphDev graph_view(const s3o_problem *p, int which) {
+    GraphDev g{};
+    g.kind = p->kind; g.d = p->d; g.est_dim = p->est_dim; g.ninfo = p->ninfo;
+    g.nv = p->nv; g.nv_pad = p->nv_pad; g.ne = p->S.ne_act; g.ne_pad = p->ne_pad; g.nf = p->S.nf; g.nb = p->S.nb;
+    g.est = p->d_est[which]; g.aux = p->d_aux; g.hidx = p->d_hidx; g.sv0 = p->d_sv0; g.sv1 = p->d_sv1;
+    g.meas = p->d_meas; g.info = p->has_info ? p->d_info : nullptr;
+    g.robust_kind = p->robust_kind; g.robust_param = p->robust_param;
+    g.math_corrected = p->math_mode == S3O_MATH_CORRECTED;
+    return g;
+}
+
+StructDev struct_view(const s3o_problem *p) {
+    StructDev s{};
+    s.rowptr = p->d_rowptr; s.colidx = p->d_colidx; s.blk_row = p->d_blk_row;
+    s.blk_ebeg = p->d_blk_ebeg; s.blk_eend = p->d_blk_eend;
+    s.colT_ptr = p->d_colT_ptr; s.colT_blk = p->d_colT_blk;
+    s.inc_ptr = p->d_inc_ptr; s.inc_ent = p->d_inc_ent; s.e_blk = p->d_e_blk;
+    return s;
+}
+
+void free_structure(s3o_problem *p) {
+    dev_free(p->d_hidx); dev_free(p->d_sv0); dev_free(p->d_sv1); dev_free(p->d_meas); dev_free(p->d_info);
+    dev_free(p->d_rowptr); dev_free(p->d_colidx); dev_free(p->d_blk_row); dev_free(p->d_blk_ebeg);
+    dev_free(p->d_blk_eend); dev_free(p->d_colT_ptr); dev_free(p->d_colT_blk); dev_free(p->d_inc_ptr);
+    dev_free(p->d_inc_ent); dev_free(p->d_e_blk);
+    dev_free(p->d_H); dev_free(p->d_b); dev_free(p->d_x); dev_free(p->d_r); dev_free(p->d_z); dev_free(p->d_p);
+    dev_free(p->d_q1); dev_free(p->d_T); dev_free(p->d_Minv); dev_free(p->d_scratch);
+    p->built = false;
+    p->linearized = false;
+}
+
+template <class T>
+int upload(s3o_problem *p, T **dst, const std::vector<T> &src) {
+    int rc = dev_alloc(dst, src.size());
+    if (rc) return rc;
+    if (!src.empty()) {
+        S3O_CUDA(cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, p->stream));
+        p->stats.h2d_bytes += (int64_t)(src.size() * sizeof(T));
+    }
+    return S3O_OK;
+}
+
+int check_launch(s3o_problem *p, int n) {
+    p->stats.kernel_launches += n;
+    S3O_CUDA(cudaGetLastError());
+    return S3O_OK;
+}
+
+int sync_scalars(s3o_problem *p) {
+    S3O_CUDA(cudaMemcpyAsync(p->h_sc, p->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, p->stream));
+    S3O_CUDA(cudaStreamSynchronize(p->stream));
+    p->stats.d2h_bytes += sizeof(DevScalars);
+    return S3O_OK;
+}
+
+int ensure_built(s3o_problem *p) {
+    if (p->built) return S3O_OK;
+    return s3o_build_structure(p, nullptr, nullptr);
+}
+
+int do_chi2(s3o_problem *p, int which) {
+    if (p->S.ne_act == 0) {
+        S3O_CUDA(cudaMemsetAsync(&p->d_sc->chi2, 0, sizeof(double), p->stream));
+        return S3O_OK;
+    }
+    launch_chi2(graph_view(p, which), p->d_partials, p->d_sc, p->stream);
+    return check_launch(p, 1);
+}
+
+int do_linearize(s3o_problem *p) {
+    const GraphDev g = graph_view(p, p->cur);
+    launch_linearize(g, p->jac_mode, p->jac_h, p->d_scratch, p->stream);
+    launch_assemble(g, struct_view(p), p->d_scratch, p->d_H, p->d_b, p->stream);
+    p->linearized = true;
+    return check_launch(p, 2);
+}
+
+// Solve (H + lambda I) x = b; leaves x in d_x.  Returns the PCG status in *status (1 converged,
+// 2 iteration cap, 3 breakdown) and the iteration count.
+int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel_res) {
+    const int nf = p->S.nf, d = p->d;
+    const StructDev s = struct_view(p);
+    launch_precond(d, p->d_H, p->d_rowptr, nf, lambda, p->d_Minv, p->d_sc, p->stream);
+    launch_pcg_init(d, nf, p->d_b, p->d_Minv, p->d_x, p->d_r, p->d_z, p->d_p, p->d_partials, p->d_sc, p->pcg_tol,
+                    p->pcg_max_iter, p->stream);
+    int rc = check_launch(p, 2);
+    if (rc) return rc;
+    int batch = 8, launched = 0;
+    for (;;) {
+        for (int k = 0; k < batch; ++k) {
+            launch_spmv(d, p->d_H, s, nf, lambda, p->d_p, p->d_q1, p->d_T, p->d_partials, p->d_sc, 1, p->stream);
+            launch_pcg_update(d, s, nf, p->d_q1, p->d_T, p->d_Minv, p->d_p, p->d_x, p->d_r, p->d_z, p->d_partials,
+                              p->d_sc, p->stream);
+            launch_pcg_pupdate(d, nf, p->d_z, p->d_p, p->d_sc, p->stream);
+        }
+        launched += batch;
+        rc = check_launch(p, 3 * batch);
+        if (rc) return rc;
+        rc = sync_scalars(p);
+        if (rc) return rc;
+        if (p->h_sc->done || launched >= p->pcg_max_iter + batch) break;
+        if (batch < 64) batch *= 2;
+    }
+    p->stats.pcg_iterations += p->h_sc->iters;
+    if (status) *status = p->h_sc->done ? p->h_sc->done : 2;
+    if (iters) *iters = p->h_sc->iters;
+    if (rel_res) *rel_res = p->h_sc->rr0 > 0 ? std::sqrt(p->h_sc->rr / p->h_sc->rr0) : 0.0;
+    return S3O_OK;
+}
+
+}  // namespace
+
+// ======================================================================================
+// C ABI
+// ======================================================================================
+extern "C" {
+
+const char *s3o_last_error(void) { return g_err; }
+int s3o_version(void) { return 100; }
+
+int s3o_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int s3o_create(int kind, int device, s3o_problem **out) {
+    if (!out) { set_error("s3o_create: out is NULL"); return S3O_ERR_INVALID; }
+    *out = nullptr;
+    int d, est_dim;
+    switch (kind) {
+    case S3O_KIND_SIM3: d = 7; est_dim = 8; break;
+    case S3O_KIND_SCALE_TRANS: d = 4; est_dim = 4; break;
+    case S3O_KIND_SCALE: d = 1; est_dim = 1; break;
+    default: set_error("s3o_create: unsupported kind %d", kind); return S3O_ERR_UNSUPPORTED;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("s3o_create: no CUDA device available (this library has no CPU path)");
+        return S3O_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { set_error("s3o_create: device %d out of range (%d devices)", device, ndev); return S3O_ERR_INVALID; }
+    S3O_CUDA(cudaSetDevice(device));
+    s3o_problem *p = new s3o_problem();
+    p->kind = kind; p->d = d; p->est_dim = est_dim; p->ninfo = d * (d + 1) / 2; p->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); delete p; return S3O_ERR_CUDA; }
+    p->own_stream = true;
+    for (auto &ev : p->ev) cudaEventCreate(&ev);
+    if (dev_alloc(&p->d_sc, 1) || dev_alloc(&p->d_partials, 2 * kMaxPartials) ||
+        cudaMallocHost((void **)&p->h_sc, sizeof(DevScalars)) != cudaSuccess) {
+        s3o_destroy(p);
+        return S3O_ERR_CUDA;
+    }
+    cudaMemsetAsync(p->d_sc, 0, sizeof(DevScalars), p->stream);
+    memset(p->h_sc, 0, sizeof(DevScalars));
+    p->stats.dim = d;
+    *out = p;
+    return S3O_OK;
+}
+
+int s3o_destroy(s3o_problem *p) {
+    if (!p) return S3O_OK;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    free_structure(p);
+    dev_free(p->d_meas_aos); dev_free(p->d_info_aos);
+    dev_free(p->d_est[0]); dev_free(p->d_est[1]); dev_free(p->d_aux);
+    dev_free(p->d_sc); dev_free(p->d_partials);
+    if (p->h_sc) cudaFreeHost(p->h_sc);
+    for (auto &ev : p->ev) if (ev) cudaEventDestroy(ev);
+    if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+    return S3O_OK;
+}
+
+int s3o_set_stream(s3o_problem *p, void *cuda_stream) {
+    if (!p) return S3O_ERR_INVALID;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
+    p->own_stream = false;
+    p->stream = (cudaStream_t)cuda_stream;
+    if (!cuda_stream) {
+        S3O_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+        p->own_stream = true;
+    }
+    return S3O_OK;
+}
+
+static int upload_estimates(s3o_problem *p, const double *est) {
+    double *tmp = nullptr;
+    const size_t cnt = (size_t)p->nv * p->est_dim;
+    int rc = dev_alloc(&tmp, cnt);
+    if (rc) return rc;
+    cudaError_t e = cudaMemcpyAsync(tmp, est, cnt * sizeof(double), cudaMemcpyHostToDevice, p->stream);
+    if (e == cudaSuccess) {
+        launch_pack_vertices(tmp, p->nv, p->nv_pad, p->est_dim, p->d_est[p->cur], p->stream);
+        e = cudaStreamSynchronize(p->stream);
+    }
+    cudaFree(tmp);
+    if (e != cudaSuccess) { set_error("upload_estimates: %s", cudaGetErrorString(e)); return S3O_ERR_CUDA; }
+    p->stats.h2d_bytes += (int64_t)(cnt * sizeof(double));
+    p->stats.kernel_launches += 1;
+    return S3O_OK;
+}
+
+int s3o_set_vertices(s3o_problem *p, int n, const double *est, const uint8_t *fixed, const double *aux) {
+    if (!p || n < 0 || (n > 0 && !est)) { set_error("s3o_set_vertices: bad arguments"); return S3O_ERR_INVALID; }
+    if (p->kind == S3O_KIND_SCALE_TRANS && !aux && n > 0) { set_error("s3o_set_vertices: SCALE_TRANS needs aux rotations"); return S3O_ERR_INVALID; }
+    cudaSetDevice(p->device);
+    free_structure(p);
+    dev_free(p->d_est[0]); dev_free(p->d_est[1]); dev_free(p->d_aux);
+    p->nv = n;
+    p->nv_pad = pad32(n);
+    p->cur = 0;
+    p->fixed.assign(n, 0);
+    if (fixed) memcpy(p->fixed.data(), fixed, n);
+    int rc;
+    if ((rc = dev_alloc(&p->d_est[0], (size_t)p->nv_pad * p->est_dim))) return rc;
+    if ((rc = dev_alloc(&p->d_est[1], (size_t)p->nv_pad * p->est_dim))) return rc;
+    S3O_CUDA(cudaMemsetAsync(p->d_est[0], 0, (size_t)p->nv_pad * p->est_dim * sizeof(double), p->stream));
+    S3O_CUDA(cudaMemsetAsync(p->d_est[1], 0, (size_t)p->nv_pad * p->est_dim * sizeof(double), p->stream));
+    if ((rc = upload_estimates(p, est))) return rc;
+    p->has_aux = aux != nullptr;
+    if (aux) {
+        double *tmp = nullptr;
+        if ((rc = dev_alloc(&tmp, (size_t)n * 4))) return rc;
+        if ((rc = dev_alloc(&p->d_aux, (size_t)p->nv_pad * 4))) { cudaFree(tmp); return rc; }
+        cudaError_t e = cudaMemcpyAsync(tmp, aux, (size_t)n * 4 * sizeof(double), cudaMemcpyHostToDevice, p->stream);
+        if (e == cudaSuccess) {
+            launch_pack_vertices(tmp, n, p->nv_pad, 4, p->d_aux, p->stream);
+            e = cudaStreamSynchronize(p->stream);
+        }
+        cudaFree(tmp);
+        if (e != cudaSuccess) { set_error("s3o_set_vertices(aux): %s", cudaGetErrorString(e)); return S3O_ERR_CUDA; }
+        p->stats.h2d_bytes += (int64_t)n * 32;
+        p->stats.kernel_launches += 1;
+    }
+    p->stats.n_vertices = n;
+    return S3O_OK;
+}
+
+int s3o_set_estimates(s3o_problem *p, const double *est) {
+    if (!p || !est || !p->d_est[0]) { set_error("s3o_set_estimates: call s3o_set_vertices first"); return S3O_ERR_INVALID; }
+    cudaSetDevice(p->device);
+    p->linearized = false;
+    return upload_estimates(p, est);
+}
+
+int s3o_set_edges(s3o_problem *p, int n, const int32_t *v0, const int32_t *v1, const double *meas, const double *info) {
+    if (!p || n < 0 || (n > 0 && (!v0 || !v1 || !meas))) { set_error("s3o_set_edges: bad arguments"); return S3O_ERR_INVALID; }
+    for (int k = 0; k < n; ++k)
+        if (v0[k] < 0 || v0[k] >= p->nv || v1[k] < 0 || v1[k] >= p->nv || v0[k] == v1[k]) {
+            set_error("s3o_set_edges: edge %d has invalid vertices (%d,%d), n_vertices=%d", k, v0[k], v1[k], p->nv);
+            return S3O_ERR_INVALID;
+        }
+    cudaSetDevice(p->device);
+    free_structure(p);
+    dev_free(p->d_meas_aos); dev_free(p->d_info_aos);
+    p->ne = n;
+    p->v0.assign(v0, v0 + n);
+    p->v1.assign(v1, v1 + n);
+    p->has_info = info != nullptr;
+    int rc;
+    const size_t mcount = (size_t)n * p->est_dim, icount = (size_t)n * p->d * p->d;
+    if ((rc = dev_alloc(&p->d_meas_aos, mcount))) return rc;
+    if (n) S3O_CUDA(cudaMemcpyAsync(p->d_meas_aos, meas, mcount * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    p->stats.h2d_bytes += (int64_t)(mcount * sizeof(double));
+    if (info) {
+        if ((rc = dev_alloc(&p->d_info_aos, icount))) return rc;
+        if (n) S3O_CUDA(cudaMemcpyAsync(p->d_info_aos, info, icount * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        p->stats.h2d_bytes += (int64_t)(icount * sizeof(double));
+    }
+    S3O_CUDA(cudaStreamSynchronize(p->stream));
+    p->stats.n_edges = n;
+    return S3O_OK;
+}
+
+int s3o_set_robust(s3o_problem *p, int kind, double param) {
+    if (!p || kind < S3O_ROBUST_NONE || kind > S3O_ROBUST_PTAM_LS) { set_error("s3o_set_robust: bad kind"); return S3O_ERR_INVALID; }
+    if (kind != S3O_ROBUST_NONE && kind != S3O_ROBUST_PTAM_LS && !(param > 0)) { set_error("s3o_set_robust: param must be > 0"); return S3O_ERR_INVALID; }
+    p->robust_kind = kind;
+    p->robust_param = param;
+    p->linearized = false;
+    return S3O_OK;
+}
+
+int s3o_set_jacobian_mode(s3o_problem *p, int mode, double h) {
+    if (!p || (mode != S3O_JAC_NUMERIC && mode != S3O_JAC_ANALYTIC)) { set_error("s3o_set_jacobian_mode: bad mode"); return S3O_ERR_INVALID; }
+    p->jac_mode = mode;
+    if (h > 0) p->jac_h = h;
+    p->linearized = false;
+    return S3O_OK;
+}
+
+int s3o_set_math_mode(s3o_problem *p, int mode) {
+    if (!p || (mode != S3O_MATH_REFERENCE && mode != S3O_MATH_CORRECTED)) { set_error("s3o_set_math_mode: bad mode"); return S3O_ERR_INVALID; }
+    p->math_mode = mode;
+    p->linearized = false;
+    return S3O_OK;
+}
+
+int s3o_set_lm(s3o_problem *p, double tau, double user_lambda_init, int max_trials) {
+    if (!p) return S3O_ERR_INVALID;
+    if (tau > 0) p->tau = tau;
+    p->user_lambda = user_lambda_init;
+    if (max_trials > 0) p->max_trials = max_trials;
+    return S3O_OK;
+}
+
+int s3o_set_pcg(s3o_problem *p, double rel_tol, int max_iter) {
+    if (!p) return S3O_ERR_INVALID;
+    if (rel_tol > 0) p->pcg_tol = rel_tol;
+    if (max_iter > 0) p->pcg_max_iter = max_iter;
+    return S3O_OK;
+}
+
+int s3o_build_structure(s3o_problem *p, int *n_free, int *n_blocks) {
+    if (!p) return S3O_ERR_INVALID;
+    if (!p->d_est[0]) { set_error("s3o_build_structure: no vertices"); return S3O_ERR_INVALID; }
+    cudaSetDevice(p->device);
+    if (!p->built) {
+        if (p->ne > 0 && !p->d_meas_aos) { set_error("s3o_build_structure: edges were consumed; call s3o_set_edges again"); return S3O_ERR_INVALID; }
+        free_structure(p);
+        HostStructure &S = p->S;
+        build_structure_host(p->nv, p->fixed.data(), p->ne, p->v0.data(), p->v1.data(), S);
+        p->ne_pad = pad32(S.ne_act);
+        int rc = 0;
+        std::vector<int32_t> blk_row(S.nb);
+        for (int r = 0; r < S.nf; ++r)
+            for (int k = S.rowptr[r]; k < S.rowptr[r + 1]; ++k) blk_row[k] = r;
+        int32_t *d_perm = nullptr;
+        rc = rc ? rc : upload(p, &p->d_hidx, S.hidx);
+        rc = rc ? rc : upload(p, &p->d_sv0, S.sv0);
+        rc = rc ? rc : upload(p, &p->d_sv1, S.sv1);
+        rc = rc ? rc : upload(p, &p->d_rowptr, S.rowptr);
+        rc = rc ? rc : upload(p, &p->d_colidx, S.colidx);
+        rc = rc ? rc : upload(p, &p->d_blk_row, blk_row);
+        rc = rc ? rc : upload(p, &p->d_blk_ebeg, S.blk_ebeg);
+        rc = rc ? rc : upload(p, &p->d_blk_eend, S.blk_eend);
+        rc = rc ? rc : upload(p, &p->d_colT_ptr, S.colT_ptr);
+        rc = rc ? rc : upload(p, &p->d_colT_blk, S.colT_blk);
+        rc = rc ? rc : upload(p, &p->d_inc_ptr, S.inc_ptr);
+        rc = rc ? rc : upload(p, &p->d_inc_ent, S.inc_ent);
+        rc = rc ? rc : upload(p, &p->d_e_blk, S.e_blk);
+        rc = rc ? rc : upload(p, &d_perm, S.perm);
+        rc = rc ? rc : dev_alloc(&p->d_meas, (size_t)p->ne_pad * p->est_dim);
+        if (p->has_info) rc = rc ? rc : dev_alloc(&p->d_info, (size_t)p->ne_pad * p->ninfo);
+        const size_t nfd = (size_t)S.nf * p->d, dd = (size_t)p->d * p->d;
+        rc = rc ? rc : dev_alloc(&p->d_H, (size_t)S.nb * dd);
+        rc = rc ? rc : dev_alloc(&p->d_b, nfd);
+        rc = rc ? rc : dev_alloc(&p->d_x, nfd);
+        rc = rc ? rc : dev_alloc(&p->d_r, nfd);
+        rc = rc ? rc : dev_alloc(&p->d_z, nfd);
+        rc = rc ? rc : dev_alloc(&p->d_p, nfd);
+        rc = rc ? rc : dev_alloc(&p->d_q1, nfd);
+        rc = rc ? rc : dev_alloc(&p->d_T, (size_t)S.nb * p->d);
+        rc = rc ? rc : dev_alloc(&p->d_Minv, (size_t)S.nf * dd);
+        rc = rc ? rc : dev_alloc(&p->d_scratch, (size_t)p->ne_pad * scratch_stride(p->d));
+        if (rc) { dev_free(d_perm); free_structure(p); return rc; }
+        if (S.ne_act > 0) {
+            cudaMemsetAsync(p->d_meas, 0, (size_t)p->ne_pad * p->est_dim * sizeof(double), p->stream);
+            if (p->has_info) cudaMemsetAsync(p->d_info, 0, (size_t)p->ne_pad * p->ninfo * sizeof(double), p->stream);
+            launch_pack_edges(p->d_meas_aos, p->has_info ? p->d_info_aos : nullptr, d_perm, S.ne_act, p->ne_pad,
+                              p->est_dim, p->d, p->d_meas, p->d_info, p->stream);
+            p->stats.kernel_launches += 1;
+        }
+        cudaMemsetAsync(p->d_x, 0, nfd * sizeof(double), p->stream);
+        cudaError_t e = cudaStreamSynchronize(p->stream);
+        dev_free(d_perm);
+        if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) {
+            set_error("s3o_build_structure: %s", cudaGetErrorString(e));
+            free_structure(p);
+            return S3O_ERR_CUDA;
+        }
+        dev_free(p->d_meas_aos);
+        dev_free(p->d_info_aos);
+        p->built = true;
+        p->stats.n_free = S.nf; p->stats.n_blocks = S.nb;
+    }
+    if (n_free) *n_free = p->S.nf;
+    if (n_blocks) *n_blocks = p->S.nb;
+    return S3O_OK;
+}
+
+int s3o_host_structure(int n_vertices, const uint8_t *fixed, int n_edges, const int32_t *v0, const int32_t *v1,
+                       int *n_free, int *n_blocks, int32_t *colptr, int32_t *rowidx, int32_t *hidx) {
+    if (n_vertices < 0 || n_edges < 0 || (n_edges > 0 && (!v0 || !v1))) { set_error("s3o_host_structure: bad arguments"); return S3O_ERR_INVALID; }
+    for (int k = 0; k < n_edges; ++k)
+        if (v0[k] < 0 || v0[k] >= n_vertices || v1[k] < 0 || v1[k] >= n_vertices || v0[k] == v1[k]) {
+            set_error("s3o_host_structure: edge %d has invalid vertices", k);
+            return S3O_ERR_INVALID;
+        }
+    HostStructure S;
+    build_structure_host(n_vertices, fixed, n_edges, v0, v1, S);
+    if (n_free) *n_free = S.nf;
+    if (n_blocks) *n_blocks = S.nb;
+    if (colptr) memcpy(colptr, S.ccs_colptr.data(), sizeof(int32_t) * (S.nf + 1));
+    if (rowidx) memcpy(rowidx, S.ccs_rowidx.data(), sizeof(int32_t) * S.nb);
+    if (hidx) memcpy(hidx, S.hidx.data(), sizeof(int32_t) * n_vertices);
+    return S3O_OK;
+}
+
+int s3o_get_structure(s3o_problem *p, int32_t *colptr, int32_t *rowidx) {
+    if (!p || !p->built) { set_error("s3o_get_structure: structure not built"); return S3O_ERR_INVALID; }
+    if (colptr) memcpy(colptr, p->S.ccs_colptr.data(), sizeof(int32_t) * (p->S.nf + 1));
+    if (rowidx) memcpy(rowidx, p->S.ccs_rowidx.data(), sizeof(int32_t) * p->S.nb);
+    return S3O_OK;
+}
+
+int s3o_get_hessian_index(s3o_problem *p, int32_t *hidx) {
+    if (!p || !p->built || !hidx) { set_error("s3o_get_hessian_index: structure not built"); return S3O_ERR_INVALID; }
+    memcpy(hidx, p->S.hidx.data(), sizeof(int32_t) * p->nv);
+    return S3O_OK;
+}
+
+int s3o_chi2(s3o_problem *p, double *chi2) {
+    if (!p || !chi2) return S3O_ERR_INVALID;
+    cudaSetDevice(p->device);
+    int rc = ensure_built(p);
+    if (rc) return rc;
+    if ((rc = do_chi2(p, p->cur))) return rc;
+    if ((rc = sync_scalars(p))) return rc;
+    *chi2 = p->h_sc->chi2;
+    return S3O_OK;
+}
+
+int s3o_edge_errors(s3o_problem *p, double *err) {
+    if (!p || !err) return S3O_ERR_INVALID;
+    cudaSetDevice(p->device);
+    int rc = ensure_built(p);
+    if (rc) return rc;
+    const int na = p->S.ne_act, d = p->d;
+    double *d_err = nullptr;
+    if ((rc = dev_alloc(&d_err, (size_t)na * d))) return rc;
+    launch_edge_errors(graph_view(p, p->cur), d_err, nullptr, p->stream);
+    std::vector<double> tmp((size_t)na * d);
+    cudaError_t e = cudaMemcpyAsync(tmp.data(), d_err, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+    cudaFree(d_err);
+    if (e != cudaSuccess) { set_error("s3o_edge_errors: %s", cudaGetErrorString(e)); return S3O_ERR_CUDA; }
+    p->stats.kernel_launches += 1;
+    p->stats.d2h_bytes += (int64_t)(tmp.size() * sizeof(double));
+    memset(err, 0, sizeof(double) * (size_t)p->ne * d);
+    for (int t = 0; t < na; ++t) memcpy(err + (size_t)p->S.perm[t] * d, tmp.data() + (size_t)t * d, sizeof(double) * d);
+    return S3O_OK;
+}
+
+int s3o_linearize(s3o_problem *p) {
+    if (!p) return S3O_ERR_INVALID;
+    cudaSetDevice(p->device);
+    int rc = ensure_built(p);
+    if (rc) return rc;
+    if ((rc = do_linearize(p))) return rc;
+    S3O_CUDA(cudaStreamSynchronize(p->stream));
+    return S3O_OK;
+}
+
+int s3o_get_hessian(s3o_problem *p, double *blocks, double *b) {
+    if (!p || !p->built || !p->linearized) { set_error("s3o_get_hessian: call s3o_linearize first"); return S3O_ERR_INVALID; }
+    cudaSetDevice(p->device);
+    const size_t dd = (size_t)p->d * p->d;
+    if (blocks) {
+        std::vector<double> tmp((size_t)p->S.nb * dd);
+        S3O_CUDA(cudaMemcpyAsync(tmp.data(), p->d_H, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        S3O_CUDA(cudaStreamSynchronize(p->stream));
+        p->stats.d2h_bytes += (int64_t)(tmp.size() * sizeof(double));
+        for (int c = 0; c < p->S.nb; ++c)
+            memcpy(blocks + (size_t)c * dd, tmp.data() + (size_t)p->S.ccs2bsr[c] * dd, dd * sizeof(double));
+    }
+    if (b) {
+        S3O_CUDA(cudaMemcpyAsync(b, p->d_b, (size_t)p->S.nf * p->d * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        S3O_CUDA(cudaStreamSynchronize(p->stream));
+        p->stats.d2h_bytes += (int64_t)p->S.nf * p->d * 8;
+    }
+    return S3O_OK;
+}
+
+int s3o_max_diag(s3o_problem *p, double *max_diag) {
+    if (!p || !p->built || !p->linearized || !max_diag) { set_error("s3o_max_diag: call s3o_linearize first"); return S3O_ERR_INVALID; }
+    cudaSetDevice(p->device);
+    launch_maxdiag(p->d, p->d_H, p->d_rowptr, p->S.nf, p->d_partials, p->d_sc, p->stream);
+    int rc = check_launch(p, 1);
+    if (rc) return rc;
+    if ((rc = sync_scalars(p))) return rc;
+    *max_diag = p->h_sc->maxdiag;
+    return S3O_OK;
+}
+
+int s3o_solve(s3o_problem *p, double lambda, double *x, int *pcg_iters, double *rel_residual) {
+    if (!p || !p->built || !p->linearized) { set_error("s3o_solve: call s3o_linearize first"); return S3O_ERR_INVALID; }
+    cudaSetDevice(p->device);
+    int status = 0;
+    int rc = do_solve(p, lambda, &status, pcg_iters, rel_residual);
+    if (rc) return rc;
+    if (x) {
+        S3O_CUDA(cudaMemcpyAsync(x, p->d_x, (size_t)p->S.nf * p->d * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+        S3O_CUDA(cudaStreamSynchronize(p->stream));
+        p->stats.d2h_bytes += (int64_t)p->S.nf * p->d * 8;
+    }
+    return status == 3 ? S3O_RESULT_FAIL : S3O_OK;
+}
+
+int s3o_hessian_multiply(s3o_problem *p, double lambda, const double *x, double *y) {
+    if (!p || !p->built || !p->linearized || !x || !y) { set_error("s3o_hessian_multiply: call s3o_linearize first"); return S3O_ERR_INVALID; }
+    cudaSetDevice(p->device);
+    const size_t bytes = (size_t)p->S.nf * p->d * sizeof(double);
+    S3O_CUDA(cudaMemcpyAsync(p->d_p, x, bytes, cudaMemcpyHostToDevice, p->stream));
+    launch_spmv(p->d, p->d_H, struct_view(p), p->S.nf, lambda, p->d_p, p->d_q1, p->d_T, p->d_partials, p->d_sc, 0, p->stream);
+    launch_finish_q(p->d, struct_view(p), p->S.nf, p->d_q1, p->d_T, p->d_z, p->stream);
+    int rc = check_launch(p, 2);
+    if (rc) return rc;
+    S3O_CUDA(cudaMemcpyAsync(y, p->d_z, bytes, cudaMemcpyDeviceToHost, p->stream));
+    S3O_CUDA(cudaStreamSynchronize(p->stream));
+    p->stats.h2d_bytes += (int64_t)bytes;
+    p->stats.d2h_bytes += (int64_t)bytes;
+    return S3O_OK;
+}
+
+int s3o_update(s3o_problem *p, const double *x) {
+    if (!p || !x) return S3O_ERR_INVALID;
+    cudaSetDevice(p->device);
+    int rc = ensure_built(p);
+    if (rc) return rc;
+    const size_t bytes = (size_t)p->S.nf * p->d * sizeof(double);
+    S3O_CUDA(cudaMemcpyAsync(p->d_x, x, bytes, cudaMemcpyHostToDevice, p->stream));
+    launch_retract(graph_view(p, p->cur), p->d_x, p->d_est[p->cur ^ 1], p->stream);
+    if ((rc = check_launch(p, 1))) return rc;
+    S3O_CUDA(cudaStreamSynchronize(p->stream));
+    p->cur ^= 1;
+    p->linearized = false;
+    p->stats.h2d_bytes += (int64_t)bytes;
+    return S3O_OK;
+}
+
+int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterations, double *final_chi2,
+                 double *final_lambda, double *hist, int hist_cap) {
+    if (!p) return S3O_ERR_INVALID;
+    cudaSetDevice(p->device);
+    int rc = ensure_built(p);
+    if (rc) return rc;
+    if (iterations) *iterations = -1;
+    if (p->S.nf == 0) { set_error("s3o_optimize: 0 vertices to optimize"); return S3O_ERR_INVALID; }
+    const int nf = p->S.nf, d = p->d;
+    double lambda = 0, ni = 2, currentChi = 0;
+    int done = 0;
+    p->stats.ms_linearize = p->stats.ms_solve = p->stats.ms_chi2 = p->stats.ms_update = p->stats.ms_total = 0;
+    cudaEventRecord(p->ev[0], p->stream);
+    int result = S3O_RESULT_OK;
+    for (int it = 0; it < max_iter; ++it) {
+        if (it == 0) {
+            if ((rc = do_chi2(p, p->cur))) return rc;
+        }
+        cudaEventRecord(p->ev[1], p->stream);
+        if ((rc = do_linearize(p))) return rc;
+        cudaEventRecord(p->ev[2], p->stream);
+        if (it == 0) {
+            launch_maxdiag(d, p->d_H, p->d_rowptr, nf, p->d_partials, p->d_sc, p->stream);
+            if ((rc = check_launch(p, 1))) return rc;
+            if ((rc = sync_scalars(p))) return rc;
+            currentChi = p->h_sc->chi2;
+            lambda = p->user_lambda > 0 ? p->user_lambda : p->tau * p->h_sc->maxdiag;
+            ni = 2;
+        }
+        const double chi_start = currentChi;
+        double rho = 0;
+        int qmax = 0, pcg_total = 0;
+        do {
+            cudaEventRecord(p->ev[3], p->stream);
+            int status = 0, iters = 0;
+            if ((rc = do_solve(p, lambda, &status, &iters, nullptr))) return rc;
+            pcg_total += iters;
+            cudaEventRecord(p->ev[4], p->stream);
+            const int trial = p->cur ^ 1;
+            launch_retract(graph_view(p, p->cur), p->d_x, p->d_est[trial], p->stream);
+            launch_scale(nf * d, p->d_x, p->d_b, lambda, p->d_partials, p->d_sc, p->stream);
+            if ((rc = check_launch(p, 2))) return rc;
+            if ((rc = do_chi2(p, trial))) return rc;
+            cudaEventRecord(p->ev[5], p->stream);
+            if ((rc = sync_scalars(p))) return rc;
+            float ms = 0;
+            cudaEventElapsedTime(&ms, p->ev[3], p->ev[4]); p->stats.ms_solve += ms;
+            cudaEventElapsedTime(&ms, p->ev[4], p->ev[5]); p->stats.ms_update += ms;
+            double tempChi = p->h_sc->chi2;
+            const bool ok2 = status != 3;
+            if (!ok2) tempChi = DBL_MAX;
+            rho = currentChi - tempChi;
+            double scale = p->h_sc->scale;
+            scale += 1e-3;
+            rho /= scale;
+            if (rho > 0 && std::isfinite(tempChi)) {
+                double alpha = 1. - std::pow((2 * rho - 1), 3);
+                alpha = std::min(alpha, 2. / 3.);
+                const double scaleFactor = std::max(1. / 3., alpha);
+                lambda *= scaleFactor;
+                ni = 2;
+                currentChi = tempChi;
+                p->cur = trial;            // discardTop: keep the updated estimates
+            } else {
+                lambda *= ni;              // pop: the current buffer still holds the old estimates
+                ni *= 2;
+            }
+            qmax++;
+            p->stats.lm_trials++;
+        } while (rho < 0 && qmax < p->max_trials);
+        {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, p->ev[1], p->ev[2]);
+            p->stats.ms_linearize += ms;
+        }
+        done = it + 1;
+        p->stats.lm_iterations++;
+        if (hist && it < hist_cap) {
+            hist[it * 5 + 0] = currentChi; hist[it * 5 + 1] = lambda; hist[it * 5 + 2] = qmax;
+            hist[it * 5 + 3] = rho; hist[it * 5 + 4] = pcg_total;
+        }
+        if (qmax == p->max_trials || rho == 0) { result = S3O_RESULT_TERMINATE; break; }
+        if (stop_rel_gain > 0) {
+            const double gain = (chi_start - currentChi) / currentChi;
+            if (gain >= 0 && gain < stop_rel_gain) break;
+        }
+    }
+    cudaEventRecord(p->ev[1], p->stream);
+    S3O_CUDA(cudaStreamSynchronize(p->stream));
+    {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]);
+        p->stats.ms_total = ms;
+    }
+    p->linearized = false;
+    if (iterations) *iterations = done;
+    if (final_chi2) *final_chi2 = currentChi;
+    if (final_lambda) *final_lambda = lambda;
+    (void)result;
+    return S3O_OK;
+}
+
+int s3o_get_vertices(s3o_problem *p, double *est) {
+    if (!p || !est || !p->d_est[0]) { set_error("s3o_get_vertices: no vertices"); return S3O_ERR_INVALID; }
+    cudaSetDevice(p->device);
+    double *tmp = nullptr;
+    const size_t cnt = (size_t)p->nv * p->est_dim;
+    int rc = dev_alloc(&tmp, cnt);
+    if (rc) return rc;
+    launch_unpack_vertices(p->d_est[p->cur], p->nv, p->nv_pad, p->est_dim, tmp, p->stream);
+    cudaError_t e = cudaMemcpyAsync(est, tmp, cnt * sizeof(double), cudaMemcpyDeviceToHost, p->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) { set_error("s3o_get_vertices: %s", cudaGetErrorString(e)); return S3O_ERR_CUDA; }
+    p->stats.d2h_bytes += (int64_t)(cnt * sizeof(double));
+    p->stats.kernel_launches += 1;
+    return S3O_OK;
+}
+
+int s3o_get_stats(s3o_problem *p, s3o_stats *out) {
+    if (!p || !out) return S3O_ERR_INVALID;
+    p->stats.n_vertices = p->nv; p->stats.n_edges = p->ne; p->stats.dim = p->d;
+    p->stats.n_free = p->built ? p->S.nf : 0;
+    p->stats.n_blocks = p->built ? p->S.nb : 0;
+    *out = p->stats;
+    return S3O_OK;
+}
+
+int s3o_reset_stats(s3o_problem *p) {
+    if (!p) return S3O_ERR_INVALID;
+    p->stats = s3o_stats{};
+    return S3O_OK;
+}
+
+int s3o_estimate_sigma_squared(s3o_problem *p, int robust_kind, double *sigma_squared) {
+    if (!p || !sigma_squared) return S3O_ERR_INVALID;
+    cudaSetDevice(p->device);
+    int rc = ensure_built(p);
+    if (rc) return rc;
+    const int na = p->S.ne_act, d = p->d;
+    double *d_err = nullptr, *d_chi = nullptr;
+    if ((rc = dev_alloc(&d_err, (size_t)na * d))) return rc;
+    if ((rc = dev_alloc(&d_chi, (size_t)na))) { cudaFree(d_err); return rc; }
+    launch_edge_errors(graph_view(p, p->cur), d_err, d_chi, p->stream);
+    std::vector<double> chi(na);
+    cudaError_t e = cudaMemcpyAsync(chi.data(), d_chi, sizeof(double) * na, cudaMemcpyDeviceToHost, p->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+    cudaFree(d_err); cudaFree(d_chi);
+    if (e != cudaSuccess) { set_error("s3o_estimate_sigma_squared: %s", cudaGetErrorString(e)); return S3O_ERR_CUDA; }
+    p->stats.kernel_launches += 1;
+    if (na == 0) { *sigma_squared = 0; return S3O_OK; }
+    if (robust_kind == S3O_ROBUST_PTAM_LS) {       // MEstimator.h:190-198
+        double sum = 0;
+        for (double c : chi) sum += c;
+        *sigma_squared = sum / na;
+        return S3O_OK;
+    }
+    // MEstimator.h:79-89 / :113-123 / :157-167: median of the sorted squared errors
+    std::nth_element(chi.begin(), chi.begin() + na / 2, chi.end());
+    const double med = chi[na / 2];
+    double sigma = 1.4826 * (1 + 5.0 / (na * 2 - 6)) * std::sqrt(med);
+    sigma *= (robust_kind == S3O_ROBUST_PTAM_HUBER) ? 1.345 : 4.6851;
+    *sigma_squared = sigma * sigma;
+    return S3O_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,373 @@
+// sim3_math.cuh -- device-side Sim3 Lie-group math (fp64) for the sm_100a kernels.
+//
+// Convention (reference: sim3_rv.h:125-190 exp, :241-320 ln, :199-220 inverse/compose;
+// g2o::Sim3 storage and tangent order):
+//   state   = unit quaternion (x,y,z,w) + translation + scale, x -> s*(R x) + t
+//   tangent = [omega(3), upsilon(3), sigma]
+//   eps     = 1e-5 four-way branch on |sigma| and theta / trace, small-angle R = I + Om + Om^2
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace s3o {
+
+struct Sim3 {
+    double qx, qy, qz, qw;
+    double tx, ty, tz;
+    double s;
+};
+
+#define S3O_EPS 0.00001
+
+__device__ __forceinline__ void quat_to_rot(double x, double y, double z, double w, double R[9]) {
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+    const double twx = tx * w, twy = ty * w, twz = tz * w;
+    const double txx = tx * x, txy = ty * x, txz = tz * x;
+    const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    R[0] = 1 - (tyy + tzz); R[1] = txy - twz;       R[2] = txz + twy;
+    R[3] = txy + twz;       R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
+}
+
+__device__ __forceinline__ void rot_to_quat(const double R[9], double &x, double &y, double &z, double &w) {
+    double t = R[0] + R[4] + R[8];
+    if (t > 0) {
+        t = sqrt(t + 1.0);
+        w = 0.5 * t;
+        t = 0.5 / t;
+        x = (R[7] - R[5]) * t;
+        y = (R[2] - R[6]) * t;
+        z = (R[3] - R[1]) * t;
+    } else if (R[0] >= R[4] && R[0] >= R[8]) {       // i = 0
+        t = sqrt(R[0] - R[4] - R[8] + 1.0);
+        x = 0.5 * t; t = 0.5 / t;
+        w = (R[7] - R[5]) * t; y = (R[3] + R[1]) * t; z = (R[6] + R[2]) * t;
+    } else if (R[4] > R[0] && R[4] >= R[8]) {        // i = 1
+        t = sqrt(R[4] - R[8] - R[0] + 1.0);
+        y = 0.5 * t; t = 0.5 / t;
+        w = (R[2] - R[6]) * t; z = (R[7] + R[5]) * t; x = (R[1] + R[3]) * t;
+    } else {                                          // i = 2
+        t = sqrt(R[8] - R[0] - R[4] + 1.0);
+        z = 0.5 * t; t = 0.5 / t;
+        w = (R[3] - R[1]) * t; x = (R[2] + R[6]) * t; y = (R[5] + R[7]) * t;
+    }
+}
+
+__device__ __forceinline__ void quat_rotate(double qx, double qy, double qz, double qw,
+                                            double vx, double vy, double vz,
+                                            double &ox, double &oy, double &oz) {
+    double ux = qy * vz - qz * vy, uy = qz * vx - qx * vz, uz = qx * vy - qy * vx;
+    ux += ux; uy += uy; uz += uz;
+    ox = vx + qw * ux + (qy * uz - qz * uy);
+    oy = vy + qw * uy + (qz * ux - qx * uz);
+    oz = vz + qw * uz + (qx * uy - qy * ux);
+}
+
+__device__ __forceinline__ Sim3 sim3_mul(const Sim3 &a, const Sim3 &b) {
+    Sim3 c;
+    c.qw = a.qw * b.qw - a.qx * b.qx - a.qy * b.qy - a.qz * b.qz;
+    c.qx = a.qw * b.qx + a.qx * b.qw + a.qy * b.qz - a.qz * b.qy;
+    c.qy = a.qw * b.qy + a.qy * b.qw + a.qz * b.qx - a.qx * b.qz;
+    c.qz = a.qw * b.qz + a.qz * b.qw + a.qx * b.qy - a.qy * b.qx;
+    double rx, ry, rz;
+    quat_rotate(a.qx, a.qy, a.qz, a.qw, b.tx, b.ty, b.tz, rx, ry, rz);
+    c.tx = a.s * rx + a.tx;
+    c.ty = a.s * ry + a.ty;
+    c.tz = a.s * rz + a.tz;
+    c.s = a.s * b.s;
+    return c;
+}
+
+__device__ __forceinline__ Sim3 sim3_inv(const Sim3 &a) {
+    Sim3 c;
+    c.qx = -a.qx; c.qy = -a.qy; c.qz = -a.qz; c.qw = a.qw;
+    const double k = -1. / a.s;
+    quat_rotate(c.qx, c.qy, c.qz, c.qw, k * a.tx, k * a.ty, k * a.tz, c.tx, c.ty, c.tz);
+    c.s = 1. / a.s;
+    return c;
+}
+
+__device__ __forceinline__ void mat3_mul(const double A[9], const double B[9], double C[9]) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            C[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
+}
+
+__device__ __forceinline__ void skew3(double x, double y, double z, double S[9]) {
+    S[0] = 0;  S[1] = -z; S[2] = y;
+    S[3] = z;  S[4] = 0;  S[5] = -x;
+    S[6] = -y; S[7] = x;  S[8] = 0;
+}
+
+// coefficients of W = A*Om + B*Om^2 + C*I  (sim3_rv.h:143-181 / :261-303)
+// corrected=false: exactly as written in the reference (sim3_rv.h:165,:291: small-angle B without
+// the "-1", R = I + Om + Om^2).  corrected=true: the consistent Taylor limits (B with "-1",
+// R = I + Om + Om^2/2) -- see s3o_set_math_mode.
+__device__ __forceinline__ void sim3_abc(double sigma, double s, double theta, bool small_angle, bool corrected,
+                                         double &A, double &B, double &C) {
+    if (fabs(sigma) < S3O_EPS) {
+        C = 1;
+        if (small_angle) {
+            A = 1. / 2.;
+            B = 1. / 6.;
+        } else {
+            const double theta2 = theta * theta;
+            double sn, cs;
+            sincos(theta, &sn, &cs);
+            A = (1 - cs) / theta2;
+            B = (theta - sn) / (theta2 * theta);
+        }
+    } else {
+        C = (s - 1) / sigma;
+        if (small_angle) {
+            const double sigma2 = sigma * sigma;
+            A = ((sigma - 1) * s + 1) / sigma2;
+            B = corrected ? ((0.5 * sigma2 - sigma + 1) * s - 1) / (sigma2 * sigma)
+                          : ((0.5 * sigma2 - sigma + 1) * s) / (sigma2 * sigma);   // as written at sim3_rv.h:165
+        } else {
+            double sn, cs;
+            sincos(theta, &sn, &cs);
+            const double a = s * sn;
+            const double b = s * cs;
+            const double theta2 = theta * theta;
+            const double c = theta2 + sigma * sigma;
+            A = (a * sigma + (1 - b) * theta) / (theta * c);
+            B = (C - ((b - 1) * sigma + a * theta) / c) * 1. / theta2;
+        }
+    }
+}
+
+__device__ __forceinline__ Sim3 sim3_exp(const double v[7], bool corrected) {
+    const double sigma = v[6];
+    const double theta = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    double Om[9], Om2[9], R[9];
+    skew3(v[0], v[1], v[2], Om);
+    mat3_mul(Om, Om, Om2);
+    const double s = exp(sigma);
+    const bool small_angle = theta < S3O_EPS;
+    double A, B, C;
+    sim3_abc(sigma, s, theta, small_angle, corrected, A, B, C);
+    if (small_angle) {
+        const double k2 = corrected ? 0.5 : 1.0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = Om[i] + k2 * Om2[i];
+    } else {
+        double sn, cs;
+        sincos(theta, &sn, &cs);
+        const double k1 = sn / theta, k2 = (1 - cs) / (theta * theta);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = k1 * Om[i] + k2 * Om2[i];
+    }
+    R[0] += 1; R[4] += 1; R[8] += 1;
+    Sim3 S;
+    rot_to_quat(R, S.qx, S.qy, S.qz, S.qw);
+    double W[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) W[i] = A * Om[i] + B * Om2[i];
+    W[0] += C; W[4] += C; W[8] += C;
+    S.tx = W[0] * v[3] + W[1] * v[4] + W[2] * v[5];
+    S.ty = W[3] * v[3] + W[4] * v[4] + W[5] * v[5];
+    S.tz = W[6] * v[3] + W[7] * v[4] + W[8] * v[5];
+    S.s = s;
+    return S;
+}
+
+// 3x3 solve with partial pivoting (the reference back-substitutes an LU of W, sim3_rv.h:305-307)
+__device__ __forceinline__ void solve3(const double Ain[9], double b0, double b1, double b2,
+                                       double &x0, double &x1, double &x2) {
+    double a[3][4] = { { Ain[0], Ain[1], Ain[2], b0 }, { Ain[3], Ain[4], Ain[5], b1 }, { Ain[6], Ain[7], Ain[8], b2 } };
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        int piv = k;
+#pragma unroll
+        for (int i = k + 1; i < 3; ++i)
+            if (fabs(a[i][k]) > fabs(a[piv][k])) piv = i;
+#pragma unroll
+        for (int i = k + 1; i < 3; ++i)
+            if (i == piv) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { double t = a[k][j]; a[k][j] = a[i][j]; a[i][j] = t; }
+            }
+#pragma unroll
+        for (int i = k + 1; i < 3; ++i) {
+            const double f = a[i][k] / a[k][k];
+#pragma unroll
+            for (int j = k; j < 4; ++j) a[i][j] -= f * a[k][j];
+        }
+    }
+    x2 = a[2][3] / a[2][2];
+    x1 = (a[1][3] - a[1][2] * x2) / a[1][1];
+    x0 = (a[0][3] - a[0][1] * x1 - a[0][2] * x2) / a[0][0];
+}
+
+__device__ __forceinline__ void sim3_log(const Sim3 &S, double v[7], bool corrected) {
+    const double s = S.s;
+    const double sigma = log(s);
+    double R[9];
+    quat_to_rot(S.qx, S.qy, S.qz, S.qw, R);
+    const double d = 0.5 * (R[0] + R[4] + R[8] - 1);
+    const double d0 = R[7] - R[5], d1 = R[2] - R[6], d2 = R[3] - R[1];
+    const bool small_angle = d > 1 - S3O_EPS;
+    double theta = 0, k = 0.5;
+    if (!small_angle) {
+        theta = acos(d);
+        k = theta / (2 * sqrt(1 - d * d));
+    }
+    const double w0 = k * d0, w1 = k * d1, w2 = k * d2;
+    double A, B, C;
+    sim3_abc(sigma, s, theta, small_angle, corrected, A, B, C);
+    double Om[9], Om2[9], W[9];
+    skew3(w0, w1, w2, Om);
+    mat3_mul(Om, Om, Om2);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) W[i] = A * Om[i] + B * Om2[i];
+    W[0] += C; W[4] += C; W[8] += C;
+    v[0] = w0; v[1] = w1; v[2] = w2;
+    solve3(W, S.tx, S.ty, S.tz, v[3], v[4], v[5]);
+    v[6] = sigma;
+}
+
+// EdgeSim3::computeError: e = log(C * Si * Sj^-1)   
+__device__ __forceinline__ void sim3_edge_error(const Sim3 &C, const Sim3 &Si, const Sim3 &Sj, double e[7],
+                                                bool corrected) {
+    sim3_log(sim3_mul(sim3_mul(C, Si), sim3_inv(Sj)), e, corrected);
+}
+
+__device__ __forceinline__ bool inv3(const double A[9], double I[9]) {
+    const double c0 = A[4] * A[8] - A[5] * A[7];
+    const double c1 = A[5] * A[6] - A[3] * A[8];
+    const double c2 = A[3] * A[7] - A[4] * A[6];
+    const double det = A[0] * c0 + A[1] * c1 + A[2] * c2;
+    const double id = 1.0 / det;
+    I[0] = c0 * id; I[1] = (A[2] * A[7] - A[1] * A[8]) * id; I[2] = (A[1] * A[5] - A[2] * A[4]) * id;
+    I[3] = c1 * id; I[4] = (A[0] * A[8] - A[2] * A[6]) * id; I[5] = (A[2] * A[3] - A[0] * A[5]) * id;
+    I[6] = c2 * id; I[7] = (A[1] * A[6] - A[0] * A[7]) * id; I[8] = (A[0] * A[4] - A[1] * A[3]) * id;
+    return det != 0.0;
+}
+
+// Inverse left Jacobian of Sim3 in block form.  With ad_e = [[Om,0,0],[Up,M,-ups],[0,0,0]],
+// M = Om + sigma*I, the series Jl(e) = sum_n ad_e^n/(n+1)! has the block structure
+//   Jl = [[Jw,0,0],[Q,W,w],[0,0,1]],  ad^n = [[Om^n,0,0],[P_n,M^n,-M^(n-1) ups],[0,0,0]],
+//   P_n = M P_(n-1) + Up Om^(n-1).
+// Jl^-1 = [[Jw^-1,0,0],[X,W^-1,y],[0,0,1]],  X = -W^-1 Q Jw^-1,  y = -W^-1 w.
+struct JlInv {
+    double Jw[9];  // Jw^-1
+    double X[9];
+    double Wi[9];  // W^-1
+    double y[3];
+};
+
+__device__ __noinline__ void sim3_jl_inv(const double e[7], JlInv &out) {
+    double Om[9], Up[9], M[9];
+    skew3(e[0], e[1], e[2], Om);
+    skew3(e[3], e[4], e[5], Up);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) M[i] = Om[i];
+    M[0] += e[6]; M[4] += e[6]; M[8] += e[6];
+    double Omn[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
+    double Mn[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
+    double Pn[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+    double vn[3] = { 0, 0, 0 };
+    double Jw[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
+    double W[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
+    double Q[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+    double w[3] = { 0, 0, 0 };
+    double c = 1.0;
+    for (int n = 1; n < 80; ++n) {
+        double T1[9], T2[9];
+        mat3_mul(M, Pn, T1);
+        mat3_mul(Up, Omn, T2);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Pn[i] = T1[i] + T2[i];
+        if (n == 1) {
+            vn[0] = e[3]; vn[1] = e[4]; vn[2] = e[5];
+        } else {
+            const double a0 = M[0] * vn[0] + M[1] * vn[1] + M[2] * vn[2];
+            const double a1 = M[3] * vn[0] + M[4] * vn[1] + M[5] * vn[2];
+            const double a2 = M[6] * vn[0] + M[7] * vn[1] + M[8] * vn[2];
+            vn[0] = a0; vn[1] = a1; vn[2] = a2;
+        }
+        mat3_mul(Om, Omn, T1);
+        mat3_mul(M, Mn, T2);
+        c /= (double)(n + 1);
+        double mx = 0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            Omn[i] = T1[i];
+            Mn[i] = T2[i];
+            Jw[i] += c * Omn[i];
+            W[i] += c * Mn[i];
+            Q[i] += c * Pn[i];
+            mx = fmax(mx, fmax(fabs(Omn[i]), fmax(fabs(Mn[i]), fabs(Pn[i]))));
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            w[i] -= c * vn[i];
+            mx = fmax(mx, fabs(vn[i]));
+        }
+        if (c * mx < 1e-18) break;
+    }
+    inv3(Jw, out.Jw);
+    inv3(W, out.Wi);
+    double T[9];
+    mat3_mul(out.Wi, Q, T);
+    mat3_mul(T, out.Jw, out.X);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) out.X[i] = -out.X[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        out.y[i] = -(out.Wi[i * 3] * w[0] + out.Wi[i * 3 + 1] * w[1] + out.Wi[i * 3 + 2] * w[2]);
+}
+
+// Analytic Jacobians of e = log(C Si Sj^-1) w.r.t. left perturbations S <- exp(delta) S:
+//   Ji = Jl^-1(e) * Ad_C,   Jj = -Jl^-1(-e)           (below row a18)
+// J is row-major 7x7.
+__device__ __forceinline__ void sim3_edge_jacobians(const Sim3 &C, const double e[7], double Ji[49], double Jj[49]) {
+    JlInv L;
+    sim3_jl_inv(e, L);
+    double R[9], Tx[9], TR[9];
+    quat_to_rot(C.qx, C.qy, C.qz, C.qw, R);
+    skew3(C.tx, C.ty, C.tz, Tx);
+    mat3_mul(Tx, R, TR);
+    double A11[9], A21[9], T1[9], T2[9], A22[9];
+    mat3_mul(L.Jw, R, A11);
+    mat3_mul(L.X, R, T1);
+    mat3_mul(L.Wi, TR, T2);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) A21[i] = T1[i] + T2[i];
+    mat3_mul(L.Wi, R, A22);
+#pragma unroll
+    for (int i = 0; i < 49; ++i) Ji[i] = 0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            Ji[r * 7 + c] = A11[r * 3 + c];
+            Ji[(3 + r) * 7 + c] = A21[r * 3 + c];
+            Ji[(3 + r) * 7 + 3 + c] = C.s * A22[r * 3 + c];
+        }
+        Ji[(3 + r) * 7 + 6] = L.y[r] - (L.Wi[r * 3] * C.tx + L.Wi[r * 3 + 1] * C.ty + L.Wi[r * 3 + 2] * C.tz);
+    }
+    Ji[48] = 1;
+    double me[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) me[i] = -e[i];
+    sim3_jl_inv(me, L);
+#pragma unroll
+    for (int i = 0; i < 49; ++i) Jj[i] = 0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            Jj[r * 7 + c] = -L.Jw[r * 3 + c];
+            Jj[(3 + r) * 7 + c] = -L.X[r * 3 + c];
+            Jj[(3 + r) * 7 + 3 + c] = -L.Wi[r * 3 + c];
+        }
+        Jj[(3 + r) * 7 + 6] = -L.y[r];
+    }
+    Jj[48] = -1;
+}
+
+}  // namespace s3o

@@ -1,0 +1,123 @@
+"""Synthetic Sim3 pose graphs.
+
+Host-side input generation only (numpy); nothing here is on the optimisation path.
+
+sphere(n_laps, poses_per_lap): ground-truth camera centres on a radius-100 m sphere spiral, camera
+z-axis along the direction of travel, ground-truth scale s_k = exp(0.3 sin(2 pi k / N)).  Edges per
+vertex k: (k,k+1), (k,k+2), (k,k+L), (k,k+L+1), (k,k+2L) with L = poses_per_lap where in range
+(about 5N edges).  Edge convention is the reference's (kitti_surf.cpp:624-670): vertex(0) = i,
+vertex(1) = j, measurement C ~ S_j S_i^-1, so that e = log(C S_i S_j^-1) is pure noise at the ground
+truth.  Measurement noise n ~ N(0, diag(0.01, 0.05, 0.01)^2) on (omega, upsilon, sigma), information
+Omega = diag(1/sigma^2) stored as a full 7x7; initial guess = exp(N(0, (0.05, 0.5, 0.05)^2)) * GT;
+vertex 0 fixed.  Seeded with numpy's PCG64 so the oracle and the GPU path see identical arrays.
+"""
+import numpy as np
+from scipy.spatial.transform import Rotation
+
+
+def _skew(v):
+    S = np.zeros(v.shape[:-1] + (3, 3))
+    S[..., 0, 1] = -v[..., 2]; S[..., 0, 2] = v[..., 1]
+    S[..., 1, 0] = v[..., 2];  S[..., 1, 2] = -v[..., 0]
+    S[..., 2, 0] = -v[..., 1]; S[..., 2, 1] = v[..., 0]
+    return S
+
+
+def sim3_exp(v):
+    """Vectorised exact Sim3 exponential; v[...,7] = [omega, upsilon, sigma] -> (Rotation, t, s)."""
+    v = np.asarray(v, float).reshape(-1, 7)
+    om, up, sg = v[:, :3], v[:, 3:6], v[:, 6]
+    th = np.linalg.norm(om, axis=1)
+    s = np.exp(sg)
+    small_t = th < 1e-6
+    small_s = np.abs(sg) < 1e-6
+    th_ = np.where(small_t, 1.0, th)
+    sg_ = np.where(small_s, 1.0, sg)
+    C = np.where(small_s, 1.0 + 0.5 * sg, (s - 1) / sg_)
+    a, b = s * np.sin(th_), s * np.cos(th_)
+    c = th_ ** 2 + sg ** 2
+    A_gen = (a * sg + (1 - b) * th_) / (th_ * np.where(c == 0, 1.0, c))
+    B_gen = (C - ((b - 1) * sg + a * th_) / np.where(c == 0, 1.0, c)) / th_ ** 2
+    A_smallt = np.where(small_s, 0.5, ((sg - 1) * s + 1) / sg_ ** 2)
+    B_smallt = np.where(small_s, 1.0 / 6.0, ((0.5 * sg ** 2 - sg + 1) * s - 1) / sg_ ** 3)
+    A = np.where(small_t, A_smallt, A_gen)
+    B = np.where(small_t, B_smallt, B_gen)
+    Om = _skew(om)
+    W = A[:, None, None] * Om + B[:, None, None] * (Om @ Om) + C[:, None, None] * np.eye(3)
+    t = np.einsum("nij,nj->ni", W, up)
+    return Rotation.from_rotvec(om), t, s
+
+
+def _mul(Ra, ta, sa, Rb, tb, sb):
+    return Ra * Rb, sa[:, None] * Ra.apply(tb) + ta, sa * sb
+
+
+def _inv(R, t, s):
+    Ri = R.inv()
+    return Ri, -Ri.apply(t) / s[:, None], 1.0 / s
+
+
+def _pack(R, t, s):
+    q = R.as_quat()  # x y z w
+    q = np.where(q[:, 3:4] < 0, -q, q)
+    return np.concatenate([q, t, s[:, None]], axis=1)
+
+
+def sphere(n_laps=100, poses_per_lap=1000, seed=42, radius=100.0,
+           meas_sigma=(0.01, 0.05, 0.01), init_sigma=(0.05, 0.5, 0.05), full_info=True):
+    """Returns dict(est, gt, fixed, v0, v1, meas, info) -- see the module docstring."""
+    N, L = n_laps * poses_per_lap, poses_per_lap
+    rng = np.random.default_rng(seed)
+    k = np.arange(N)
+    az = 2 * np.pi * k / L
+    pol = np.pi * (0.1 + 0.8 * (k + 0.5) / N)
+    c = radius * np.stack([np.sin(pol) * np.cos(az), np.sin(pol) * np.sin(az), np.cos(pol)], axis=1)
+    # tangent of the spiral (dominant azimuthal motion) -> camera z; radial -> camera x
+    dpol = np.pi * 0.8 / N
+    daz = 2 * np.pi / L
+    tang = radius * np.stack([
+        np.cos(pol) * np.cos(az) * dpol - np.sin(pol) * np.sin(az) * daz,
+        np.cos(pol) * np.sin(az) * dpol + np.sin(pol) * np.cos(az) * daz,
+        -np.sin(pol) * dpol], axis=1)
+    z = tang / np.linalg.norm(tang, axis=1, keepdims=True)
+    x = c / np.linalg.norm(c, axis=1, keepdims=True)
+    x = x - (x * z).sum(1, keepdims=True) * z
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    y = np.cross(z, x)
+    Rc2w = np.stack([x, y, z], axis=2)
+    Rw2c = Rotation.from_matrix(np.transpose(Rc2w, (0, 2, 1)))
+    s_gt = np.exp(0.3 * np.sin(2 * np.pi * k / N))
+    t_gt = -s_gt[:, None] * Rw2c.apply(c)
+
+    offs = [1, 2, L, L + 1, 2 * L]
+    i_idx = np.concatenate([k[: N - o] for o in offs if o < N])
+    j_idx = np.concatenate([k[: N - o] + o for o in offs if o < N])
+    order = np.lexsort((j_idx, i_idx))
+    i_idx, j_idx = i_idx[order], j_idx[order]
+    E = len(i_idx)
+
+    Ri, ti, si = Rw2c[i_idx], t_gt[i_idx], s_gt[i_idx]
+    Rj, tj, sj = Rw2c[j_idx], t_gt[j_idx], s_gt[j_idx]
+    Rii, tii, sii = _inv(Ri, ti, si)
+    Rji, tji, sji = _mul(Rj, tj, sj, Rii, tii, sii)
+    sig = np.array([meas_sigma[0]] * 3 + [meas_sigma[1]] * 3 + [meas_sigma[2]])
+    noise = rng.standard_normal((E, 7)) * sig
+    Rn, tn, sn = sim3_exp(noise)
+    Rm, tm, sm = _mul(Rn, tn, sn, Rji, tji, sji)
+    meas = _pack(Rm, tm, sm)
+
+    isig = np.array([init_sigma[0]] * 3 + [init_sigma[1]] * 3 + [init_sigma[2]])
+    pert = rng.standard_normal((N, 7)) * isig
+    pert[0] = 0
+    Rp, tp, sp = sim3_exp(pert)
+    Re, te, se = _mul(Rp, tp, sp, Rw2c, t_gt, s_gt)
+    est = _pack(Re, te, se)
+    gt = _pack(Rw2c, t_gt, s_gt)
+    fixed = np.zeros(N, np.uint8)
+    fixed[0] = 1
+    info = None
+    if full_info:
+        info = np.zeros((E, 7, 7))
+        info[:, np.arange(7), np.arange(7)] = 1.0 / sig ** 2
+    return dict(est=est, gt=gt, fixed=fixed, v0=i_idx.astype(np.int32), v1=j_idx.astype(np.int32),
+                meas=meas, info=info)

@@ -1,0 +1,213 @@
+"""CPU tests of the oracle: pinned against the known answers of SURVEY.md section 8(c) / BASELINE.md 3."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from conftest import make_oracle
+
+RNG = np.random.default_rng(0)
+
+
+def rand_sim3(rng, ang=1.0, trans=3.0, sig=0.5):
+    v = np.concatenate([rng.normal(0, ang, 3), rng.normal(0, trans, 3), rng.normal(0, sig, 1)])
+    return orc.sim3_exp(v)
+
+
+def test_exp_log_roundtrip():
+    for _ in range(200):
+        v = np.concatenate([RNG.normal(0, 0.8, 3), RNG.normal(0, 2, 3), RNG.normal(0, 0.5, 1)])
+        if np.linalg.norm(v[:3]) > 3.0:
+            continue
+        S = orc.sim3_exp(v)
+        assert np.allclose(orc.sim3_log(S), v, rtol=0, atol=1e-10)
+
+
+def test_inverse_and_compose():
+    for _ in range(50):
+        A, B = rand_sim3(RNG), rand_sim3(RNG)
+        I = orc.sim3_mul(A, orc.sim3_inv(A))
+        assert np.allclose(I, [0, 0, 0, 1, 0, 0, 0, 1], atol=1e-12)
+        # map(x) = s R x + t composes
+        x = RNG.normal(size=3)
+        def mp(S, x):
+            return S[7] * orc.quat_to_rot(S[:4]) @ x + S[4:7]
+        assert np.allclose(mp(orc.sim3_mul(A, B), x), mp(A, mp(B, x)), atol=1e-10)
+
+
+def test_small_angle_branches_as_written():
+    """sim3_rv.h:143-181: small-angle R = I + Om + Om^2 and the sigma!=0 B without '-1' (reference mode)."""
+    orc.set_math_mode(orc.MATH_REFERENCE)
+    om = np.array([3e-6, -2e-6, 1e-6])
+    S = orc.sim3_exp(np.concatenate([om, [0.1, 0.2, 0.3], [0.0]]))
+    Om = np.array([[0, -om[2], om[1]], [om[2], 0, -om[0]], [-om[1], om[0], 0]])
+    assert np.allclose(orc.quat_to_rot(S[:4]), np.eye(3) + Om + Om @ Om, atol=1e-15)
+    sig = 0.01
+    S = orc.sim3_exp(np.concatenate([om, [1.0, 2.0, 3.0], [sig]]))
+    s = np.exp(sig)
+    A = ((sig - 1) * s + 1) / sig ** 2
+    B = ((0.5 * sig ** 2 - sig + 1) * s) / sig ** 3
+    Cc = (s - 1) / sig
+    W = A * Om + B * Om @ Om + Cc * np.eye(3)
+    assert np.allclose(S[4:7], W @ np.array([1.0, 2.0, 3.0]), rtol=1e-13)
+    orc.set_math_mode(orc.MATH_CORRECTED)
+    S2 = orc.sim3_exp(np.concatenate([om, [1.0, 2.0, 3.0], [sig]]))
+    Bc = ((0.5 * sig ** 2 - sig + 1) * s - 1) / sig ** 3
+    W2 = A * Om + Bc * Om @ Om + Cc * np.eye(3)
+    assert np.allclose(S2[4:7], W2 @ np.array([1.0, 2.0, 3.0]), rtol=1e-13)
+    orc.set_math_mode(orc.MATH_REFERENCE)
+
+
+def test_adjoint_identity():
+    # S exp(d) S^-1 = exp(Ad_S d)
+    for _ in range(20):
+        S = rand_sim3(RNG)
+        d = RNG.normal(0, 0.3, 7)
+        lhs = orc.sim3_mul(orc.sim3_mul(S, orc.sim3_exp(d)), orc.sim3_inv(S))
+        rhs = orc.sim3_exp(orc.sim3_adjoint(S) @ d)
+        assert np.allclose(orc.sim3_log(lhs), orc.sim3_log(rhs), atol=1e-9)
+
+
+def test_analytic_vs_numeric_jacobian():
+    """h=1e-6 central differences agree with the analytic Jacobian to ~1e-9."""
+    for _ in range(20):
+        Si, Sj = rand_sim3(RNG, 0.5, 5, 0.3), rand_sim3(RNG, 0.5, 5, 0.3)
+        noise = orc.sim3_exp(np.concatenate([RNG.normal(0, 0.2, 3), RNG.normal(0, 1, 3), RNG.normal(0, 0.2, 1)]))
+        Cm = orc.sim3_mul(noise, orc.sim3_mul(Sj, orc.sim3_inv(Si)))
+        Ai, Aj = orc.sim3_edge_jac_analytic(Cm, Si, Sj)
+        Ni, Nj = orc.sim3_edge_jac_numeric(Cm, Si, Sj, 1e-6)
+        scale = max(np.abs(Ai).max(), np.abs(Aj).max())
+        assert np.abs(Ai - Ni).max() <= 2e-8 * scale
+        assert np.abs(Aj - Nj).max() <= 2e-8 * scale
+
+
+def test_jl_inverse_large_error():
+    """Jl^-1 at the K1 loop-edge magnitude (|sigma + i theta| ~ 1.7, |upsilon| ~ 13)."""
+    e = np.array([0.010350516, 0.013424595, 0.004786277, 11.481364008, -0.514528686, 5.919704247, 1.672212412])
+    ad = orc.sim3_ad(e)
+    J = np.eye(7)
+    term = np.eye(7)
+    for n in range(1, 60):
+        term = term @ ad / (n + 1)
+        J += term
+    assert np.allclose(orc.sim3_jl_inv(e) @ J, np.eye(7), atol=1e-10)
+
+
+def test_k1_known_answers(kitti_k1):
+    p = make_oracle(kitti_k1)
+    colptr, rowidx = p.build_structure()
+    assert p.nv == 771 and p.ne == 771 and p.num_free == 770
+    assert p.num_blocks == 1540                       # 770 diag + 769 chain + 1 loop
+    assert abs(p.chi2() - 169.9259622426238) <= 1e-9
+    e = p.edge_errors()
+    ref = np.array([0.010350516, 0.013424595, 0.004786277, 11.481364008, -0.514528686, 5.919704247, 1.672212412])
+    assert np.allclose(e[0], ref, atol=5e-9)
+    assert (kitti_k1["v0"][0], kitti_k1["v1"][0]) == (21, 253)
+    assert np.abs(e[1:]).max() < 1e-12                # odometry residuals vanish at the VO guess
+    # rows ascending within each column, diagonal present
+    for c in range(p.num_free):
+        rows = rowidx[colptr[c]:colptr[c + 1]]
+        assert np.all(np.diff(rows) > 0) and rows[-1] == c
+
+
+def test_k118_known_answers(kitti_k118):
+    p = make_oracle(kitti_k118)
+    p.build_structure()
+    assert p.ne == 888 and p.num_blocks == 1657
+    assert abs(p.chi2() - 3864464.08479149) <= 1e-5
+
+
+@pytest.mark.parametrize("jac,chi_it0", [(orc.JAC_NUMERIC, 28.41977), (orc.JAC_ANALYTIC, 28.42110)])
+def test_k1_lm_iteration0(kitti_k1, jac, chi_it0):
+    p = make_oracle(kitti_k1, jac=jac)
+    p.build_structure()
+    p.linearize()
+    assert abs(1e-5 * p.max_diag() - 7.0065e-4) <= 1e-8          # lambda_0
+    n, chi2, lam, hist = p.optimize(2)
+    assert abs(hist[0, 0] - chi_it0) <= 2e-4                      # stable to ~1e-5 relative
+    if jac == orc.JAC_ANALYTIC:
+        assert abs(hist[1, 0] - 0.48860) <= 1e-4
+
+
+def test_k118_lm_history_analytic(kitti_k118):
+    p = make_oracle(kitti_k118, jac=orc.JAC_ANALYTIC)
+    p.build_structure()
+    p.linearize()
+    assert abs(1e-5 * p.max_diag() - 1.27478) <= 1e-5
+    n, chi2, lam, hist = p.optimize(12)
+    assert abs(hist[0, 0] - 407603.73) <= 1.0
+    assert abs(hist[1, 0] - 31094.0) <= 1.0
+    assert abs(hist[4, 0] - 29.416) <= 1e-2
+    assert n == 9 and hist[-1, 2] == 10                           # 10 failed trials => Terminate
+
+
+def test_ldlt_against_dense(sphere_small):
+    g = sphere_small
+    p = make_oracle(g, jac=orc.JAC_ANALYTIC)
+    colptr, rowidx = p.build_structure()
+    H, b = p.linearize()
+    lam = 1e-5 * p.max_diag()
+    rc, x = p.solve(lam)
+    assert rc == 0
+    n = p.num_free * 7
+    A = np.zeros((n, n))
+    for c in range(p.num_free):
+        for k in range(colptr[c], colptr[c + 1]):
+            r = rowidx[k]
+            A[r * 7:(r + 1) * 7, c * 7:(c + 1) * 7] = H[k]
+            if r != c:
+                A[c * 7:(c + 1) * 7, r * 7:(r + 1) * 7] = H[k].T
+    A += lam * np.eye(n)
+    assert np.linalg.norm(A @ x - b) <= 1e-10 * np.linalg.norm(b)
+
+
+def test_sphere_converges_in_corrected_mode(sphere_small):
+    orc.set_math_mode(orc.MATH_CORRECTED)
+    try:
+        res = []
+        for jac in (orc.JAC_NUMERIC, orc.JAC_ANALYTIC):
+            p = make_oracle(sphere_small, jac=jac)
+            n, chi2, lam, hist = p.optimize(40, 0.0)
+            assert np.all(hist[:5, 2] == 1)                        # first trials accepted: no stalls
+            res.append((chi2, p.vertices()))
+        assert abs(res[0][0] - res[1][0]) <= 1e-6 * res[1][0]
+        # h=1e-9 central differences carry ~1e-6 relative noise, which moves the weakly
+        # constrained modes of the stationary point by millimetres although chi2 agrees to 1e-8
+        assert np.abs(res[0][1][:, 4:7] - res[1][1][:, 4:7]).max() < 2e-2
+    finally:
+        orc.set_math_mode(orc.MATH_REFERENCE)
+
+
+def test_robust_kernels():
+    # g2o Huber (row a13)
+    rho = orc.robustify(orc.ROBUST_HUBER, 2.5, 4.0)
+    assert np.allclose(rho, [4.0, 1.0, 0.0])
+    rho = orc.robustify(orc.ROBUST_HUBER, 2.5, 100.0)
+    assert np.allclose(rho, [2 * 10 * 2.5 - 6.25, 0.25, -0.5 * 0.25 / 100.0])
+    # PTAM (MEstimator.h:54-198)
+    assert np.allclose(orc.robustify(orc.ROBUST_PTAM_TUKEY, 4.0, 1.0)[:2], [1 - 0.75 ** 3, 0.75 ** 2])
+    assert np.allclose(orc.robustify(orc.ROBUST_PTAM_TUKEY, 4.0, 5.0)[:2], [1.0, 0.0])
+    assert np.allclose(orc.robustify(orc.ROBUST_PTAM_CAUCHY, 4.0, 1.0)[:2], [np.log(1.25), 0.8])
+    assert np.allclose(orc.robustify(orc.ROBUST_PTAM_HUBER, 4.0, 9.0)[:2], [2 * (3 - 1), np.sqrt(4 / 9)])
+    err = np.arange(1.0, 12.0)
+    med = np.sort(err)[len(err) // 2]
+    sig = 4.6851 * 1.4826 * (1 + 5.0 / (len(err) * 2 - 6)) * np.sqrt(med)
+    assert np.isclose(orc.ptam_find_sigma_squared(orc.ROBUST_PTAM_TUKEY, err), sig ** 2)
+    assert np.isclose(orc.ptam_find_sigma_squared(orc.ROBUST_PTAM_LS, err), err.mean())
+
+
+def test_scale_trans_graph_zero_residual(kitti_k1):
+    from oracle import kitti_io
+    st = kitti_io.to_scale_trans_graph(kitti_k1)
+    p = make_oracle(st, kind=orc.KIND_SCALE_TRANS)
+    e = p.edge_errors()
+    assert np.abs(e[1:]).max() < 1e-10                # odometry edges are consistent with the VO guess
+    assert p.build_structure()[0][-1] == 1540
+    for jac in (orc.JAC_NUMERIC, orc.JAC_ANALYTIC):
+        p = make_oracle(st, kind=orc.KIND_SCALE_TRANS, jac=jac)
+        if jac == orc.JAC_NUMERIC:
+            p.set_jacobian_mode(jac, 1e-6)
+        H, b = p.linearize()
+        if jac == orc.JAC_NUMERIC:
+            Hn, bn = H, b
+    assert np.abs(H - Hn).max() <= 1e-6 * np.abs(H).max()
+    assert np.abs(b - bn).max() <= 1e-6 * np.abs(b).max()
