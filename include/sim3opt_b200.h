@@ -127,6 +127,16 @@ int s3o_update(s3o_problem *p, const double *x);            /* oplus on every fr
 int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterations,
                  double *final_chi2, double *final_lambda, double *hist, int hist_cap);
 int s3o_get_vertices(s3o_problem *p, double *est);
+/* resume = 1: the next s3o_optimize continues the LM sequence (keeps lambda, nu and the current
+ * chi2) instead of re-initialising lambda at its first iteration -- lets a caller drive the LM one
+ * iteration at a time.  The LM state is dropped by s3o_set_vertices / s3o_set_estimates /
+ * s3o_restore_estimates.  resume = 2: as 1, but s3o_set_estimates keeps the LM state (the caller
+ * re-uploads the estimates the previous s3o_optimize produced, e.g. after a host round trip). */
+int s3o_set_lm_resume(s3o_problem *p, int resume);
+/* device-side copy of the current estimates (g2o SparseOptimizer::push) and its restore (pop
+ * without discarding): no host traffic */
+int s3o_snapshot_estimates(s3o_problem *p);
+int s3o_restore_estimates(s3o_problem *p);
 
 /* ---- statistics ------------------------------------------------------------------------ */
 typedef struct s3o_stats {
@@ -136,6 +146,9 @@ typedef struct s3o_stats {
     int64_t lm_iterations, lm_trials;
     int64_t h2d_bytes, d2h_bytes;
     int32_t n_vertices, n_free, n_edges, n_blocks, dim;
+    /* CUDA-event time of the SpMV kernel alone, sampled on 1 of every 16 PCG iterations */
+    double ms_spmv_sampled;
+    int64_t n_spmv_sampled;
 } s3o_stats;
 int s3o_get_stats(s3o_problem *p, s3o_stats *out);
 int s3o_reset_stats(s3o_problem *p);

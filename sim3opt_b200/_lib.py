@@ -23,6 +23,7 @@ class Stats(C.Structure):
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("n_vertices", C.c_int32), ("n_free", C.c_int32), ("n_edges", C.c_int32),
         ("n_blocks", C.c_int32), ("dim", C.c_int32),
+        ("ms_spmv_sampled", C.c_double), ("n_spmv_sampled", C.c_int64),
     ]
 
 
@@ -56,6 +57,9 @@ SYMBOLS = {
     "s3o_update": (C.c_int, [C.c_void_p, _dp]),
     "s3o_optimize": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_int), _dp, _dp, _dp, C.c_int]),
     "s3o_get_vertices": (C.c_int, [C.c_void_p, _dp]),
+    "s3o_set_lm_resume": (C.c_int, [C.c_void_p, C.c_int]),
+    "s3o_snapshot_estimates": (C.c_int, [C.c_void_p]),
+    "s3o_restore_estimates": (C.c_int, [C.c_void_p]),
     "s3o_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "s3o_reset_stats": (C.c_int, [C.c_void_p]),
     "s3o_estimate_sigma_squared": (C.c_int, [C.c_void_p, C.c_int, _dp]),

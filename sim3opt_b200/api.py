@@ -168,7 +168,17 @@ class Problem:
                                         _d(hist), max_iter))
         return n.value, chi2.value, lam.value, hist[:max(n.value, 0)]
 
-    def vertices(self):
+    def set_lm_resume(self, resume=1): self._check(self.L.s3o_set_lm_resume(self.h, int(resume)))
+    def snapshot_estimates(self): self._check(self.L.s3o_snapshot_estimates(self.h))
+    def restore_estimates(self): self._check(self.L.s3o_restore_estimates(self.h))
+
+    def vertices(self, out=None):
+        if out is not None:
+            self._check(self.L.s3o_get_vertices(self.h, _d(out)))
+            return out
+        return self._vertices()
+
+    def _vertices(self):
         est = np.zeros((self.nv, self.est_dim))
         self._check(self.L.s3o_get_vertices(self.h, _d(est)))
         return est

@@ -83,6 +83,15 @@ struct s3o_problem {
     double pcg_tol = 1e-8;
     int pcg_max_iter = 1000;
     bool linearized = false;
+    // LM continuation state (s3o_set_lm_resume)
+    int lm_resume = 0;
+    bool lm_valid = false;
+    double lm_lambda = 0, lm_ni = 2, lm_chi = 0;
+    double *d_est_snap = nullptr;
+    // sampled SpMV timing
+    static constexpr int kSpmvEvents = 64;
+    cudaEvent_t spmv_ev[2 * kSpmvEvents] = {};
+    int spmv_ev_used = 0;
     // statistics
     s3o_stats stats{};
     cudaEvent_t ev[6] = {};
@@ -180,7 +189,10 @@ int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel
     int batch = 8, launched = 0;
     for (;;) {
         for (int k = 0; k < batch; ++k) {
+            const bool sample = ((launched + k) & 15) == 7 && p->spmv_ev_used < s3o_problem::kSpmvEvents;
+            if (sample) cudaEventRecord(p->spmv_ev[2 * p->spmv_ev_used], p->stream);
             launch_spmv(d, p->d_H, s, nf, lambda, p->d_p, p->d_q1, p->d_T, p->d_partials, p->d_sc, 1, p->stream);
+            if (sample) cudaEventRecord(p->spmv_ev[2 * p->spmv_ev_used++ + 1], p->stream);
             launch_pcg_update(d, s, nf, p->d_q1, p->d_T, p->d_Minv, p->d_p, p->d_x, p->d_r, p->d_z, p->d_partials,
                               p->d_sc, p->stream);
             launch_pcg_pupdate(d, nf, p->d_z, p->d_p, p->d_sc, p->stream);
@@ -190,6 +202,16 @@ int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel
         if (rc) return rc;
         rc = sync_scalars(p);
         if (rc) return rc;
+        // samples taken after convergence time an early-exit launch: keep only those within the run
+        for (int e = 0; e < p->spmv_ev_used; ++e) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, p->spmv_ev[2 * e], p->spmv_ev[2 * e + 1]) == cudaSuccess &&
+                !(p->h_sc->done && e == p->spmv_ev_used - 1 && batch > 16)) {
+                p->stats.ms_spmv_sampled += ms;
+                p->stats.n_spmv_sampled += 1;
+            }
+        }
+        p->spmv_ev_used = 0;
         if (p->h_sc->done || launched >= p->pcg_max_iter + batch) break;
         if (batch < 64) batch *= 2;
     }
@@ -240,6 +262,7 @@ int s3o_create(int kind, int device, s3o_problem **out) {
     if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); delete p; return S3O_ERR_CUDA; }
     p->own_stream = true;
     for (auto &ev : p->ev) cudaEventCreate(&ev);
+    for (auto &ev : p->spmv_ev) cudaEventCreate(&ev);
     if (dev_alloc(&p->d_sc, 1) || dev_alloc(&p->d_partials, 2 * kMaxPartials) ||
         cudaMallocHost((void **)&p->h_sc, sizeof(DevScalars)) != cudaSuccess) {
         s3o_destroy(p);
@@ -262,6 +285,8 @@ int s3o_destroy(s3o_problem *p) {
     dev_free(p->d_sc); dev_free(p->d_partials);
     if (p->h_sc) cudaFreeHost(p->h_sc);
     for (auto &ev : p->ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : p->spmv_ev) if (ev) cudaEventDestroy(ev);
+    dev_free(p->d_est_snap);
     if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
     delete p;
     return S3O_OK;
@@ -307,6 +332,8 @@ int s3o_set_vertices(s3o_problem *p, int n, const double *est, const uint8_t *fi
     p->nv = n;
     p->nv_pad = pad32(n);
     p->cur = 0;
+    p->lm_valid = false;
+    dev_free(p->d_est_snap);
     p->fixed.assign(n, 0);
     if (fixed) memcpy(p->fixed.data(), fixed, n);
     int rc;
@@ -338,6 +365,7 @@ int s3o_set_estimates(s3o_problem *p, const double *est) {
     if (!p || !est || !p->d_est[0]) { set_error("s3o_set_estimates: call s3o_set_vertices first"); return S3O_ERR_INVALID; }
     cudaSetDevice(p->device);
     p->linearized = false;
+    if (p->lm_resume != 2) p->lm_valid = false;
     return upload_estimates(p, est);
 }
 
@@ -636,19 +664,20 @@ int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterat
     if (iterations) *iterations = -1;
     if (p->S.nf == 0) { set_error("s3o_optimize: 0 vertices to optimize"); return S3O_ERR_INVALID; }
     const int nf = p->S.nf, d = p->d;
-    double lambda = 0, ni = 2, currentChi = 0;
+    const bool resume = p->lm_resume != 0 && p->lm_valid;
+    double lambda = resume ? p->lm_lambda : 0, ni = resume ? p->lm_ni : 2, currentChi = resume ? p->lm_chi : 0;
     int done = 0;
     p->stats.ms_linearize = p->stats.ms_solve = p->stats.ms_chi2 = p->stats.ms_update = p->stats.ms_total = 0;
     cudaEventRecord(p->ev[0], p->stream);
     int result = S3O_RESULT_OK;
     for (int it = 0; it < max_iter; ++it) {
-        if (it == 0) {
+        if (it == 0 && !resume) {
             if ((rc = do_chi2(p, p->cur))) return rc;
         }
         cudaEventRecord(p->ev[1], p->stream);
         if ((rc = do_linearize(p))) return rc;
         cudaEventRecord(p->ev[2], p->stream);
-        if (it == 0) {
+        if (it == 0 && !resume) {
             launch_maxdiag(d, p->d_H, p->d_rowptr, nf, p->d_partials, p->d_sc, p->stream);
             if ((rc = check_launch(p, 1))) return rc;
             if ((rc = sync_scalars(p))) return rc;
@@ -722,6 +751,7 @@ int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterat
         p->stats.ms_total = ms;
     }
     p->linearized = false;
+    p->lm_valid = true; p->lm_lambda = lambda; p->lm_ni = ni; p->lm_chi = currentChi;
     if (iterations) *iterations = done;
     if (final_chi2) *final_chi2 = currentChi;
     if (final_lambda) *final_lambda = lambda;
@@ -743,6 +773,32 @@ int s3o_get_vertices(s3o_problem *p, double *est) {
     if (e != cudaSuccess) { set_error("s3o_get_vertices: %s", cudaGetErrorString(e)); return S3O_ERR_CUDA; }
     p->stats.d2h_bytes += (int64_t)(cnt * sizeof(double));
     p->stats.kernel_launches += 1;
+    return S3O_OK;
+}
+
+int s3o_set_lm_resume(s3o_problem *p, int resume) {
+    if (!p) return S3O_ERR_INVALID;
+    if (resume < 0 || resume > 2) { set_error("s3o_set_lm_resume: mode must be 0, 1 or 2"); return S3O_ERR_INVALID; }
+    p->lm_resume = resume;
+    return S3O_OK;
+}
+
+int s3o_snapshot_estimates(s3o_problem *p) {
+    if (!p || !p->d_est[0]) { set_error("s3o_snapshot_estimates: no vertices"); return S3O_ERR_INVALID; }
+    cudaSetDevice(p->device);
+    const size_t cnt = (size_t)p->nv_pad * p->est_dim;
+    if (!p->d_est_snap) { int rc = dev_alloc(&p->d_est_snap, cnt); if (rc) return rc; }
+    S3O_CUDA(cudaMemcpyAsync(p->d_est_snap, p->d_est[p->cur], cnt * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    return S3O_OK;
+}
+
+int s3o_restore_estimates(s3o_problem *p) {
+    if (!p || !p->d_est_snap) { set_error("s3o_restore_estimates: no snapshot"); return S3O_ERR_INVALID; }
+    cudaSetDevice(p->device);
+    const size_t cnt = (size_t)p->nv_pad * p->est_dim;
+    S3O_CUDA(cudaMemcpyAsync(p->d_est[p->cur], p->d_est_snap, cnt * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    p->linearized = false;
+    p->lm_valid = false;
     return S3O_OK;
 }
 
