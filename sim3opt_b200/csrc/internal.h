@@ -40,7 +40,15 @@ struct HostStructure {
     std::vector<int32_t> inc_ptr, inc_ent;      // [nf+1], incidences: (sorted edge << 1) | side
     std::vector<int32_t> ccs_colptr, ccs_rowidx; // g2o-order upper block-CCS
     std::vector<int32_t> ccs2bsr;               // [nb] CCS position -> BSR block index
+    std::vector<int32_t> tile_row;              // [ntiles+1] first block row of each SpMV tile
+    int tile_blocks = 0;                        // tile capacity (blocks) the tiles were packed for
+    int max_row_blocks = 0;
 };
+
+// Packs whole block rows into tiles of at most `cap` blocks; a row with more than `cap` blocks
+// gets a tile of its own (processed in chunks by one CTA).
+void build_tiles(const std::vector<int32_t> &rowptr, int nf, int cap, std::vector<int32_t> &tile_row);
+int spmv_tile_blocks(int d);
 
 void build_structure_host(int nv, const uint8_t *fixed, int ne, const int32_t *v0, const int32_t *v1,
                           HostStructure &S);

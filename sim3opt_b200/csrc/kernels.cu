@@ -16,64 +16,9 @@
 #include "../../include/sim3opt_b200.h"
 #include "kernels.cuh"
 #include "sim3_math.cuh"
+#include "reduce.cuh"
 
 namespace s3o {
-
-// ======================================================================================
-// reductions
-// ======================================================================================
-template <int NT>
-__device__ __forceinline__ double block_sum(double v, double *sh /* [32] */) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __syncthreads();
-    if (lane == 0) sh[warp] = v;
-    __syncthreads();
-    if (warp == 0) {
-        v = lane < (NT / 32) ? sh[lane] : 0.0;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-    }
-    return v;  // valid in thread 0
-}
-
-template <int NT>
-__device__ __forceinline__ double block_max(double v, double *sh) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, off));
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __syncthreads();
-    if (lane == 0) sh[warp] = v;
-    __syncthreads();
-    if (warp == 0) {
-        v = lane < (NT / 32) ? sh[lane] : 0.0;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, off));
-    }
-    return v;
-}
-
-// Ticket: returns true in every thread of the last CTA to arrive; resets the counter.
-__device__ __forceinline__ bool last_block(unsigned *counter) {
-    __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned t = atomicAdd(counter, 1u);
-        s_last = (t == gridDim.x - 1);
-        if (s_last) *counter = 0;
-    }
-    __syncthreads();
-    return s_last != 0;
-}
-
-template <int NT>
-__device__ __forceinline__ double sum_partials(const double *partials, int n, double *sh) {
-    double v = 0;
-    for (int i = threadIdx.x; i < n; i += NT) v += __ldcg(partials + i);
-    return block_sum<NT>(v, sh);
-}
 
 // ======================================================================================
 // packing
@@ -770,7 +715,6 @@ void launch_precond(int d, const double *H, const int32_t *rowptr, int nf, doubl
 // t = H_ij^T p_i to T[k]; the column owner adds its T entries in fixed order (finish_q /
 // pcg_update).  p.q is formed here as sum_i p_i.(diag_i + 2 off_i), so no second pass over q
 // is needed before alpha.
-template <int D> struct GroupLanes { static constexpr int value = D > 4 ? 8 : (D > 2 ? 4 : (D > 1 ? 2 : 1)); };
 
 template <int D, int NT, int TB>
 __global__ void __launch_bounds__(NT) spmv_kernel(const double *__restrict__ H, StructDev s, int nf, double lambda,

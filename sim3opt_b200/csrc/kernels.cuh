@@ -42,6 +42,8 @@ struct StructDev {
     const int32_t *colT_ptr, *colT_blk;
     const int32_t *inc_ptr, *inc_ent;
     const int32_t *e_blk;
+    const int32_t *tile_row;  // [ntiles+1]
+    int ntiles;
 };
 
 constexpr int kMaxPartials = 4096;
@@ -79,5 +81,13 @@ void launch_pcg_pupdate(int d, int nf, const double *z, double *p, const DevScal
 void launch_scale(int n, const double *x, const double *b, double lambda, double *partials, DevScalars *sc,
                   cudaStream_t st);
 int launches_per_pcg_iter();
+// tiled thread-per-block SpMV (spmv.cu)
+int spmv_tile_blocks(int d);
+int spmv2_configure();
+int spmv3_tile_blocks(int d);
+void launch_spmv3(int d, const double *H, const StructDev &s, int nf, double lambda, const double *p, double *q1,
+                  double *T, double *partials, DevScalars *sc, int pcg_mode, int grid_cap, cudaStream_t st);
+void launch_spmv2(int d, const double *H, const StructDev &s, int nf, double lambda, const double *p, double *q1,
+                  double *T, double *partials, DevScalars *sc, int pcg_mode, cudaStream_t st);
 
 }  // namespace s3o

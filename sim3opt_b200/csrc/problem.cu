@@ -14,6 +14,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 
 #include "internal.h"
@@ -68,6 +69,9 @@ struct s3o_problem {
     bool built = false;
     int32_t *d_rowptr = nullptr, *d_colidx = nullptr, *d_blk_row = nullptr, *d_blk_ebeg = nullptr, *d_blk_eend = nullptr;
     int32_t *d_colT_ptr = nullptr, *d_colT_blk = nullptr, *d_inc_ptr = nullptr, *d_inc_ent = nullptr, *d_e_blk = nullptr;
+    int32_t *d_tile_row = nullptr;
+    int spmv_version = 3;       // 1: lane-group rows, 2: tiled thread-per-block, 3: v2 + TMA ring
+    int spmv_grid_cap = 148 * 2;
     // linear system
     double *d_H = nullptr, *d_b = nullptr, *d_x = nullptr, *d_r = nullptr, *d_z = nullptr, *d_p = nullptr;
     double *d_q1 = nullptr, *d_T = nullptr, *d_Minv = nullptr, *d_scratch = nullptr, *d_partials = nullptr;
@@ -99,6 +103,8 @@ struct s3o_problem {
 
 namespace {
 
+void run_spmv(s3o_problem *p, const StructDev &s, double lambda, const double *x, int pcg_mode);
+
 GraphDev graph_view(const s3o_problem *p, int which) {
     GraphDev g{};
     g.kind = p->kind; g.d = p->d; g.est_dim = p->est_dim; g.ninfo = p->ninfo;
@@ -116,6 +122,7 @@ StructDev struct_view(const s3o_problem *p) {
     s.blk_ebeg = p->d_blk_ebeg; s.blk_eend = p->d_blk_eend;
     s.colT_ptr = p->d_colT_ptr; s.colT_blk = p->d_colT_blk;
     s.inc_ptr = p->d_inc_ptr; s.inc_ent = p->d_inc_ent; s.e_blk = p->d_e_blk;
+    s.tile_row = p->d_tile_row; s.ntiles = (int)p->S.tile_row.size() - 1;
     return s;
 }
 
@@ -123,7 +130,7 @@ void free_structure(s3o_problem *p) {
     dev_free(p->d_hidx); dev_free(p->d_sv0); dev_free(p->d_sv1); dev_free(p->d_meas); dev_free(p->d_info);
     dev_free(p->d_rowptr); dev_free(p->d_colidx); dev_free(p->d_blk_row); dev_free(p->d_blk_ebeg);
     dev_free(p->d_blk_eend); dev_free(p->d_colT_ptr); dev_free(p->d_colT_blk); dev_free(p->d_inc_ptr);
-    dev_free(p->d_inc_ent); dev_free(p->d_e_blk);
+    dev_free(p->d_inc_ent); dev_free(p->d_e_blk); dev_free(p->d_tile_row);
     dev_free(p->d_H); dev_free(p->d_b); dev_free(p->d_x); dev_free(p->d_r); dev_free(p->d_z); dev_free(p->d_p);
     dev_free(p->d_q1); dev_free(p->d_T); dev_free(p->d_Minv); dev_free(p->d_scratch);
     p->built = false;
@@ -159,6 +166,16 @@ int ensure_built(s3o_problem *p) {
     return s3o_build_structure(p, nullptr, nullptr);
 }
 
+void run_spmv(s3o_problem *p, const StructDev &s, double lambda, const double *x, int pcg_mode) {
+    if (p->spmv_version == 1)
+        launch_spmv(p->d, p->d_H, s, p->S.nf, lambda, x, p->d_q1, p->d_T, p->d_partials, p->d_sc, pcg_mode, p->stream);
+    else if (p->spmv_version == 3 && p->S.max_row_blocks <= p->S.tile_blocks)
+        launch_spmv3(p->d, p->d_H, s, p->S.nf, lambda, x, p->d_q1, p->d_T, p->d_partials, p->d_sc, pcg_mode,
+                     p->spmv_grid_cap, p->stream);
+    else
+        launch_spmv2(p->d, p->d_H, s, p->S.nf, lambda, x, p->d_q1, p->d_T, p->d_partials, p->d_sc, pcg_mode, p->stream);
+}
+
 int do_chi2(s3o_problem *p, int which) {
     if (p->S.ne_act == 0) {
         S3O_CUDA(cudaMemsetAsync(&p->d_sc->chi2, 0, sizeof(double), p->stream));
@@ -191,7 +208,7 @@ int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel
         for (int k = 0; k < batch; ++k) {
             const bool sample = ((launched + k) & 15) == 7 && p->spmv_ev_used < s3o_problem::kSpmvEvents;
             if (sample) cudaEventRecord(p->spmv_ev[2 * p->spmv_ev_used], p->stream);
-            launch_spmv(d, p->d_H, s, nf, lambda, p->d_p, p->d_q1, p->d_T, p->d_partials, p->d_sc, 1, p->stream);
+            run_spmv(p, s, lambda, p->d_p, 1);
             if (sample) cudaEventRecord(p->spmv_ev[2 * p->spmv_ev_used++ + 1], p->stream);
             launch_pcg_update(d, s, nf, p->d_q1, p->d_T, p->d_Minv, p->d_p, p->d_x, p->d_r, p->d_z, p->d_partials,
                               p->d_sc, p->stream);
@@ -261,6 +278,9 @@ int s3o_create(int kind, int device, s3o_problem **out) {
     cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); delete p; return S3O_ERR_CUDA; }
     p->own_stream = true;
+    if (spmv2_configure() != 0) { set_error("s3o_create: cannot configure SpMV shared memory"); delete p; return S3O_ERR_CUDA; }
+    if (const char *v = getenv("S3O_SPMV_VERSION")) p->spmv_version = atoi(v);
+    if (const char *v = getenv("S3O_SPMV_GRID")) p->spmv_grid_cap = atoi(v);
     for (auto &ev : p->ev) cudaEventCreate(&ev);
     for (auto &ev : p->spmv_ev) cudaEventCreate(&ev);
     if (dev_alloc(&p->d_sc, 1) || dev_alloc(&p->d_partials, 2 * kMaxPartials) ||
@@ -465,11 +485,16 @@ int s3o_build_structure(s3o_problem *p, int *n_free, int *n_blocks) {
         rc = rc ? rc : upload(p, &p->d_inc_ptr, S.inc_ptr);
         rc = rc ? rc : upload(p, &p->d_inc_ent, S.inc_ent);
         rc = rc ? rc : upload(p, &p->d_e_blk, S.e_blk);
+        S.max_row_blocks = 0;
+        for (int r = 0; r < S.nf; ++r) S.max_row_blocks = std::max(S.max_row_blocks, S.rowptr[r + 1] - S.rowptr[r]);
+        S.tile_blocks = p->spmv_version == 3 ? spmv3_tile_blocks(p->d) : spmv_tile_blocks(p->d);
+        build_tiles(S.rowptr, S.nf, S.tile_blocks, S.tile_row);
+        rc = rc ? rc : upload(p, &p->d_tile_row, S.tile_row);
         rc = rc ? rc : upload(p, &d_perm, S.perm);
         rc = rc ? rc : dev_alloc(&p->d_meas, (size_t)p->ne_pad * p->est_dim);
         if (p->has_info) rc = rc ? rc : dev_alloc(&p->d_info, (size_t)p->ne_pad * p->ninfo);
         const size_t nfd = (size_t)S.nf * p->d, dd = (size_t)p->d * p->d;
-        rc = rc ? rc : dev_alloc(&p->d_H, (size_t)S.nb * dd);
+        rc = rc ? rc : dev_alloc(&p->d_H, (size_t)S.nb * dd + 2);   // +16 B: the TMA tile copy rounds its size up
         rc = rc ? rc : dev_alloc(&p->d_b, nfd);
         rc = rc ? rc : dev_alloc(&p->d_x, nfd);
         rc = rc ? rc : dev_alloc(&p->d_r, nfd);
@@ -628,7 +653,7 @@ int s3o_hessian_multiply(s3o_problem *p, double lambda, const double *x, double 
     cudaSetDevice(p->device);
     const size_t bytes = (size_t)p->S.nf * p->d * sizeof(double);
     S3O_CUDA(cudaMemcpyAsync(p->d_p, x, bytes, cudaMemcpyHostToDevice, p->stream));
-    launch_spmv(p->d, p->d_H, struct_view(p), p->S.nf, lambda, p->d_p, p->d_q1, p->d_T, p->d_partials, p->d_sc, 0, p->stream);
+    run_spmv(p, struct_view(p), lambda, p->d_p, 0);
     launch_finish_q(p->d, struct_view(p), p->S.nf, p->d_q1, p->d_T, p->d_z, p->stream);
     int rc = check_launch(p, 2);
     if (rc) return rc;

@@ -1,0 +1,63 @@
+// reduce.cuh -- deterministic block / grid reductions shared by the kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace s3o {
+
+template <int NT>
+__device__ __forceinline__ double block_sum(double v, double *sh /* [32] */) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        v = lane < (NT / 32) ? sh[lane] : 0.0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    }
+    return v;  // valid in thread 0
+}
+
+template <int NT>
+__device__ __forceinline__ double block_max(double v, double *sh) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, off));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        v = lane < (NT / 32) ? sh[lane] : 0.0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, off));
+    }
+    return v;
+}
+
+// Ticket: returns true in every thread of the last CTA to arrive; resets the counter.
+__device__ __forceinline__ bool last_block(unsigned *counter) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(counter, 1u);
+        s_last = (t == gridDim.x - 1);
+        if (s_last) *counter = 0;
+    }
+    __syncthreads();
+    return s_last != 0;
+}
+
+template <int NT>
+__device__ __forceinline__ double sum_partials(const double *partials, int n, double *sh) {
+    double v = 0;
+    for (int i = threadIdx.x; i < n; i += NT) v += __ldcg(partials + i);
+    return block_sum<NT>(v, sh);
+}
+
+
+template <int D> struct GroupLanes { static constexpr int value = D > 4 ? 8 : (D > 2 ? 4 : (D > 1 ? 2 : 1)); };
+
+}  // namespace s3o

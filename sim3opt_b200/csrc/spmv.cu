@@ -1,0 +1,362 @@
+// spmv.cu -- tiled symmetric BSR-upper SpMV  q = (H + lambda I) p,  one thread per block.
+//
+// Replaces the per-trial  LinearSolverEigen::solve  numeric work [EXT g2o] as
+// the inner product of the PCG.  Layout facts it relies on: blocks are BSR-upper with the diagonal
+// block first in every row; a tile is a run of whole block rows whose blocks are contiguous in
+// memory (host packs at most TB blocks per tile; a row with more blocks has a tile of its own and
+// is walked in chunks).
+//
+// Per tile:   stage   the tile's blocks (contiguous, <= TB*D*D doubles) into shared memory with
+//                     fully coalesced streaming loads
+//             phase A thread t owns block kbeg+t: reads it from shared memory once (stride D*D
+//                     doubles between lanes: conflict-free) and forms both  H p_j  (row part)
+//                     and  H^T p_i  (column part) in registers
+//             phase B the column parts leave as one coalesced copy into T[k]; the row parts are
+//                     summed per (row, component) in block order -- fixed order, no atomics --
+//                     and p.q is accumulated as  sum_i p_i . (diag_i + 2 off_i)
+#include "../../include/sim3opt_b200.h"
+#include "kernels.cuh"
+#include "reduce.cuh"
+
+namespace s3o {
+
+int spmv_tile_blocks(int d) { return d == 7 ? 128 : 256; }
+
+template <int D> struct Spmv2Cfg;
+template <> struct Spmv2Cfg<7> { static constexpr int NT = 128, TB = 128; };
+template <> struct Spmv2Cfg<4> { static constexpr int NT = 256, TB = 256; };
+template <> struct Spmv2Cfg<1> { static constexpr int NT = 256, TB = 256; };
+
+template <int D, int TB>
+constexpr size_t spmv2_smem_bytes() { return sizeof(double) * (size_t)(TB * D * D + 2 * TB * D); }
+
+template <int D, int NT, int TB>
+__global__ void __launch_bounds__(NT) spmv2_kernel(const double *__restrict__ H, StructDev s, int nf, double lambda,
+                                                   const double *__restrict__ p, double *__restrict__ q1,
+                                                   double *__restrict__ T, double *__restrict__ partials,
+                                                   DevScalars *sc, int pcg_mode) {
+    constexpr int DD = D * D;
+    extern __shared__ double smem[];
+    double *tile = smem;              // [TB*DD]
+    double *ys = tile + TB * DD;      // [TB*D] row parts
+    double *ts = ys + TB * D;         // [TB*D] column parts
+    __shared__ double sh[32];
+    if (pcg_mode && sc->done) return;
+    const int t = threadIdx.x;
+    double local = 0;
+    for (int tl = blockIdx.x; tl < s.ntiles; tl += gridDim.x) {
+        const int row0 = s.tile_row[tl], row1 = s.tile_row[tl + 1];
+        const int kbeg = s.rowptr[row0], kend = s.rowptr[row1];
+        const int nrows = row1 - row0;
+        double hub1 = 0, hub2 = 0;    // running sums of a hub row walked in chunks (thread c < D)
+        for (int sub = kbeg; sub < kend; sub += TB) {
+            const int cnt = min(TB, kend - sub);
+            // ---- stage ------------------------------------------------------------------
+            const double *src = H + (size_t)sub * DD;
+            for (int idx = t; idx < cnt * DD; idx += NT) tile[idx] = __ldcs(src + idx);
+            // ---- phase A ----------------------------------------------------------------
+            double acc[D], tt[D];
+            int i = 0, j = 0;
+            double pi[D], pj[D];
+            for (int kl = t; kl < cnt; kl += NT) {       // NT >= TB in every configuration: one pass
+                i = s.blk_row[sub + kl];
+                j = s.colidx[sub + kl];
+#pragma unroll
+                for (int c = 0; c < D; ++c) pi[c] = p[(size_t)i * D + c];
+                if (j != i) {
+#pragma unroll
+                    for (int c = 0; c < D; ++c) pj[c] = p[(size_t)j * D + c];
+                }
+            }
+            __syncthreads();
+            for (int kl = t; kl < cnt; kl += NT) {
+                const double *Hs = tile + kl * DD;
+                if (j == i) {
+#pragma unroll
+                    for (int r = 0; r < D; ++r) {
+                        double a = lambda * pi[r];
+#pragma unroll
+                        for (int c = 0; c < D; ++c) a += Hs[r * D + c] * pi[c];
+                        acc[r] = a;
+                        tt[r] = 0;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < D; ++c) tt[c] = 0;
+#pragma unroll
+                    for (int r = 0; r < D; ++r) {
+                        double a = 0;
+#pragma unroll
+                        for (int c = 0; c < D; ++c) {
+                            const double h = Hs[r * D + c];
+                            a += h * pj[c];
+                            tt[c] += h * pi[r];
+                        }
+                        acc[r] = a;
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    ys[kl * D + c] = acc[c];
+                    ts[kl * D + c] = tt[c];
+                }
+            }
+            __syncthreads();
+            // ---- phase B ----------------------------------------------------------------
+            double *Tdst = T + (size_t)sub * D;
+            for (int idx = t; idx < cnt * D; idx += NT) Tdst[idx] = ts[idx];
+            if (kend - kbeg <= TB) {
+                for (int w = t; w < nrows * D; w += NT) {
+                    const int rl = w / D, c = w - rl * D;
+                    const int row = row0 + rl;
+                    const int a = s.rowptr[row] - sub, e = s.rowptr[row + 1] - sub;
+                    const double y1 = ys[a * D + c];
+                    double y2 = 0;
+                    for (int kl = a + 1; kl < e; ++kl) y2 += ys[kl * D + c];
+                    q1[(size_t)row * D + c] = y1 + y2;
+                    local += p[(size_t)row * D + c] * (y1 + 2.0 * y2);
+                }
+            } else if (t < D) {                         // hub row: exactly one row in this tile
+                int kl = 0;
+                if (sub == kbeg) { hub1 = ys[t]; kl = 1; }
+                for (; kl < cnt; ++kl) hub2 += ys[kl * D + t];
+                if (sub + cnt >= kend) {
+                    q1[(size_t)row0 * D + t] = hub1 + hub2;
+                    local += p[(size_t)row0 * D + t] * (hub1 + 2.0 * hub2);
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (!pcg_mode) return;
+    const double bs = block_sum<NT>(local, sh);
+    if (threadIdx.x == 0) partials[blockIdx.x] = bs;
+    if (last_block(&sc->counters[3])) {
+        const double pq = sum_partials<NT>(partials, gridDim.x, sh);
+        if (threadIdx.x == 0) {
+            sc->pq = pq;
+            if (!(pq > 0) || !isfinite(pq)) { sc->done = 3; sc->alpha = 0; }
+            else sc->alpha = sc->rz / pq;
+        }
+    }
+}
+
+
+// ======================================================================================
+// v3: the same tile algorithm with the staging done by the TMA engine.
+// ======================================================================================
+// Persistent CTAs walk their tiles with a two-deep shared-memory ring: one elected thread issues a
+// single cp.async.bulk (global -> shared, completion on an mbarrier) for tile n+1 while the CTA
+// computes tile n, so the block stream never waits on registers or on the LSU.  The bulk copy needs
+// 16-byte aligned addresses and sizes; a d x d block is d*d*8 bytes (392 for d=7), so a tile that
+// starts on an odd block index is fetched from 8 bytes earlier and the tile data begins at
+// element 1 of the buffer (the H array carries 16 bytes of tail padding).
+// Precondition (checked on the host): no block row exceeds the tile capacity.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int D> struct Spmv3Cfg;
+template <> struct Spmv3Cfg<7> { static constexpr int NT = 128, TB = 112; };
+template <> struct Spmv3Cfg<4> { static constexpr int NT = 256, TB = 256; };
+template <> struct Spmv3Cfg<1> { static constexpr int NT = 256, TB = 256; };
+
+template <int D, int TB>
+constexpr size_t spmv3_smem_bytes() { return sizeof(double) * (size_t)(2 * (TB * D * D + 2) + 2 * TB * D) + 16; }
+
+template <int D, int NT, int TB>
+__global__ void __launch_bounds__(NT) spmv3_kernel(const double *__restrict__ H, StructDev s, int nf, double lambda,
+                                                   const double *__restrict__ p, double *__restrict__ q1,
+                                                   double *__restrict__ T, double *__restrict__ partials,
+                                                   DevScalars *sc, int pcg_mode) {
+    constexpr int DD = D * D;
+    constexpr int BUF = TB * DD + 2;          // doubles per ring slot (tile + alignment slack), even
+    extern __shared__ __align__(16) double smem[];
+    double *ring = smem;                      // [2][BUF]
+    double *ys = ring + 2 * BUF;              // [TB*D]
+    double *ts = ys + TB * D;                 // [TB*D]
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(ts + TB * D);   // [2]
+    __shared__ double sh[32];
+    if (pcg_mode && sc->done) return;
+    const int t = threadIdx.x;
+    if (t == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int tl, int slot) {      // called by thread 0 only
+        const int kb = s.rowptr[s.tile_row[tl]], ke = s.rowptr[s.tile_row[tl + 1]];
+        const int shift = (int)(((size_t)kb * DD) & 1);
+        const unsigned bytes = (unsigned)((((size_t)(ke - kb) * DD + shift) * 8 + 15) & ~(size_t)15);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&bar[slot], bytes);
+        tma_bulk_g2s(ring + slot * BUF, H + (size_t)kb * DD - shift, bytes, &bar[slot]);
+    };
+    double local = 0;
+    int n = 0;
+    if (t == 0 && (int)blockIdx.x < s.ntiles) issue(blockIdx.x, 0);
+    for (int tl = blockIdx.x; tl < s.ntiles; tl += gridDim.x, ++n) {
+        const int slot = n & 1;
+        const int nxt = tl + gridDim.x;
+        if (t == 0 && nxt < s.ntiles) issue(nxt, slot ^ 1);
+        const int row0 = s.tile_row[tl], row1 = s.tile_row[tl + 1];
+        const int kbeg = s.rowptr[row0], kend = s.rowptr[row1];
+        const int nrows = row1 - row0, cnt = kend - kbeg;
+        const int shift = (int)(((size_t)kbeg * DD) & 1);
+        // gather this thread's block indices and vectors while the tile is in flight
+        int i = 0, j = 0;
+        double pi[D], pj[D];
+        if (t < cnt) {
+            i = s.blk_row[kbeg + t];
+            j = s.colidx[kbeg + t];
+#pragma unroll
+            for (int c = 0; c < D; ++c) pi[c] = p[(size_t)i * D + c];
+            if (j != i) {
+#pragma unroll
+                for (int c = 0; c < D; ++c) pj[c] = p[(size_t)j * D + c];
+            }
+        }
+        mbar_wait(&bar[slot], (unsigned)((n >> 1) & 1));
+        if (t < cnt) {
+            const double *Hs = ring + slot * BUF + shift + t * DD;
+            double acc[D], tt[D];
+            if (j == i) {
+#pragma unroll
+                for (int r = 0; r < D; ++r) {
+                    double a = lambda * pi[r];
+#pragma unroll
+                    for (int c = 0; c < D; ++c) a += Hs[r * D + c] * pi[c];
+                    acc[r] = a;
+                    tt[r] = 0;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < D; ++c) tt[c] = 0;
+#pragma unroll
+                for (int r = 0; r < D; ++r) {
+                    double a = 0;
+#pragma unroll
+                    for (int c = 0; c < D; ++c) {
+                        const double h = Hs[r * D + c];
+                        a += h * pj[c];
+                        tt[c] += h * pi[r];
+                    }
+                    acc[r] = a;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                ys[t * D + c] = acc[c];
+                ts[t * D + c] = tt[c];
+            }
+        }
+        __syncthreads();
+        double *Tdst = T + (size_t)kbeg * D;
+        for (int idx = t; idx < cnt * D; idx += NT) Tdst[idx] = ts[idx];
+        for (int w = t; w < nrows * D; w += NT) {
+            const int rl = w / D, c = w - rl * D;
+            const int row = row0 + rl;
+            const int a = s.rowptr[row] - kbeg, e = s.rowptr[row + 1] - kbeg;
+            const double y1 = ys[a * D + c];
+            double y2 = 0;
+            for (int kl = a + 1; kl < e; ++kl) y2 += ys[kl * D + c];
+            q1[(size_t)row * D + c] = y1 + y2;
+            local += p[(size_t)row * D + c] * (y1 + 2.0 * y2);
+        }
+        __syncthreads();
+    }
+    if (!pcg_mode) return;
+    const double bs = block_sum<NT>(local, sh);
+    if (threadIdx.x == 0) partials[blockIdx.x] = bs;
+    if (last_block(&sc->counters[3])) {
+        const double pq = sum_partials<NT>(partials, gridDim.x, sh);
+        if (threadIdx.x == 0) {
+            sc->pq = pq;
+            if (!(pq > 0) || !isfinite(pq)) { sc->done = 3; sc->alpha = 0; }
+            else sc->alpha = sc->rz / pq;
+        }
+    }
+}
+
+int spmv3_tile_blocks(int d) { return d == 7 ? Spmv3Cfg<7>::TB : 256; }
+
+void launch_spmv3(int d, const double *H, const StructDev &s, int nf, double lambda, const double *p, double *q1,
+                  double *T, double *partials, DevScalars *sc, int pcg_mode, int grid_cap, cudaStream_t st) {
+    if (nf == 0 || s.ntiles == 0) return;
+    const int grid = s.ntiles < grid_cap ? s.ntiles : grid_cap;
+#define S3O_SPMV3(D)                                                                                              \
+    spmv3_kernel<D, Spmv3Cfg<D>::NT, Spmv3Cfg<D>::TB><<<grid, Spmv3Cfg<D>::NT, spmv3_smem_bytes<D, Spmv3Cfg<D>::TB>(), st>>>( \
+        H, s, nf, lambda, p, q1, T, partials, sc, pcg_mode);
+    switch (d) {
+    case 7: S3O_SPMV3(7) break;
+    case 4: S3O_SPMV3(4) break;
+    case 1: S3O_SPMV3(1) break;
+    }
+#undef S3O_SPMV3
+}
+
+static int g_spmv2_ready = 0;
+
+int spmv2_configure() {
+    if (g_spmv2_ready) return 0;
+    cudaError_t e;
+    e = cudaFuncSetAttribute(spmv2_kernel<7, Spmv2Cfg<7>::NT, Spmv2Cfg<7>::TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)spmv2_smem_bytes<7, Spmv2Cfg<7>::TB>());
+    if (e != cudaSuccess) return -1;
+    e = cudaFuncSetAttribute(spmv2_kernel<4, Spmv2Cfg<4>::NT, Spmv2Cfg<4>::TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)spmv2_smem_bytes<4, Spmv2Cfg<4>::TB>());
+    if (e != cudaSuccess) return -1;
+    e = cudaFuncSetAttribute(spmv2_kernel<1, Spmv2Cfg<1>::NT, Spmv2Cfg<1>::TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)spmv2_smem_bytes<1, Spmv2Cfg<1>::TB>());
+    if (e != cudaSuccess) return -1;
+    e = cudaFuncSetAttribute(spmv3_kernel<7, Spmv3Cfg<7>::NT, Spmv3Cfg<7>::TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)spmv3_smem_bytes<7, Spmv3Cfg<7>::TB>());
+    if (e != cudaSuccess) return -1;
+    e = cudaFuncSetAttribute(spmv3_kernel<4, Spmv3Cfg<4>::NT, Spmv3Cfg<4>::TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)spmv3_smem_bytes<4, Spmv3Cfg<4>::TB>());
+    if (e != cudaSuccess) return -1;
+    e = cudaFuncSetAttribute(spmv3_kernel<1, Spmv3Cfg<1>::NT, Spmv3Cfg<1>::TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)spmv3_smem_bytes<1, Spmv3Cfg<1>::TB>());
+    if (e != cudaSuccess) return -1;
+    g_spmv2_ready = 1;
+    return 0;
+}
+
+void launch_spmv2(int d, const double *H, const StructDev &s, int nf, double lambda, const double *p, double *q1,
+                  double *T, double *partials, DevScalars *sc, int pcg_mode, cudaStream_t st) {
+    if (nf == 0 || s.ntiles == 0) return;
+    const int cap = 148 * 24;   // persistent-style grid: a multiple of the SM count, <= kMaxPartials
+    const int grid = s.ntiles < cap ? s.ntiles : cap;
+#define S3O_SPMV2(D)                                                                                              \
+    spmv2_kernel<D, Spmv2Cfg<D>::NT, Spmv2Cfg<D>::TB><<<grid, Spmv2Cfg<D>::NT, spmv2_smem_bytes<D, Spmv2Cfg<D>::TB>(), st>>>( \
+        H, s, nf, lambda, p, q1, T, partials, sc, pcg_mode);
+    switch (d) {
+    case 7: S3O_SPMV2(7) break;
+    case 4: S3O_SPMV2(4) break;
+    case 1: S3O_SPMV2(1) break;
+    }
+#undef S3O_SPMV2
+}
+
+}  // namespace s3o

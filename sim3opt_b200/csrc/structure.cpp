@@ -143,4 +143,23 @@ void build_structure_host(int nv, const uint8_t *fixed, int ne, const int32_t *v
     S.ccs_colptr[nf] = pos;
 }
 
+
+void build_tiles(const std::vector<int32_t> &rowptr, int nf, int cap, std::vector<int32_t> &tile_row) {
+    tile_row.clear();
+    tile_row.push_back(0);
+    int r = 0;
+    while (r < nf) {
+        const int start = r;
+        int blocks = 0;
+        while (r < nf) {
+            const int nb_row = rowptr[r + 1] - rowptr[r];
+            if (blocks + nb_row > cap && r > start) break;
+            blocks += nb_row;
+            ++r;
+            if (blocks >= cap) break;   // also closes a hub row's own tile
+        }
+        tile_row.push_back(r);
+    }
+}
+
 }  // namespace s3o

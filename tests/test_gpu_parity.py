@@ -260,3 +260,39 @@ def test_resume_and_snapshot(sphere_small):
     assert np.array_equal(a.vertices(), v0)
     n2, chi_a2, _, _ = a.optimize(3)
     assert chi_a2 == chi_a                              # bitwise reproducible solve
+
+
+def test_hub_vertex_rows_longer_than_a_tile():
+    """A star graph: one block row holds 400 off-diagonal blocks (> one SpMV tile)."""
+    orc = _orc()
+    rng = np.random.default_rng(3)
+    n = 402
+    est = np.zeros((n, 8))
+    for k in range(n):
+        est[k] = orc.sim3_exp(np.concatenate([rng.normal(0, 0.3, 3), rng.normal(0, 2, 3), rng.normal(0, 0.1, 1)]))
+    fixed = np.zeros(n, np.uint8)
+    fixed[0] = 1
+    v0 = np.concatenate([[0], np.ones(n - 2, np.int32), np.arange(2, n - 1)]).astype(np.int32)
+    v1 = np.concatenate([[1], np.arange(2, n), np.arange(3, n)]).astype(np.int32)
+    meas = np.zeros((len(v0), 8))
+    for e in range(len(v0)):
+        noise = orc.sim3_exp(rng.normal(0, 0.05, 7))
+        meas[e] = orc.sim3_mul(noise, orc.sim3_mul(est[v1[e]], orc.sim3_inv(est[v0[e]])))
+    g = dict(est=est, fixed=fixed, v0=v0, v1=v1, meas=meas)
+    gpu, cpu = make_gpu(g, jac=1), make_oracle(g, jac=orc.JAC_ANALYTIC)
+    colptr, rowidx = gpu.build_structure()
+    cp_c, ri_c = cpu.build_structure()
+    assert np.array_equal(colptr, cp_c) and np.array_equal(rowidx, ri_c)
+    Hg, bg = gpu.linearize()
+    Hc, bc = cpu.linearize()
+    assert np.abs(Hg - Hc).max() <= 1e-10 * np.abs(Hc).max()
+    A = dense_from_blocks(colptr, rowidx, Hg, 7)
+    x = rng.normal(size=A.shape[0])
+    y = gpu.hessian_multiply(0.5, x)
+    ref = A @ x + 0.5 * x
+    assert np.abs(y - ref).max() <= 1e-12 * np.abs(ref).max()
+    gpu.set_pcg(1e-12, 5000)
+    rc, xs, iters, rel = gpu.solve(1e-3)
+    assert rc == 0
+    Ad = A + 1e-3 * np.eye(len(bg))
+    assert np.linalg.norm(Ad @ xs - bg) <= 1e-10 * np.linalg.norm(bg)
