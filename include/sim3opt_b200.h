@@ -76,6 +76,23 @@ int s3o_destroy(s3o_problem *p);
  * NULL = a private non-blocking stream created by s3o_create */
 int s3o_set_stream(s3o_problem *p, void *cuda_stream);
 
+/* ---- partitioned solve across the GPUs of one box -----------------
+ * One process per GPU.  Rank 0 obtains a 128-byte NCCL unique id, the host program broadcasts it
+ * (e.g. torch.distributed), and every rank calls s3o_set_comm BEFORE s3o_set_edges.  Every rank
+ * passes the SAME full vertex and edge arrays; the library keeps the rows of the free-vertex range
+ * it owns (rank r owns Hessian indices [r*seg, (r+1)*seg), seg = ceil(n_free/world)), evaluates the
+ * edges that touch them, exchanges halo entries of the PCG direction over NVLink (NCCL send/recv),
+ * all-reduces the PCG dot products / chi2 / scale, and all-gathers the step before retracting, so
+ * all ranks hold the same estimates after s3o_optimize.  Lock-step getters (s3o_get_hessian,
+ * s3o_solve's x, ...) then refer to the local rows. */
+int s3o_comm_unique_id(char *id128);
+int s3o_set_comm(s3o_problem *p, int rank, int world, const char *id128);
+/* host-only twin: the partition plan of one rank (counts only + the ghost list) for tests */
+int s3o_host_partition(int n_vertices, const uint8_t *fixed, int n_edges, const int32_t *v0, const int32_t *v1,
+                       int rank, int world, int32_t *n_own, int32_t *n_ghost, int32_t *n_local_edges,
+                       int32_t *n_primary, int32_t *ghosts /* n_vertices */, int32_t *send_count /* world */,
+                       int32_t *recv_count /* world */, int32_t *send_idx_global /* n_vertices*(world-1) upper bound */);
+
 /* ---- graph (replaces addVertex / addEdge) --------------------------------------------- */
 /* est: n x est_dim (SIM3 8, SCALE_TRANS 4, SCALE 1); fixed: n bytes or NULL;
  * aux: n x 4 rotation quaternions (SCALE_TRANS only, vST->Rw2i at kitti_surf.cpp:792-793) */

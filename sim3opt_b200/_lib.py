@@ -35,6 +35,9 @@ SYMBOLS = {
     "s3o_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "s3o_destroy": (C.c_int, [C.c_void_p]),
     "s3o_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "s3o_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "s3o_set_comm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
+    "s3o_host_partition": (C.c_int, [C.c_int, _up, C.c_int, _ip, _ip, C.c_int, C.c_int, _ip, _ip, _ip, _ip, _ip, _ip, _ip, _ip]),
     "s3o_set_vertices": (C.c_int, [C.c_void_p, C.c_int, _dp, _up, _dp]),
     "s3o_set_edges": (C.c_int, [C.c_void_p, C.c_int, _ip, _ip, _dp, _dp]),
     "s3o_set_estimates": (C.c_int, [C.c_void_p, _dp]),

@@ -64,6 +64,10 @@ class Problem:
         except Exception:
             pass
 
+    def set_comm(self, rank, world, unique_id):
+        """Partitioned solve: call before set_edges on every rank with the id rank 0 generated."""
+        self._check(self.L.s3o_set_comm(self.h, int(rank), int(world), bytes(unique_id) if unique_id else None))
+
     def set_stream(self, cuda_stream_handle):
         self._check(self.L.s3o_set_stream(self.h, C.c_void_p(int(cuda_stream_handle) if cuda_stream_handle else None)))
 
@@ -194,6 +198,39 @@ class Problem:
         out = C.c_double(0)
         self._check(self.L.s3o_estimate_sigma_squared(self.h, robust_kind, C.byref(out)))
         return out.value
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it; broadcast it to the other ranks)."""
+    L = _lib.load()
+    buf = C.create_string_buffer(128)
+    rc = L.s3o_comm_unique_id(buf)
+    if rc != 0:
+        raise S3OError(f"s3o error {rc}: {L.s3o_last_error().decode()}")
+    return buf.raw
+
+
+def host_partition(n_vertices, fixed, v0, v1, rank, world):
+    """Partition plan of one rank, computed on the host (no device needed)."""
+    L = _lib.load()
+    v0 = np.ascontiguousarray(v0, np.int32)
+    v1 = np.ascontiguousarray(v1, np.int32)
+    fx = np.zeros(n_vertices, np.uint8) if fixed is None else np.ascontiguousarray(fixed, np.uint8)
+    scal = [C.c_int32(0) for _ in range(4)]
+    ghosts = np.zeros(max(n_vertices, 1), np.int32)
+    send_idx = np.zeros(max(n_vertices * max(world - 1, 1), 1), np.int32)
+    send_count = np.zeros(world, np.int32)
+    recv_count = np.zeros(world, np.int32)
+    rc = L.s3o_host_partition(n_vertices, fx.ctypes.data_as(_up), len(v0), v0.ctypes.data_as(_ip),
+                              v1.ctypes.data_as(_ip), rank, world, *[C.byref(x) for x in scal],
+                              ghosts.ctypes.data_as(_ip), send_count.ctypes.data_as(_ip),
+                              recv_count.ctypes.data_as(_ip), send_idx.ctypes.data_as(_ip))
+    if rc != 0:
+        raise S3OError(f"s3o error {rc}: {L.s3o_last_error().decode()}")
+    n_own, n_ghost, n_local, n_primary = (x.value for x in scal)
+    return dict(n_own=n_own, n_ghost=n_ghost, n_local_edges=n_local, n_primary=n_primary,
+                ghosts=ghosts[:n_ghost].copy(), send_count=send_count, recv_count=recv_count,
+                send_idx=send_idx[:int(send_count.sum())].copy())
 
 
 def host_structure(n_vertices, fixed, v0, v1):

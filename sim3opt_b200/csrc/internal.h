@@ -52,5 +52,27 @@ int spmv_tile_blocks(int d);
 
 void build_structure_host(int nv, const uint8_t *fixed, int ne, const int32_t *v0, const int32_t *v1,
                           HostStructure &S);
+// same with an explicit Hessian-index map (hidx[v] in [0,nfree) or -1): used by the partitioned path,
+// where "free" means owned or ghost on this rank
+void build_structure_from_hidx(int nv, const int32_t *hidx, int nfree, int ne, const int32_t *v0, const int32_t *v1,
+                               HostStructure &S);
+
+// Vertex-range partition of the free vertices across `world` ranks.
+// Rank r owns global Hessian indices [r*seg, min((r+1)*seg, nf)), seg = ceil(nf/world).
+struct PartitionPlan {
+    int rank = 0, world = 1;
+    int nf_global = 0, seg = 0;
+    int own_lo = 0, n_own = 0, n_ghost = 0;
+    std::vector<int32_t> ghidx;        // [nv] global Hessian index, -1 fixed
+    std::vector<int32_t> lhidx;        // [nv] local Hessian index: owned [0,n_own), ghosts after, else -1
+    std::vector<int32_t> ghosts;       // global Hessian indices of the ghosts, ascending
+    std::vector<int32_t> local_edges;  // user edge indices with at least one owned endpoint (user order)
+    std::vector<uint8_t> primary;      // per local edge: 1 if this rank counts its chi2
+    std::vector<int32_t> recv_count, recv_off;   // [world] ghost runs per owner (in ghost order)
+    std::vector<int32_t> send_count, send_off;   // [world]
+    std::vector<int32_t> send_idx;               // local owned indices to pack, grouped by peer
+};
+void build_partition_plan(int nv, const uint8_t *fixed, int ne, const int32_t *v0, const int32_t *v1, int rank,
+                          int world, PartitionPlan &P);
 
 }  // namespace s3o

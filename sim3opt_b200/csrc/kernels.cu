@@ -218,6 +218,7 @@ __global__ void __launch_bounds__(NT) chi2_kernel(GraphDev g, double *__restrict
     __shared__ double sh[32];
     double local = 0;
     for (int t = blockIdx.x * NT + threadIdx.x; t < g.ne; t += gridDim.x * NT) {
+        if (g.primary && !g.primary[t]) continue;   // partitioned solve: cut edges are counted by one rank
         const int vi = g.sv0[t], vj = g.sv1[t];
         double xi[EST], xj[EST], m[EST], qi[4], qj[4], e[D];
         load_planes<EST>(g.est, g.nv_pad, vi, xi);
@@ -558,7 +559,7 @@ __global__ void retract_kernel(GraphDev g, const double *__restrict__ x, double 
     if (v >= g.nv) return;
     double xs[EST];
     load_planes<EST>(g.est, g.nv_pad, v, xs);
-    const int hcol = g.hidx[v];
+    const int hcol = g.ghidx ? g.ghidx[v] : g.hidx[v];
     if (hcol >= 0) {
         double delta[D];
 #pragma unroll
@@ -782,8 +783,7 @@ __global__ void __launch_bounds__(NT) spmv_kernel(const double *__restrict__ H, 
         const double pq = sum_partials<NT>(partials, gridDim.x, sh);
         if (threadIdx.x == 0) {
             sc->pq = pq;
-            if (!(pq > 0) || !isfinite(pq)) { sc->done = 3; sc->alpha = 0; }
-            else sc->alpha = sc->rz / pq;
+            fin_spmv(sc);
         }
     }
 }
@@ -836,7 +836,7 @@ __global__ void __launch_bounds__(NT) pcg_init_kernel(int nf, const double *__re
                                                       double *__restrict__ x, double *__restrict__ r,
                                                       double *__restrict__ z, double *__restrict__ p,
                                                       double *__restrict__ partials, DevScalars *sc, double tol,
-                                                      int max_iter) {
+                                                      int max_iter, int dist) {
     constexpr int GL = GroupLanes<D>::value, DD = D * D, RPC = NT / GL;
     __shared__ double sh[32];
     const int g = threadIdx.x / GL, l = threadIdx.x % GL;
@@ -868,9 +868,8 @@ __global__ void __launch_bounds__(NT) pcg_init_kernel(int nf, const double *__re
         const double rz = sum_partials<NT>(partials, gridDim.x, sh);
         const double rr = sum_partials<NT>(partials + kMaxPartials, gridDim.x, sh);
         if (threadIdx.x == 0) {
-            sc->rz = rz; sc->rr = rr; sc->rr0 = rr; sc->tol2 = tol * tol;
-            sc->iters = 0; sc->max_iter = max_iter; sc->alpha = 0; sc->beta = 0; sc->pq = 0;
-            sc->done = (rr == 0.0 || !(rz > 0)) ? 1 : 0;
+            sc->rz_new = rz; sc->rr = rr;
+            if (!dist) fin_init(sc, tol, max_iter);
         }
     }
 }
@@ -880,7 +879,7 @@ __global__ void __launch_bounds__(NT) pcg_update_kernel(StructDev s, int nf, con
                                                         const double *__restrict__ T, const double *__restrict__ Minv,
                                                         const double *__restrict__ p, double *__restrict__ x,
                                                         double *__restrict__ r, double *__restrict__ z,
-                                                        double *__restrict__ partials, DevScalars *sc) {
+                                                        double *__restrict__ partials, DevScalars *sc, int dist) {
     constexpr int GL = GroupLanes<D>::value, DD = D * D, RPC = NT / GL;
     __shared__ double sh[32];
     if (sc->done) return;
@@ -917,13 +916,9 @@ __global__ void __launch_bounds__(NT) pcg_update_kernel(StructDev s, int nf, con
         const double rz = sum_partials<NT>(partials, gridDim.x, sh);
         const double rr = sum_partials<NT>(partials + kMaxPartials, gridDim.x, sh);
         if (threadIdx.x == 0) {
-            sc->beta = rz / sc->rz;
-            sc->rz = rz;
+            sc->rz_new = rz;
             sc->rr = rr;
-            sc->iters += 1;
-            if (!(rr > sc->tol2 * sc->rr0)) sc->done = 1;            // converged (also catches NaN)
-            else if (sc->iters >= sc->max_iter) sc->done = 2;
-            else if (!(rz > 0)) sc->done = 3;
+            if (!dist) fin_update(sc);
         }
     }
 }
@@ -943,23 +938,23 @@ static int vec_grid(int nf, int rpc) {
 }
 
 void launch_pcg_init(int d, int nf, const double *b, const double *Minv, double *x, double *r, double *z, double *p,
-                     double *partials, DevScalars *sc, double tol, int max_iter, cudaStream_t st) {
+                     double *partials, DevScalars *sc, double tol, int max_iter, int dist, cudaStream_t st) {
     constexpr int NT = 256;
     switch (d) {
-    case 7: pcg_init_kernel<7, NT><<<vec_grid(nf, NT / 8), NT, 0, st>>>(nf, b, Minv, x, r, z, p, partials, sc, tol, max_iter); break;
-    case 4: pcg_init_kernel<4, NT><<<vec_grid(nf, NT / 4), NT, 0, st>>>(nf, b, Minv, x, r, z, p, partials, sc, tol, max_iter); break;
-    case 1: pcg_init_kernel<1, NT><<<vec_grid(nf, NT), NT, 0, st>>>(nf, b, Minv, x, r, z, p, partials, sc, tol, max_iter); break;
+    case 7: pcg_init_kernel<7, NT><<<vec_grid(nf, NT / 8), NT, 0, st>>>(nf, b, Minv, x, r, z, p, partials, sc, tol, max_iter, dist); break;
+    case 4: pcg_init_kernel<4, NT><<<vec_grid(nf, NT / 4), NT, 0, st>>>(nf, b, Minv, x, r, z, p, partials, sc, tol, max_iter, dist); break;
+    case 1: pcg_init_kernel<1, NT><<<vec_grid(nf, NT), NT, 0, st>>>(nf, b, Minv, x, r, z, p, partials, sc, tol, max_iter, dist); break;
     }
 }
 
 void launch_pcg_update(int d, const StructDev &s, int nf, const double *q1, const double *T, const double *Minv,
                        const double *p, double *x, double *r, double *z, double *partials, DevScalars *sc,
-                       cudaStream_t st) {
+                       int dist, cudaStream_t st) {
     constexpr int NT = 256;
     switch (d) {
-    case 7: pcg_update_kernel<7, NT><<<vec_grid(nf, NT / 8), NT, 0, st>>>(s, nf, q1, T, Minv, p, x, r, z, partials, sc); break;
-    case 4: pcg_update_kernel<4, NT><<<vec_grid(nf, NT / 4), NT, 0, st>>>(s, nf, q1, T, Minv, p, x, r, z, partials, sc); break;
-    case 1: pcg_update_kernel<1, NT><<<vec_grid(nf, NT), NT, 0, st>>>(s, nf, q1, T, Minv, p, x, r, z, partials, sc); break;
+    case 7: pcg_update_kernel<7, NT><<<vec_grid(nf, NT / 8), NT, 0, st>>>(s, nf, q1, T, Minv, p, x, r, z, partials, sc, dist); break;
+    case 4: pcg_update_kernel<4, NT><<<vec_grid(nf, NT / 4), NT, 0, st>>>(s, nf, q1, T, Minv, p, x, r, z, partials, sc, dist); break;
+    case 1: pcg_update_kernel<1, NT><<<vec_grid(nf, NT), NT, 0, st>>>(s, nf, q1, T, Minv, p, x, r, z, partials, sc, dist); break;
     }
 }
 
@@ -969,5 +964,27 @@ void launch_pcg_pupdate(int d, int nf, const double *z, double *p, const DevScal
 }
 
 int launches_per_pcg_iter() { return 3; }
+
+__global__ void pcg_fin_init_kernel(DevScalars *sc, double tol, int max_iter) { fin_init(sc, tol, max_iter); }
+__global__ void pcg_fin_spmv_kernel(DevScalars *sc) { if (!sc->done) fin_spmv(sc); }
+__global__ void pcg_fin_update_kernel(DevScalars *sc) { if (!sc->done) fin_update(sc); }
+void launch_pcg_fin_init(DevScalars *sc, double tol, int max_iter, cudaStream_t st) { pcg_fin_init_kernel<<<1, 1, 0, st>>>(sc, tol, max_iter); }
+void launch_pcg_fin_spmv(DevScalars *sc, cudaStream_t st) { pcg_fin_spmv_kernel<<<1, 1, 0, st>>>(sc); }
+void launch_pcg_fin_update(DevScalars *sc, cudaStream_t st) { pcg_fin_update_kernel<<<1, 1, 0, st>>>(sc); }
+
+// gathers the rows a peer needs (halo send buffer): out[n][d] = vec[idx[n]][d]
+__global__ void pack_rows_kernel(int d, const double *__restrict__ vec, const int32_t *__restrict__ idx, int n,
+                                 double *__restrict__ out, const DevScalars *sc) {
+    if (sc->done) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * d) return;
+    const int k = t / d, c = t - k * d;
+    out[t] = vec[(size_t)idx[k] * d + c];
+}
+void launch_pack_rows(int d, const double *vec, const int32_t *idx, int n, double *out, const DevScalars *sc,
+                      cudaStream_t st) {
+    if (n == 0) return;
+    pack_rows_kernel<<<(n * d + 255) / 256, 256, 0, st>>>(d, vec, idx, n, out, sc);
+}
 
 }  // namespace s3o

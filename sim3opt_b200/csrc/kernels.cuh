@@ -9,9 +9,11 @@ namespace s3o {
 // device; the host reads this struct back once per LM trial (and per PCG batch).
 struct DevScalars {
     double rz;        // r.z of the current iterate
+    double rz_new;    // r.z after the update   } adjacent: all-reduced together
+    double rr;        // |r|^2                  } in the partitioned solve
     double pq;        // p.(H+lambda I)p
     double alpha, beta;
-    double rr, rr0;   // |r|^2, |b|^2
+    double rr0;       // |b|^2
     double tol2;      // (rel_tol)^2
     double chi2;      // last chi2 reduction
     double scale;     // sum x_j (lambda x_j + b_j)   (computeScale)
@@ -34,6 +36,8 @@ struct GraphDev {
     int robust_kind;
     double robust_param;
     bool math_corrected;     // s3o_set_math_mode
+    const uint8_t *primary;  // [ne] partitioned solve: 1 if this rank counts the edge's chi2 (null: all)
+    const int32_t *ghidx;    // [nv] partitioned solve: global Hessian index addressing the gathered step
 };
 
 struct StructDev {
@@ -44,6 +48,7 @@ struct StructDev {
     const int32_t *e_blk;
     const int32_t *tile_row;  // [ntiles+1]
     int ntiles;
+    int n_own;                // rows owned by this rank (= nf on one GPU); columns >= n_own are ghosts
 };
 
 constexpr int kMaxPartials = 4096;
@@ -65,18 +70,25 @@ void launch_assemble(const GraphDev &g, const StructDev &s, const double *scratc
 void launch_retract(const GraphDev &g, const double *x, double *est_out, cudaStream_t st);
 
 // ---- linear algebra on the BSR-upper Hessian --------------------------------------------
+// `dist` != 0: the kernel only leaves its local sums in DevScalars; the caller all-reduces them and
+// launches the matching launch_pcg_fin_* kernel.
 void launch_maxdiag(int d, const double *H, const int32_t *rowptr, int nf, double *partials, DevScalars *sc,
                     cudaStream_t st);
+void launch_pcg_fin_init(DevScalars *sc, double tol, int max_iter, cudaStream_t st);
+void launch_pcg_fin_spmv(DevScalars *sc, cudaStream_t st);
+void launch_pcg_fin_update(DevScalars *sc, cudaStream_t st);
+void launch_pack_rows(int d, const double *vec, const int32_t *idx, int n, double *out, const DevScalars *sc,
+                      cudaStream_t st);
 void launch_precond(int d, const double *H, const int32_t *rowptr, int nf, double lambda, double *Minv,
                     DevScalars *sc, cudaStream_t st);
 void launch_spmv(int d, const double *H, const StructDev &s, int nf, double lambda, const double *p, double *q1,
                  double *T, double *partials, DevScalars *sc, int pcg_mode, cudaStream_t st);
 void launch_finish_q(int d, const StructDev &s, int nf, const double *q1, const double *T, double *q, cudaStream_t st);
 void launch_pcg_init(int d, int nf, const double *b, const double *Minv, double *x, double *r, double *z, double *p,
-                     double *partials, DevScalars *sc, double tol, int max_iter, cudaStream_t st);
+                     double *partials, DevScalars *sc, double tol, int max_iter, int dist, cudaStream_t st);
 void launch_pcg_update(int d, const StructDev &s, int nf, const double *q1, const double *T, const double *Minv,
                        const double *p, double *x, double *r, double *z, double *partials, DevScalars *sc,
-                       cudaStream_t st);
+                       int dist, cudaStream_t st);
 void launch_pcg_pupdate(int d, int nf, const double *z, double *p, const DevScalars *sc, cudaStream_t st);
 void launch_scale(int n, const double *x, const double *b, double lambda, double *partials, DevScalars *sc,
                   cudaStream_t st);
@@ -86,8 +98,8 @@ int spmv_tile_blocks(int d);
 int spmv2_configure();
 int spmv3_tile_blocks(int d);
 void launch_spmv3(int d, const double *H, const StructDev &s, int nf, double lambda, const double *p, double *q1,
-                  double *T, double *partials, DevScalars *sc, int pcg_mode, int grid_cap, cudaStream_t st);
+                  double *T, double *partials, DevScalars *sc, int pcg_mode, int grid_cap, int dist, cudaStream_t st);
 void launch_spmv2(int d, const double *H, const StructDev &s, int nf, double lambda, const double *p, double *q1,
-                  double *T, double *partials, DevScalars *sc, int pcg_mode, cudaStream_t st);
+                  double *T, double *partials, DevScalars *sc, int pcg_mode, int dist, cudaStream_t st);
 
 }  // namespace s3o

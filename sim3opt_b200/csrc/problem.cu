@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <vector>
 
+#include "comm.h"
 #include "internal.h"
 #include "kernels.cuh"
 
@@ -70,6 +71,14 @@ struct s3o_problem {
     int32_t *d_rowptr = nullptr, *d_colidx = nullptr, *d_blk_row = nullptr, *d_blk_ebeg = nullptr, *d_blk_eend = nullptr;
     int32_t *d_colT_ptr = nullptr, *d_colT_blk = nullptr, *d_inc_ptr = nullptr, *d_inc_ent = nullptr, *d_e_blk = nullptr;
     int32_t *d_tile_row = nullptr;
+    // partitioned solve (one process per GPU, NCCL): s3o_set_comm
+    Comm comm;
+    bool dist = false;
+    PartitionPlan plan;
+    int user_ne = 0;                       // edges passed by the caller (plan.local_edges index into them)
+    int32_t *d_ghidx = nullptr, *d_send_idx = nullptr;
+    uint8_t *d_primary = nullptr;
+    double *d_sendbuf = nullptr, *d_xg = nullptr;
     int spmv_version = 3;       // 1: lane-group rows, 2: tiled thread-per-block, 3: v2 + TMA ring
     int spmv_grid_cap = 148 * 2;
     // linear system
@@ -113,6 +122,8 @@ GraphDev graph_view(const s3o_problem *p, int which) {
     g.meas = p->d_meas; g.info = p->has_info ? p->d_info : nullptr;
     g.robust_kind = p->robust_kind; g.robust_param = p->robust_param;
     g.math_corrected = p->math_mode == S3O_MATH_CORRECTED;
+    g.primary = p->dist ? p->d_primary : nullptr;
+    g.ghidx = p->dist ? p->d_ghidx : nullptr;
     return g;
 }
 
@@ -123,6 +134,7 @@ StructDev struct_view(const s3o_problem *p) {
     s.colT_ptr = p->d_colT_ptr; s.colT_blk = p->d_colT_blk;
     s.inc_ptr = p->d_inc_ptr; s.inc_ent = p->d_inc_ent; s.e_blk = p->d_e_blk;
     s.tile_row = p->d_tile_row; s.ntiles = (int)p->S.tile_row.size() - 1;
+    s.n_own = p->dist ? p->plan.n_own : p->S.nf;
     return s;
 }
 
@@ -131,6 +143,7 @@ void free_structure(s3o_problem *p) {
     dev_free(p->d_rowptr); dev_free(p->d_colidx); dev_free(p->d_blk_row); dev_free(p->d_blk_ebeg);
     dev_free(p->d_blk_eend); dev_free(p->d_colT_ptr); dev_free(p->d_colT_blk); dev_free(p->d_inc_ptr);
     dev_free(p->d_inc_ent); dev_free(p->d_e_blk); dev_free(p->d_tile_row);
+    dev_free(p->d_ghidx); dev_free(p->d_send_idx); dev_free(p->d_primary); dev_free(p->d_sendbuf); dev_free(p->d_xg);
     dev_free(p->d_H); dev_free(p->d_b); dev_free(p->d_x); dev_free(p->d_r); dev_free(p->d_z); dev_free(p->d_p);
     dev_free(p->d_q1); dev_free(p->d_T); dev_free(p->d_Minv); dev_free(p->d_scratch);
     p->built = false;
@@ -154,6 +167,20 @@ int check_launch(s3o_problem *p, int n) {
     return S3O_OK;
 }
 
+// rows this rank solves for (all free vertices on one GPU)
+inline int own_rows(const s3o_problem *p) { return p->dist ? p->plan.n_own : p->S.nf; }
+
+int allreduce_sum(s3o_problem *p, double *field, int count) {
+    if (!p->dist) return S3O_OK;
+    if (comm_allreduce_sum(p->comm, field, count, p->stream)) { set_error("%s", comm_last_error()); return S3O_ERR_NCCL; }
+    return S3O_OK;
+}
+int allreduce_max(s3o_problem *p, double *field, int count) {
+    if (!p->dist) return S3O_OK;
+    if (comm_allreduce_max(p->comm, field, count, p->stream)) { set_error("%s", comm_last_error()); return S3O_ERR_NCCL; }
+    return S3O_OK;
+}
+
 int sync_scalars(s3o_problem *p) {
     S3O_CUDA(cudaMemcpyAsync(p->h_sc, p->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, p->stream));
     S3O_CUDA(cudaStreamSynchronize(p->stream));
@@ -167,22 +194,24 @@ int ensure_built(s3o_problem *p) {
 }
 
 void run_spmv(s3o_problem *p, const StructDev &s, double lambda, const double *x, int pcg_mode) {
-    if (p->spmv_version == 1)
+    if (p->spmv_version == 1 && !p->dist)
         launch_spmv(p->d, p->d_H, s, p->S.nf, lambda, x, p->d_q1, p->d_T, p->d_partials, p->d_sc, pcg_mode, p->stream);
     else if (p->spmv_version == 3 && p->S.max_row_blocks <= p->S.tile_blocks)
-        launch_spmv3(p->d, p->d_H, s, p->S.nf, lambda, x, p->d_q1, p->d_T, p->d_partials, p->d_sc, pcg_mode,
-                     p->spmv_grid_cap, p->stream);
+        launch_spmv3(p->d, p->d_H, s, own_rows(p), lambda, x, p->d_q1, p->d_T, p->d_partials, p->d_sc, pcg_mode,
+                     p->spmv_grid_cap, p->dist, p->stream);
     else
-        launch_spmv2(p->d, p->d_H, s, p->S.nf, lambda, x, p->d_q1, p->d_T, p->d_partials, p->d_sc, pcg_mode, p->stream);
+        launch_spmv2(p->d, p->d_H, s, own_rows(p), lambda, x, p->d_q1, p->d_T, p->d_partials, p->d_sc, pcg_mode,
+                     p->dist, p->stream);
 }
 
 int do_chi2(s3o_problem *p, int which) {
     if (p->S.ne_act == 0) {
         S3O_CUDA(cudaMemsetAsync(&p->d_sc->chi2, 0, sizeof(double), p->stream));
-        return S3O_OK;
+        return allreduce_sum(p, &p->d_sc->chi2, 1);
     }
     launch_chi2(graph_view(p, which), p->d_partials, p->d_sc, p->stream);
-    return check_launch(p, 1);
+    int rc = check_launch(p, 1);
+    return rc ? rc : allreduce_sum(p, &p->d_sc->chi2, 1);
 }
 
 int do_linearize(s3o_problem *p) {
@@ -196,26 +225,53 @@ int do_linearize(s3o_problem *p) {
 // Solve (H + lambda I) x = b; leaves x in d_x.  Returns the PCG status in *status (1 converged,
 // 2 iteration cap, 3 breakdown) and the iteration count.
 int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel_res) {
-    const int nf = p->S.nf, d = p->d;
+    const int nf = own_rows(p), d = p->d;
+    const int dist = p->dist ? 1 : 0;
     const StructDev s = struct_view(p);
+    const PartitionPlan &P = p->plan;
+    auto halo = [&]() -> int {     // bring the ghost entries of p up to date before the product
+        if (!dist) return S3O_OK;
+        launch_pack_rows(d, p->d_p, p->d_send_idx, (int)P.send_idx.size(), p->d_sendbuf, p->d_sc, p->stream);
+        p->stats.kernel_launches += 1;
+        if (comm_halo(p->comm, p->d_sendbuf, P.send_off.data(), P.send_count.data(), p->d_p + (size_t)P.n_own * d,
+                      P.recv_off.data(), P.recv_count.data(), d, p->stream)) {
+            set_error("%s", comm_last_error());
+            return S3O_ERR_NCCL;
+        }
+        return S3O_OK;
+    };
     launch_precond(d, p->d_H, p->d_rowptr, nf, lambda, p->d_Minv, p->d_sc, p->stream);
     launch_pcg_init(d, nf, p->d_b, p->d_Minv, p->d_x, p->d_r, p->d_z, p->d_p, p->d_partials, p->d_sc, p->pcg_tol,
-                    p->pcg_max_iter, p->stream);
+                    p->pcg_max_iter, dist, p->stream);
     int rc = check_launch(p, 2);
     if (rc) return rc;
+    if (dist) {
+        if ((rc = allreduce_sum(p, &p->d_sc->rz_new, 2))) return rc;
+        launch_pcg_fin_init(p->d_sc, p->pcg_tol, p->pcg_max_iter, p->stream);
+        p->stats.kernel_launches += 1;
+    }
     int batch = 8, launched = 0;
     for (;;) {
         for (int k = 0; k < batch; ++k) {
             const bool sample = ((launched + k) & 15) == 7 && p->spmv_ev_used < s3o_problem::kSpmvEvents;
+            if ((rc = halo())) return rc;
             if (sample) cudaEventRecord(p->spmv_ev[2 * p->spmv_ev_used], p->stream);
             run_spmv(p, s, lambda, p->d_p, 1);
             if (sample) cudaEventRecord(p->spmv_ev[2 * p->spmv_ev_used++ + 1], p->stream);
+            if (dist) {
+                if ((rc = allreduce_sum(p, &p->d_sc->pq, 1))) return rc;
+                launch_pcg_fin_spmv(p->d_sc, p->stream);
+            }
             launch_pcg_update(d, s, nf, p->d_q1, p->d_T, p->d_Minv, p->d_p, p->d_x, p->d_r, p->d_z, p->d_partials,
-                              p->d_sc, p->stream);
+                              p->d_sc, dist, p->stream);
+            if (dist) {
+                if ((rc = allreduce_sum(p, &p->d_sc->rz_new, 2))) return rc;
+                launch_pcg_fin_update(p->d_sc, p->stream);
+            }
             launch_pcg_pupdate(d, nf, p->d_z, p->d_p, p->d_sc, p->stream);
         }
         launched += batch;
-        rc = check_launch(p, 3 * batch);
+        rc = check_launch(p, (dist ? 5 : 3) * batch);
         if (rc) return rc;
         rc = sync_scalars(p);
         if (rc) return rc;
@@ -303,12 +359,32 @@ int s3o_destroy(s3o_problem *p) {
     dev_free(p->d_meas_aos); dev_free(p->d_info_aos);
     dev_free(p->d_est[0]); dev_free(p->d_est[1]); dev_free(p->d_aux);
     dev_free(p->d_sc); dev_free(p->d_partials);
+    comm_destroy(p->comm);
     if (p->h_sc) cudaFreeHost(p->h_sc);
     for (auto &ev : p->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : p->spmv_ev) if (ev) cudaEventDestroy(ev);
     dev_free(p->d_est_snap);
     if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
     delete p;
+    return S3O_OK;
+}
+
+int s3o_comm_unique_id(char *id128) {
+    if (!id128) return S3O_ERR_INVALID;
+    if (comm_unique_id(id128)) { set_error("%s", comm_last_error()); return S3O_ERR_NCCL; }
+    return S3O_OK;
+}
+
+int s3o_set_comm(s3o_problem *p, int rank, int world, const char *id128) {
+    if (!p || world < 1 || rank < 0 || rank >= world || (world > 1 && !id128)) { set_error("s3o_set_comm: bad arguments"); return S3O_ERR_INVALID; }
+    if (p->kind != S3O_KIND_SIM3 && world > 1) { /* every kind works; kept general */ }
+    cudaSetDevice(p->device);
+    free_structure(p);
+    comm_destroy(p->comm);
+    p->dist = false;
+    if (world == 1) return S3O_OK;
+    if (comm_init(p->comm, rank, world, id128)) { set_error("%s", comm_last_error()); return S3O_ERR_NCCL; }
+    p->dist = true;
     return S3O_OK;
 }
 
@@ -399,10 +475,32 @@ int s3o_set_edges(s3o_problem *p, int n, const int32_t *v0, const int32_t *v1, c
     cudaSetDevice(p->device);
     free_structure(p);
     dev_free(p->d_meas_aos); dev_free(p->d_info_aos);
-    p->ne = n;
-    p->v0.assign(v0, v0 + n);
-    p->v1.assign(v1, v1 + n);
+    p->user_ne = n;
     p->has_info = info != nullptr;
+    std::vector<double> meas_loc, info_loc;
+    if (p->dist) {
+        // keep only the edges that touch a vertex this rank owns (cut edges live on both sides)
+        build_partition_plan(p->nv, p->fixed.data(), n, v0, v1, p->comm.rank, p->comm.world, p->plan);
+        const PartitionPlan &P = p->plan;
+        const int nl = (int)P.local_edges.size();
+        const int ed = p->est_dim, dd = p->d * p->d;
+        p->v0.resize(nl); p->v1.resize(nl);
+        meas_loc.resize((size_t)nl * ed);
+        if (info) info_loc.resize((size_t)nl * dd);
+        for (int t = 0; t < nl; ++t) {
+            const size_t k = (size_t)P.local_edges[t];
+            p->v0[t] = v0[k]; p->v1[t] = v1[k];
+            memcpy(&meas_loc[(size_t)t * ed], meas + k * ed, sizeof(double) * ed);
+            if (info) memcpy(&info_loc[(size_t)t * dd], info + k * dd, sizeof(double) * dd);
+        }
+        n = nl;
+        meas = meas_loc.data();
+        if (info) info = info_loc.data();
+    } else {
+        p->v0.assign(v0, v0 + n);
+        p->v1.assign(v1, v1 + n);
+    }
+    p->ne = n;
     int rc;
     const size_t mcount = (size_t)n * p->est_dim, icount = (size_t)n * p->d * p->d;
     if ((rc = dev_alloc(&p->d_meas_aos, mcount))) return rc;
@@ -414,7 +512,7 @@ int s3o_set_edges(s3o_problem *p, int n, const int32_t *v0, const int32_t *v1, c
         p->stats.h2d_bytes += (int64_t)(icount * sizeof(double));
     }
     S3O_CUDA(cudaStreamSynchronize(p->stream));
-    p->stats.n_edges = n;
+    p->stats.n_edges = p->user_ne;
     return S3O_OK;
 }
 
@@ -465,7 +563,12 @@ int s3o_build_structure(s3o_problem *p, int *n_free, int *n_blocks) {
         if (p->ne > 0 && !p->d_meas_aos) { set_error("s3o_build_structure: edges were consumed; call s3o_set_edges again"); return S3O_ERR_INVALID; }
         free_structure(p);
         HostStructure &S = p->S;
-        build_structure_host(p->nv, p->fixed.data(), p->ne, p->v0.data(), p->v1.data(), S);
+        if (p->dist)
+            build_structure_from_hidx(p->nv, p->plan.lhidx.data(), p->plan.n_own + p->plan.n_ghost, p->ne,
+                                      p->v0.data(), p->v1.data(), S);
+        else
+            build_structure_host(p->nv, p->fixed.data(), p->ne, p->v0.data(), p->v1.data(), S);
+        const int rows_own = p->dist ? p->plan.n_own : S.nf;
         p->ne_pad = pad32(S.ne_act);
         int rc = 0;
         std::vector<int32_t> blk_row(S.nb);
@@ -486,14 +589,25 @@ int s3o_build_structure(s3o_problem *p, int *n_free, int *n_blocks) {
         rc = rc ? rc : upload(p, &p->d_inc_ent, S.inc_ent);
         rc = rc ? rc : upload(p, &p->d_e_blk, S.e_blk);
         S.max_row_blocks = 0;
-        for (int r = 0; r < S.nf; ++r) S.max_row_blocks = std::max(S.max_row_blocks, S.rowptr[r + 1] - S.rowptr[r]);
+        for (int r = 0; r < rows_own; ++r) S.max_row_blocks = std::max(S.max_row_blocks, S.rowptr[r + 1] - S.rowptr[r]);
         S.tile_blocks = p->spmv_version == 3 ? spmv3_tile_blocks(p->d) : spmv_tile_blocks(p->d);
-        build_tiles(S.rowptr, S.nf, S.tile_blocks, S.tile_row);
+        build_tiles(S.rowptr, rows_own, S.tile_blocks, S.tile_row);
+        if (p->dist) {
+            const PartitionPlan &P = p->plan;
+            std::vector<uint8_t> prim(S.ne_act);
+            for (int t = 0; t < S.ne_act; ++t) prim[t] = P.primary[S.perm[t]];
+            rc = rc ? rc : upload(p, &p->d_primary, prim);
+            rc = rc ? rc : upload(p, &p->d_ghidx, P.ghidx);
+            rc = rc ? rc : upload(p, &p->d_send_idx, P.send_idx);
+            rc = rc ? rc : dev_alloc(&p->d_sendbuf, P.send_idx.size() * p->d);
+            rc = rc ? rc : dev_alloc(&p->d_xg, (size_t)P.world * P.seg * p->d);
+        }
         rc = rc ? rc : upload(p, &p->d_tile_row, S.tile_row);
         rc = rc ? rc : upload(p, &d_perm, S.perm);
         rc = rc ? rc : dev_alloc(&p->d_meas, (size_t)p->ne_pad * p->est_dim);
         if (p->has_info) rc = rc ? rc : dev_alloc(&p->d_info, (size_t)p->ne_pad * p->ninfo);
-        const size_t nfd = (size_t)S.nf * p->d, dd = (size_t)p->d * p->d;
+        // vectors are sized for owned + ghost rows; x also serves as the all-gather send buffer (seg rows)
+        const size_t nfd = (size_t)std::max(S.nf, p->dist ? p->plan.seg : 0) * p->d, dd = (size_t)p->d * p->d;
         rc = rc ? rc : dev_alloc(&p->d_H, (size_t)S.nb * dd + 2);   // +16 B: the TMA tile copy rounds its size up
         rc = rc ? rc : dev_alloc(&p->d_b, nfd);
         rc = rc ? rc : dev_alloc(&p->d_x, nfd);
@@ -548,6 +662,24 @@ int s3o_host_structure(int n_vertices, const uint8_t *fixed, int n_edges, const 
     return S3O_OK;
 }
 
+int s3o_host_partition(int n_vertices, const uint8_t *fixed, int n_edges, const int32_t *v0, const int32_t *v1,
+                       int rank, int world, int32_t *n_own, int32_t *n_ghost, int32_t *n_local_edges,
+                       int32_t *n_primary, int32_t *ghosts, int32_t *send_count, int32_t *recv_count,
+                       int32_t *send_idx_global) {
+    if (n_vertices < 0 || n_edges < 0 || world < 1 || rank < 0 || rank >= world) { set_error("s3o_host_partition: bad arguments"); return S3O_ERR_INVALID; }
+    PartitionPlan P;
+    build_partition_plan(n_vertices, fixed, n_edges, v0, v1, rank, world, P);
+    if (n_own) *n_own = P.n_own;
+    if (n_ghost) *n_ghost = P.n_ghost;
+    if (n_local_edges) *n_local_edges = (int32_t)P.local_edges.size();
+    if (n_primary) { int c = 0; for (uint8_t f : P.primary) c += f; *n_primary = c; }
+    if (ghosts) memcpy(ghosts, P.ghosts.data(), sizeof(int32_t) * P.ghosts.size());
+    if (send_count) memcpy(send_count, P.send_count.data(), sizeof(int32_t) * world);
+    if (recv_count) memcpy(recv_count, P.recv_count.data(), sizeof(int32_t) * world);
+    if (send_idx_global) for (size_t k = 0; k < P.send_idx.size(); ++k) send_idx_global[k] = P.send_idx[k] + P.own_lo;
+    return S3O_OK;
+}
+
 int s3o_get_structure(s3o_problem *p, int32_t *colptr, int32_t *rowidx) {
     if (!p || !p->built) { set_error("s3o_get_structure: structure not built"); return S3O_ERR_INVALID; }
     if (colptr) memcpy(colptr, p->S.ccs_colptr.data(), sizeof(int32_t) * (p->S.nf + 1));
@@ -588,8 +720,12 @@ int s3o_edge_errors(s3o_problem *p, double *err) {
     if (e != cudaSuccess) { set_error("s3o_edge_errors: %s", cudaGetErrorString(e)); return S3O_ERR_CUDA; }
     p->stats.kernel_launches += 1;
     p->stats.d2h_bytes += (int64_t)(tmp.size() * sizeof(double));
-    memset(err, 0, sizeof(double) * (size_t)p->ne * d);
-    for (int t = 0; t < na; ++t) memcpy(err + (size_t)p->S.perm[t] * d, tmp.data() + (size_t)t * d, sizeof(double) * d);
+    // caller's edge order; in the partitioned solve only the edges this rank evaluates are filled
+    memset(err, 0, sizeof(double) * (size_t)(p->dist ? p->user_ne : p->ne) * d);
+    for (int t = 0; t < na; ++t) {
+        const size_t user = p->dist ? (size_t)p->plan.local_edges[p->S.perm[t]] : (size_t)p->S.perm[t];
+        memcpy(err + user * d, tmp.data() + (size_t)t * d, sizeof(double) * d);
+    }
     return S3O_OK;
 }
 
@@ -626,9 +762,10 @@ int s3o_get_hessian(s3o_problem *p, double *blocks, double *b) {
 int s3o_max_diag(s3o_problem *p, double *max_diag) {
     if (!p || !p->built || !p->linearized || !max_diag) { set_error("s3o_max_diag: call s3o_linearize first"); return S3O_ERR_INVALID; }
     cudaSetDevice(p->device);
-    launch_maxdiag(p->d, p->d_H, p->d_rowptr, p->S.nf, p->d_partials, p->d_sc, p->stream);
+    launch_maxdiag(p->d, p->d_H, p->d_rowptr, own_rows(p), p->d_partials, p->d_sc, p->stream);
     int rc = check_launch(p, 1);
     if (rc) return rc;
+    if ((rc = allreduce_max(p, &p->d_sc->maxdiag, 1))) return rc;
     if ((rc = sync_scalars(p))) return rc;
     *max_diag = p->h_sc->maxdiag;
     return S3O_OK;
@@ -687,8 +824,8 @@ int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterat
     int rc = ensure_built(p);
     if (rc) return rc;
     if (iterations) *iterations = -1;
-    if (p->S.nf == 0) { set_error("s3o_optimize: 0 vertices to optimize"); return S3O_ERR_INVALID; }
-    const int nf = p->S.nf, d = p->d;
+    if (p->S.nf == 0 || (p->dist && p->plan.nf_global == 0)) { set_error("s3o_optimize: 0 vertices to optimize"); return S3O_ERR_INVALID; }
+    const int nf = own_rows(p), d = p->d;
     const bool resume = p->lm_resume != 0 && p->lm_valid;
     double lambda = resume ? p->lm_lambda : 0, ni = resume ? p->lm_ni : 2, currentChi = resume ? p->lm_chi : 0;
     int done = 0;
@@ -705,6 +842,7 @@ int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterat
         if (it == 0 && !resume) {
             launch_maxdiag(d, p->d_H, p->d_rowptr, nf, p->d_partials, p->d_sc, p->stream);
             if ((rc = check_launch(p, 1))) return rc;
+            if ((rc = allreduce_max(p, &p->d_sc->maxdiag, 1))) return rc;
             if ((rc = sync_scalars(p))) return rc;
             currentChi = p->h_sc->chi2;
             lambda = p->user_lambda > 0 ? p->user_lambda : p->tau * p->h_sc->maxdiag;
@@ -720,9 +858,18 @@ int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterat
             pcg_total += iters;
             cudaEventRecord(p->ev[4], p->stream);
             const int trial = p->cur ^ 1;
-            launch_retract(graph_view(p, p->cur), p->d_x, p->d_est[trial], p->stream);
+            const double *xfull = p->d_x;
+            if (p->dist) {   // every rank retracts all vertices from the gathered step
+                if (comm_allgather(p->comm, p->d_x, p->d_xg, (size_t)p->plan.seg * d, p->stream)) {
+                    set_error("%s", comm_last_error());
+                    return S3O_ERR_NCCL;
+                }
+                xfull = p->d_xg;
+            }
+            launch_retract(graph_view(p, p->cur), xfull, p->d_est[trial], p->stream);
             launch_scale(nf * d, p->d_x, p->d_b, lambda, p->d_partials, p->d_sc, p->stream);
             if ((rc = check_launch(p, 2))) return rc;
+            if ((rc = allreduce_sum(p, &p->d_sc->scale, 1))) return rc;
             if ((rc = do_chi2(p, trial))) return rc;
             cudaEventRecord(p->ev[5], p->stream);
             if ((rc = sync_scalars(p))) return rc;

@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "kernels.cuh"
+
 namespace s3o {
 
 template <int NT>
@@ -57,6 +59,30 @@ __device__ __forceinline__ double sum_partials(const double *partials, int n, do
     return block_sum<NT>(v, sh);
 }
 
+
+// ---- PCG scalar bookkeeping (run by the last CTA on one GPU, or by a 1-thread kernel after the
+// NCCL all-reduce in the partitioned solve) ----------------------------------------------------
+__device__ __forceinline__ void fin_init(DevScalars *sc, double tol, int max_iter) {
+    sc->rz = sc->rz_new;
+    sc->rr0 = sc->rr;
+    sc->tol2 = tol * tol;
+    sc->iters = 0; sc->max_iter = max_iter; sc->alpha = 0; sc->beta = 0; sc->pq = 0;
+    sc->done = (sc->rr == 0.0 || !(sc->rz > 0)) ? 1 : 0;
+}
+__device__ __forceinline__ void fin_spmv(DevScalars *sc) {
+    const double pq = sc->pq;
+    if (!(pq > 0) || !isfinite(pq)) { sc->done = 3; sc->alpha = 0; }
+    else sc->alpha = sc->rz / pq;
+}
+__device__ __forceinline__ void fin_update(DevScalars *sc) {
+    const double rz = sc->rz_new;
+    sc->beta = rz / sc->rz;
+    sc->rz = rz;
+    sc->iters += 1;
+    if (!(sc->rr > sc->tol2 * sc->rr0)) sc->done = 1;            // converged (also catches NaN)
+    else if (sc->iters >= sc->max_iter) sc->done = 2;
+    else if (!(rz > 0)) sc->done = 3;
+}
 
 template <int D> struct GroupLanes { static constexpr int value = D > 4 ? 8 : (D > 2 ? 4 : (D > 1 ? 2 : 1)); };
 

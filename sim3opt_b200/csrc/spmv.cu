@@ -28,18 +28,19 @@ template <> struct Spmv2Cfg<4> { static constexpr int NT = 256, TB = 256; };
 template <> struct Spmv2Cfg<1> { static constexpr int NT = 256, TB = 256; };
 
 template <int D, int TB>
-constexpr size_t spmv2_smem_bytes() { return sizeof(double) * (size_t)(TB * D * D + 2 * TB * D); }
+constexpr size_t spmv2_smem_bytes() { return sizeof(double) * (size_t)(TB * D * D + 2 * TB * D + TB); }
 
 template <int D, int NT, int TB>
 __global__ void __launch_bounds__(NT) spmv2_kernel(const double *__restrict__ H, StructDev s, int nf, double lambda,
                                                    const double *__restrict__ p, double *__restrict__ q1,
                                                    double *__restrict__ T, double *__restrict__ partials,
-                                                   DevScalars *sc, int pcg_mode) {
+                                                   DevScalars *sc, int pcg_mode, int dist) {
     constexpr int DD = D * D;
     extern __shared__ double smem[];
     double *tile = smem;              // [TB*DD]
     double *ys = tile + TB * DD;      // [TB*D] row parts
     double *ts = ys + TB * D;         // [TB*D] column parts
+    double *wt = ts + TB * D;         // [TB] weight of a block's row part in p.q (1: diagonal or ghost column, 2: owned off-diagonal)
     __shared__ double sh[32];
     if (pcg_mode && sc->done) return;
     const int t = threadIdx.x;
@@ -71,6 +72,8 @@ __global__ void __launch_bounds__(NT) spmv2_kernel(const double *__restrict__ H,
             __syncthreads();
             for (int kl = t; kl < cnt; kl += NT) {
                 const double *Hs = tile + kl * DD;
+                const bool ghost = j >= s.n_own;     // partitioned solve: the column belongs to another rank
+                wt[kl] = (j == i || ghost) ? 1.0 : 2.0;
                 if (j == i) {
 #pragma unroll
                     for (int r = 0; r < D; ++r) {
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(NT) spmv2_kernel(const double *__restrict__ H,
 #pragma unroll
                 for (int c = 0; c < D; ++c) {
                     ys[kl * D + c] = acc[c];
-                    ts[kl * D + c] = tt[c];
+                    ts[kl * D + c] = ghost ? 0.0 : tt[c];
                 }
             }
             __syncthreads();
@@ -110,19 +113,24 @@ __global__ void __launch_bounds__(NT) spmv2_kernel(const double *__restrict__ H,
                     const int rl = w / D, c = w - rl * D;
                     const int row = row0 + rl;
                     const int a = s.rowptr[row] - sub, e = s.rowptr[row + 1] - sub;
-                    const double y1 = ys[a * D + c];
-                    double y2 = 0;
-                    for (int kl = a + 1; kl < e; ++kl) y2 += ys[kl * D + c];
-                    q1[(size_t)row * D + c] = y1 + y2;
-                    local += p[(size_t)row * D + c] * (y1 + 2.0 * y2);
+                    double y = 0, yw = 0;
+                    for (int kl = a; kl < e; ++kl) {
+                        const double v = ys[kl * D + c];
+                        y += v;
+                        yw += wt[kl] * v;
+                    }
+                    q1[(size_t)row * D + c] = y;
+                    local += p[(size_t)row * D + c] * yw;
                 }
             } else if (t < D) {                         // hub row: exactly one row in this tile
-                int kl = 0;
-                if (sub == kbeg) { hub1 = ys[t]; kl = 1; }
-                for (; kl < cnt; ++kl) hub2 += ys[kl * D + t];
+                for (int kl = 0; kl < cnt; ++kl) {
+                    const double v = ys[kl * D + t];
+                    hub1 += v;
+                    hub2 += wt[kl] * v;
+                }
                 if (sub + cnt >= kend) {
-                    q1[(size_t)row0 * D + t] = hub1 + hub2;
-                    local += p[(size_t)row0 * D + t] * (hub1 + 2.0 * hub2);
+                    q1[(size_t)row0 * D + t] = hub1;
+                    local += p[(size_t)row0 * D + t] * hub2;
                 }
             }
             __syncthreads();
@@ -135,8 +143,7 @@ __global__ void __launch_bounds__(NT) spmv2_kernel(const double *__restrict__ H,
         const double pq = sum_partials<NT>(partials, gridDim.x, sh);
         if (threadIdx.x == 0) {
             sc->pq = pq;
-            if (!(pq > 0) || !isfinite(pq)) { sc->done = 3; sc->alpha = 0; }
-            else sc->alpha = sc->rz / pq;
+            if (!dist) fin_spmv(sc);
         }
     }
 }
@@ -182,20 +189,21 @@ template <> struct Spmv3Cfg<4> { static constexpr int NT = 256, TB = 256; };
 template <> struct Spmv3Cfg<1> { static constexpr int NT = 256, TB = 256; };
 
 template <int D, int TB>
-constexpr size_t spmv3_smem_bytes() { return sizeof(double) * (size_t)(2 * (TB * D * D + 2) + 2 * TB * D) + 16; }
+constexpr size_t spmv3_smem_bytes() { return sizeof(double) * (size_t)(2 * (TB * D * D + 2) + 2 * TB * D + TB) + 16; }
 
 template <int D, int NT, int TB>
 __global__ void __launch_bounds__(NT) spmv3_kernel(const double *__restrict__ H, StructDev s, int nf, double lambda,
                                                    const double *__restrict__ p, double *__restrict__ q1,
                                                    double *__restrict__ T, double *__restrict__ partials,
-                                                   DevScalars *sc, int pcg_mode) {
+                                                   DevScalars *sc, int pcg_mode, int dist) {
     constexpr int DD = D * D;
     constexpr int BUF = TB * DD + 2;          // doubles per ring slot (tile + alignment slack), even
     extern __shared__ __align__(16) double smem[];
     double *ring = smem;                      // [2][BUF]
     double *ys = ring + 2 * BUF;              // [TB*D]
     double *ts = ys + TB * D;                 // [TB*D]
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(ts + TB * D);   // [2]
+    double *wt = ts + TB * D;                 // [TB] p.q weight of each block's row part
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(wt + TB);       // [2]
     __shared__ double sh[32];
     if (pcg_mode && sc->done) return;
     const int t = threadIdx.x;
@@ -241,6 +249,8 @@ __global__ void __launch_bounds__(NT) spmv3_kernel(const double *__restrict__ H,
         if (t < cnt) {
             const double *Hs = ring + slot * BUF + shift + t * DD;
             double acc[D], tt[D];
+            const bool ghost = j >= s.n_own;          // partitioned solve: column owned by another rank
+            wt[t] = (j == i || ghost) ? 1.0 : 2.0;
             if (j == i) {
 #pragma unroll
                 for (int r = 0; r < D; ++r) {
@@ -268,7 +278,7 @@ __global__ void __launch_bounds__(NT) spmv3_kernel(const double *__restrict__ H,
 #pragma unroll
             for (int c = 0; c < D; ++c) {
                 ys[t * D + c] = acc[c];
-                ts[t * D + c] = tt[c];
+                ts[t * D + c] = ghost ? 0.0 : tt[c];
             }
         }
         __syncthreads();
@@ -278,11 +288,14 @@ __global__ void __launch_bounds__(NT) spmv3_kernel(const double *__restrict__ H,
             const int rl = w / D, c = w - rl * D;
             const int row = row0 + rl;
             const int a = s.rowptr[row] - kbeg, e = s.rowptr[row + 1] - kbeg;
-            const double y1 = ys[a * D + c];
-            double y2 = 0;
-            for (int kl = a + 1; kl < e; ++kl) y2 += ys[kl * D + c];
-            q1[(size_t)row * D + c] = y1 + y2;
-            local += p[(size_t)row * D + c] * (y1 + 2.0 * y2);
+            double y = 0, yw = 0;
+            for (int kl = a; kl < e; ++kl) {
+                const double v = ys[kl * D + c];
+                y += v;
+                yw += wt[kl] * v;
+            }
+            q1[(size_t)row * D + c] = y;
+            local += p[(size_t)row * D + c] * yw;
         }
         __syncthreads();
     }
@@ -293,8 +306,7 @@ __global__ void __launch_bounds__(NT) spmv3_kernel(const double *__restrict__ H,
         const double pq = sum_partials<NT>(partials, gridDim.x, sh);
         if (threadIdx.x == 0) {
             sc->pq = pq;
-            if (!(pq > 0) || !isfinite(pq)) { sc->done = 3; sc->alpha = 0; }
-            else sc->alpha = sc->rz / pq;
+            if (!dist) fin_spmv(sc);
         }
     }
 }
@@ -302,12 +314,12 @@ __global__ void __launch_bounds__(NT) spmv3_kernel(const double *__restrict__ H,
 int spmv3_tile_blocks(int d) { return d == 7 ? Spmv3Cfg<7>::TB : 256; }
 
 void launch_spmv3(int d, const double *H, const StructDev &s, int nf, double lambda, const double *p, double *q1,
-                  double *T, double *partials, DevScalars *sc, int pcg_mode, int grid_cap, cudaStream_t st) {
+                  double *T, double *partials, DevScalars *sc, int pcg_mode, int grid_cap, int dist, cudaStream_t st) {
     if (nf == 0 || s.ntiles == 0) return;
     const int grid = s.ntiles < grid_cap ? s.ntiles : grid_cap;
 #define S3O_SPMV3(D)                                                                                              \
     spmv3_kernel<D, Spmv3Cfg<D>::NT, Spmv3Cfg<D>::TB><<<grid, Spmv3Cfg<D>::NT, spmv3_smem_bytes<D, Spmv3Cfg<D>::TB>(), st>>>( \
-        H, s, nf, lambda, p, q1, T, partials, sc, pcg_mode);
+        H, s, nf, lambda, p, q1, T, partials, sc, pcg_mode, dist);
     switch (d) {
     case 7: S3O_SPMV3(7) break;
     case 4: S3O_SPMV3(4) break;
@@ -344,13 +356,13 @@ int spmv2_configure() {
 }
 
 void launch_spmv2(int d, const double *H, const StructDev &s, int nf, double lambda, const double *p, double *q1,
-                  double *T, double *partials, DevScalars *sc, int pcg_mode, cudaStream_t st) {
+                  double *T, double *partials, DevScalars *sc, int pcg_mode, int dist, cudaStream_t st) {
     if (nf == 0 || s.ntiles == 0) return;
     const int cap = 148 * 24;   // persistent-style grid: a multiple of the SM count, <= kMaxPartials
     const int grid = s.ntiles < cap ? s.ntiles : cap;
 #define S3O_SPMV2(D)                                                                                              \
     spmv2_kernel<D, Spmv2Cfg<D>::NT, Spmv2Cfg<D>::TB><<<grid, Spmv2Cfg<D>::NT, spmv2_smem_bytes<D, Spmv2Cfg<D>::TB>(), st>>>( \
-        H, s, nf, lambda, p, q1, T, partials, sc, pcg_mode);
+        H, s, nf, lambda, p, q1, T, partials, sc, pcg_mode, dist);
     switch (d) {
     case 7: S3O_SPMV2(7) break;
     case 4: S3O_SPMV2(4) break;

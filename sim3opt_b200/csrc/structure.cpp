@@ -16,16 +16,22 @@ namespace s3o {
 
 void build_structure_host(int nv, const uint8_t *fixed, int ne, const int32_t *v0, const int32_t *v1,
                           HostStructure &S) {
+    std::vector<int32_t> hidx(nv);
+    int nf = 0;
+    for (int v = 0; v < nv; ++v) hidx[v] = (fixed && fixed[v]) ? -1 : nf++;
+    build_structure_from_hidx(nv, hidx.data(), nf, ne, v0, v1, S);
+}
+
+void build_structure_from_hidx(int nv, const int32_t *hidx_in, int nfree, int ne, const int32_t *v0,
+                               const int32_t *v1, HostStructure &S) {
     S = HostStructure();
     S.nv = nv;
     S.ne = ne;
-    S.hidx.resize(nv);
-    S.free2v.clear();
-    for (int v = 0; v < nv; ++v) {
-        if (fixed && fixed[v]) S.hidx[v] = -1;
-        else { S.hidx[v] = (int32_t)S.free2v.size(); S.free2v.push_back(v); }
-    }
-    const int nf = S.nf = (int)S.free2v.size();
+    S.hidx.assign(hidx_in, hidx_in + nv);
+    S.free2v.assign(nfree, -1);
+    for (int v = 0; v < nv; ++v)
+        if (S.hidx[v] >= 0) S.free2v[S.hidx[v]] = v;
+    const int nf = S.nf = nfree;
 
     // sort active edges by (row=min, col=max) Hessian pair; one-free-end edges sort at (h,h).
     // Ties keep the caller's edge order, so the summation order inside a block is reproducible.
@@ -160,6 +166,63 @@ void build_tiles(const std::vector<int32_t> &rowptr, int nf, int cap, std::vecto
         }
         tile_row.push_back(r);
     }
+}
+
+void build_partition_plan(int nv, const uint8_t *fixed, int ne, const int32_t *v0, const int32_t *v1, int rank,
+                          int world, PartitionPlan &P) {
+    P = PartitionPlan();
+    P.rank = rank;
+    P.world = world;
+    P.ghidx.resize(nv);
+    int nf = 0;
+    for (int v = 0; v < nv; ++v) P.ghidx[v] = (fixed && fixed[v]) ? -1 : nf++;
+    P.nf_global = nf;
+    P.seg = world > 0 ? (nf + world - 1) / world : nf;
+    if (P.seg == 0) P.seg = 1;
+    P.own_lo = std::min(nf, rank * P.seg);
+    const int own_hi = std::min(nf, (rank + 1) * P.seg);
+    P.n_own = own_hi - P.own_lo;
+    auto owner = [&](int g) { return g / P.seg; };
+    // local edges, ghosts and what every peer needs from us
+    std::vector<std::vector<int32_t>> need_from_me(world);   // global Hessian indices I own that peer q needs
+    for (int k = 0; k < ne; ++k) {
+        const int ga = P.ghidx[v0[k]], gb = P.ghidx[v1[k]];
+        if (ga < 0 && gb < 0) continue;
+        const int oa = ga >= 0 ? owner(ga) : -1, ob = gb >= 0 ? owner(gb) : -1;
+        if (oa != rank && ob != rank) continue;
+        P.local_edges.push_back(k);
+        int gmin = ga < 0 ? gb : (gb < 0 ? ga : std::min(ga, gb));
+        P.primary.push_back(owner(gmin) == rank ? 1 : 0);
+        if (ga >= 0 && gb >= 0 && oa != ob) {
+            if (oa == rank) { P.ghosts.push_back(gb); need_from_me[ob].push_back(ga); }
+            else            { P.ghosts.push_back(ga); need_from_me[oa].push_back(gb); }
+        }
+    }
+    std::sort(P.ghosts.begin(), P.ghosts.end());
+    P.ghosts.erase(std::unique(P.ghosts.begin(), P.ghosts.end()), P.ghosts.end());
+    P.n_ghost = (int)P.ghosts.size();
+    P.recv_count.assign(world, 0);
+    P.recv_off.assign(world, 0);
+    for (int g : P.ghosts) P.recv_count[owner(g)]++;
+    for (int q = 1; q < world; ++q) P.recv_off[q] = P.recv_off[q - 1] + P.recv_count[q - 1];
+    P.send_count.assign(world, 0);
+    P.send_off.assign(world, 0);
+    P.send_idx.clear();
+    for (int q = 0; q < world; ++q) {
+        auto &lst = need_from_me[q];
+        std::sort(lst.begin(), lst.end());
+        lst.erase(std::unique(lst.begin(), lst.end()), lst.end());
+        P.send_off[q] = (int32_t)P.send_idx.size();
+        P.send_count[q] = (int32_t)lst.size();
+        for (int g : lst) P.send_idx.push_back(g - P.own_lo);
+    }
+    // local Hessian numbering: owned first (global order), then ghosts (global order)
+    P.lhidx.assign(nv, -1);
+    std::vector<int32_t> g2l(nf, -1);
+    for (int g = P.own_lo; g < own_hi; ++g) g2l[g] = g - P.own_lo;
+    for (int t = 0; t < P.n_ghost; ++t) g2l[P.ghosts[t]] = P.n_own + t;
+    for (int v = 0; v < nv; ++v)
+        if (P.ghidx[v] >= 0) P.lhidx[v] = g2l[P.ghidx[v]];
 }
 
 }  // namespace s3o

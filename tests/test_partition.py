@@ -1,0 +1,93 @@
+"""CPU tests of the multi-GPU host logic: the vertex-range partition plan.
+
+The N>1 path is exercised with a real world_size-2 gloo group: each rank computes its own plan through
+the C ABI, the ranks exchange their halo lists and check that they agree.
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def _plans(g, world):
+    from sim3opt_b200 import api
+    n = len(g["est"])
+    return [api.host_partition(n, g["fixed"], g["v0"], g["v1"], r, world) for r in range(world)]
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_partition_covers_graph(sphere_small, world):
+    g = sphere_small
+    plans = _plans(g, world)
+    nf = int((g["fixed"] == 0).sum())
+    assert sum(p["n_own"] for p in plans) == nf
+    # every active edge has exactly one primary rank
+    assert sum(p["n_primary"] for p in plans) == len(g["v0"])
+    seg = -(-nf // world)
+    for r, p in enumerate(plans):
+        assert p["n_own"] == max(0, min(nf, (r + 1) * seg) - min(nf, r * seg))
+        assert np.all(np.diff(p["ghosts"]) > 0)
+        assert np.all((p["ghosts"] // seg) != r)                      # a ghost is never owned
+        assert p["recv_count"].sum() == p["n_ghost"] and p["recv_count"][r] == 0
+    # what q receives from r is exactly what r sends to q, in the same order
+    for r in range(world):
+        off = np.concatenate([[0], np.cumsum(plans[r]["send_count"])])
+        for q in range(world):
+            sent = plans[r]["send_idx"][off[q]:off[q + 1]]
+            recv = plans[q]["ghosts"][(plans[q]["ghosts"] // seg) == r]
+            assert np.array_equal(sent, recv)
+    if world == 1:
+        assert plans[0]["n_ghost"] == 0 and plans[0]["n_local_edges"] == len(g["v0"])
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from sim3opt_b200 import api, synth
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = synth.sphere(n_laps=10, poses_per_lap=30, seed=3)
+        n = len(g["est"])
+        plan = api.host_partition(n, g["fixed"], g["v0"], g["v1"], rank, world)
+        # exchange ghost lists and send lists
+        objs = [None] * world
+        dist.all_gather_object(objs, (plan["ghosts"].tolist(), plan["send_idx"].tolist(), plan["send_count"].tolist(),
+                                      plan["n_own"], plan["n_primary"]))
+        nf = int((g["fixed"] == 0).sum())
+        seg = -(-nf // world)
+        ok = sum(o[3] for o in objs) == nf and sum(o[4] for o in objs) == len(g["v0"])
+        for r in range(world):
+            off = np.concatenate([[0], np.cumsum(objs[r][2])])
+            sent_to_me = objs[r][1][off[rank]:off[rank + 1]]
+            mine = [x for x in plan["ghosts"].tolist() if x // seg == r]
+            ok = ok and sent_to_me == mine
+        # the allreduce every PCG iteration relies on: a sum of per-rank partials
+        t = torch.tensor([float(plan["n_primary"])], dtype=torch.float64)
+        dist.all_reduce(t)
+        ok = ok and int(t.item()) == len(g["v0"])
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partition_world2_gloo():
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]

@@ -1,0 +1,73 @@
+"""Partitioned solve vs single-GPU solve of the same graph (run under torchrun, one rank per GPU).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tools/dist_check.py [laps] [poses_per_lap] [lm_iters]
+Prints "DIST_CHECK PASS" on rank 0 when chi2 histories agree to 1e-9 relative and the estimates to 1e-8.
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import sim3opt_b200 as s3
+from sim3opt_b200 import synth
+
+
+def main():
+    laps = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+    per = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+    iters = int(sys.argv[3]) if len(sys.argv) > 3 else 6
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    g = synth.sphere(laps, per, seed=11)
+    box = [s3.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+
+    def make(comm):
+        p = s3.Problem(s3.KIND_SIM3, device=local)
+        p.set_math_mode(s3.MATH_CORRECTED)
+        p.set_pcg(1e-12, 20000)
+        if comm:
+            p.set_comm(rank, world, box[0])
+        p.set_vertices(g["est"], g["fixed"])
+        p.set_edges(g["v0"], g["v1"], g["meas"], g["info"])
+        return p
+
+    pd = make(True)
+    chi0 = pd.chi2()
+    n, chi2, lam, hist = pd.optimize(iters)
+    vd = pd.vertices()
+    ok = True
+    if rank == 0:
+        ps = make(False)
+        chi0s = ps.chi2()
+        ns, chi2s, lams, hists = ps.optimize(iters)
+        vs = ps.vertices()
+        rel = np.abs(hist[:, 0] - hists[:, 0]) / hists[:, 0]
+        dv = np.abs(vd - vs).max()
+        ok = (abs(chi0 - chi0s) <= 1e-12 * chi0s and n == ns and rel.max() <= 1e-9 and dv <= 1e-8
+              and np.array_equal(hist[:, 2], hists[:, 2]))
+        print("chi2_0 dist %.12g single %.12g" % (chi0, chi0s))
+        print("chi2 history rel diff", rel)
+        print("pcg iters dist", hist[:, 4], "single", hists[:, 4])
+        print("max |vertex diff| %.3e" % dv)
+        print("DIST_CHECK", "PASS" if ok else "FAIL", "world", world)
+    # every rank holds the same estimates after the solve
+    t = torch.from_numpy(vd.copy()).cuda()
+    ref = t.clone()
+    dist.broadcast(ref, src=0)
+    same = bool((t == ref).all().item())
+    flags = torch.tensor([1.0 if same else 0.0], device="cuda")
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("ESTIMATES_IDENTICAL_ACROSS_RANKS", bool(flags.item() == 1.0))
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
