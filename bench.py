@@ -163,6 +163,10 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # libraries (NCCL's version banner, torchrun notices) must not pollute the one JSON line on stdout
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -283,8 +287,10 @@ def run_ours(args):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     n_off = nb - nf
     # B_spmv = 392 N_b + 4 N_b + 4 (N_f + 1) + 2*56 N_f   (each unique block once)
-    bytes_spmv = 392 * nb + 4 * nb + 4 * (nf + 1) + 2 * 56 * nf
-    roof = {"bound": "hbm", "kernel": "spmv_kernel<7,256,64>", "achieved": None, "peak": peak, "unit": "GB/s",
+    # (partitioned solve: the launch on one rank covers that rank's rows and blocks only)
+    nb_l, nf_l = (nb, nf) if world == 1 else (st["n_blocks"], -(-nf // world))
+    bytes_spmv = 392 * nb_l + 4 * nb_l + 4 * (nf_l + 1) + 2 * 56 * nf_l
+    roof = {"bound": "hbm", "kernel": "spmv3_kernel<7,128,112> (TMA ring)", "achieved": None, "peak": peak, "unit": "GB/s",
             "frac": None, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_spmv}
     if st["n_spmv_sampled"] > 0:
         avg_ms = st["ms_spmv_sampled"] / st["n_spmv_sampled"]
@@ -333,7 +339,9 @@ def run_ours(args):
         "solves_completed": len(drv.solves),
         "chi2_history_first_solve": drv.solves[0] if drv.solves else drv.cur,
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
