@@ -137,6 +137,15 @@ int s3o_solve(s3o_problem *p, double lambda, double *x, int *pcg_iters, double *
 int s3o_hessian_multiply(s3o_problem *p, double lambda, const double *x, double *y);
 int s3o_update(s3o_problem *p, const double *x);            /* oplus on every free vertex */
 
+/* Eigenvector of the smallest eigenvalue of H = J^T Omega J at the current estimates, by inverse
+ * iteration with the PCG solver (replaces the dense Eigen::JacobiSVD null-vector solve of the
+ * stepwise scale initialisation, kitti_surf.cpp:887-934: H of the 1-DoF scale graph with no fixed
+ * vertex is the Gram matrix of the reference's constraint matrix).  x: n_free*d, unit 2-norm, in
+ * Hessian-index order; lambda_min / lambda_max: smallest / largest eigenvalue estimates (squared
+ * singular values of J); stops when the eigenvalue estimate changes by less than tol relative. */
+int s3o_smallest_eigenvector(s3o_problem *p, int max_iter, double tol, double *x, double *lambda_min,
+                             double *lambda_max, int *iterations);
+
 /* ---- the hot call (replaces optimizer.optimize(n)) ------------------------------------- */
 /* hist (may be NULL): per LM iteration [chi2, lambda, trials, rho, pcg_iters]; returns via
  * out-params the number of iterations run (g2o's return value), final chi2 and lambda.

@@ -164,6 +164,14 @@ class Problem:
         x = _f64(x)
         self._check(self.L.s3o_update(self.h, _d(x)))
 
+    def smallest_eigenvector(self, max_iter=50, tol=1e-12):
+        """(x, lambda_min, lambda_max, iterations) of H at the current estimates (stepwise scale init)."""
+        self.build_structure()
+        x = np.zeros(self.num_free * self.d)
+        lmin, lmax, it = C.c_double(0), C.c_double(0), C.c_int(0)
+        self._check(self.L.s3o_smallest_eigenvector(self.h, max_iter, tol, _d(x), C.byref(lmin), C.byref(lmax), C.byref(it)))
+        return x, lmin.value, lmax.value, it.value
+
     # ---- the hot call ------------------------------------------------------------
     def optimize(self, max_iter, stop_rel_gain=0.0):
         hist = np.zeros((max(max_iter, 1), 5))

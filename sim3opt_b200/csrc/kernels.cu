@@ -965,6 +965,22 @@ void launch_pcg_pupdate(int d, int nf, const double *z, double *p, const DevScal
 
 int launches_per_pcg_iter() { return 3; }
 
+// small vector helpers of s3o_smallest_eigenvector
+__global__ void scale_vec_kernel(int n, const double *__restrict__ in, double s, double *__restrict__ out) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) out[t] = in[t] * s;
+}
+__global__ void fill_kernel(int n, double a, double b, double *__restrict__ out) {   // a, b, a, b, ...
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) out[t] = (t & 1) ? b : a;
+}
+void launch_scale_vec(int n, const double *in, double s, double *out, cudaStream_t st) {
+    scale_vec_kernel<<<reduce_grid(n, 256), 256, 0, st>>>(n, in, s, out);
+}
+void launch_fill_const(int n, double v, double *out, cudaStream_t st) { fill_kernel<<<reduce_grid(n, 256), 256, 0, st>>>(n, v, v, out); }
+void launch_fill_alternating(int n, double *out, cudaStream_t st) {
+    const double v = 1.0 / sqrt((double)(n > 0 ? n : 1));
+    fill_kernel<<<reduce_grid(n, 256), 256, 0, st>>>(n, v, -v, out);
+}
+
 __global__ void pcg_fin_init_kernel(DevScalars *sc, double tol, int max_iter) { fin_init(sc, tol, max_iter); }
 __global__ void pcg_fin_spmv_kernel(DevScalars *sc) { if (!sc->done) fin_spmv(sc); }
 __global__ void pcg_fin_update_kernel(DevScalars *sc) { if (!sc->done) fin_update(sc); }

@@ -93,6 +93,9 @@ void launch_pcg_pupdate(int d, int nf, const double *z, double *p, const DevScal
 void launch_scale(int n, const double *x, const double *b, double lambda, double *partials, DevScalars *sc,
                   cudaStream_t st);
 int launches_per_pcg_iter();
+void launch_scale_vec(int n, const double *in, double s, double *out, cudaStream_t st);
+void launch_fill_const(int n, double v, double *out, cudaStream_t st);
+void launch_fill_alternating(int n, double *out, cudaStream_t st);
 // tiled thread-per-block SpMV (spmv.cu)
 int spmv_tile_blocks(int d);
 int spmv2_configure();

@@ -931,6 +931,75 @@ int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterat
     return S3O_OK;
 }
 
+// Eigenvector of the smallest eigenvalue of H (the Gram matrix J^T Omega J at the current
+// estimates) by inverse iteration  y = (H + shift I)^-1 x,  x = y / |y|  with the PCG solver, all
+// vectors on the device.  This is the stepwise pipeline's scale initialisation
+// (kitti_surf.cpp:887-934: last right singular vector of the scale-constraint matrix, whose Gram
+// matrix is the Hessian of the 1-DoF scale graph with no vertex fixed).  lambda_max comes from a
+// short power iteration and only feeds the reference's conditioning warning.
+int s3o_smallest_eigenvector(s3o_problem *p, int max_iter, double tol, double *x, double *lambda_min,
+                             double *lambda_max, int *iterations) {
+    if (!p || !x) { set_error("s3o_smallest_eigenvector: bad arguments"); return S3O_ERR_INVALID; }
+    if (p->dist) { set_error("s3o_smallest_eigenvector: not available in the partitioned solve"); return S3O_ERR_UNSUPPORTED; }
+    cudaSetDevice(p->device);
+    int rc = ensure_built(p);
+    if (rc) return rc;
+    if (p->S.nf == 0) { set_error("s3o_smallest_eigenvector: 0 free vertices"); return S3O_ERR_INVALID; }
+    if ((rc = do_linearize(p))) return rc;
+    const int n = p->S.nf * p->d;
+    const StructDev s = struct_view(p);
+    launch_maxdiag(p->d, p->d_H, p->d_rowptr, p->S.nf, p->d_partials, p->d_sc, p->stream);
+    if ((rc = check_launch(p, 1)) || (rc = sync_scalars(p))) return rc;
+    const double maxdiag = p->h_sc->maxdiag;
+    auto dot = [&](const double *a, const double *b, double *out) -> int {   // sum a_j b_j
+        launch_scale(n, a, b, 0.0, p->d_partials, p->d_sc, p->stream);
+        int r = check_launch(p, 1);
+        if (r || (r = sync_scalars(p))) return r;
+        *out = p->h_sc->scale;
+        return S3O_OK;
+    };
+    // ---- largest eigenvalue: power iteration from an alternating-sign vector (d_r as x, d_z as y)
+    double lmax = 0;
+    launch_fill_alternating(n, p->d_r, p->stream);
+    for (int it = 0; it < 30; ++it) {
+        run_spmv(p, s, 0.0, p->d_r, 0);
+        launch_finish_q(p->d, s, p->S.nf, p->d_q1, p->d_T, p->d_z, p->stream);
+        if ((rc = check_launch(p, 2))) return rc;
+        double yy = 0, xy = 0;
+        if ((rc = dot(p->d_z, p->d_z, &yy)) || (rc = dot(p->d_z, p->d_r, &xy))) return rc;
+        if (!(yy > 0)) break;
+        lmax = xy;                                  // x normalised: Rayleigh quotient x^T H x
+        launch_scale_vec(n, p->d_z, 1.0 / std::sqrt(yy), p->d_r, p->stream);
+        p->stats.kernel_launches += 1;
+    }
+    // ---- smallest eigenvalue: inverse iteration (d_b holds the normalised iterate)
+    const double shift = 1e-13 * maxdiag;
+    launch_fill_const(n, 1.0 / std::sqrt((double)n), p->d_b, p->stream);
+    double theta = 0, theta_prev = -1;
+    int done = 0;
+    for (int it = 0; it < std::max(max_iter, 1); ++it) {
+        int status = 0;
+        if ((rc = do_solve(p, shift, &status, nullptr, nullptr))) return rc;
+        double yy = 0, xy = 0;
+        if ((rc = dot(p->d_x, p->d_x, &yy)) || (rc = dot(p->d_x, p->d_b, &xy))) return rc;
+        if (!(yy > 0) || !std::isfinite(yy)) { set_error("s3o_smallest_eigenvector: inverse iteration broke down"); return S3O_ERR_INVALID; }
+        theta = xy / yy - shift;
+        launch_scale_vec(n, p->d_x, 1.0 / std::sqrt(yy), p->d_b, p->stream);
+        p->stats.kernel_launches += 1;
+        done = it + 1;
+        if (it > 0 && std::fabs(theta - theta_prev) <= tol * std::fabs(theta)) break;
+        theta_prev = theta;
+    }
+    S3O_CUDA(cudaMemcpyAsync(x, p->d_b, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    S3O_CUDA(cudaStreamSynchronize(p->stream));
+    p->stats.d2h_bytes += (int64_t)n * 8;
+    p->linearized = false;                          // b was overwritten
+    if (lambda_min) *lambda_min = theta;
+    if (lambda_max) *lambda_max = lmax;
+    if (iterations) *iterations = done;
+    return S3O_OK;
+}
+
 int s3o_get_vertices(s3o_problem *p, double *est) {
     if (!p || !est || !p->d_est[0]) { set_error("s3o_get_vertices: no vertices"); return S3O_ERR_INVALID; }
     cudaSetDevice(p->device);
