@@ -30,7 +30,7 @@ struct Options {
     string mode, dataDir, outFile;
     bool oneConstraint = true, stepwise = true, numeric = false;
     int stages = 2, iters = 100, precision = 6;
-    double pcgTol = 1e-10;
+    double pcgTol = 1e-13;
     int pcgMaxIter = 100000;
 };
 

@@ -60,7 +60,7 @@ def test_direct_pipeline_matches_python_path(kitti_pgo, tmp_path, kitti_k1, kitt
     assert m, out
     assert int(m.group(2)) == 770 and int(m.group(3)) == (1657 if all_loops else 1540)
     gpu = make_gpu(g, jac=1)
-    gpu.set_pcg(1e-10, 100000)
+    gpu.set_pcg(1e-13, 100000)
     n, chi2, lam, hist = gpu.optimize(4)
     # same library, same graph (the C++ loaders and the Python loaders agree to round-off):
     # iteration 0 is stable, later iterations amplify the 1e-16 input differences
