@@ -126,14 +126,6 @@ int orc_set_edges(orc_problem *p, int n, const int *v0, const int *v1, const dou
     return 0;
 }
 
-int orc_set_ba(orc_problem *p, int n_cam, const double *cams, const unsigned char *cam_fixed, int n_pt,
-               const double *pts, int n_obs, const int *obs_pt, const int *obs_cam, const double *uv,
-               double info_scale, double focal, double cx, double cy) {
-    (void)p; (void)n_cam; (void)cams; (void)cam_fixed; (void)n_pt; (void)pts; (void)n_obs; (void)obs_pt;
-    (void)obs_cam; (void)uv; (void)info_scale; (void)focal; (void)cx; (void)cy;
-    return -1; /* BA lives in ba.c (orc_ba_*) */
-}
-
 void orc_set_robust(orc_problem *p, int kind, double param) { p->robust_kind = kind; p->robust_param = param; }
 void orc_set_jacobian_mode(orc_problem *p, int mode, double h) { p->jac_mode = mode; if (h > 0) p->jac_h = h; }
 void orc_set_lm(orc_problem *p, double tau, double user_lambda_init, int max_trials) {
@@ -454,7 +446,6 @@ void orc_update(orc_problem *p, const double *x) {
 }
 
 void orc_get_vertices(const orc_problem *p, double *est) { memcpy(est, p->est, sizeof(double) * (size_t)p->nv * p->est_dim); }
-void orc_get_points(const orc_problem *p, double *pts) { (void)p; (void)pts; }
 void orc_get_timing(const orc_problem *p, double t[4]) { memcpy(t, p->timing, sizeof p->timing); }
 
 /* ---- OptimizationAlgorithmLevenberg::solve inside SparseOptimizer::optimize -- */

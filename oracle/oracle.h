@@ -85,10 +85,6 @@ void orc_destroy(orc_problem *p);
 int orc_set_vertices(orc_problem *p, int n, const double *est, const unsigned char *fixed, const double *aux);
 /* meas is n x est_dim; info is n x d x d row-major or NULL (= identity) */
 int orc_set_edges(orc_problem *p, int n, const int *v0, const int *v1, const double *meas, const double *info);
-/* BA: cameras n_cam x 7 (SE3Quat), points n_pt x 3, obs: point idx, cam idx, uv */
-int orc_set_ba(orc_problem *p, int n_cam, const double *cams, const unsigned char *cam_fixed, int n_pt,
-               const double *pts, int n_obs, const int *obs_pt, const int *obs_cam, const double *uv,
-               double info_scale, double focal, double cx, double cy);
 void orc_set_robust(orc_problem *p, int kind, double param);
 void orc_set_jacobian_mode(orc_problem *p, int mode, double h);
 void orc_set_lm(orc_problem *p, double tau, double user_lambda_init, int max_trials);
@@ -115,13 +111,44 @@ int orc_solve(orc_problem *p, double lambda, double *x);
 /* vertices <- oplus(x) */
 void orc_update(orc_problem *p, const double *x);
 void orc_get_vertices(const orc_problem *p, double *est);
-void orc_get_points(const orc_problem *p, double *pts);
 
 /* g2o SparseOptimizer::optimize(max_iter) with OptimizationAlgorithmLevenberg.
  * hist (may be NULL): per iteration [chi2, lambda, trials, rho]; returns iterations done.
  * stop_rel_gain > 0 additionally stops when 0 <= (chi2_prev-chi2)/chi2 < stop_rel_gain. */
 int orc_optimize(orc_problem *p, int max_iter, double stop_rel_gain, double *hist, int hist_cap,
                  double *final_chi2, double *final_lambda);
+
+/* ---- bundle adjustment (ba.c; bal_example.cpp:44-243) --------------------
+ * cameras n_cam x 7 SE3Quat [qx qy qz qw tx ty tz] (world -> camera), points n_pt x 3,
+ * observations (camera index, point index, u, v), info n_obs x 3 packed [xx xy yy] or NULL (= I2).
+ * Hessian order: free cameras (6 each) then free points (3 each).  Hpl[k] = Jc^T O' Jp (6x3) per
+ * observation k (zero when either end is fixed). */
+typedef struct orc_ba orc_ba;
+orc_ba *orc_ba_create(void);
+void orc_ba_destroy(orc_ba *p);
+int orc_ba_set(orc_ba *p, int n_cam, const double *cams, const unsigned char *cam_fixed, int n_pt, const double *pts,
+               const unsigned char *pt_fixed, int n_obs, const int *obs_cam, const int *obs_pt, const double *uv,
+               const double *info, double focal, double cx, double cy);
+void orc_ba_set_robust(orc_ba *p, int kind, double param);
+void orc_ba_set_lm(orc_ba *p, double tau, double user_lambda_init, int max_trials);
+int orc_ba_build_structure(orc_ba *p);          /* returns the number of upper blocks of H_schur */
+int orc_ba_num_free_cameras(const orc_ba *p);
+int orc_ba_num_free_points(const orc_ba *p);
+int orc_ba_num_blocks(const orc_ba *p);
+void orc_ba_get_structure(const orc_ba *p, int *colptr, int *rowidx);   /* g2o-order upper block-CCS of H_schur */
+double orc_ba_chi2(orc_ba *p);
+void orc_ba_edge_errors(orc_ba *p, double *err /* n_obs x 2 */);
+void orc_ba_edge_jacobians(const orc_ba *p, int k, double Jp[6], double Jc[12]);
+void orc_ba_linearize(orc_ba *p);
+void orc_ba_get_system(const orc_ba *p, double *Hpp, double *Hll, double *Hpl, double *b);
+double orc_ba_max_diag(const orc_ba *p);
+int orc_ba_schur(orc_ba *p, double lambda, double *S /* nblocks x 36 */, double *bs /* 6 ncf */);
+int orc_ba_solve(orc_ba *p, double lambda, double *x /* 6 ncf + 3 npf */);
+void orc_ba_update(orc_ba *p, const double *x);
+void orc_ba_get_cameras(const orc_ba *p, double *cams);
+void orc_ba_get_points(const orc_ba *p, double *pts);
+int orc_ba_optimize(orc_ba *p, int max_iter, double stop_rel_gain, double *hist, int hist_cap, double *final_chi2,
+                    double *final_lambda);
 
 /* seconds spent in [linearize, solve, chi2/update] during the last orc_optimize */
 void orc_get_timing(const orc_problem *p, double t[4]);

@@ -80,6 +80,31 @@ def _declare(L):
     L.orc_sim3_edge_jac_numeric.argtypes = [_dp, _dp, _dp, C.c_double, _dp, _dp]
     L.orc_sim3_edge_jac_analytic.argtypes = [_dp] * 5
     L.orc_robustify.argtypes = [C.c_int, C.c_double, C.c_double, _dp]
+    # bundle adjustment (ba.c)
+    vp = C.c_void_p
+    L.orc_ba_create.restype = vp
+    L.orc_ba_destroy.argtypes = [vp]
+    L.orc_ba_set.argtypes = [vp, C.c_int, _dp, _up, C.c_int, _dp, _up, C.c_int, _ip, _ip, _dp, _dp,
+                             C.c_double, C.c_double, C.c_double]
+    L.orc_ba_set_robust.argtypes = [vp, C.c_int, C.c_double]
+    L.orc_ba_set_lm.argtypes = [vp, C.c_double, C.c_double, C.c_int]
+    for name in ("orc_ba_build_structure", "orc_ba_num_free_cameras", "orc_ba_num_free_points", "orc_ba_num_blocks",
+                 "orc_ba_linearize"):
+        getattr(L, name).argtypes = [vp]
+    L.orc_ba_get_structure.argtypes = [vp, _ip, _ip]
+    L.orc_ba_chi2.restype = C.c_double
+    L.orc_ba_chi2.argtypes = [vp]
+    L.orc_ba_edge_errors.argtypes = [vp, _dp]
+    L.orc_ba_edge_jacobians.argtypes = [vp, C.c_int, _dp, _dp]
+    L.orc_ba_get_system.argtypes = [vp, _dp, _dp, _dp, _dp]
+    L.orc_ba_max_diag.restype = C.c_double
+    L.orc_ba_max_diag.argtypes = [vp]
+    L.orc_ba_schur.argtypes = [vp, C.c_double, _dp, _dp]
+    L.orc_ba_solve.argtypes = [vp, C.c_double, _dp]
+    L.orc_ba_update.argtypes = [vp, _dp]
+    L.orc_ba_get_cameras.argtypes = [vp, _dp]
+    L.orc_ba_get_points.argtypes = [vp, _dp]
+    L.orc_ba_optimize.argtypes = [vp, C.c_int, C.c_double, _dp, C.c_int, _dp, _dp]
     L.orc_ptam_find_sigma_squared.restype = C.c_double
     L.orc_ptam_find_sigma_squared.argtypes = [C.c_int, _dp, C.c_int]
 
@@ -271,3 +296,101 @@ class Problem:
         t = np.zeros(4)
         self.L.orc_get_timing(self.h, _d(t))
         return t
+
+
+class BAProblem:
+    """Bundle-adjustment oracle (ba.c): cameras SE3Quat [q xyzw, t], points xyz, observations
+    (camera, point, u, v); Huber etc. through set_robust; LM with Schur complement + sparse LDLT."""
+
+    def __init__(self):
+        self.L = lib()
+        self.h = C.c_void_p(self.L.orc_ba_create())
+        self.nc = self.np_ = self.no = 0
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_ba_destroy(self.h)
+            self.h = None
+
+    def set(self, cams, pts, obs_cam, obs_pt, uv, focal, cx, cy, cam_fixed=None, pt_fixed=None, info=None):
+        cams = _f64(cams).reshape(-1, 7)
+        pts = _f64(pts).reshape(-1, 3)
+        oc = np.ascontiguousarray(obs_cam, np.int32)
+        op = np.ascontiguousarray(obs_pt, np.int32)
+        uv = _f64(uv).reshape(-1, 2)
+        self.nc, self.np_, self.no = len(cams), len(pts), len(oc)
+        cf = np.zeros(self.nc, np.uint8) if cam_fixed is None else np.ascontiguousarray(cam_fixed, np.uint8)
+        pf = np.zeros(self.np_, np.uint8) if pt_fixed is None else np.ascontiguousarray(pt_fixed, np.uint8)
+        infop = None
+        if info is not None:
+            info = _f64(info).reshape(self.no, 3)
+            infop = _d(info)
+        rc = self.L.orc_ba_set(self.h, self.nc, _d(cams), cf.ctypes.data_as(_up), self.np_, _d(pts),
+                               pf.ctypes.data_as(_up), self.no, oc.ctypes.data_as(_ip), op.ctypes.data_as(_ip), _d(uv),
+                               infop, float(focal), float(cx), float(cy))
+        if rc != 0:
+            raise ValueError("orc_ba_set: observation index out of range")
+
+    def set_robust(self, kind, param): self.L.orc_ba_set_robust(self.h, kind, float(param))
+    def set_lm(self, tau=0.0, lambda_init=0.0, max_trials=0): self.L.orc_ba_set_lm(self.h, tau, lambda_init, max_trials)
+
+    def build_structure(self):
+        nb = self.L.orc_ba_build_structure(self.h)
+        self.ncf = self.L.orc_ba_num_free_cameras(self.h)
+        self.npf = self.L.orc_ba_num_free_points(self.h)
+        colptr = np.zeros(self.ncf + 1, np.int32)
+        rowidx = np.zeros(max(nb, 1), np.int32)
+        self.L.orc_ba_get_structure(self.h, colptr.ctypes.data_as(_ip), rowidx.ctypes.data_as(_ip))
+        self.nb = nb
+        return colptr, rowidx[:nb]
+
+    def chi2(self): return self.L.orc_ba_chi2(self.h)
+
+    def edge_errors(self):
+        e = np.zeros((self.no, 2))
+        self.L.orc_ba_edge_errors(self.h, _d(e))
+        return e
+
+    def edge_jacobians(self, k):
+        Jp, Jc = np.zeros((2, 3)), np.zeros((2, 6))
+        self.L.orc_ba_edge_jacobians(self.h, int(k), _d(Jp), _d(Jc))
+        return Jp, Jc
+
+    def linearize(self):
+        self.L.orc_ba_linearize(self.h)
+        Hpp, Hll = np.zeros((self.ncf, 6, 6)), np.zeros((self.npf, 3, 3))
+        Hpl, b = np.zeros((self.no, 6, 3)), np.zeros(6 * self.ncf + 3 * self.npf)
+        self.L.orc_ba_get_system(self.h, _d(Hpp), _d(Hll), _d(Hpl), _d(b))
+        return Hpp, Hll, Hpl, b
+
+    def max_diag(self): return self.L.orc_ba_max_diag(self.h)
+
+    def schur(self, lam):
+        S, bs = np.zeros((self.nb, 6, 6)), np.zeros(6 * self.ncf)
+        rc = self.L.orc_ba_schur(self.h, float(lam), _d(S), _d(bs))
+        return rc, S, bs
+
+    def solve(self, lam):
+        x = np.zeros(6 * self.ncf + 3 * self.npf)
+        rc = self.L.orc_ba_solve(self.h, float(lam), _d(x))
+        return rc, x
+
+    def update(self, x):
+        x = _f64(x)
+        self.L.orc_ba_update(self.h, _d(x))
+
+    def cameras(self):
+        c = np.zeros((self.nc, 7))
+        self.L.orc_ba_get_cameras(self.h, _d(c))
+        return c
+
+    def points(self):
+        p = np.zeros((self.np_, 3))
+        self.L.orc_ba_get_points(self.h, _d(p))
+        return p
+
+    def optimize(self, max_iter, stop_rel_gain=0.0):
+        hist = np.zeros((max(max_iter, 1), 4))
+        chi2, lam = C.c_double(0), C.c_double(0)
+        n = self.L.orc_ba_optimize(self.h, max_iter, stop_rel_gain, _d(hist), max_iter, C.byref(chi2), C.byref(lam))
+        return n, chi2.value, lam.value, hist[:max(n, 0)]

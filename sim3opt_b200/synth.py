@@ -121,3 +121,59 @@ def sphere(n_laps=100, poses_per_lap=1000, seed=42, radius=100.0,
         info[:, np.arange(7), np.arange(7)] = 1.0 / sig ** 2
     return dict(est=est, gt=gt, fixed=fixed, v0=i_idx.astype(np.int32), v1=j_idx.astype(np.int32),
                 meas=meas, info=info)
+
+
+def ba_loop(n_cams=1000, n_points=500000, obs_per_point=10, seed=42, loop_length=200.0, focal=718.856,
+            cx=607.1928, cy=185.2157, pixel_sigma=1.0, cam_pert=(0.01, 0.1), point_pert=0.2):
+    """Synthetic bundle adjustment of SURVEY.md 8(d) config 5 (bal_example.cpp:87-88 intrinsics).
+
+    Cameras ride a horizontal circle of circumference loop_length looking along the direction of
+    travel; a point is created in front of a randomly chosen "home" camera (depth 5-50 m, lateral
+    +-0.35*depth, vertical +-0.12*depth, i.e. inside the image) and is observed by that camera and
+    the obs_per_point-1 cameras behind it on the path that still see it in front (z > 1 m).
+    Returns dict(cams[n,7] SE3Quat world->camera [q xyzw, t], points[m,3], cams_gt, points_gt,
+    obs_cam, obs_pt, uv, focal, cx, cy).  Observations are sorted by (point, camera) -- the order the
+    reference's file format lists them in is arbitrary (bal_example.cpp:132-166)."""
+    rng = np.random.default_rng(seed)
+    C = n_cams
+    r = loop_length / (2 * np.pi)
+    ang = 2 * np.pi * np.arange(C) / C
+    centre = np.stack([r * np.cos(ang), r * np.sin(ang), np.zeros(C)], axis=1)
+    zc = np.stack([-np.sin(ang), np.cos(ang), np.zeros(C)], axis=1)           # direction of travel
+    yc = np.tile(np.array([0.0, 0.0, -1.0]), (C, 1))                          # image y points down
+    xc = np.cross(yc, zc)
+    Rc2w = np.stack([xc, yc, zc], axis=2)
+    Rw2c = Rotation.from_matrix(np.transpose(Rc2w, (0, 2, 1)))
+    t_gt = -Rw2c.apply(centre)
+    home = rng.integers(0, C, n_points)
+    depth = rng.uniform(5.0, 50.0, n_points)
+    lat = rng.uniform(-0.35, 0.35, n_points) * depth
+    ver = rng.uniform(-0.12, 0.12, n_points) * depth
+    Xc = np.stack([lat, ver, depth], axis=1)
+    pts_gt = np.einsum("nij,nj->ni", Rc2w[home], Xc) + centre[home]
+    obs_cam, obs_pt, uv = [], [], []
+    for back in range(obs_per_point):
+        cam = (home - back) % C
+        Xk = Rw2c[cam].apply(pts_gt) + t_gt[cam]
+        ok = Xk[:, 2] > 1.0
+        u = focal * Xk[:, 0] / Xk[:, 2] + cx
+        v = focal * Xk[:, 1] / Xk[:, 2] + cy
+        idx = np.nonzero(ok)[0]
+        obs_cam.append(cam[idx]); obs_pt.append(idx); uv.append(np.stack([u[idx], v[idx]], axis=1))
+    obs_cam = np.concatenate(obs_cam); obs_pt = np.concatenate(obs_pt); uv = np.concatenate(uv)
+    order = np.lexsort((obs_cam, obs_pt))
+    obs_cam, obs_pt, uv = obs_cam[order], obs_pt[order], uv[order]
+    uv = uv + rng.standard_normal(uv.shape) * pixel_sigma
+    # perturbed initial guess: cameras exp([dw, dt]) * T_gt, points + noise
+    dw = rng.standard_normal((C, 3)) * cam_pert[0]
+    dt = rng.standard_normal((C, 3)) * cam_pert[1]
+    Rp = Rotation.from_rotvec(dw)
+    R_est = Rp * Rw2c
+    t_est = Rp.apply(t_gt) + dt
+    q = R_est.as_quat(); q = np.where(q[:, 3:4] < 0, -q, q)
+    qg = Rw2c.as_quat(); qg = np.where(qg[:, 3:4] < 0, -qg, qg)
+    cams = np.concatenate([q, t_est], axis=1)
+    cams_gt = np.concatenate([qg, t_gt], axis=1)
+    pts = pts_gt + rng.standard_normal(pts_gt.shape) * point_pert
+    return dict(cams=cams, points=pts, cams_gt=cams_gt, points_gt=pts_gt, obs_cam=obs_cam.astype(np.int32),
+                obs_pt=obs_pt.astype(np.int32), uv=uv, focal=focal, cx=cx, cy=cy)
