@@ -164,6 +164,39 @@ int s3o_set_lm_resume(s3o_problem *p, int resume);
 int s3o_snapshot_estimates(s3o_problem *p);
 int s3o_restore_estimates(s3o_problem *p);
 
+/* ---- bundle adjustment, kind S3O_KIND_BA (replaces the g2o calls of ba_demo, bal_example.cpp:44-243)
+ *   new VertexSE3Expmap; setId(0..C-1); setEstimate(SE3Quat(q_w2c, t))     :110-117,:168-185  s3o_ba_set_cameras
+ *   new VertexSBAPointXYZ; setMarginalized(true); setEstimate(p)           :119-129,:187-194  s3o_ba_set_points
+ *   new EdgeProjectXYZ2UV; setVertex(0, point); setVertex(1, cam);
+ *     setInformation(I/sigma^2); setMeasurement(uv); setParameterId(0,0)   :131-166           s3o_ba_set_observations
+ *   RobustKernelHuber, setDelta(2.5)                                       :149-153           s3o_set_robust
+ *   CameraParameters(f, pp, 0)                                             :87-96             s3o_ba_set_intrinsics
+ *   initializeOptimization / optimize(n)                                   :198,:213          s3o_build_structure / s3o_optimize
+ * Camera state: 7 doubles [qx qy qz qw tx ty tz] (g2o SE3Quat, world -> camera), tangent [omega, upsilon];
+ * point: xyz.  Hessian order: free cameras (6 each, id order) then free points (3 each).  The points
+ * are always marginalised (Schur complement, as BlockSolver_6_3 does): s3o_build_structure returns the
+ * number of free cameras and of upper blocks of H_schur, s3o_get_structure its g2o-order block-CCS;
+ * s3o_solve / s3o_update take x = [6 n_free_cameras | 3 n_free_points].  Call order: cameras and
+ * points first, then observations. */
+int s3o_ba_set_cameras(s3o_problem *p, int n, const double *est /* n x 7 */, const uint8_t *fixed /* or NULL */);
+int s3o_ba_set_points(s3o_problem *p, int n, const double *xyz /* n x 3 */, const uint8_t *fixed /* or NULL */);
+/* info: n x 3 packed symmetric [xx xy yy], or NULL for identity */
+int s3o_ba_set_observations(s3o_problem *p, int n, const int32_t *cam_idx, const int32_t *point_idx,
+                            const double *uv /* n x 2 */, const double *info);
+int s3o_ba_set_intrinsics(s3o_problem *p, double focal, double cx, double cy);
+int s3o_ba_set_estimates(s3o_problem *p, const double *cams /* or NULL */, const double *points /* or NULL */);
+int s3o_ba_get_cameras(s3o_problem *p, double *est);
+int s3o_ba_get_points(s3o_problem *p, double *xyz);
+int s3o_ba_get_sizes(s3o_problem *p, int *n_free_cameras, int *n_free_points, int *n_schur_blocks,
+                     int64_t *n_contributions);
+/* lock-step read-outs: errors n_obs x 2 and Hpl n_obs x 6 x 3 (= Jc^T O' Jp) in the caller's
+ * observation order; Hpp n_free_cameras x 6 x 6; Hll n_free_points x 3 x 3; b = [b_cameras | b_points] */
+int s3o_ba_edge_errors(s3o_problem *p, double *err);
+int s3o_ba_get_system(s3o_problem *p, double *Hpp, double *Hll, double *Hpl, double *b);
+/* damped Schur complement S = (Hpp + lambda I) - sum Hpl (Hll + lambda I)^-1 Hpl^T (blocks in the CCS
+ * order of s3o_get_structure) and bs = bp - sum Hpl (Hll + lambda I)^-1 bl */
+int s3o_ba_get_schur(s3o_problem *p, double lambda, double *blocks, double *bs);
+
 /* ---- statistics ------------------------------------------------------------------------ */
 typedef struct s3o_stats {
     double ms_linearize, ms_solve, ms_chi2, ms_update, ms_total; /* CUDA-event time, last optimize */

@@ -64,6 +64,17 @@ SYMBOLS = {
     "s3o_set_lm_resume": (C.c_int, [C.c_void_p, C.c_int]),
     "s3o_snapshot_estimates": (C.c_int, [C.c_void_p]),
     "s3o_restore_estimates": (C.c_int, [C.c_void_p]),
+    "s3o_ba_set_cameras": (C.c_int, [C.c_void_p, C.c_int, _dp, _up]),
+    "s3o_ba_set_points": (C.c_int, [C.c_void_p, C.c_int, _dp, _up]),
+    "s3o_ba_set_observations": (C.c_int, [C.c_void_p, C.c_int, _ip, _ip, _dp, _dp]),
+    "s3o_ba_set_intrinsics": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double]),
+    "s3o_ba_set_estimates": (C.c_int, [C.c_void_p, _dp, _dp]),
+    "s3o_ba_get_cameras": (C.c_int, [C.c_void_p, _dp]),
+    "s3o_ba_get_points": (C.c_int, [C.c_void_p, _dp]),
+    "s3o_ba_get_sizes": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
+    "s3o_ba_edge_errors": (C.c_int, [C.c_void_p, _dp]),
+    "s3o_ba_get_system": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp]),
+    "s3o_ba_get_schur": (C.c_int, [C.c_void_p, C.c_double, _dp, _dp]),
     "s3o_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "s3o_reset_stats": (C.c_int, [C.c_void_p]),
     "s3o_estimate_sigma_squared": (C.c_int, [C.c_void_p, C.c_int, _dp]),

@@ -14,8 +14,8 @@ JAC_NUMERIC, JAC_ANALYTIC = 0, 1
 MATH_REFERENCE, MATH_CORRECTED = 0, 1
 ROBUST_NONE, ROBUST_HUBER, ROBUST_PTAM_TUKEY, ROBUST_PTAM_CAUCHY, ROBUST_PTAM_HUBER, ROBUST_PTAM_LS = range(6)
 
-_EST_DIM = {KIND_SIM3: 8, KIND_SCALE_TRANS: 4, KIND_SCALE: 1}
-_DIM = {KIND_SIM3: 7, KIND_SCALE_TRANS: 4, KIND_SCALE: 1}
+_EST_DIM = {KIND_SIM3: 8, KIND_SCALE_TRANS: 4, KIND_SCALE: 1, KIND_BA: 7}
+_DIM = {KIND_SIM3: 7, KIND_SCALE_TRANS: 4, KIND_SCALE: 1, KIND_BA: 6}
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -257,3 +257,82 @@ def host_structure(n_vertices, fixed, v0, v1):
     if rc != 0:
         raise S3OError(f"s3o error {rc}: {L.s3o_last_error().decode()}")
     return colptr[:nf.value + 1].copy(), rowidx[:nb.value].copy(), hidx[:n_vertices].copy()
+
+
+class BAProblem(Problem):
+    """Bundle adjustment (kind S3O_KIND_BA): the g2o calls of ba_demo (bal_example.cpp:44-243).
+
+    Shares chi2 / linearize_only / max_diag / optimize / stats / set_robust / set_lm / set_pcg /
+    snapshot / restore with Problem; x of solve / update is [6 n_free_cameras | 3 n_free_points]."""
+
+    def __init__(self, device=0, stream=None):
+        super().__init__(KIND_BA, device, stream)
+        self.nc = self.npts = self.no = 0
+
+    def set(self, cams, points, obs_cam, obs_pt, uv, focal, cx, cy, cam_fixed=None, pt_fixed=None, info=None):
+        cams = _f64(cams).reshape(-1, 7)
+        points = _f64(points).reshape(-1, 3)
+        oc = np.ascontiguousarray(obs_cam, np.int32)
+        op = np.ascontiguousarray(obs_pt, np.int32)
+        uv = _f64(uv).reshape(-1, 2)
+        self.nc, self.npts, self.no = len(cams), len(points), len(oc)
+        self.ne = self.no
+        cf = None if cam_fixed is None else np.ascontiguousarray(cam_fixed, np.uint8)
+        pf = None if pt_fixed is None else np.ascontiguousarray(pt_fixed, np.uint8)
+        self._check(self.L.s3o_ba_set_cameras(self.h, self.nc, _d(cams), None if cf is None else cf.ctypes.data_as(_up)))
+        self._check(self.L.s3o_ba_set_points(self.h, self.npts, _d(points), None if pf is None else pf.ctypes.data_as(_up)))
+        infop = None
+        if info is not None:
+            info = _f64(info).reshape(self.no, 3)
+            infop = _d(info)
+        self._check(self.L.s3o_ba_set_observations(self.h, self.no, oc.ctypes.data_as(_ip), op.ctypes.data_as(_ip), _d(uv), infop))
+        self._check(self.L.s3o_ba_set_intrinsics(self.h, float(focal), float(cx), float(cy)))
+
+    def build_structure(self):
+        colptr, rowidx = super().build_structure()
+        ncf, npf, nb, ncon = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int64(0)
+        self._check(self.L.s3o_ba_get_sizes(self.h, C.byref(ncf), C.byref(npf), C.byref(nb), C.byref(ncon)))
+        self.ncf, self.npf, self.nb, self.ncon = ncf.value, npf.value, nb.value, ncon.value
+        return colptr, rowidx
+
+    def set_estimates(self, cams=None, points=None):
+        c = None if cams is None else _f64(cams).reshape(self.nc, 7)
+        q = None if points is None else _f64(points).reshape(self.npts, 3)
+        self._check(self.L.s3o_ba_set_estimates(self.h, None if c is None else _d(c), None if q is None else _d(q)))
+
+    def cameras(self, out=None):
+        c = np.zeros((self.nc, 7)) if out is None else out
+        self._check(self.L.s3o_ba_get_cameras(self.h, _d(c)))
+        return c
+
+    def points(self, out=None):
+        q = np.zeros((self.npts, 3)) if out is None else out
+        self._check(self.L.s3o_ba_get_points(self.h, _d(q)))
+        return q
+
+    def edge_errors(self):
+        e = np.zeros((self.no, 2))
+        self._check(self.L.s3o_ba_edge_errors(self.h, _d(e)))
+        return e
+
+    def linearize(self):
+        self.build_structure()
+        self._check(self.L.s3o_linearize(self.h))
+        Hpp, Hll = np.zeros((self.ncf, 6, 6)), np.zeros((self.npf, 3, 3))
+        Hpl, b = np.zeros((self.no, 6, 3)), np.zeros(6 * self.ncf + 3 * self.npf)
+        self._check(self.L.s3o_ba_get_system(self.h, _d(Hpp), _d(Hll), _d(Hpl), _d(b)))
+        return Hpp, Hll, Hpl, b
+
+    def schur(self, lam):
+        S, bs = np.zeros((self.nb, 6, 6)), np.zeros(6 * self.ncf)
+        self._check(self.L.s3o_ba_get_schur(self.h, float(lam), _d(S), _d(bs)))
+        return S, bs
+
+    def solve(self, lam):
+        x = np.zeros(6 * self.ncf + 3 * self.npf)
+        it, rel = C.c_int(0), C.c_double(0)
+        rc = self.L.s3o_solve(self.h, float(lam), _d(x), C.byref(it), C.byref(rel))
+        return rc, x, it.value, rel.value
+
+    def vertices(self, out=None):
+        raise S3OError("BAProblem: use cameras() / points()")

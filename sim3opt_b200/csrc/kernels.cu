@@ -609,6 +609,7 @@ void launch_maxdiag(int d, const double *H, const int32_t *rowptr, int nf, doubl
     switch (d) {
     case 7: maxdiag_kernel<7, NT><<<grid, NT, 0, st>>>(H, rowptr, nf, partials, sc); break;
     case 4: maxdiag_kernel<4, NT><<<grid, NT, 0, st>>>(H, rowptr, nf, partials, sc); break;
+    case 6: maxdiag_kernel<6, NT><<<grid, NT, 0, st>>>(H, rowptr, nf, partials, sc); break;
     case 1: maxdiag_kernel<1, NT><<<grid, NT, 0, st>>>(H, rowptr, nf, partials, sc); break;
     }
 }
@@ -703,6 +704,7 @@ void launch_precond(int d, const double *H, const int32_t *rowptr, int nf, doubl
     switch (d) {
     case 7: precond_kernel<7><<<grid, 128, 0, st>>>(H, rowptr, nf, lambda, Minv, sc); break;
     case 4: precond_kernel<4><<<grid, 128, 0, st>>>(H, rowptr, nf, lambda, Minv, sc); break;
+    case 6: precond_kernel<6><<<grid, 128, 0, st>>>(H, rowptr, nf, lambda, Minv, sc); break;
     case 1: precond_kernel<1><<<grid, 128, 0, st>>>(H, rowptr, nf, lambda, Minv, sc); break;
     }
 }
@@ -788,7 +790,7 @@ __global__ void __launch_bounds__(NT) spmv_kernel(const double *__restrict__ H, 
     }
 }
 
-template <int D> struct SpmvCfg { static constexpr int NT = 256; static constexpr int TB = D == 7 ? 64 : (D == 4 ? 128 : 512); };
+template <int D> struct SpmvCfg { static constexpr int NT = 256; static constexpr int TB = D >= 6 ? 64 : (D == 4 ? 128 : 512); };
 
 void launch_spmv(int d, const double *H, const StructDev &s, int nf, double lambda, const double *p, double *q1,
                  double *T, double *partials, DevScalars *sc, int pcg_mode, cudaStream_t st) {
@@ -802,6 +804,7 @@ void launch_spmv(int d, const double *H, const StructDev &s, int nf, double lamb
     switch (d) {
     case 7: S3O_SPMV(7) break;
     case 4: S3O_SPMV(4) break;
+    case 6: S3O_SPMV(6) break;
     case 1: S3O_SPMV(1) break;
     }
 #undef S3O_SPMV
@@ -824,6 +827,7 @@ void launch_finish_q(int d, const StructDev &s, int nf, const double *q1, const 
     switch (d) {
     case 7: finish_q_kernel<7><<<grid, 256, 0, st>>>(s, nf, q1, T, q); break;
     case 4: finish_q_kernel<4><<<grid, 256, 0, st>>>(s, nf, q1, T, q); break;
+    case 6: finish_q_kernel<6><<<grid, 256, 0, st>>>(s, nf, q1, T, q); break;
     case 1: finish_q_kernel<1><<<grid, 256, 0, st>>>(s, nf, q1, T, q); break;
     }
 }
@@ -943,6 +947,7 @@ void launch_pcg_init(int d, int nf, const double *b, const double *Minv, double 
     switch (d) {
     case 7: pcg_init_kernel<7, NT><<<vec_grid(nf, NT / 8), NT, 0, st>>>(nf, b, Minv, x, r, z, p, partials, sc, tol, max_iter, dist); break;
     case 4: pcg_init_kernel<4, NT><<<vec_grid(nf, NT / 4), NT, 0, st>>>(nf, b, Minv, x, r, z, p, partials, sc, tol, max_iter, dist); break;
+    case 6: pcg_init_kernel<6, NT><<<vec_grid(nf, NT / 8), NT, 0, st>>>(nf, b, Minv, x, r, z, p, partials, sc, tol, max_iter, dist); break;
     case 1: pcg_init_kernel<1, NT><<<vec_grid(nf, NT), NT, 0, st>>>(nf, b, Minv, x, r, z, p, partials, sc, tol, max_iter, dist); break;
     }
 }
@@ -954,6 +959,7 @@ void launch_pcg_update(int d, const StructDev &s, int nf, const double *q1, cons
     switch (d) {
     case 7: pcg_update_kernel<7, NT><<<vec_grid(nf, NT / 8), NT, 0, st>>>(s, nf, q1, T, Minv, p, x, r, z, partials, sc, dist); break;
     case 4: pcg_update_kernel<4, NT><<<vec_grid(nf, NT / 4), NT, 0, st>>>(s, nf, q1, T, Minv, p, x, r, z, partials, sc, dist); break;
+    case 6: pcg_update_kernel<6, NT><<<vec_grid(nf, NT / 8), NT, 0, st>>>(s, nf, q1, T, Minv, p, x, r, z, partials, sc, dist); break;
     case 1: pcg_update_kernel<1, NT><<<vec_grid(nf, NT), NT, 0, st>>>(s, nf, q1, T, Minv, p, x, r, z, partials, sc, dist); break;
     }
 }

@@ -17,9 +17,7 @@
 #include <cstdlib>
 #include <vector>
 
-#include "comm.h"
-#include "internal.h"
-#include "kernels.cuh"
+#include "problem.h"
 
 namespace s3o {
 
@@ -31,87 +29,12 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
-template <class T>
-static int dev_alloc(T **ptr, size_t count) {
-    *ptr = nullptr;
-    if (count == 0) count = 1;
-    S3O_CUDA(cudaMalloc((void **)ptr, count * sizeof(T)));
-    return S3O_OK;
-}
-template <class T>
-static void dev_free(T *&ptr) {
-    if (ptr) cudaFree(ptr);
-    ptr = nullptr;
-}
-
 }  // namespace s3o
 
 using namespace s3o;
 
-struct s3o_problem {
-    int kind = 0, d = 0, est_dim = 0, ninfo = 0, device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    // host-side graph description
-    int nv = 0, ne = 0;
-    std::vector<uint8_t> fixed;
-    std::vector<int32_t> v0, v1;
-    bool has_info = false, has_aux = false;
-    double *d_meas_aos = nullptr, *d_info_aos = nullptr;  // caller-ordered staging until the structure is built
-    // device graph
-    int nv_pad = 0, ne_pad = 0;
-    double *d_est[2] = { nullptr, nullptr };
-    int cur = 0;
-    double *d_aux = nullptr;
-    int32_t *d_hidx = nullptr, *d_sv0 = nullptr, *d_sv1 = nullptr;
-    double *d_meas = nullptr, *d_info = nullptr;
-    // structure
-    HostStructure S;
-    bool built = false;
-    int32_t *d_rowptr = nullptr, *d_colidx = nullptr, *d_blk_row = nullptr, *d_blk_ebeg = nullptr, *d_blk_eend = nullptr;
-    int32_t *d_colT_ptr = nullptr, *d_colT_blk = nullptr, *d_inc_ptr = nullptr, *d_inc_ent = nullptr, *d_e_blk = nullptr;
-    int32_t *d_tile_row = nullptr;
-    // partitioned solve (one process per GPU, NCCL): s3o_set_comm
-    Comm comm;
-    bool dist = false;
-    PartitionPlan plan;
-    int user_ne = 0;                       // edges passed by the caller (plan.local_edges index into them)
-    int32_t *d_ghidx = nullptr, *d_send_idx = nullptr;
-    uint8_t *d_primary = nullptr;
-    double *d_sendbuf = nullptr, *d_xg = nullptr;
-    int spmv_version = 3;       // 1: lane-group rows, 2: tiled thread-per-block, 3: v2 + TMA ring
-    int spmv_grid_cap = 148 * 2;
-    // linear system
-    double *d_H = nullptr, *d_b = nullptr, *d_x = nullptr, *d_r = nullptr, *d_z = nullptr, *d_p = nullptr;
-    double *d_q1 = nullptr, *d_T = nullptr, *d_Minv = nullptr, *d_scratch = nullptr, *d_partials = nullptr;
-    DevScalars *d_sc = nullptr, *h_sc = nullptr;
-    // parameters
-    int robust_kind = S3O_ROBUST_NONE;
-    double robust_param = 0;
-    int math_mode = S3O_MATH_REFERENCE;
-    int jac_mode = S3O_JAC_ANALYTIC;
-    double jac_h = 1e-9;
-    double tau = 1e-5, user_lambda = 0;
-    int max_trials = 10;
-    double pcg_tol = 1e-8;
-    int pcg_max_iter = 1000;
-    bool linearized = false;
-    // LM continuation state (s3o_set_lm_resume)
-    int lm_resume = 0;
-    bool lm_valid = false;
-    double lm_lambda = 0, lm_ni = 2, lm_chi = 0;
-    double *d_est_snap = nullptr;
-    // sampled SpMV timing
-    static constexpr int kSpmvEvents = 64;
-    cudaEvent_t spmv_ev[2 * kSpmvEvents] = {};
-    int spmv_ev_used = 0;
-    // statistics
-    s3o_stats stats{};
-    cudaEvent_t ev[6] = {};
-};
 
 namespace {
-
 void run_spmv(s3o_problem *p, const StructDev &s, double lambda, const double *x, int pcg_mode);
 
 GraphDev graph_view(const s3o_problem *p, int which) {
@@ -126,6 +49,10 @@ GraphDev graph_view(const s3o_problem *p, int which) {
     g.ghidx = p->dist ? p->d_ghidx : nullptr;
     return g;
 }
+
+}  // namespace
+
+namespace s3o {
 
 StructDev struct_view(const s3o_problem *p) {
     StructDev s{};
@@ -150,22 +77,15 @@ void free_structure(s3o_problem *p) {
     p->linearized = false;
 }
 
-template <class T>
-int upload(s3o_problem *p, T **dst, const std::vector<T> &src) {
-    int rc = dev_alloc(dst, src.size());
-    if (rc) return rc;
-    if (!src.empty()) {
-        S3O_CUDA(cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, p->stream));
-        p->stats.h2d_bytes += (int64_t)(src.size() * sizeof(T));
-    }
-    return S3O_OK;
-}
-
 int check_launch(s3o_problem *p, int n) {
     p->stats.kernel_launches += n;
     S3O_CUDA(cudaGetLastError());
     return S3O_OK;
 }
+
+}  // namespace s3o
+
+namespace {
 
 // rows this rank solves for (all free vertices on one GPU)
 inline int own_rows(const s3o_problem *p) { return p->dist ? p->plan.n_own : p->S.nf; }
@@ -181,12 +101,18 @@ int allreduce_max(s3o_problem *p, double *field, int count) {
     return S3O_OK;
 }
 
+}  // namespace
+
+namespace s3o {
 int sync_scalars(s3o_problem *p) {
     S3O_CUDA(cudaMemcpyAsync(p->h_sc, p->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, p->stream));
     S3O_CUDA(cudaStreamSynchronize(p->stream));
     p->stats.d2h_bytes += sizeof(DevScalars);
     return S3O_OK;
 }
+}  // namespace s3o
+
+namespace {
 
 int ensure_built(s3o_problem *p) {
     if (p->built) return S3O_OK;
@@ -205,6 +131,7 @@ void run_spmv(s3o_problem *p, const StructDev &s, double lambda, const double *x
 }
 
 int do_chi2(s3o_problem *p, int which) {
+    if (p->kind == S3O_KIND_BA) return ba_chi2(p, which);
     if (p->S.ne_act == 0) {
         S3O_CUDA(cudaMemsetAsync(&p->d_sc->chi2, 0, sizeof(double), p->stream));
         return allreduce_sum(p, &p->d_sc->chi2, 1);
@@ -215,6 +142,7 @@ int do_chi2(s3o_problem *p, int which) {
 }
 
 int do_linearize(s3o_problem *p) {
+    if (p->kind == S3O_KIND_BA) return ba_linearize(p);
     const GraphDev g = graph_view(p, p->cur);
     launch_linearize(g, p->jac_mode, p->jac_h, p->d_scratch, p->stream);
     launch_assemble(g, struct_view(p), p->d_scratch, p->d_H, p->d_b, p->stream);
@@ -222,6 +150,9 @@ int do_linearize(s3o_problem *p) {
     return check_launch(p, 2);
 }
 
+}  // namespace
+
+namespace s3o {
 // Solve (H + lambda I) x = b; leaves x in d_x.  Returns the PCG status in *status (1 converged,
 // 2 iteration cap, 3 breakdown) and the iteration count.
 int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel_res) {
@@ -294,8 +225,49 @@ int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel
     if (rel_res) *rel_res = p->h_sc->rr0 > 0 ? std::sqrt(p->h_sc->rr / p->h_sc->rr0) : 0.0;
     return S3O_OK;
 }
+}  // namespace s3o
 
-}  // namespace
+namespace s3o {
+
+// BSR-upper arrays of p->S (rows, columns, block->row, column view, SpMV tiles) -> device
+int upload_structure_arrays(s3o_problem *p, int rows_own) {
+    HostStructure &S = p->S;
+    std::vector<int32_t> blk_row(S.nb);
+    for (int r = 0; r < S.nf; ++r)
+        for (int k = S.rowptr[r]; k < S.rowptr[r + 1]; ++k) blk_row[k] = r;
+    int rc = 0;
+    rc = rc ? rc : upload(p, &p->d_rowptr, S.rowptr);
+    rc = rc ? rc : upload(p, &p->d_colidx, S.colidx);
+    rc = rc ? rc : upload(p, &p->d_blk_row, blk_row);
+    rc = rc ? rc : upload(p, &p->d_colT_ptr, S.colT_ptr);
+    rc = rc ? rc : upload(p, &p->d_colT_blk, S.colT_blk);
+    S.max_row_blocks = 0;
+    for (int r = 0; r < rows_own; ++r) S.max_row_blocks = std::max(S.max_row_blocks, S.rowptr[r + 1] - S.rowptr[r]);
+    S.tile_blocks = p->spmv_version == 3 ? spmv3_tile_blocks(p->d) : spmv_tile_blocks(p->d);
+    build_tiles(S.rowptr, rows_own, S.tile_blocks, S.tile_row);
+    rc = rc ? rc : upload(p, &p->d_tile_row, S.tile_row);
+    return rc;
+}
+
+// H, b and the PCG vectors for p->S; vectors are sized for owned + ghost rows, and x also serves
+// as the all-gather send buffer (seg rows) in the partitioned solve
+int alloc_linear_system(s3o_problem *p) {
+    const HostStructure &S = p->S;
+    const size_t nfd = (size_t)std::max(S.nf, p->dist ? p->plan.seg : 0) * p->d, dd = (size_t)p->d * p->d;
+    int rc = 0;
+    rc = rc ? rc : dev_alloc(&p->d_H, (size_t)S.nb * dd + 2);   // +16 B: the TMA tile copy rounds its size up
+    rc = rc ? rc : dev_alloc(&p->d_b, nfd);
+    rc = rc ? rc : dev_alloc(&p->d_x, nfd);
+    rc = rc ? rc : dev_alloc(&p->d_r, nfd);
+    rc = rc ? rc : dev_alloc(&p->d_z, nfd);
+    rc = rc ? rc : dev_alloc(&p->d_p, nfd);
+    rc = rc ? rc : dev_alloc(&p->d_q1, nfd);
+    rc = rc ? rc : dev_alloc(&p->d_T, (size_t)S.nb * p->d);
+    rc = rc ? rc : dev_alloc(&p->d_Minv, (size_t)S.nf * dd);
+    return rc;
+}
+
+}  // namespace s3o
 
 // ======================================================================================
 // C ABI
@@ -319,6 +291,7 @@ int s3o_create(int kind, int device, s3o_problem **out) {
     case S3O_KIND_SIM3: d = 7; est_dim = 8; break;
     case S3O_KIND_SCALE_TRANS: d = 4; est_dim = 4; break;
     case S3O_KIND_SCALE: d = 1; est_dim = 1; break;
+    case S3O_KIND_BA: d = 6; est_dim = 7; break;     // Schur-complement system: 6x6 camera blocks
     default: set_error("s3o_create: unsupported kind %d", kind); return S3O_ERR_UNSUPPORTED;
     }
     int ndev = 0;
@@ -356,6 +329,7 @@ int s3o_destroy(s3o_problem *p) {
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
     free_structure(p);
+    ba_destroy(p);
     dev_free(p->d_meas_aos); dev_free(p->d_info_aos);
     dev_free(p->d_est[0]); dev_free(p->d_est[1]); dev_free(p->d_aux);
     dev_free(p->d_sc); dev_free(p->d_partials);
@@ -421,6 +395,7 @@ static int upload_estimates(s3o_problem *p, const double *est) {
 
 int s3o_set_vertices(s3o_problem *p, int n, const double *est, const uint8_t *fixed, const double *aux) {
     if (!p || n < 0 || (n > 0 && !est)) { set_error("s3o_set_vertices: bad arguments"); return S3O_ERR_INVALID; }
+    if (p->kind == S3O_KIND_BA) { set_error("s3o_set_vertices: a BA problem takes s3o_ba_set_cameras / s3o_ba_set_points"); return S3O_ERR_INVALID; }
     if (p->kind == S3O_KIND_SCALE_TRANS && !aux && n > 0) { set_error("s3o_set_vertices: SCALE_TRANS needs aux rotations"); return S3O_ERR_INVALID; }
     cudaSetDevice(p->device);
     free_structure(p);
@@ -458,6 +433,7 @@ int s3o_set_vertices(s3o_problem *p, int n, const double *est, const uint8_t *fi
 }
 
 int s3o_set_estimates(s3o_problem *p, const double *est) {
+    if (p && p->kind == S3O_KIND_BA) { set_error("s3o_set_estimates: a BA problem takes s3o_ba_set_estimates"); return S3O_ERR_INVALID; }
     if (!p || !est || !p->d_est[0]) { set_error("s3o_set_estimates: call s3o_set_vertices first"); return S3O_ERR_INVALID; }
     cudaSetDevice(p->device);
     p->linearized = false;
@@ -467,6 +443,7 @@ int s3o_set_estimates(s3o_problem *p, const double *est) {
 
 int s3o_set_edges(s3o_problem *p, int n, const int32_t *v0, const int32_t *v1, const double *meas, const double *info) {
     if (!p || n < 0 || (n > 0 && (!v0 || !v1 || !meas))) { set_error("s3o_set_edges: bad arguments"); return S3O_ERR_INVALID; }
+    if (p->kind == S3O_KIND_BA) { set_error("s3o_set_edges: a BA problem takes s3o_ba_set_observations"); return S3O_ERR_INVALID; }
     for (int k = 0; k < n; ++k)
         if (v0[k] < 0 || v0[k] >= p->nv || v1[k] < 0 || v1[k] >= p->nv || v0[k] == v1[k]) {
             set_error("s3o_set_edges: edge %d has invalid vertices (%d,%d), n_vertices=%d", k, v0[k], v1[k], p->nv);
@@ -557,6 +534,13 @@ int s3o_set_pcg(s3o_problem *p, double rel_tol, int max_iter) {
 
 int s3o_build_structure(s3o_problem *p, int *n_free, int *n_blocks) {
     if (!p) return S3O_ERR_INVALID;
+    if (p->kind == S3O_KIND_BA) {
+        cudaSetDevice(p->device);
+        if (!p->built) { int rc = ba_build_structure(p); if (rc) return rc; }
+        if (n_free) *n_free = p->S.nf;
+        if (n_blocks) *n_blocks = p->S.nb;
+        return S3O_OK;
+    }
     if (!p->d_est[0]) { set_error("s3o_build_structure: no vertices"); return S3O_ERR_INVALID; }
     cudaSetDevice(p->device);
     if (!p->built) {
@@ -571,27 +555,16 @@ int s3o_build_structure(s3o_problem *p, int *n_free, int *n_blocks) {
         const int rows_own = p->dist ? p->plan.n_own : S.nf;
         p->ne_pad = pad32(S.ne_act);
         int rc = 0;
-        std::vector<int32_t> blk_row(S.nb);
-        for (int r = 0; r < S.nf; ++r)
-            for (int k = S.rowptr[r]; k < S.rowptr[r + 1]; ++k) blk_row[k] = r;
         int32_t *d_perm = nullptr;
         rc = rc ? rc : upload(p, &p->d_hidx, S.hidx);
         rc = rc ? rc : upload(p, &p->d_sv0, S.sv0);
         rc = rc ? rc : upload(p, &p->d_sv1, S.sv1);
-        rc = rc ? rc : upload(p, &p->d_rowptr, S.rowptr);
-        rc = rc ? rc : upload(p, &p->d_colidx, S.colidx);
-        rc = rc ? rc : upload(p, &p->d_blk_row, blk_row);
         rc = rc ? rc : upload(p, &p->d_blk_ebeg, S.blk_ebeg);
         rc = rc ? rc : upload(p, &p->d_blk_eend, S.blk_eend);
-        rc = rc ? rc : upload(p, &p->d_colT_ptr, S.colT_ptr);
-        rc = rc ? rc : upload(p, &p->d_colT_blk, S.colT_blk);
         rc = rc ? rc : upload(p, &p->d_inc_ptr, S.inc_ptr);
         rc = rc ? rc : upload(p, &p->d_inc_ent, S.inc_ent);
         rc = rc ? rc : upload(p, &p->d_e_blk, S.e_blk);
-        S.max_row_blocks = 0;
-        for (int r = 0; r < rows_own; ++r) S.max_row_blocks = std::max(S.max_row_blocks, S.rowptr[r + 1] - S.rowptr[r]);
-        S.tile_blocks = p->spmv_version == 3 ? spmv3_tile_blocks(p->d) : spmv_tile_blocks(p->d);
-        build_tiles(S.rowptr, rows_own, S.tile_blocks, S.tile_row);
+        rc = rc ? rc : upload_structure_arrays(p, rows_own);
         if (p->dist) {
             const PartitionPlan &P = p->plan;
             std::vector<uint8_t> prim(S.ne_act);
@@ -602,22 +575,12 @@ int s3o_build_structure(s3o_problem *p, int *n_free, int *n_blocks) {
             rc = rc ? rc : dev_alloc(&p->d_sendbuf, P.send_idx.size() * p->d);
             rc = rc ? rc : dev_alloc(&p->d_xg, (size_t)P.world * P.seg * p->d);
         }
-        rc = rc ? rc : upload(p, &p->d_tile_row, S.tile_row);
         rc = rc ? rc : upload(p, &d_perm, S.perm);
         rc = rc ? rc : dev_alloc(&p->d_meas, (size_t)p->ne_pad * p->est_dim);
         if (p->has_info) rc = rc ? rc : dev_alloc(&p->d_info, (size_t)p->ne_pad * p->ninfo);
-        // vectors are sized for owned + ghost rows; x also serves as the all-gather send buffer (seg rows)
-        const size_t nfd = (size_t)std::max(S.nf, p->dist ? p->plan.seg : 0) * p->d, dd = (size_t)p->d * p->d;
-        rc = rc ? rc : dev_alloc(&p->d_H, (size_t)S.nb * dd + 2);   // +16 B: the TMA tile copy rounds its size up
-        rc = rc ? rc : dev_alloc(&p->d_b, nfd);
-        rc = rc ? rc : dev_alloc(&p->d_x, nfd);
-        rc = rc ? rc : dev_alloc(&p->d_r, nfd);
-        rc = rc ? rc : dev_alloc(&p->d_z, nfd);
-        rc = rc ? rc : dev_alloc(&p->d_p, nfd);
-        rc = rc ? rc : dev_alloc(&p->d_q1, nfd);
-        rc = rc ? rc : dev_alloc(&p->d_T, (size_t)S.nb * p->d);
-        rc = rc ? rc : dev_alloc(&p->d_Minv, (size_t)S.nf * dd);
+        rc = rc ? rc : alloc_linear_system(p);
         rc = rc ? rc : dev_alloc(&p->d_scratch, (size_t)p->ne_pad * scratch_stride(p->d));
+        const size_t nfd = (size_t)std::max(S.nf, p->dist ? p->plan.seg : 0) * p->d;
         if (rc) { dev_free(d_perm); free_structure(p); return rc; }
         if (S.ne_act > 0) {
             cudaMemsetAsync(p->d_meas, 0, (size_t)p->ne_pad * p->est_dim * sizeof(double), p->stream);
@@ -706,6 +669,7 @@ int s3o_chi2(s3o_problem *p, double *chi2) {
 
 int s3o_edge_errors(s3o_problem *p, double *err) {
     if (!p || !err) return S3O_ERR_INVALID;
+    if (p->kind == S3O_KIND_BA) return s3o_ba_edge_errors(p, err);
     cudaSetDevice(p->device);
     int rc = ensure_built(p);
     if (rc) return rc;
@@ -740,6 +704,7 @@ int s3o_linearize(s3o_problem *p) {
 }
 
 int s3o_get_hessian(s3o_problem *p, double *blocks, double *b) {
+    if (p && p->kind == S3O_KIND_BA) { set_error("s3o_get_hessian: a BA problem exposes s3o_ba_get_system / s3o_ba_get_schur"); return S3O_ERR_INVALID; }
     if (!p || !p->built || !p->linearized) { set_error("s3o_get_hessian: call s3o_linearize first"); return S3O_ERR_INVALID; }
     cudaSetDevice(p->device);
     const size_t dd = (size_t)p->d * p->d;
@@ -762,8 +727,12 @@ int s3o_get_hessian(s3o_problem *p, double *blocks, double *b) {
 int s3o_max_diag(s3o_problem *p, double *max_diag) {
     if (!p || !p->built || !p->linearized || !max_diag) { set_error("s3o_max_diag: call s3o_linearize first"); return S3O_ERR_INVALID; }
     cudaSetDevice(p->device);
-    launch_maxdiag(p->d, p->d_H, p->d_rowptr, own_rows(p), p->d_partials, p->d_sc, p->stream);
-    int rc = check_launch(p, 1);
+    int rc;
+    if (p->kind == S3O_KIND_BA) rc = ba_max_diag(p);
+    else {
+        launch_maxdiag(p->d, p->d_H, p->d_rowptr, own_rows(p), p->d_partials, p->d_sc, p->stream);
+        rc = check_launch(p, 1);
+    }
     if (rc) return rc;
     if ((rc = allreduce_max(p, &p->d_sc->maxdiag, 1))) return rc;
     if ((rc = sync_scalars(p))) return rc;
@@ -775,6 +744,12 @@ int s3o_solve(s3o_problem *p, double lambda, double *x, int *pcg_iters, double *
     if (!p || !p->built || !p->linearized) { set_error("s3o_solve: call s3o_linearize first"); return S3O_ERR_INVALID; }
     cudaSetDevice(p->device);
     int status = 0;
+    if (p->kind == S3O_KIND_BA) {       // x = [cameras 6 n_free_cameras | points 3 n_free_points]
+        int rc = ba_solve(p, lambda, &status, pcg_iters, rel_residual);
+        if (rc) return rc;
+        if (x && (rc = ba_download_step(p, x))) return rc;
+        return status == 3 ? S3O_RESULT_FAIL : S3O_OK;
+    }
     int rc = do_solve(p, lambda, &status, pcg_iters, rel_residual);
     if (rc) return rc;
     if (x) {
@@ -806,6 +781,14 @@ int s3o_update(s3o_problem *p, const double *x) {
     cudaSetDevice(p->device);
     int rc = ensure_built(p);
     if (rc) return rc;
+    if (p->kind == S3O_KIND_BA) {
+        if ((rc = ba_upload_step(p, x))) return rc;
+        if ((rc = ba_retract_and_scale(p, 0.0, p->cur ^ 1))) return rc;
+        S3O_CUDA(cudaStreamSynchronize(p->stream));
+        p->cur ^= 1;
+        p->linearized = false;
+        return S3O_OK;
+    }
     const size_t bytes = (size_t)p->S.nf * p->d * sizeof(double);
     S3O_CUDA(cudaMemcpyAsync(p->d_x, x, bytes, cudaMemcpyHostToDevice, p->stream));
     launch_retract(graph_view(p, p->cur), p->d_x, p->d_est[p->cur ^ 1], p->stream);
@@ -840,8 +823,11 @@ int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterat
         if ((rc = do_linearize(p))) return rc;
         cudaEventRecord(p->ev[2], p->stream);
         if (it == 0 && !resume) {
-            launch_maxdiag(d, p->d_H, p->d_rowptr, nf, p->d_partials, p->d_sc, p->stream);
-            if ((rc = check_launch(p, 1))) return rc;
+            if (p->kind == S3O_KIND_BA) { if ((rc = ba_max_diag(p))) return rc; }
+            else {
+                launch_maxdiag(d, p->d_H, p->d_rowptr, nf, p->d_partials, p->d_sc, p->stream);
+                if ((rc = check_launch(p, 1))) return rc;
+            }
             if ((rc = allreduce_max(p, &p->d_sc->maxdiag, 1))) return rc;
             if ((rc = sync_scalars(p))) return rc;
             currentChi = p->h_sc->chi2;
@@ -854,7 +840,9 @@ int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterat
         do {
             cudaEventRecord(p->ev[3], p->stream);
             int status = 0, iters = 0;
-            if ((rc = do_solve(p, lambda, &status, &iters, nullptr))) return rc;
+            if (p->kind == S3O_KIND_BA) rc = ba_solve(p, lambda, &status, &iters, nullptr);
+            else rc = do_solve(p, lambda, &status, &iters, nullptr);
+            if (rc) return rc;
             pcg_total += iters;
             cudaEventRecord(p->ev[4], p->stream);
             const int trial = p->cur ^ 1;
@@ -866,9 +854,13 @@ int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterat
                 }
                 xfull = p->d_xg;
             }
-            launch_retract(graph_view(p, p->cur), xfull, p->d_est[trial], p->stream);
-            launch_scale(nf * d, p->d_x, p->d_b, lambda, p->d_partials, p->d_sc, p->stream);
-            if ((rc = check_launch(p, 2))) return rc;
+            if (p->kind == S3O_KIND_BA) {
+                if ((rc = ba_retract_and_scale(p, lambda, trial))) return rc;
+            } else {
+                launch_retract(graph_view(p, p->cur), xfull, p->d_est[trial], p->stream);
+                launch_scale(nf * d, p->d_x, p->d_b, lambda, p->d_partials, p->d_sc, p->stream);
+                if ((rc = check_launch(p, 2))) return rc;
+            }
             if ((rc = allreduce_sum(p, &p->d_sc->scale, 1))) return rc;
             if ((rc = do_chi2(p, trial))) return rc;
             cudaEventRecord(p->ev[5], p->stream);
@@ -940,7 +932,7 @@ int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterat
 int s3o_smallest_eigenvector(s3o_problem *p, int max_iter, double tol, double *x, double *lambda_min,
                              double *lambda_max, int *iterations) {
     if (!p || !x) { set_error("s3o_smallest_eigenvector: bad arguments"); return S3O_ERR_INVALID; }
-    if (p->dist) { set_error("s3o_smallest_eigenvector: not available in the partitioned solve"); return S3O_ERR_UNSUPPORTED; }
+    if (p->dist || p->kind == S3O_KIND_BA) { set_error("s3o_smallest_eigenvector: not available for this problem"); return S3O_ERR_UNSUPPORTED; }
     cudaSetDevice(p->device);
     int rc = ensure_built(p);
     if (rc) return rc;
@@ -1001,6 +993,7 @@ int s3o_smallest_eigenvector(s3o_problem *p, int max_iter, double tol, double *x
 }
 
 int s3o_get_vertices(s3o_problem *p, double *est) {
+    if (p && p->kind == S3O_KIND_BA) { set_error("s3o_get_vertices: a BA problem takes s3o_ba_get_cameras / s3o_ba_get_points"); return S3O_ERR_INVALID; }
     if (!p || !est || !p->d_est[0]) { set_error("s3o_get_vertices: no vertices"); return S3O_ERR_INVALID; }
     cudaSetDevice(p->device);
     double *tmp = nullptr;
@@ -1025,6 +1018,7 @@ int s3o_set_lm_resume(s3o_problem *p, int resume) {
 }
 
 int s3o_snapshot_estimates(s3o_problem *p) {
+    if (p && p->kind == S3O_KIND_BA) { cudaSetDevice(p->device); int rc = ensure_built(p); return rc ? rc : ba_snapshot(p, 0); }
     if (!p || !p->d_est[0]) { set_error("s3o_snapshot_estimates: no vertices"); return S3O_ERR_INVALID; }
     cudaSetDevice(p->device);
     const size_t cnt = (size_t)p->nv_pad * p->est_dim;
@@ -1034,6 +1028,12 @@ int s3o_snapshot_estimates(s3o_problem *p) {
 }
 
 int s3o_restore_estimates(s3o_problem *p) {
+    if (p && p->kind == S3O_KIND_BA) {
+        cudaSetDevice(p->device);
+        p->linearized = false;
+        p->lm_valid = false;
+        return ba_snapshot(p, 1);
+    }
     if (!p || !p->d_est_snap) { set_error("s3o_restore_estimates: no snapshot"); return S3O_ERR_INVALID; }
     cudaSetDevice(p->device);
     const size_t cnt = (size_t)p->nv_pad * p->est_dim;
@@ -1045,7 +1045,8 @@ int s3o_restore_estimates(s3o_problem *p) {
 
 int s3o_get_stats(s3o_problem *p, s3o_stats *out) {
     if (!p || !out) return S3O_ERR_INVALID;
-    p->stats.n_vertices = p->nv; p->stats.n_edges = p->ne; p->stats.dim = p->d;
+    p->stats.n_vertices = p->nv; p->stats.dim = p->d;
+    if (p->kind != S3O_KIND_BA) p->stats.n_edges = p->ne;
     p->stats.n_free = p->built ? p->S.nf : 0;
     p->stats.n_blocks = p->built ? p->S.nb : 0;
     *out = p->stats;
@@ -1060,6 +1061,7 @@ int s3o_reset_stats(s3o_problem *p) {
 
 int s3o_estimate_sigma_squared(s3o_problem *p, int robust_kind, double *sigma_squared) {
     if (!p || !sigma_squared) return S3O_ERR_INVALID;
+    if (p->kind == S3O_KIND_BA) { set_error("s3o_estimate_sigma_squared: pose-graph kinds only"); return S3O_ERR_UNSUPPORTED; }
     cudaSetDevice(p->device);
     int rc = ensure_built(p);
     if (rc) return rc;

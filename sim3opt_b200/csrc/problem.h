@@ -1,0 +1,131 @@
+// problem.h -- the s3o_problem object and the host-side helpers shared by problem.cu and ba.cu.
+#pragma once
+#include <vector>
+
+#include "comm.h"
+#include "internal.h"
+#include "kernels.cuh"
+
+namespace s3o {
+
+template <class T>
+int dev_alloc(T **ptr, size_t count) {
+    *ptr = nullptr;
+    if (count == 0) count = 1;
+    S3O_CUDA(cudaMalloc((void **)ptr, count * sizeof(T)));
+    return S3O_OK;
+}
+template <class T>
+void dev_free(T *&ptr) {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+}
+
+struct BaState;   // bundle adjustment (ba.cu)
+
+}  // namespace s3o
+
+using s3o::Comm;
+using s3o::DevScalars;
+using s3o::HostStructure;
+using s3o::PartitionPlan;
+
+struct s3o_problem {
+    int kind = 0, d = 0, est_dim = 0, ninfo = 0, device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // host-side graph description
+    int nv = 0, ne = 0;
+    std::vector<uint8_t> fixed;
+    std::vector<int32_t> v0, v1;
+    bool has_info = false, has_aux = false;
+    double *d_meas_aos = nullptr, *d_info_aos = nullptr;  // caller-ordered staging until the structure is built
+    // device graph
+    int nv_pad = 0, ne_pad = 0;
+    double *d_est[2] = { nullptr, nullptr };
+    int cur = 0;
+    double *d_aux = nullptr;
+    int32_t *d_hidx = nullptr, *d_sv0 = nullptr, *d_sv1 = nullptr;
+    double *d_meas = nullptr, *d_info = nullptr;
+    // structure
+    HostStructure S;
+    bool built = false;
+    int32_t *d_rowptr = nullptr, *d_colidx = nullptr, *d_blk_row = nullptr, *d_blk_ebeg = nullptr, *d_blk_eend = nullptr;
+    int32_t *d_colT_ptr = nullptr, *d_colT_blk = nullptr, *d_inc_ptr = nullptr, *d_inc_ent = nullptr, *d_e_blk = nullptr;
+    int32_t *d_tile_row = nullptr;
+    // partitioned solve (one process per GPU, NCCL): s3o_set_comm
+    Comm comm;
+    bool dist = false;
+    PartitionPlan plan;
+    int user_ne = 0;                       // edges passed by the caller (plan.local_edges index into them)
+    int32_t *d_ghidx = nullptr, *d_send_idx = nullptr;
+    uint8_t *d_primary = nullptr;
+    double *d_sendbuf = nullptr, *d_xg = nullptr;
+    int spmv_version = 3;       // 1: lane-group rows, 2: tiled thread-per-block, 3: v2 + TMA ring
+    int spmv_grid_cap = 148 * 2;
+    // linear system
+    double *d_H = nullptr, *d_b = nullptr, *d_x = nullptr, *d_r = nullptr, *d_z = nullptr, *d_p = nullptr;
+    double *d_q1 = nullptr, *d_T = nullptr, *d_Minv = nullptr, *d_scratch = nullptr, *d_partials = nullptr;
+    DevScalars *d_sc = nullptr, *h_sc = nullptr;
+    // parameters
+    int robust_kind = S3O_ROBUST_NONE;
+    double robust_param = 0;
+    int math_mode = S3O_MATH_REFERENCE;
+    int jac_mode = S3O_JAC_ANALYTIC;
+    double jac_h = 1e-9;
+    double tau = 1e-5, user_lambda = 0;
+    int max_trials = 10;
+    double pcg_tol = 1e-8;
+    int pcg_max_iter = 1000;
+    bool linearized = false;
+    // LM continuation state (s3o_set_lm_resume)
+    int lm_resume = 0;
+    bool lm_valid = false;
+    double lm_lambda = 0, lm_ni = 2, lm_chi = 0;
+    double *d_est_snap = nullptr;
+    // sampled SpMV timing
+    static constexpr int kSpmvEvents = 64;
+    cudaEvent_t spmv_ev[2 * kSpmvEvents] = {};
+    int spmv_ev_used = 0;
+    // statistics
+    s3o_stats stats{};
+    cudaEvent_t ev[6] = {};
+    // bundle adjustment (kind S3O_KIND_BA): cameras / points / observations live in ba.cu
+    s3o::BaState *ba = nullptr;
+};
+
+namespace s3o {
+
+template <class T>
+int upload(s3o_problem *p, T **dst, const std::vector<T> &src) {
+    int rc = dev_alloc(dst, src.size());
+    if (rc) return rc;
+    if (!src.empty()) {
+        S3O_CUDA(cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, p->stream));
+        p->stats.h2d_bytes += (int64_t)(src.size() * sizeof(T));
+    }
+    return S3O_OK;
+}
+
+StructDev struct_view(const s3o_problem *p);
+void free_structure(s3o_problem *p);
+int check_launch(s3o_problem *p, int n);
+int sync_scalars(s3o_problem *p);
+int upload_structure_arrays(s3o_problem *p, int rows_own);   // BSR / tile arrays of p->S -> device
+int alloc_linear_system(s3o_problem *p);                      // H, b, x, r, z, p, q1, T, Minv for p->S
+// Solve (H + lambda I) x = b by block-Jacobi PCG on the system held in p->d_H / p->d_b; x in p->d_x
+int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel_res);
+
+// ---- bundle adjustment hooks (ba.cu), called from the C ABI in problem.cu --------------------
+void ba_destroy(s3o_problem *p);
+int ba_build_structure(s3o_problem *p);
+int ba_chi2(s3o_problem *p, int which);
+int ba_linearize(s3o_problem *p);
+int ba_max_diag(s3o_problem *p);
+int ba_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel_res);   // full step in ba->d_x
+int ba_retract_and_scale(s3o_problem *p, double lambda, int trial);
+int ba_upload_step(s3o_problem *p, const double *x);
+int ba_download_step(s3o_problem *p, double *x);
+int ba_snapshot(s3o_problem *p, int restore);
+
+}  // namespace s3o

@@ -259,7 +259,7 @@ struct JlInv {
     double y[3];
 };
 
-__device__ __noinline__ void sim3_jl_inv(const double e[7], JlInv &out) {
+static __device__ __noinline__ void sim3_jl_inv(const double e[7], JlInv &out) {
     double Om[9], Up[9], M[9];
     skew3(e[0], e[1], e[2], Om);
     skew3(e[3], e[4], e[5], Up);

@@ -20,10 +20,11 @@
 
 namespace s3o {
 
-int spmv_tile_blocks(int d) { return d == 7 ? 128 : 256; }
+int spmv_tile_blocks(int d) { return d >= 6 ? 128 : 256; }
 
 template <int D> struct Spmv2Cfg;
 template <> struct Spmv2Cfg<7> { static constexpr int NT = 128, TB = 128; };
+template <> struct Spmv2Cfg<6> { static constexpr int NT = 128, TB = 128; };
 template <> struct Spmv2Cfg<4> { static constexpr int NT = 256, TB = 256; };
 template <> struct Spmv2Cfg<1> { static constexpr int NT = 256, TB = 256; };
 
@@ -185,6 +186,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigne
 
 template <int D> struct Spmv3Cfg;
 template <> struct Spmv3Cfg<7> { static constexpr int NT = 128, TB = 112; };
+template <> struct Spmv3Cfg<6> { static constexpr int NT = 128, TB = 128; };
 template <> struct Spmv3Cfg<4> { static constexpr int NT = 256, TB = 256; };
 template <> struct Spmv3Cfg<1> { static constexpr int NT = 256, TB = 256; };
 
@@ -311,7 +313,7 @@ __global__ void __launch_bounds__(NT) spmv3_kernel(const double *__restrict__ H,
     }
 }
 
-int spmv3_tile_blocks(int d) { return d == 7 ? Spmv3Cfg<7>::TB : 256; }
+int spmv3_tile_blocks(int d) { return d == 7 ? Spmv3Cfg<7>::TB : (d == 6 ? Spmv3Cfg<6>::TB : 256); }
 
 void launch_spmv3(int d, const double *H, const StructDev &s, int nf, double lambda, const double *p, double *q1,
                   double *T, double *partials, DevScalars *sc, int pcg_mode, int grid_cap, int dist, cudaStream_t st) {
@@ -323,6 +325,7 @@ void launch_spmv3(int d, const double *H, const StructDev &s, int nf, double lam
     switch (d) {
     case 7: S3O_SPMV3(7) break;
     case 4: S3O_SPMV3(4) break;
+    case 6: S3O_SPMV3(6) break;
     case 1: S3O_SPMV3(1) break;
     }
 #undef S3O_SPMV3
@@ -335,6 +338,12 @@ int spmv2_configure() {
     cudaError_t e;
     e = cudaFuncSetAttribute(spmv2_kernel<7, Spmv2Cfg<7>::NT, Spmv2Cfg<7>::TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)spmv2_smem_bytes<7, Spmv2Cfg<7>::TB>());
+    if (e != cudaSuccess) return -1;
+    e = cudaFuncSetAttribute(spmv2_kernel<6, Spmv2Cfg<6>::NT, Spmv2Cfg<6>::TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)spmv2_smem_bytes<6, Spmv2Cfg<6>::TB>());
+    if (e != cudaSuccess) return -1;
+    e = cudaFuncSetAttribute(spmv3_kernel<6, Spmv3Cfg<6>::NT, Spmv3Cfg<6>::TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)spmv3_smem_bytes<6, Spmv3Cfg<6>::TB>());
     if (e != cudaSuccess) return -1;
     e = cudaFuncSetAttribute(spmv2_kernel<4, Spmv2Cfg<4>::NT, Spmv2Cfg<4>::TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)spmv2_smem_bytes<4, Spmv2Cfg<4>::TB>());
@@ -366,6 +375,7 @@ void launch_spmv2(int d, const double *H, const StructDev &s, int nf, double lam
     switch (d) {
     case 7: S3O_SPMV2(7) break;
     case 4: S3O_SPMV2(4) break;
+    case 6: S3O_SPMV2(6) break;
     case 1: S3O_SPMV2(1) break;
     }
 #undef S3O_SPMV2
