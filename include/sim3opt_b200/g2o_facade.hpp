@@ -120,6 +120,7 @@ public:
     virtual void packEstimate(double *x) const = 0;
     virtual void unpackEstimate(const double *x) = 0;
     virtual bool packAux(double * /*q4*/) const { return false; }
+    virtual int baRole() const { return -1; }   // kind BA only: 0 = camera (pose), 1 = point (landmark)
 
 private:
     friend class SparseOptimizer;
@@ -187,6 +188,91 @@ protected:
     E measurement_;
     InformationType information_;
     ErrorVector error_;
+};
+
+// ---- g2o::SE3Quat (row a17): x -> r x + t, tangent [omega, upsilon] ---------------------------------
+class SE3Quat {
+public:
+    SE3Quat() {}
+    SE3Quat(const Quaternion &q, const Vector3 &t) : r_(q), t_(t) { normalizeRotation(); }
+    SE3Quat(const Matrix3 &R, const Vector3 &t) : r_(R), t_(t) { normalizeRotation(); }
+    const Quaternion &rotation() const { return r_; }
+    const Vector3 &translation() const { return t_; }
+    void setRotation(const Quaternion &q) { r_ = q; }
+    void setTranslation(const Vector3 &t) { t_ = t; }
+    Vector3 map(const Vector3 &xyz) const { return r_ * xyz + t_; }
+    SE3Quat inverse() const { const Quaternion ri = r_.conjugate(); return SE3Quat(ri, ri * (t_ * -1.0)); }
+    SE3Quat operator*(const SE3Quat &o) const { return SE3Quat(r_ * o.r_, r_ * o.t_ + t_); }
+    void normalizeRotation() {
+        if (r_.w() < 0) r_ = Quaternion(-r_.w(), -r_.x(), -r_.y(), -r_.z());
+        r_.normalize();
+    }
+    void pack(double *x) const { x[0] = r_.x(); x[1] = r_.y(); x[2] = r_.z(); x[3] = r_.w(); x[4] = t_[0]; x[5] = t_[1]; x[6] = t_[2]; }
+    static SE3Quat unpack(const double *x) { SE3Quat T; T.r_ = Quaternion(x[3], x[0], x[1], x[2]); T.t_ = Vector3(x[4], x[5], x[6]); return T; }
+
+private:
+    Quaternion r_;
+    Vector3 t_;
+};
+
+// ---- parameters (bal_example.cpp:90-96) -------------------------------------------------------------
+class Parameter {
+public:
+    virtual ~Parameter() {}
+    int id() const { return id_; }
+    void setId(int id) { id_ = id; }
+
+private:
+    int id_ = -1;
+};
+class CameraParameters : public Parameter {
+public:
+    CameraParameters() : focal_length(1.0), baseline(0.5) {}
+    CameraParameters(double f, const Matrix<double, 2, 1> &pp, double b) : focal_length(f), principle_point(pp), baseline(b) {}
+    Matrix<double, 2, 1> cam_map(const Vector3 &x) const {
+        Matrix<double, 2, 1> uv;
+        uv[0] = x[0] / x[2] * focal_length + principle_point[0];
+        uv[1] = x[1] / x[2] * focal_length + principle_point[1];
+        return uv;
+    }
+    double focal_length;
+    Matrix<double, 2, 1> principle_point;
+    double baseline;
+};
+
+// ---- BA vertex / edge types (bal_example.cpp:113,:121,:143) ----------------------------------------
+class VertexSE3Expmap : public BaseVertex<6, SE3Quat> {      // oplus: T <- exp(delta) T
+public:
+    int estimateDimension() const override { return 7; }
+    int s3oKind() const override { return S3O_KIND_BA; }
+    int baRole() const override { return 0; }
+    void packEstimate(double *x) const override { estimate_.pack(x); }
+    void unpackEstimate(const double *x) override { estimate_ = SE3Quat::unpack(x); }
+};
+class VertexSBAPointXYZ : public BaseVertex<3, Vector3> {     // oplus: p += delta
+public:
+    int estimateDimension() const override { return 3; }
+    int s3oKind() const override { return S3O_KIND_BA; }
+    int baRole() const override { return 1; }
+    void packEstimate(double *x) const override { for (int i = 0; i < 3; ++i) x[i] = estimate_[i]; }
+    void unpackEstimate(const double *x) override { for (int i = 0; i < 3; ++i) estimate_[i] = x[i]; }
+};
+// vertex(0) = point, vertex(1) = camera; e = z - cam_map(T.map(p))
+class EdgeProjectXYZ2UV : public BaseBinaryEdge<2, Matrix<double, 2, 1>, VertexSBAPointXYZ, VertexSE3Expmap> {
+public:
+    int s3oKind() const override { return S3O_KIND_BA; }
+    void packMeasurement(double *m) const override { m[0] = measurement_[0]; m[1] = measurement_[1]; }
+    void computeError() {      // host-side read-out (bal_example.cpp:162-165); the solve evaluates on the device
+        const VertexSE3Expmap *cam = static_cast<const VertexSE3Expmap *>(vertex(1));
+        const VertexSBAPointXYZ *pt = static_cast<const VertexSBAPointXYZ *>(vertex(0));
+        if (!cam || !pt || !camera_) return;
+        error_ = measurement_ - camera_->cam_map(cam->estimate().map(pt->estimate()));
+    }
+    const CameraParameters *cameraParameters() const { return camera_; }
+
+private:
+    friend class SparseOptimizer;
+    const CameraParameters *camera_ = nullptr;
 };
 
 // ---- solver plug-in slot (kitti_surf.cpp:553-557, :728-732; bal_example.cpp:73-83) --------------
@@ -261,7 +347,17 @@ public:
         if (problem_) s3o_destroy(problem_);
         for (auto &kv : vertices_) delete kv.second;
         for (Edge *e : edges_) delete e;
+        for (auto &kv : parameters_) delete kv.second;
         delete algorithm_;
+    }
+    bool addParameter(Parameter *prm) {                      // owned by the graph, as in g2o
+        if (!prm || prm->id() < 0 || parameters_.count(prm->id())) return false;
+        parameters_[prm->id()] = prm;
+        return true;
+    }
+    Parameter *parameter(int id) const {
+        auto it = parameters_.find(id);
+        return it == parameters_.end() ? nullptr : it->second;
     }
 
     void setAlgorithm(OptimizationAlgorithm *a) { if (a != algorithm_) delete algorithm_; algorithm_ = a; }
@@ -281,6 +377,10 @@ public:
         for (int i = 0; i < 2; ++i) {
             auto it = vertices_.find(e->vertex(i)->id());
             if (it == vertices_.end() || it->second != e->vertex(i)) return false;
+        }
+        if (auto *proj = dynamic_cast<EdgeProjectXYZ2UV *>(e)) {   // g2o resolves parameters in addEdge
+            proj->camera_ = dynamic_cast<const CameraParameters *>(parameter(e->parameterId()));
+            if (!proj->camera_) return false;
         }
         edges_.push_back(e);
         initialized_ = false;
@@ -316,6 +416,7 @@ public:
         if (problem_) { s3o_destroy(problem_); problem_ = nullptr; }
         if (s3o_create(kind, device_, &problem_) != S3O_OK) return fail(s3o_last_error());
         kind_ = kind;
+        if (kind == S3O_KIND_BA) return initializeBA();
         const int n = (int)vertices_.size();
         const Vertex *first = vertices_.begin()->second;
         est_dim_ = first->estimateDimension();
@@ -378,6 +479,7 @@ public:
         if (!initialized_ || !problem_) { error_ = "optimize: initializeOptimization() has not succeeded"; return -1; }
         if (iterations <= 0) return 0;
         if (!uploadEstimates()) return -1;
+        if (pcg_tol_ > 0) s3o_set_pcg(problem_, pcg_tol_, pcg_max_iter_);
         double tau = 1e-5, lam0 = 0;
         int max_trials = 10;
         if (algorithm_) { tau = algorithm_->tau(); lam0 = algorithm_->userLambdaInit(); max_trials = algorithm_->maxTrialsAfterFailure(); }
@@ -407,8 +509,14 @@ public:
     // computeActiveErrors + activeChi2 / activeRobustChi2 (kittiDetector.h:928-950 style read-outs)
     void computeActiveErrors() {
         if (!initialized_ || !uploadEstimates()) return;
-        std::vector<double> err((size_t)edges_.size() * dim_);
+        const int ed = kind_ == S3O_KIND_BA ? 2 : dim_;
+        std::vector<double> err((size_t)edges_.size() * ed);
         if (s3o_edge_errors(problem_, err.data()) != S3O_OK) { error_ = s3o_last_error(); return; }
+        if (kind_ == S3O_KIND_BA) {
+            for (size_t k = 0; k < edges_.size(); ++k) edges_[k]->unpackError(&err[k * 2]);
+            if (s3o_chi2(problem_, &chi2_) != S3O_OK) error_ = s3o_last_error();
+            return;
+        }
         for (size_t k = 0; k < edges_.size(); ++k) edges_[k]->unpackError(&err[k * dim_]);
         if (s3o_chi2(problem_, &chi2_) != S3O_OK) error_ = s3o_last_error();
     }
@@ -426,12 +534,73 @@ public:
 
 private:
     bool fail(const char *msg) { error_ = msg ? msg : "unknown error"; return false; }
+    // BA graph (bal_example.cpp:98-198): cameras and points in id order, observations in insertion order
+    bool initializeBA() {
+        order_.clear(); points_.clear(); dense_.clear();
+        for (auto &kv : vertices_) {
+            Vertex *v = kv.second;
+            if (v->baRole() == 0) { dense_[kv.first] = (int)order_.size(); order_.push_back(v); }
+            else if (v->baRole() == 1) { dense_[kv.first] = (int)points_.size(); points_.push_back(v); }
+            else return fail("initializeOptimization: unknown vertex type in a BA graph");
+        }
+        const int nc = (int)order_.size(), np = (int)points_.size(), ne = (int)edges_.size();
+        est_.assign((size_t)nc * 7, 0.0);
+        pts_.assign((size_t)np * 3, 0.0);
+        std::vector<uint8_t> cfix(nc), pfix(np);
+        for (int k = 0; k < nc; ++k) { order_[k]->packEstimate(&est_[(size_t)k * 7]); cfix[k] = order_[k]->fixed(); }
+        for (int k = 0; k < np; ++k) { points_[k]->packEstimate(&pts_[(size_t)k * 3]); pfix[k] = points_[k]->fixed(); }
+        std::vector<int32_t> oc(ne), op(ne);
+        std::vector<double> uv((size_t)ne * 2), info;
+        bool identity = true;
+        for (Edge *e : edges_) identity = identity && e->informationIsIdentity();
+        if (!identity) info.resize((size_t)ne * 3);
+        const RobustKernel *rk = nullptr;
+        const CameraParameters *cam = nullptr;
+        for (int k = 0; k < ne; ++k) {
+            Edge *e = edges_[k];
+            if (e->vertex(0)->baRole() != 1 || e->vertex(1)->baRole() != 0) return fail("initializeOptimization: EdgeProjectXYZ2UV needs vertex(0) = point, vertex(1) = camera");
+            op[k] = dense_[e->vertex(0)->id()];
+            oc[k] = dense_[e->vertex(1)->id()];
+            e->packMeasurement(&uv[(size_t)k * 2]);
+            if (!identity) { double m[4]; e->packInformation(m); info[(size_t)k * 3] = m[0]; info[(size_t)k * 3 + 1] = m[1]; info[(size_t)k * 3 + 2] = m[3]; }
+            if (e->robustKernel()) rk = e->robustKernel();
+            if (auto *proj = dynamic_cast<EdgeProjectXYZ2UV *>(e)) cam = proj->cameraParameters();
+        }
+        if (!cam) return fail("initializeOptimization: no CameraParameters (addParameter + setParameterId)");
+        if (s3o_ba_set_cameras(problem_, nc, est_.data(), cfix.data()) != S3O_OK ||
+            s3o_ba_set_points(problem_, np, pts_.data(), pfix.data()) != S3O_OK ||
+            s3o_ba_set_observations(problem_, ne, oc.data(), op.data(), uv.data(), identity ? nullptr : info.data()) != S3O_OK ||
+            s3o_ba_set_intrinsics(problem_, cam->focal_length, cam->principle_point[0], cam->principle_point[1]) != S3O_OK)
+            return fail(s3o_last_error());
+        if (rk && s3o_set_robust(problem_, rk->s3oKind(), rk->delta()) != S3O_OK) return fail(s3o_last_error());
+        if (pcg_tol_ > 0) s3o_set_pcg(problem_, pcg_tol_, pcg_max_iter_);
+        int nf = 0, nb = 0;
+        if (s3o_build_structure(problem_, &nf, &nb) != S3O_OK) return fail(s3o_last_error());
+        int hc = 0, hp = 0;      // free cameras numbered first, then the marginalised points
+        for (Vertex *v : order_) v->hessian_index_ = v->fixed() ? -1 : hc++;
+        for (Vertex *v : points_) v->hessian_index_ = v->fixed() ? -1 : hc + hp++;
+        est_dim_ = 7; dim_ = 6; n_free_ = nf; n_blocks_ = nb;
+        initialized_ = true;
+        return true;
+    }
     bool uploadEstimates() {
+        if (kind_ == S3O_KIND_BA) {
+            for (size_t k = 0; k < order_.size(); ++k) order_[k]->packEstimate(&est_[k * 7]);
+            for (size_t k = 0; k < points_.size(); ++k) points_[k]->packEstimate(&pts_[k * 3]);
+            if (s3o_ba_set_estimates(problem_, est_.data(), pts_.data()) != S3O_OK) { error_ = s3o_last_error(); return false; }
+            return true;
+        }
         for (size_t k = 0; k < order_.size(); ++k) order_[k]->packEstimate(&est_[k * est_dim_]);
         if (s3o_set_estimates(problem_, est_.data()) != S3O_OK) { error_ = s3o_last_error(); return false; }
         return true;
     }
     bool downloadEstimates() {
+        if (kind_ == S3O_KIND_BA) {
+            if (s3o_ba_get_cameras(problem_, est_.data()) != S3O_OK || s3o_ba_get_points(problem_, pts_.data()) != S3O_OK) { error_ = s3o_last_error(); return false; }
+            for (size_t k = 0; k < order_.size(); ++k) if (!order_[k]->fixed()) order_[k]->unpackEstimate(&est_[k * 7]);
+            for (size_t k = 0; k < points_.size(); ++k) if (!points_[k]->fixed()) points_[k]->unpackEstimate(&pts_[k * 3]);
+            return true;
+        }
         if (s3o_get_vertices(problem_, est_.data()) != S3O_OK) { error_ = s3o_last_error(); return false; }
         for (size_t k = 0; k < order_.size(); ++k)
             if (!order_[k]->fixed()) order_[k]->unpackEstimate(&est_[k * est_dim_]);
@@ -442,9 +611,10 @@ private:
     EdgeContainer edges_;
     OptimizationAlgorithm *algorithm_ = nullptr;
     s3o_problem *problem_ = nullptr;
-    std::vector<Vertex *> order_;
+    std::vector<Vertex *> order_, points_;      // pose-graph vertices or BA cameras; BA points
     std::map<int, int> dense_;
-    std::vector<double> est_, hist_;
+    std::map<int, Parameter *> parameters_;
+    std::vector<double> est_, pts_, hist_;
     std::string error_;
     bool verbose_ = false, initialized_ = false;
     int device_ = 0, kind_ = 0, est_dim_ = 0, dim_ = 0, n_free_ = 0, n_blocks_ = 0;

@@ -177,3 +177,19 @@ def ba_loop(n_cams=1000, n_points=500000, obs_per_point=10, seed=42, loop_length
     pts = pts_gt + rng.standard_normal(pts_gt.shape) * point_pert
     return dict(cams=cams, points=pts, cams_gt=cams_gt, points_gt=pts_gt, obs_cam=obs_cam.astype(np.int32),
                 obs_pt=obs_pt.astype(np.int32), uv=uv, focal=focal, cx=cx, cy=cy)
+
+
+def write_bal(path, g):
+    """Writes a ba_loop() problem in the text layout ba_demo reads (bal_example.cpp:104-194): header,
+    observations "cam point u v", 9 numbers per camera (angle-axis, t, f, k1, k2), points; %.17g."""
+    rot = Rotation.from_quat(g["cams"][:, :4]).as_rotvec()
+    with open(path, "w") as f:
+        f.write(f"{len(g['cams'])} {len(g['points'])} {len(g['uv'])}\n")
+        for c, p, (u, v) in zip(g["obs_cam"], g["obs_pt"], g["uv"]):
+            f.write(f"{c} {p} {u:.17g} {v:.17g}\n")
+        for aa, cam in zip(rot, g["cams"]):
+            for x in list(aa) + list(cam[4:7]) + [g["focal"], 0.0, 0.0]:
+                f.write(f"{x:.17g}\n")
+        for pt in g["points"]:
+            for x in pt:
+                f.write(f"{x:.17g}\n")

@@ -15,6 +15,7 @@ import pytest
 from conftest import KITTI_DIR, ROOT, make_gpu, make_oracle
 
 BIN = os.path.join(ROOT, "examples", "bin", "kitti_pgo")
+BA_BIN = os.path.join(ROOT, "examples", "bin", "ba_demo")
 
 
 @pytest.fixture(scope="module")
@@ -129,3 +130,30 @@ def test_scale_null_vector_matches_dense_svd(kitti_k1, kitti_k118):
         assert np.abs(x - ref).max() <= 1e-6 * np.abs(ref).max()
         assert abs(np.sqrt(max(lmin, 0)) - sv[-1]) <= 1e-6 * sv[0]
         assert abs(np.sqrt(lmax) - sv[0]) <= 0.05 * sv[0]
+
+
+@pytest.mark.gpu
+def test_ba_demo_matches_oracle(kitti_pgo, tmp_path):
+    """examples/ba_demo.cpp (bal_example.cpp:44-243 through the facade) on a synthetic BAL file."""
+    from oracle import oracle as orc
+    from sim3opt_b200 import synth
+    g = synth.ba_loop(30, 900, 6, seed=21)
+    bal = str(tmp_path / "problem.txt")
+    synth.write_bal(bal, g)
+    out_file = str(tmp_path / "cams.txt")
+    out = run(BA_BIN, "-i", "8", "-o", out_file, "-v", bal)
+    cpu = orc.BAProblem()
+    cpu.set(g["cams"], g["points"], g["obs_cam"], g["obs_pt"], g["uv"], g["focal"], g["cx"], g["cy"])
+    cpu.set_robust(1, 2.5)
+    cpu.build_structure()
+    chi0 = cpu.chi2()
+    assert abs(float(re.search(r"initial chi2 (\S+)", out).group(1)) - chi0) <= 1e-9 * chi0
+    assert f"free cameras 30 schur blocks {cpu.nb}" in out
+    n, chi2, lam, hist = cpu.optimize(8)
+    m = re.search(r"iterations (\d+) chi2_final (\S+)", out)
+    assert int(m.group(1)) == n and abs(float(m.group(2)) - chi2) <= 1e-5 * chi2
+    res = read_result(out_file)                      # id, t_c_in_w, q_c2w (xyzw)
+    cams = cpu.cameras()
+    for k in (0, 13, 29):
+        R = orc.quat_to_rot(cams[k, :4])
+        assert np.abs(res[k, 1:4] - (-R.T @ cams[k, 4:7])).max() <= 1e-4
