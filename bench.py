@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--workload", default="s1m", choices=sorted(WORKLOADS))
     ap.add_argument("--pcg-tol", type=float, default=1e-3)
     ap.add_argument("--pcg-max-iter", type=int, default=2000)
+    ap.add_argument("--precond", default="auto", choices=["auto", "block-jacobi", "multilevel"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=42)
     return ap.parse_args()
@@ -206,6 +207,11 @@ def run_ours(args):
     prob.set_math_mode(s3.MATH_CORRECTED)
     prob.set_jacobian_mode(s3.JAC_ANALYTIC)
     prob.set_pcg(args.pcg_tol, args.pcg_max_iter)
+    precond = {"auto": s3.PRECOND_AUTO, "block-jacobi": s3.PRECOND_BLOCK_JACOBI, "multilevel": s3.PRECOND_MULTILEVEL}[args.precond]
+    if world > 1:
+        precond = s3.PRECOND_BLOCK_JACOBI        # the multilevel correction is single-GPU so far
+    prob.set_preconditioner(precond)
+    multilevel = precond == s3.PRECOND_MULTILEVEL or (precond == s3.PRECOND_AUTO and world == 1 and nv >= 20000)
     if world > 1:
         # vertex-range partition: rank 0 creates the NCCL id, every rank joins before set_edges
         box = [s3.comm_unique_id() if rank == 0 else None]
@@ -236,6 +242,7 @@ def run_ours(args):
             self.last_chi = None
             self.solves = []
             self.cur = []
+            self.trace = []          # per step: [chi2, lambda, trials, rho, pcg iterations]
 
         def step(self):
             if self.in_solve == 0:
@@ -243,6 +250,7 @@ def run_ours(args):
             n, chi2, lam, hist = prob.optimize(1, 0.0)
             self.in_solve += 1
             self.cur.append(chi2)
+            self.trace.append([float(v) for v in np.asarray(hist).reshape(-1)[:5]])
             conv = False
             if self.last_chi is not None and chi2 > 0:
                 gain = (self.last_chi - chi2) / chi2
@@ -256,7 +264,7 @@ def run_ours(args):
     drv = Driver()
     for _ in range(args.warmup):
         drv.step()
-    drv.in_solve, drv.last_chi, drv.cur = 0, None, []       # timed region starts a fresh solve
+    drv.in_solve, drv.last_chi, drv.cur, drv.trace = 0, None, [], []   # timed region starts a fresh solve
 
     prob.reset_stats()
     sampler = ClockSampler(local_rank)
@@ -289,6 +297,7 @@ def run_ours(args):
     e2e_steps = args.steps
     prob.set_lm_resume(2)                   # keep lambda/nu across the host round trip of the estimates
     in_solve, last_chi = 0, None
+    e2e_trace = []
     barrier()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
@@ -299,6 +308,7 @@ def run_ours(args):
             prob.set_estimates(est_np)
         n_, chi2_, lam_, _h = prob.optimize(1, 0.0)
         prob.vertices(out=est_np)           # D2H of the step's result
+        e2e_trace.append([float(v) for v in np.asarray(_h).reshape(-1)[:5]] + [time.perf_counter() - t0])
         in_solve += 1
         conv = last_chi is not None and chi2_ > 0 and 0 <= (last_chi - chi2_) / chi2_ < STOP_REL_GAIN
         last_chi = chi2_
@@ -325,7 +335,7 @@ def run_ours(args):
     # (partitioned solve: the launch on one rank covers that rank's rows and blocks only)
     nb_l, nf_l = (nb, nf) if world == 1 else (st["n_blocks"], -(-nf // world))
     bytes_spmv = 392 * nb_l + 4 * nb_l + 4 * (nf_l + 1) + 2 * 56 * nf_l
-    roof = {"bound": "hbm", "kernel": "spmv3_kernel<7,128,112> (TMA ring)", "achieved": None, "peak": peak, "unit": "GB/s",
+    roof = {"bound": "hbm", "kernel": "spmv4_kernel<7,128,112,2> (TMA ring, prefetch pipeline)", "achieved": None, "peak": peak, "unit": "GB/s",
             "frac": None, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_spmv}
     if st["n_spmv_sampled"] > 0:
         avg_ms = st["ms_spmv_sampled"] / st["n_spmv_sampled"]
@@ -357,7 +367,8 @@ def run_ours(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.workload}: synthetic Sim3 sphere pose graph, {nv} poses / {ne} edges, seed {args.seed}",
                    "free_vertices": nf, "hessian_blocks": nb, "block_dim": 7, "jacobians": "analytic",
-                   "linear_solver": f"block-Jacobi PCG rel_tol={args.pcg_tol} max_iter={args.pcg_max_iter}",
+                   "linear_solver": ("multilevel (aggregation + block-Jacobi)" if multilevel else "block-Jacobi")
+                                    + f" PCG rel_tol={args.pcg_tol} max_iter={args.pcg_max_iter}",
                    "math_mode": "corrected", "l2_policy": "inputs larger than L2 (Hessian blocks %.2f GB)" % (392 * nb / 1e9),
                    "step": "one LM iteration; solves restart from a device snapshot on the 1e-6 gain rule",
                    "partition": "none" if world == 1 else f"vertex range over {world} ranks, NCCL halo + all-reduce"},
@@ -370,6 +381,7 @@ def run_ours(args):
         "pcg_iterations": int(st["pcg_iterations"]), "lm_trials": int(st["lm_trials"]),
         "phase_ms": {"linearize": st["ms_linearize"], "solve": st["ms_solve"], "update_chi2": st["ms_update"]},
         "solves_completed": len(drv.solves),
+        "step_trace": drv.trace, "e2e_step_trace": e2e_trace,
         "chi2_history_first_solve": drv.solves[0] if drv.solves else drv.cur,
     }
     sys.stdout.flush()

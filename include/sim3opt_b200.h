@@ -62,6 +62,12 @@ enum s3o_robust { S3O_ROBUST_NONE = 0, S3O_ROBUST_HUBER = 1, S3O_ROBUST_PTAM_TUK
  * rotation drops below 4.5e-3 rad while sigma != 0; graphs that must converge to a minimum
  * (the synthetic configs) are run in CORRECTED mode on both the CPU and the GPU side. */
 enum s3o_math_mode { S3O_MATH_REFERENCE = 0, S3O_MATH_CORRECTED = 1 };
+/* Preconditioner of the PCG that stands in for LinearSolverEigen::solve [EXT g2o] (the plug-in slot
+ * filled at kitti_surf.cpp:553-558).  BLOCK_JACOBI: (H_ii + lambda I)^-1 per vertex.  MULTILEVEL:
+ * block-Jacobi plus an aggregation coarse-space correction on the gauge near-null space
+ * delta_i = Ad(S_i S_root^-1) xi (Sim3 problems on one GPU).  AUTO (default): MULTILEVEL for Sim3
+ * graphs with >= 20000 free vertices on one GPU, BLOCK_JACOBI otherwise. */
+enum s3o_preconditioner { S3O_PRECOND_AUTO = 0, S3O_PRECOND_BLOCK_JACOBI = 1, S3O_PRECOND_MULTILEVEL = 2 };
 /* g2o OptimizationAlgorithm::SolverResult */
 enum s3o_solver_result { S3O_RESULT_TERMINATE = 2, S3O_RESULT_OK = 1, S3O_RESULT_FAIL = -1 };
 
@@ -110,6 +116,7 @@ int s3o_set_math_mode(s3o_problem *p, int mode);
 int s3o_set_lm(s3o_problem *p, double tau, double user_lambda_init, int max_trials);
 /* block-Jacobi PCG: relative residual tolerance |r|/|b| and iteration cap */
 int s3o_set_pcg(s3o_problem *p, double rel_tol, int max_iter);
+int s3o_set_preconditioner(s3o_problem *p, int kind /* s3o_preconditioner */);
 
 /* ---- structure (replaces initializeOptimization + BlockSolver::buildStructure) -------- */
 int s3o_build_structure(s3o_problem *p, int *n_free, int *n_blocks);
@@ -123,6 +130,12 @@ int s3o_get_hessian_index(s3o_problem *p, int32_t *hidx);
  * ints (upper bounds); hidx (may be NULL) n_vertices ints. */
 int s3o_host_structure(int n_vertices, const uint8_t *fixed, int n_edges, const int32_t *v0, const int32_t *v1,
                        int *n_free, int *n_blocks, int32_t *colptr, int32_t *rowidx, int32_t *hidx);
+
+/* Host-only view of the aggregation hierarchy the MULTILEVEL preconditioner builds for a graph:
+ * n_levels coarse levels, their vertex and (full-pattern) block counts (first `cap` entries), and
+ * the aggregate of every free vertex on the finest level (aggregate0: n_free ints, may be NULL). */
+int s3o_host_multilevel(int n_vertices, const uint8_t *fixed, int n_edges, const int32_t *v0, const int32_t *v1,
+                        int cap, int *n_levels, int32_t *level_vertices, int32_t *level_blocks, int32_t *aggregate0);
 
 /* ---- lock-step pieces (each mirrors one g2o step; used by the parity tests) ------------ */
 int s3o_chi2(s3o_problem *p, double *chi2);                 /* computeActiveErrors + activeRobustChi2 */

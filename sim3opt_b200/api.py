@@ -12,6 +12,7 @@ from . import _lib
 KIND_SIM3, KIND_SCALE_TRANS, KIND_SCALE, KIND_BA = 0, 1, 2, 3
 JAC_NUMERIC, JAC_ANALYTIC = 0, 1
 MATH_REFERENCE, MATH_CORRECTED = 0, 1
+PRECOND_AUTO, PRECOND_BLOCK_JACOBI, PRECOND_MULTILEVEL = 0, 1, 2
 ROBUST_NONE, ROBUST_HUBER, ROBUST_PTAM_TUKEY, ROBUST_PTAM_CAUCHY, ROBUST_PTAM_HUBER, ROBUST_PTAM_LS = range(6)
 
 _EST_DIM = {KIND_SIM3: 8, KIND_SCALE_TRANS: 4, KIND_SCALE: 1, KIND_BA: 7}
@@ -102,6 +103,7 @@ class Problem:
     def set_math_mode(self, mode): self._check(self.L.s3o_set_math_mode(self.h, int(mode)))
     def set_lm(self, tau=0.0, lambda_init=0.0, max_trials=0): self._check(self.L.s3o_set_lm(self.h, tau, lambda_init, max_trials))
     def set_pcg(self, rel_tol=0.0, max_iter=0): self._check(self.L.s3o_set_pcg(self.h, rel_tol, max_iter))
+    def set_preconditioner(self, kind): self._check(self.L.s3o_set_preconditioner(self.h, int(kind)))
 
     # ---- structure ---------------------------------------------------------------
     def build_structure(self):
@@ -239,6 +241,24 @@ def host_partition(n_vertices, fixed, v0, v1, rank, world):
     return dict(n_own=n_own, n_ghost=n_ghost, n_local_edges=n_local, n_primary=n_primary,
                 ghosts=ghosts[:n_ghost].copy(), send_count=send_count, recv_count=recv_count,
                 send_idx=send_idx[:int(send_count.sum())].copy())
+
+
+def host_multilevel(n_vertices, fixed, v0, v1):
+    """Aggregation hierarchy of the multilevel preconditioner (host only): per-level vertex counts,
+    per-level block counts, and the finest-level aggregate of every free vertex."""
+    L = _lib.load()
+    v0 = np.ascontiguousarray(v0, np.int32)
+    v1 = np.ascontiguousarray(v1, np.int32)
+    fx = np.zeros(n_vertices, np.uint8) if fixed is None else np.ascontiguousarray(fixed, np.uint8)
+    nl = C.c_int(0)
+    nvert, nblk = np.zeros(16, np.int32), np.zeros(16, np.int32)
+    agg = np.full(max(int((fx == 0).sum()), 1), -1, np.int32)
+    rc = L.s3o_host_multilevel(n_vertices, fx.ctypes.data_as(_up), len(v0), v0.ctypes.data_as(_ip),
+                               v1.ctypes.data_as(_ip), 16, C.byref(nl), nvert.ctypes.data_as(_ip),
+                               nblk.ctypes.data_as(_ip), agg.ctypes.data_as(_ip))
+    if rc != 0:
+        raise S3OError(f"s3o error {rc}: {L.s3o_last_error().decode()}")
+    return nvert[:nl.value].copy(), nblk[:nl.value].copy(), agg[:int((fx == 0).sum())]
 
 
 def host_structure(n_vertices, fixed, v0, v1):

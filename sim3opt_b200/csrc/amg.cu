@@ -1,0 +1,644 @@
+// amg.cu -- multilevel preconditioner of the Sim3 pose-graph PCG: device side (see amg.h).
+//
+// Values flow per LM trial:   frames (per linearisation)  ->  Galerkin operators level by level
+// ->  block-Jacobi inverses per level  ->  dense inverse of the coarsest level.
+// Per PCG iteration:          restriction of r  ->  V(1,1)-cycle on the coarse levels  ->
+//                             z = D^-1 r + P0 x_1,  r.z  and the PCG scalar bookkeeping.
+// All sums run in list order (no atomics), so a solve is bitwise reproducible.
+#include "amg.h"
+#include "problem.h"
+#include "reduce.cuh"
+#include "sim3_math.cuh"
+
+namespace s3o {
+
+namespace {
+
+constexpr int D = 7, DD = 49, NREL = 13;
+constexpr int kCoarsestMax = 16;        // dense inverse held in shared memory: (16*7)^2 doubles = 98 KB
+constexpr int kMaxLevels = 12;
+constexpr double kOmega = 0.7;          // damping of the block-Jacobi smoother on the coarse levels
+
+struct LevelDev {       // transfer level l -> l+1 plus operator and vectors of level l+1
+    int n_fine = 0, n = 0, nblk = 0, nub = 0, pad_fine = 0;
+    int32_t *agg = nullptr, *mem_ptr = nullptr, *mem_idx = nullptr, *vid = nullptr;
+    int32_t *rowptr = nullptr, *colidx = nullptr, *blk_row = nullptr, *dpos = nullptr;
+    int32_t *gal_ptr = nullptr, *gal_ent = nullptr, *gal_i = nullptr, *gal_j = nullptr, *gal_out = nullptr, *gal_mirror = nullptr;
+    double *rel = nullptr;      // [13][pad_fine]: R (row-major), t, s of S_i S_root^-1 for every level-l vertex
+    double *A = nullptr, *Dinv = nullptr, *r = nullptr, *x = nullptr, *x2 = nullptr, *t = nullptr;
+};
+
+}  // namespace
+
+struct AmgState {
+    std::vector<AmgHostLevel> host;
+    std::vector<LevelDev> lev;
+    int32_t *d_vid0 = nullptr;      // level-0 vertex ids (free2v)
+    int32_t *d_blk_row0 = nullptr;  // borrowed from the problem
+    double *d_dense = nullptr;      // inverse of the coarsest operator, [N][N]
+    bool dense = false;
+    bool frames_valid = false;
+};
+
+namespace {
+
+struct Rel { double R[9], t[3], s; };
+
+__device__ __forceinline__ Rel load_rel(const double *__restrict__ rel, int pad, int i) {
+    Rel r;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) r.R[k] = __ldg(rel + (size_t)k * pad + i);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) r.t[k] = __ldg(rel + (size_t)(9 + k) * pad + i);
+    r.s = __ldg(rel + (size_t)12 * pad + i);
+    return r;
+}
+
+// out = Ad(S) v,  Ad(S) = [[R,0,0],[[t]x R, sR, -t],[0,0,1]]  on tangents [omega, upsilon, sigma]
+__device__ __forceinline__ void ad_apply(const Rel &S, const double v[7], double out[7]) {
+    double a[3], b[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        a[r] = S.R[r * 3] * v[0] + S.R[r * 3 + 1] * v[1] + S.R[r * 3 + 2] * v[2];
+        b[r] = S.R[r * 3] * v[3] + S.R[r * 3 + 1] * v[4] + S.R[r * 3 + 2] * v[5];
+    }
+    out[0] = a[0]; out[1] = a[1]; out[2] = a[2];
+    out[3] = (S.t[1] * a[2] - S.t[2] * a[1]) + S.s * b[0] - S.t[0] * v[6];
+    out[4] = (S.t[2] * a[0] - S.t[0] * a[2]) + S.s * b[1] - S.t[1] * v[6];
+    out[5] = (S.t[0] * a[1] - S.t[1] * a[0]) + S.s * b[2] - S.t[2] * v[6];
+    out[6] = v[6];
+}
+
+// out = Ad(S)^T w:  [R^T (a + b x t);  s R^T b;  c - t.b]   for w = [a, b, c]
+__device__ __forceinline__ void adT_apply(const Rel &S, const double w[7], double out[7]) {
+    const double u0 = w[0] + (w[4] * S.t[2] - w[5] * S.t[1]);
+    const double u1 = w[1] + (w[5] * S.t[0] - w[3] * S.t[2]);
+    const double u2 = w[2] + (w[3] * S.t[1] - w[4] * S.t[0]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        out[c] = S.R[c] * u0 + S.R[3 + c] * u1 + S.R[6 + c] * u2;
+        out[3 + c] = S.s * (S.R[c] * w[3] + S.R[3 + c] * w[4] + S.R[6 + c] * w[5]);
+    }
+    out[6] = w[6] - (S.t[0] * w[3] + S.t[1] * w[4] + S.t[2] * w[5]);
+}
+
+// ---- frames: rel_i = S_i S_root(i)^-1 --------------------------------------------------------
+__global__ void amg_rel_kernel(const double *__restrict__ est, int nv_pad, const int32_t *__restrict__ vid_fine,
+                               const int32_t *__restrict__ agg, const int32_t *__restrict__ vid_coarse, int n_fine,
+                               int pad, double *__restrict__ rel) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_fine) return;
+    const int vi = vid_fine[i], vr = vid_coarse[agg[i]];
+    Sim3 Si, Sr;
+    Si.qx = est[vi]; Si.qy = est[(size_t)nv_pad + vi]; Si.qz = est[(size_t)2 * nv_pad + vi]; Si.qw = est[(size_t)3 * nv_pad + vi];
+    Si.tx = est[(size_t)4 * nv_pad + vi]; Si.ty = est[(size_t)5 * nv_pad + vi]; Si.tz = est[(size_t)6 * nv_pad + vi];
+    Si.s = est[(size_t)7 * nv_pad + vi];
+    Sr.qx = est[vr]; Sr.qy = est[(size_t)nv_pad + vr]; Sr.qz = est[(size_t)2 * nv_pad + vr]; Sr.qw = est[(size_t)3 * nv_pad + vr];
+    Sr.tx = est[(size_t)4 * nv_pad + vr]; Sr.ty = est[(size_t)5 * nv_pad + vr]; Sr.tz = est[(size_t)6 * nv_pad + vr];
+    Sr.s = est[(size_t)7 * nv_pad + vr];
+    const Sim3 S = sim3_mul(Si, sim3_inv(Sr));
+    double R[9];
+    const double qn = 1.0 / sqrt(S.qx * S.qx + S.qy * S.qy + S.qz * S.qz + S.qw * S.qw);
+    quat_to_rot(S.qx * qn, S.qy * qn, S.qz * qn, S.qw * qn, R);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) rel[(size_t)k * pad + i] = R[k];
+    rel[(size_t)9 * pad + i] = S.tx; rel[(size_t)10 * pad + i] = S.ty; rel[(size_t)11 * pad + i] = S.tz;
+    rel[(size_t)12 * pad + i] = S.s;
+}
+
+// ---- Galerkin product: one 8-lane group per upper coarse block, lane c holds column c --------
+// Entry lists carry (block | flag, row vertex, column vertex) so the only dependent loads per
+// entry are the frames and the block itself; the next entry's indices are fetched one step ahead.
+template <bool FINE_UPPER>
+__global__ void __launch_bounds__(128, 4) amg_galerkin_kernel(const double *__restrict__ Af, const int32_t *__restrict__ gal_i,
+                                                              const int32_t *__restrict__ gal_j, const double *__restrict__ rel,
+                                                              int pad, double lambda, int nub,
+                                                              const int32_t *__restrict__ gal_ptr, const int32_t *__restrict__ gal_ent,
+                                                              const int32_t *__restrict__ gal_out,
+                                                              const int32_t *__restrict__ gal_mirror, double *__restrict__ Ac) {
+    const int ub = blockIdx.x * (blockDim.x / 8) + threadIdx.x / 8;
+    const int c = threadIdx.x & 7;
+    if (ub >= nub || c >= D) return;
+    double acc[D];
+#pragma unroll
+    for (int r = 0; r < D; ++r) acc[r] = 0;
+    double ec[D];
+#pragma unroll
+    for (int r = 0; r < D; ++r) ec[r] = (r == c) ? 1.0 : 0.0;
+    const int ebeg = gal_ptr[ub], eend = gal_ptr[ub + 1];
+    int ent = 0, i = 0, j = 0;
+    if (ebeg < eend) { ent = __ldg(gal_ent + ebeg); i = __ldg(gal_i + ebeg); j = __ldg(gal_j + ebeg); }
+    for (int e = ebeg; e < eend; ++e) {
+        const int k = ent >> 2, flag = ent & 3;
+        const int ci = i, cj = j;
+        if (e + 1 < eend) { ent = __ldg(gal_ent + e + 1); i = __ldg(gal_i + e + 1); j = __ldg(gal_j + e + 1); }
+        const Rel ri = load_rel(rel, pad, ci);
+        const Rel rj = (ci == cj) ? ri : load_rel(rel, pad, cj);
+        const double *A = Af + (size_t)k * DD;
+        double v[D], w[D], u[D];
+        if (flag != 1) {        // column c of P_i^T A P_j
+            ad_apply(rj, ec, v);
+#pragma unroll
+            for (int r = 0; r < D; ++r) {
+                double a = 0;
+#pragma unroll
+                for (int q = 0; q < D; ++q) a += __ldg(A + r * D + q) * v[q];
+                w[r] = a;
+            }
+            if (FINE_UPPER && ci == cj) {
+#pragma unroll
+                for (int r = 0; r < D; ++r) w[r] += lambda * v[r];
+            }
+            adT_apply(ri, w, u);
+#pragma unroll
+            for (int r = 0; r < D; ++r) acc[r] += u[r];
+        }
+        if (flag != 0) {        // column c of P_j^T A^T P_i
+            ad_apply(ri, ec, v);
+#pragma unroll
+            for (int r = 0; r < D; ++r) {
+                double a = 0;
+#pragma unroll
+                for (int q = 0; q < D; ++q) a += __ldg(A + q * D + r) * v[q];
+                w[r] = a;
+            }
+            adT_apply(rj, w, u);
+#pragma unroll
+            for (int r = 0; r < D; ++r) acc[r] += u[r];
+        }
+    }
+    double *out = Ac + (size_t)gal_out[ub] * DD;
+#pragma unroll
+    for (int r = 0; r < D; ++r) out[r * D + c] = acc[r];
+    const int m = gal_mirror[ub];
+    if (m >= 0) {
+        double *om = Ac + (size_t)m * DD;
+#pragma unroll
+        for (int r = 0; r < D; ++r) om[c * D + r] = acc[r];
+    }
+}
+
+// ---- dense inverse of the coarsest operator (one CTA, matrix in shared memory) -----------------
+__global__ void __launch_bounds__(256) amg_dense_inverse_kernel(const double *__restrict__ A, const int32_t *__restrict__ rowptr,
+                                                                const int32_t *__restrict__ colidx, int n,
+                                                                double *__restrict__ inv, DevScalars *sc) {
+    extern __shared__ double a[];
+    const int N = n * D;
+    double *col = a + N * N;
+    for (int t = threadIdx.x; t < N * N; t += blockDim.x) a[t] = 0;
+    __syncthreads();
+    for (int I = 0; I < n; ++I)
+        for (int k = rowptr[I]; k < rowptr[I + 1]; ++k) {
+            const int J = colidx[k];
+            for (int t = threadIdx.x; t < DD; t += blockDim.x) a[(I * D + t / D) * N + J * D + t % D] = A[(size_t)k * DD + t];
+        }
+    __syncthreads();
+    for (int k = 0; k < N; ++k) {       // in-place Gauss-Jordan, no pivoting (SPD)
+        for (int t = threadIdx.x; t < N; t += blockDim.x) col[t] = a[t * N + k];
+        __syncthreads();
+        double piv = col[k];
+        if (!(piv > 0)) { piv = 1; if (threadIdx.x == 0) sc->precond_fail = 1; }
+        const double ip = 1.0 / piv;
+        for (int t = threadIdx.x; t < N; t += blockDim.x) a[k * N + t] = (t == k) ? ip : a[k * N + t] * ip;
+        __syncthreads();
+        for (int t = threadIdx.x; t < N * N; t += blockDim.x) {
+            const int i = t / N, j = t - i * N;
+            if (i == k) continue;
+            a[t] = (j == k) ? -col[i] * ip : a[t] - col[i] * a[k * N + j];
+        }
+        __syncthreads();
+    }
+    for (int t = threadIdx.x; t < N * N; t += blockDim.x) inv[t] = a[t];
+}
+
+// ---- coarse-level row kernels: an 8-lane group owns one block row, lane l one component ---------
+// mode 0: x_out = omega Dinv r                      (first smoothing sweep from x = 0)
+// mode 1: t_out = r - A x                           (residual)
+// mode 2: x_out = x + omega Dinv (r - A x)          (smoothing sweep)
+template <int MODE>
+__global__ void __launch_bounds__(128) amg_row_kernel(int n, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+                                                      const double *__restrict__ A, const double *__restrict__ Dinv,
+                                                      const double *__restrict__ r, const double *__restrict__ x,
+                                                      double *__restrict__ out, double omega, const DevScalars *sc,
+                                                      int check_done) {
+    if (check_done && sc->done) return;
+    const int i = blockIdx.x * (blockDim.x / 8) + threadIdx.x / 8;
+    const int l = threadIdx.x & 7;
+    const bool act = i < n && l < D;
+    double res = act ? r[(size_t)i * D + l] : 0.0;
+    if (MODE != 0 && act) {
+        double acc = 0;
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            const double *xj = x + (size_t)colidx[k] * D;
+            const double *Ak = A + (size_t)k * DD + l * D;
+#pragma unroll
+            for (int c = 0; c < D; ++c) acc += Ak[c] * xj[c];
+        }
+        res -= acc;
+    }
+    if (MODE == 1) {
+        if (act) out[(size_t)i * D + l] = res;
+        return;
+    }
+    double z = 0;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        const double rc = __shfl_sync(0xffffffffu, res, c, 8);
+        if (act) z += Dinv[(size_t)i * DD + l * D + c] * rc;
+    }
+    if (act) out[(size_t)i * D + l] = (MODE == 2 ? x[(size_t)i * D + l] : 0.0) + omega * z;
+}
+
+// ---- transfers ---------------------------------------------------------------------------------
+// r_coarse[I] = sum over members i of Ad(rel_i)^T t_i   (members ascending)
+__global__ void __launch_bounds__(128) amg_restrict_kernel(int n, const int32_t *__restrict__ mem_ptr,
+                                                           const int32_t *__restrict__ mem_idx, const double *__restrict__ rel,
+                                                           int pad, const double *__restrict__ t, double *__restrict__ rc,
+                                                           const DevScalars *sc, int check_done) {
+    if (check_done && sc->done) return;
+    const int I = blockIdx.x * blockDim.x + threadIdx.x;
+    if (I >= n) return;
+    double acc[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) acc[c] = 0;
+    for (int m = mem_ptr[I]; m < mem_ptr[I + 1]; ++m) {
+        const int i = mem_idx[m];
+        const Rel S = load_rel(rel, pad, i);
+        double w[D], u[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) w[c] = t[(size_t)i * D + c];
+        adT_apply(S, w, u);
+#pragma unroll
+        for (int c = 0; c < D; ++c) acc[c] += u[c];
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c) rc[(size_t)I * D + c] = acc[c];
+}
+
+// x_i += Ad(rel_i) xc[agg_i]
+__global__ void __launch_bounds__(128) amg_prolong_kernel(int n_fine, const int32_t *__restrict__ agg, const double *__restrict__ rel,
+                                                          int pad, const double *__restrict__ xc, double *__restrict__ x,
+                                                          const DevScalars *sc, int check_done) {
+    if (check_done && sc->done) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_fine) return;
+    const Rel S = load_rel(rel, pad, i);
+    const int I = agg[i];
+    double v[D], u[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) v[c] = xc[(size_t)I * D + c];
+    ad_apply(S, v, u);
+#pragma unroll
+    for (int c = 0; c < D; ++c) x[(size_t)i * D + c] += u[c];
+}
+
+// Fine level: z_i = zJ_i + Ad(rel_i) xc[agg_i]  (zJ = D^-1 r already in z), r.z, PCG bookkeeping.
+template <int NT>
+__global__ void __launch_bounds__(NT) amg_prolong0_kernel(int nf, const int32_t *__restrict__ agg, const double *__restrict__ rel,
+                                                          int pad, const double *__restrict__ xc, const double *__restrict__ r,
+                                                          double *__restrict__ z, double *__restrict__ p_out,
+                                                          double *__restrict__ partials, DevScalars *sc, int init, double tol,
+                                                          int max_iter) {
+    __shared__ double sh[32];
+    if (!init && sc->done) return;
+    double lrz = 0;
+    for (int i = blockIdx.x * NT + threadIdx.x; i < nf; i += gridDim.x * NT) {
+        const Rel S = load_rel(rel, pad, i);
+        const int I = agg[i];
+        double v[D], u[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) v[c] = xc[(size_t)I * D + c];
+        ad_apply(S, v, u);
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            const double zc = z[(size_t)i * D + c] + u[c];
+            z[(size_t)i * D + c] = zc;
+            if (p_out) p_out[(size_t)i * D + c] = zc;
+            lrz += r[(size_t)i * D + c] * zc;
+        }
+    }
+    const double bs = block_sum<NT>(lrz, sh);
+    if (threadIdx.x == 0) partials[blockIdx.x] = bs;
+    if (last_block(&sc->counters[6])) {
+        const double rz = sum_partials<NT>(partials, gridDim.x, sh);
+        if (threadIdx.x == 0) {
+            sc->rz_new = rz;
+            if (init) fin_init(sc, tol, max_iter);
+            else fin_update(sc);
+        }
+    }
+}
+
+// ---- tail of the V-cycle: every level with at most kTailRows rows, in ONE launch ---------------
+// The small levels are latency-bound (a handful of CTAs each); one 1024-thread CTA walks them all
+// with __syncthreads() between the phases instead of ~5 launches per level.
+constexpr int kTailRows = 1024, kTailThreads = 512, kTailMaxLevels = kMaxLevels;
+
+struct TailLevel {
+    int n, pad_fine;                                  // rows of this level; pad of the transfer's rel planes
+    const int32_t *rowptr, *colidx;                   // operator of this level
+    const int32_t *mem_ptr, *mem_idx, *agg;           // transfer (previous level -> this level)
+    const double *A, *Dinv, *rel;
+    double *r, *x, *x2, *t;
+};
+struct TailParams {
+    int nlev, dense, N;
+    const double *inv;
+    TailLevel lev[kTailMaxLevels];
+};
+
+template <int MODE>
+__device__ __forceinline__ void tail_rows(const TailLevel &L, const double *__restrict__ x, double *__restrict__ out, double omega) {
+    const int groups = kTailThreads / 8, g = threadIdx.x / 8, l = threadIdx.x & 7;
+    for (int base = 0; base < L.n; base += groups) {
+        const int i = base + g;
+        const bool act = i < L.n && l < D;
+        double res = act ? L.r[(size_t)i * D + l] : 0.0;
+        if (MODE != 0 && act) {
+            double acc = 0;
+            for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k) {
+                const double *xj = x + (size_t)L.colidx[k] * D;
+                const double *Ak = L.A + (size_t)k * DD + l * D;
+#pragma unroll
+                for (int c = 0; c < D; ++c) acc += Ak[c] * xj[c];
+            }
+            res -= acc;
+        }
+        if (MODE == 1) {
+            if (act) out[(size_t)i * D + l] = res;
+            continue;
+        }
+        double z = 0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            const double rc = __shfl_sync(0xffffffffu, res, c, 8);
+            if (act) z += L.Dinv[(size_t)i * DD + l * D + c] * rc;
+        }
+        if (act) out[(size_t)i * D + l] = (MODE == 2 ? x[(size_t)i * D + l] : 0.0) + omega * z;
+    }
+}
+
+__global__ void __launch_bounds__(kTailThreads) amg_tail_kernel(const __grid_constant__ TailParams P, double omega,
+                                                                const DevScalars *sc, int check_done) {
+    if (check_done && sc->done) return;
+    const int last = P.nlev - 1;
+    for (int l = 0; l <= last; ++l) {
+        const TailLevel &L = P.lev[l];
+        if (l == last) {
+            if (P.dense) {
+                for (int t = threadIdx.x; t < P.N; t += kTailThreads) {
+                    double acc = 0;
+                    for (int c = 0; c < P.N; ++c) acc += P.inv[(size_t)c * P.N + t] * L.r[c];
+                    L.x2[t] = acc;
+                }
+            } else {            // no dense inverse: five damped block-Jacobi sweeps (a fixed linear operator)
+                tail_rows<0>(L, nullptr, L.x, omega);
+                __syncthreads();
+                for (int k = 0; k < 2; ++k) {
+                    tail_rows<2>(L, L.x, L.x2, omega);
+                    __syncthreads();
+                    tail_rows<2>(L, L.x2, L.x, omega);
+                    __syncthreads();
+                }
+                for (int t = threadIdx.x; t < L.n * D; t += kTailThreads) L.x2[t] = L.x[t];
+            }
+            __syncthreads();
+            break;
+        }
+        tail_rows<0>(L, nullptr, L.x, omega);
+        __syncthreads();
+        tail_rows<1>(L, L.x, L.t, omega);
+        __syncthreads();
+        const TailLevel &C = P.lev[l + 1];
+        for (int I = threadIdx.x; I < C.n; I += kTailThreads) {
+            double acc[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) acc[c] = 0;
+            for (int m = C.mem_ptr[I]; m < C.mem_ptr[I + 1]; ++m) {
+                const int i = C.mem_idx[m];
+                const Rel S = load_rel(C.rel, C.pad_fine, i);
+                double w[D], u[D];
+#pragma unroll
+                for (int c = 0; c < D; ++c) w[c] = L.t[(size_t)i * D + c];
+                adT_apply(S, w, u);
+#pragma unroll
+                for (int c = 0; c < D; ++c) acc[c] += u[c];
+            }
+#pragma unroll
+            for (int c = 0; c < D; ++c) C.r[(size_t)I * D + c] = acc[c];
+        }
+        __syncthreads();
+    }
+    // every level leaves its result in x2 (the host swaps x and x2 after the launch)
+    for (int l = last - 1; l >= 0; --l) {
+        const TailLevel &L = P.lev[l];
+        const TailLevel &C = P.lev[l + 1];
+        for (int i = threadIdx.x; i < L.n; i += kTailThreads) {
+            const Rel S = load_rel(C.rel, C.pad_fine, i);
+            const int I = C.agg[i];
+            double v[D], u[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) v[c] = C.x2[(size_t)I * D + c];
+            ad_apply(S, v, u);
+#pragma unroll
+            for (int c = 0; c < D; ++c) L.x[(size_t)i * D + c] += u[c];
+        }
+        __syncthreads();
+        tail_rows<2>(L, L.x, L.x2, omega);
+        __syncthreads();
+    }
+}
+
+template <class T>
+int up(s3o_problem *p, T **dst, const std::vector<T> &src) { return upload(p, dst, src); }
+
+void free_level(LevelDev &L) {
+    dev_free(L.agg); dev_free(L.mem_ptr); dev_free(L.mem_idx); dev_free(L.vid);
+    dev_free(L.rowptr); dev_free(L.colidx); dev_free(L.blk_row); dev_free(L.dpos);
+    dev_free(L.gal_ptr); dev_free(L.gal_ent); dev_free(L.gal_i); dev_free(L.gal_j); dev_free(L.gal_out); dev_free(L.gal_mirror);
+    dev_free(L.rel); dev_free(L.A); dev_free(L.Dinv); dev_free(L.r); dev_free(L.x); dev_free(L.x2); dev_free(L.t);
+}
+
+}  // namespace
+
+void amg_destroy(s3o_problem *p) {
+    if (!p->amg) return;
+    for (auto &L : p->amg->lev) free_level(L);
+    dev_free(p->amg->d_vid0);
+    dev_free(p->amg->d_dense);
+    delete p->amg;
+    p->amg = nullptr;
+}
+
+int amg_levels(const s3o_problem *p) { return p->amg ? (int)p->amg->lev.size() : 0; }
+
+// Builds the hierarchy for the current structure (host) and uploads it.  Returns S3O_OK with no
+// levels when the graph is too small to coarsen (the caller then stays with block-Jacobi).
+int amg_setup(s3o_problem *p) {
+    if (p->amg) return S3O_OK;
+    if (p->kind != S3O_KIND_SIM3 || p->dist) { set_error("multilevel preconditioner: Sim3 problems on one GPU only"); return S3O_ERR_UNSUPPORTED; }
+    AmgState *st = new AmgState();
+    p->amg = st;
+    amg_build_hierarchy(p->S, kCoarsestMax, kMaxLevels, st->host);
+    const int nl = (int)st->host.size();
+    if (nl == 0) return S3O_OK;
+    int rc = up(p, &st->d_vid0, p->S.free2v);
+    st->lev.resize(nl);
+    for (int l = 0; l < nl && !rc; ++l) {
+        const AmgHostLevel &H = st->host[l];
+        LevelDev &L = st->lev[l];
+        L.n_fine = H.n_fine; L.n = H.n; L.nblk = (int)H.colidx.size(); L.nub = H.nub; L.pad_fine = pad32(H.n_fine);
+        rc = rc ? rc : up(p, &L.agg, H.agg);
+        rc = rc ? rc : up(p, &L.mem_ptr, H.mem_ptr);
+        rc = rc ? rc : up(p, &L.mem_idx, H.mem_idx);
+        rc = rc ? rc : up(p, &L.vid, H.vid);
+        rc = rc ? rc : up(p, &L.rowptr, H.rowptr);
+        rc = rc ? rc : up(p, &L.colidx, H.colidx);
+        rc = rc ? rc : up(p, &L.blk_row, H.blk_row);
+        rc = rc ? rc : up(p, &L.dpos, H.dpos);
+        rc = rc ? rc : up(p, &L.gal_ptr, H.gal_ptr);
+        rc = rc ? rc : up(p, &L.gal_ent, H.gal_ent);
+        rc = rc ? rc : up(p, &L.gal_i, H.gal_i);
+        rc = rc ? rc : up(p, &L.gal_j, H.gal_j);
+        rc = rc ? rc : up(p, &L.gal_out, H.gal_out);
+        rc = rc ? rc : up(p, &L.gal_mirror, H.gal_mirror);
+        rc = rc ? rc : dev_alloc(&L.rel, (size_t)NREL * L.pad_fine);
+        rc = rc ? rc : dev_alloc(&L.A, (size_t)L.nblk * DD);
+        rc = rc ? rc : dev_alloc(&L.Dinv, (size_t)L.n * DD);
+        rc = rc ? rc : dev_alloc(&L.r, (size_t)L.n * D);
+        rc = rc ? rc : dev_alloc(&L.x, (size_t)L.n * D);
+        rc = rc ? rc : dev_alloc(&L.x2, (size_t)L.n * D);
+        rc = rc ? rc : dev_alloc(&L.t, (size_t)L.n * D);
+    }
+    const int nc = st->host.back().n;
+    st->dense = nc <= kCoarsestMax;
+    if (!rc && st->dense) {
+        rc = dev_alloc(&st->d_dense, (size_t)nc * D * nc * D);
+        const int smem = (nc * D * nc * D + nc * D) * (int)sizeof(double);
+        if (!rc && cudaFuncSetAttribute(amg_dense_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+            set_error("amg_setup: cannot reserve %d bytes of shared memory", smem);
+            rc = S3O_ERR_CUDA;
+        }
+    }
+    if (!rc) { cudaError_t e = cudaStreamSynchronize(p->stream); if (e != cudaSuccess) { set_error("amg_setup: %s", cudaGetErrorString(e)); rc = S3O_ERR_CUDA; } }
+    // the host lists are only needed for the upload; keep the small per-level sizes
+    for (auto &H : st->host) {
+        std::vector<int32_t>().swap(H.gal_ent); std::vector<int32_t>().swap(H.gal_i); std::vector<int32_t>().swap(H.gal_j);
+        std::vector<int32_t>().swap(H.agg); std::vector<int32_t>().swap(H.mem_idx);
+    }
+    if (rc) amg_destroy(p);
+    return rc;
+}
+
+// Relative frames of every level at the current linearisation point.
+int amg_update_frames(s3o_problem *p) {
+    AmgState *st = p->amg;
+    if (!st || st->lev.empty()) return S3O_OK;
+    const double *est = p->d_est[p->cur];
+    for (size_t l = 0; l < st->lev.size(); ++l) {
+        LevelDev &L = st->lev[l];
+        const int32_t *vid_fine = l == 0 ? st->d_vid0 : st->lev[l - 1].vid;
+        amg_rel_kernel<<<(L.n_fine + 127) / 128, 128, 0, p->stream>>>(est, p->nv_pad, vid_fine, L.agg, L.vid, L.n_fine,
+                                                                       L.pad_fine, L.rel);
+    }
+    st->frames_valid = true;
+    return check_launch(p, (int)st->lev.size());
+}
+
+// Galerkin operators, smoother inverses and the coarsest inverse for (H + lambda I).
+int amg_update_values(s3o_problem *p, double lambda) {
+    AmgState *st = p->amg;
+    if (!st || st->lev.empty()) return S3O_OK;
+    int rc;
+    if (!st->frames_valid && (rc = amg_update_frames(p))) return rc;
+    int launches = 0;
+    for (size_t l = 0; l < st->lev.size(); ++l) {
+        LevelDev &L = st->lev[l];
+        const int grid = (L.nub + 15) / 16;
+        if (l == 0)
+            amg_galerkin_kernel<true><<<grid, 128, 0, p->stream>>>(p->d_H, L.gal_i, L.gal_j, L.rel, L.pad_fine, lambda,
+                                                                    L.nub, L.gal_ptr, L.gal_ent, L.gal_out, L.gal_mirror, L.A);
+        else {
+            const LevelDev &F = st->lev[l - 1];
+            amg_galerkin_kernel<false><<<grid, 128, 0, p->stream>>>(F.A, L.gal_i, L.gal_j, L.rel, L.pad_fine, 0.0, L.nub,
+                                                                     L.gal_ptr, L.gal_ent, L.gal_out, L.gal_mirror, L.A);
+        }
+        launch_precond(D, L.A, L.dpos, L.n, 0.0, L.Dinv, p->d_sc, p->stream);
+        launches += 2;
+    }
+    if (st->dense) {
+        const LevelDev &C = st->lev.back();
+        const int N = C.n * D;
+        amg_dense_inverse_kernel<<<1, 256, (size_t)(N * N + N) * sizeof(double), p->stream>>>(C.A, C.rowptr, C.colidx, C.n,
+                                                                                              st->d_dense, p->d_sc);
+        launches += 1;
+    }
+    return check_launch(p, launches);
+}
+
+// z += P0 V(P0^T r) on the fine vectors of the problem (z holds D^-1 r on entry); finishes the
+// PCG scalars (r.z, beta / convergence test).  init: first application of a solve (also sets p = z).
+int amg_apply(s3o_problem *p, int init) {
+    AmgState *st = p->amg;
+    const int nl = (int)st->lev.size();
+    const DevScalars *sc = p->d_sc;
+    const int chk = init ? 0 : 1;
+    cudaStream_t s = p->stream;
+    int launches = 0;
+    auto rows = [](int n) { return (n + 15) / 16; };
+    int lt = 0;                 // first level handled by the one-CTA tail kernel
+    while (lt < nl && st->lev[lt].n > kTailRows) ++lt;
+    if (lt == nl) lt = nl - 1;  // a large coarsest level: the tail kernel still runs its smoothing sweeps
+    {   // fine residual -> level 1
+        LevelDev &L = st->lev[0];
+        amg_restrict_kernel<<<(L.n + 127) / 128, 128, 0, s>>>(L.n, L.mem_ptr, L.mem_idx, L.rel, L.pad_fine, p->d_r, L.r, sc, chk);
+        ++launches;
+    }
+    for (int l = 0; l < lt; ++l) {
+        LevelDev &L = st->lev[l];
+        LevelDev &C = st->lev[l + 1];
+        amg_row_kernel<0><<<rows(L.n), 128, 0, s>>>(L.n, L.rowptr, L.colidx, L.A, L.Dinv, L.r, nullptr, L.x, kOmega, sc, chk);
+        amg_row_kernel<1><<<rows(L.n), 128, 0, s>>>(L.n, L.rowptr, L.colidx, L.A, L.Dinv, L.r, L.x, L.t, kOmega, sc, chk);
+        amg_restrict_kernel<<<(C.n + 127) / 128, 128, 0, s>>>(C.n, C.mem_ptr, C.mem_idx, C.rel, C.pad_fine, L.t, C.r, sc, chk);
+        launches += 3;
+    }
+    {
+        TailParams P{};
+        P.nlev = nl - lt;
+        P.dense = st->dense ? 1 : 0;
+        P.N = st->lev.back().n * D;
+        P.inv = st->d_dense;
+        for (int l = lt; l < nl; ++l) {
+            LevelDev &L = st->lev[l];
+            TailLevel &T = P.lev[l - lt];
+            T.n = L.n; T.pad_fine = L.pad_fine;
+            T.rowptr = L.rowptr; T.colidx = L.colidx; T.mem_ptr = L.mem_ptr; T.mem_idx = L.mem_idx; T.agg = L.agg;
+            T.A = L.A; T.Dinv = L.Dinv; T.rel = L.rel; T.r = L.r; T.x = L.x; T.x2 = L.x2; T.t = L.t;
+        }
+        amg_tail_kernel<<<1, kTailThreads, 0, s>>>(P, kOmega, sc, chk);
+        for (int l = lt; l < nl; ++l) std::swap(st->lev[l].x, st->lev[l].x2);
+        ++launches;
+    }
+    for (int l = lt - 1; l >= 0; --l) {
+        LevelDev &L = st->lev[l];
+        LevelDev &C = st->lev[l + 1];
+        amg_prolong_kernel<<<(L.n + 127) / 128, 128, 0, s>>>(L.n, C.agg, C.rel, C.pad_fine, C.x, L.x, sc, chk);
+        amg_row_kernel<2><<<rows(L.n), 128, 0, s>>>(L.n, L.rowptr, L.colidx, L.A, L.Dinv, L.r, L.x, L.x2, kOmega, sc, chk);
+        std::swap(L.x, L.x2);
+        launches += 2;
+    }
+    {
+        LevelDev &L = st->lev[0];
+        constexpr int NT = 256;
+        int grid = (L.n_fine + NT - 1) / NT;
+        if (grid > 148 * 8) grid = 148 * 8;
+        amg_prolong0_kernel<NT><<<grid, NT, 0, s>>>(L.n_fine, L.agg, L.rel, L.pad_fine, L.x, p->d_r, p->d_z, init ? p->d_p : nullptr,
+                                                    p->d_partials, p->d_sc, init, p->pcg_tol, p->pcg_max_iter);
+        ++launches;
+    }
+    return check_launch(p, launches);
+}
+
+void amg_invalidate_frames(s3o_problem *p) { if (p->amg) p->amg->frames_valid = false; }
+
+}  // namespace s3o

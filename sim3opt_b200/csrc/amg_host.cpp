@@ -1,0 +1,185 @@
+// amg_host.cpp -- aggregation hierarchy of the multilevel preconditioner (structure only, host).
+// See amg.h.  Deterministic: vertices are visited in index order, lists are sorted.
+#include <algorithm>
+
+#include "amg.h"
+
+namespace s3o {
+namespace {
+
+struct Pattern {            // blocks of one level
+    int n = 0, nblk = 0;
+    const int32_t *brow = nullptr, *bcol = nullptr;
+    bool upper = false;     // level 0: only (i <= j) stored
+};
+
+// adjacency (both directions, self excluded), neighbours ascending
+void build_adjacency(const Pattern &F, std::vector<int32_t> &ptr, std::vector<int32_t> &idx) {
+    ptr.assign(F.n + 1, 0);
+    for (int k = 0; k < F.nblk; ++k) {
+        const int i = F.brow[k], j = F.bcol[k];
+        if (i == j) continue;
+        ptr[i + 1]++;
+        if (F.upper) ptr[j + 1]++;
+    }
+    for (int i = 0; i < F.n; ++i) ptr[i + 1] += ptr[i];
+    idx.resize(ptr[F.n]);
+    std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
+    for (int k = 0; k < F.nblk; ++k) {
+        const int i = F.brow[k], j = F.bcol[k];
+        if (i == j) continue;
+        idx[fill[i]++] = j;
+        if (F.upper) idx[fill[j]++] = i;
+    }
+    for (int i = 0; i < F.n; ++i) std::sort(idx.begin() + ptr[i], idx.begin() + ptr[i + 1]);
+}
+
+// Greedy neighbourhood aggregation: a vertex whose whole neighbourhood is still free seeds an
+// aggregate {vertex + neighbours}; leftovers join the aggregate of their first aggregated
+// neighbour, isolated leftovers stay alone.
+void aggregate(int n, const std::vector<int32_t> &ptr, const std::vector<int32_t> &idx, std::vector<int32_t> &agg,
+               std::vector<int32_t> &root) {
+    agg.assign(n, -1);
+    root.clear();
+    for (int i = 0; i < n; ++i) {
+        if (agg[i] >= 0) continue;
+        bool free_nb = true;
+        for (int t = ptr[i]; t < ptr[i + 1] && free_nb; ++t) free_nb = agg[idx[t]] < 0;
+        if (!free_nb) continue;
+        const int a = (int)root.size();
+        root.push_back(i);
+        agg[i] = a;
+        for (int t = ptr[i]; t < ptr[i + 1]; ++t) agg[idx[t]] = a;
+    }
+    const int n_seeded = (int)root.size();
+    std::vector<int32_t> join(n, -1);
+    for (int i = 0; i < n; ++i) {
+        if (agg[i] >= 0) continue;
+        for (int t = ptr[i]; t < ptr[i + 1]; ++t) {
+            const int a = agg[idx[t]];
+            if (a >= 0 && a < n_seeded) { join[i] = a; break; }
+        }
+    }
+    for (int i = 0; i < n; ++i) {
+        if (agg[i] >= 0) continue;
+        if (join[i] >= 0) agg[i] = join[i];
+        else { agg[i] = (int)root.size(); root.push_back(i); }
+    }
+}
+
+int find_col(const AmgHostLevel &L, int I, int J) {
+    const int32_t *b = L.colidx.data() + L.rowptr[I], *e = L.colidx.data() + L.rowptr[I + 1];
+    return (int)(std::lower_bound(b, e, J) - L.colidx.data());
+}
+
+}  // namespace
+
+void amg_build_hierarchy(const HostStructure &S, int coarsest_max, int max_levels, std::vector<AmgHostLevel> &levels) {
+    levels.clear();
+    if (S.nf == 0) return;
+    levels.reserve((size_t)max_levels + 1);     // the loop keeps pointers into levels.back()
+    std::vector<int32_t> blk_row0(S.nb);
+    for (int r = 0; r < S.nf; ++r)
+        for (int k = S.rowptr[r]; k < S.rowptr[r + 1]; ++k) blk_row0[k] = r;
+    Pattern F;
+    F.n = S.nf; F.nblk = S.nb; F.brow = blk_row0.data(); F.bcol = S.colidx.data(); F.upper = true;
+    const std::vector<int32_t> *vid_fine = &S.free2v;
+
+    while (F.n > coarsest_max && (int)levels.size() < max_levels) {
+        std::vector<int32_t> aptr, aidx;
+        build_adjacency(F, aptr, aidx);
+        AmgHostLevel L;
+        L.n_fine = F.n;
+        aggregate(F.n, aptr, aidx, L.agg, L.root);
+        L.n = (int)L.root.size();
+        if (L.n * 10 > F.n * 9) break;          // aggregation stalled (isolated vertices): stop here
+        L.vid.resize(L.n);
+        for (int a = 0; a < L.n; ++a) L.vid[a] = (*vid_fine)[L.root[a]];
+        // members
+        L.mem_ptr.assign(L.n + 1, 0);
+        for (int i = 0; i < F.n; ++i) L.mem_ptr[L.agg[i] + 1]++;
+        for (int a = 0; a < L.n; ++a) L.mem_ptr[a + 1] += L.mem_ptr[a];
+        L.mem_idx.resize(F.n);
+        {
+            std::vector<int32_t> fill(L.mem_ptr.begin(), L.mem_ptr.end() - 1);
+            for (int i = 0; i < F.n; ++i) L.mem_idx[fill[L.agg[i]]++] = i;
+        }
+        // coarse pattern
+        std::vector<uint64_t> keys;
+        keys.reserve((size_t)F.nblk * (F.upper ? 2 : 1));
+        for (int k = 0; k < F.nblk; ++k) {
+            const uint32_t I = (uint32_t)L.agg[F.brow[k]], J = (uint32_t)L.agg[F.bcol[k]];
+            keys.push_back(((uint64_t)I << 32) | J);
+            if (F.upper && I != J) keys.push_back(((uint64_t)J << 32) | I);
+        }
+        std::sort(keys.begin(), keys.end());
+        keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+        const int nblk = (int)keys.size();
+        L.rowptr.assign(L.n + 1, 0);
+        L.colidx.resize(nblk);
+        L.blk_row.resize(nblk);
+        L.dpos.assign(L.n, -1);
+        for (int t = 0; t < nblk; ++t) {
+            const int I = (int)(keys[t] >> 32), J = (int)(uint32_t)keys[t];
+            L.rowptr[I + 1]++;
+            L.colidx[t] = J;
+            L.blk_row[t] = I;
+            if (I == J) L.dpos[I] = t;
+        }
+        for (int a = 0; a < L.n; ++a) L.rowptr[a + 1] += L.rowptr[a];
+        // upper blocks and their mirrors
+        std::vector<int32_t> ubidx(nblk, -1);
+        for (int t = 0; t < nblk; ++t) {
+            const int I = L.blk_row[t], J = L.colidx[t];
+            if (I > J) continue;
+            ubidx[t] = (int32_t)L.gal_out.size();
+            L.gal_out.push_back(t);
+            L.gal_mirror.push_back(I == J ? -1 : find_col(L, J, I));
+            L.gal_I.push_back(I);
+            L.gal_J.push_back(J);
+        }
+        L.nub = (int)L.gal_out.size();
+        // contributors, ascending in the fine block index
+        auto target = [&](int k, int &ub, int &flag) {
+            const int i = F.brow[k], j = F.bcol[k];
+            const int I = L.agg[i], J = L.agg[j];
+            if (F.upper) {
+                if (i == j) { ub = ubidx[L.dpos[I]]; flag = 0; }
+                else if (I == J) { ub = ubidx[L.dpos[I]]; flag = 2; }
+                else if (I < J) { ub = ubidx[find_col(L, I, J)]; flag = 0; }
+                else { ub = ubidx[find_col(L, J, I)]; flag = 1; }
+            } else {
+                if (I > J) { ub = -1; flag = 0; }
+                else { ub = ubidx[find_col(L, I, J)]; flag = 0; }
+            }
+        };
+        L.gal_ptr.assign(L.nub + 1, 0);
+        for (int k = 0; k < F.nblk; ++k) {
+            int ub, flag;
+            target(k, ub, flag);
+            if (ub >= 0) L.gal_ptr[ub + 1]++;
+        }
+        for (int u = 0; u < L.nub; ++u) L.gal_ptr[u + 1] += L.gal_ptr[u];
+        L.gal_ent.resize(L.gal_ptr[L.nub]);
+        L.gal_i.resize(L.gal_ent.size());
+        L.gal_j.resize(L.gal_ent.size());
+        {
+            std::vector<int32_t> fill(L.gal_ptr.begin(), L.gal_ptr.end() - 1);
+            for (int k = 0; k < F.nblk; ++k) {
+                int ub, flag;
+                target(k, ub, flag);
+                if (ub < 0) continue;
+                const int pos = fill[ub]++;
+                L.gal_ent[pos] = (k << 2) | flag;
+                L.gal_i[pos] = F.brow[k];
+                L.gal_j[pos] = F.bcol[k];
+            }
+        }
+        levels.push_back(std::move(L));
+        const AmgHostLevel &B = levels.back();
+        F.n = B.n; F.nblk = (int)B.colidx.size(); F.brow = B.blk_row.data(); F.bcol = B.colidx.data(); F.upper = false;
+        vid_fine = &B.vid;
+    }
+}
+
+}  // namespace s3o

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "problem.h"
+#include "amg.h"
 
 namespace s3o {
 
@@ -73,6 +74,7 @@ void free_structure(s3o_problem *p) {
     dev_free(p->d_ghidx); dev_free(p->d_send_idx); dev_free(p->d_primary); dev_free(p->d_sendbuf); dev_free(p->d_xg);
     dev_free(p->d_H); dev_free(p->d_b); dev_free(p->d_x); dev_free(p->d_r); dev_free(p->d_z); dev_free(p->d_p);
     dev_free(p->d_q1); dev_free(p->d_T); dev_free(p->d_Minv); dev_free(p->d_scratch);
+    amg_destroy(p);
     p->built = false;
     p->linearized = false;
 }
@@ -122,7 +124,11 @@ int ensure_built(s3o_problem *p) {
 void run_spmv(s3o_problem *p, const StructDev &s, double lambda, const double *x, int pcg_mode) {
     if (p->spmv_version == 1 && !p->dist)
         launch_spmv(p->d, p->d_H, s, p->S.nf, lambda, x, p->d_q1, p->d_T, p->d_partials, p->d_sc, pcg_mode, p->stream);
-    else if (p->spmv_version == 3 && p->S.max_row_blocks <= p->S.tile_blocks)
+    else if (p->spmv_version == 4 && p->d == 7 && p->S.max_row_blocks <= p->S.tile_blocks &&
+             spmv4_fits(s.ntiles, p->spmv_grid_cap))
+        launch_spmv4(p->d_H, s, own_rows(p), lambda, x, p->d_q1, p->d_T, p->d_partials, p->d_sc, pcg_mode,
+                     p->spmv_grid_cap, p->dist, p->stream);
+    else if (p->spmv_version >= 3 && p->S.max_row_blocks <= p->S.tile_blocks)
         launch_spmv3(p->d, p->d_H, s, own_rows(p), lambda, x, p->d_q1, p->d_T, p->d_partials, p->d_sc, pcg_mode,
                      p->spmv_grid_cap, p->dist, p->stream);
     else
@@ -146,6 +152,7 @@ int do_linearize(s3o_problem *p) {
     const GraphDev g = graph_view(p, p->cur);
     launch_linearize(g, p->jac_mode, p->jac_h, p->d_scratch, p->stream);
     launch_assemble(g, struct_view(p), p->d_scratch, p->d_H, p->d_b, p->stream);
+    amg_invalidate_frames(p);
     p->linearized = true;
     return check_launch(p, 2);
 }
@@ -153,6 +160,12 @@ int do_linearize(s3o_problem *p) {
 }  // namespace
 
 namespace s3o {
+// multilevel preconditioner: Sim3 graphs on one GPU; AUTO switches it on for large graphs
+bool wants_multilevel(const s3o_problem *p) {
+    return !p->dist && p->kind == S3O_KIND_SIM3 &&
+           (p->precond == S3O_PRECOND_MULTILEVEL || (p->precond == S3O_PRECOND_AUTO && p->S.nf >= 20000));
+}
+
 // Solve (H + lambda I) x = b; leaves x in d_x.  Returns the PCG status in *status (1 converged,
 // 2 iteration cap, 3 breakdown) and the iteration count.
 int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel_res) {
@@ -171,11 +184,22 @@ int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel
         }
         return S3O_OK;
     };
+    bool amg = false;
+    int rc;
+    if (wants_multilevel(p)) {
+        if ((rc = amg_setup(p))) return rc;
+        amg = amg_levels(p) > 0;
+    }
     launch_precond(d, p->d_H, p->d_rowptr, nf, lambda, p->d_Minv, p->d_sc, p->stream);
+    if (amg && (rc = amg_update_values(p, lambda))) return rc;
+    // with the multilevel correction the vector kernels leave r.z to amg_apply (like the partitioned
+    // solve leaves it to the all-reduce)
+    const int defer = dist || amg;
     launch_pcg_init(d, nf, p->d_b, p->d_Minv, p->d_x, p->d_r, p->d_z, p->d_p, p->d_partials, p->d_sc, p->pcg_tol,
-                    p->pcg_max_iter, dist, p->stream);
-    int rc = check_launch(p, 2);
+                    p->pcg_max_iter, defer, p->stream);
+    rc = check_launch(p, 2);
     if (rc) return rc;
+    if (amg && (rc = amg_apply(p, 1))) return rc;
     if (dist) {
         if ((rc = allreduce_sum(p, &p->d_sc->rz_new, 2))) return rc;
         launch_pcg_fin_init(p->d_sc, p->pcg_tol, p->pcg_max_iter, p->stream);
@@ -186,7 +210,10 @@ int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel
         for (int k = 0; k < batch; ++k) {
             const bool sample = ((launched + k) & 15) == 7 && p->spmv_ev_used < s3o_problem::kSpmvEvents;
             if ((rc = halo())) return rc;
-            if (sample) cudaEventRecord(p->spmv_ev[2 * p->spmv_ev_used], p->stream);
+            if (sample) {
+                p->spmv_ev_iter[p->spmv_ev_used] = launched + k;
+                cudaEventRecord(p->spmv_ev[2 * p->spmv_ev_used], p->stream);
+            }
             run_spmv(p, s, lambda, p->d_p, 1);
             if (sample) cudaEventRecord(p->spmv_ev[2 * p->spmv_ev_used++ + 1], p->stream);
             if (dist) {
@@ -194,7 +221,8 @@ int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel
                 launch_pcg_fin_spmv(p->d_sc, p->stream);
             }
             launch_pcg_update(d, s, nf, p->d_q1, p->d_T, p->d_Minv, p->d_p, p->d_x, p->d_r, p->d_z, p->d_partials,
-                              p->d_sc, dist, p->stream);
+                              p->d_sc, defer, p->stream);
+            if (amg && (rc = amg_apply(p, 0))) return rc;
             if (dist) {
                 if ((rc = allreduce_sum(p, &p->d_sc->rz_new, 2))) return rc;
                 launch_pcg_fin_update(p->d_sc, p->stream);
@@ -206,11 +234,12 @@ int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel
         if (rc) return rc;
         rc = sync_scalars(p);
         if (rc) return rc;
-        // samples taken after convergence time an early-exit launch: keep only those within the run
+        // a launch after convergence exits at once: keep only the samples of iterations that ran
+        // (launch index < iterations executed)
         for (int e = 0; e < p->spmv_ev_used; ++e) {
             float ms = 0;
             if (cudaEventElapsedTime(&ms, p->spmv_ev[2 * e], p->spmv_ev[2 * e + 1]) == cudaSuccess &&
-                !(p->h_sc->done && e == p->spmv_ev_used - 1 && batch > 16)) {
+                (!p->h_sc->done || p->spmv_ev_iter[e] < p->h_sc->iters)) {
                 p->stats.ms_spmv_sampled += ms;
                 p->stats.n_spmv_sampled += 1;
             }
@@ -243,7 +272,8 @@ int upload_structure_arrays(s3o_problem *p, int rows_own) {
     rc = rc ? rc : upload(p, &p->d_colT_blk, S.colT_blk);
     S.max_row_blocks = 0;
     for (int r = 0; r < rows_own; ++r) S.max_row_blocks = std::max(S.max_row_blocks, S.rowptr[r + 1] - S.rowptr[r]);
-    S.tile_blocks = p->spmv_version == 3 ? spmv3_tile_blocks(p->d) : spmv_tile_blocks(p->d);
+    S.tile_blocks = (p->spmv_version == 4 && p->d == 7) ? spmv4_tile_blocks()
+                    : (p->spmv_version >= 3 ? spmv3_tile_blocks(p->d) : spmv_tile_blocks(p->d));
     build_tiles(S.rowptr, rows_own, S.tile_blocks, S.tile_row);
     rc = rc ? rc : upload(p, &p->d_tile_row, S.tile_row);
     return rc;
@@ -310,6 +340,7 @@ int s3o_create(int kind, int device, s3o_problem **out) {
     if (spmv2_configure() != 0) { set_error("s3o_create: cannot configure SpMV shared memory"); delete p; return S3O_ERR_CUDA; }
     if (const char *v = getenv("S3O_SPMV_VERSION")) p->spmv_version = atoi(v);
     if (const char *v = getenv("S3O_SPMV_GRID")) p->spmv_grid_cap = atoi(v);
+    if (const char *v = getenv("S3O_SPMV4_CFG")) spmv4_set_cfg(atoi(v));
     for (auto &ev : p->ev) cudaEventCreate(&ev);
     for (auto &ev : p->spmv_ev) cudaEventCreate(&ev);
     if (dev_alloc(&p->d_sc, 1) || dev_alloc(&p->d_partials, 2 * kMaxPartials) ||
@@ -338,6 +369,7 @@ int s3o_destroy(s3o_problem *p) {
     for (auto &ev : p->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : p->spmv_ev) if (ev) cudaEventDestroy(ev);
     dev_free(p->d_est_snap);
+    dev_free(p->d_stage);
     if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
     delete p;
     return S3O_OK;
@@ -376,17 +408,24 @@ int s3o_set_stream(s3o_problem *p, void *cuda_stream) {
     return S3O_OK;
 }
 
+// caller-ordered (AoS) staging buffer of the vertex estimates: allocated once per vertex set, so
+// the per-step host round trip of the estimates never pays a cudaMalloc / cudaFree (both
+// device-synchronising, and measured at up to 0.4 s after a long solve)
+static int ensure_stage(s3o_problem *p) {
+    if (p->d_stage) return S3O_OK;
+    return dev_alloc(&p->d_stage, (size_t)p->nv * p->est_dim);
+}
+
 static int upload_estimates(s3o_problem *p, const double *est) {
-    double *tmp = nullptr;
     const size_t cnt = (size_t)p->nv * p->est_dim;
-    int rc = dev_alloc(&tmp, cnt);
+    int rc = ensure_stage(p);
     if (rc) return rc;
+    double *tmp = p->d_stage;
     cudaError_t e = cudaMemcpyAsync(tmp, est, cnt * sizeof(double), cudaMemcpyHostToDevice, p->stream);
     if (e == cudaSuccess) {
         launch_pack_vertices(tmp, p->nv, p->nv_pad, p->est_dim, p->d_est[p->cur], p->stream);
         e = cudaStreamSynchronize(p->stream);
     }
-    cudaFree(tmp);
     if (e != cudaSuccess) { set_error("upload_estimates: %s", cudaGetErrorString(e)); return S3O_ERR_CUDA; }
     p->stats.h2d_bytes += (int64_t)(cnt * sizeof(double));
     p->stats.kernel_launches += 1;
@@ -405,6 +444,7 @@ int s3o_set_vertices(s3o_problem *p, int n, const double *est, const uint8_t *fi
     p->cur = 0;
     p->lm_valid = false;
     dev_free(p->d_est_snap);
+    dev_free(p->d_stage);
     p->fixed.assign(n, 0);
     if (fixed) memcpy(p->fixed.data(), fixed, n);
     int rc;
@@ -525,6 +565,20 @@ int s3o_set_lm(s3o_problem *p, double tau, double user_lambda_init, int max_tria
     return S3O_OK;
 }
 
+int s3o_set_preconditioner(s3o_problem *p, int kind) {
+    if (!p) return S3O_ERR_INVALID;
+    if (kind != S3O_PRECOND_AUTO && kind != S3O_PRECOND_BLOCK_JACOBI && kind != S3O_PRECOND_MULTILEVEL) {
+        set_error("s3o_set_preconditioner: unknown kind %d", kind);
+        return S3O_ERR_INVALID;
+    }
+    if (kind == S3O_PRECOND_MULTILEVEL && p->kind != S3O_KIND_SIM3) {
+        set_error("s3o_set_preconditioner: the multilevel preconditioner is built on Sim3 adjoints (kind SIM3 only)");
+        return S3O_ERR_UNSUPPORTED;
+    }
+    p->precond = kind;
+    return S3O_OK;
+}
+
 int s3o_set_pcg(s3o_problem *p, double rel_tol, int max_iter) {
     if (!p) return S3O_ERR_INVALID;
     if (rel_tol > 0) p->pcg_tol = rel_tol;
@@ -601,6 +655,8 @@ int s3o_build_structure(s3o_problem *p, int *n_free, int *n_blocks) {
         dev_free(p->d_info_aos);
         p->built = true;
         p->stats.n_free = S.nf; p->stats.n_blocks = S.nb;
+        // the aggregation hierarchy is structure work too: build it here rather than inside the first solve
+        if (wants_multilevel(p) && (rc = amg_setup(p))) return rc;
     }
     if (n_free) *n_free = p->S.nf;
     if (n_blocks) *n_blocks = p->S.nb;
@@ -640,6 +696,27 @@ int s3o_host_partition(int n_vertices, const uint8_t *fixed, int n_edges, const 
     if (send_count) memcpy(send_count, P.send_count.data(), sizeof(int32_t) * world);
     if (recv_count) memcpy(recv_count, P.recv_count.data(), sizeof(int32_t) * world);
     if (send_idx_global) for (size_t k = 0; k < P.send_idx.size(); ++k) send_idx_global[k] = P.send_idx[k] + P.own_lo;
+    return S3O_OK;
+}
+
+int s3o_host_multilevel(int n_vertices, const uint8_t *fixed, int n_edges, const int32_t *v0, const int32_t *v1,
+                        int cap, int *n_levels, int32_t *level_vertices, int32_t *level_blocks, int32_t *aggregate0) {
+    if (n_vertices < 0 || n_edges < 0 || (n_edges > 0 && (!v0 || !v1)) || !n_levels) { set_error("s3o_host_multilevel: bad arguments"); return S3O_ERR_INVALID; }
+    for (int k = 0; k < n_edges; ++k)
+        if (v0[k] < 0 || v0[k] >= n_vertices || v1[k] < 0 || v1[k] >= n_vertices || v0[k] == v1[k]) {
+            set_error("s3o_host_multilevel: edge %d has invalid vertices", k);
+            return S3O_ERR_INVALID;
+        }
+    HostStructure S;
+    build_structure_host(n_vertices, fixed, n_edges, v0, v1, S);
+    std::vector<s3o::AmgHostLevel> lv;
+    s3o::amg_build_hierarchy(S, 16, 12, lv);
+    *n_levels = (int)lv.size();
+    for (int l = 0; l < (int)lv.size() && l < cap; ++l) {
+        if (level_vertices) level_vertices[l] = lv[l].n;
+        if (level_blocks) level_blocks[l] = (int32_t)lv[l].colidx.size();
+    }
+    if (aggregate0 && !lv.empty()) memcpy(aggregate0, lv[0].agg.data(), sizeof(int32_t) * S.nf);
     return S3O_OK;
 }
 
@@ -996,14 +1073,13 @@ int s3o_get_vertices(s3o_problem *p, double *est) {
     if (p && p->kind == S3O_KIND_BA) { set_error("s3o_get_vertices: a BA problem takes s3o_ba_get_cameras / s3o_ba_get_points"); return S3O_ERR_INVALID; }
     if (!p || !est || !p->d_est[0]) { set_error("s3o_get_vertices: no vertices"); return S3O_ERR_INVALID; }
     cudaSetDevice(p->device);
-    double *tmp = nullptr;
     const size_t cnt = (size_t)p->nv * p->est_dim;
-    int rc = dev_alloc(&tmp, cnt);
+    int rc = ensure_stage(p);
     if (rc) return rc;
+    double *tmp = p->d_stage;
     launch_unpack_vertices(p->d_est[p->cur], p->nv, p->nv_pad, p->est_dim, tmp, p->stream);
     cudaError_t e = cudaMemcpyAsync(est, tmp, cnt * sizeof(double), cudaMemcpyDeviceToHost, p->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
-    cudaFree(tmp);
     if (e != cudaSuccess) { set_error("s3o_get_vertices: %s", cudaGetErrorString(e)); return S3O_ERR_CUDA; }
     p->stats.d2h_bytes += (int64_t)(cnt * sizeof(double));
     p->stats.kernel_launches += 1;

@@ -22,6 +22,7 @@ void dev_free(T *&ptr) {
 }
 
 struct BaState;   // bundle adjustment (ba.cu)
+struct AmgState;  // multilevel preconditioner (amg.cu)
 
 }  // namespace s3o
 
@@ -61,7 +62,7 @@ struct s3o_problem {
     int32_t *d_ghidx = nullptr, *d_send_idx = nullptr;
     uint8_t *d_primary = nullptr;
     double *d_sendbuf = nullptr, *d_xg = nullptr;
-    int spmv_version = 3;       // 1: lane-group rows, 2: tiled thread-per-block, 3: v2 + TMA ring
+    int spmv_version = 4;       // 1: lane-group rows, 2: tiled thread-per-block, 3: v2 + TMA ring, 4: v3 + prefetch pipeline (d = 7)
     int spmv_grid_cap = 148 * 2;
     // linear system
     double *d_H = nullptr, *d_b = nullptr, *d_x = nullptr, *d_r = nullptr, *d_z = nullptr, *d_p = nullptr;
@@ -77,21 +78,26 @@ struct s3o_problem {
     int max_trials = 10;
     double pcg_tol = 1e-8;
     int pcg_max_iter = 1000;
+    int precond = S3O_PRECOND_AUTO;         // s3o_set_preconditioner
     bool linearized = false;
     // LM continuation state (s3o_set_lm_resume)
     int lm_resume = 0;
     bool lm_valid = false;
     double lm_lambda = 0, lm_ni = 2, lm_chi = 0;
     double *d_est_snap = nullptr;
+    double *d_stage = nullptr;             // AoS staging of the estimates (upload / download)
     // sampled SpMV timing
     static constexpr int kSpmvEvents = 64;
     cudaEvent_t spmv_ev[2 * kSpmvEvents] = {};
     int spmv_ev_used = 0;
+    int spmv_ev_iter[kSpmvEvents] = {};     // PCG iteration (launch index within the solve) of each sample
     // statistics
     s3o_stats stats{};
     cudaEvent_t ev[6] = {};
     // bundle adjustment (kind S3O_KIND_BA): cameras / points / observations live in ba.cu
     s3o::BaState *ba = nullptr;
+    // multilevel preconditioner of the pose-graph PCG (amg.cu), built on first use
+    s3o::AmgState *amg = nullptr;
 };
 
 namespace s3o {
@@ -115,6 +121,16 @@ int upload_structure_arrays(s3o_problem *p, int rows_own);   // BSR / tile array
 int alloc_linear_system(s3o_problem *p);                      // H, b, x, r, z, p, q1, T, Minv for p->S
 // Solve (H + lambda I) x = b by block-Jacobi PCG on the system held in p->d_H / p->d_b; x in p->d_x
 int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel_res);
+
+// ---- multilevel preconditioner (amg.cu) -------------------------------------------------------
+bool wants_multilevel(const s3o_problem *p);
+int amg_setup(s3o_problem *p);                        // hierarchy for p->S (host build + upload)
+void amg_destroy(s3o_problem *p);
+int amg_levels(const s3o_problem *p);                 // coarse levels (0: graph too small, block-Jacobi only)
+void amg_invalidate_frames(s3o_problem *p);           // the linearisation point moved
+int amg_update_frames(s3o_problem *p);
+int amg_update_values(s3o_problem *p, double lambda); // Galerkin operators for (H + lambda I)
+int amg_apply(s3o_problem *p, int init);              // z += P0 V(P0^T r), r.z and the PCG scalars
 
 // ---- bundle adjustment hooks (ba.cu), called from the C ABI in problem.cu --------------------
 void ba_destroy(s3o_problem *p);

@@ -1,0 +1,89 @@
+"""Multilevel (aggregation) preconditioner of the pose-graph PCG -- GPU tests through the C ABI.
+
+The preconditioner only changes how fast the PCG reaches the solution of (H + lambda I) x = b, never
+the solution: the checks are the same backward-error / oracle gates as for block-Jacobi
+(tests/test_gpu_parity.py), plus iteration counts and bitwise reproducibility.
+"""
+import numpy as np
+import pytest
+
+from conftest import make_gpu, make_oracle
+from test_gpu_parity import dense_from_blocks
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sphere_mid():
+    from sim3opt_b200 import synth
+    return synth.sphere(n_laps=10, poses_per_lap=300, seed=11)
+
+
+@pytest.fixture(params=["kitti_k1", "kitti_k118", "sphere_small", "sphere_mid"])
+def graph(request):
+    return request.getfixturevalue(request.param)
+
+
+def test_solve_backward_error(graph):
+    import sim3opt_b200 as s3
+    gpu = make_gpu(graph, jac=1)
+    colptr, rowidx = gpu.build_structure()
+    H, b = gpu.linearize()
+    lam = 1e-5 * gpu.max_diag()
+    gpu.set_pcg(1e-11, 50000)
+    gpu.set_preconditioner(s3.PRECOND_BLOCK_JACOBI)
+    rc1, x1, it1, rel1 = gpu.solve(lam)
+    gpu.set_preconditioner(s3.PRECOND_MULTILEVEL)
+    rc2, x2, it2, rel2 = gpu.solve(lam)
+    assert rc1 == 0 and rc2 == 0 and rel2 <= 1e-11
+    A = dense_from_blocks(colptr, rowidx, H, 7) + lam * np.eye(len(b))
+    assert np.linalg.norm(A @ x2 - b) <= 1e-10 * np.linalg.norm(b)
+    assert it2 <= it1
+    # reproducible to the bit: every sum runs in list order
+    rc3, x3, it3, _ = gpu.solve(lam)
+    assert it3 == it2 and np.array_equal(x2, x3)
+
+
+def test_fewer_iterations_at_small_damping(sphere_mid):
+    """The coarse-space correction pays when lambda is small (late LM iterations)."""
+    import sim3opt_b200 as s3
+    gpu = make_gpu(sphere_mid, jac=1, math_mode=s3.MATH_CORRECTED)
+    gpu.linearize_only()
+    lam = 1e-8 * gpu.max_diag()
+    gpu.set_pcg(1e-8, 50000)
+    gpu.set_preconditioner(s3.PRECOND_BLOCK_JACOBI)
+    _, x1, it1, _ = gpu.solve(lam)
+    gpu.set_preconditioner(s3.PRECOND_MULTILEVEL)
+    _, x2, it2, _ = gpu.solve(lam)
+    assert it2 * 3 <= it1, (it1, it2)
+    assert np.abs(x1 - x2).max() <= 1e-3 * np.abs(x1).max()      # both stop at a 1e-8 residual; cond(H) bounds the error
+
+
+def test_lm_matches_block_jacobi_and_oracle(sphere_small):
+    """End-to-end LM with the multilevel PCG lands on the oracle's minimum (BASELINE tolerances)."""
+    from oracle import oracle as orc
+    import sim3opt_b200 as s3
+    orc.set_math_mode(orc.MATH_CORRECTED)
+    try:
+        gpu = make_gpu(sphere_small, jac=1, math_mode=s3.MATH_CORRECTED)
+        gpu.set_preconditioner(s3.PRECOND_MULTILEVEL)
+        gpu.set_pcg(1e-10, 20000)
+        cpu = make_oracle(sphere_small, jac=orc.JAC_ANALYTIC)
+        n_g, chi_g, _, _ = gpu.optimize(40)
+        n_c, chi_c, _, _ = cpu.optimize(40)
+    finally:
+        orc.set_math_mode(orc.MATH_REFERENCE)
+    assert abs(chi_g - chi_c) <= 1e-4 * chi_c
+    vg, vc = gpu.vertices(), cpu.vertices()
+    assert np.abs(vg[:, 4:7] - vc[:, 4:7]).max() <= 1e-4
+    dots = np.abs((vg[:, :4] * vc[:, :4]).sum(1) / (np.linalg.norm(vg[:, :4], axis=1) * np.linalg.norm(vc[:, :4], axis=1)))
+    assert (2 * np.arccos(np.clip(dots, -1, 1))).max() <= 1e-5
+
+
+def test_multilevel_rejected_for_other_kinds(kitti_k1):
+    import sim3opt_b200 as s3
+    from oracle import kitti_io
+    st = kitti_io.to_scale_trans_graph(kitti_k1)
+    gpu = make_gpu(st, kind=s3.KIND_SCALE_TRANS)
+    with pytest.raises(s3.S3OError):
+        gpu.set_preconditioner(s3.PRECOND_MULTILEVEL)

@@ -1,0 +1,39 @@
+"""Host side of the multilevel preconditioner: the aggregation hierarchy (no device needed)."""
+import numpy as np
+
+import sim3opt_b200 as s3
+from sim3opt_b200 import synth
+
+
+def test_hierarchy_sizes_and_aggregates():
+    g = synth.sphere(10, 1000, seed=42)
+    nv = len(g["est"])
+    sizes, blocks, agg = s3.host_multilevel(nv, g["fixed"], g["v0"], g["v1"])
+    nf = int((np.asarray(g["fixed"]) == 0).sum())
+    assert len(agg) == nf and len(sizes) >= 2
+    assert np.all(np.diff(np.concatenate([[nf], sizes])) < 0)        # strictly coarser every level
+    assert sizes[-1] <= 16                                          # coarsest level fits the dense inverse
+    assert agg.min() == 0 and agg.max() == sizes[0] - 1
+    assert np.all(np.bincount(agg, minlength=sizes[0]) >= 1)        # every aggregate is non-empty
+    assert np.all(blocks >= sizes)                                  # every level keeps its diagonal blocks
+    # aggregates are connected neighbourhoods: every member is the seed or adjacent to a member
+    colptr, rowidx, hidx = s3.host_structure(nv, g["fixed"], g["v0"], g["v1"])
+    cols = np.repeat(np.arange(nf), np.diff(colptr))
+    off = rowidx != cols
+    same = agg[rowidx[off]] == agg[cols[off]]
+    touched = np.zeros(nf, bool)
+    touched[rowidx[off][same]] = True
+    touched[cols[off][same]] = True
+    sizes0 = np.bincount(agg)
+    assert np.all(touched[sizes0[agg] > 1])
+    # deterministic
+    sizes2, blocks2, agg2 = s3.host_multilevel(nv, g["fixed"], g["v0"], g["v1"])
+    assert np.array_equal(sizes, sizes2) and np.array_equal(blocks, blocks2) and np.array_equal(agg, agg2)
+
+
+def test_tiny_graph_has_no_levels(kitti_k1):
+    g = synth.sphere(2, 6, seed=1)      # 12 poses: nothing to coarsen
+    sizes, blocks, agg = s3.host_multilevel(len(g["est"]), g["fixed"], g["v0"], g["v1"])
+    assert len(sizes) == 0
+    sizes, blocks, agg = s3.host_multilevel(len(kitti_k1["est"]), kitti_k1["fixed"], kitti_k1["v0"], kitti_k1["v1"])
+    assert len(sizes) >= 2 and sizes[0] < 771 // 2

@@ -144,6 +144,16 @@ def vcycle(levels, l, r, omega=0.7, sweeps=1):
     return x
 
 
+def acycle(levels, l, r, omega=0.7, sweeps=1, additive_levels=1):
+    """additive at the first `additive_levels` levels (no extra fine-level products), V-cycle below"""
+    L = levels[l]
+    if l == len(levels) - 1:
+        return L.dense @ r
+    if l >= additive_levels:
+        return vcycle(levels, l, r, omega, sweeps)
+    return omega * bjac(L, r) + L.P @ acycle(levels, l + 1, L.P.T @ r, omega, sweeps, additive_levels)
+
+
 def pcg(A, b, M, tol, maxit=20000):
     x = np.zeros_like(b)
     r = b.copy()
@@ -188,6 +198,8 @@ def main():
     H, b = p.linearize()
     if lam is None:
         lam = 1e-5 * p.max_diag()
+    if os.environ.get("LAM"):
+        lam = float(os.environ["LAM"])      # study a later-iteration damping without running the LM there
     print("lambda", lam, "max diag", p.max_diag())
     nf, d = len(colptr) - 1, 7
     cols = np.repeat(np.arange(nf), np.diff(colptr))
@@ -214,6 +226,11 @@ def main():
     t0 = time.time()
     levels = build_hierarchy(A, R, t, s)
     print(f"hierarchy: {len(levels)} levels ({time.time() - t0:.1f}s)")
+    for omega in (0.6, 0.8, 1.0):
+        for nadd in (1, 99):
+            for tol in (1e-3, 1e-8):
+                x, it = pcg(A, b, lambda r: acycle(levels, 0, r, omega, 1, nadd), tol)
+                print(f"additive x{nadd} (omega={omega}) PCG tol {tol:g}: {it} iterations")
     for omega in (0.6, 0.8):
         for sweeps in (1, 2):
             for tol in (1e-3, 1e-8):

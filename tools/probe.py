@@ -15,6 +15,7 @@ p.set_math_mode(s3.MATH_CORRECTED)
 t = time.time(); p.set_vertices(g["est"], g["fixed"]); p.set_edges(g["v0"], g["v1"], g["meas"], g["info"]); print("upload %.3fs" % (time.time() - t))
 t = time.time(); p.build_structure(); print("structure %.3fs" % (time.time() - t), p.num_free, p.num_blocks)
 p.set_pcg(tol, 5000)
+p.set_preconditioner(int(os.environ.get("PRECOND", "0")))
 print("chi2_0", p.chi2())
 t = time.time(); n, chi2, lam, hist = p.optimize(iters); wall = time.time() - t
 st = p.stats()
