@@ -330,9 +330,11 @@ __global__ void __launch_bounds__(NT) amg_prolong0_kernel(int nf, const int32_t 
 }
 
 // ---- tail of the V-cycle: every level with at most kTailRows rows, in ONE launch ---------------
-// The small levels are latency-bound (a handful of CTAs each); one 1024-thread CTA walks them all
-// with __syncthreads() between the phases instead of ~5 launches per level.
-constexpr int kTailRows = 1024, kTailThreads = 512, kTailMaxLevels = kMaxLevels;
+// The small levels are latency-bound (dependent index -> value loads, a handful of rows each).
+// One thread-block cluster of 8 CTAs walks them all, separated by cluster barriers instead of
+// ~5 kernel boundaries per level.  Vectors that change between phases are read with ld.cg (L2),
+// since another CTA of the cluster wrote them.
+constexpr int kTailRows = 1024, kTailThreads = 512, kTailCtas = 8, kTailMaxLevels = kMaxLevels;
 
 struct TailLevel {
     int n, pad_fine;                                  // rows of this level; pad of the transfer's rel planes
@@ -347,20 +349,32 @@ struct TailParams {
     TailLevel lev[kTailMaxLevels];
 };
 
+__device__ __forceinline__ void tail_sync() {
+    __threadfence();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned tail_cta_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
 template <int MODE>
-__device__ __forceinline__ void tail_rows(const TailLevel &L, const double *__restrict__ x, double *__restrict__ out, double omega) {
-    const int groups = kTailThreads / 8, g = threadIdx.x / 8, l = threadIdx.x & 7;
+__device__ __forceinline__ void tail_rows(const TailLevel &L, const double *x, double *out, double omega, int gtid) {
+    constexpr int groups = kTailThreads * kTailCtas / 8;
+    const int g = gtid / 8, l = gtid & 7;
     for (int base = 0; base < L.n; base += groups) {
         const int i = base + g;
         const bool act = i < L.n && l < D;
-        double res = act ? L.r[(size_t)i * D + l] : 0.0;
+        double res = act ? __ldcg(L.r + (size_t)i * D + l) : 0.0;
         if (MODE != 0 && act) {
             double acc = 0;
-            for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k) {
+            const int kb = L.rowptr[i], ke = L.rowptr[i + 1];
+            for (int k = kb; k < ke; ++k) {
                 const double *xj = x + (size_t)L.colidx[k] * D;
                 const double *Ak = L.A + (size_t)k * DD + l * D;
 #pragma unroll
-                for (int c = 0; c < D; ++c) acc += Ak[c] * xj[c];
+                for (int c = 0; c < D; ++c) acc += Ak[c] * __ldcg(xj + c);
             }
             res -= acc;
         }
@@ -374,43 +388,45 @@ __device__ __forceinline__ void tail_rows(const TailLevel &L, const double *__re
             const double rc = __shfl_sync(0xffffffffu, res, c, 8);
             if (act) z += L.Dinv[(size_t)i * DD + l * D + c] * rc;
         }
-        if (act) out[(size_t)i * D + l] = (MODE == 2 ? x[(size_t)i * D + l] : 0.0) + omega * z;
+        if (act) out[(size_t)i * D + l] = (MODE == 2 ? __ldcg(x + (size_t)i * D + l) : 0.0) + omega * z;
     }
 }
 
-__global__ void __launch_bounds__(kTailThreads) amg_tail_kernel(const __grid_constant__ TailParams P, double omega,
-                                                                const DevScalars *sc, int check_done) {
-    if (check_done && sc->done) return;
+__global__ void __cluster_dims__(kTailCtas, 1, 1) __launch_bounds__(kTailThreads)
+amg_tail_kernel(const __grid_constant__ TailParams P, double omega, const DevScalars *sc, int check_done) {
+    if (check_done && sc->done) return;       // uniform over the cluster: nobody reaches a barrier
+    constexpr int NTH = kTailThreads * kTailCtas;
+    const int gtid = (int)tail_cta_rank() * kTailThreads + threadIdx.x;
     const int last = P.nlev - 1;
     for (int l = 0; l <= last; ++l) {
         const TailLevel &L = P.lev[l];
         if (l == last) {
             if (P.dense) {
-                for (int t = threadIdx.x; t < P.N; t += kTailThreads) {
+                for (int t = gtid; t < P.N; t += NTH) {
                     double acc = 0;
-                    for (int c = 0; c < P.N; ++c) acc += P.inv[(size_t)c * P.N + t] * L.r[c];
+                    for (int c = 0; c < P.N; ++c) acc += P.inv[(size_t)c * P.N + t] * __ldcg(L.r + c);
                     L.x2[t] = acc;
                 }
             } else {            // no dense inverse: five damped block-Jacobi sweeps (a fixed linear operator)
-                tail_rows<0>(L, nullptr, L.x, omega);
-                __syncthreads();
+                tail_rows<0>(L, nullptr, L.x, omega, gtid);
+                tail_sync();
                 for (int k = 0; k < 2; ++k) {
-                    tail_rows<2>(L, L.x, L.x2, omega);
-                    __syncthreads();
-                    tail_rows<2>(L, L.x2, L.x, omega);
-                    __syncthreads();
+                    tail_rows<2>(L, L.x, L.x2, omega, gtid);
+                    tail_sync();
+                    tail_rows<2>(L, L.x2, L.x, omega, gtid);
+                    tail_sync();
                 }
-                for (int t = threadIdx.x; t < L.n * D; t += kTailThreads) L.x2[t] = L.x[t];
+                for (int t = gtid; t < L.n * D; t += NTH) L.x2[t] = __ldcg(L.x + t);
             }
-            __syncthreads();
+            tail_sync();
             break;
         }
-        tail_rows<0>(L, nullptr, L.x, omega);
-        __syncthreads();
-        tail_rows<1>(L, L.x, L.t, omega);
-        __syncthreads();
+        tail_rows<0>(L, nullptr, L.x, omega, gtid);
+        tail_sync();
+        tail_rows<1>(L, L.x, L.t, omega, gtid);
+        tail_sync();
         const TailLevel &C = P.lev[l + 1];
-        for (int I = threadIdx.x; I < C.n; I += kTailThreads) {
+        for (int I = gtid; I < C.n; I += NTH) {
             double acc[D];
 #pragma unroll
             for (int c = 0; c < D; ++c) acc[c] = 0;
@@ -419,7 +435,7 @@ __global__ void __launch_bounds__(kTailThreads) amg_tail_kernel(const __grid_con
                 const Rel S = load_rel(C.rel, C.pad_fine, i);
                 double w[D], u[D];
 #pragma unroll
-                for (int c = 0; c < D; ++c) w[c] = L.t[(size_t)i * D + c];
+                for (int c = 0; c < D; ++c) w[c] = __ldcg(L.t + (size_t)i * D + c);
                 adT_apply(S, w, u);
 #pragma unroll
                 for (int c = 0; c < D; ++c) acc[c] += u[c];
@@ -427,25 +443,25 @@ __global__ void __launch_bounds__(kTailThreads) amg_tail_kernel(const __grid_con
 #pragma unroll
             for (int c = 0; c < D; ++c) C.r[(size_t)I * D + c] = acc[c];
         }
-        __syncthreads();
+        tail_sync();
     }
     // every level leaves its result in x2 (the host swaps x and x2 after the launch)
     for (int l = last - 1; l >= 0; --l) {
         const TailLevel &L = P.lev[l];
         const TailLevel &C = P.lev[l + 1];
-        for (int i = threadIdx.x; i < L.n; i += kTailThreads) {
+        for (int i = gtid; i < L.n; i += NTH) {
             const Rel S = load_rel(C.rel, C.pad_fine, i);
             const int I = C.agg[i];
             double v[D], u[D];
 #pragma unroll
-            for (int c = 0; c < D; ++c) v[c] = C.x2[(size_t)I * D + c];
+            for (int c = 0; c < D; ++c) v[c] = __ldcg(C.x2 + (size_t)I * D + c);
             ad_apply(S, v, u);
 #pragma unroll
-            for (int c = 0; c < D; ++c) L.x[(size_t)i * D + c] += u[c];
+            for (int c = 0; c < D; ++c) L.x[(size_t)i * D + c] = __ldcg(L.x + (size_t)i * D + c) + u[c];
         }
-        __syncthreads();
-        tail_rows<2>(L, L.x, L.x2, omega);
-        __syncthreads();
+        tail_sync();
+        tail_rows<2>(L, L.x, L.x2, omega, gtid);
+        tail_sync();
     }
 }
 
@@ -615,7 +631,7 @@ int amg_apply(s3o_problem *p, int init) {
             T.rowptr = L.rowptr; T.colidx = L.colidx; T.mem_ptr = L.mem_ptr; T.mem_idx = L.mem_idx; T.agg = L.agg;
             T.A = L.A; T.Dinv = L.Dinv; T.rel = L.rel; T.r = L.r; T.x = L.x; T.x2 = L.x2; T.t = L.t;
         }
-        amg_tail_kernel<<<1, kTailThreads, 0, s>>>(P, kOmega, sc, chk);
+        amg_tail_kernel<<<kTailCtas, kTailThreads, 0, s>>>(P, kOmega, sc, chk);
         for (int l = lt; l < nl; ++l) std::swap(st->lev[l].x, st->lev[l].x2);
         ++launches;
     }

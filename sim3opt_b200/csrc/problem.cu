@@ -341,6 +341,10 @@ int s3o_create(int kind, int device, s3o_problem **out) {
     if (const char *v = getenv("S3O_SPMV_VERSION")) p->spmv_version = atoi(v);
     if (const char *v = getenv("S3O_SPMV_GRID")) p->spmv_grid_cap = atoi(v);
     if (const char *v = getenv("S3O_SPMV4_CFG")) spmv4_set_cfg(atoi(v));
+    if (const char *v = getenv("S3O_PRECOND")) {        // experiment switch; s3o_set_preconditioner overrides it
+        const int k = atoi(v);
+        if (k >= S3O_PRECOND_AUTO && k <= S3O_PRECOND_MULTILEVEL && (k != S3O_PRECOND_MULTILEVEL || kind == S3O_KIND_SIM3)) p->precond = k;
+    }
     for (auto &ev : p->ev) cudaEventCreate(&ev);
     for (auto &ev : p->spmv_ev) cudaEventCreate(&ev);
     if (dev_alloc(&p->d_sc, 1) || dev_alloc(&p->d_partials, 2 * kMaxPartials) ||

@@ -114,6 +114,12 @@ def build_hierarchy(A, R, t, s, d=7, min_size=40, max_levels=10, verbose=True):
         pat = sp.csr_matrix((np.ones(len(pat.indices)), pat.indices, pat.indptr), shape=(n, n))
         agg, roots = aggregate(pat, n)
         nc = len(roots)
+        if os.environ.get("DOUBLE") and (os.environ["DOUBLE"] == "all" or len(levels) == 1):
+            # aggressive coarsening: aggregate the aggregate graph once more, keep the first-pass root of the coarse root
+            Pa = sp.csr_matrix((np.ones(n), (np.arange(n), agg)), shape=(n, nc))
+            pat2 = (Pa.T @ pat @ Pa).tocsr(); pat2.data[:] = 1
+            agg2, roots2 = aggregate(pat2, nc)
+            agg = agg2[agg]; roots = roots[roots2]; nc = len(roots)
         Rr, tr, sr = R[roots][agg], t[roots][agg], s[roots][agg]
         Rrel, trel, srel = rel_pose(R, t, s, Rr, tr, sr)
         Pb = adjoint(Rrel, trel, srel)
