@@ -208,10 +208,8 @@ def run_ours(args):
     prob.set_jacobian_mode(s3.JAC_ANALYTIC)
     prob.set_pcg(args.pcg_tol, args.pcg_max_iter)
     precond = {"auto": s3.PRECOND_AUTO, "block-jacobi": s3.PRECOND_BLOCK_JACOBI, "multilevel": s3.PRECOND_MULTILEVEL}[args.precond]
-    if world > 1:
-        precond = s3.PRECOND_BLOCK_JACOBI        # the multilevel correction is single-GPU so far
     prob.set_preconditioner(precond)
-    multilevel = precond == s3.PRECOND_MULTILEVEL or (precond == s3.PRECOND_AUTO and world == 1 and nv >= 20000)
+    multilevel = precond == s3.PRECOND_MULTILEVEL or (precond == s3.PRECOND_AUTO and nv >= 20000)
     if world > 1:
         # vertex-range partition: rank 0 creates the NCCL id, every rank joins before set_edges
         box = [s3.comm_unique_id() if rank == 0 else None]
@@ -371,7 +369,7 @@ def run_ours(args):
                                     + f" PCG rel_tol={args.pcg_tol} max_iter={args.pcg_max_iter}",
                    "math_mode": "corrected", "l2_policy": "inputs larger than L2 (Hessian blocks %.2f GB)" % (392 * nb / 1e9),
                    "step": "one LM iteration; solves restart from a device snapshot on the 1e-6 gain rule",
-                   "partition": "none" if world == 1 else f"vertex range over {world} ranks, NCCL halo + all-reduce"},
+                   "partition": "none" if world == 1 else f"vertex range over {world} ranks, NCCL halo + all-reduce; coarse levels of the multilevel PCG replicated"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "LM iterations/s", "h2d_bytes_per_step": nv * 64, "d2h_bytes_per_step": nv * 64 + 160,
                 "steps": e2e_steps},

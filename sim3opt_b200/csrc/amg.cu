@@ -5,7 +5,10 @@
 // Per PCG iteration:          restriction of r  ->  V(1,1)-cycle on the coarse levels  ->
 //                             z = D^-1 r + P0 x_1,  r.z  and the PCG scalar bookkeeping.
 // All sums run in list order (no atomics), so a solve is bitwise reproducible.
+#include <algorithm>
+
 #include "amg.h"
+#include "comm.h"
 #include "problem.h"
 #include "reduce.cuh"
 #include "sim3_math.cuh"
@@ -38,6 +41,12 @@ struct AmgState {
     double *d_dense = nullptr;      // inverse of the coarsest operator, [N][N]
     bool dense = false;
     bool frames_valid = false;
+    // partitioned solve: the fine level is local (owned + ghost rows), level 1 and below are replicated.
+    // Rank q computes the level-1 rows [crow[q], crow[q+1]) (its own aggregates); the segments are
+    // exchanged with in-place all-gathers: the residual r_1 every PCG iteration, the operator A_1 every trial.
+    bool dist = false;
+    int n_own = 0;
+    std::vector<size_t> r_off, r_cnt, a_off, a_cnt;
 };
 
 namespace {
@@ -115,7 +124,8 @@ __global__ void __launch_bounds__(128, 4) amg_galerkin_kernel(const double *__re
                                                               int pad, double lambda, int nub,
                                                               const int32_t *__restrict__ gal_ptr, const int32_t *__restrict__ gal_ent,
                                                               const int32_t *__restrict__ gal_out,
-                                                              const int32_t *__restrict__ gal_mirror, double *__restrict__ Ac) {
+                                                              const int32_t *__restrict__ gal_mirror, double *__restrict__ Ac,
+                                                              int write_mirror) {
     const int ub = blockIdx.x * (blockDim.x / 8) + threadIdx.x / 8;
     const int c = threadIdx.x & 7;
     if (ub >= nub || c >= D) return;
@@ -170,12 +180,24 @@ __global__ void __launch_bounds__(128, 4) amg_galerkin_kernel(const double *__re
     double *out = Ac + (size_t)gal_out[ub] * DD;
 #pragma unroll
     for (int r = 0; r < D; ++r) out[r * D + c] = acc[r];
-    const int m = gal_mirror[ub];
+    const int m = write_mirror ? gal_mirror[ub] : -1;
     if (m >= 0) {
         double *om = Ac + (size_t)m * DD;
 #pragma unroll
         for (int r = 0; r < D; ++r) om[c * D + r] = acc[r];
     }
+}
+
+// lower blocks of a level from its upper blocks (partitioned solve: after the all-gather of A_1)
+__global__ void amg_mirror_kernel(int nub, const int32_t *__restrict__ gal_out, const int32_t *__restrict__ gal_mirror,
+                                  double *__restrict__ A) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ub = t / DD, e = t - ub * DD;
+    if (ub >= nub) return;
+    const int m = gal_mirror[ub];
+    if (m < 0) return;
+    const int r = e / D, c = e - r * D;
+    A[(size_t)m * DD + c * D + r] = A[(size_t)gal_out[ub] * DD + e];
 }
 
 // ---- dense inverse of the coarsest operator (one CTA, matrix in shared memory) -----------------
@@ -298,7 +320,7 @@ __global__ void __launch_bounds__(NT) amg_prolong0_kernel(int nf, const int32_t 
                                                           int pad, const double *__restrict__ xc, const double *__restrict__ r,
                                                           double *__restrict__ z, double *__restrict__ p_out,
                                                           double *__restrict__ partials, DevScalars *sc, int init, double tol,
-                                                          int max_iter) {
+                                                          int max_iter, int dist) {
     __shared__ double sh[32];
     if (!init && sc->done) return;
     double lrz = 0;
@@ -323,7 +345,8 @@ __global__ void __launch_bounds__(NT) amg_prolong0_kernel(int nf, const int32_t 
         const double rz = sum_partials<NT>(partials, gridDim.x, sh);
         if (threadIdx.x == 0) {
             sc->rz_new = rz;
-            if (init) fin_init(sc, tol, max_iter);
+            if (dist) {}                       // partitioned solve: the caller all-reduces r.z, then finishes
+            else if (init) fin_init(sc, tol, max_iter);
             else fin_update(sc);
         }
     }
@@ -475,6 +498,68 @@ void free_level(LevelDev &L) {
     dev_free(L.rel); dev_free(L.A); dev_free(L.Dinv); dev_free(L.r); dev_free(L.x); dev_free(L.x2); dev_free(L.t);
 }
 
+// Partitioned solve: rewrite level 0 of the global hierarchy in this rank's local indices.
+// Local fine indices are the rank's Hessian rows (owned first, then ghosts); coarse indices stay global.
+void localize_fine_level(s3o_problem *p, const HostStructure &Sg, AmgState *st) {
+    const PartitionPlan &P = p->plan;
+    const HostStructure &S = p->S;
+    AmgHostLevel &H = st->host[0];
+    const int nloc = S.nf, world = P.world;
+    st->dist = true;
+    st->n_own = P.n_own;
+    // coarse rows per rank: aggregates are numbered by ascending root, roots never leave their rank's range
+    std::vector<int> crow(world + 1, H.n);
+    for (int q = 0; q <= world; ++q)
+        crow[q] = (int)(std::lower_bound(H.root.begin(), H.root.end(), (int32_t)std::min<int64_t>((int64_t)q * P.seg, P.nf_global)) - H.root.begin());
+    crow[world] = H.n;
+    st->r_off.resize(world); st->r_cnt.resize(world); st->a_off.resize(world); st->a_cnt.resize(world);
+    for (int q = 0; q < world; ++q) {
+        st->r_off[q] = (size_t)crow[q] * D;
+        st->r_cnt[q] = (size_t)(crow[q + 1] - crow[q]) * D;
+        st->a_off[q] = (size_t)H.rowptr[crow[q]] * DD;
+        st->a_cnt[q] = (size_t)(H.rowptr[crow[q + 1]] - H.rowptr[crow[q]]) * DD;
+    }
+    const int Ilo = crow[P.rank], Ihi = crow[P.rank + 1];
+    auto local_of = [&](int g) { return P.lhidx[Sg.free2v[g]]; };     // global Hessian index -> local index (or -1)
+    // aggregate (global coarse id) of every local vertex
+    std::vector<int32_t> agg(nloc);
+    for (int li = 0; li < nloc; ++li) agg[li] = H.agg[P.ghidx[S.free2v[li]]];
+    // members of my aggregates, in local indices (all owned)
+    std::vector<int32_t> mem_ptr(H.n + 1, 0), mem_idx;
+    for (int I = 0; I < H.n; ++I) {
+        if (I >= Ilo && I < Ihi)
+            for (int m = H.mem_ptr[I]; m < H.mem_ptr[I + 1]; ++m) mem_idx.push_back(local_of(H.mem_idx[m]));
+        mem_ptr[I + 1] = (int32_t)mem_idx.size();
+    }
+    // Galerkin entries of my coarse rows, with local block / vertex indices
+    std::vector<int32_t> gptr(H.nub + 1, 0), gent, gi, gj;
+    for (int ub = 0; ub < H.nub; ++ub) {
+        if (H.gal_I[ub] >= Ilo && H.gal_I[ub] < Ihi) {
+            for (int e = H.gal_ptr[ub]; e < H.gal_ptr[ub + 1]; ++e) {
+                const int flag = H.gal_ent[e] & 3;
+                const int li = local_of(H.gal_i[e]), lj = local_of(H.gal_j[e]);
+                int k = S.rowptr[li];                                   // diagonal block
+                if (li != lj) {
+                    const int32_t *b = S.colidx.data() + S.rowptr[li] + 1, *en = S.colidx.data() + S.rowptr[li + 1];
+                    k = (int)(std::lower_bound(b, en, lj) - S.colidx.data());
+                }
+                gent.push_back((k << 2) | flag);
+                gi.push_back(li);
+                gj.push_back(lj);
+            }
+        }
+        gptr[ub + 1] = (int32_t)gent.size();
+    }
+    H.n_fine = nloc;
+    H.agg.swap(agg);
+    H.mem_ptr.swap(mem_ptr);
+    H.mem_idx.swap(mem_idx);
+    H.gal_ptr.swap(gptr);
+    H.gal_ent.swap(gent);
+    H.gal_i.swap(gi);
+    H.gal_j.swap(gj);
+}
+
 }  // namespace
 
 void amg_destroy(s3o_problem *p) {
@@ -492,10 +577,19 @@ int amg_levels(const s3o_problem *p) { return p->amg ? (int)p->amg->lev.size() :
 // levels when the graph is too small to coarsen (the caller then stays with block-Jacobi).
 int amg_setup(s3o_problem *p) {
     if (p->amg) return S3O_OK;
-    if (p->kind != S3O_KIND_SIM3 || p->dist) { set_error("multilevel preconditioner: Sim3 problems on one GPU only"); return S3O_ERR_UNSUPPORTED; }
+    if (p->kind != S3O_KIND_SIM3) { set_error("multilevel preconditioner: Sim3 problems only"); return S3O_ERR_UNSUPPORTED; }
     AmgState *st = new AmgState();
     p->amg = st;
-    amg_build_hierarchy(p->S, kCoarsestMax, kMaxLevels, st->host);
+    if (p->dist) {
+        // every rank builds the same global hierarchy (aggregates confined to the ranks' vertex ranges),
+        // then keeps the part of the fine transfer that touches its own rows
+        HostStructure Sg;
+        build_structure_host(p->nv, p->fixed.data(), (int)p->gv0.size(), p->gv0.data(), p->gv1.data(), Sg);
+        amg_build_hierarchy(Sg, kCoarsestMax, kMaxLevels, st->host, p->plan.seg);
+        if (!st->host.empty()) localize_fine_level(p, Sg, st);
+    } else {
+        amg_build_hierarchy(p->S, kCoarsestMax, kMaxLevels, st->host);
+    }
     const int nl = (int)st->host.size();
     if (nl == 0) return S3O_OK;
     int rc = up(p, &st->d_vid0, p->S.free2v);
@@ -572,12 +666,23 @@ int amg_update_values(s3o_problem *p, double lambda) {
         LevelDev &L = st->lev[l];
         const int grid = (L.nub + 15) / 16;
         if (l == 0)
+        {
             amg_galerkin_kernel<true><<<grid, 128, 0, p->stream>>>(p->d_H, L.gal_i, L.gal_j, L.rel, L.pad_fine, lambda,
-                                                                    L.nub, L.gal_ptr, L.gal_ent, L.gal_out, L.gal_mirror, L.A);
+                                                                    L.nub, L.gal_ptr, L.gal_ent, L.gal_out, L.gal_mirror, L.A,
+                                                                    st->dist ? 0 : 1);
+            if (st->dist) {     // every rank computed the upper blocks of its own coarse rows
+                if (comm_allgatherv(p->comm, L.A, st->a_off.data(), st->a_cnt.data(), p->stream)) {
+                    set_error("%s", comm_last_error());
+                    return S3O_ERR_NCCL;
+                }
+                amg_mirror_kernel<<<(L.nub * DD + 255) / 256, 256, 0, p->stream>>>(L.nub, L.gal_out, L.gal_mirror, L.A);
+                ++launches;
+            }
+        }
         else {
             const LevelDev &F = st->lev[l - 1];
             amg_galerkin_kernel<false><<<grid, 128, 0, p->stream>>>(F.A, L.gal_i, L.gal_j, L.rel, L.pad_fine, 0.0, L.nub,
-                                                                     L.gal_ptr, L.gal_ent, L.gal_out, L.gal_mirror, L.A);
+                                                                     L.gal_ptr, L.gal_ent, L.gal_out, L.gal_mirror, L.A, 1);
         }
         launch_precond(D, L.A, L.dpos, L.n, 0.0, L.Dinv, p->d_sc, p->stream);
         launches += 2;
@@ -609,6 +714,10 @@ int amg_apply(s3o_problem *p, int init) {
         LevelDev &L = st->lev[0];
         amg_restrict_kernel<<<(L.n + 127) / 128, 128, 0, s>>>(L.n, L.mem_ptr, L.mem_idx, L.rel, L.pad_fine, p->d_r, L.r, sc, chk);
         ++launches;
+        if (st->dist && comm_allgatherv(p->comm, L.r, st->r_off.data(), st->r_cnt.data(), s)) {
+            set_error("%s", comm_last_error());
+            return S3O_ERR_NCCL;
+        }
     }
     for (int l = 0; l < lt; ++l) {
         LevelDev &L = st->lev[l];
@@ -646,10 +755,12 @@ int amg_apply(s3o_problem *p, int init) {
     {
         LevelDev &L = st->lev[0];
         constexpr int NT = 256;
-        int grid = (L.n_fine + NT - 1) / NT;
+        const int rows = st->dist ? st->n_own : L.n_fine;
+        int grid = (rows + NT - 1) / NT;
         if (grid > 148 * 8) grid = 148 * 8;
-        amg_prolong0_kernel<NT><<<grid, NT, 0, s>>>(L.n_fine, L.agg, L.rel, L.pad_fine, L.x, p->d_r, p->d_z, init ? p->d_p : nullptr,
-                                                    p->d_partials, p->d_sc, init, p->pcg_tol, p->pcg_max_iter);
+        if (grid < 1) grid = 1;
+        amg_prolong0_kernel<NT><<<grid, NT, 0, s>>>(rows, L.agg, L.rel, L.pad_fine, L.x, p->d_r, p->d_z, init ? p->d_p : nullptr,
+                                                    p->d_partials, p->d_sc, init, p->pcg_tol, p->pcg_max_iter, st->dist ? 1 : 0);
         ++launches;
     }
     return check_launch(p, launches);

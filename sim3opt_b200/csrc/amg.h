@@ -44,6 +44,8 @@ struct AmgHostLevel {
 
 // Builds the hierarchy below the BSR-upper structure S (level 0).  Stops when a level has at
 // most `coarsest_max` vertices, when aggregation stalls, or after `max_levels` transfers.
-void amg_build_hierarchy(const HostStructure &S, int coarsest_max, int max_levels, std::vector<AmgHostLevel> &levels);
+// seg > 0 (partitioned solve): level-0 aggregates stay inside the index segments [r*seg, (r+1)*seg).
+void amg_build_hierarchy(const HostStructure &S, int coarsest_max, int max_levels, std::vector<AmgHostLevel> &levels,
+                         int seg = 0);
 
 }  // namespace s3o

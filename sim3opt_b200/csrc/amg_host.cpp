@@ -13,12 +13,13 @@ struct Pattern {            // blocks of one level
     bool upper = false;     // level 0: only (i <= j) stored
 };
 
-// adjacency (both directions, self excluded), neighbours ascending
-void build_adjacency(const Pattern &F, std::vector<int32_t> &ptr, std::vector<int32_t> &idx) {
+// adjacency (both directions, self excluded), neighbours ascending; seg > 0: pairs whose ends lie in
+// different index segments (ranks of the partitioned solve) are left out, so no aggregate crosses a cut
+void build_adjacency(const Pattern &F, int seg, std::vector<int32_t> &ptr, std::vector<int32_t> &idx) {
     ptr.assign(F.n + 1, 0);
     for (int k = 0; k < F.nblk; ++k) {
         const int i = F.brow[k], j = F.bcol[k];
-        if (i == j) continue;
+        if (i == j || (seg > 0 && i / seg != j / seg)) continue;
         ptr[i + 1]++;
         if (F.upper) ptr[j + 1]++;
     }
@@ -27,7 +28,7 @@ void build_adjacency(const Pattern &F, std::vector<int32_t> &ptr, std::vector<in
     std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
     for (int k = 0; k < F.nblk; ++k) {
         const int i = F.brow[k], j = F.bcol[k];
-        if (i == j) continue;
+        if (i == j || (seg > 0 && i / seg != j / seg)) continue;
         idx[fill[i]++] = j;
         if (F.upper) idx[fill[j]++] = i;
     }
@@ -65,6 +66,16 @@ void aggregate(int n, const std::vector<int32_t> &ptr, const std::vector<int32_t
         if (join[i] >= 0) agg[i] = join[i];
         else { agg[i] = (int)root.size(); root.push_back(i); }
     }
+    // number the aggregates by ascending root, so coarse indices follow the fine order (and a
+    // vertex-range partition of the fine level induces contiguous coarse ranges)
+    const int na = (int)root.size();
+    std::vector<int32_t> order(na), newid(na);
+    for (int a = 0; a < na; ++a) order[a] = a;
+    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return root[a] < root[b]; });
+    std::vector<int32_t> sorted_root(na);
+    for (int t = 0; t < na; ++t) { newid[order[t]] = t; sorted_root[t] = root[order[t]]; }
+    root.swap(sorted_root);
+    for (int i = 0; i < n; ++i) agg[i] = newid[agg[i]];
 }
 
 int find_col(const AmgHostLevel &L, int I, int J) {
@@ -74,7 +85,8 @@ int find_col(const AmgHostLevel &L, int I, int J) {
 
 }  // namespace
 
-void amg_build_hierarchy(const HostStructure &S, int coarsest_max, int max_levels, std::vector<AmgHostLevel> &levels) {
+void amg_build_hierarchy(const HostStructure &S, int coarsest_max, int max_levels, std::vector<AmgHostLevel> &levels,
+                         int seg) {
     levels.clear();
     if (S.nf == 0) return;
     levels.reserve((size_t)max_levels + 1);     // the loop keeps pointers into levels.back()
@@ -87,7 +99,7 @@ void amg_build_hierarchy(const HostStructure &S, int coarsest_max, int max_level
 
     while (F.n > coarsest_max && (int)levels.size() < max_levels) {
         std::vector<int32_t> aptr, aidx;
-        build_adjacency(F, aptr, aidx);
+        build_adjacency(F, levels.empty() ? seg : 0, aptr, aidx);
         AmgHostLevel L;
         L.n_fine = F.n;
         aggregate(F.n, aptr, aidx, L.agg, L.root);

@@ -3,7 +3,8 @@
 // (bench.py / tests, via torch.distributed) broadcasts.  Collectives used on the data path:
 //   all-reduce of 1-2 fp64 scalars (PCG dot products, chi2, computeScale, max diagonal),
 //   grouped send/recv of the halo entries of p before every SpMV,
-//   all-gather of the step x before the retraction.
+//   all-gather of the step x before the retraction,
+//   in-place all-gather of unequal segments (grouped broadcasts) for the multilevel preconditioner.
 #include <dlfcn.h>
 #include <nccl.h>
 #include <stdio.h>
@@ -21,6 +22,7 @@ struct Api {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -52,6 +54,7 @@ int comm_load() {
     S3O_SYM(CommDestroy, "ncclCommDestroy")
     S3O_SYM(AllReduce, "ncclAllReduce")
     S3O_SYM(AllGather, "ncclAllGather")
+    S3O_SYM(Broadcast, "ncclBroadcast")
     S3O_SYM(Send, "ncclSend")
     S3O_SYM(Recv, "ncclRecv")
     S3O_SYM(GroupStart, "ncclGroupStart")
@@ -102,6 +105,19 @@ int comm_allreduce_max(Comm &c, double *buf, size_t count, cudaStream_t st) {
 int comm_allgather(Comm &c, const double *send, double *recv, size_t count_per_rank, cudaStream_t st) {
     ncclResult_t r = g.AllGather(send, recv, count_per_rank, ncclDouble, (ncclComm_t)c.nccl, st);
     return r == ncclSuccess ? 0 : fail("ncclAllGather", r);
+}
+
+// in-place all-gather of unequal segments: rank q owns buf[off[q] .. off[q]+count[q])
+int comm_allgatherv(Comm &c, double *buf, const size_t *off, const size_t *count, cudaStream_t st) {
+    ncclResult_t r = g.GroupStart();
+    if (r != ncclSuccess) return fail("ncclGroupStart", r);
+    for (int q = 0; q < c.world; ++q) {
+        if (count[q] == 0) continue;
+        r = g.Broadcast(buf + off[q], buf + off[q], count[q], ncclDouble, q, (ncclComm_t)c.nccl, st);
+        if (r != ncclSuccess) { g.GroupEnd(); return fail("ncclBroadcast", r); }
+    }
+    r = g.GroupEnd();
+    return r == ncclSuccess ? 0 : fail("ncclGroupEnd", r);
 }
 
 int comm_halo(Comm &c, const double *sendbuf, const int *send_off, const int *send_count, double *recvbuf,

@@ -162,8 +162,9 @@ int do_linearize(s3o_problem *p) {
 namespace s3o {
 // multilevel preconditioner: Sim3 graphs on one GPU; AUTO switches it on for large graphs
 bool wants_multilevel(const s3o_problem *p) {
-    return !p->dist && p->kind == S3O_KIND_SIM3 &&
-           (p->precond == S3O_PRECOND_MULTILEVEL || (p->precond == S3O_PRECOND_AUTO && p->S.nf >= 20000));
+    const int nf = p->dist ? p->plan.nf_global : p->S.nf;
+    return p->kind == S3O_KIND_SIM3 &&
+           (p->precond == S3O_PRECOND_MULTILEVEL || (p->precond == S3O_PRECOND_AUTO && nf >= 20000));
 }
 
 // Solve (H + lambda I) x = b; leaves x in d_x.  Returns the PCG status in *status (1 converged,
@@ -503,6 +504,8 @@ int s3o_set_edges(s3o_problem *p, int n, const int32_t *v0, const int32_t *v1, c
         // keep only the edges that touch a vertex this rank owns (cut edges live on both sides)
         build_partition_plan(p->nv, p->fixed.data(), n, v0, v1, p->comm.rank, p->comm.world, p->plan);
         const PartitionPlan &P = p->plan;
+        p->gv0.assign(v0, v0 + n);
+        p->gv1.assign(v1, v1 + n);
         const int nl = (int)P.local_edges.size();
         const int ed = p->est_dim, dd = p->d * p->d;
         p->v0.resize(nl); p->v1.resize(nl);

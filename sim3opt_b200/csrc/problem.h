@@ -59,6 +59,7 @@ struct s3o_problem {
     bool dist = false;
     PartitionPlan plan;
     int user_ne = 0;                       // edges passed by the caller (plan.local_edges index into them)
+    std::vector<int32_t> gv0, gv1;         // all edges' endpoints (the multilevel hierarchy is built on the global graph)
     int32_t *d_ghidx = nullptr, *d_send_idx = nullptr;
     uint8_t *d_primary = nullptr;
     double *d_sendbuf = nullptr, *d_xg = nullptr;

@@ -11,7 +11,8 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-def test_partitioned_solve_matches_single_gpu():
+@pytest.mark.parametrize("precond", [1, 2])     # block-Jacobi, multilevel (replicated coarse levels)
+def test_partitioned_solve_matches_single_gpu(precond):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -20,7 +21,7 @@ def test_partitioned_solve_matches_single_gpu():
     port = s.getsockname()[1]
     s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "dist_check.py"), "30", "80", "5"]
+           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "dist_check.py"), "30", "80", "5", str(precond)]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert "DIST_CHECK PASS" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
     assert "ESTIMATES_IDENTICAL_ACROSS_RANKS True" in out.stdout

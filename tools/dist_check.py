@@ -1,7 +1,7 @@
 """Partitioned solve vs single-GPU solve of the same graph (run under torchrun, one rank per GPU).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        tools/dist_check.py [laps] [poses_per_lap] [lm_iters]
+        tools/dist_check.py [laps] [poses_per_lap] [lm_iters] [preconditioner 0|1|2]
 Prints "DIST_CHECK PASS" on rank 0 when chi2 histories agree to 1e-9 relative and the estimates to 1e-8.
 """
 import os
@@ -20,6 +20,7 @@ def main():
     laps = int(sys.argv[1]) if len(sys.argv) > 1 else 40
     per = int(sys.argv[2]) if len(sys.argv) > 2 else 100
     iters = int(sys.argv[3]) if len(sys.argv) > 3 else 6
+    precond = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -31,6 +32,7 @@ def main():
         p = s3.Problem(s3.KIND_SIM3, device=local)
         p.set_math_mode(s3.MATH_CORRECTED)
         p.set_pcg(1e-12, 20000)
+        p.set_preconditioner(precond)
         if comm:
             p.set_comm(rank, world, box[0])
         p.set_vertices(g["est"], g["fixed"])
