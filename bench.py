@@ -46,7 +46,7 @@ MAX_LM_ITERS = 30
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="s1m", choices=sorted(WORKLOADS))
@@ -379,6 +379,11 @@ def run_ours(args):
         "pcg_iterations": int(st["pcg_iterations"]), "lm_trials": int(st["lm_trials"]),
         "phase_ms": {"linearize": st["ms_linearize"], "solve": st["ms_solve"], "update_chi2": st["ms_update"]},
         "solves_completed": len(drv.solves),
+        # time-to-converge (BASELINE metric, second half): device time of one solve from the initial guess to
+        # g2o's relative-gain stop (1e-6), averaged over the solves completed inside the timed region
+        "time_to_converge_s": (ms * 1e-3 * sum(len(sv) for sv in drv.solves) / args.steps / len(drv.solves)) if drv.solves else None,
+        "lm_iterations_to_converge": (sum(len(sv) for sv in drv.solves) / len(drv.solves)) if drv.solves else None,
+        "final_chi2": drv.solves[0][-1] if drv.solves else None,
         "step_trace": drv.trace, "e2e_step_trace": e2e_trace,
         "chi2_history_first_solve": drv.solves[0] if drv.solves else drv.cur,
     }
