@@ -47,6 +47,11 @@ struct AmgState {
     bool dist = false;
     int n_own = 0;
     std::vector<size_t> r_off, r_cnt, a_off, a_cnt;
+    // r_1 goes through ONE equal-count ncclAllGather (padded to the largest segment) plus an unpad
+    // kernel: eight grouped broadcasts cost several times the latency of one all-gather
+    size_t r_max = 0;
+    double *d_rpad = nullptr;       // [world][r_max]
+    int32_t *d_unpad_src = nullptr; // [n_1 * 7] position in d_rpad of every entry of r_1
 };
 
 namespace {
@@ -271,30 +276,52 @@ __global__ void __launch_bounds__(128) amg_row_kernel(int n, const int32_t *__re
     if (act) out[(size_t)i * D + l] = (MODE == 2 ? x[(size_t)i * D + l] : 0.0) + omega * z;
 }
 
+__global__ void amg_unpad_kernel(int n, const int32_t *__restrict__ src, const double *__restrict__ padded,
+                                 double *__restrict__ out, const DevScalars *sc, int check_done) {
+    if (check_done && sc->done) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) out[t] = padded[src[t]];
+}
+
 // ---- transfers ---------------------------------------------------------------------------------
-// r_coarse[I] = sum over members i of Ad(rel_i)^T t_i   (members ascending)
+// r_coarse[I] = sum over members i of Ad(rel_i)^T t_i.  An 8-lane group owns one aggregate: lane m
+// takes members m, m+8, ... (ascending), the eight partial sums are combined by a fixed butterfly,
+// so the result is reproducible.
 __global__ void __launch_bounds__(128) amg_restrict_kernel(int n, const int32_t *__restrict__ mem_ptr,
                                                            const int32_t *__restrict__ mem_idx, const double *__restrict__ rel,
                                                            int pad, const double *__restrict__ t, double *__restrict__ rc,
                                                            const DevScalars *sc, int check_done) {
     if (check_done && sc->done) return;
-    const int I = blockIdx.x * blockDim.x + threadIdx.x;
-    if (I >= n) return;
+    const int I = blockIdx.x * (blockDim.x / 8) + threadIdx.x / 8;
+    const int lane = threadIdx.x & 7;
+    const bool act = I < n;
     double acc[D];
 #pragma unroll
     for (int c = 0; c < D; ++c) acc[c] = 0;
-    for (int m = mem_ptr[I]; m < mem_ptr[I + 1]; ++m) {
-        const int i = mem_idx[m];
-        const Rel S = load_rel(rel, pad, i);
-        double w[D], u[D];
+    if (act) {
+        const int mb = mem_ptr[I], me = mem_ptr[I + 1];
+        for (int m = mb + lane; m < me; m += 8) {
+            const int i = mem_idx[m];
+            const Rel S = load_rel(rel, pad, i);
+            double w[D], u[D];
 #pragma unroll
-        for (int c = 0; c < D; ++c) w[c] = t[(size_t)i * D + c];
-        adT_apply(S, w, u);
+            for (int c = 0; c < D; ++c) w[c] = t[(size_t)i * D + c];
+            adT_apply(S, w, u);
 #pragma unroll
-        for (int c = 0; c < D; ++c) acc[c] += u[c];
+            for (int c = 0; c < D; ++c) acc[c] += u[c];
+        }
     }
 #pragma unroll
-    for (int c = 0; c < D; ++c) rc[(size_t)I * D + c] = acc[c];
+    for (int off = 4; off > 0; off >>= 1) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], off, 8);
+    }
+    if (act && lane < D) {
+        double v = acc[0];
+#pragma unroll
+        for (int c = 1; c < D; ++c) v = (lane == c) ? acc[c] : v;
+        rc[(size_t)I * D + lane] = v;
+    }
 }
 
 // x_i += Ad(rel_i) xc[agg_i]
@@ -518,6 +545,7 @@ void localize_fine_level(s3o_problem *p, const HostStructure &Sg, AmgState *st) 
         st->r_cnt[q] = (size_t)(crow[q + 1] - crow[q]) * D;
         st->a_off[q] = (size_t)H.rowptr[crow[q]] * DD;
         st->a_cnt[q] = (size_t)(H.rowptr[crow[q + 1]] - H.rowptr[crow[q]]) * DD;
+        st->r_max = std::max(st->r_max, st->r_cnt[q]);
     }
     const int Ilo = crow[P.rank], Ihi = crow[P.rank + 1];
     auto local_of = [&](int g) { return P.lhidx[Sg.free2v[g]]; };     // global Hessian index -> local index (or -1)
@@ -567,6 +595,8 @@ void amg_destroy(s3o_problem *p) {
     for (auto &L : p->amg->lev) free_level(L);
     dev_free(p->amg->d_vid0);
     dev_free(p->amg->d_dense);
+    dev_free(p->amg->d_rpad);
+    dev_free(p->amg->d_unpad_src);
     delete p->amg;
     p->amg = nullptr;
 }
@@ -615,10 +645,18 @@ int amg_setup(s3o_problem *p) {
         rc = rc ? rc : dev_alloc(&L.rel, (size_t)NREL * L.pad_fine);
         rc = rc ? rc : dev_alloc(&L.A, (size_t)L.nblk * DD);
         rc = rc ? rc : dev_alloc(&L.Dinv, (size_t)L.n * DD);
-        rc = rc ? rc : dev_alloc(&L.r, (size_t)L.n * D);
+        rc = rc ? rc : dev_alloc(&L.r, (size_t)L.n * D + (l == 0 ? st->r_max : 0));
         rc = rc ? rc : dev_alloc(&L.x, (size_t)L.n * D);
         rc = rc ? rc : dev_alloc(&L.x2, (size_t)L.n * D);
         rc = rc ? rc : dev_alloc(&L.t, (size_t)L.n * D);
+    }
+    if (!rc && st->dist) {
+        const int world = (int)st->r_cnt.size();
+        std::vector<int32_t> src((size_t)st->host[0].n * D);
+        for (int q = 0; q < world; ++q)
+            for (size_t t = 0; t < st->r_cnt[q]; ++t) src[st->r_off[q] + t] = (int32_t)(q * st->r_max + t);
+        rc = up(p, &st->d_unpad_src, src);
+        rc = rc ? rc : dev_alloc(&st->d_rpad, (size_t)world * st->r_max);
     }
     const int nc = st->host.back().n;
     st->dense = nc <= kCoarsestMax;
@@ -712,11 +750,16 @@ int amg_apply(s3o_problem *p, int init) {
     if (lt == nl) lt = nl - 1;  // a large coarsest level: the tail kernel still runs its smoothing sweeps
     {   // fine residual -> level 1
         LevelDev &L = st->lev[0];
-        amg_restrict_kernel<<<(L.n + 127) / 128, 128, 0, s>>>(L.n, L.mem_ptr, L.mem_idx, L.rel, L.pad_fine, p->d_r, L.r, sc, chk);
+        amg_restrict_kernel<<<(L.n + 15) / 16, 128, 0, s>>>(L.n, L.mem_ptr, L.mem_idx, L.rel, L.pad_fine, p->d_r, L.r, sc, chk);
         ++launches;
-        if (st->dist && comm_allgatherv(p->comm, L.r, st->r_off.data(), st->r_cnt.data(), s)) {
-            set_error("%s", comm_last_error());
-            return S3O_ERR_NCCL;
+        if (st->dist) {
+            // my segment starts at L.r + r_off[rank]; the padded tail of the send is ignored by the unpad map
+            if (comm_allgather(p->comm, L.r + st->r_off[p->comm.rank], st->d_rpad, st->r_max, s)) {
+                set_error("%s", comm_last_error());
+                return S3O_ERR_NCCL;
+            }
+            amg_unpad_kernel<<<(L.n * D + 255) / 256, 256, 0, s>>>(L.n * D, st->d_unpad_src, st->d_rpad, L.r, sc, chk);
+            ++launches;
         }
     }
     for (int l = 0; l < lt; ++l) {
@@ -724,7 +767,7 @@ int amg_apply(s3o_problem *p, int init) {
         LevelDev &C = st->lev[l + 1];
         amg_row_kernel<0><<<rows(L.n), 128, 0, s>>>(L.n, L.rowptr, L.colidx, L.A, L.Dinv, L.r, nullptr, L.x, kOmega, sc, chk);
         amg_row_kernel<1><<<rows(L.n), 128, 0, s>>>(L.n, L.rowptr, L.colidx, L.A, L.Dinv, L.r, L.x, L.t, kOmega, sc, chk);
-        amg_restrict_kernel<<<(C.n + 127) / 128, 128, 0, s>>>(C.n, C.mem_ptr, C.mem_idx, C.rel, C.pad_fine, L.t, C.r, sc, chk);
+        amg_restrict_kernel<<<(C.n + 15) / 16, 128, 0, s>>>(C.n, C.mem_ptr, C.mem_idx, C.rel, C.pad_fine, L.t, C.r, sc, chk);
         launches += 3;
     }
     {

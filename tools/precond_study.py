@@ -114,7 +114,8 @@ def build_hierarchy(A, R, t, s, d=7, min_size=40, max_levels=10, verbose=True):
         pat = sp.csr_matrix((np.ones(len(pat.indices)), pat.indices, pat.indptr), shape=(n, n))
         agg, roots = aggregate(pat, n)
         nc = len(roots)
-        if os.environ.get("DOUBLE") and (os.environ["DOUBLE"] == "all" or len(levels) == 1):
+        if os.environ.get("DOUBLE") and (os.environ["DOUBLE"] == "all" or (os.environ["DOUBLE"] == "1" and len(levels) == 1)
+                                         or (os.environ["DOUBLE"] == "coarse" and len(levels) > 1)):
             # aggressive coarsening: aggregate the aggregate graph once more, keep the first-pass root of the coarse root
             Pa = sp.csr_matrix((np.ones(n), (np.arange(n), agg)), shape=(n, nc))
             pat2 = (Pa.T @ pat @ Pa).tocsr(); pat2.data[:] = 1
