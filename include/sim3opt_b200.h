@@ -65,8 +65,11 @@ enum s3o_math_mode { S3O_MATH_REFERENCE = 0, S3O_MATH_CORRECTED = 1 };
 /* Preconditioner of the PCG that stands in for LinearSolverEigen::solve [EXT g2o] (the plug-in slot
  * filled at kitti_surf.cpp:553-558).  BLOCK_JACOBI: (H_ii + lambda I)^-1 per vertex.  MULTILEVEL:
  * block-Jacobi plus an aggregation coarse-space correction on the gauge near-null space
- * delta_i = Ad(S_i S_root^-1) xi (Sim3 problems on one GPU).  AUTO (default): MULTILEVEL for Sim3
- * graphs with >= 20000 free vertices on one GPU, BLOCK_JACOBI otherwise. */
+ * of the graph (Sim3: delta_i = Ad(S_i S_root^-1) xi; scale-trans: (s_i/s_root) diag(1, R_i R_root^T);
+ * scale: s_i/s_root); pose-graph kinds only, also in the partitioned solve (Sim3).  AUTO (default):
+ * MULTILEVEL for graphs with >= 20000 free vertices; smaller Sim3 / scale-trans graphs start with
+ * BLOCK_JACOBI, switch to MULTILEVEL once a solve has needed more than 256 PCG iterations, and back
+ * when a MULTILEVEL solve finishes within 8. */
 enum s3o_preconditioner { S3O_PRECOND_AUTO = 0, S3O_PRECOND_BLOCK_JACOBI = 1, S3O_PRECOND_MULTILEVEL = 2 };
 /* g2o OptimizationAlgorithm::SolverResult */
 enum s3o_solver_result { S3O_RESULT_TERMINATE = 2, S3O_RESULT_OK = 1, S3O_RESULT_FAIL = -1 };

@@ -1,4 +1,4 @@
-// amg.cu -- multilevel preconditioner of the Sim3 pose-graph PCG: device side (see amg.h).
+// amg.cu -- multilevel preconditioner of the pose-graph PCG (Sim3, scale-trans, scale): device side (see amg.h).
 //
 // Values flow per LM trial:   frames (per linearisation)  ->  Galerkin operators level by level
 // ->  block-Jacobi inverses per level  ->  dense inverse of the coarsest level.
@@ -17,7 +17,8 @@ namespace s3o {
 
 namespace {
 
-constexpr int D = 7, DD = 49, NREL = 13;
+#define DD (D * D)       /* D: template parameter in the kernels, p->d in the host code */
+constexpr int NREL = 13;             // doubles of transfer data per vertex: a 3x3 matrix, a 3-vector, a scalar
 constexpr int kCoarsestMax = 16;        // dense inverse held in shared memory: (16*7)^2 doubles = 98 KB
 constexpr int kMaxLevels = 12;
 constexpr double kOmega = 0.7;          // damping of the block-Jacobi smoother on the coarse levels
@@ -27,6 +28,7 @@ struct LevelDev {       // transfer level l -> l+1 plus operator and vectors of 
     int32_t *agg = nullptr, *mem_ptr = nullptr, *mem_idx = nullptr, *vid = nullptr;
     int32_t *rowptr = nullptr, *colidx = nullptr, *blk_row = nullptr, *dpos = nullptr;
     int32_t *gal_ptr = nullptr, *gal_ent = nullptr, *gal_i = nullptr, *gal_j = nullptr, *gal_out = nullptr, *gal_mirror = nullptr;
+    int32_t *gal_order = nullptr;
     double *rel = nullptr;      // [13][pad_fine]: R (row-major), t, s of S_i S_root^-1 for every level-l vertex
     double *A = nullptr, *Dinv = nullptr, *r = nullptr, *x = nullptr, *x2 = nullptr, *t = nullptr;
 };
@@ -68,72 +70,118 @@ __device__ __forceinline__ Rel load_rel(const double *__restrict__ rel, int pad,
     return r;
 }
 
-// out = Ad(S) v,  Ad(S) = [[R,0,0],[[t]x R, sR, -t],[0,0,1]]  on tangents [omega, upsilon, sigma]
-__device__ __forceinline__ void ad_apply(const Rel &S, const double v[7], double out[7]) {
-    double a[3], b[3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        a[r] = S.R[r * 3] * v[0] + S.R[r * 3 + 1] * v[1] + S.R[r * 3 + 2] * v[2];
-        b[r] = S.R[r * 3] * v[3] + S.R[r * 3 + 1] * v[4] + S.R[r * 3 + 2] * v[5];
-    }
-    out[0] = a[0]; out[1] = a[1]; out[2] = a[2];
-    out[3] = (S.t[1] * a[2] - S.t[2] * a[1]) + S.s * b[0] - S.t[0] * v[6];
-    out[4] = (S.t[2] * a[0] - S.t[0] * a[2]) + S.s * b[1] - S.t[1] * v[6];
-    out[5] = (S.t[0] * a[1] - S.t[1] * a[0]) + S.s * b[2] - S.t[2] * v[6];
-    out[6] = v[6];
-}
+// The prolongation block P_i maps the tangent of an aggregate's root to the tangent of member i along
+// the gauge freedom of the graph (a right-multiplied world similarity G):
+//   Sim3 (d=7)        S_i G = exp(delta_i) S_i          =>  P_i = Ad(S_i S_root^-1)
+//   scale-trans (d=4) delta_i = (s_i sigma, s_i R_i c)  =>  P_i = (s_i/s_root) diag(1, R_i R_root^T)
+//   scale (d=1)       delta_i = s_i sigma               =>  P_i = s_i/s_root
+// All three are held as Rel = (3x3 matrix R, 3-vector t, scalar s).
+template <int D> struct Xf;
 
-// out = Ad(S)^T w:  [R^T (a + b x t);  s R^T b;  c - t.b]   for w = [a, b, c]
-__device__ __forceinline__ void adT_apply(const Rel &S, const double w[7], double out[7]) {
-    const double u0 = w[0] + (w[4] * S.t[2] - w[5] * S.t[1]);
-    const double u1 = w[1] + (w[5] * S.t[0] - w[3] * S.t[2]);
-    const double u2 = w[2] + (w[3] * S.t[1] - w[4] * S.t[0]);
+template <> struct Xf<7> {
+    // out = Ad(S) v,  Ad(S) = [[R,0,0],[[t]x R, sR, -t],[0,0,1]]  on tangents [omega, upsilon, sigma]
+    static __device__ __forceinline__ void apply(const Rel &S, const double v[7], double out[7]) {
+        double a[3], b[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        out[c] = S.R[c] * u0 + S.R[3 + c] * u1 + S.R[6 + c] * u2;
-        out[3 + c] = S.s * (S.R[c] * w[3] + S.R[3 + c] * w[4] + S.R[6 + c] * w[5]);
+        for (int r = 0; r < 3; ++r) {
+            a[r] = S.R[r * 3] * v[0] + S.R[r * 3 + 1] * v[1] + S.R[r * 3 + 2] * v[2];
+            b[r] = S.R[r * 3] * v[3] + S.R[r * 3 + 1] * v[4] + S.R[r * 3 + 2] * v[5];
+        }
+        out[0] = a[0]; out[1] = a[1]; out[2] = a[2];
+        out[3] = (S.t[1] * a[2] - S.t[2] * a[1]) + S.s * b[0] - S.t[0] * v[6];
+        out[4] = (S.t[2] * a[0] - S.t[0] * a[2]) + S.s * b[1] - S.t[1] * v[6];
+        out[5] = (S.t[0] * a[1] - S.t[1] * a[0]) + S.s * b[2] - S.t[2] * v[6];
+        out[6] = v[6];
     }
-    out[6] = w[6] - (S.t[0] * w[3] + S.t[1] * w[4] + S.t[2] * w[5]);
-}
+    // out = Ad(S)^T w:  [R^T (a + b x t);  s R^T b;  c - t.b]   for w = [a, b, c]
+    static __device__ __forceinline__ void applyT(const Rel &S, const double w[7], double out[7]) {
+        const double u0 = w[0] + (w[4] * S.t[2] - w[5] * S.t[1]);
+        const double u1 = w[1] + (w[5] * S.t[0] - w[3] * S.t[2]);
+        const double u2 = w[2] + (w[3] * S.t[1] - w[4] * S.t[0]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            out[c] = S.R[c] * u0 + S.R[3 + c] * u1 + S.R[6 + c] * u2;
+            out[3 + c] = S.s * (S.R[c] * w[3] + S.R[3 + c] * w[4] + S.R[6 + c] * w[5]);
+        }
+        out[6] = w[6] - (S.t[0] * w[3] + S.t[1] * w[4] + S.t[2] * w[5]);
+    }
+};
 
-// ---- frames: rel_i = S_i S_root(i)^-1 --------------------------------------------------------
-__global__ void amg_rel_kernel(const double *__restrict__ est, int nv_pad, const int32_t *__restrict__ vid_fine,
-                               const int32_t *__restrict__ agg, const int32_t *__restrict__ vid_coarse, int n_fine,
-                               int pad, double *__restrict__ rel) {
+template <> struct Xf<4> {      // P = s diag(1, R)
+    static __device__ __forceinline__ void apply(const Rel &S, const double v[4], double out[4]) {
+        out[0] = S.s * v[0];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) out[1 + r] = S.s * (S.R[r * 3] * v[1] + S.R[r * 3 + 1] * v[2] + S.R[r * 3 + 2] * v[3]);
+    }
+    static __device__ __forceinline__ void applyT(const Rel &S, const double w[4], double out[4]) {
+        out[0] = S.s * w[0];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) out[1 + c] = S.s * (S.R[c] * w[1] + S.R[3 + c] * w[2] + S.R[6 + c] * w[3]);
+    }
+};
+
+template <> struct Xf<1> {      // P = s
+    static __device__ __forceinline__ void apply(const Rel &S, const double v[1], double out[1]) { out[0] = S.s * v[0]; }
+    static __device__ __forceinline__ void applyT(const Rel &S, const double w[1], double out[1]) { out[0] = S.s * w[0]; }
+};
+
+// ---- frames: the transfer data of every level-l vertex relative to its aggregate's root -------
+template <int KIND>
+__global__ void amg_rel_kernel(const double *__restrict__ est, const double *__restrict__ aux, int nv_pad,
+                               const int32_t *__restrict__ vid_fine, const int32_t *__restrict__ agg,
+                               const int32_t *__restrict__ vid_coarse, int n_fine, int pad, double *__restrict__ rel) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_fine) return;
     const int vi = vid_fine[i], vr = vid_coarse[agg[i]];
-    Sim3 Si, Sr;
-    Si.qx = est[vi]; Si.qy = est[(size_t)nv_pad + vi]; Si.qz = est[(size_t)2 * nv_pad + vi]; Si.qw = est[(size_t)3 * nv_pad + vi];
-    Si.tx = est[(size_t)4 * nv_pad + vi]; Si.ty = est[(size_t)5 * nv_pad + vi]; Si.tz = est[(size_t)6 * nv_pad + vi];
-    Si.s = est[(size_t)7 * nv_pad + vi];
-    Sr.qx = est[vr]; Sr.qy = est[(size_t)nv_pad + vr]; Sr.qz = est[(size_t)2 * nv_pad + vr]; Sr.qw = est[(size_t)3 * nv_pad + vr];
-    Sr.tx = est[(size_t)4 * nv_pad + vr]; Sr.ty = est[(size_t)5 * nv_pad + vr]; Sr.tz = est[(size_t)6 * nv_pad + vr];
-    Sr.s = est[(size_t)7 * nv_pad + vr];
-    const Sim3 S = sim3_mul(Si, sim3_inv(Sr));
-    double R[9];
-    const double qn = 1.0 / sqrt(S.qx * S.qx + S.qy * S.qy + S.qz * S.qz + S.qw * S.qw);
-    quat_to_rot(S.qx * qn, S.qy * qn, S.qz * qn, S.qw * qn, R);
+    double R[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 }, t[3] = { 0, 0, 0 }, sc = 1;
+    if constexpr (KIND == S3O_KIND_SIM3) {
+        Sim3 Si, Sr;
+        Si.qx = est[vi]; Si.qy = est[(size_t)nv_pad + vi]; Si.qz = est[(size_t)2 * nv_pad + vi]; Si.qw = est[(size_t)3 * nv_pad + vi];
+        Si.tx = est[(size_t)4 * nv_pad + vi]; Si.ty = est[(size_t)5 * nv_pad + vi]; Si.tz = est[(size_t)6 * nv_pad + vi];
+        Si.s = est[(size_t)7 * nv_pad + vi];
+        Sr.qx = est[vr]; Sr.qy = est[(size_t)nv_pad + vr]; Sr.qz = est[(size_t)2 * nv_pad + vr]; Sr.qw = est[(size_t)3 * nv_pad + vr];
+        Sr.tx = est[(size_t)4 * nv_pad + vr]; Sr.ty = est[(size_t)5 * nv_pad + vr]; Sr.tz = est[(size_t)6 * nv_pad + vr];
+        Sr.s = est[(size_t)7 * nv_pad + vr];
+        const Sim3 S = sim3_mul(Si, sim3_inv(Sr));
+        const double qn = 1.0 / sqrt(S.qx * S.qx + S.qy * S.qy + S.qz * S.qz + S.qw * S.qw);
+        quat_to_rot(S.qx * qn, S.qy * qn, S.qz * qn, S.qw * qn, R);
+        t[0] = S.tx; t[1] = S.ty; t[2] = S.tz;
+        sc = S.s;
+    } else if constexpr (KIND == S3O_KIND_SCALE_TRANS) {
+        // estimate planes [s tx ty tz]; aux planes = the fixed rotation quaternion of every vertex
+        double Ri[9], Rr[9];
+        quat_to_rot(aux[vi], aux[(size_t)nv_pad + vi], aux[(size_t)2 * nv_pad + vi], aux[(size_t)3 * nv_pad + vi], Ri);
+        quat_to_rot(aux[vr], aux[(size_t)nv_pad + vr], aux[(size_t)2 * nv_pad + vr], aux[(size_t)3 * nv_pad + vr], Rr);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                R[r * 3 + c] = Ri[r * 3] * Rr[c * 3] + Ri[r * 3 + 1] * Rr[c * 3 + 1] + Ri[r * 3 + 2] * Rr[c * 3 + 2];   // R_i R_root^T
+        sc = est[vi] / est[vr];
+    } else {
+        sc = est[vi] / est[vr];
+    }
 #pragma unroll
     for (int k = 0; k < 9; ++k) rel[(size_t)k * pad + i] = R[k];
-    rel[(size_t)9 * pad + i] = S.tx; rel[(size_t)10 * pad + i] = S.ty; rel[(size_t)11 * pad + i] = S.tz;
-    rel[(size_t)12 * pad + i] = S.s;
+    rel[(size_t)9 * pad + i] = t[0]; rel[(size_t)10 * pad + i] = t[1]; rel[(size_t)11 * pad + i] = t[2];
+    rel[(size_t)12 * pad + i] = sc;
 }
 
 // ---- Galerkin product: one 8-lane group per upper coarse block, lane c holds column c --------
 // Entry lists carry (block | flag, row vertex, column vertex) so the only dependent loads per
 // entry are the frames and the block itself; the next entry's indices are fetched one step ahead.
-template <bool FINE_UPPER>
+template <int D, bool FINE_UPPER>
 __global__ void __launch_bounds__(128, 4) amg_galerkin_kernel(const double *__restrict__ Af, const int32_t *__restrict__ gal_i,
                                                               const int32_t *__restrict__ gal_j, const double *__restrict__ rel,
                                                               int pad, double lambda, int nub,
                                                               const int32_t *__restrict__ gal_ptr, const int32_t *__restrict__ gal_ent,
                                                               const int32_t *__restrict__ gal_out,
                                                               const int32_t *__restrict__ gal_mirror, double *__restrict__ Ac,
-                                                              int write_mirror) {
-    const int ub = blockIdx.x * (blockDim.x / 8) + threadIdx.x / 8;
+                                                              int write_mirror, const int32_t *__restrict__ gal_order) {
+    const int slot = blockIdx.x * (blockDim.x / 8) + threadIdx.x / 8;
     const int c = threadIdx.x & 7;
-    if (ub >= nub || c >= D) return;
+    if (slot >= nub || c >= D) return;
+    const int ub = gal_order[slot];       // lists of equal length share a warp
     double acc[D];
 #pragma unroll
     for (int r = 0; r < D; ++r) acc[r] = 0;
@@ -152,7 +200,7 @@ __global__ void __launch_bounds__(128, 4) amg_galerkin_kernel(const double *__re
         const double *A = Af + (size_t)k * DD;
         double v[D], w[D], u[D];
         if (flag != 1) {        // column c of P_i^T A P_j
-            ad_apply(rj, ec, v);
+            Xf<D>::apply(rj, ec, v);
 #pragma unroll
             for (int r = 0; r < D; ++r) {
                 double a = 0;
@@ -164,12 +212,12 @@ __global__ void __launch_bounds__(128, 4) amg_galerkin_kernel(const double *__re
 #pragma unroll
                 for (int r = 0; r < D; ++r) w[r] += lambda * v[r];
             }
-            adT_apply(ri, w, u);
+            Xf<D>::applyT(ri, w, u);
 #pragma unroll
             for (int r = 0; r < D; ++r) acc[r] += u[r];
         }
         if (flag != 0) {        // column c of P_j^T A^T P_i
-            ad_apply(ri, ec, v);
+            Xf<D>::apply(ri, ec, v);
 #pragma unroll
             for (int r = 0; r < D; ++r) {
                 double a = 0;
@@ -177,7 +225,7 @@ __global__ void __launch_bounds__(128, 4) amg_galerkin_kernel(const double *__re
                 for (int q = 0; q < D; ++q) a += __ldg(A + q * D + r) * v[q];
                 w[r] = a;
             }
-            adT_apply(rj, w, u);
+            Xf<D>::applyT(rj, w, u);
 #pragma unroll
             for (int r = 0; r < D; ++r) acc[r] += u[r];
         }
@@ -194,6 +242,7 @@ __global__ void __launch_bounds__(128, 4) amg_galerkin_kernel(const double *__re
 }
 
 // lower blocks of a level from its upper blocks (partitioned solve: after the all-gather of A_1)
+template <int D>
 __global__ void amg_mirror_kernel(int nub, const int32_t *__restrict__ gal_out, const int32_t *__restrict__ gal_mirror,
                                   double *__restrict__ A) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -206,6 +255,7 @@ __global__ void amg_mirror_kernel(int nub, const int32_t *__restrict__ gal_out, 
 }
 
 // ---- dense inverse of the coarsest operator (one CTA, matrix in shared memory) -----------------
+template <int D>
 __global__ void __launch_bounds__(256) amg_dense_inverse_kernel(const double *__restrict__ A, const int32_t *__restrict__ rowptr,
                                                                 const int32_t *__restrict__ colidx, int n,
                                                                 double *__restrict__ inv, DevScalars *sc) {
@@ -242,7 +292,7 @@ __global__ void __launch_bounds__(256) amg_dense_inverse_kernel(const double *__
 // mode 0: x_out = omega Dinv r                      (first smoothing sweep from x = 0)
 // mode 1: t_out = r - A x                           (residual)
 // mode 2: x_out = x + omega Dinv (r - A x)          (smoothing sweep)
-template <int MODE>
+template <int D, int MODE>
 __global__ void __launch_bounds__(128) amg_row_kernel(int n, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
                                                       const double *__restrict__ A, const double *__restrict__ Dinv,
                                                       const double *__restrict__ r, const double *__restrict__ x,
@@ -287,6 +337,7 @@ __global__ void amg_unpad_kernel(int n, const int32_t *__restrict__ src, const d
 // r_coarse[I] = sum over members i of Ad(rel_i)^T t_i.  An 8-lane group owns one aggregate: lane m
 // takes members m, m+8, ... (ascending), the eight partial sums are combined by a fixed butterfly,
 // so the result is reproducible.
+template <int D>
 __global__ void __launch_bounds__(128) amg_restrict_kernel(int n, const int32_t *__restrict__ mem_ptr,
                                                            const int32_t *__restrict__ mem_idx, const double *__restrict__ rel,
                                                            int pad, const double *__restrict__ t, double *__restrict__ rc,
@@ -306,7 +357,7 @@ __global__ void __launch_bounds__(128) amg_restrict_kernel(int n, const int32_t 
             double w[D], u[D];
 #pragma unroll
             for (int c = 0; c < D; ++c) w[c] = t[(size_t)i * D + c];
-            adT_apply(S, w, u);
+            Xf<D>::applyT(S, w, u);
 #pragma unroll
             for (int c = 0; c < D; ++c) acc[c] += u[c];
         }
@@ -325,6 +376,7 @@ __global__ void __launch_bounds__(128) amg_restrict_kernel(int n, const int32_t 
 }
 
 // x_i += Ad(rel_i) xc[agg_i]
+template <int D>
 __global__ void __launch_bounds__(128) amg_prolong_kernel(int n_fine, const int32_t *__restrict__ agg, const double *__restrict__ rel,
                                                           int pad, const double *__restrict__ xc, double *__restrict__ x,
                                                           const DevScalars *sc, int check_done) {
@@ -336,13 +388,13 @@ __global__ void __launch_bounds__(128) amg_prolong_kernel(int n_fine, const int3
     double v[D], u[D];
 #pragma unroll
     for (int c = 0; c < D; ++c) v[c] = xc[(size_t)I * D + c];
-    ad_apply(S, v, u);
+    Xf<D>::apply(S, v, u);
 #pragma unroll
     for (int c = 0; c < D; ++c) x[(size_t)i * D + c] += u[c];
 }
 
 // Fine level: z_i = zJ_i + Ad(rel_i) xc[agg_i]  (zJ = D^-1 r already in z), r.z, PCG bookkeeping.
-template <int NT>
+template <int D, int NT>
 __global__ void __launch_bounds__(NT) amg_prolong0_kernel(int nf, const int32_t *__restrict__ agg, const double *__restrict__ rel,
                                                           int pad, const double *__restrict__ xc, const double *__restrict__ r,
                                                           double *__restrict__ z, double *__restrict__ p_out,
@@ -357,7 +409,7 @@ __global__ void __launch_bounds__(NT) amg_prolong0_kernel(int nf, const int32_t 
         double v[D], u[D];
 #pragma unroll
         for (int c = 0; c < D; ++c) v[c] = xc[(size_t)I * D + c];
-        ad_apply(S, v, u);
+        Xf<D>::apply(S, v, u);
 #pragma unroll
         for (int c = 0; c < D; ++c) {
             const double zc = z[(size_t)i * D + c] + u[c];
@@ -409,7 +461,7 @@ __device__ __forceinline__ unsigned tail_cta_rank() {
     return r;
 }
 
-template <int MODE>
+template <int D, int MODE>
 __device__ __forceinline__ void tail_rows(const TailLevel &L, const double *x, double *out, double omega, int gtid) {
     constexpr int groups = kTailThreads * kTailCtas / 8;
     const int g = gtid / 8, l = gtid & 7;
@@ -442,6 +494,7 @@ __device__ __forceinline__ void tail_rows(const TailLevel &L, const double *x, d
     }
 }
 
+template <int D>
 __global__ void __cluster_dims__(kTailCtas, 1, 1) __launch_bounds__(kTailThreads)
 amg_tail_kernel(const __grid_constant__ TailParams P, double omega, const DevScalars *sc, int check_done) {
     if (check_done && sc->done) return;       // uniform over the cluster: nobody reaches a barrier
@@ -458,12 +511,12 @@ amg_tail_kernel(const __grid_constant__ TailParams P, double omega, const DevSca
                     L.x2[t] = acc;
                 }
             } else {            // no dense inverse: five damped block-Jacobi sweeps (a fixed linear operator)
-                tail_rows<0>(L, nullptr, L.x, omega, gtid);
+                tail_rows<D, 0>(L, nullptr, L.x, omega, gtid);
                 tail_sync();
                 for (int k = 0; k < 2; ++k) {
-                    tail_rows<2>(L, L.x, L.x2, omega, gtid);
+                    tail_rows<D, 2>(L, L.x, L.x2, omega, gtid);
                     tail_sync();
-                    tail_rows<2>(L, L.x2, L.x, omega, gtid);
+                    tail_rows<D, 2>(L, L.x2, L.x, omega, gtid);
                     tail_sync();
                 }
                 for (int t = gtid; t < L.n * D; t += NTH) L.x2[t] = __ldcg(L.x + t);
@@ -471,9 +524,9 @@ amg_tail_kernel(const __grid_constant__ TailParams P, double omega, const DevSca
             tail_sync();
             break;
         }
-        tail_rows<0>(L, nullptr, L.x, omega, gtid);
+        tail_rows<D, 0>(L, nullptr, L.x, omega, gtid);
         tail_sync();
-        tail_rows<1>(L, L.x, L.t, omega, gtid);
+        tail_rows<D, 1>(L, L.x, L.t, omega, gtid);
         tail_sync();
         const TailLevel &C = P.lev[l + 1];
         for (int I = gtid; I < C.n; I += NTH) {
@@ -486,7 +539,7 @@ amg_tail_kernel(const __grid_constant__ TailParams P, double omega, const DevSca
                 double w[D], u[D];
 #pragma unroll
                 for (int c = 0; c < D; ++c) w[c] = __ldcg(L.t + (size_t)i * D + c);
-                adT_apply(S, w, u);
+                Xf<D>::applyT(S, w, u);
 #pragma unroll
                 for (int c = 0; c < D; ++c) acc[c] += u[c];
             }
@@ -505,12 +558,12 @@ amg_tail_kernel(const __grid_constant__ TailParams P, double omega, const DevSca
             double v[D], u[D];
 #pragma unroll
             for (int c = 0; c < D; ++c) v[c] = __ldcg(C.x2 + (size_t)I * D + c);
-            ad_apply(S, v, u);
+            Xf<D>::apply(S, v, u);
 #pragma unroll
             for (int c = 0; c < D; ++c) L.x[(size_t)i * D + c] = __ldcg(L.x + (size_t)i * D + c) + u[c];
         }
         tail_sync();
-        tail_rows<2>(L, L.x, L.x2, omega, gtid);
+        tail_rows<D, 2>(L, L.x, L.x2, omega, gtid);
         tail_sync();
     }
 }
@@ -521,7 +574,7 @@ int up(s3o_problem *p, T **dst, const std::vector<T> &src) { return upload(p, ds
 void free_level(LevelDev &L) {
     dev_free(L.agg); dev_free(L.mem_ptr); dev_free(L.mem_idx); dev_free(L.vid);
     dev_free(L.rowptr); dev_free(L.colidx); dev_free(L.blk_row); dev_free(L.dpos);
-    dev_free(L.gal_ptr); dev_free(L.gal_ent); dev_free(L.gal_i); dev_free(L.gal_j); dev_free(L.gal_out); dev_free(L.gal_mirror);
+    dev_free(L.gal_ptr); dev_free(L.gal_ent); dev_free(L.gal_i); dev_free(L.gal_j); dev_free(L.gal_order); dev_free(L.gal_out); dev_free(L.gal_mirror);
     dev_free(L.rel); dev_free(L.A); dev_free(L.Dinv); dev_free(L.r); dev_free(L.x); dev_free(L.x2); dev_free(L.t);
 }
 
@@ -530,6 +583,7 @@ void free_level(LevelDev &L) {
 void localize_fine_level(s3o_problem *p, const HostStructure &Sg, AmgState *st) {
     const PartitionPlan &P = p->plan;
     const HostStructure &S = p->S;
+    const int D = p->d;
     AmgHostLevel &H = st->host[0];
     const int nloc = S.nf, world = P.world;
     st->dist = true;
@@ -607,7 +661,8 @@ int amg_levels(const s3o_problem *p) { return p->amg ? (int)p->amg->lev.size() :
 // levels when the graph is too small to coarsen (the caller then stays with block-Jacobi).
 int amg_setup(s3o_problem *p) {
     if (p->amg) return S3O_OK;
-    if (p->kind != S3O_KIND_SIM3) { set_error("multilevel preconditioner: Sim3 problems only"); return S3O_ERR_UNSUPPORTED; }
+    if (p->kind == S3O_KIND_BA) { set_error("multilevel preconditioner: pose-graph problems only"); return S3O_ERR_UNSUPPORTED; }
+    const int D = p->d;
     AmgState *st = new AmgState();
     p->amg = st;
     if (p->dist) {
@@ -641,6 +696,14 @@ int amg_setup(s3o_problem *p) {
         rc = rc ? rc : up(p, &L.gal_i, H.gal_i);
         rc = rc ? rc : up(p, &L.gal_j, H.gal_j);
         rc = rc ? rc : up(p, &L.gal_out, H.gal_out);
+        {   // the lists may have been localised (partitioned solve): order by their final lengths
+            std::vector<int32_t> order(H.nub);
+            for (int u = 0; u < H.nub; ++u) order[u] = u;
+            std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+                return H.gal_ptr[a + 1] - H.gal_ptr[a] > H.gal_ptr[b + 1] - H.gal_ptr[b];
+            });
+            rc = rc ? rc : up(p, &L.gal_order, order);
+        }
         rc = rc ? rc : up(p, &L.gal_mirror, H.gal_mirror);
         rc = rc ? rc : dev_alloc(&L.rel, (size_t)NREL * L.pad_fine);
         rc = rc ? rc : dev_alloc(&L.A, (size_t)L.nblk * DD);
@@ -663,7 +726,10 @@ int amg_setup(s3o_problem *p) {
     if (!rc && st->dense) {
         rc = dev_alloc(&st->d_dense, (size_t)nc * D * nc * D);
         const int smem = (nc * D * nc * D + nc * D) * (int)sizeof(double);
-        if (!rc && cudaFuncSetAttribute(amg_dense_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+        cudaError_t ea = D == 7 ? cudaFuncSetAttribute(amg_dense_inverse_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                       : D == 4 ? cudaFuncSetAttribute(amg_dense_inverse_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                                : cudaFuncSetAttribute(amg_dense_inverse_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (!rc && ea != cudaSuccess) {
             set_error("amg_setup: cannot reserve %d bytes of shared memory", smem);
             rc = S3O_ERR_CUDA;
         }
@@ -678,49 +744,52 @@ int amg_setup(s3o_problem *p) {
     return rc;
 }
 
+namespace {
 // Relative frames of every level at the current linearisation point.
-int amg_update_frames(s3o_problem *p) {
+template <int D, int KIND>
+int update_frames_t(s3o_problem *p) {
     AmgState *st = p->amg;
     if (!st || st->lev.empty()) return S3O_OK;
     const double *est = p->d_est[p->cur];
     for (size_t l = 0; l < st->lev.size(); ++l) {
         LevelDev &L = st->lev[l];
         const int32_t *vid_fine = l == 0 ? st->d_vid0 : st->lev[l - 1].vid;
-        amg_rel_kernel<<<(L.n_fine + 127) / 128, 128, 0, p->stream>>>(est, p->nv_pad, vid_fine, L.agg, L.vid, L.n_fine,
-                                                                       L.pad_fine, L.rel);
+        amg_rel_kernel<KIND><<<(L.n_fine + 127) / 128, 128, 0, p->stream>>>(est, p->d_aux, p->nv_pad, vid_fine, L.agg, L.vid,
+                                                                             L.n_fine, L.pad_fine, L.rel);
     }
     st->frames_valid = true;
     return check_launch(p, (int)st->lev.size());
 }
 
 // Galerkin operators, smoother inverses and the coarsest inverse for (H + lambda I).
-int amg_update_values(s3o_problem *p, double lambda) {
+template <int D, int KIND>
+int update_values_t(s3o_problem *p, double lambda) {
     AmgState *st = p->amg;
     if (!st || st->lev.empty()) return S3O_OK;
     int rc;
-    if (!st->frames_valid && (rc = amg_update_frames(p))) return rc;
+    if (!st->frames_valid && (rc = update_frames_t<D, KIND>(p))) return rc;
     int launches = 0;
     for (size_t l = 0; l < st->lev.size(); ++l) {
         LevelDev &L = st->lev[l];
         const int grid = (L.nub + 15) / 16;
         if (l == 0)
         {
-            amg_galerkin_kernel<true><<<grid, 128, 0, p->stream>>>(p->d_H, L.gal_i, L.gal_j, L.rel, L.pad_fine, lambda,
+            amg_galerkin_kernel<D, true><<<grid, 128, 0, p->stream>>>(p->d_H, L.gal_i, L.gal_j, L.rel, L.pad_fine, lambda,
                                                                     L.nub, L.gal_ptr, L.gal_ent, L.gal_out, L.gal_mirror, L.A,
-                                                                    st->dist ? 0 : 1);
+                                                                    st->dist ? 0 : 1, L.gal_order);
             if (st->dist) {     // every rank computed the upper blocks of its own coarse rows
                 if (comm_allgatherv(p->comm, L.A, st->a_off.data(), st->a_cnt.data(), p->stream)) {
                     set_error("%s", comm_last_error());
                     return S3O_ERR_NCCL;
                 }
-                amg_mirror_kernel<<<(L.nub * DD + 255) / 256, 256, 0, p->stream>>>(L.nub, L.gal_out, L.gal_mirror, L.A);
+                amg_mirror_kernel<D><<<(L.nub * DD + 255) / 256, 256, 0, p->stream>>>(L.nub, L.gal_out, L.gal_mirror, L.A);
                 ++launches;
             }
         }
         else {
             const LevelDev &F = st->lev[l - 1];
-            amg_galerkin_kernel<false><<<grid, 128, 0, p->stream>>>(F.A, L.gal_i, L.gal_j, L.rel, L.pad_fine, 0.0, L.nub,
-                                                                     L.gal_ptr, L.gal_ent, L.gal_out, L.gal_mirror, L.A, 1);
+            amg_galerkin_kernel<D, false><<<grid, 128, 0, p->stream>>>(F.A, L.gal_i, L.gal_j, L.rel, L.pad_fine, 0.0, L.nub,
+                                                                     L.gal_ptr, L.gal_ent, L.gal_out, L.gal_mirror, L.A, 1, L.gal_order);
         }
         launch_precond(D, L.A, L.dpos, L.n, 0.0, L.Dinv, p->d_sc, p->stream);
         launches += 2;
@@ -728,7 +797,7 @@ int amg_update_values(s3o_problem *p, double lambda) {
     if (st->dense) {
         const LevelDev &C = st->lev.back();
         const int N = C.n * D;
-        amg_dense_inverse_kernel<<<1, 256, (size_t)(N * N + N) * sizeof(double), p->stream>>>(C.A, C.rowptr, C.colidx, C.n,
+        amg_dense_inverse_kernel<D><<<1, 256, (size_t)(N * N + N) * sizeof(double), p->stream>>>(C.A, C.rowptr, C.colidx, C.n,
                                                                                               st->d_dense, p->d_sc);
         launches += 1;
     }
@@ -737,7 +806,8 @@ int amg_update_values(s3o_problem *p, double lambda) {
 
 // z += P0 V(P0^T r) on the fine vectors of the problem (z holds D^-1 r on entry); finishes the
 // PCG scalars (r.z, beta / convergence test).  init: first application of a solve (also sets p = z).
-int amg_apply(s3o_problem *p, int init) {
+template <int D>
+int apply_t(s3o_problem *p, int init) {
     AmgState *st = p->amg;
     const int nl = (int)st->lev.size();
     const DevScalars *sc = p->d_sc;
@@ -750,7 +820,7 @@ int amg_apply(s3o_problem *p, int init) {
     if (lt == nl) lt = nl - 1;  // a large coarsest level: the tail kernel still runs its smoothing sweeps
     {   // fine residual -> level 1
         LevelDev &L = st->lev[0];
-        amg_restrict_kernel<<<(L.n + 15) / 16, 128, 0, s>>>(L.n, L.mem_ptr, L.mem_idx, L.rel, L.pad_fine, p->d_r, L.r, sc, chk);
+        amg_restrict_kernel<D><<<(L.n + 15) / 16, 128, 0, s>>>(L.n, L.mem_ptr, L.mem_idx, L.rel, L.pad_fine, p->d_r, L.r, sc, chk);
         ++launches;
         if (st->dist) {
             // my segment starts at L.r + r_off[rank]; the padded tail of the send is ignored by the unpad map
@@ -765,9 +835,9 @@ int amg_apply(s3o_problem *p, int init) {
     for (int l = 0; l < lt; ++l) {
         LevelDev &L = st->lev[l];
         LevelDev &C = st->lev[l + 1];
-        amg_row_kernel<0><<<rows(L.n), 128, 0, s>>>(L.n, L.rowptr, L.colidx, L.A, L.Dinv, L.r, nullptr, L.x, kOmega, sc, chk);
-        amg_row_kernel<1><<<rows(L.n), 128, 0, s>>>(L.n, L.rowptr, L.colidx, L.A, L.Dinv, L.r, L.x, L.t, kOmega, sc, chk);
-        amg_restrict_kernel<<<(C.n + 15) / 16, 128, 0, s>>>(C.n, C.mem_ptr, C.mem_idx, C.rel, C.pad_fine, L.t, C.r, sc, chk);
+        amg_row_kernel<D, 0><<<rows(L.n), 128, 0, s>>>(L.n, L.rowptr, L.colidx, L.A, L.Dinv, L.r, nullptr, L.x, kOmega, sc, chk);
+        amg_row_kernel<D, 1><<<rows(L.n), 128, 0, s>>>(L.n, L.rowptr, L.colidx, L.A, L.Dinv, L.r, L.x, L.t, kOmega, sc, chk);
+        amg_restrict_kernel<D><<<(C.n + 15) / 16, 128, 0, s>>>(C.n, C.mem_ptr, C.mem_idx, C.rel, C.pad_fine, L.t, C.r, sc, chk);
         launches += 3;
     }
     {
@@ -783,15 +853,15 @@ int amg_apply(s3o_problem *p, int init) {
             T.rowptr = L.rowptr; T.colidx = L.colidx; T.mem_ptr = L.mem_ptr; T.mem_idx = L.mem_idx; T.agg = L.agg;
             T.A = L.A; T.Dinv = L.Dinv; T.rel = L.rel; T.r = L.r; T.x = L.x; T.x2 = L.x2; T.t = L.t;
         }
-        amg_tail_kernel<<<kTailCtas, kTailThreads, 0, s>>>(P, kOmega, sc, chk);
+        amg_tail_kernel<D><<<kTailCtas, kTailThreads, 0, s>>>(P, kOmega, sc, chk);
         for (int l = lt; l < nl; ++l) std::swap(st->lev[l].x, st->lev[l].x2);
         ++launches;
     }
     for (int l = lt - 1; l >= 0; --l) {
         LevelDev &L = st->lev[l];
         LevelDev &C = st->lev[l + 1];
-        amg_prolong_kernel<<<(L.n + 127) / 128, 128, 0, s>>>(L.n, C.agg, C.rel, C.pad_fine, C.x, L.x, sc, chk);
-        amg_row_kernel<2><<<rows(L.n), 128, 0, s>>>(L.n, L.rowptr, L.colidx, L.A, L.Dinv, L.r, L.x, L.x2, kOmega, sc, chk);
+        amg_prolong_kernel<D><<<(L.n + 127) / 128, 128, 0, s>>>(L.n, C.agg, C.rel, C.pad_fine, C.x, L.x, sc, chk);
+        amg_row_kernel<D, 2><<<rows(L.n), 128, 0, s>>>(L.n, L.rowptr, L.colidx, L.A, L.Dinv, L.r, L.x, L.x2, kOmega, sc, chk);
         std::swap(L.x, L.x2);
         launches += 2;
     }
@@ -802,12 +872,34 @@ int amg_apply(s3o_problem *p, int init) {
         int grid = (rows + NT - 1) / NT;
         if (grid > 148 * 8) grid = 148 * 8;
         if (grid < 1) grid = 1;
-        amg_prolong0_kernel<NT><<<grid, NT, 0, s>>>(rows, L.agg, L.rel, L.pad_fine, L.x, p->d_r, p->d_z, init ? p->d_p : nullptr,
+        amg_prolong0_kernel<D, NT><<<grid, NT, 0, s>>>(rows, L.agg, L.rel, L.pad_fine, L.x, p->d_r, p->d_z, init ? p->d_p : nullptr,
                                                     p->d_partials, p->d_sc, init, p->pcg_tol, p->pcg_max_iter, st->dist ? 1 : 0);
         ++launches;
     }
     return check_launch(p, launches);
 }
+
+}  // namespace
+
+#define S3O_AMG_DISPATCH(CALL7, CALL4, CALL1)                  \
+    switch (p->kind) {                                         \
+    case S3O_KIND_SIM3: return CALL7;                          \
+    case S3O_KIND_SCALE_TRANS: return CALL4;                   \
+    case S3O_KIND_SCALE: return CALL1;                         \
+    default: set_error("multilevel preconditioner: pose-graph problems only"); return S3O_ERR_UNSUPPORTED; \
+    }
+int amg_update_frames(s3o_problem *p) {
+    S3O_AMG_DISPATCH((update_frames_t<7, S3O_KIND_SIM3>(p)), (update_frames_t<4, S3O_KIND_SCALE_TRANS>(p)),
+                     (update_frames_t<1, S3O_KIND_SCALE>(p)))
+}
+int amg_update_values(s3o_problem *p, double lambda) {
+    S3O_AMG_DISPATCH((update_values_t<7, S3O_KIND_SIM3>(p, lambda)), (update_values_t<4, S3O_KIND_SCALE_TRANS>(p, lambda)),
+                     (update_values_t<1, S3O_KIND_SCALE>(p, lambda)))
+}
+int amg_apply(s3o_problem *p, int init) {
+    S3O_AMG_DISPATCH(apply_t<7>(p, init), apply_t<4>(p, init), apply_t<1>(p, init))
+}
+#undef S3O_AMG_DISPATCH
 
 void amg_invalidate_frames(s3o_problem *p) { if (p->amg) p->amg->frames_valid = false; }
 

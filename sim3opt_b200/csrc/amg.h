@@ -4,7 +4,9 @@
 // [EXT g2o]), is solved by PCG.  Block-Jacobi alone needs O(graph diameter)
 // iterations once lambda is small; this adds a coarse-space correction built on the gauge
 // near-null space of a pose graph: moving every pose of an aggregate rigidly with its root,
-// delta_i = Ad(S_i S_root^-1) xi  (left-multiplicative tangent, VertexSim3Expmap::oplusImpl).
+// delta_i = Ad(S_i S_root^-1) xi  (left-multiplicative tangent, VertexSim3Expmap::oplusImpl);
+// for the 4-DoF scale+translation and 1-DoF scale graphs of the stepwise pipeline the same gauge
+// (a right-multiplied world similarity) gives (s_i/s_root) diag(1, R_i R_root^T) and s_i/s_root.
 //
 //   z = D^-1 r  +  P0 * V(P0^T r)          fine level: additive (no extra product with H)
 //   V = V(1,1)-cycle with damped block-Jacobi smoothing on the Galerkin operators
@@ -13,6 +15,8 @@
 // The hierarchy (aggregates, coarse patterns, Galerkin contributor lists) depends on the block
 // structure only and is built once on the host; the values are recomputed on the device per LM
 // trial (amg.cu).  Every list is ordered, so the device sums are reproducible.
+// Partitioned solve (one process per GPU): aggregates never cross a rank's vertex range, the fine
+// transfer is local, and level 1 and below are replicated on every rank (amg.cu, AmgState).
 #pragma once
 #include <stdint.h>
 #include <vector>
@@ -40,6 +44,7 @@ struct AmgHostLevel {
     std::vector<int32_t> gal_out;         // [nub] position of (I,J) in the level-(l+1) block array
     std::vector<int32_t> gal_mirror;      // [nub] position of (J,I), -1 on the diagonal
     std::vector<int32_t> gal_I, gal_J;    // [nub]
+    std::vector<int32_t> gal_order;       // [nub] upper blocks by descending list length (warps get equal work)
 };
 
 // Builds the hierarchy below the BSR-upper structure S (level 0).  Stops when a level has at

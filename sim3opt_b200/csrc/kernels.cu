@@ -505,6 +505,14 @@ __global__ void assemble_kernel(GraphDev g, StructDev s, const double *__restric
     const long long k64 = tid / EL;
     if (k64 >= g.nb) return;
     const int k = (int)k64, el = (int)(tid - k64 * EL);
+    const int src = __ldg(s.blk_src + k);
+    if (src >= 0) {       // off-diagonal block fed by one edge: a (possibly transposed) copy of its A^T O' B
+        if (el < DD) {
+            const int r = el / D, c = el - r * D;
+            H[(size_t)k * DD + el] = scratch[(size_t)(src >> 1) * STRIDE + 2 * (NS + D) + ((src & 1) ? c * D + r : r * D + c)];
+        }
+        return;
+    }
     const int row = s.blk_row[k], col = s.colidx[k];
     if (row == col) {
         int off;
@@ -517,7 +525,16 @@ __global__ void assemble_kernel(GraphDev g, StructDev s, const double *__restric
         }
         double acc = 0;
         const int ib = s.inc_ptr[row], ie = s.inc_ptr[row + 1];
-        for (int n = ib; n < ie; ++n) {
+        int n = ib;
+        for (; n + 4 <= ie; n += 4) {     // four independent loads in flight, summed in list order
+            const int e0 = s.inc_ent[n], e1 = s.inc_ent[n + 1], e2 = s.inc_ent[n + 2], e3 = s.inc_ent[n + 3];
+            const double v0 = scratch[(size_t)(e0 >> 1) * STRIDE + (e0 & 1) * (NS + D) + off];
+            const double v1 = scratch[(size_t)(e1 >> 1) * STRIDE + (e1 & 1) * (NS + D) + off];
+            const double v2 = scratch[(size_t)(e2 >> 1) * STRIDE + (e2 & 1) * (NS + D) + off];
+            const double v3 = scratch[(size_t)(e3 >> 1) * STRIDE + (e3 & 1) * (NS + D) + off];
+            acc += v0; acc += v1; acc += v2; acc += v3;
+        }
+        for (; n < ie; ++n) {
             const int ent = s.inc_ent[n];
             acc += scratch[(size_t)(ent >> 1) * STRIDE + (ent & 1) * (NS + D) + off];
         }

@@ -43,6 +43,7 @@ struct GraphDev {
 struct StructDev {
     const int32_t *rowptr, *colidx, *blk_row;
     const int32_t *blk_ebeg, *blk_eend;
+    const int32_t *blk_src;   // [nb] single-edge off-diagonal blocks: (sorted edge << 1) | transposed, else -1
     const int32_t *colT_ptr, *colT_blk;
     const int32_t *inc_ptr, *inc_ent;
     const int32_t *e_blk;

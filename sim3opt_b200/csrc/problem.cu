@@ -58,7 +58,7 @@ namespace s3o {
 StructDev struct_view(const s3o_problem *p) {
     StructDev s{};
     s.rowptr = p->d_rowptr; s.colidx = p->d_colidx; s.blk_row = p->d_blk_row;
-    s.blk_ebeg = p->d_blk_ebeg; s.blk_eend = p->d_blk_eend;
+    s.blk_ebeg = p->d_blk_ebeg; s.blk_eend = p->d_blk_eend; s.blk_src = p->d_blk_src;
     s.colT_ptr = p->d_colT_ptr; s.colT_blk = p->d_colT_blk;
     s.inc_ptr = p->d_inc_ptr; s.inc_ent = p->d_inc_ent; s.e_blk = p->d_e_blk;
     s.tile_row = p->d_tile_row; s.ntiles = (int)p->S.tile_row.size() - 1;
@@ -70,11 +70,12 @@ void free_structure(s3o_problem *p) {
     dev_free(p->d_hidx); dev_free(p->d_sv0); dev_free(p->d_sv1); dev_free(p->d_meas); dev_free(p->d_info);
     dev_free(p->d_rowptr); dev_free(p->d_colidx); dev_free(p->d_blk_row); dev_free(p->d_blk_ebeg);
     dev_free(p->d_blk_eend); dev_free(p->d_colT_ptr); dev_free(p->d_colT_blk); dev_free(p->d_inc_ptr);
-    dev_free(p->d_inc_ent); dev_free(p->d_e_blk); dev_free(p->d_tile_row);
+    dev_free(p->d_inc_ent); dev_free(p->d_e_blk); dev_free(p->d_tile_row); dev_free(p->d_blk_src);
     dev_free(p->d_ghidx); dev_free(p->d_send_idx); dev_free(p->d_primary); dev_free(p->d_sendbuf); dev_free(p->d_xg);
     dev_free(p->d_H); dev_free(p->d_b); dev_free(p->d_x); dev_free(p->d_r); dev_free(p->d_z); dev_free(p->d_p);
     dev_free(p->d_q1); dev_free(p->d_T); dev_free(p->d_Minv); dev_free(p->d_scratch);
     amg_destroy(p);
+    p->auto_multilevel = false;
     p->built = false;
     p->linearized = false;
 }
@@ -163,8 +164,8 @@ namespace s3o {
 // multilevel preconditioner: Sim3 graphs on one GPU; AUTO switches it on for large graphs
 bool wants_multilevel(const s3o_problem *p) {
     const int nf = p->dist ? p->plan.nf_global : p->S.nf;
-    return p->kind == S3O_KIND_SIM3 &&
-           (p->precond == S3O_PRECOND_MULTILEVEL || (p->precond == S3O_PRECOND_AUTO && nf >= 20000));
+    return p->kind != S3O_KIND_BA &&
+           (p->precond == S3O_PRECOND_MULTILEVEL || (p->precond == S3O_PRECOND_AUTO && (nf >= 20000 || p->auto_multilevel)));
 }
 
 // Solve (H + lambda I) x = b; leaves x in d_x.  Returns the PCG status in *status (1 converged,
@@ -250,6 +251,13 @@ int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel
         if (batch < 64) batch *= 2;
     }
     p->stats.pcg_iterations += p->h_sc->iters;
+    // AUTO on a small graph: block-Jacobi until a solve turns out to be ill-conditioned (small lambda on
+    // a long chain), the multilevel correction from the next solve on
+    // (and back once the multilevel solves get so cheap -- large lambda -- that its setup dominates)
+    if (p->precond == S3O_PRECOND_AUTO && (p->kind == S3O_KIND_SIM3 || p->kind == S3O_KIND_SCALE_TRANS)) {
+        if (!amg && p->h_sc->iters > 256) p->auto_multilevel = true;
+        else if (amg && p->auto_multilevel && p->h_sc->iters <= 8) p->auto_multilevel = false;
+    }
     if (status) *status = p->h_sc->done ? p->h_sc->done : 2;
     if (iters) *iters = p->h_sc->iters;
     if (rel_res) *rel_res = p->h_sc->rr0 > 0 ? std::sqrt(p->h_sc->rr / p->h_sc->rr0) : 0.0;
@@ -344,7 +352,7 @@ int s3o_create(int kind, int device, s3o_problem **out) {
     if (const char *v = getenv("S3O_SPMV4_CFG")) spmv4_set_cfg(atoi(v));
     if (const char *v = getenv("S3O_PRECOND")) {        // experiment switch; s3o_set_preconditioner overrides it
         const int k = atoi(v);
-        if (k >= S3O_PRECOND_AUTO && k <= S3O_PRECOND_MULTILEVEL && (k != S3O_PRECOND_MULTILEVEL || kind == S3O_KIND_SIM3)) p->precond = k;
+        if (k >= S3O_PRECOND_AUTO && k <= S3O_PRECOND_MULTILEVEL && (k != S3O_PRECOND_MULTILEVEL || kind != S3O_KIND_BA)) p->precond = k;
     }
     for (auto &ev : p->ev) cudaEventCreate(&ev);
     for (auto &ev : p->spmv_ev) cudaEventCreate(&ev);
@@ -482,7 +490,7 @@ int s3o_set_estimates(s3o_problem *p, const double *est) {
     if (!p || !est || !p->d_est[0]) { set_error("s3o_set_estimates: call s3o_set_vertices first"); return S3O_ERR_INVALID; }
     cudaSetDevice(p->device);
     p->linearized = false;
-    if (p->lm_resume != 2) p->lm_valid = false;
+    if (p->lm_resume != 2) { p->lm_valid = false; p->auto_multilevel = false; }
     return upload_estimates(p, est);
 }
 
@@ -578,8 +586,8 @@ int s3o_set_preconditioner(s3o_problem *p, int kind) {
         set_error("s3o_set_preconditioner: unknown kind %d", kind);
         return S3O_ERR_INVALID;
     }
-    if (kind == S3O_PRECOND_MULTILEVEL && p->kind != S3O_KIND_SIM3) {
-        set_error("s3o_set_preconditioner: the multilevel preconditioner is built on Sim3 adjoints (kind SIM3 only)");
+    if (kind == S3O_PRECOND_MULTILEVEL && p->kind == S3O_KIND_BA) {
+        set_error("s3o_set_preconditioner: the multilevel preconditioner is built on the gauge modes of a pose graph (not BA)");
         return S3O_ERR_UNSUPPORTED;
     }
     p->precond = kind;
@@ -622,6 +630,7 @@ int s3o_build_structure(s3o_problem *p, int *n_free, int *n_blocks) {
         rc = rc ? rc : upload(p, &p->d_sv1, S.sv1);
         rc = rc ? rc : upload(p, &p->d_blk_ebeg, S.blk_ebeg);
         rc = rc ? rc : upload(p, &p->d_blk_eend, S.blk_eend);
+        rc = rc ? rc : upload(p, &p->d_blk_src, S.blk_src);
         rc = rc ? rc : upload(p, &p->d_inc_ptr, S.inc_ptr);
         rc = rc ? rc : upload(p, &p->d_inc_ent, S.inc_ent);
         rc = rc ? rc : upload(p, &p->d_e_blk, S.e_blk);
@@ -1123,6 +1132,7 @@ int s3o_restore_estimates(s3o_problem *p) {
     S3O_CUDA(cudaMemcpyAsync(p->d_est[p->cur], p->d_est_snap, cnt * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
     p->linearized = false;
     p->lm_valid = false;
+    p->auto_multilevel = false;     // a new solve starts: AUTO decides again (keeps solves reproducible)
     return S3O_OK;
 }
 

@@ -54,6 +54,7 @@ struct s3o_problem {
     int32_t *d_rowptr = nullptr, *d_colidx = nullptr, *d_blk_row = nullptr, *d_blk_ebeg = nullptr, *d_blk_eend = nullptr;
     int32_t *d_colT_ptr = nullptr, *d_colT_blk = nullptr, *d_inc_ptr = nullptr, *d_inc_ent = nullptr, *d_e_blk = nullptr;
     int32_t *d_tile_row = nullptr;
+    int32_t *d_blk_src = nullptr;
     // partitioned solve (one process per GPU, NCCL): s3o_set_comm
     Comm comm;
     bool dist = false;
@@ -80,6 +81,7 @@ struct s3o_problem {
     double pcg_tol = 1e-8;
     int pcg_max_iter = 1000;
     int precond = S3O_PRECOND_AUTO;         // s3o_set_preconditioner
+    bool auto_multilevel = false;           // AUTO: a block-Jacobi solve needed > 256 iterations
     bool linearized = false;
     // LM continuation state (s3o_set_lm_resume)
     int lm_resume = 0;

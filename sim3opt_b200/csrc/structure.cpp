@@ -97,6 +97,15 @@ void build_structure_from_hidx(int nv, const int32_t *hidx_in, int nfree, int ne
         S.sv1[t] = v1[S.perm[t]];
     }
 
+    // off-diagonal blocks fed by a single edge (the common case) carry their source directly
+    S.blk_src.assign(nb, -1);
+    for (int k = 0; k < nb; ++k)
+        if (S.blk_eend[k] - S.blk_ebeg[k] == 1) {
+            const int t = S.blk_ebeg[k];
+            const bool transposed = S.hidx[S.sv0[t]] > S.hidx[S.sv1[t]];   // vertex(0) on the max side: A^T O' B is the transpose
+            S.blk_src[k] = (t << 1) | (transposed ? 1 : 0);
+        }
+
     // incidences per free vertex, ordered by sorted edge position (fixed summation order)
     S.inc_ptr.assign(nf + 1, 0);
     for (int t = 0; t < na; ++t) {

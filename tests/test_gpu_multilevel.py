@@ -80,10 +80,55 @@ def test_lm_matches_block_jacobi_and_oracle(sphere_small):
     assert (2 * np.arccos(np.clip(dots, -1, 1))).max() <= 1e-5
 
 
-def test_multilevel_rejected_for_other_kinds(kitti_k1):
+def test_scale_trans_multilevel(kitti_k1, kitti_k118):
+    """4-DoF scale+translation graph of the stepwise pipeline (kitti_surf.cpp:834-839,872-877): the
+    coarse space is delta_i = (s_i/s_root) diag(1, R_i R_root^T) xi; same solution, far fewer iterations."""
     import sim3opt_b200 as s3
     from oracle import kitti_io
-    st = kitti_io.to_scale_trans_graph(kitti_k1)
-    gpu = make_gpu(st, kind=s3.KIND_SCALE_TRANS)
-    with pytest.raises(s3.S3OError):
+    for g in (kitti_k1, kitti_k118):
+        st = kitti_io.to_scale_trans_graph(g)
+        gpu = make_gpu(st, kind=s3.KIND_SCALE_TRANS, jac=1)
+        colptr, rowidx = gpu.build_structure()
+        H, b = gpu.linearize()
+        lam = 1e-7 * gpu.max_diag()
+        gpu.set_pcg(1e-11, 200000)
+        gpu.set_preconditioner(s3.PRECOND_BLOCK_JACOBI)
+        rc1, x1, it1, _ = gpu.solve(lam)
         gpu.set_preconditioner(s3.PRECOND_MULTILEVEL)
+        rc2, x2, it2, rel2 = gpu.solve(lam)
+        assert rc1 == 0 and rc2 == 0 and rel2 <= 1e-11
+        A = dense_from_blocks(colptr, rowidx, H, 4) + lam * np.eye(len(b))
+        assert np.linalg.norm(A @ x2 - b) <= 1e-10 * np.linalg.norm(b)
+        assert it2 * 4 <= it1, (it1, it2)
+
+
+def test_scale_null_vector_multilevel(kitti_k118):
+    """1-DoF scale graph (kitti_surf.cpp:891-934): inverse iteration with the multilevel PCG finds the
+    same null vector as numpy's dense SVD."""
+    import sim3opt_b200 as s3
+    g = kitti_k118
+    n = len(g["est"])
+    v0, v1, s = g["v0"], g["v1"], g["meas"][:, 7]
+    A = np.zeros((len(v0), n))
+    for r, (i, j, m) in enumerate(zip(v0, v1, s)):
+        A[r, i] = m
+        A[r, j] = -1.0
+    _, sv, Vt = np.linalg.svd(A)
+    ref = Vt[-1] / Vt[-1][0]
+    p = s3.Problem(s3.KIND_SCALE)
+    p.set_vertices(np.ones((n, 1)))
+    p.set_edges(v0, v1, s.reshape(-1, 1))
+    p.set_pcg(1e-13, 100000)
+    p.set_preconditioner(s3.PRECOND_MULTILEVEL)
+    x, lmin, lmax, its = p.smallest_eigenvector(60, 1e-13)
+    x = x / x[0]
+    assert np.abs(x - ref).max() <= 1e-6 * np.abs(ref).max()
+
+
+def test_multilevel_rejected_for_ba():
+    import sim3opt_b200 as s3
+    from sim3opt_b200 import synth
+    g = synth.ba_loop(8, 60, 4, seed=1)
+    p = s3.BAProblem()
+    p.set(g["cams"], g["points"], g["obs_cam"], g["obs_pt"], g["uv"], g["focal"], g["cx"], g["cy"])
+    assert p.L.s3o_set_preconditioner(p.h, s3.PRECOND_MULTILEVEL) == -5      # S3O_ERR_UNSUPPORTED
