@@ -136,9 +136,11 @@ int s3o_host_structure(int n_vertices, const uint8_t *fixed, int n_edges, const 
 
 /* Host-only view of the aggregation hierarchy the MULTILEVEL preconditioner builds for a graph:
  * n_levels coarse levels, their vertex and (full-pattern) block counts (first `cap` entries), and
- * the aggregate of every free vertex on the finest level (aggregate0: n_free ints, may be NULL). */
+ * the aggregate of every free vertex on the finest level (aggregate0: n_free ints, may be NULL).
+ * With world > 1 no aggregate crosses the vertex ranges of s3o_host_partition. */
 int s3o_host_multilevel(int n_vertices, const uint8_t *fixed, int n_edges, const int32_t *v0, const int32_t *v1,
-                        int cap, int *n_levels, int32_t *level_vertices, int32_t *level_blocks, int32_t *aggregate0);
+                        int world /* ranks of the partitioned solve, 1 = one GPU */, int cap, int *n_levels,
+                        int32_t *level_vertices, int32_t *level_blocks, int32_t *aggregate0);
 
 /* ---- lock-step pieces (each mirrors one g2o step; used by the parity tests) ------------ */
 int s3o_chi2(s3o_problem *p, double *chi2);                 /* computeActiveErrors + activeRobustChi2 */

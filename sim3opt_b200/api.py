@@ -243,7 +243,7 @@ def host_partition(n_vertices, fixed, v0, v1, rank, world):
                 send_idx=send_idx[:int(send_count.sum())].copy())
 
 
-def host_multilevel(n_vertices, fixed, v0, v1):
+def host_multilevel(n_vertices, fixed, v0, v1, world=1):
     """Aggregation hierarchy of the multilevel preconditioner (host only): per-level vertex counts,
     per-level block counts, and the finest-level aggregate of every free vertex."""
     L = _lib.load()
@@ -254,7 +254,7 @@ def host_multilevel(n_vertices, fixed, v0, v1):
     nvert, nblk = np.zeros(16, np.int32), np.zeros(16, np.int32)
     agg = np.full(max(int((fx == 0).sum()), 1), -1, np.int32)
     rc = L.s3o_host_multilevel(n_vertices, fx.ctypes.data_as(_up), len(v0), v0.ctypes.data_as(_ip),
-                               v1.ctypes.data_as(_ip), 16, C.byref(nl), nvert.ctypes.data_as(_ip),
+                               v1.ctypes.data_as(_ip), int(world), 16, C.byref(nl), nvert.ctypes.data_as(_ip),
                                nblk.ctypes.data_as(_ip), agg.ctypes.data_as(_ip))
     if rc != 0:
         raise S3OError(f"s3o error {rc}: {L.s3o_last_error().decode()}")

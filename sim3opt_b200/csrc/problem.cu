@@ -716,8 +716,9 @@ int s3o_host_partition(int n_vertices, const uint8_t *fixed, int n_edges, const 
 }
 
 int s3o_host_multilevel(int n_vertices, const uint8_t *fixed, int n_edges, const int32_t *v0, const int32_t *v1,
-                        int cap, int *n_levels, int32_t *level_vertices, int32_t *level_blocks, int32_t *aggregate0) {
-    if (n_vertices < 0 || n_edges < 0 || (n_edges > 0 && (!v0 || !v1)) || !n_levels) { set_error("s3o_host_multilevel: bad arguments"); return S3O_ERR_INVALID; }
+                        int world, int cap, int *n_levels, int32_t *level_vertices, int32_t *level_blocks,
+                        int32_t *aggregate0) {
+    if (n_vertices < 0 || n_edges < 0 || (n_edges > 0 && (!v0 || !v1)) || !n_levels || world < 1) { set_error("s3o_host_multilevel: bad arguments"); return S3O_ERR_INVALID; }
     for (int k = 0; k < n_edges; ++k)
         if (v0[k] < 0 || v0[k] >= n_vertices || v1[k] < 0 || v1[k] >= n_vertices || v0[k] == v1[k]) {
             set_error("s3o_host_multilevel: edge %d has invalid vertices", k);
@@ -726,7 +727,9 @@ int s3o_host_multilevel(int n_vertices, const uint8_t *fixed, int n_edges, const
     HostStructure S;
     build_structure_host(n_vertices, fixed, n_edges, v0, v1, S);
     std::vector<s3o::AmgHostLevel> lv;
-    s3o::amg_build_hierarchy(S, 16, 12, lv);
+    // world > 1: the hierarchy of the partitioned solve (aggregates stay inside the ranks' vertex ranges)
+    const int seg = world > 1 ? (S.nf + world - 1) / world : 0;
+    s3o::amg_build_hierarchy(S, 16, 12, lv, seg);
     *n_levels = (int)lv.size();
     for (int l = 0; l < (int)lv.size() && l < cap; ++l) {
         if (level_vertices) level_vertices[l] = lv[l].n;

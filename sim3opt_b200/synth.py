@@ -123,6 +123,83 @@ def sphere(n_laps=100, poses_per_lap=1000, seed=42, radius=100.0,
                 meas=meas, info=info)
 
 
+def manhattan3d(n_poses=10000, seed=42, box=None, loop_radius=2.0, max_loops_per_pose=3, min_gap=10,
+                meas_sigma=(0.01, 0.05, 0.01), init_sigma=(0.05, 0.3, 0.05)):
+    """Manhattan-3D variant of config 3: a unit-step random walk on a 3-D grid confined to
+    a box (reflecting walls), camera z-axis along the last step, ground-truth scale exp(0.2 sin(2 pi k/N));
+    odometry edges (k, k+1) plus loop edges (i, j), j >= i + min_gap, between poses at most `loop_radius`
+    cells apart (at most `max_loops_per_pose` per pose, nearest in time first).  Same edge convention,
+    noise model and return dict as sphere(); the graph is irregular (ragged block rows)."""
+    N = int(n_poses)
+    rng = np.random.default_rng(seed)
+    if box is None:
+        box = max(4, int(round((N / 4.0) ** (1.0 / 3.0))))
+    dirs = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]])
+    pos = np.zeros((N, 3), np.int64)
+    step = np.zeros((N, 3), np.int64)
+    step[0] = dirs[0]
+    choice = rng.integers(0, 6, N)
+    for k in range(1, N):
+        d = dirs[choice[k]]
+        q = pos[k - 1] + d
+        bad = (q < 0) | (q >= box)
+        d = np.where(bad, -d, d)
+        pos[k] = pos[k - 1] + d
+        step[k] = d
+    # camera frame: z along the step, x any perpendicular axis
+    z = step.astype(float)
+    x = np.where(np.abs(z[:, [0]]) > 0.5, np.array([[0.0, 1.0, 0.0]]), np.array([[1.0, 0.0, 0.0]]))
+    y = np.cross(z, x)
+    Rc2w = np.stack([x, y, z], axis=2)
+    Rw2c = Rotation.from_matrix(np.transpose(Rc2w, (0, 2, 1)))
+    k = np.arange(N)
+    s_gt = np.exp(0.2 * np.sin(2 * np.pi * k / N))
+    c = pos.astype(float)
+    t_gt = -s_gt[:, None] * Rw2c.apply(c)
+    # loop edges through a cell hash
+    cells = {}
+    for idx in range(N):
+        cells.setdefault(tuple(pos[idx]), []).append(idx)
+    r = int(np.ceil(loop_radius))
+    offs = [(a, b, cc) for a in range(-r, r + 1) for b in range(-r, r + 1) for cc in range(-r, r + 1)
+            if a * a + b * b + cc * cc <= loop_radius * loop_radius]
+    li, lj = [], []
+    for j in range(N):
+        cand = []
+        pj = pos[j]
+        for o in offs:
+            for i in cells.get((pj[0] + o[0], pj[1] + o[1], pj[2] + o[2]), ()):
+                if i <= j - min_gap:
+                    cand.append(i)
+        cand.sort(reverse=True)
+        for i in cand[:max_loops_per_pose]:
+            li.append(i); lj.append(j)
+    i_idx = np.concatenate([k[:-1], np.array(li, np.int64)])
+    j_idx = np.concatenate([k[1:], np.array(lj, np.int64)])
+    order = np.lexsort((j_idx, i_idx))
+    i_idx, j_idx = i_idx[order], j_idx[order]
+    E = len(i_idx)
+    Ri, ti, si = Rw2c[i_idx], t_gt[i_idx], s_gt[i_idx]
+    Rj, tj, sj = Rw2c[j_idx], t_gt[j_idx], s_gt[j_idx]
+    Rii, tii, sii = _inv(Ri, ti, si)
+    Rji, tji, sji = _mul(Rj, tj, sj, Rii, tii, sii)
+    sig = np.array([meas_sigma[0]] * 3 + [meas_sigma[1]] * 3 + [meas_sigma[2]])
+    Rn, tn, sn = sim3_exp(rng.standard_normal((E, 7)) * sig)
+    Rm, tm, sm = _mul(Rn, tn, sn, Rji, tji, sji)
+    meas = _pack(Rm, tm, sm)
+    isig = np.array([init_sigma[0]] * 3 + [init_sigma[1]] * 3 + [init_sigma[2]])
+    pert = rng.standard_normal((N, 7)) * isig
+    pert[0] = 0
+    Rp, tp, sp = sim3_exp(pert)
+    Re, te, se = _mul(Rp, tp, sp, Rw2c, t_gt, s_gt)
+    fixed = np.zeros(N, np.uint8)
+    fixed[0] = 1
+    info = np.zeros((E, 7, 7))
+    info[:, np.arange(7), np.arange(7)] = 1.0 / sig ** 2
+    return dict(est=_pack(Re, te, se), gt=_pack(Rw2c, t_gt, s_gt), fixed=fixed, v0=i_idx.astype(np.int32),
+                v1=j_idx.astype(np.int32), meas=meas, info=info)
+
+
 def ba_loop(n_cams=1000, n_points=500000, obs_per_point=10, seed=42, loop_length=200.0, focal=718.856,
             cx=607.1928, cy=185.2157, pixel_sigma=1.0, cam_pert=(0.01, 0.1), point_pert=0.2):
     """Synthetic bundle adjustment of SURVEY.md 8(d) config 5 (bal_example.cpp:87-88 intrinsics).

@@ -42,6 +42,12 @@ def sphere_small():
     return synth.sphere(n_laps=12, poses_per_lap=40, seed=7)
 
 
+@pytest.fixture(scope="session")
+def manhattan_small():
+    from sim3opt_b200 import synth
+    return synth.manhattan3d(500, seed=5)
+
+
 def make_oracle(g, kind=None, jac=None, robust=None):
     from oracle import oracle as orc
     p = orc.Problem(orc.KIND_SIM3 if kind is None else kind)

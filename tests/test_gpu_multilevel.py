@@ -19,7 +19,7 @@ def sphere_mid():
     return synth.sphere(n_laps=10, poses_per_lap=300, seed=11)
 
 
-@pytest.fixture(params=["kitti_k1", "kitti_k118", "sphere_small", "sphere_mid"])
+@pytest.fixture(params=["kitti_k1", "kitti_k118", "sphere_small", "sphere_mid", "manhattan_small"])
 def graph(request):
     return request.getfixturevalue(request.param)
 

@@ -22,7 +22,7 @@ def graphs(request):
     return request.getfixturevalue(request.param)
 
 
-@pytest.fixture(params=["kitti_k1", "kitti_k118", "sphere_small"])
+@pytest.fixture(params=["kitti_k1", "kitti_k118", "sphere_small", "manhattan_small"])
 def graph(request):
     return request.getfixturevalue(request.param)
 
@@ -159,6 +159,27 @@ def test_sphere_end_to_end_tolerances(sphere_small):
     vg, vc = gpu.vertices(), cpu.vertices()
     assert np.abs(vg[:, 4:7] - vc[:, 4:7]).max() <= 1e-4
     # rotation difference angle from quaternions
+    dots = np.abs((vg[:, :4] * vc[:, :4]).sum(1) / (np.linalg.norm(vg[:, :4], axis=1) * np.linalg.norm(vc[:, :4], axis=1)))
+    assert (2 * np.arccos(np.clip(dots, -1, 1))).max() <= 1e-5
+    assert np.abs(vg[:, 7] - vc[:, 7]).max() <= 1e-5
+
+
+def test_manhattan_end_to_end_tolerances(manhattan_small):
+    """Same gate on the irregular Manhattan-3D variant of config 3 (ragged block rows, many loop edges)."""
+    orc = _orc()
+    import sim3opt_b200 as s3
+    orc.set_math_mode(orc.MATH_CORRECTED)
+    try:
+        gpu = make_gpu(manhattan_small, jac=1, math_mode=s3.MATH_CORRECTED)
+        cpu = make_oracle(manhattan_small, jac=orc.JAC_ANALYTIC)
+        gpu.set_pcg(1e-10, 20000)
+        n_g, chi_g, _, _ = gpu.optimize(30)
+        n_c, chi_c, _, _ = cpu.optimize(30)
+    finally:
+        orc.set_math_mode(orc.MATH_REFERENCE)
+    assert abs(chi_g - chi_c) <= 1e-4 * chi_c
+    vg, vc = gpu.vertices(), cpu.vertices()
+    assert np.abs(vg[:, 4:7] - vc[:, 4:7]).max() <= 1e-4
     dots = np.abs((vg[:, :4] * vc[:, :4]).sum(1) / (np.linalg.norm(vg[:, :4], axis=1) * np.linalg.norm(vc[:, :4], axis=1)))
     assert (2 * np.arccos(np.clip(dots, -1, 1))).max() <= 1e-5
     assert np.abs(vg[:, 7] - vc[:, 7]).max() <= 1e-5

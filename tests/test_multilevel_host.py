@@ -37,3 +37,21 @@ def test_tiny_graph_has_no_levels(kitti_k1):
     assert len(sizes) == 0
     sizes, blocks, agg = s3.host_multilevel(len(kitti_k1["est"]), kitti_k1["fixed"], kitti_k1["v0"], kitti_k1["v1"])
     assert len(sizes) >= 2 and sizes[0] < 771 // 2
+
+
+def test_partitioned_hierarchy_respects_vertex_ranges():
+    """World-size-N hierarchy (the partitioned solve): aggregates stay inside a rank's vertex range and
+    are numbered rank by rank, so every rank owns a contiguous range of coarse rows."""
+    g = synth.sphere(8, 500, seed=3)
+    nv = len(g["est"])
+    nf = int((np.asarray(g["fixed"]) == 0).sum())
+    for world in (2, 4, 8):
+        sizes, blocks, agg = s3.host_multilevel(nv, g["fixed"], g["v0"], g["v1"], world=world)
+        seg = -(-nf // world)
+        owner = np.arange(nf) // seg
+        # one owner per aggregate
+        lo = np.full(sizes[0], world, np.int64); hi = np.full(sizes[0], -1, np.int64)
+        np.minimum.at(lo, agg, owner); np.maximum.at(hi, agg, owner)
+        assert np.array_equal(lo, hi)
+        assert np.all(np.diff(lo) >= 0)                  # coarse numbering follows the ranks
+        assert np.all(np.diff(np.concatenate([[nf], sizes])) < 0)

@@ -211,3 +211,29 @@ def test_scale_trans_graph_zero_residual(kitti_k1):
             Hn, bn = H, b
     assert np.abs(H - Hn).max() <= 1e-6 * np.abs(H).max()
     assert np.abs(b - bn).max() <= 1e-6 * np.abs(b).max()
+
+
+def test_manhattan_generator_and_oracle_convergence():
+    """Manhattan-3D variant of config 3: deterministic generator, irregular graph, and the
+    oracle LM reaches chi2 ~ sigma^2 * dof from the perturbed start."""
+    from oracle import oracle as orc
+    from sim3opt_b200 import synth
+    g = synth.manhattan3d(300, seed=9)
+    g2 = synth.manhattan3d(300, seed=9)
+    assert all(np.array_equal(g[k], g2[k]) for k in ("est", "v0", "v1", "meas"))
+    nv, ne = len(g["est"]), len(g["v0"])
+    assert ne > nv and np.all(g["v0"] < g["v1"])
+    deg = np.bincount(np.concatenate([g["v0"], g["v1"]]), minlength=nv)
+    assert deg.max() >= 6 and deg.min() >= 1                     # ragged rows
+    orc.set_math_mode(orc.MATH_CORRECTED)
+    try:
+        p = orc.Problem(orc.KIND_SIM3)
+        p.set_vertices(g["est"], g["fixed"])
+        p.set_edges(g["v0"], g["v1"], g["meas"], g["info"])
+        p.set_jacobian_mode(orc.JAC_ANALYTIC)
+        n, chi2, lam, hist = p.optimize(20)
+    finally:
+        orc.set_math_mode(orc.MATH_REFERENCE)
+    dof = 7 * (ne - (nv - 1))
+    assert 0.8 * dof <= chi2 <= 1.2 * dof
+    assert np.abs(p.vertices()[:, 4:7] - g["gt"][:, 4:7]).max() < 1.0
