@@ -499,15 +499,22 @@ constexpr size_t spmv4_smem_bytes() {
 static int g_spmv4_cfg = 0;     // 0: TB=112 NS=2, 1: TB=80 NS=3, 2: TB=56 NS=4   (S3O_SPMV4_CFG)
 int spmv4_tile_blocks() { return g_spmv4_cfg == 0 ? 112 : (g_spmv4_cfg == 1 ? 80 : 56); }
 void spmv4_set_cfg(int cfg) { g_spmv4_cfg = cfg < 0 || cfg > 2 ? 0 : cfg; }
+// persistent grid: grid_cap CTAs (2 per SM); a graph with more than grid_cap * KMAX tiles gets the next
+// multiple of grid_cap that keeps every CTA's descriptor list within KMAX
+static int spmv4_grid(int ntiles, int grid_cap) {
+    if (ntiles <= grid_cap) return ntiles;
+    const int waves = (int)(((long long)ntiles + (long long)grid_cap * Spmv4Cfg::KMAX - 1) / ((long long)grid_cap * Spmv4Cfg::KMAX));
+    return grid_cap * waves;
+}
 bool spmv4_fits(int ntiles, int grid_cap) {
-    const int grid = ntiles < grid_cap ? ntiles : grid_cap;
-    return grid > 0 && (ntiles + grid - 1) / grid <= Spmv4Cfg::KMAX;
+    const int grid = spmv4_grid(ntiles, grid_cap);
+    return grid > 0 && grid <= kMaxPartials && (ntiles + grid - 1) / grid <= Spmv4Cfg::KMAX;
 }
 
 void launch_spmv4(const double *H, const StructDev &s, int nf, double lambda, const double *p, double *q1, double *T,
                   double *partials, DevScalars *sc, int pcg_mode, int grid_cap, int dist, cudaStream_t st) {
     if (nf == 0 || s.ntiles == 0) return;
-    const int grid = s.ntiles < grid_cap ? s.ntiles : grid_cap;
+    const int grid = spmv4_grid(s.ntiles, grid_cap);
     constexpr int NT = Spmv4Cfg::NT, KM = Spmv4Cfg::KMAX;
     switch (g_spmv4_cfg) {
     case 0: spmv4_kernel<7, NT, 112, 2, KM><<<grid, NT, spmv4_smem_bytes<112, 2>(), st>>>(H, s, nf, lambda, p, q1, T, partials, sc, pcg_mode, dist); break;
