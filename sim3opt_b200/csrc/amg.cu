@@ -39,7 +39,6 @@ struct AmgState {
     std::vector<AmgHostLevel> host;
     std::vector<LevelDev> lev;
     int32_t *d_vid0 = nullptr;      // level-0 vertex ids (free2v)
-    int32_t *d_blk_row0 = nullptr;  // borrowed from the problem
     double *d_dense = nullptr;      // inverse of the coarsest operator, [N][N]
     bool dense = false;
     bool frames_valid = false;

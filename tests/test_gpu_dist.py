@@ -11,8 +11,9 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("precond", [1, 2])     # block-Jacobi, multilevel (replicated coarse levels)
-def test_partitioned_solve_matches_single_gpu(precond):
+@pytest.mark.parametrize("precond,graph", [(1, "sphere"), (2, "sphere"), (2, "manhattan")])
+def test_partitioned_solve_matches_single_gpu(precond, graph):
+    """block-Jacobi and multilevel (replicated coarse levels) PCG; regular and irregular (many cut loop edges) graphs"""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -21,7 +22,7 @@ def test_partitioned_solve_matches_single_gpu(precond):
     port = s.getsockname()[1]
     s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "dist_check.py"), "30", "80", "5", str(precond)]
+           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "dist_check.py"), "30", "80", "5", str(precond), graph]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert "DIST_CHECK PASS" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
     assert "ESTIMATES_IDENTICAL_ACROSS_RANKS True" in out.stdout

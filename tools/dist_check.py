@@ -1,7 +1,7 @@
 """Partitioned solve vs single-GPU solve of the same graph (run under torchrun, one rank per GPU).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        tools/dist_check.py [laps] [poses_per_lap] [lm_iters] [preconditioner 0|1|2]
+        tools/dist_check.py [laps] [poses_per_lap] [lm_iters] [preconditioner 0|1|2] [sphere|manhattan]
 Prints "DIST_CHECK PASS" on rank 0 when chi2 histories agree to 1e-9 relative and the estimates to 1e-8.
 """
 import os
@@ -24,7 +24,8 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    g = synth.sphere(laps, per, seed=11)
+    graph = sys.argv[5] if len(sys.argv) > 5 else "sphere"
+    g = synth.sphere(laps, per, seed=11) if graph == "sphere" else synth.manhattan3d(laps * per, seed=11)
     box = [s3.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=0)
 

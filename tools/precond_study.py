@@ -225,7 +225,8 @@ def main():
     S = est[free]
     R, t, s = quat_to_R(S[:, 0:4]), S[:, 4:7], S[:, 7]
 
-    for tol in (1e-3, 1e-8):
+    tols = (1e-3,) if os.environ.get("FAST") else (1e-3, 1e-8)
+    for tol in tols:
         L0 = Level(); L0.Dinv = block_diag_inv(A, nf, d)
         t0 = time.time()
         x, it = pcg(A, b, lambda r: bjac(L0, r), tol)
@@ -235,10 +236,10 @@ def main():
     print(f"hierarchy: {len(levels)} levels ({time.time() - t0:.1f}s)")
     for omega in (0.6, 0.8, 1.0):
         for nadd in (1, 99):
-            for tol in (1e-3, 1e-8):
+            for tol in tols:
                 x, it = pcg(A, b, lambda r: acycle(levels, 0, r, omega, 1, nadd), tol)
                 print(f"additive x{nadd} (omega={omega}) PCG tol {tol:g}: {it} iterations")
-    for omega in (0.6, 0.8):
+    for omega in (() if os.environ.get("FAST") else (0.6, 0.8)):
         for sweeps in (1, 2):
             for tol in (1e-3, 1e-8):
                 x, it = pcg(A, b, lambda r: vcycle(levels, 0, r, omega, sweeps), tol)
