@@ -313,14 +313,35 @@ __device__ __forceinline__ void warp_store_piece(double *stage, const double *va
     __syncwarp();
 }
 
+// same, but every element of the warp has its own destination (dptr[el], staged in shared memory)
+template <int S>
+__device__ __forceinline__ void warp_store_piece_to(double *stage, const double *vals, double **dptr, double *mine,
+                                                    int lane, int nvalid) {
+#pragma unroll
+    for (int f = 0; f < S; ++f) stage[lane * S + f] = vals[f];
+    dptr[lane] = mine;
+    __syncwarp();
+    for (int idx = lane; idx < nvalid * S; idx += 32) {
+        const int el = idx / S, f = idx - el * S;
+        dptr[el][f] = stage[idx];
+    }
+    __syncwarp();
+}
+
+// The cross term of an edge that is the only one feeding its off-diagonal block goes straight into
+// the Hessian (Hdirect != null): assemble_kernel then has nothing to do for that block.
 template <int KIND, int JAC, int NT>
-__global__ void __launch_bounds__(NT) linearize_kernel(GraphDev g, double h, double *__restrict__ scratch) {
+__global__ void __launch_bounds__(NT) linearize_kernel(GraphDev g, double h, double *__restrict__ scratch,
+                                                       const int32_t *__restrict__ e_blk,
+                                                       const int32_t *__restrict__ blk_src, double *__restrict__ Hdirect) {
     constexpr int D = Model<KIND>::D, EST = Model<KIND>::EST, DD = D * D;
     constexpr int NS = packed_size(D), STRIDE = scr_stride(D);
     constexpr int SMAX = DD > NS + D ? DD : NS + D;
     __shared__ double stage_all[(NT / 32) * 32 * SMAX];
+    __shared__ double *dptr_all[NT];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *stage = stage_all + warp * 32 * SMAX;
+    double **dptr = dptr_all + warp * 32;
     const int e0 = (blockIdx.x * NT + warp * 32);
     if (e0 >= g.ne) return;
     const int t = e0 + lane;
@@ -433,6 +454,13 @@ __global__ void __launch_bounds__(NT) linearize_kernel(GraphDev g, double h, dou
     }
     warp_store_piece<NS + D>(stage, out, rec0, STRIDE, lane, nvalid);
     // ---- cross term Hij = (A^T O') B
+    double *cross_dst = rec0 + (size_t)lane * STRIDE + 2 * (NS + D);
+    bool flip = false;         // stored block is (min,max): vertex(0) on the max side -> transpose
+    if (valid && Hdirect) {
+        const int kb = e_blk[t];
+        const int src = kb >= 0 ? blk_src[kb] : -1;
+        if (src >= 0) { cross_dst = Hdirect + (size_t)kb * DD; flip = (src & 1) != 0; }
+    }
     if (valid) {
 #pragma unroll
         for (int r = 0; r < D; ++r)
@@ -443,8 +471,14 @@ __global__ void __launch_bounds__(NT) linearize_kernel(GraphDev g, double h, dou
                 for (int k = 0; k < D; ++k) acc += P[r * D + k] * B[k * D + c];
                 out[r * D + c] = acc;
             }
+        if (flip) {
+#pragma unroll
+            for (int r = 0; r < D; ++r)
+#pragma unroll
+                for (int c = r + 1; c < D; ++c) { const double tmp = out[r * D + c]; out[r * D + c] = out[c * D + r]; out[c * D + r] = tmp; }
+        }
     }
-    warp_store_piece<DD>(stage, out, rec0 + 2 * (NS + D), STRIDE, lane, nvalid);
+    warp_store_piece_to<DD>(stage, out, dptr, cross_dst, lane, nvalid);
     // ---- vertex(1) side: P = B^T O'
     if (valid) {
 #pragma unroll
@@ -477,15 +511,16 @@ __global__ void __launch_bounds__(NT) linearize_kernel(GraphDev g, double h, dou
     warp_store_piece<NS + D>(stage, out, rec0 + (NS + D), STRIDE, lane, nvalid);
 }
 
-void launch_linearize(const GraphDev &g, int jac_mode, double h, double *scratch, cudaStream_t st) {
+void launch_linearize(const GraphDev &g, int jac_mode, double h, double *scratch, const int32_t *e_blk,
+                      const int32_t *blk_src, double *Hdirect, cudaStream_t st) {
     if (g.ne == 0) return;
     constexpr int NT = 64;
     const int grid = (g.ne + NT - 1) / NT;
 #define S3O_LIN(KIND)                                                                                  \
     if (jac_mode == S3O_JAC_ANALYTIC)                                                                  \
-        linearize_kernel<KIND, S3O_JAC_ANALYTIC, NT><<<grid, NT, 0, st>>>(g, h, scratch);              \
+        linearize_kernel<KIND, S3O_JAC_ANALYTIC, NT><<<grid, NT, 0, st>>>(g, h, scratch, e_blk, blk_src, Hdirect);              \
     else                                                                                               \
-        linearize_kernel<KIND, S3O_JAC_NUMERIC, NT><<<grid, NT, 0, st>>>(g, h, scratch);
+        linearize_kernel<KIND, S3O_JAC_NUMERIC, NT><<<grid, NT, 0, st>>>(g, h, scratch, e_blk, blk_src, Hdirect);
     switch (g.kind) {
     case S3O_KIND_SIM3: S3O_LIN(S3O_KIND_SIM3) break;
     case S3O_KIND_SCALE_TRANS: S3O_LIN(S3O_KIND_SCALE_TRANS) break;
@@ -506,13 +541,7 @@ __global__ void assemble_kernel(GraphDev g, StructDev s, const double *__restric
     if (k64 >= g.nb) return;
     const int k = (int)k64, el = (int)(tid - k64 * EL);
     const int src = __ldg(s.blk_src + k);
-    if (src >= 0) {       // off-diagonal block fed by one edge: a (possibly transposed) copy of its A^T O' B
-        if (el < DD) {
-            const int r = el / D, c = el - r * D;
-            H[(size_t)k * DD + el] = scratch[(size_t)(src >> 1) * STRIDE + 2 * (NS + D) + ((src & 1) ? c * D + r : r * D + c)];
-        }
-        return;
-    }
+    if (src >= 0) return;   // off-diagonal block fed by one edge: linearize_kernel wrote it in place
     const int row = s.blk_row[k], col = s.colidx[k];
     if (row == col) {
         int off;

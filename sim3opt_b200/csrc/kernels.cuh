@@ -64,7 +64,9 @@ void launch_pack_edges(const double *meas_aos, const double *info_aos, const int
 void launch_chi2(const GraphDev &g, double *partials, DevScalars *sc, cudaStream_t st);
 void launch_edge_errors(const GraphDev &g, double *err_sorted /* [ne][d] */, double *chi2_sorted /* [ne] or null */,
                         cudaStream_t st);
-void launch_linearize(const GraphDev &g, int jac_mode, double h, double *scratch /* [ne][scr] */, cudaStream_t st);
+// e_blk / blk_src / Hdirect: single-edge off-diagonal blocks are written straight into the Hessian
+void launch_linearize(const GraphDev &g, int jac_mode, double h, double *scratch /* [ne][scr] */, const int32_t *e_blk,
+                      const int32_t *blk_src, double *Hdirect, cudaStream_t st);
 int scratch_stride(int d);
 void launch_assemble(const GraphDev &g, const StructDev &s, const double *scratch, double *H, double *b,
                      cudaStream_t st);

@@ -151,7 +151,7 @@ int do_chi2(s3o_problem *p, int which) {
 int do_linearize(s3o_problem *p) {
     if (p->kind == S3O_KIND_BA) return ba_linearize(p);
     const GraphDev g = graph_view(p, p->cur);
-    launch_linearize(g, p->jac_mode, p->jac_h, p->d_scratch, p->stream);
+    launch_linearize(g, p->jac_mode, p->jac_h, p->d_scratch, p->d_e_blk, p->d_blk_src, p->d_H, p->stream);
     launch_assemble(g, struct_view(p), p->d_scratch, p->d_H, p->d_b, p->stream);
     amg_invalidate_frames(p);
     p->linearized = true;
