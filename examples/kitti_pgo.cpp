@@ -11,6 +11,7 @@
 // usage: kitti_pgo direct   <dataDir> <outFile> [--all-loops] [--iters N] [--numeric] [--pcg-tol T] [--precision P]
 //        kitti_pgo stepwise <dataDir> <outFile> [--all-loops] [--stages 2|3] [--no-stepwise] [--iters N]
 //        kitti_pgo dry-run  <dataDir> [--all-loops]        (no GPU: loads, builds, prints structure sizes)
+//        kitti_pgo align    <resultFile> <gtPoseFile> [--only-scale]   (kitti_surf.cpp:1381-1452: Umeyama + RMSE)
 #define S3O_FACADE_EIGEN_NAMES
 #include <chrono>
 #include <cstring>
@@ -273,6 +274,35 @@ int runStepwise(const Options &o) {
     return 0;
 }
 
+// ALIGN_TRAJECTORIES_OPTIMIZED (kitti_surf.cpp:1381-1452): similarity-align an optimised key-frame
+// trajectory to the KITTI ground truth and report RMSE / max deviation / their ratio to the path length.
+int runAlign(const string &resultFile, const string &gtFile, bool onlyScale) {
+    vector<g2o::Vector3> gt, opt;
+    vector<int> ids;
+    if (!ReadKITTIPosePositions(gtFile, gt)) { std::cerr << "cannot read " << gtFile << "\n"; return 2; }
+    if (!ReadOptimizedSim3Positions(resultFile, ids, opt)) { std::cerr << "cannot read " << resultFile << "\n"; return 2; }
+    std::cout << "Num of lines:" << gt.size() << "\nNum of lines:" << opt.size() << "\n";
+    double totalDistance = 0;
+    for (size_t j = 1; j < gt.size(); ++j) totalDistance += (gt[j] - gt[j - 1]).norm();
+    vector<double> q, t;
+    for (size_t j = 0; j < ids.size(); ++j) {
+        if (ids[j] < 0 || ids[j] >= (int)gt.size()) { std::cerr << "frame id " << ids[j] << " not in the ground truth\n"; return 2; }
+        for (int c = 0; c < 3; ++c) { q.push_back(opt[j][c]); t.push_back(gt[ids[j]][c]); }
+    }
+    double S221[16], rmse = 0, maxError = 0;
+    if (s3o_align_similarity(0, (int)ids.size(), q.data(), t.data(), onlyScale ? 1 : 0, S221, &rmse, &maxError) != S3O_OK) {
+        std::cerr << s3o_last_error() << "\n";
+        return 3;
+    }
+    std::cout << "estimated similarity transform by umeyama \n";
+    std::cout.precision(9);
+    for (int r = 0; r < 4; ++r) std::cout << S221[r * 4] << " " << S221[r * 4 + 1] << " " << S221[r * 4 + 2] << " " << S221[r * 4 + 3] << "\n";
+    std::cout << "RMSE and Max deviation " << rmse << " " << maxError << "\n";
+    std::cout << "total distance " << totalDistance << " ratio of rmse and max error " << rmse / totalDistance << " "
+              << maxError / totalDistance << "\n";
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -284,6 +314,10 @@ int main(int argc, char **argv) {
     }
     o.mode = argv[1];
     o.dataDir = argv[2];
+    if (o.mode == "align") {       // kitti_pgo align <resultFile> <gtPoseFile> [--only-scale]
+        if (argc < 4) { std::cerr << "usage: kitti_pgo align <resultFile> <gtPoseFile> [--only-scale]\n"; return 1; }
+        return runAlign(argv[2], argv[3], argc > 4 && string(argv[4]) == "--only-scale");
+    }
     int k = 3;
     if (o.mode != "dry-run") {
         if (argc < 4) { std::cerr << "missing <outFile>\n"; return 1; }

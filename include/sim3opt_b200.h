@@ -230,6 +230,15 @@ typedef struct s3o_stats {
 int s3o_get_stats(s3o_problem *p, s3o_stats *out);
 int s3o_reset_stats(s3o_problem *p);
 
+/* ---- trajectory alignment and its RMSE (evaluation modes of the reference, kitti_surf.cpp:1091-1161,
+ * :1432-1452) ---------------------------------------------------------------------------------
+ * Similarity S221 (4x4 row-major, [cR t; 0 1]) that maps the query positions onto the train positions:
+ * Eigen::umeyama(query, train, true), or with only_scale != 0 the reference's extent-ratio scale
+ * (mean over the x and z axes, no rotation / translation).  rmse and max_dev are those of
+ * train_i - S221 query_i.  n x 3 arrays, row-major.  Moments are reduced on `device`. */
+int s3o_align_similarity(int device, int n, const double *query_xyz, const double *train_xyz, int only_scale,
+                         double *S221 /* 16 */, double *rmse, double *max_dev);
+
 /* ---- PTAM sigma estimate (MEstimator.h FindSigmaSquared) on the current edge chi2 values - */
 int s3o_estimate_sigma_squared(s3o_problem *p, int robust_kind, double *sigma_squared);
 

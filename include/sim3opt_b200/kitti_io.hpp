@@ -133,5 +133,39 @@ inline void WriteSim3Line(std::ostream &os, int frame_id, const g2o::Sim3 &Siw, 
        << q[3] << "\n";
 }
 
+// KITTI odometry ground truth: every line holds the 12 numbers of the 3x4 T_c2w, row-major
+// (readKITTIPoseFile, kitti_surf.cpp:1166-1190).  Keeps the camera positions (column 3).
+inline bool ReadKITTIPosePositions(const std::string &poseFile, std::vector<g2o::Vector3> &positions) {
+    std::ifstream in(poseFile);
+    if (!in) return false;
+    positions.clear();
+    double m[12];
+    while (in >> m[0]) {
+        for (int j = 1; j < 12; ++j) if (!(in >> m[j])) return false;
+        positions.push_back(g2o::Vector3(m[3], m[7], m[11]));
+    }
+    return true;
+}
+
+// Result file of the optimisers: a '%' comment line, then "kfId s_w2i t_i_in_w q_i2w(xyzw)" per key frame
+// (readOptimizedSim3PoseFile, kitti_surf.cpp:1197-1228; the scale and the rotation are read and dropped).
+inline bool ReadOptimizedSim3Positions(const std::string &poseFile, std::vector<int> &frameIds,
+                                       std::vector<g2o::Vector3> &positions) {
+    std::ifstream in(poseFile);
+    if (!in) return false;
+    std::string header;
+    std::getline(in, header);
+    frameIds.clear();
+    positions.clear();
+    int id;
+    double s, x, y, z, q[4];
+    while (in >> id) {
+        if (!(in >> s >> x >> y >> z >> q[0] >> q[1] >> q[2] >> q[3])) return false;
+        frameIds.push_back(id);
+        positions.push_back(g2o::Vector3(x, y, z));
+    }
+    return true;
+}
+
 }  // namespace kitti
 }  // namespace s3o

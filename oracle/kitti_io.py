@@ -107,3 +107,20 @@ def to_scale_trans_graph(g):
     aux = g["est"][:, :4].copy()
     meas = np.concatenate([g["meas"][:, 7:8], g["meas"][:, 4:7]], axis=1)
     return dict(est=est, aux=aux, fixed=g["fixed"], v0=g["v0"], v1=g["v1"], meas=meas)
+
+
+def load_kitti_gt_positions(pose_file):
+    """readKITTIPoseFile (kitti_surf.cpp:1166-1190): every line holds the 12 numbers of the 3x4 T_c2w in
+    row-major order; returns the camera positions [n,3] (column 3)."""
+    M = np.loadtxt(pose_file).reshape(-1, 3, 4)
+    return M[:, :, 3].copy()
+
+
+def camera_positions(est):
+    """Camera centres in the world of Sim3 estimates S_iw = (q, t, s): -R^T t / s (what the result writer
+    stores as t_i_in_w, kitti_surf.cpp:678-703)."""
+    est = np.asarray(est, float).reshape(-1, 8)
+    out = np.zeros((len(est), 3))
+    for k, S in enumerate(est):
+        out[k] = orc.sim3_inv(S)[4:7]
+    return out

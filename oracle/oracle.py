@@ -394,3 +394,35 @@ class BAProblem:
         chi2, lam = C.c_double(0), C.c_double(0)
         n = self.L.orc_ba_optimize(self.h, max_iter, stop_rel_gain, _d(hist), max_iter, C.byref(chi2), C.byref(lam))
         return n, chi2.value, lam.value, hist[:max(n, 0)]
+
+
+# ---- trajectory alignment (evaluation modes of the reference) --------------------------------------
+def umeyama(query, train, only_scale=False):
+    """estimateSimilarityTransform + the RMSE loop (kitti_surf.cpp:1091-1161, :1432-1452).
+
+    Eigen::umeyama(query, train, with_scaling=True) [EXT Eigen; S. Umeyama, "Least-squares estimation of
+    transformation parameters between two point patterns", PAMI 13(4), 1991, eq. 40-43]: with the means mq,
+    mt, the query variance vq = mean |q - mq|^2 and Sigma = mean (t - mt)(q - mq)^T = U D V^T,
+    S = diag(1, 1, sign(det U det V)),  R = U S V^T,  c = trace(D S) / vq,  t = mt - c R mq.
+    only_scale: the reference's extent-ratio variant (:1104-1136).  Returns (S221 4x4, rmse, max_dev)."""
+    q = np.asarray(query, float).reshape(-1, 3)
+    t = np.asarray(train, float).reshape(-1, 3)
+    S = np.eye(4)
+    if only_scale:
+        ratio = (t.max(0) - t.min(0)) / (q.max(0) - q.min(0))
+        S[:3, :3] *= 0.5 * (ratio[0] + ratio[2])
+    else:
+        mq, mt = q.mean(0), t.mean(0)
+        vq = ((q - mq) ** 2).sum(1).mean()
+        Sigma = (t - mt).T @ (q - mq) / len(q)
+        U, D, Vt = np.linalg.svd(Sigma)
+        sgn = np.ones(3)
+        if np.linalg.det(U) * np.linalg.det(Vt) < 0:
+            sgn[2] = -1
+        R = U @ np.diag(sgn) @ Vt
+        c = (D * sgn).sum() / vq
+        S[:3, :3] = c * R
+        S[:3, 3] = mt - c * R @ mq
+    dev = t - (q @ S[:3, :3].T + S[:3, 3])
+    d = np.sqrt((dev ** 2).sum(1))
+    return S, float(np.sqrt((d ** 2).mean())), float(d.max())

@@ -50,6 +50,7 @@ SYMBOLS = {
     "s3o_build_structure": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "s3o_host_structure": (C.c_int, [C.c_int, _up, C.c_int, _ip, _ip, C.POINTER(C.c_int), C.POINTER(C.c_int), _ip, _ip, _ip]),
     "s3o_host_multilevel": (C.c_int, [C.c_int, _up, C.c_int, _ip, _ip, C.c_int, C.c_int, C.POINTER(C.c_int), _ip, _ip, _ip]),
+    "s3o_align_similarity": (C.c_int, [C.c_int, C.c_int, _dp, _dp, C.c_int, _dp, _dp, _dp]),
     "s3o_get_structure": (C.c_int, [C.c_void_p, _ip, _ip]),
     "s3o_get_hessian_index": (C.c_int, [C.c_void_p, _ip]),
     "s3o_chi2": (C.c_int, [C.c_void_p, _dp]),

@@ -243,6 +243,22 @@ def host_partition(n_vertices, fixed, v0, v1, rank, world):
                 send_idx=send_idx[:int(send_count.sum())].copy())
 
 
+def align_similarity(query_xyz, train_xyz, only_scale=False, device=0):
+    """Umeyama similarity of the query positions onto the train positions (kitti_surf.cpp:1091-1161) and the
+    RMSE / max deviation of the aligned points (:1432-1452).  Returns (S221 4x4, rmse, max_dev)."""
+    L = _lib.load()
+    q = _f64(query_xyz).reshape(-1, 3)
+    t = _f64(train_xyz).reshape(-1, 3)
+    if len(q) != len(t):
+        raise S3OError("align_similarity: trajectories differ in length")
+    S = np.zeros(16)
+    rmse, mx = C.c_double(0), C.c_double(0)
+    rc = L.s3o_align_similarity(int(device), len(q), _d(q), _d(t), 1 if only_scale else 0, _d(S), C.byref(rmse), C.byref(mx))
+    if rc != 0:
+        raise S3OError(f"s3o error {rc}: {L.s3o_last_error().decode()}")
+    return S.reshape(4, 4), rmse.value, mx.value
+
+
 def host_multilevel(n_vertices, fixed, v0, v1, world=1):
     """Aggregation hierarchy of the multilevel preconditioner (host only): per-level vertex counts,
     per-level block counts, and the finest-level aggregate of every free vertex."""

@@ -157,3 +157,22 @@ def test_ba_demo_matches_oracle(kitti_pgo, tmp_path):
     for k in (0, 13, 29):
         R = orc.quat_to_rot(cams[k, :4])
         assert np.abs(res[k, 1:4] - (-R.T @ cams[k, 4:7])).max() <= 1e-4
+
+
+@pytest.mark.gpu
+def test_align_mode_reports_rmse_against_ground_truth(kitti_pgo, tmp_path, kitti_k1):
+    """kitti_pgo align (kitti_surf.cpp:1381-1452): result file of the direct pipeline -> Umeyama alignment to the
+    KITTI-00 ground truth; numbers agree with the oracle's alignment of the same estimates."""
+    from oracle import oracle as orc, kitti_io
+    out_file = str(tmp_path / "direct.txt")
+    run(kitti_pgo, "direct", KITTI_DIR, out_file, "--iters", "3", "--precision", "17")
+    out = run(kitti_pgo, "align", out_file, os.path.join(KITTI_DIR, "00.txt"))
+    m = re.search(r"RMSE and Max deviation (\S+) (\S+)", out)
+    m2 = re.search(r"total distance (\S+) ratio of rmse and max error (\S+) (\S+)", out)
+    res = read_result(out_file)
+    gt = kitti_io.load_kitti_gt_positions(os.path.join(KITTI_DIR, "00.txt"))
+    S, rmse, mx = orc.umeyama(res[:, 2:5], gt[res[:, 0].astype(int)])
+    assert abs(float(m.group(1)) - rmse) <= 1e-6 * rmse and abs(float(m.group(2)) - mx) <= 1e-6 * mx
+    total = np.linalg.norm(np.diff(gt, axis=0), axis=1).sum()
+    assert abs(float(m2.group(1)) - total) <= 1e-6 * total
+    assert abs(float(m2.group(2)) - rmse / total) <= 1e-6 * rmse / total
