@@ -12,6 +12,7 @@
 //        kitti_pgo stepwise <dataDir> <outFile> [--all-loops] [--stages 2|3] [--no-stepwise] [--iters N]
 //        kitti_pgo dry-run  <dataDir> [--all-loops]        (no GPU: loads, builds, prints structure sizes)
 //        kitti_pgo align    <resultFile> <gtPoseFile> [--only-scale]   (kitti_surf.cpp:1381-1452: Umeyama + RMSE)
+//        kitti_pgo reproject <keyFrameDir> <resultFile> <out.bal>       (drawPTAMPoints.cpp:285-456: map -> BAL)
 #define S3O_FACADE_EIGEN_NAMES
 #include <chrono>
 #include <cstring>
@@ -20,6 +21,7 @@
 
 #include "sim3opt_b200/g2o_facade.hpp"
 #include "sim3opt_b200/kitti_io.hpp"
+#include "sim3opt_b200/map_io.hpp"
 
 using namespace s3o::kitti;
 using std::string;
@@ -303,6 +305,18 @@ int runAlign(const string &resultFile, const string &gtFile, bool onlyScale) {
     return 0;
 }
 
+// figureKITTIBA (drawPTAMPoints.cpp:285-456, called at kitti_surf.cpp:1337,1375): key-frame dumps + optimised
+// trajectory -> BAL file for ba_demo.  S221 is the identity here, as at the reference's call sites.
+int runReproject(const string &keyFrameDir, const string &resultFile, const string &balFile) {
+    s3o::mapio::BalProblem P;
+    string err;
+    if (!s3o::mapio::ReprojectMap(keyFrameDir, resultFile, RobotVision::Sim3<>(), P, &err)) { std::cerr << err << "\n"; return 2; }
+    if (!s3o::mapio::SaveBALFile(P, balFile)) { std::cerr << "cannot write " << balFile << "\n"; return 2; }
+    std::cout << "cameras " << P.Rw2c.size() << " points " << P.points.size() << " observations " << P.obs.size() << "\n";
+    std::cout << "saved output file " << balFile << "\n";
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -317,6 +331,10 @@ int main(int argc, char **argv) {
     if (o.mode == "align") {       // kitti_pgo align <resultFile> <gtPoseFile> [--only-scale]
         if (argc < 4) { std::cerr << "usage: kitti_pgo align <resultFile> <gtPoseFile> [--only-scale]\n"; return 1; }
         return runAlign(argv[2], argv[3], argc > 4 && string(argv[4]) == "--only-scale");
+    }
+    if (o.mode == "reproject") {   // kitti_pgo reproject <keyFrameDir> <resultFile> <out.bal>
+        if (argc < 5) { std::cerr << "usage: kitti_pgo reproject <keyFrameDir> <resultFile> <out.bal>\n"; return 1; }
+        return runReproject(argv[2], argv[3], argv[4]);
     }
     int k = 3;
     if (o.mode != "dry-run") {
