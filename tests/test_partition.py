@@ -67,6 +67,52 @@ def _gloo_worker(rank, world, port, q):
             sent_to_me = objs[r][1][off[rank]:off[rank + 1]]
             mine = [x for x in plan["ghosts"].tolist() if x // seg == r]
             ok = ok and sent_to_me == mine
+        # a partitioned product y = (H + lambda I) x over the plan's halo lists: every rank holds its own rows
+        # of H (from the oracle's linearisation) and its own segment of x, receives exactly its ghosts, and the
+        # gathered result equals the global product -- i.e. the ghosts cover every column the owned rows touch
+        from oracle import oracle as orc
+        p = orc.Problem(orc.KIND_SIM3)
+        p.set_vertices(g["est"], g["fixed"])
+        p.set_edges(g["v0"], g["v1"], g["meas"], g["info"])
+        p.set_jacobian_mode(orc.JAC_ANALYTIC)
+        colptr, rowidx = p.build_structure()
+        H, _b = p.linearize()
+        d = 7
+        A = np.zeros((nf * d, nf * d))
+        for c in range(nf):
+            for k in range(colptr[c], colptr[c + 1]):
+                r = rowidx[k]
+                A[r * d:(r + 1) * d, c * d:(c + 1) * d] = H[k]
+                A[c * d:(c + 1) * d, r * d:(r + 1) * d] = H[k].T
+        A += 0.3 * np.eye(nf * d)
+        x = np.random.default_rng(1).normal(size=(nf, d))
+        lo, hi = min(nf, rank * seg), min(nf, (rank + 1) * seg)
+        known = {i: x[i] for i in range(lo, hi)}                       # what this rank may read
+        off = np.concatenate([[0], np.cumsum(plan["send_count"])])
+        reqs, bufs = [], {}
+        for peer in range(world):
+            if peer == rank:
+                continue
+            send = plan["send_idx"][off[peer]:off[peer + 1]]
+            if len(send):
+                reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(x[send])), peer))
+            gh = [gi for gi in plan["ghosts"].tolist() if gi // seg == peer]
+            if gh:
+                bufs[peer] = (gh, torch.zeros((len(gh), d), dtype=torch.float64))
+                reqs.append(dist.irecv(bufs[peer][1], peer))
+        for rq in reqs:
+            rq.wait()
+        for peer, (gh, buf) in bufs.items():
+            for gi, row in zip(gh, buf.numpy()):
+                known[gi] = row
+        y_own = np.zeros((hi - lo, d))
+        for i in range(lo, hi):
+            cols = np.nonzero(np.abs(A[i * d:(i + 1) * d]).reshape(d, nf, d).max(axis=(0, 2)))[0]
+            for j in cols:
+                y_own[i - lo] += A[i * d:(i + 1) * d, j * d:(j + 1) * d] @ known[int(j)]     # KeyError = a missing ghost
+        ys = [None] * world
+        dist.all_gather_object(ys, y_own)
+        ok = ok and np.abs(np.concatenate(ys).reshape(-1) - A @ x.reshape(-1)).max() <= 1e-9 * np.abs(A @ x.reshape(-1)).max()
         # the allreduce every PCG iteration relies on: a sum of per-rank partials
         t = torch.tensor([float(plan["n_primary"])], dtype=torch.float64)
         dist.all_reduce(t)
