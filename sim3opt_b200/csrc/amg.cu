@@ -53,6 +53,8 @@ struct AmgState {
     size_t r_max = 0;
     double *d_rpad = nullptr;       // [world][r_max]
     int32_t *d_unpad_src = nullptr; // [n_1 * 7] position in d_rpad of every entry of r_1
+    int32_t *d_scal_pos = nullptr;  // [world] position in d_rpad of every rank's two partial scalars
+    size_t r_seg = 0;               // doubles per rank in d_rpad: r_max + 2
 };
 
 namespace {
@@ -325,11 +327,26 @@ __global__ void __launch_bounds__(128) amg_row_kernel(int n, const int32_t *__re
     if (act) out[(size_t)i * D + l] = (MODE == 2 ? x[(size_t)i * D + l] : 0.0) + omega * z;
 }
 
+// Partitioned solve: every rank's all-gather segment carries, after its rows of r_1, its partial sums
+// r.zJ and |r|^2 (two doubles) -- the second all-reduce of a PCG iteration rides on this all-gather.
+__global__ void amg_scalars_to_vec_kernel(double *__restrict__ slot, const DevScalars *sc, int check_done) {
+    if (check_done && sc->done) return;
+    slot[0] = sc->rz_new;
+    slot[1] = sc->rr;
+}
+// r_1 out of the padded all-gather buffer; thread 0 also sums the ranks' partial scalars in rank order
 __global__ void amg_unpad_kernel(int n, const int32_t *__restrict__ src, const double *__restrict__ padded,
-                                 double *__restrict__ out, const DevScalars *sc, int check_done) {
+                                 double *__restrict__ out, DevScalars *sc, int check_done, int world,
+                                 const int32_t *__restrict__ scal_pos) {
     if (check_done && sc->done) return;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) out[t] = padded[src[t]];
+    if (t == 0) {
+        double rz = 0, rr = 0;
+        for (int q = 0; q < world; ++q) { rz += padded[scal_pos[q]]; rr += padded[scal_pos[q] + 1]; }
+        sc->rz_new = rz;
+        sc->rr = rr;
+    }
 }
 
 // ---- transfers ---------------------------------------------------------------------------------
@@ -392,16 +409,36 @@ __global__ void __launch_bounds__(128) amg_prolong_kernel(int n_fine, const int3
     for (int c = 0; c < D; ++c) x[(size_t)i * D + c] += u[c];
 }
 
-// Fine level: z_i = zJ_i + Ad(rel_i) xc[agg_i]  (zJ = D^-1 r already in z), r.z, PCG bookkeeping.
-template <int D, int NT>
-__global__ void __launch_bounds__(NT) amg_prolong0_kernel(int nf, const int32_t *__restrict__ agg, const double *__restrict__ rel,
-                                                          int pad, const double *__restrict__ xc, const double *__restrict__ r,
-                                                          double *__restrict__ z, double *__restrict__ p_out,
-                                                          double *__restrict__ partials, DevScalars *sc, int init, double tol,
-                                                          int max_iter, int dist) {
+// r.z of the multilevel preconditioner without forming z:  r.(zJ + P0 x_1) = r.zJ + (P0^T r).x_1 = r.zJ + r_1.x_1.
+// r.zJ is already in sc->rz_new (pcg_update / pcg_init; summed over the ranks in the partitioned solve), this
+// adds the coarse dot product and finishes the PCG scalars (beta, convergence test).
+template <int NT>
+__global__ void __launch_bounds__(NT) amg_coarse_dot_kernel(int n, const double *__restrict__ r1, const double *__restrict__ x1,
+                                                            double *__restrict__ partials, DevScalars *sc, int init, double tol,
+                                                            int max_iter) {
     __shared__ double sh[32];
     if (!init && sc->done) return;
-    double lrz = 0;
+    double local = 0;
+    for (int t = blockIdx.x * NT + threadIdx.x; t < n; t += gridDim.x * NT) local += r1[t] * x1[t];
+    const double bs = block_sum<NT>(local, sh);
+    if (threadIdx.x == 0) partials[blockIdx.x] = bs;
+    if (last_block(&sc->counters[6])) {
+        const double dot = sum_partials<NT>(partials, gridDim.x, sh);
+        if (threadIdx.x == 0) {
+            sc->rz_new += dot;
+            if (init) fin_init(sc, tol, max_iter);
+            else fin_update(sc);
+        }
+    }
+}
+
+// Fine level, fused with the search-direction update:  p_i = (zJ_i + P_i x_1[agg_i]) + beta p_i  (zJ = D^-1 r in z).
+template <int D, int NT>
+__global__ void __launch_bounds__(NT) amg_prolong0_kernel(int nf, const int32_t *__restrict__ agg, const double *__restrict__ rel,
+                                                          int pad, const double *__restrict__ xc, const double *__restrict__ z,
+                                                          double *__restrict__ p, const DevScalars *sc, int init) {
+    if (!init && sc->done) return;
+    const double beta = init ? 0.0 : sc->beta;
     for (int i = blockIdx.x * NT + threadIdx.x; i < nf; i += gridDim.x * NT) {
         const Rel S = load_rel(rel, pad, i);
         const int I = agg[i];
@@ -412,20 +449,7 @@ __global__ void __launch_bounds__(NT) amg_prolong0_kernel(int nf, const int32_t 
 #pragma unroll
         for (int c = 0; c < D; ++c) {
             const double zc = z[(size_t)i * D + c] + u[c];
-            z[(size_t)i * D + c] = zc;
-            if (p_out) p_out[(size_t)i * D + c] = zc;
-            lrz += r[(size_t)i * D + c] * zc;
-        }
-    }
-    const double bs = block_sum<NT>(lrz, sh);
-    if (threadIdx.x == 0) partials[blockIdx.x] = bs;
-    if (last_block(&sc->counters[6])) {
-        const double rz = sum_partials<NT>(partials, gridDim.x, sh);
-        if (threadIdx.x == 0) {
-            sc->rz_new = rz;
-            if (dist) {}                       // partitioned solve: the caller all-reduces r.z, then finishes
-            else if (init) fin_init(sc, tol, max_iter);
-            else fin_update(sc);
+            p[(size_t)i * D + c] = init ? zc : zc + beta * p[(size_t)i * D + c];
         }
     }
 }
@@ -650,6 +674,7 @@ void amg_destroy(s3o_problem *p) {
     dev_free(p->amg->d_dense);
     dev_free(p->amg->d_rpad);
     dev_free(p->amg->d_unpad_src);
+    dev_free(p->amg->d_scal_pos);
     delete p->amg;
     p->amg = nullptr;
 }
@@ -707,18 +732,22 @@ int amg_setup(s3o_problem *p) {
         rc = rc ? rc : dev_alloc(&L.rel, (size_t)NREL * L.pad_fine);
         rc = rc ? rc : dev_alloc(&L.A, (size_t)L.nblk * DD);
         rc = rc ? rc : dev_alloc(&L.Dinv, (size_t)L.n * DD);
-        rc = rc ? rc : dev_alloc(&L.r, (size_t)L.n * D + (l == 0 ? st->r_max : 0));
+        rc = rc ? rc : dev_alloc(&L.r, (size_t)L.n * D + (l == 0 ? st->r_max + 2 : 0));
         rc = rc ? rc : dev_alloc(&L.x, (size_t)L.n * D);
         rc = rc ? rc : dev_alloc(&L.x2, (size_t)L.n * D);
         rc = rc ? rc : dev_alloc(&L.t, (size_t)L.n * D);
     }
     if (!rc && st->dist) {
         const int world = (int)st->r_cnt.size();
-        std::vector<int32_t> src((size_t)st->host[0].n * D);
-        for (int q = 0; q < world; ++q)
-            for (size_t t = 0; t < st->r_cnt[q]; ++t) src[st->r_off[q] + t] = (int32_t)(q * st->r_max + t);
+        st->r_seg = st->r_max + 2;
+        std::vector<int32_t> src((size_t)st->host[0].n * D), spos(world);
+        for (int q = 0; q < world; ++q) {
+            for (size_t t = 0; t < st->r_cnt[q]; ++t) src[st->r_off[q] + t] = (int32_t)(q * st->r_seg + t);
+            spos[q] = (int32_t)(q * st->r_seg + st->r_cnt[q]);
+        }
         rc = up(p, &st->d_unpad_src, src);
-        rc = rc ? rc : dev_alloc(&st->d_rpad, (size_t)world * st->r_max);
+        rc = rc ? rc : up(p, &st->d_scal_pos, spos);
+        rc = rc ? rc : dev_alloc(&st->d_rpad, (size_t)world * st->r_seg);
     }
     const int nc = st->host.back().n;
     st->dense = nc <= kCoarsestMax;
@@ -803,8 +832,10 @@ int update_values_t(s3o_problem *p, double lambda) {
     return check_launch(p, launches);
 }
 
-// z += P0 V(P0^T r) on the fine vectors of the problem (z holds D^-1 r on entry); finishes the
-// PCG scalars (r.z, beta / convergence test).  init: first application of a solve (also sets p = z).
+// One application of the multilevel preconditioner inside the PCG, fused with what follows it:
+// r_1 = P0^T r, x_1 = V(r_1), r.z = r.zJ + r_1.x_1 (PCG scalars: beta, convergence test), and the new search
+// direction p = (zJ + P0 x_1) + beta p.  z holds zJ = D^-1 r on entry and is not completed -- nothing needs z
+// itself.  init: first application of a solve (p = z).
 template <int D>
 int apply_t(s3o_problem *p, int init) {
     AmgState *st = p->amg;
@@ -822,13 +853,17 @@ int apply_t(s3o_problem *p, int init) {
         amg_restrict_kernel<D><<<(L.n + 15) / 16, 128, 0, s>>>(L.n, L.mem_ptr, L.mem_idx, L.rel, L.pad_fine, p->d_r, L.r, sc, chk);
         ++launches;
         if (st->dist) {
-            // my segment starts at L.r + r_off[rank]; the padded tail of the send is ignored by the unpad map
-            if (comm_allgather(p->comm, L.r + st->r_off[p->comm.rank], st->d_rpad, st->r_max, s)) {
+            // my segment starts at L.r + r_off[rank], followed by my partial r.zJ and |r|^2; the padded tail of
+            // the send is ignored by the unpad map
+            double *mine = L.r + st->r_off[p->comm.rank];
+            amg_scalars_to_vec_kernel<<<1, 1, 0, s>>>(mine + st->r_cnt[p->comm.rank], sc, chk);
+            if (comm_allgather(p->comm, mine, st->d_rpad, st->r_seg, s)) {
                 set_error("%s", comm_last_error());
                 return S3O_ERR_NCCL;
             }
-            amg_unpad_kernel<<<(L.n * D + 255) / 256, 256, 0, s>>>(L.n * D, st->d_unpad_src, st->d_rpad, L.r, sc, chk);
-            ++launches;
+            amg_unpad_kernel<<<(L.n * D + 255) / 256, 256, 0, s>>>(L.n * D, st->d_unpad_src, st->d_rpad, L.r, p->d_sc, chk,
+                                                                   p->comm.world, st->d_scal_pos);
+            launches += 2;
         }
     }
     for (int l = 0; l < lt; ++l) {
@@ -871,9 +906,12 @@ int apply_t(s3o_problem *p, int init) {
         int grid = (rows + NT - 1) / NT;
         if (grid > 148 * 8) grid = 148 * 8;
         if (grid < 1) grid = 1;
-        amg_prolong0_kernel<D, NT><<<grid, NT, 0, s>>>(rows, L.agg, L.rel, L.pad_fine, L.x, p->d_r, p->d_z, init ? p->d_p : nullptr,
-                                                    p->d_partials, p->d_sc, init, p->pcg_tol, p->pcg_max_iter, st->dist ? 1 : 0);
-        ++launches;
+        int dgrid = (L.n * D + NT - 1) / NT;
+        if (dgrid > 148) dgrid = 148;
+        if (dgrid < 1) dgrid = 1;
+        amg_coarse_dot_kernel<NT><<<dgrid, NT, 0, s>>>(L.n * D, L.r, L.x, p->d_partials, p->d_sc, init, p->pcg_tol, p->pcg_max_iter);
+        amg_prolong0_kernel<D, NT><<<grid, NT, 0, s>>>(rows, L.agg, L.rel, L.pad_fine, L.x, p->d_z, p->d_p, sc, init);
+        launches += 2;
     }
     return check_launch(p, launches);
 }

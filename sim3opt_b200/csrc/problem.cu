@@ -201,8 +201,9 @@ int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel
                     p->pcg_max_iter, defer, p->stream);
     rc = check_launch(p, 2);
     if (rc) return rc;
-    if (amg && (rc = amg_apply(p, 1))) return rc;
-    if (dist) {
+    if (amg) {      // restriction, V-cycle, r.z (riding on the r_1 all-gather when partitioned), p = z
+        if ((rc = amg_apply(p, 1))) return rc;
+    } else if (dist) {
         if ((rc = allreduce_sum(p, &p->d_sc->rz_new, 2))) return rc;
         launch_pcg_fin_init(p->d_sc, p->pcg_tol, p->pcg_max_iter, p->stream);
         p->stats.kernel_launches += 1;
@@ -224,7 +225,10 @@ int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel
             }
             launch_pcg_update(d, s, nf, p->d_q1, p->d_T, p->d_Minv, p->d_p, p->d_x, p->d_r, p->d_z, p->d_partials,
                               p->d_sc, defer, p->stream);
-            if (amg && (rc = amg_apply(p, 0))) return rc;
+            if (amg) {      // ... r.z, beta and p = z + beta p included
+                if ((rc = amg_apply(p, 0))) return rc;
+                continue;
+            }
             if (dist) {
                 if ((rc = allreduce_sum(p, &p->d_sc->rz_new, 2))) return rc;
                 launch_pcg_fin_update(p->d_sc, p->stream);
@@ -232,7 +236,7 @@ int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel
             launch_pcg_pupdate(d, nf, p->d_z, p->d_p, p->d_sc, p->stream);
         }
         launched += batch;
-        rc = check_launch(p, (dist ? 5 : 3) * batch);
+        rc = check_launch(p, (amg ? (dist ? 3 : 2) : (dist ? 5 : 3)) * batch);
         if (rc) return rc;
         rc = sync_scalars(p);
         if (rc) return rc;
