@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(128) amg_row_kernel(int n, const int32_t *__re
 #pragma unroll
     for (int c = 0; c < D; ++c) {
         const double rc = __shfl_sync(0xffffffffu, res, c, 8);
-        if (act) z += Dinv[(size_t)i * DD + l * D + c] * rc;
+        if (act) z += Dinv[(size_t)i * sym_size<D>() + sym_off<D>(l, c)] * rc;
     }
     if (act) out[(size_t)i * D + l] = (MODE == 2 ? x[(size_t)i * D + l] : 0.0) + omega * z;
 }
@@ -511,7 +511,7 @@ __device__ __forceinline__ void tail_rows(const TailLevel &L, const double *x, d
 #pragma unroll
         for (int c = 0; c < D; ++c) {
             const double rc = __shfl_sync(0xffffffffu, res, c, 8);
-            if (act) z += L.Dinv[(size_t)i * DD + l * D + c] * rc;
+            if (act) z += L.Dinv[(size_t)i * sym_size<D>() + sym_off<D>(l, c)] * rc;
         }
         if (act) out[(size_t)i * D + l] = (MODE == 2 ? __ldcg(x + (size_t)i * D + l) : 0.0) + omega * z;
     }

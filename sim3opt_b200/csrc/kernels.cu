@@ -684,7 +684,7 @@ void launch_scale(int n, const double *x, const double *b, double lambda, double
 }
 
 // ======================================================================================
-// block-Jacobi preconditioner: Minv_i = (H_ii + lambda I)^-1 by Cholesky
+// block-Jacobi preconditioner: Minv_i = (H_ii + lambda I)^-1 by Cholesky, stored as its packed upper triangle
 // ======================================================================================
 template <int D>
 __global__ void precond_kernel(const double *__restrict__ H, const int32_t *__restrict__ rowptr, int nf, double lambda,
@@ -729,16 +729,17 @@ __global__ void precond_kernel(const double *__restrict__ H, const int32_t *__re
             Li[r * D + c] = v / L[r * D + r];
         }
     }
-    // Minv = Li^T Li
-    double *out = Minv + (size_t)i * DD;
+    // Minv = Li^T Li, packed upper triangle (sym_off)
+    double *out = Minv + (size_t)i * sym_size<D>();
+    int f = 0;
 #pragma unroll
     for (int r = 0; r < D; ++r)
 #pragma unroll
-        for (int c = 0; c < D; ++c) {
+        for (int c = r; c < D; ++c) {
             double v = 0;
 #pragma unroll
-            for (int k = (r > c ? r : c); k < D; ++k) v += Li[k * D + r] * Li[k * D + c];
-            out[r * D + c] = ok ? v : (r == c ? 1.0 : 0.0);
+            for (int k = c; k < D; ++k) v += Li[k * D + r] * Li[k * D + c];
+            out[f++] = ok ? v : (r == c ? 1.0 : 0.0);
         }
     if (!ok) sc->precond_fail = 1;
 }
@@ -900,7 +901,7 @@ __global__ void __launch_bounds__(NT) pcg_init_kernel(int nf, const double *__re
 #pragma unroll
         for (int c = 0; c < D; ++c) {
             const double rc = __shfl_sync(0xffffffffu, rl, c, GL);
-            if (act) zl += Minv[(size_t)i * DD + l * D + c] * rc;
+            if (act) zl += Minv[(size_t)i * sym_size<D>() + sym_off<D>(l, c)] * rc;
         }
         if (act) {
             x[(size_t)i * D + l] = 0;
@@ -951,7 +952,7 @@ __global__ void __launch_bounds__(NT) pcg_update_kernel(StructDev s, int nf, con
 #pragma unroll
         for (int c = 0; c < D; ++c) {
             const double rc = __shfl_sync(0xffffffffu, rl, c, GL);
-            if (act) zl += Minv[(size_t)i * DD + l * D + c] * rc;
+            if (act) zl += Minv[(size_t)i * sym_size<D>() + sym_off<D>(l, c)] * rc;
         }
         if (act) {
             z[(size_t)i * D + l] = zl;

@@ -84,6 +84,15 @@ __device__ __forceinline__ void fin_update(DevScalars *sc) {
     else if (!(rz > 0)) sc->done = 3;
 }
 
+// Symmetric d x d blocks that are only ever multiplied with vectors (block-Jacobi inverses) are stored as
+// their packed upper triangle, row by row: D(D+1)/2 doubles per block instead of D*D.
+template <int D> __host__ __device__ constexpr int sym_size() { return D * (D + 1) / 2; }
+template <int D>
+__device__ __forceinline__ int sym_off(int r, int c) {
+    const int lo = r < c ? r : c, hi = r < c ? c : r;
+    return lo * D - (lo * (lo - 1)) / 2 + (hi - lo);
+}
+
 template <int D> struct GroupLanes { static constexpr int value = D > 4 ? 8 : (D > 2 ? 4 : (D > 1 ? 2 : 1)); };
 
 }  // namespace s3o

@@ -9,7 +9,7 @@ laps = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 per = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 tol = float(sys.argv[4]) if len(sys.argv) > 4 else 1e-8
-t = time.time(); g = synth.sphere(laps, per); print("gen %.2fs N=%d E=%d" % (time.time() - t, len(g["est"]), len(g["v0"])))
+t = time.time(); g = (synth.manhattan3d(laps * per) if os.environ.get("GRAPH") == "manhattan" else synth.sphere(laps, per)); print("gen %.2fs N=%d E=%d" % (time.time() - t, len(g["est"]), len(g["v0"])))
 p = s3.Problem(s3.KIND_SIM3)
 p.set_math_mode(s3.MATH_CORRECTED)
 t = time.time(); p.set_vertices(g["est"], g["fixed"]); p.set_edges(g["v0"], g["v1"], g["meas"], g["info"]); print("upload %.3fs" % (time.time() - t))
