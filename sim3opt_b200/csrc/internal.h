@@ -37,6 +37,7 @@ struct HostStructure {
     std::vector<int32_t> blk_ebeg, blk_eend;    // [nb] sorted-edge range feeding each off-diag block
                                                 //      (diag blocks: empty range)
     std::vector<int32_t> blk_src;               // [nb] off-diag block fed by exactly one edge: (sorted edge << 1) | transposed; else -1
+    std::vector<int32_t> multi_blk;             // off-diagonal blocks fed by more than one edge (duplicate edges)
     std::vector<int32_t> colT_ptr, colT_blk;    // [nf+1], [nb-nf]: off-diag blocks by column (rows ascending)
     std::vector<int32_t> inc_ptr, inc_ent;      // [nf+1], incidences: (sorted edge << 1) | side
     std::vector<int32_t> ccs_colptr, ccs_rowidx; // g2o-order upper block-CCS

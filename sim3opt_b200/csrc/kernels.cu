@@ -536,14 +536,15 @@ template <int D>
 __global__ void assemble_kernel(GraphDev g, StructDev s, const double *__restrict__ scratch, double *__restrict__ H,
                                 double *__restrict__ b) {
     constexpr int DD = D * D, NS = packed_size(D), STRIDE = scr_stride(D), EL = DD + D;
+    // work items: the nf diagonal blocks (+ b), then the few off-diagonal blocks fed by more than one edge;
+    // single-edge off-diagonal blocks were written in place by linearize_kernel
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long k64 = tid / EL;
-    if (k64 >= g.nb) return;
-    const int k = (int)k64, el = (int)(tid - k64 * EL);
-    const int src = __ldg(s.blk_src + k);
-    if (src >= 0) return;   // off-diagonal block fed by one edge: linearize_kernel wrote it in place
-    const int row = s.blk_row[k], col = s.colidx[k];
-    if (row == col) {
+    const long long w64 = tid / EL;
+    if (w64 >= (long long)g.nf + s.n_multi) return;
+    const int w = (int)w64, el = (int)(tid - w64 * EL);
+    const int k = w < g.nf ? s.rowptr[w] : s.multi_blk[w - g.nf];
+    const int row = w < g.nf ? w : s.blk_row[k];
+    if (w < g.nf) {
         int off;
         if (el < DD) {
             const int r = el / D, c = el - r * D;
@@ -586,7 +587,7 @@ void launch_assemble(const GraphDev &g, const StructDev &s, const double *scratc
                      cudaStream_t st) {
     if (g.nb == 0) return;
     const int el = g.d * g.d + g.d;
-    const long long total = (long long)g.nb * el;
+    const long long total = ((long long)g.nf + s.n_multi) * el;
     const int grid = (int)((total + 255) / 256);
     switch (g.d) {
     case 7: assemble_kernel<7><<<grid, 256, 0, st>>>(g, s, scratch, H, b); break;

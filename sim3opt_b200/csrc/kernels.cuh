@@ -44,6 +44,8 @@ struct StructDev {
     const int32_t *rowptr, *colidx, *blk_row;
     const int32_t *blk_ebeg, *blk_eend;
     const int32_t *blk_src;   // [nb] single-edge off-diagonal blocks: (sorted edge << 1) | transposed, else -1
+    const int32_t *multi_blk; // [n_multi] off-diagonal blocks fed by more than one edge
+    int n_multi;
     const int32_t *colT_ptr, *colT_blk;
     const int32_t *inc_ptr, *inc_ent;
     const int32_t *e_blk;

@@ -59,6 +59,7 @@ StructDev struct_view(const s3o_problem *p) {
     StructDev s{};
     s.rowptr = p->d_rowptr; s.colidx = p->d_colidx; s.blk_row = p->d_blk_row;
     s.blk_ebeg = p->d_blk_ebeg; s.blk_eend = p->d_blk_eend; s.blk_src = p->d_blk_src;
+    s.multi_blk = p->d_multi_blk; s.n_multi = (int)p->S.multi_blk.size();
     s.colT_ptr = p->d_colT_ptr; s.colT_blk = p->d_colT_blk;
     s.inc_ptr = p->d_inc_ptr; s.inc_ent = p->d_inc_ent; s.e_blk = p->d_e_blk;
     s.tile_row = p->d_tile_row; s.ntiles = (int)p->S.tile_row.size() - 1;
@@ -70,7 +71,7 @@ void free_structure(s3o_problem *p) {
     dev_free(p->d_hidx); dev_free(p->d_sv0); dev_free(p->d_sv1); dev_free(p->d_meas); dev_free(p->d_info);
     dev_free(p->d_rowptr); dev_free(p->d_colidx); dev_free(p->d_blk_row); dev_free(p->d_blk_ebeg);
     dev_free(p->d_blk_eend); dev_free(p->d_colT_ptr); dev_free(p->d_colT_blk); dev_free(p->d_inc_ptr);
-    dev_free(p->d_inc_ent); dev_free(p->d_e_blk); dev_free(p->d_tile_row); dev_free(p->d_blk_src);
+    dev_free(p->d_inc_ent); dev_free(p->d_e_blk); dev_free(p->d_tile_row); dev_free(p->d_blk_src); dev_free(p->d_multi_blk);
     dev_free(p->d_ghidx); dev_free(p->d_send_idx); dev_free(p->d_primary); dev_free(p->d_sendbuf); dev_free(p->d_xg);
     dev_free(p->d_H); dev_free(p->d_b); dev_free(p->d_x); dev_free(p->d_r); dev_free(p->d_z); dev_free(p->d_p);
     dev_free(p->d_q1); dev_free(p->d_T); dev_free(p->d_Minv); dev_free(p->d_scratch);
@@ -635,6 +636,7 @@ int s3o_build_structure(s3o_problem *p, int *n_free, int *n_blocks) {
         rc = rc ? rc : upload(p, &p->d_blk_ebeg, S.blk_ebeg);
         rc = rc ? rc : upload(p, &p->d_blk_eend, S.blk_eend);
         rc = rc ? rc : upload(p, &p->d_blk_src, S.blk_src);
+        rc = rc ? rc : upload(p, &p->d_multi_blk, S.multi_blk);
         rc = rc ? rc : upload(p, &p->d_inc_ptr, S.inc_ptr);
         rc = rc ? rc : upload(p, &p->d_inc_ent, S.inc_ent);
         rc = rc ? rc : upload(p, &p->d_e_blk, S.e_blk);

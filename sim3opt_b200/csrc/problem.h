@@ -54,7 +54,7 @@ struct s3o_problem {
     int32_t *d_rowptr = nullptr, *d_colidx = nullptr, *d_blk_row = nullptr, *d_blk_ebeg = nullptr, *d_blk_eend = nullptr;
     int32_t *d_colT_ptr = nullptr, *d_colT_blk = nullptr, *d_inc_ptr = nullptr, *d_inc_ent = nullptr, *d_e_blk = nullptr;
     int32_t *d_tile_row = nullptr;
-    int32_t *d_blk_src = nullptr;
+    int32_t *d_blk_src = nullptr, *d_multi_blk = nullptr;
     // partitioned solve (one process per GPU, NCCL): s3o_set_comm
     Comm comm;
     bool dist = false;

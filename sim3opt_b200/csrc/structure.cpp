@@ -104,6 +104,8 @@ void build_structure_from_hidx(int nv, const int32_t *hidx_in, int nfree, int ne
             const int t = S.blk_ebeg[k];
             const bool transposed = S.hidx[S.sv0[t]] > S.hidx[S.sv1[t]];   // vertex(0) on the max side: A^T O' B is the transpose
             S.blk_src[k] = (t << 1) | (transposed ? 1 : 0);
+        } else if (S.blk_eend[k] - S.blk_ebeg[k] > 1) {
+            S.multi_blk.push_back(k);
         }
 
     // incidences per free vertex, ordered by sorted edge position (fixed summation order)

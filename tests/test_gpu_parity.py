@@ -283,6 +283,30 @@ def test_resume_and_snapshot(sphere_small):
     assert chi_a2 == chi_a                              # bitwise reproducible solve
 
 
+def test_duplicate_edges_share_a_block(sphere_small):
+    """Several edges between one vertex pair (both orientations) sum into one Hessian block in edge order."""
+    orc = _orc()
+    g = dict(sphere_small)
+    rng = np.random.default_rng(8)
+    pick = rng.choice(len(g["v0"]), 25, replace=False)
+    v0 = np.concatenate([g["v0"], g["v0"][pick[:15]], g["v1"][pick[15:]]]).astype(np.int32)       # last 10 reversed
+    v1 = np.concatenate([g["v1"], g["v1"][pick[:15]], g["v0"][pick[15:]]]).astype(np.int32)
+    meas_rev = np.array([orc.sim3_inv(m) for m in g["meas"][pick[15:]]])
+    g["v0"], g["v1"] = v0, v1
+    g["meas"] = np.concatenate([g["meas"], g["meas"][pick[:15]], meas_rev])
+    g["info"] = np.concatenate([g["info"], g["info"][pick]])
+    gpu, cpu = make_gpu(g, jac=1), make_oracle(g, jac=orc.JAC_ANALYTIC)
+    cp_g, ri_g = gpu.build_structure()
+    cp_c, ri_c = cpu.build_structure()
+    assert np.array_equal(cp_g, cp_c) and np.array_equal(ri_g, ri_c)
+    Hg, bg = gpu.linearize()
+    Hc, bc = cpu.linearize()
+    assert np.abs(Hg - Hc).max() <= 1e-10 * np.abs(Hc).max()
+    assert np.abs(bg - bc).max() <= 1e-10 * np.abs(bc).max()
+    Hg2, _ = gpu.linearize()
+    assert np.array_equal(Hg, Hg2)
+
+
 def test_hub_vertex_rows_longer_than_a_tile():
     """A star graph: one block row holds 400 off-diagonal blocks (> one SpMV tile)."""
     orc = _orc()
