@@ -330,7 +330,10 @@ __device__ __forceinline__ void warp_store_piece_to(double *stage, const double 
 
 // The cross term of an edge that is the only one feeding its off-diagonal block goes straight into
 // the Hessian (Hdirect != null): assemble_kernel then has nothing to do for that block.
-template <int KIND, int JAC, int NT>
+// DIAG: the information matrices are diagonal (or absent = identity): Omega' is held as D weights, A^T O' and
+// B^T O' are column scalings -- same numbers as the dense path (its extra terms are exact zeros), 2 of the 5
+// 7x7x7 products and a 49-double array less.
+template <int KIND, int JAC, int NT, bool DIAG>
 __global__ void __launch_bounds__(NT) linearize_kernel(GraphDev g, double h, double *__restrict__ scratch,
                                                        const int32_t *__restrict__ e_blk,
                                                        const int32_t *__restrict__ blk_src, double *__restrict__ Hdirect) {
@@ -348,7 +351,7 @@ __global__ void __launch_bounds__(NT) linearize_kernel(GraphDev g, double h, dou
     const bool valid = t < g.ne;
     const int nvalid = min(32, g.ne - e0);
 
-    double A[DD], B[DD], O[DD], e[D], P[DD];
+    double A[DD], B[DD], O[DIAG ? D : DD], e[D], P[DD];
     double out[SMAX];
     bool fi = false, fj = false;
     if (valid) {
@@ -390,7 +393,21 @@ __global__ void __launch_bounds__(NT) linearize_kernel(GraphDev g, double h, dou
                 }
             }
         }
-        // O' = rho1 * Omega (full symmetric, row-major)
+        // O' = rho1 * Omega (full symmetric, row-major; or its diagonal)
+        if constexpr (DIAG) {
+#pragma unroll
+            for (int r = 0; r < D; ++r)
+                O[r] = g.info ? __ldg(g.info + (size_t)(r * D - (r * (r - 1)) / 2) * g.ne_pad + t) : 1.0;
+            if (g.robust_kind != S3O_ROBUST_NONE) {
+                double c2 = 0;
+#pragma unroll
+                for (int r = 0; r < D; ++r) c2 += e[r] * (O[r] * e[r]);
+                double r0, r1;
+                robustify(g.robust_kind, g.robust_param, c2, r0, r1);
+#pragma unroll
+                for (int k = 0; k < D; ++k) O[k] *= r1;
+            }
+        } else {
         if (g.info) {
             int f = 0;
 #pragma unroll
@@ -421,6 +438,7 @@ __global__ void __launch_bounds__(NT) linearize_kernel(GraphDev g, double h, dou
 #pragma unroll
             for (int k = 0; k < DD; ++k) O[k] *= r1;
         }
+        }
     }
     double *rec0 = scratch + (size_t)e0 * STRIDE;
     // ---- vertex(0) side: P = A^T O'
@@ -430,8 +448,11 @@ __global__ void __launch_bounds__(NT) linearize_kernel(GraphDev g, double h, dou
 #pragma unroll
             for (int c = 0; c < D; ++c) {
                 double acc = 0;
+                if constexpr (DIAG) acc = A[c * D + r] * O[c];
+                else {
 #pragma unroll
-                for (int k = 0; k < D; ++k) acc += A[k * D + r] * O[k * D + c];
+                    for (int k = 0; k < D; ++k) acc += A[k * D + r] * O[k * D + c];
+                }
                 P[r * D + c] = acc;
             }
         int f = 0;
@@ -486,8 +507,11 @@ __global__ void __launch_bounds__(NT) linearize_kernel(GraphDev g, double h, dou
 #pragma unroll
             for (int c = 0; c < D; ++c) {
                 double acc = 0;
+                if constexpr (DIAG) acc = B[c * D + r] * O[c];
+                else {
 #pragma unroll
-                for (int k = 0; k < D; ++k) acc += B[k * D + r] * O[k * D + c];
+                    for (int k = 0; k < D; ++k) acc += B[k * D + r] * O[k * D + c];
+                }
                 P[r * D + c] = acc;
             }
         int f = 0;
@@ -516,11 +540,15 @@ void launch_linearize(const GraphDev &g, int jac_mode, double h, double *scratch
     if (g.ne == 0) return;
     constexpr int NT = 64;
     const int grid = (g.ne + NT - 1) / NT;
+    const bool diag = g.info == nullptr || g.info_diag;
 #define S3O_LIN(KIND)                                                                                  \
-    if (jac_mode == S3O_JAC_ANALYTIC)                                                                  \
-        linearize_kernel<KIND, S3O_JAC_ANALYTIC, NT><<<grid, NT, 0, st>>>(g, h, scratch, e_blk, blk_src, Hdirect);              \
-    else                                                                                               \
-        linearize_kernel<KIND, S3O_JAC_NUMERIC, NT><<<grid, NT, 0, st>>>(g, h, scratch, e_blk, blk_src, Hdirect);
+    if (jac_mode == S3O_JAC_ANALYTIC) {                                                                \
+        if (diag) linearize_kernel<KIND, S3O_JAC_ANALYTIC, NT, true><<<grid, NT, 0, st>>>(g, h, scratch, e_blk, blk_src, Hdirect);   \
+        else linearize_kernel<KIND, S3O_JAC_ANALYTIC, NT, false><<<grid, NT, 0, st>>>(g, h, scratch, e_blk, blk_src, Hdirect);      \
+    } else {                                                                                           \
+        if (diag) linearize_kernel<KIND, S3O_JAC_NUMERIC, NT, true><<<grid, NT, 0, st>>>(g, h, scratch, e_blk, blk_src, Hdirect);    \
+        else linearize_kernel<KIND, S3O_JAC_NUMERIC, NT, false><<<grid, NT, 0, st>>>(g, h, scratch, e_blk, blk_src, Hdirect);       \
+    }
     switch (g.kind) {
     case S3O_KIND_SIM3: S3O_LIN(S3O_KIND_SIM3) break;
     case S3O_KIND_SCALE_TRANS: S3O_LIN(S3O_KIND_SCALE_TRANS) break;

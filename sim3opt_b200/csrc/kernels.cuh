@@ -33,6 +33,7 @@ struct GraphDev {
     const int32_t *sv0, *sv1; // [ne]
     const double *meas;      // [est_dim][ne_pad]
     const double *info;      // [ninfo][ne_pad] or null (identity)
+    bool info_diag;          // every information matrix is diagonal (checked on the host in s3o_set_edges)
     int robust_kind;
     double robust_param;
     bool math_corrected;     // s3o_set_math_mode

@@ -43,7 +43,7 @@ GraphDev graph_view(const s3o_problem *p, int which) {
     g.kind = p->kind; g.d = p->d; g.est_dim = p->est_dim; g.ninfo = p->ninfo;
     g.nv = p->nv; g.nv_pad = p->nv_pad; g.ne = p->S.ne_act; g.ne_pad = p->ne_pad; g.nf = p->S.nf; g.nb = p->S.nb;
     g.est = p->d_est[which]; g.aux = p->d_aux; g.hidx = p->d_hidx; g.sv0 = p->d_sv0; g.sv1 = p->d_sv1;
-    g.meas = p->d_meas; g.info = p->has_info ? p->d_info : nullptr;
+    g.meas = p->d_meas; g.info = p->has_info ? p->d_info : nullptr; g.info_diag = p->info_diag;
     g.robust_kind = p->robust_kind; g.robust_param = p->robust_param;
     g.math_corrected = p->math_mode == S3O_MATH_CORRECTED;
     g.primary = p->dist ? p->d_primary : nullptr;
@@ -512,6 +512,15 @@ int s3o_set_edges(s3o_problem *p, int n, const int32_t *v0, const int32_t *v1, c
     dev_free(p->d_meas_aos); dev_free(p->d_info_aos);
     p->user_ne = n;
     p->has_info = info != nullptr;
+    p->info_diag = false;
+    if (info) {     // diagonal information matrices (the usual case) take the cheaper linearisation path
+        const int dd = p->d * p->d;
+        bool diag = true;
+        for (size_t k = 0; k < (size_t)n && diag; ++k)
+            for (int e = 0; e < dd && diag; ++e)
+                if (e / p->d != e % p->d && info[k * dd + e] != 0.0) diag = false;
+        p->info_diag = diag;
+    }
     std::vector<double> meas_loc, info_loc;
     if (p->dist) {
         // keep only the edges that touch a vertex this rank owns (cut edges live on both sides)

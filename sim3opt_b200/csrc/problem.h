@@ -39,7 +39,7 @@ struct s3o_problem {
     int nv = 0, ne = 0;
     std::vector<uint8_t> fixed;
     std::vector<int32_t> v0, v1;
-    bool has_info = false, has_aux = false;
+    bool has_info = false, has_aux = false, info_diag = false;
     double *d_meas_aos = nullptr, *d_info_aos = nullptr;  // caller-ordered staging until the structure is built
     // device graph
     int nv_pad = 0, ne_pad = 0;

@@ -283,6 +283,25 @@ def test_resume_and_snapshot(sphere_small):
     assert chi_a2 == chi_a                              # bitwise reproducible solve
 
 
+@pytest.mark.parametrize("robust", [None, (1, 2.5)])
+def test_dense_information_matrices(sphere_small, robust):
+    """Full (non-diagonal) SPD information matrices take the dense linearisation path; diagonal ones and NULL
+    (identity) the cheaper one -- both against the oracle, with and without a robust kernel."""
+    orc = _orc()
+    g = dict(sphere_small)
+    rng = np.random.default_rng(12)
+    M = rng.normal(0, 1, (len(g["v0"]), 7, 7))
+    g["info"] = np.einsum("nij,nkj->nik", M, M) + 7 * np.eye(7)
+    for graph in (g, sphere_small, {k: v for k, v in sphere_small.items() if k != "info"}):
+        gpu, cpu = make_gpu(graph, jac=1, robust=robust), make_oracle(graph, jac=orc.JAC_ANALYTIC, robust=robust)
+        c_g, c_c = gpu.chi2(), cpu.chi2()
+        assert abs(c_g - c_c) <= 1e-11 * c_c
+        Hg, bg = gpu.linearize()
+        Hc, bc = cpu.linearize()
+        assert np.abs(Hg - Hc).max() <= 1e-10 * np.abs(Hc).max()
+        assert np.abs(bg - bc).max() <= 1e-10 * np.abs(bc).max()
+
+
 def test_duplicate_edges_share_a_block(sphere_small):
     """Several edges between one vertex pair (both orientations) sum into one Hessian block in edge order."""
     orc = _orc()
