@@ -386,7 +386,12 @@ def run_ours(args):
                                     + f" PCG rel_tol={args.pcg_tol} max_iter={args.pcg_max_iter}",
                    "math_mode": "corrected", "l2_policy": "inputs larger than L2 (Hessian blocks %.2f GB)" % (392 * nb / 1e9),
                    "step": "one LM iteration; solves restart from a device snapshot on the 1e-6 gain rule",
-                   "partition": "none" if world == 1 else f"vertex range over {world} ranks, NCCL halo + all-reduce; coarse levels of the multilevel PCG replicated"},
+                   "partition": "none" if world == 1 else (
+                       f"vertex range over {world} ranks; halo: "
+                       + ("NVLink peer-to-peer loads inside the SpMV (CUDA IPC)" if st["p2p_halo"] else "NCCL send/recv")
+                       + "; NCCL all-reduce / all-gather for the scalars and the level-1 residual; coarse levels of the "
+                         "multilevel PCG replicated"),
+                   "multilevel_levels": int(st["multilevel_levels"])},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "LM iterations/s", "h2d_bytes_per_step": nv * 64, "d2h_bytes_per_step": nv * 64 + 160,
                 "steps": e2e_steps},

@@ -226,6 +226,9 @@ typedef struct s3o_stats {
     /* CUDA-event time of the SpMV kernel alone, sampled on 1 of every 16 PCG iterations */
     double ms_spmv_sampled;
     int64_t n_spmv_sampled;
+    int32_t multilevel_levels; /* coarse levels of the multilevel preconditioner in use (0: block-Jacobi) */
+    int32_t p2p_halo;          /* partitioned solve: 1 if the SpMV reads ghost columns from the peers' memory (CUDA IPC
+                                  over NVLink), 0 if they are exchanged by NCCL send/recv */
 } s3o_stats;
 int s3o_get_stats(s3o_problem *p, s3o_stats *out);
 int s3o_reset_stats(s3o_problem *p);

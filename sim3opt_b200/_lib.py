@@ -24,6 +24,7 @@ class Stats(C.Structure):
         ("n_vertices", C.c_int32), ("n_free", C.c_int32), ("n_edges", C.c_int32),
         ("n_blocks", C.c_int32), ("dim", C.c_int32),
         ("ms_spmv_sampled", C.c_double), ("n_spmv_sampled", C.c_int64),
+        ("multilevel_levels", C.c_int32), ("p2p_halo", C.c_int32),
     ]
 
 

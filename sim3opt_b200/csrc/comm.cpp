@@ -120,6 +120,12 @@ int comm_allgatherv(Comm &c, double *buf, const size_t *off, const size_t *count
     return r == ncclSuccess ? 0 : fail("ncclGroupEnd", r);
 }
 
+// all-gather of opaque bytes (IPC handles of the peer-to-peer halo), device buffers
+int comm_allgather_bytes(Comm &c, const void *send, void *recv, size_t bytes_per_rank, cudaStream_t st) {
+    ncclResult_t r = g.AllGather(send, recv, bytes_per_rank, ncclChar, (ncclComm_t)c.nccl, st);
+    return r == ncclSuccess ? 0 : fail("ncclAllGather(bytes)", r);
+}
+
 int comm_halo(Comm &c, const double *sendbuf, const int *send_off, const int *send_count, double *recvbuf,
               const int *recv_off, const int *recv_count, int unit, cudaStream_t st) {
     ncclResult_t r = g.GroupStart();

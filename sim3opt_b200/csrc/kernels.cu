@@ -1047,6 +1047,31 @@ void launch_pcg_pupdate(int d, int nf, const double *z, double *p, const DevScal
 
 int launches_per_pcg_iter() { return 3; }
 
+// ---- peer-to-peer halo flags (partitioned solve) -------------------------------------------------
+// Every rank owns one epoch counter in device memory that its neighbours map through CUDA IPC.  Before a
+// product the rank publishes the epoch (its p is complete: the kernels that wrote it precede this one on the
+// stream) and waits until every neighbour whose entries it reads has published the same epoch.  Overwriting
+// p for the next product is safe without a second flag: it happens after the all-reduce of p.q and the
+// all-gather of the same iteration, which every neighbour enters only after its product has finished.
+__global__ void halo_signal_kernel(long long *own_flag, long long epoch) {
+    *reinterpret_cast<volatile long long *>(own_flag) = epoch;
+    __threadfence_system();
+}
+__global__ void halo_wait_kernel(long long *const *peer_flags, int n_peers, long long epoch, DevScalars *sc) {
+    const int t = threadIdx.x;
+    if (t >= n_peers) return;
+    const volatile long long *f = peer_flags[t];
+    long long spins = 0;
+    while (*f < epoch) {
+        if (++spins > (1ll << 31)) { sc->done = 3; break; }     // a peer died: report a breakdown instead of hanging
+    }
+    __threadfence_system();
+}
+void launch_halo_signal(long long *own_flag, long long epoch, cudaStream_t st) { halo_signal_kernel<<<1, 1, 0, st>>>(own_flag, epoch); }
+void launch_halo_wait(long long *const *peer_flags, int n_peers, long long epoch, DevScalars *sc, cudaStream_t st) {
+    if (n_peers > 0) halo_wait_kernel<<<1, 32, 0, st>>>(peer_flags, n_peers, epoch, sc);
+}
+
 // small vector helpers of s3o_smallest_eigenvector
 __global__ void scale_vec_kernel(int n, const double *__restrict__ in, double s, double *__restrict__ out) {
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) out[t] = in[t] * s;

@@ -53,6 +53,8 @@ struct StructDev {
     const int32_t *tile_row;  // [ntiles+1]
     int ntiles;
     int n_own;                // rows owned by this rank (= nf on one GPU); columns >= n_own are ghosts
+    double *const *ghost_src; // partitioned solve with peer-to-peer halos: where ghost column g lives in its owner's p
+                              // (CUDA IPC mapping of the peer's vector); null: ghosts are local copies filled by NCCL
 };
 
 constexpr int kMaxPartials = 4096;
@@ -99,6 +101,9 @@ void launch_pcg_pupdate(int d, int nf, const double *z, double *p, const DevScal
 void launch_scale(int n, const double *x, const double *b, double lambda, double *partials, DevScalars *sc,
                   cudaStream_t st);
 int launches_per_pcg_iter();
+// peer-to-peer halo: publish "my p is complete for this product" / wait until every neighbour has
+void launch_halo_signal(long long *own_flag, long long epoch, cudaStream_t st);
+void launch_halo_wait(long long *const *peer_flags, int n_peers, long long epoch, DevScalars *sc, cudaStream_t st);
 void launch_scale_vec(int n, const double *in, double s, double *out, cudaStream_t st);
 void launch_fill_const(int n, double v, double *out, cudaStream_t st);
 void launch_fill_alternating(int n, double *out, cudaStream_t st);

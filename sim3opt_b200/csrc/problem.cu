@@ -55,6 +55,15 @@ GraphDev graph_view(const s3o_problem *p, int which) {
 
 namespace s3o {
 
+// undo setup_p2p: unmap the peers' memory before the vectors they alias on the other side go away
+void close_p2p(s3o_problem *p) {
+    for (void *m : p->ipc_mapped) cudaIpcCloseMemHandle(m);
+    p->ipc_mapped.clear();
+    dev_free(p->d_flag); dev_free(p->d_ghost_src); dev_free(p->d_peer_flags);
+    p->p2p = false;
+    p->n_peers = 0;
+}
+
 StructDev struct_view(const s3o_problem *p) {
     StructDev s{};
     s.rowptr = p->d_rowptr; s.colidx = p->d_colidx; s.blk_row = p->d_blk_row;
@@ -64,6 +73,7 @@ StructDev struct_view(const s3o_problem *p) {
     s.inc_ptr = p->d_inc_ptr; s.inc_ent = p->d_inc_ent; s.e_blk = p->d_e_blk;
     s.tile_row = p->d_tile_row; s.ntiles = (int)p->S.tile_row.size() - 1;
     s.n_own = p->dist ? p->plan.n_own : p->S.nf;
+    s.ghost_src = nullptr;      // set per product by run_spmv when the peer-to-peer halo is active
     return s;
 }
 
@@ -75,6 +85,7 @@ void free_structure(s3o_problem *p) {
     dev_free(p->d_ghidx); dev_free(p->d_send_idx); dev_free(p->d_primary); dev_free(p->d_sendbuf); dev_free(p->d_xg);
     dev_free(p->d_H); dev_free(p->d_b); dev_free(p->d_x); dev_free(p->d_r); dev_free(p->d_z); dev_free(p->d_p);
     dev_free(p->d_q1); dev_free(p->d_T); dev_free(p->d_Minv); dev_free(p->d_scratch);
+    close_p2p(p);
     amg_destroy(p);
     p->auto_multilevel = false;
     p->built = false;
@@ -123,13 +134,20 @@ int ensure_built(s3o_problem *p) {
     return s3o_build_structure(p, nullptr, nullptr);
 }
 
+bool uses_spmv4(const s3o_problem *p) {
+    const int ntiles = (int)p->S.tile_row.size() - 1;
+    return p->spmv_version == 4 && p->d == 7 && p->S.max_row_blocks <= p->S.tile_blocks && spmv4_fits(ntiles, p->spmv_grid_cap);
+}
+
 void run_spmv(s3o_problem *p, const StructDev &s, double lambda, const double *x, int pcg_mode) {
     if (p->spmv_version == 1 && !p->dist)
         launch_spmv(p->d, p->d_H, s, p->S.nf, lambda, x, p->d_q1, p->d_T, p->d_partials, p->d_sc, pcg_mode, p->stream);
-    else if (p->spmv_version == 4 && p->d == 7 && p->S.max_row_blocks <= p->S.tile_blocks &&
-             spmv4_fits(s.ntiles, p->spmv_grid_cap))
-        launch_spmv4(p->d_H, s, own_rows(p), lambda, x, p->d_q1, p->d_T, p->d_partials, p->d_sc, pcg_mode,
+    else if (uses_spmv4(p)) {
+        StructDev s4 = s;
+        if (p->p2p && x == p->d_p) s4.ghost_src = p->d_ghost_src;      // ghost columns read from the owners' p
+        launch_spmv4(p->d_H, s4, own_rows(p), lambda, x, p->d_q1, p->d_T, p->d_partials, p->d_sc, pcg_mode,
                      p->spmv_grid_cap, p->dist, p->stream);
+    }
     else if (p->spmv_version >= 3 && p->S.max_row_blocks <= p->S.tile_blocks)
         launch_spmv3(p->d, p->d_H, s, own_rows(p), lambda, x, p->d_q1, p->d_T, p->d_partials, p->d_sc, pcg_mode,
                      p->spmv_grid_cap, p->dist, p->stream);
@@ -178,6 +196,13 @@ int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel
     const PartitionPlan &P = p->plan;
     auto halo = [&]() -> int {     // bring the ghost entries of p up to date before the product
         if (!dist) return S3O_OK;
+        if (p->p2p) {               // the SpMV reads them from the owners' memory: publish my epoch, wait for theirs
+            ++p->halo_epoch;
+            launch_halo_signal(p->d_flag, p->halo_epoch, p->stream);
+            launch_halo_wait(p->d_peer_flags, p->n_peers, p->halo_epoch, p->d_sc, p->stream);
+            p->stats.kernel_launches += 2;
+            return S3O_OK;
+        }
         launch_pack_rows(d, p->d_p, p->d_send_idx, (int)P.send_idx.size(), p->d_sendbuf, p->d_sc, p->stream);
         p->stats.kernel_launches += 1;
         if (comm_halo(p->comm, p->d_sendbuf, P.send_off.data(), P.send_count.data(), p->d_p + (size_t)P.n_own * d,
@@ -615,6 +640,73 @@ int s3o_set_pcg(s3o_problem *p, double rel_tol, int max_iter) {
     return S3O_OK;
 }
 
+namespace {
+// Peer-to-peer halo: every rank exports its p vector and an epoch flag through CUDA IPC, the handles travel by
+// one NCCL all-gather, and each rank maps the vectors of the ranks it has ghosts from.  The SpMV then loads
+// ghost columns straight from the owner's HBM over NVLink (ghost_src table).  All ranks take the same
+// decision: if any mapping fails anywhere, everybody stays on the NCCL send/recv halo.
+int setup_p2p(s3o_problem *p) {
+    p->want_p2p_setup = false;
+    if (getenv("S3O_NO_P2P") || !uses_spmv4(p)) return S3O_OK;
+    const PartitionPlan &P = p->plan;
+    const int world = P.world, rank = P.rank, d = p->d;
+    struct Handles { cudaIpcMemHandle_t vec, flag; };
+    int rc = dev_alloc(&p->d_flag, 1);
+    if (rc) return rc;
+    S3O_CUDA(cudaMemsetAsync(p->d_flag, 0, sizeof(long long), p->stream));
+    Handles mine{};
+    int ok = cudaIpcGetMemHandle(&mine.vec, p->d_p) == cudaSuccess && cudaIpcGetMemHandle(&mine.flag, p->d_flag) == cudaSuccess;
+    cudaGetLastError();
+    unsigned char *d_h = nullptr;
+    if ((rc = dev_alloc(&d_h, sizeof(Handles) * (size_t)(world + 1)))) return rc;
+    S3O_CUDA(cudaMemcpyAsync(d_h + sizeof(Handles) * world, &mine, sizeof(Handles), cudaMemcpyHostToDevice, p->stream));
+    if (comm_allgather_bytes(p->comm, d_h + sizeof(Handles) * world, d_h, sizeof(Handles), p->stream)) {
+        cudaFree(d_h); set_error("%s", comm_last_error()); return S3O_ERR_NCCL;
+    }
+    std::vector<Handles> all(world);
+    S3O_CUDA(cudaMemcpyAsync(all.data(), d_h, sizeof(Handles) * world, cudaMemcpyDeviceToHost, p->stream));
+    S3O_CUDA(cudaStreamSynchronize(p->stream));
+    cudaFree(d_h);
+    std::vector<double *> peer_vec(world, nullptr);
+    std::vector<long long *> flags;
+    for (int q = 0; q < world && ok; ++q) {
+        if (q == rank || P.recv_count[q] == 0) continue;
+        void *v = nullptr, *f = nullptr;
+        if (cudaIpcOpenMemHandle(&v, all[q].vec, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+        p->ipc_mapped.push_back(v);
+        if (cudaIpcOpenMemHandle(&f, all[q].flag, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+        p->ipc_mapped.push_back(f);
+        peer_vec[q] = (double *)v;
+        flags.push_back((long long *)f);
+    }
+    cudaGetLastError();
+    // collective decision: 1 only if every rank mapped everything it needs
+    double *d_ok = nullptr;
+    if ((rc = dev_alloc(&d_ok, 1))) return rc;
+    const double fail = ok ? 0.0 : 1.0;
+    S3O_CUDA(cudaMemcpyAsync(d_ok, &fail, sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    if (comm_allreduce_max(p->comm, d_ok, 1, p->stream)) { cudaFree(d_ok); set_error("%s", comm_last_error()); return S3O_ERR_NCCL; }
+    double any_fail = 1;
+    S3O_CUDA(cudaMemcpyAsync(&any_fail, d_ok, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    S3O_CUDA(cudaStreamSynchronize(p->stream));
+    cudaFree(d_ok);
+    if (any_fail != 0.0) { close_p2p(p); return S3O_OK; }       // NCCL halo everywhere
+    std::vector<double *> src(P.n_ghost);
+    for (int t = 0; t < P.n_ghost; ++t) {
+        const int gidx = P.ghosts[t], q = gidx / P.seg;
+        src[t] = peer_vec[q] + (size_t)(gidx - q * P.seg) * d;
+    }
+    rc = upload(p, &p->d_ghost_src, src);
+    rc = rc ? rc : upload(p, &p->d_peer_flags, flags);
+    if (rc) return rc;
+    S3O_CUDA(cudaStreamSynchronize(p->stream));
+    p->n_peers = (int)flags.size();
+    p->halo_epoch = 0;
+    p->p2p = true;
+    return S3O_OK;
+}
+}  // namespace
+
 int s3o_build_structure(s3o_problem *p, int *n_free, int *n_blocks) {
     if (!p) return S3O_ERR_INVALID;
     if (p->kind == S3O_KIND_BA) {
@@ -660,6 +752,7 @@ int s3o_build_structure(s3o_problem *p, int *n_free, int *n_blocks) {
             rc = rc ? rc : dev_alloc(&p->d_sendbuf, P.send_idx.size() * p->d);
             rc = rc ? rc : dev_alloc(&p->d_xg, (size_t)P.world * P.seg * p->d);
         }
+        p->want_p2p_setup = p->dist;
         rc = rc ? rc : upload(p, &d_perm, S.perm);
         rc = rc ? rc : dev_alloc(&p->d_meas, (size_t)p->ne_pad * p->est_dim);
         if (p->has_info) rc = rc ? rc : dev_alloc(&p->d_info, (size_t)p->ne_pad * p->ninfo);
@@ -686,6 +779,7 @@ int s3o_build_structure(s3o_problem *p, int *n_free, int *n_blocks) {
         dev_free(p->d_info_aos);
         p->built = true;
         p->stats.n_free = S.nf; p->stats.n_blocks = S.nb;
+        if (p->want_p2p_setup && (rc = setup_p2p(p))) return rc;
         // the aggregation hierarchy is structure work too: build it here rather than inside the first solve
         if (wants_multilevel(p) && (rc = amg_setup(p))) return rc;
     }
@@ -1160,6 +1254,8 @@ int s3o_get_stats(s3o_problem *p, s3o_stats *out) {
     if (p->kind != S3O_KIND_BA) p->stats.n_edges = p->ne;
     p->stats.n_free = p->built ? p->S.nf : 0;
     p->stats.n_blocks = p->built ? p->S.nb : 0;
+    p->stats.multilevel_levels = amg_levels(p);
+    p->stats.p2p_halo = p->p2p ? 1 : 0;
     *out = p->stats;
     return S3O_OK;
 }

@@ -64,6 +64,15 @@ struct s3o_problem {
     int32_t *d_ghidx = nullptr, *d_send_idx = nullptr;
     uint8_t *d_primary = nullptr;
     double *d_sendbuf = nullptr, *d_xg = nullptr;
+    // peer-to-peer halo (NVLink loads inside the SpMV instead of pack + NCCL send/recv): CUDA IPC mappings of
+    // the neighbours' p vectors and epoch flags
+    bool p2p = false, want_p2p_setup = false;
+    long long halo_epoch = 0;
+    long long *d_flag = nullptr;               // my epoch flag (mapped by the neighbours)
+    double **d_ghost_src = nullptr;            // [n_ghost] address of every ghost column inside its owner's p
+    long long **d_peer_flags = nullptr;        // [n_peers] the neighbours' flags
+    int n_peers = 0;
+    std::vector<void *> ipc_mapped;            // to cudaIpcCloseMemHandle
     int spmv_version = 4;       // 1: lane-group rows, 2: tiled thread-per-block, 3: v2 + TMA ring, 4: v3 + prefetch pipeline (d = 7)
     int spmv_grid_cap = 148 * 2;
     // linear system
@@ -118,6 +127,7 @@ int upload(s3o_problem *p, T **dst, const std::vector<T> &src) {
 
 StructDev struct_view(const s3o_problem *p);
 void free_structure(s3o_problem *p);
+void close_p2p(s3o_problem *p);
 int check_launch(s3o_problem *p, int n);
 int sync_scalars(s3o_problem *p);
 int upload_structure_arrays(s3o_problem *p, int rows_own);   // BSR / tile arrays of p->S -> device

@@ -380,8 +380,14 @@ __global__ void __launch_bounds__(NT) spmv4_kernel(const double *__restrict__ H,
 #pragma unroll
             for (int c = 0; c < D; ++c) pi[c] = p[(size_t)i * D + c];
             if (j != i) {
+                if (s.ghost_src && j >= s.n_own) {       // ghost column: read the owner's p over NVLink
+                    const double *src = s.ghost_src[j - s.n_own];
 #pragma unroll
-                for (int c = 0; c < D; ++c) pj[c] = p[(size_t)j * D + c];
+                    for (int c = 0; c < D; ++c) pj[c] = __ldcg(src + c);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < D; ++c) pj[c] = p[(size_t)j * D + c];
+                }
             }
         }
         const int nrows = drow_e[0] - drow[0];
@@ -408,8 +414,14 @@ __global__ void __launch_bounds__(NT) spmv4_kernel(const double *__restrict__ H,
 #pragma unroll
                 for (int c = 0; c < D; ++c) pin[c] = p[(size_t)ib * D + c];
                 if (jb != ib) {
+                    if (s.ghost_src && jb >= s.n_own) {
+                        const double *src = s.ghost_src[jb - s.n_own];
 #pragma unroll
-                    for (int c = 0; c < D; ++c) pjn[c] = p[(size_t)jb * D + c];
+                        for (int c = 0; c < D; ++c) pjn[c] = __ldcg(src + c);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < D; ++c) pjn[c] = p[(size_t)jb * D + c];
+                    }
                 }
             }
             const int nrows = drow_e[n + 1] - drow[n + 1];

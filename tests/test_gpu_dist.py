@@ -26,3 +26,6 @@ def test_partitioned_solve_matches_single_gpu(precond, graph):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert "DIST_CHECK PASS" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
     assert "ESTIMATES_IDENTICAL_ACROSS_RANKS True" in out.stdout
+    assert "P2P_HALO 1" in out.stdout            # ghost columns read over NVLink inside the SpMV (CUDA IPC mappings)
+    if precond == 2:
+        assert "MULTILEVEL_LEVELS 0" not in out.stdout

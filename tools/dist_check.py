@@ -59,6 +59,7 @@ def main():
         print("pcg iters dist", hist[:, 4], "single", hists[:, 4])
         print("max |vertex diff| %.3e" % dv)
         print("DIST_CHECK", "PASS" if ok else "FAIL", "world", world)
+        print("P2P_HALO", pd.stats()["p2p_halo"], "MULTILEVEL_LEVELS", pd.stats()["multilevel_levels"])
     # every rank holds the same estimates after the solve
     t = torch.from_numpy(vd.copy()).cuda()
     ref = t.clone()
