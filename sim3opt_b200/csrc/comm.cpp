@@ -2,7 +2,8 @@
 // One process per GPU; the communicator is created from a unique id that the host program
 // (bench.py / tests, via torch.distributed) broadcasts.  Collectives used on the data path:
 //   all-reduce of 1-2 fp64 scalars (PCG dot products, chi2, computeScale, max diagonal),
-//   grouped send/recv of the halo entries of p before every SpMV,
+//   grouped send/recv of the halo entries of p before every SpMV (fallback: normally the SpMV loads them from
+//   the peers' memory over NVLink, see setup_p2p in problem.cu; the IPC handles travel by an all-gather here),
 //   all-gather of the step x before the retraction,
 //   in-place all-gather of unequal segments (grouped broadcasts) for the multilevel preconditioner.
 #include <dlfcn.h>
