@@ -1063,7 +1063,7 @@ __global__ void halo_wait_kernel(long long *const *peer_flags, int n_peers, long
     const volatile long long *f = peer_flags[t];
     long long spins = 0;
     while (*f < epoch) {
-        if (++spins > (1ll << 31)) { sc->done = 3; break; }     // a peer died: report a breakdown instead of hanging
+        if (++spins > (1ll << 25)) { sc->done = 3; break; }     // ~1 minute: a peer died, report a breakdown instead of hanging
     }
     __threadfence_system();
 }
