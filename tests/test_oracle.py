@@ -237,3 +237,53 @@ def test_manhattan_generator_and_oracle_convergence():
     dof = 7 * (ne - (nv - 1))
     assert 0.8 * dof <= chi2 <= 1.2 * dof
     assert np.abs(p.vertices()[:, 4:7] - g["gt"][:, 4:7]).max() < 1.0
+
+
+def _generator(omega, upsilon, sigma):
+    """4x4 Lie-algebra element of Sim3 acting on homogeneous points: x -> s R x + t  <=>  [[sR, t], [0, 1]]."""
+    G = np.zeros((4, 4))
+    G[0, 1], G[0, 2], G[1, 0], G[1, 2], G[2, 0], G[2, 1] = -omega[2], omega[1], omega[2], -omega[0], -omega[1], omega[0]
+    G[:3, :3] += sigma * np.eye(3)
+    G[:3, 3] = upsilon
+    return G
+
+
+def test_exp_log_against_matrix_exponential():
+    """Independent pin of the generic exp / ln branches (sim3_rv.h:168-181, :292-303): the closed-form coefficients
+    A, B, C must reproduce scipy's Pade matrix exponential / logarithm of the 4x4 generator."""
+    from scipy.linalg import expm, logm
+    rng = np.random.default_rng(21)
+    for _ in range(40):
+        v = np.concatenate([rng.normal(0, 0.8, 3), rng.normal(0, 3.0, 3), rng.normal(0, 0.5, 1)])
+        S = orc.sim3_exp(v)
+        M = expm(_generator(v[:3], v[3:6], v[6]))
+        R = orc.quat_to_rot(S[:4])
+        assert np.abs(S[7] * R - M[:3, :3]).max() <= 1e-12 * max(1.0, S[7])
+        assert np.abs(S[4:7] - M[:3, 3]).max() <= 1e-11 * max(1.0, np.abs(M[:3, 3]).max())
+        L = np.real(logm(M))
+        back = orc.sim3_log(S)
+        assert np.abs(back - v).max() <= 1e-9
+        assert abs(L[0, 0] - back[6]) <= 1e-9 and np.abs(L[:3, 3] - back[3:6]).max() <= 1e-8
+    # SE3 (bundle-adjustment cameras): the same check with sigma = 0
+    for _ in range(20):
+        v = np.concatenate([rng.normal(0, 0.8, 3), rng.normal(0, 3.0, 3)])
+        T = orc.se3_exp(v)
+        M = expm(_generator(v[:3], v[3:6], 0.0))
+        assert np.abs(orc.quat_to_rot(T[:4]) - M[:3, :3]).max() <= 1e-12
+        assert np.abs(T[4:7] - M[:3, 3]).max() <= 1e-11 * max(1.0, np.abs(M[:3, 3]).max())
+
+
+def test_corrected_small_angle_limits_against_matrix_exponential():
+    """The CORRECTED math mode is the one consistent with the true exponential in the
+    theta < eps, sigma != 0 branch; the as-written reference coefficient is not."""
+    from scipy.linalg import expm
+    v = np.array([2e-6, -1e-6, 3e-6, 1.5, -0.7, 2.2, 0.4])
+    M = expm(_generator(v[:3], v[3:6], v[6]))
+    orc.set_math_mode(orc.MATH_CORRECTED)
+    try:
+        S = orc.sim3_exp(v)
+    finally:
+        orc.set_math_mode(orc.MATH_REFERENCE)
+    assert np.abs(S[4:7] - M[:3, 3]).max() <= 1e-9
+    S_ref = orc.sim3_exp(v)
+    assert np.abs(S_ref[4:7] - M[:3, 3]).max() <= 1e-4          # the as-written B only matters at O(theta^2)
