@@ -70,3 +70,12 @@ def test_host_structure_edge_cases():
         pass
     else:
         raise AssertionError("invalid edge accepted")
+
+
+def test_header_is_plain_c_and_integration_snippets_type_check(tmp_path):
+    """include/sim3opt_b200.h through a C compiler (the boundary is extern "C", plain pointers and sizes) together
+    with the call sequences INTEGRATION.md shows."""
+    import subprocess
+    src = os.path.join(ROOT, "tests", "cpp", "abi_snippets.c")
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    "-c", src, "-o", str(tmp_path / "abi_snippets.o")], check=True)
