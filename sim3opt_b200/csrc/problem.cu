@@ -967,6 +967,7 @@ int s3o_solve(s3o_problem *p, double lambda, double *x, int *pcg_iters, double *
 
 int s3o_hessian_multiply(s3o_problem *p, double lambda, const double *x, double *y) {
     if (!p || !p->built || !p->linearized || !x || !y) { set_error("s3o_hessian_multiply: call s3o_linearize first"); return S3O_ERR_INVALID; }
+    if (p->dist) { set_error("s3o_hessian_multiply: a lock-step getter of the single-GPU problem (the partitioned solve holds owned rows only)"); return S3O_ERR_UNSUPPORTED; }
     cudaSetDevice(p->device);
     const size_t bytes = (size_t)p->S.nf * p->d * sizeof(double);
     S3O_CUDA(cudaMemcpyAsync(p->d_p, x, bytes, cudaMemcpyHostToDevice, p->stream));
