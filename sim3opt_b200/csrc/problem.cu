@@ -338,6 +338,73 @@ int alloc_linear_system(s3o_problem *p) {
 
 }  // namespace s3o
 
+namespace {
+// Peer-to-peer halo: every rank exports its p vector and an epoch flag through CUDA IPC, the handles travel by
+// one NCCL all-gather, and each rank maps the vectors of the ranks it has ghosts from.  The SpMV then loads
+// ghost columns straight from the owner's HBM over NVLink (ghost_src table).  All ranks take the same
+// decision: if any mapping fails anywhere, everybody stays on the NCCL send/recv halo.
+int setup_p2p(s3o_problem *p) {
+    p->want_p2p_setup = false;
+    if (getenv("S3O_NO_P2P") || !uses_spmv4(p)) return S3O_OK;
+    const PartitionPlan &P = p->plan;
+    const int world = P.world, rank = P.rank, d = p->d;
+    struct Handles { cudaIpcMemHandle_t vec, flag; };
+    int rc = dev_alloc(&p->d_flag, 1);
+    if (rc) return rc;
+    S3O_CUDA(cudaMemsetAsync(p->d_flag, 0, sizeof(long long), p->stream));
+    Handles mine{};
+    int ok = cudaIpcGetMemHandle(&mine.vec, p->d_p) == cudaSuccess && cudaIpcGetMemHandle(&mine.flag, p->d_flag) == cudaSuccess;
+    cudaGetLastError();
+    unsigned char *d_h = nullptr;
+    if ((rc = dev_alloc(&d_h, sizeof(Handles) * (size_t)(world + 1)))) return rc;
+    S3O_CUDA(cudaMemcpyAsync(d_h + sizeof(Handles) * world, &mine, sizeof(Handles), cudaMemcpyHostToDevice, p->stream));
+    if (comm_allgather_bytes(p->comm, d_h + sizeof(Handles) * world, d_h, sizeof(Handles), p->stream)) {
+        cudaFree(d_h); set_error("%s", comm_last_error()); return S3O_ERR_NCCL;
+    }
+    std::vector<Handles> all(world);
+    S3O_CUDA(cudaMemcpyAsync(all.data(), d_h, sizeof(Handles) * world, cudaMemcpyDeviceToHost, p->stream));
+    S3O_CUDA(cudaStreamSynchronize(p->stream));
+    cudaFree(d_h);
+    std::vector<double *> peer_vec(world, nullptr);
+    std::vector<long long *> flags;
+    for (int q = 0; q < world && ok; ++q) {
+        if (q == rank || P.recv_count[q] == 0) continue;
+        void *v = nullptr, *f = nullptr;
+        if (cudaIpcOpenMemHandle(&v, all[q].vec, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+        p->ipc_mapped.push_back(v);
+        if (cudaIpcOpenMemHandle(&f, all[q].flag, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+        p->ipc_mapped.push_back(f);
+        peer_vec[q] = (double *)v;
+        flags.push_back((long long *)f);
+    }
+    cudaGetLastError();
+    // collective decision: 1 only if every rank mapped everything it needs
+    double *d_ok = nullptr;
+    if ((rc = dev_alloc(&d_ok, 1))) return rc;
+    const double fail = ok ? 0.0 : 1.0;
+    S3O_CUDA(cudaMemcpyAsync(d_ok, &fail, sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    if (comm_allreduce_max(p->comm, d_ok, 1, p->stream)) { cudaFree(d_ok); set_error("%s", comm_last_error()); return S3O_ERR_NCCL; }
+    double any_fail = 1;
+    S3O_CUDA(cudaMemcpyAsync(&any_fail, d_ok, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    S3O_CUDA(cudaStreamSynchronize(p->stream));
+    cudaFree(d_ok);
+    if (any_fail != 0.0) { close_p2p(p); return S3O_OK; }       // NCCL halo everywhere
+    std::vector<double *> src(P.n_ghost);
+    for (int t = 0; t < P.n_ghost; ++t) {
+        const int gidx = P.ghosts[t], q = gidx / P.seg;
+        src[t] = peer_vec[q] + (size_t)(gidx - q * P.seg) * d;
+    }
+    rc = upload(p, &p->d_ghost_src, src);
+    rc = rc ? rc : upload(p, &p->d_peer_flags, flags);
+    if (rc) return rc;
+    S3O_CUDA(cudaStreamSynchronize(p->stream));
+    p->n_peers = (int)flags.size();
+    p->halo_epoch = 0;
+    p->p2p = true;
+    return S3O_OK;
+}
+}  // namespace
+
 // ======================================================================================
 // C ABI
 // ======================================================================================
@@ -639,73 +706,6 @@ int s3o_set_pcg(s3o_problem *p, double rel_tol, int max_iter) {
     if (max_iter > 0) p->pcg_max_iter = max_iter;
     return S3O_OK;
 }
-
-namespace {
-// Peer-to-peer halo: every rank exports its p vector and an epoch flag through CUDA IPC, the handles travel by
-// one NCCL all-gather, and each rank maps the vectors of the ranks it has ghosts from.  The SpMV then loads
-// ghost columns straight from the owner's HBM over NVLink (ghost_src table).  All ranks take the same
-// decision: if any mapping fails anywhere, everybody stays on the NCCL send/recv halo.
-int setup_p2p(s3o_problem *p) {
-    p->want_p2p_setup = false;
-    if (getenv("S3O_NO_P2P") || !uses_spmv4(p)) return S3O_OK;
-    const PartitionPlan &P = p->plan;
-    const int world = P.world, rank = P.rank, d = p->d;
-    struct Handles { cudaIpcMemHandle_t vec, flag; };
-    int rc = dev_alloc(&p->d_flag, 1);
-    if (rc) return rc;
-    S3O_CUDA(cudaMemsetAsync(p->d_flag, 0, sizeof(long long), p->stream));
-    Handles mine{};
-    int ok = cudaIpcGetMemHandle(&mine.vec, p->d_p) == cudaSuccess && cudaIpcGetMemHandle(&mine.flag, p->d_flag) == cudaSuccess;
-    cudaGetLastError();
-    unsigned char *d_h = nullptr;
-    if ((rc = dev_alloc(&d_h, sizeof(Handles) * (size_t)(world + 1)))) return rc;
-    S3O_CUDA(cudaMemcpyAsync(d_h + sizeof(Handles) * world, &mine, sizeof(Handles), cudaMemcpyHostToDevice, p->stream));
-    if (comm_allgather_bytes(p->comm, d_h + sizeof(Handles) * world, d_h, sizeof(Handles), p->stream)) {
-        cudaFree(d_h); set_error("%s", comm_last_error()); return S3O_ERR_NCCL;
-    }
-    std::vector<Handles> all(world);
-    S3O_CUDA(cudaMemcpyAsync(all.data(), d_h, sizeof(Handles) * world, cudaMemcpyDeviceToHost, p->stream));
-    S3O_CUDA(cudaStreamSynchronize(p->stream));
-    cudaFree(d_h);
-    std::vector<double *> peer_vec(world, nullptr);
-    std::vector<long long *> flags;
-    for (int q = 0; q < world && ok; ++q) {
-        if (q == rank || P.recv_count[q] == 0) continue;
-        void *v = nullptr, *f = nullptr;
-        if (cudaIpcOpenMemHandle(&v, all[q].vec, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
-        p->ipc_mapped.push_back(v);
-        if (cudaIpcOpenMemHandle(&f, all[q].flag, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
-        p->ipc_mapped.push_back(f);
-        peer_vec[q] = (double *)v;
-        flags.push_back((long long *)f);
-    }
-    cudaGetLastError();
-    // collective decision: 1 only if every rank mapped everything it needs
-    double *d_ok = nullptr;
-    if ((rc = dev_alloc(&d_ok, 1))) return rc;
-    const double fail = ok ? 0.0 : 1.0;
-    S3O_CUDA(cudaMemcpyAsync(d_ok, &fail, sizeof(double), cudaMemcpyHostToDevice, p->stream));
-    if (comm_allreduce_max(p->comm, d_ok, 1, p->stream)) { cudaFree(d_ok); set_error("%s", comm_last_error()); return S3O_ERR_NCCL; }
-    double any_fail = 1;
-    S3O_CUDA(cudaMemcpyAsync(&any_fail, d_ok, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-    S3O_CUDA(cudaStreamSynchronize(p->stream));
-    cudaFree(d_ok);
-    if (any_fail != 0.0) { close_p2p(p); return S3O_OK; }       // NCCL halo everywhere
-    std::vector<double *> src(P.n_ghost);
-    for (int t = 0; t < P.n_ghost; ++t) {
-        const int gidx = P.ghosts[t], q = gidx / P.seg;
-        src[t] = peer_vec[q] + (size_t)(gidx - q * P.seg) * d;
-    }
-    rc = upload(p, &p->d_ghost_src, src);
-    rc = rc ? rc : upload(p, &p->d_peer_flags, flags);
-    if (rc) return rc;
-    S3O_CUDA(cudaStreamSynchronize(p->stream));
-    p->n_peers = (int)flags.size();
-    p->halo_epoch = 0;
-    p->p2p = true;
-    return S3O_OK;
-}
-}  // namespace
 
 int s3o_build_structure(s3o_problem *p, int *n_free, int *n_blocks) {
     if (!p) return S3O_ERR_INVALID;
