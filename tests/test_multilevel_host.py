@@ -55,3 +55,29 @@ def test_partitioned_hierarchy_respects_vertex_ranges():
         assert np.array_equal(lo, hi)
         assert np.all(np.diff(lo) >= 0)                  # coarse numbering follows the ranks
         assert np.all(np.diff(np.concatenate([[nf], sizes])) < 0)
+
+
+def test_partitioned_galerkin_contributions_are_local():
+    """The invariant the partitioned multilevel PCG relies on (csrc/amg.cu, localize_fine_level): every fine block
+    (gi < gj) that contributes to an upper level-1 block (min(I,J), max(I,J)) is stored on the rank that owns that
+    coarse row -- i.e. that rank owns the block's row vertex gi (cut edges live in the row of their lower end),
+    and when the coarse block is taken transposed (I > J) both ends are its own."""
+    for gname, g in (("sphere", synth.sphere(8, 500, seed=3)), ("manhattan", synth.manhattan3d(3000, seed=4))):
+        nv = len(g["est"])
+        nf = int((np.asarray(g["fixed"]) == 0).sum())
+        colptr, rowidx, hidx = s3.host_structure(nv, g["fixed"], g["v0"], g["v1"])
+        cols = np.repeat(np.arange(nf), np.diff(colptr))
+        off = rowidx != cols
+        gi, gj = rowidx[off], cols[off]                       # upper blocks: row < column
+        assert np.all(gi < gj)
+        for world in (2, 3, 8):
+            sizes, blocks, agg = s3.host_multilevel(nv, g["fixed"], g["v0"], g["v1"], world=world)
+            seg = -(-nf // world)
+            owner_v = np.arange(nf) // seg
+            owner_c = np.zeros(sizes[0], np.int64)
+            owner_c[agg] = owner_v                            # aggregates are rank-confined (tested above)
+            I, J = agg[gi], agg[gj]
+            row_owner = owner_c[np.minimum(I, J)]
+            assert np.all(row_owner == owner_v[gi]), gname    # the block sits in a row this rank owns
+            flipped = I > J
+            assert np.all(owner_v[gj[flipped]] == owner_v[gi[flipped]]), gname
