@@ -287,3 +287,48 @@ def test_corrected_small_angle_limits_against_matrix_exponential():
     assert np.abs(S[4:7] - M[:3, 3]).max() <= 1e-9
     S_ref = orc.sim3_exp(v)
     assert np.abs(S_ref[4:7] - M[:3, 3]).max() <= 1e-4          # the as-written B only matters at O(theta^2)
+
+
+def test_gauge_null_space_behind_the_multilevel_coarse_space(kitti_k1):
+    """a right-multiplied world similarity leaves every edge error unchanged, so at a
+    zero-residual state with no vertex fixed the Hessian annihilates delta_i = Ad(S_i) xi (Sim3) and
+    delta_i = (s_i sigma, s_i R_i c) (scale-trans).  Checked on the odometry chain of KITTI-00 (loop edge dropped)."""
+    from oracle import kitti_io
+    g = kitti_k1
+    keep = np.arange(1, len(g["v0"]))                       # edge 0 is the loop closure; the rest has zero residual
+    n = 60
+    sel = keep[(g["v0"][keep] < n) & (g["v1"][keep] < n)]
+    est = g["est"][:n].copy()
+    est[:, 7] = np.exp(np.linspace(-0.3, 0.4, n))           # spread the scales: the null vectors depend on them
+    meas = np.array([orc.sim3_mul(est[j], orc.sim3_inv(est[i])) for i, j in zip(g["v0"][sel], g["v1"][sel])])
+
+    def dense_hessian(kind, e, m, aux=None):
+        p = orc.Problem(kind)
+        p.set_vertices(e, np.zeros(n, np.uint8), aux)
+        p.set_edges(g["v0"][sel], g["v1"][sel], m)
+        p.set_jacobian_mode(orc.JAC_ANALYTIC)
+        colptr, rowidx = p.build_structure()
+        assert p.chi2() <= 1e-18
+        H, _ = p.linearize()
+        d = H.shape[1]
+        A = np.zeros((n * d, n * d))
+        for c in range(n):
+            for k in range(colptr[c], colptr[c + 1]):
+                r = rowidx[k]
+                A[r * d:(r + 1) * d, c * d:(c + 1) * d] = H[k]
+                A[c * d:(c + 1) * d, r * d:(r + 1) * d] = H[k].T
+        return A
+
+    rng = np.random.default_rng(0)
+    A7 = dense_hessian(orc.KIND_SIM3, est, meas)
+    for _ in range(3):
+        xi = rng.normal(size=7)
+        delta = np.concatenate([orc.sim3_adjoint(S) @ xi for S in est])
+        assert np.abs(A7 @ delta).max() <= 1e-8 * np.abs(A7).max() * np.abs(delta).max()
+    st = kitti_io.to_scale_trans_graph(dict(est=est, meas=meas, fixed=np.zeros(n, np.uint8), v0=g["v0"][sel], v1=g["v1"][sel]))
+    A4 = dense_hessian(orc.KIND_SCALE_TRANS, st["est"], st["meas"], st["aux"])
+    for _ in range(3):
+        sigma, c = rng.normal(), rng.normal(size=3)
+        delta = np.concatenate([np.concatenate([[s[0] * sigma], s[0] * (orc.quat_to_rot(q) @ c)])
+                                for s, q in zip(st["est"], st["aux"])])
+        assert np.abs(A4 @ delta).max() <= 1e-8 * np.abs(A4).max() * np.abs(delta).max()
