@@ -71,6 +71,14 @@ enum s3o_math_mode { S3O_MATH_REFERENCE = 0, S3O_MATH_CORRECTED = 1 };
  * BLOCK_JACOBI, switch to MULTILEVEL once a solve has needed more than 256 PCG iterations, and back
  * when a MULTILEVEL solve finishes within 8. */
 enum s3o_preconditioner { S3O_PRECOND_AUTO = 0, S3O_PRECOND_BLOCK_JACOBI = 1, S3O_PRECOND_MULTILEVEL = 2 };
+/* Linear solver behind BlockSolver::solve (the LinearSolverEigen slot, kitti_surf.cpp:553-557).  DIRECT: sparse
+ * block Cholesky on the device -- symbolic analysis once per structure (multiple-minimum-degree order whose
+ * elimination rounds are the parallel schedule), numeric factorisation + triangular solves per LM trial in one
+ * kernel; exact like the reference's LDL^T.  PCG: preconditioned conjugate gradients (s3o_set_pcg,
+ * s3o_set_preconditioner).  AUTO (default): DIRECT when the factor is small and shallow (<= 400 000 block
+ * products, <= 64 elimination rounds: the KITTI-size chain-dominated graphs of the reference), PCG otherwise and
+ * always in the partitioned solve. */
+enum s3o_linear_solver { S3O_LINSOLVER_AUTO = 0, S3O_LINSOLVER_PCG = 1, S3O_LINSOLVER_DIRECT = 2 };
 /* g2o OptimizationAlgorithm::SolverResult */
 enum s3o_solver_result { S3O_RESULT_TERMINATE = 2, S3O_RESULT_OK = 1, S3O_RESULT_FAIL = -1 };
 
@@ -120,6 +128,7 @@ int s3o_set_lm(s3o_problem *p, double tau, double user_lambda_init, int max_tria
 /* block-Jacobi PCG: relative residual tolerance |r|/|b| and iteration cap */
 int s3o_set_pcg(s3o_problem *p, double rel_tol, int max_iter);
 int s3o_set_preconditioner(s3o_problem *p, int kind /* s3o_preconditioner */);
+int s3o_set_linear_solver(s3o_problem *p, int kind /* s3o_linear_solver */);
 
 /* ---- structure (replaces initializeOptimization + BlockSolver::buildStructure) -------- */
 int s3o_build_structure(s3o_problem *p, int *n_free, int *n_blocks);
@@ -142,6 +151,17 @@ int s3o_host_multilevel(int n_vertices, const uint8_t *fixed, int n_edges, const
                         int world /* ranks of the partitioned solve, 1 = one GPU */, int cap, int *n_levels,
                         int32_t *level_vertices, int32_t *level_blocks, int32_t *aggregate0);
 
+/* Host-only view of the factorisation plan the DIRECT linear solver builds for a graph (no device needed; for
+ * tests and tools).  Blocks of L are listed column by column in elimination order, pivot block first.  Call once
+ * with every array NULL to get counts = [n_free, rounds, blocks of L, update-list entries, block products], then
+ * with buffers: perm[n_free] elimination position -> Hessian index; lev_ptr[rounds+1] columns of each round;
+ * cptr[n_free+1]; brow[nL] row position of each block; src[nL] (BSR-upper block << 1) | transposed or -1 for
+ * fill-in (BSR order: s3o_host_structure's blocks sorted by (row, col), diagonal first in each row);
+ * upd_ptr[nL+1], upd_a/upd_b: block t -= L[upd_a] L[upd_b]^T in list order.  max_pairs <= 0: no limit. */
+int s3o_host_direct_plan(int n_vertices, const uint8_t *fixed, int n_edges, const int32_t *v0, const int32_t *v1,
+                         int64_t max_pairs, int64_t *counts /* 5 */, int32_t *perm, int32_t *lev_ptr, int32_t *cptr,
+                         int32_t *brow, int32_t *src, int32_t *upd_ptr, int32_t *upd_a, int32_t *upd_b);
+
 /* ---- lock-step pieces (each mirrors one g2o step; used by the parity tests) ------------ */
 int s3o_chi2(s3o_problem *p, double *chi2);                 /* computeActiveErrors + activeRobustChi2 */
 int s3o_edge_errors(s3o_problem *p, double *err /* n_edges x d, caller's edge order */);
@@ -153,7 +173,9 @@ int s3o_max_diag(s3o_problem *p, double *max_diag);
 int s3o_solve(s3o_problem *p, double lambda, double *x, int *pcg_iters, double *rel_residual);
 /* y = (H + lambda I) x on the device (x, y: n_free*d host arrays) -- for backward-error checks */
 int s3o_hessian_multiply(s3o_problem *p, double lambda, const double *x, double *y);
-int s3o_update(s3o_problem *p, const double *x);            /* oplus on every free vertex */
+/* oplus on every free vertex.  Partitioned solve: x holds the rows this rank owns (n_own * d); the step is
+ * all-gathered inside, so the call is collective and leaves identical estimates on every rank. */
+int s3o_update(s3o_problem *p, const double *x);
 
 /* Eigenvector of the smallest eigenvalue of H = J^T Omega J at the current estimates, by inverse
  * iteration with the PCG solver (replaces the dense Eigen::JacobiSVD null-vector solve of the
@@ -229,6 +251,10 @@ typedef struct s3o_stats {
     int32_t multilevel_levels; /* coarse levels of the multilevel preconditioner in use (0: block-Jacobi) */
     int32_t p2p_halo;          /* partitioned solve: 1 if the SpMV reads ghost columns from the peers' memory (CUDA IPC
                                   over NVLink), 0 if they are exchanged by NCCL send/recv */
+    int64_t direct_solves;     /* exact solves (sparse block Cholesky) since create / reset */
+    int32_t direct_levels;     /* elimination rounds of the factorisation plan (0: PCG in use) */
+    int32_t direct_blocks;     /* blocks of the factor L */
+    int64_t pcg_unconverged;   /* PCG solves that ended on the iteration cap or a breakdown (inexact LM steps) */
 } s3o_stats;
 int s3o_get_stats(s3o_problem *p, s3o_stats *out);
 int s3o_reset_stats(s3o_problem *p);

@@ -27,6 +27,32 @@
 
 #define MAXD 7
 
+/* worker threads of the per-edge loops (orc_set_threads); 1 = the reference's behaviour (single thread,
+ * CMakeLists.txt has no OpenMP flag and build.sh:49 does not enable g2o's) */
+static int g_threads = 1;
+void orc_set_threads(int n) { g_threads = n > 1 ? n : 1; }
+int orc_get_threads(void) { return g_threads; }
+
+/* static-schedule parallel for over [0,n) on g_threads POSIX threads (libgomp is not in this image) */
+#include <pthread.h>
+typedef void (*range_fn)(void *ctx, int lo, int hi);
+typedef struct { range_fn fn; void *ctx; int lo, hi; } par_task;
+static void *par_run(void *arg) { par_task *t = (par_task *)arg; t->fn(t->ctx, t->lo, t->hi); return 0; }
+static void par_for(int n, range_fn fn, void *ctx) {
+    int nt = g_threads;
+    if (nt > n) nt = n;
+    if (nt <= 1) { fn(ctx, 0, n); return; }
+    pthread_t th[256];
+    par_task task[256];
+    if (nt > 256) nt = 256;
+    for (int t = 0; t < nt; ++t) {
+        task[t].fn = fn; task[t].ctx = ctx;
+        task[t].lo = (int)((long long)n * t / nt); task[t].hi = (int)((long long)n * (t + 1) / nt);
+        if (t + 1 == nt || pthread_create(&th[t], 0, par_run, &task[t]) != 0) { par_run(&task[t]); th[t] = 0; }
+    }
+    for (int t = 0; t + 1 < nt; ++t) if (th[t]) pthread_join(th[t], 0);
+}
+
 struct orc_problem {
     int kind, d, est_dim;
     int nv, ne;
@@ -338,85 +364,137 @@ void orc_edge_errors(orc_problem *p, double *err) {
         edge_error(p, k, p->est + (size_t)p->ev0[k] * p->est_dim, p->est + (size_t)p->ev1[k] * p->est_dim, err + (size_t)k * p->d);
 }
 
+static double edge_rho0(const orc_problem *p, int k) {
+    double e[MAXD];
+    edge_error(p, k, p->est + (size_t)p->ev0[k] * p->est_dim, p->est + (size_t)p->ev1[k] * p->est_dim, e);
+    double c = edge_chi2(p, k, e);
+    if (p->robust_kind != ORC_ROBUST_NONE) {
+        double rho[3];
+        orc_robustify(p->robust_kind, p->robust_param, c, rho);
+        c = rho[0];
+    }
+    return c;
+}
+
+typedef struct { const orc_problem *p; double *c; } chi_ctx;
+static void chi_range(void *ctx, int lo, int hi) {
+    chi_ctx *c = (chi_ctx *)ctx;
+    for (int k = lo; k < hi; ++k) c->c[k] = edge_rho0(c->p, k);
+}
+
 double orc_chi2(orc_problem *p) { /* computeActiveErrors + activeRobustChi2 */
     double total = 0;
-    for (int k = 0; k < p->ne; ++k) {
-        double e[MAXD];
-        edge_error(p, k, p->est + (size_t)p->ev0[k] * p->est_dim, p->est + (size_t)p->ev1[k] * p->est_dim, e);
-        double c = edge_chi2(p, k, e);
-        if (p->robust_kind != ORC_ROBUST_NONE) {
-            double rho[3];
-            orc_robustify(p->robust_kind, p->robust_param, c, rho);
-            c = rho[0];
-        }
-        total += c;
+    if (g_threads <= 1) {
+        for (int k = 0; k < p->ne; ++k) total += edge_rho0(p, k);
+        return total;
     }
+    /* threads: per-edge values in parallel, summed serially in edge order (same bits as 1 thread) */
+    double *c = (double *)malloc(sizeof(double) * (p->ne > 0 ? p->ne : 1));
+    chi_ctx cx = { p, c };
+    par_for(p->ne, chi_range, &cx);
+    for (int k = 0; k < p->ne; ++k) total += c[k];
+    free(c);
     return total;
 }
 
 /* ---- buildSystem (rows a11, a12, a16) -------------------------------------- */
+/* One edge's linearizeOplus + constructQuadraticForm products (no accumulation):
+ * c = [Hii dd | Hij dd | Hjj dd | bi d | bj d].  Hij is A^T O' B as g2o forms it (row side = vertex(0)). */
+#define CONTRIB_STRIDE (3 * MAXD * MAXD + 2 * MAXD)
+static void edge_contrib(const orc_problem *p, int k, double *c) {
+    const int d = p->d, dd = d * d, ed = p->est_dim;
+    const int vi = p->ev0[k], vj = p->ev1[k];
+    const int hi = p->hidx[vi], hj = p->hidx[vj];
+    if (hi < 0 && hj < 0) return;
+    const double *xi = p->est + (size_t)vi * ed, *xj = p->est + (size_t)vj * ed;
+    double e[MAXD], A[MAXD * MAXD], B[MAXD * MAXD], Oe[MAXD], AtO[MAXD * MAXD], BtO[MAXD * MAXD];
+    double *Hii = c, *Hij = c + dd, *Hjj = c + 2 * dd, *bi = c + 3 * dd, *bj = c + 3 * dd + d;
+    edge_error(p, k, xi, xj, e);
+    edge_jacobians(p, k, xi, xj, hi >= 0, hj >= 0, A, B);
+    const double *O = p->info ? p->info + (size_t)k * dd : 0;
+    double w = 1.0;
+    if (p->robust_kind != ORC_ROBUST_NONE) {
+        double rho[3];
+        orc_robustify(p->robust_kind, p->robust_param, edge_chi2(p, k, e), rho);
+        w = rho[1];
+    }
+    for (int i = 0; i < d; ++i) { /* omega_r = -rho1 * Omega e */
+        double acc = 0;
+        if (O) for (int j = 0; j < d; ++j) acc += O[i * d + j] * e[j]; else acc = e[i];
+        Oe[i] = -w * acc;
+    }
+    if (hi >= 0) {
+        for (int r = 0; r < d; ++r)
+            for (int cc = 0; cc < d; ++cc) {
+                double acc = 0;
+                if (O) for (int t = 0; t < d; ++t) acc += A[t * d + r] * O[t * d + cc]; else acc = A[cc * d + r];
+                AtO[r * d + cc] = w * acc;
+            }
+        for (int r = 0; r < d; ++r) { double acc = 0; for (int t = 0; t < d; ++t) acc += A[t * d + r] * Oe[t]; bi[r] = acc; }
+        for (int r = 0; r < d; ++r)
+            for (int cc = 0; cc < d; ++cc) { double acc = 0; for (int t = 0; t < d; ++t) acc += AtO[r * d + t] * A[t * d + cc]; Hii[r * d + cc] = acc; }
+        if (hj >= 0)
+            for (int r = 0; r < d; ++r)
+                for (int cc = 0; cc < d; ++cc) { double acc = 0; for (int t = 0; t < d; ++t) acc += AtO[r * d + t] * B[t * d + cc]; Hij[r * d + cc] = acc; }
+    }
+    if (hj >= 0) {
+        for (int r = 0; r < d; ++r)
+            for (int cc = 0; cc < d; ++cc) {
+                double acc = 0;
+                if (O) for (int t = 0; t < d; ++t) acc += B[t * d + r] * O[t * d + cc]; else acc = B[cc * d + r];
+                BtO[r * d + cc] = w * acc;
+            }
+        for (int r = 0; r < d; ++r) { double acc = 0; for (int t = 0; t < d; ++t) acc += B[t * d + r] * Oe[t]; bj[r] = acc; }
+        for (int r = 0; r < d; ++r)
+            for (int cc = 0; cc < d; ++cc) { double acc = 0; for (int t = 0; t < d; ++t) acc += BtO[r * d + t] * B[t * d + cc]; Hjj[r * d + cc] = acc; }
+    }
+}
+
+typedef struct { const orc_problem *p; double *buf; int k0; } lin_ctx;
+static void lin_range(void *ctx, int lo, int hi) {
+    lin_ctx *c = (lin_ctx *)ctx;
+    for (int k = lo; k < hi; ++k) edge_contrib(c->p, c->k0 + k, c->buf + (size_t)k * CONTRIB_STRIDE);
+}
+
+/* The per-edge products are independent (g2o's optional OpenMP build parallelises exactly this loop);
+ * the accumulation into H and b stays serial and in edge order, so the sums are the same bits for any
+ * thread count. */
 void orc_linearize(orc_problem *p) {
     if (!p->built) orc_build_structure(p);
-    const int d = p->d, dd = d * d, ed = p->est_dim;
+    const int d = p->d, dd = d * d;
     memset(p->H, 0, sizeof(double) * (size_t)p->nblocks * dd);
     memset(p->b, 0, sizeof(double) * (size_t)p->nfree * d);
-    for (int k = 0; k < p->ne; ++k) {
-        const int vi = p->ev0[k], vj = p->ev1[k];
-        const int hi = p->hidx[vi], hj = p->hidx[vj];
-        if (hi < 0 && hj < 0) continue;
-        const double *xi = p->est + (size_t)vi * ed, *xj = p->est + (size_t)vj * ed;
-        double e[MAXD], A[MAXD * MAXD], B[MAXD * MAXD], Oe[MAXD], AtO[MAXD * MAXD], BtO[MAXD * MAXD];
-        edge_error(p, k, xi, xj, e);
-        edge_jacobians(p, k, xi, xj, hi >= 0, hj >= 0, A, B);
-        const double *O = p->info ? p->info + (size_t)k * dd : 0;
-        double w = 1.0;
-        if (p->robust_kind != ORC_ROBUST_NONE) {
-            double rho[3];
-            orc_robustify(p->robust_kind, p->robust_param, edge_chi2(p, k, e), rho);
-            w = rho[1];
-        }
-        for (int i = 0; i < d; ++i) { /* omega_r = -rho1 * Omega e */
-            double acc = 0;
-            if (O) for (int j = 0; j < d; ++j) acc += O[i * d + j] * e[j]; else acc = e[i];
-            Oe[i] = -w * acc;
-        }
-        if (hi >= 0) {
-            for (int r = 0; r < d; ++r)
-                for (int c = 0; c < d; ++c) {
-                    double acc = 0;
-                    if (O) for (int t = 0; t < d; ++t) acc += A[t * d + r] * O[t * d + c]; else acc = A[c * d + r];
-                    AtO[r * d + c] = w * acc;
-                }
-            double *bi = p->b + (size_t)hi * d;
-            for (int r = 0; r < d; ++r) { double acc = 0; for (int t = 0; t < d; ++t) acc += A[t * d + r] * Oe[t]; bi[r] += acc; }
-            double *Hii = p->H + (size_t)p->diag_slot[hi] * dd;
-            for (int r = 0; r < d; ++r)
-                for (int c = 0; c < d; ++c) { double acc = 0; for (int t = 0; t < d; ++t) acc += AtO[r * d + t] * A[t * d + c]; Hii[r * d + c] += acc; }
-            if (hj >= 0) {
-                double *Hij = p->H + (size_t)p->e_slot[k] * dd;
-                if (hi < hj) {
-                    for (int r = 0; r < d; ++r)
-                        for (int c = 0; c < d; ++c) { double acc = 0; for (int t = 0; t < d; ++t) acc += AtO[r * d + t] * B[t * d + c]; Hij[r * d + c] += acc; }
-                } else { /* _hessianRowMajor: the stored block is (hj,hi) = (A^T O B)^T */
-                    for (int r = 0; r < d; ++r)
-                        for (int c = 0; c < d; ++c) { double acc = 0; for (int t = 0; t < d; ++t) acc += AtO[r * d + t] * B[t * d + c]; Hij[c * d + r] += acc; }
+    enum { CHUNK = 16384 };
+    double *buf = (double *)malloc(sizeof(double) * CHUNK * CONTRIB_STRIDE);
+    for (int k0 = 0; k0 < p->ne; k0 += CHUNK) {
+        const int k1 = k0 + CHUNK < p->ne ? k0 + CHUNK : p->ne;
+        lin_ctx lc = { p, buf, k0 };
+        par_for(k1 - k0, lin_range, &lc);
+        for (int k = k0; k < k1; ++k) {
+            const int hi = p->hidx[p->ev0[k]], hj = p->hidx[p->ev1[k]];
+            if (hi < 0 && hj < 0) continue;
+            const double *c = buf + (size_t)(k - k0) * CONTRIB_STRIDE;
+            if (hi >= 0) {
+                double *bi = p->b + (size_t)hi * d, *Hii = p->H + (size_t)p->diag_slot[hi] * dd;
+                for (int r = 0; r < d; ++r) bi[r] += c[3 * dd + r];
+                for (int t = 0; t < dd; ++t) Hii[t] += c[t];
+                if (hj >= 0) {
+                    double *Hij = p->H + (size_t)p->e_slot[k] * dd;
+                    if (hi < hj) { for (int t = 0; t < dd; ++t) Hij[t] += c[dd + t]; }
+                    else { /* _hessianRowMajor: the stored block is (hj,hi) = (A^T O B)^T */
+                        for (int r = 0; r < d; ++r)
+                            for (int cc = 0; cc < d; ++cc) Hij[cc * d + r] += c[dd + r * d + cc];
+                    }
                 }
             }
-        }
-        if (hj >= 0) {
-            for (int r = 0; r < d; ++r)
-                for (int c = 0; c < d; ++c) {
-                    double acc = 0;
-                    if (O) for (int t = 0; t < d; ++t) acc += B[t * d + r] * O[t * d + c]; else acc = B[c * d + r];
-                    BtO[r * d + c] = w * acc;
-                }
-            double *bj = p->b + (size_t)hj * d;
-            for (int r = 0; r < d; ++r) { double acc = 0; for (int t = 0; t < d; ++t) acc += B[t * d + r] * Oe[t]; bj[r] += acc; }
-            double *Hjj = p->H + (size_t)p->diag_slot[hj] * dd;
-            for (int r = 0; r < d; ++r)
-                for (int c = 0; c < d; ++c) { double acc = 0; for (int t = 0; t < d; ++t) acc += BtO[r * d + t] * B[t * d + c]; Hjj[r * d + c] += acc; }
+            if (hj >= 0) {
+                double *bj = p->b + (size_t)hj * d, *Hjj = p->H + (size_t)p->diag_slot[hj] * dd;
+                for (int r = 0; r < d; ++r) bj[r] += c[3 * dd + d + r];
+                for (int t = 0; t < dd; ++t) Hjj[t] += c[2 * dd + t];
+            }
         }
     }
+    free(buf);
 }
 
 void orc_get_H(const orc_problem *p, double *blocks) { memcpy(blocks, p->H, sizeof(double) * (size_t)p->nblocks * p->d * p->d); }

@@ -150,6 +150,11 @@ void orc_ba_get_points(const orc_ba *p, double *pts);
 int orc_ba_optimize(orc_ba *p, int max_iter, double stop_rel_gain, double *hist, int hist_cap, double *final_chi2,
                     double *final_lambda);
 
+/* worker threads of the per-edge loops (linearisation, chi2); the sparse LDL^T stays serial like
+ * Eigen::SimplicialLDLT.  Results do not depend on the thread count (sums are taken in edge order). */
+void orc_set_threads(int n);
+int orc_get_threads(void);
+
 /* seconds spent in [linearize, solve, chi2/update] during the last orc_optimize */
 void orc_get_timing(const orc_problem *p, double t[4]);
 

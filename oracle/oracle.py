@@ -72,6 +72,8 @@ def _declare(L):
     L.orc_get_vertices.argtypes = [C.c_void_p, _dp]
     L.orc_optimize.argtypes = [C.c_void_p, C.c_int, C.c_double, _dp, C.c_int, _dp, _dp]
     L.orc_get_timing.argtypes = [C.c_void_p, _dp]
+    L.orc_set_threads.argtypes = [C.c_int]
+    L.orc_get_threads.restype = C.c_int
     for name, n_in in (("orc_sim3_exp", 1), ("orc_sim3_log", 1), ("orc_sim3_inv", 1), ("orc_sim3_adjoint", 1),
                        ("orc_sim3_ad", 1), ("orc_sim3_jl_inv", 1), ("orc_quat_to_rot", 1), ("orc_rot_to_quat", 1),
                        ("orc_roteu2ro", 1), ("orc_se3_exp", 1), ("orc_sim3_mul", 2), ("orc_se3_mul", 2)):
@@ -176,6 +178,15 @@ MATH_REFERENCE, MATH_CORRECTED = 0, 1
 
 def set_math_mode(mode):
     lib().orc_set_math_mode(int(mode))
+
+
+def set_threads(n):
+    """Worker threads of the per-edge loops (1 = the reference's single-threaded behaviour)."""
+    lib().orc_set_threads(int(n))
+
+
+def get_threads():
+    return int(lib().orc_get_threads())
 
 
 def robustify(kind, param, e2):

@@ -25,6 +25,8 @@ class Stats(C.Structure):
         ("n_blocks", C.c_int32), ("dim", C.c_int32),
         ("ms_spmv_sampled", C.c_double), ("n_spmv_sampled", C.c_int64),
         ("multilevel_levels", C.c_int32), ("p2p_halo", C.c_int32),
+        ("direct_solves", C.c_int64), ("direct_levels", C.c_int32), ("direct_blocks", C.c_int32),
+        ("pcg_unconverged", C.c_int64),
     ]
 
 
@@ -48,9 +50,11 @@ SYMBOLS = {
     "s3o_set_lm": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int]),
     "s3o_set_pcg": (C.c_int, [C.c_void_p, C.c_double, C.c_int]),
     "s3o_set_preconditioner": (C.c_int, [C.c_void_p, C.c_int]),
+    "s3o_set_linear_solver": (C.c_int, [C.c_void_p, C.c_int]),
     "s3o_build_structure": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "s3o_host_structure": (C.c_int, [C.c_int, _up, C.c_int, _ip, _ip, C.POINTER(C.c_int), C.POINTER(C.c_int), _ip, _ip, _ip]),
     "s3o_host_multilevel": (C.c_int, [C.c_int, _up, C.c_int, _ip, _ip, C.c_int, C.c_int, C.POINTER(C.c_int), _ip, _ip, _ip]),
+    "s3o_host_direct_plan": (C.c_int, [C.c_int, _up, C.c_int, _ip, _ip, C.c_int64, C.POINTER(C.c_int64), _ip, _ip, _ip, _ip, _ip, _ip, _ip, _ip]),
     "s3o_align_similarity": (C.c_int, [C.c_int, C.c_int, _dp, _dp, C.c_int, _dp, _dp, _dp]),
     "s3o_get_structure": (C.c_int, [C.c_void_p, _ip, _ip]),
     "s3o_get_hessian_index": (C.c_int, [C.c_void_p, _ip]),

@@ -13,6 +13,7 @@ KIND_SIM3, KIND_SCALE_TRANS, KIND_SCALE, KIND_BA = 0, 1, 2, 3
 JAC_NUMERIC, JAC_ANALYTIC = 0, 1
 MATH_REFERENCE, MATH_CORRECTED = 0, 1
 PRECOND_AUTO, PRECOND_BLOCK_JACOBI, PRECOND_MULTILEVEL = 0, 1, 2
+LINSOLVER_AUTO, LINSOLVER_PCG, LINSOLVER_DIRECT = 0, 1, 2
 ROBUST_NONE, ROBUST_HUBER, ROBUST_PTAM_TUKEY, ROBUST_PTAM_CAUCHY, ROBUST_PTAM_HUBER, ROBUST_PTAM_LS = range(6)
 
 _EST_DIM = {KIND_SIM3: 8, KIND_SCALE_TRANS: 4, KIND_SCALE: 1, KIND_BA: 7}
@@ -104,6 +105,7 @@ class Problem:
     def set_lm(self, tau=0.0, lambda_init=0.0, max_trials=0): self._check(self.L.s3o_set_lm(self.h, tau, lambda_init, max_trials))
     def set_pcg(self, rel_tol=0.0, max_iter=0): self._check(self.L.s3o_set_pcg(self.h, rel_tol, max_iter))
     def set_preconditioner(self, kind): self._check(self.L.s3o_set_preconditioner(self.h, int(kind)))
+    def set_linear_solver(self, kind): self._check(self.L.s3o_set_linear_solver(self.h, int(kind)))
 
     # ---- structure ---------------------------------------------------------------
     def build_structure(self):
@@ -293,6 +295,33 @@ def host_structure(n_vertices, fixed, v0, v1):
     if rc != 0:
         raise S3OError(f"s3o error {rc}: {L.s3o_last_error().decode()}")
     return colptr[:nf.value + 1].copy(), rowidx[:nb.value].copy(), hidx[:n_vertices].copy()
+
+
+def host_direct_plan(n_vertices, fixed, v0, v1, max_pairs=0):
+    """Factorisation plan of the DIRECT linear solver (host only): dict with perm, lev_ptr, cptr, brow, src,
+    upd_ptr, upd_a, upd_b and the counts n, rounds, n_pairs."""
+    L = _lib.load()
+    v0 = np.ascontiguousarray(v0, np.int32)
+    v1 = np.ascontiguousarray(v1, np.int32)
+    fx = np.zeros(n_vertices, np.uint8) if fixed is None else np.ascontiguousarray(fixed, np.uint8)
+    counts = (C.c_int64 * 5)()
+    null = C.POINTER(C.c_int32)()
+
+    def call(*arrs):
+        rc = L.s3o_host_direct_plan(n_vertices, fx.ctypes.data_as(_up), len(v0), v0.ctypes.data_as(_ip),
+                                    v1.ctypes.data_as(_ip), int(max_pairs), counts, *arrs)
+        if rc != 0:
+            raise S3OError(f"s3o error {rc}: {L.s3o_last_error().decode()}")
+
+    call(*([null] * 8))
+    n, nlev, nL, nupd, pairs = (int(c) for c in counts)
+    out = {"perm": np.zeros(n, np.int32), "lev_ptr": np.zeros(nlev + 1, np.int32), "cptr": np.zeros(n + 1, np.int32),
+           "brow": np.zeros(nL, np.int32), "src": np.zeros(nL, np.int32), "upd_ptr": np.zeros(nL + 1, np.int32),
+           "upd_a": np.zeros(max(nupd, 1), np.int32), "upd_b": np.zeros(max(nupd, 1), np.int32)}
+    call(*(out[k].ctypes.data_as(_ip) for k in ("perm", "lev_ptr", "cptr", "brow", "src", "upd_ptr", "upd_a", "upd_b")))
+    out["upd_a"], out["upd_b"] = out["upd_a"][:nupd], out["upd_b"][:nupd]
+    out.update(n=n, rounds=nlev, n_pairs=pairs)
+    return out
 
 
 class BAProblem(Problem):

@@ -1,0 +1,364 @@
+// direct.cu -- numeric sparse block Cholesky + triangular solves on the device (see direct.h).
+//
+// One kernel per LM trial does what LinearSolverEigen::solve [EXT g2o] does per trial (numeric LDL^T of
+// Hpp + lambda I, two triangular solves; reference plug-in site kitti_surf.cpp:553-557):
+//   scatter   L <- permuted (H + lambda I), fill-in blocks zeroed
+//   per level (the independent sets of the multiple-minimum-degree order, direct_host.cpp):
+//     gather  every block of the level's columns subtracts its ordered list of L_ij L_kj^T products
+//     pivot   Cholesky of the level's d x d diagonal blocks, inverse of the triangular factor kept
+//     scale   sub-diagonal blocks of the level's columns times L_kk^-T
+//   forward / backward substitution level by level (8-lane group per block row, shuffles inside the group)
+// Every block has one writer and a fixed summation order: bitwise reproducible.  Small factors (the KITTI-size
+// graphs) run in ONE CTA with __syncthreads between phases -- the whole solve is one launch and no
+// host round trip; larger ones run as a cooperative grid (one CTA per SM) with grid barriers.
+#include <cooperative_groups.h>
+
+#include "direct.h"
+#include "problem.h"
+#include "reduce.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace s3o {
+
+struct DirectDev {
+    int n, nlev, nL;
+    const int32_t *perm, *lev_ptr, *cptr, *brow, *bcol, *src, *upd_ptr, *upd_a, *upd_b, *row_ptr, *row_blk, *row_col;
+    double *L;       // [nL][D*D]
+    double *Linv;    // [n][D*D]   inverse of the lower-triangular pivot factors
+    double *y;       // [n][D]     solve workspace, elimination order
+    int *fail;
+};
+
+struct DirectState {
+    DirectPlan plan;
+    bool analyzed = false, available = false;
+    int32_t *d_perm = nullptr, *d_lev_ptr = nullptr, *d_cptr = nullptr, *d_brow = nullptr, *d_bcol = nullptr, *d_src = nullptr;
+    int32_t *d_upd_ptr = nullptr, *d_upd_a = nullptr, *d_upd_b = nullptr, *d_row_ptr = nullptr, *d_row_blk = nullptr, *d_row_col = nullptr;
+    double *d_L = nullptr, *d_Linv = nullptr, *d_y = nullptr;
+    int *d_fail = nullptr;
+    int coop_grid = 0;          // 0: single CTA
+    bool factored = false;
+};
+
+namespace {
+
+constexpr int kDirectNT = 512;
+
+// loads of data written earlier in the same kernel by other SMs must bypass the (non-coherent) L1
+template <bool COOP> __device__ __forceinline__ double ldw(const double *p) { return COOP ? __ldcg(p) : *p; }
+
+template <bool COOP> __device__ __forceinline__ void phase_sync() {
+    if constexpr (COOP) cg::this_grid().sync();
+    else __syncthreads();
+}
+
+template <int D, bool COOP>
+__global__ void __launch_bounds__(kDirectNT) direct_kernel(DirectDev P, const double *__restrict__ H, double lambda,
+                                                           const double *__restrict__ b, double *__restrict__ x,
+                                                           DevScalars *sc, int do_factor) {
+    constexpr int DD = D * D, GL = GroupLanes<D>::value;
+    const int tid = blockIdx.x * kDirectNT + threadIdx.x, nthreads = gridDim.x * kDirectNT;
+    if (do_factor) {
+        if (tid == 0) *P.fail = 0;
+        // ---- scatter (H + lambda I) into the factor's storage, elimination order
+        for (long long item = tid; item < (long long)P.nL * DD; item += nthreads) {
+            const int t = (int)(item / DD), e = (int)(item - (long long)t * DD);
+            const int r = e / D, c = e - r * D;
+            const int s = P.src[t];
+            double v = 0;
+            if (s >= 0) {
+                const double *Hb = H + (size_t)(s >> 1) * DD;
+                v = (s & 1) ? Hb[c * D + r] : Hb[e];
+            }
+            if (r == c && P.brow[t] == P.bcol[t]) v += lambda;
+            P.L[item] = v;
+        }
+        phase_sync<COOP>();
+        for (int lev = 0; lev < P.nlev; ++lev) {
+            const int c0 = P.lev_ptr[lev], c1 = P.lev_ptr[lev + 1];
+            const int t0 = P.cptr[c0], t1 = P.cptr[c1];
+            // ---- gather: target -= sum L[a] L[b]^T (columns of earlier levels, fixed order)
+            for (int item = tid; item < (t1 - t0) * DD; item += nthreads) {
+                const int t = t0 + item / DD, e = item % DD;
+                const int q0 = P.upd_ptr[t], q1 = P.upd_ptr[t + 1];
+                if (q0 == q1) continue;
+                const int r = e / D, c = e - r * D;
+                double acc = ldw<COOP>(P.L + (size_t)t * DD + e);
+                for (int q = q0; q < q1; ++q) {
+                    const double *La = P.L + (size_t)P.upd_a[q] * DD + r * D;
+                    const double *Lb = P.L + (size_t)P.upd_b[q] * DD + c * D;
+                    double s = 0;
+#pragma unroll
+                    for (int m = 0; m < D; ++m) s += ldw<COOP>(La + m) * ldw<COOP>(Lb + m);
+                    acc -= s;
+                }
+                P.L[(size_t)t * DD + e] = acc;
+            }
+            phase_sync<COOP>();
+            // ---- pivots: lower Cholesky of the diagonal blocks and the inverse of the factor
+            for (int k = c0 + tid; k < c1; k += nthreads) {
+                double A[DD], Li[DD];
+                double *Ld = P.L + (size_t)P.cptr[k] * DD;
+#pragma unroll
+                for (int i = 0; i < DD; ++i) A[i] = ldw<COOP>(Ld + i);
+                bool ok = true;
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    double djj = A[j * D + j];
+#pragma unroll
+                    for (int m = 0; m < j; ++m) djj -= A[j * D + m] * A[j * D + m];
+                    if (!(djj > 0) || !isfinite(djj)) { ok = false; djj = 1; }
+                    const double ljj = sqrt(djj), inv = 1.0 / ljj;
+                    A[j * D + j] = ljj;
+#pragma unroll
+                    for (int r = j + 1; r < D; ++r) {
+                        double v = A[r * D + j];
+#pragma unroll
+                        for (int m = 0; m < j; ++m) v -= A[r * D + m] * A[j * D + m];
+                        A[r * D + j] = v * inv;
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < D; ++c)
+#pragma unroll
+                    for (int r = 0; r < D; ++r) {
+                        if (r < c) { Li[r * D + c] = 0; continue; }
+                        double v = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+                        for (int m = c; m < r; ++m) v -= A[r * D + m] * Li[m * D + c];
+                        Li[r * D + c] = v / A[r * D + r];
+                    }
+#pragma unroll
+                for (int r = 0; r < D; ++r)
+#pragma unroll
+                    for (int c = 0; c < D; ++c) {
+                        Ld[r * D + c] = c <= r ? A[r * D + c] : 0.0;
+                        P.Linv[(size_t)k * DD + r * D + c] = Li[r * D + c];
+                    }
+                if (!ok) *P.fail = 1;
+            }
+            phase_sync<COOP>();
+            // ---- scale: L_ik = A_ik L_kk^-T, one thread per block row (rows are independent)
+            for (int item = tid; item < (t1 - t0) * D; item += nthreads) {
+                const int t = t0 + item / D, r = item % D;
+                const int k = P.bcol[t];
+                if (P.brow[t] == k) continue;
+                double a[D];
+                double *row = P.L + (size_t)t * DD + r * D;
+                const double *Li = P.Linv + (size_t)k * DD;
+#pragma unroll
+                for (int m = 0; m < D; ++m) a[m] = ldw<COOP>(row + m);
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    double s = 0;
+#pragma unroll
+                    for (int m = 0; m <= c; ++m) s += a[m] * ldw<COOP>(Li + c * D + m);
+                    row[c] = s;
+                }
+            }
+            phase_sync<COOP>();
+        }
+    }
+    // ---- forward substitution  y = L^-1 P b   (GL-lane group per block row)
+    const int group = tid / GL, lane = tid % GL, ngroups = nthreads / GL;
+    for (int lev = 0; lev < P.nlev; ++lev) {
+        const int c0 = P.lev_ptr[lev], c1 = P.lev_ptr[lev + 1];
+        for (int kb = c0; kb < c1; kb += ngroups) {       // uniform trip count: the shuffles below stay convergent
+            const int k = kb + group;
+            const bool act = k < c1 && lane < D;
+            double acc = 0;
+            if (act) {
+                acc = b[(size_t)P.perm[k] * D + lane];
+                for (int q = P.row_ptr[k]; q < P.row_ptr[k + 1]; ++q) {
+                    const double *Lt = P.L + (size_t)P.row_blk[q] * DD + lane * D;
+                    const double *yj = P.y + (size_t)P.row_col[q] * D;
+                    double s = 0;
+#pragma unroll
+                    for (int m = 0; m < D; ++m) s += ldw<COOP>(Lt + m) * ldw<COOP>(yj + m);
+                    acc -= s;
+                }
+            }
+            double yl = 0;
+#pragma unroll
+            for (int m = 0; m < D; ++m) {
+                const double am = __shfl_sync(0xffffffffu, acc, m, GL);
+                if (act && m <= lane) yl += ldw<COOP>(P.Linv + (size_t)k * DD + lane * D + m) * am;
+            }
+            if (act) P.y[(size_t)k * D + lane] = yl;
+        }
+        phase_sync<COOP>();
+    }
+    // ---- backward substitution  x = P^T L^-T y
+    for (int lev = P.nlev - 1; lev >= 0; --lev) {
+        const int c0 = P.lev_ptr[lev], c1 = P.lev_ptr[lev + 1];
+        for (int kb = c0; kb < c1; kb += ngroups) {
+            const int k = kb + group;
+            const bool act = k < c1 && lane < D;
+            double acc = 0;
+            if (act) {
+                acc = ldw<COOP>(P.y + (size_t)k * D + lane);
+                for (int t = P.cptr[k] + 1; t < P.cptr[k + 1]; ++t) {
+                    const double *Lt = P.L + (size_t)t * DD + lane;
+                    const double *xi = P.y + (size_t)P.brow[t] * D;
+                    double s = 0;
+#pragma unroll
+                    for (int m = 0; m < D; ++m) s += ldw<COOP>(Lt + m * D) * ldw<COOP>(xi + m);
+                    acc -= s;
+                }
+            }
+            double xl = 0;
+#pragma unroll
+            for (int m = 0; m < D; ++m) {
+                const double am = __shfl_sync(0xffffffffu, acc, m, GL);
+                if (act && m >= lane) xl += ldw<COOP>(P.Linv + (size_t)k * DD + m * D + lane) * am;
+            }
+            if (act) {
+                P.y[(size_t)k * D + lane] = xl;
+                x[(size_t)P.perm[k] * D + lane] = xl;
+            }
+        }
+        phase_sync<COOP>();
+    }
+    if (tid == 0) {     // the PCG bookkeeping the LM driver reads: an exact solve, 0 iterations
+        const int failed = *reinterpret_cast<volatile int *>(P.fail);
+        sc->done = failed ? 3 : 1;
+        sc->iters = 0;
+        sc->rr = 0;
+        sc->rr0 = 1;
+    }
+}
+
+template <class T>
+int up(s3o_problem *p, T **dst, const std::vector<T> &src) { return upload(p, dst, src); }
+
+void free_direct_arrays(DirectState *D) {
+    dev_free(D->d_perm); dev_free(D->d_lev_ptr); dev_free(D->d_cptr); dev_free(D->d_brow); dev_free(D->d_bcol); dev_free(D->d_src);
+    dev_free(D->d_upd_ptr); dev_free(D->d_upd_a); dev_free(D->d_upd_b); dev_free(D->d_row_ptr); dev_free(D->d_row_blk);
+    dev_free(D->d_row_col); dev_free(D->d_L); dev_free(D->d_Linv); dev_free(D->d_y); dev_free(D->d_fail);
+}
+
+template <int D>
+int launch_direct(s3o_problem *p, const DirectDev &P, double lambda, int do_factor) {
+    DirectState *S = p->direct;
+    if (S->coop_grid <= 0) {
+        direct_kernel<D, false><<<1, kDirectNT, 0, p->stream>>>(P, p->d_H, lambda, p->d_b, p->d_x, p->d_sc, do_factor);
+        return S3O_OK;
+    }
+    const double *H = p->d_H, *b = p->d_b;
+    double *x = p->d_x;
+    DevScalars *sc = p->d_sc;
+    DirectDev Pc = P;
+    void *args[] = { &Pc, &H, &lambda, &b, &x, &sc, &do_factor };
+    S3O_CUDA(cudaLaunchCooperativeKernel((void *)direct_kernel<D, true>, dim3(S->coop_grid), dim3(kDirectNT), args, 0, p->stream));
+    return S3O_OK;
+}
+
+template <int D>
+int coop_capacity(int device) {
+    int per_sm = 0, sms = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, direct_kernel<D, true>, kDirectNT, 0) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
+    return per_sm > 0 ? sms : 0;      // one CTA per SM
+}
+
+}  // namespace
+
+void direct_destroy(s3o_problem *p) {
+    if (!p->direct) return;
+    free_direct_arrays(p->direct);
+    delete p->direct;
+    p->direct = nullptr;
+}
+
+// Block products above which the AUTO rule stays with PCG / above which the analysis is abandoned.
+static constexpr long long kAutoMaxPairs = 400000, kForcedMaxPairs = 60000000;
+static constexpr int kAutoMaxLevels = 64;
+
+// Symbolic analysis + upload, once per structure.  Returns S3O_OK also when the factor is too large
+// (direct_available() then says no).
+int direct_setup(s3o_problem *p) {
+    if (p->direct && p->direct->analyzed) return S3O_OK;
+    if (!p->direct) p->direct = new DirectState();
+    DirectState *D = p->direct;
+    D->analyzed = true;
+    D->available = false;
+    if (p->dist || p->S.nf == 0) return S3O_OK;
+    const bool forced = p->linsolver == S3O_LINSOLVER_DIRECT;
+    if (!direct_analyze(p->S.nf, p->S.rowptr, p->S.colidx, forced ? kForcedMaxPairs : kAutoMaxPairs, D->plan)) return S3O_OK;
+    const DirectPlan &P = D->plan;
+    if (!forced && P.nlev > kAutoMaxLevels) return S3O_OK;
+    const int nL = (int)P.brow.size(), d = p->d;
+    std::vector<int32_t> bcol(nL);
+    for (int j = 0; j < P.n; ++j)
+        for (int t = P.cptr[j]; t < P.cptr[j + 1]; ++t) bcol[t] = j;
+    int rc = 0;
+    rc = rc ? rc : up(p, &D->d_perm, P.perm);
+    rc = rc ? rc : up(p, &D->d_lev_ptr, P.lev_ptr);
+    rc = rc ? rc : up(p, &D->d_cptr, P.cptr);
+    rc = rc ? rc : up(p, &D->d_brow, P.brow);
+    rc = rc ? rc : up(p, &D->d_bcol, bcol);
+    rc = rc ? rc : up(p, &D->d_src, P.src);
+    rc = rc ? rc : up(p, &D->d_upd_ptr, P.upd_ptr);
+    rc = rc ? rc : up(p, &D->d_upd_a, P.upd_a);
+    rc = rc ? rc : up(p, &D->d_upd_b, P.upd_b);
+    rc = rc ? rc : up(p, &D->d_row_ptr, P.row_ptr);
+    rc = rc ? rc : up(p, &D->d_row_blk, P.row_blk);
+    rc = rc ? rc : up(p, &D->d_row_col, P.row_col);
+    rc = rc ? rc : dev_alloc(&D->d_L, (size_t)nL * d * d);
+    rc = rc ? rc : dev_alloc(&D->d_Linv, (size_t)P.n * d * d);
+    rc = rc ? rc : dev_alloc(&D->d_y, (size_t)P.n * d);
+    rc = rc ? rc : dev_alloc(&D->d_fail, 1);
+    if (rc) { free_direct_arrays(D); return rc; }
+    S3O_CUDA(cudaStreamSynchronize(p->stream));
+    // one CTA while the whole factorisation is a few thousand block products (latency-bound: CTA barriers are
+    // ~10x cheaper than grid barriers); a cooperative grid beyond that
+    D->coop_grid = 0;
+    if (P.n_pairs > 20000) {
+        int cap = 0;
+        switch (d) {
+        case 7: cap = coop_capacity<7>(p->device); break;
+        case 6: cap = coop_capacity<6>(p->device); break;
+        case 4: cap = coop_capacity<4>(p->device); break;
+        case 1: cap = coop_capacity<1>(p->device); break;
+        }
+        D->coop_grid = cap;
+    }
+    D->available = true;
+    D->factored = false;
+    p->stats.direct_levels = P.nlev;
+    p->stats.direct_blocks = nL;
+    return S3O_OK;
+}
+
+bool direct_available(const s3o_problem *p) { return p->direct && p->direct->available; }
+void direct_invalidate(s3o_problem *p) { if (p->direct) p->direct->factored = false; }
+
+// Solve (H + lambda I) x = b exactly: numeric factorisation (skipped when reuse_factor and a factor of the
+// same system is still held) + both triangular solves, one launch.  x in p->d_x; status through DevScalars.
+int direct_solve(s3o_problem *p, double lambda, bool reuse_factor) {
+    DirectState *D = p->direct;
+    if (!D || !D->available) { set_error("direct_solve: no factorisation plan"); return S3O_ERR_INVALID; }
+    const DirectPlan &Pl = D->plan;
+    DirectDev P{};
+    P.n = Pl.n; P.nlev = Pl.nlev; P.nL = (int)Pl.brow.size();
+    P.perm = D->d_perm; P.lev_ptr = D->d_lev_ptr; P.cptr = D->d_cptr; P.brow = D->d_brow; P.bcol = D->d_bcol; P.src = D->d_src;
+    P.upd_ptr = D->d_upd_ptr; P.upd_a = D->d_upd_a; P.upd_b = D->d_upd_b;
+    P.row_ptr = D->d_row_ptr; P.row_blk = D->d_row_blk; P.row_col = D->d_row_col;
+    P.L = D->d_L; P.Linv = D->d_Linv; P.y = D->d_y; P.fail = D->d_fail;
+    const int do_factor = (reuse_factor && D->factored) ? 0 : 1;
+    int rc = S3O_OK;
+    switch (p->d) {
+    case 7: rc = launch_direct<7>(p, P, lambda, do_factor); break;
+    case 6: rc = launch_direct<6>(p, P, lambda, do_factor); break;
+    case 4: rc = launch_direct<4>(p, P, lambda, do_factor); break;
+    case 1: rc = launch_direct<1>(p, P, lambda, do_factor); break;
+    default: set_error("direct_solve: block dimension %d", p->d); return S3O_ERR_UNSUPPORTED;
+    }
+    if (rc) return rc;
+    D->factored = true;
+    p->stats.direct_solves += 1;
+    return check_launch(p, 1);
+}
+
+}  // namespace s3o

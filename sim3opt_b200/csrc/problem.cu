@@ -19,6 +19,7 @@
 
 #include "problem.h"
 #include "amg.h"
+#include "direct.h"
 
 namespace s3o {
 
@@ -55,7 +56,8 @@ GraphDev graph_view(const s3o_problem *p, int which) {
 
 namespace s3o {
 
-// undo setup_p2p: unmap the peers' memory before the vectors they alias on the other side go away
+// undo setup_p2p: unmap the peers' memory (free_structure then synchronises the ranks before any exported
+// vector is freed)
 void close_p2p(s3o_problem *p) {
     for (void *m : p->ipc_mapped) cudaIpcCloseMemHandle(m);
     p->ipc_mapped.clear();
@@ -78,6 +80,18 @@ StructDev struct_view(const s3o_problem *p) {
 }
 
 void free_structure(s3o_problem *p) {
+    // Peer-to-peer halo: unmap the neighbours' vectors FIRST, then meet every rank at a barrier, and only then
+    // free the vector the neighbours had mapped (cudaFree of an exported allocation before the importers'
+    // cudaIpcCloseMemHandle is undefined behaviour).  free_structure is reached collectively (s3o_set_vertices /
+    // s3o_set_edges / s3o_set_comm / s3o_destroy are called by every rank), so the barrier matches.
+    if (p->p2p) {
+        if (p->stream) cudaStreamSynchronize(p->stream);
+        close_p2p(p);
+        if (p->dist && p->comm.nccl && p->d_sc) {
+            comm_allreduce_max(p->comm, &p->d_sc->maxdiag, 1, p->stream);
+            cudaStreamSynchronize(p->stream);
+        }
+    }
     dev_free(p->d_hidx); dev_free(p->d_sv0); dev_free(p->d_sv1); dev_free(p->d_meas); dev_free(p->d_info);
     dev_free(p->d_rowptr); dev_free(p->d_colidx); dev_free(p->d_blk_row); dev_free(p->d_blk_ebeg);
     dev_free(p->d_blk_eend); dev_free(p->d_colT_ptr); dev_free(p->d_colT_blk); dev_free(p->d_inc_ptr);
@@ -87,6 +101,7 @@ void free_structure(s3o_problem *p) {
     dev_free(p->d_q1); dev_free(p->d_T); dev_free(p->d_Minv); dev_free(p->d_scratch);
     close_p2p(p);
     amg_destroy(p);
+    direct_destroy(p);
     p->auto_multilevel = false;
     p->built = false;
     p->linearized = false;
@@ -173,6 +188,7 @@ int do_linearize(s3o_problem *p) {
     launch_linearize(g, p->jac_mode, p->jac_h, p->d_scratch, p->d_e_blk, p->d_blk_src, p->d_H, p->stream);
     launch_assemble(g, struct_view(p), p->d_scratch, p->d_H, p->d_b, p->stream);
     amg_invalidate_frames(p);
+    direct_invalidate(p);
     p->linearized = true;
     return check_launch(p, 2);
 }
@@ -189,7 +205,26 @@ bool wants_multilevel(const s3o_problem *p) {
 
 // Solve (H + lambda I) x = b; leaves x in d_x.  Returns the PCG status in *status (1 converged,
 // 2 iteration cap, 3 breakdown) and the iteration count.
-int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel_res) {
+int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel_res, bool defer_sync) {
+    if (p->linsolver != S3O_LINSOLVER_PCG) {       // exact solve when the factor is small (direct.cu)
+        int rcd = p->dist ? S3O_OK : direct_setup(p);
+        if (rcd) return rcd;
+        if (direct_available(p)) {
+            if ((rcd = direct_solve(p, lambda, p->reuse_factor))) return rcd;
+            if (status) *status = 0;
+            if (iters) *iters = 0;
+            if (rel_res) *rel_res = 0;
+            if (defer_sync) return S3O_OK;
+            if ((rcd = sync_scalars(p))) return rcd;
+            if (status) *status = p->h_sc->done;
+            return S3O_OK;
+        }
+        if (p->linsolver == S3O_LINSOLVER_DIRECT) {
+            set_error("s3o_set_linear_solver(DIRECT): %s", p->dist ? "not available in the partitioned solve"
+                                                                   : "the factor of this graph is too large; use PCG");
+            return S3O_ERR_UNSUPPORTED;
+        }
+    }
     const int nf = own_rows(p), d = p->d;
     const int dist = p->dist ? 1 : 0;
     const StructDev s = struct_view(p);
@@ -281,6 +316,7 @@ int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel
         if (batch < 64) batch *= 2;
     }
     p->stats.pcg_iterations += p->h_sc->iters;
+    if (p->h_sc->done != 1) p->stats.pcg_unconverged += 1;      // iteration cap or breakdown: the step is inexact
     // AUTO on a small graph: block-Jacobi until a solve turns out to be ill-conditioned (small lambda on
     // a long chain), the multilevel correction from the next solve on
     // (and back once the multilevel solves get so cheap -- large lambda -- that its setup dominates)
@@ -378,6 +414,7 @@ int setup_p2p(s3o_problem *p) {
         flags.push_back((long long *)f);
     }
     cudaGetLastError();
+    if (flags.size() > 32) ok = 0;      // halo_wait_kernel polls one flag per lane of one warp
     // collective decision: 1 only if every rank mapped everything it needs
     double *d_ok = nullptr;
     if ((rc = dev_alloc(&d_ok, 1))) return rc;
@@ -493,7 +530,10 @@ int s3o_comm_unique_id(char *id128) {
 
 int s3o_set_comm(s3o_problem *p, int rank, int world, const char *id128) {
     if (!p || world < 1 || rank < 0 || rank >= world || (world > 1 && !id128)) { set_error("s3o_set_comm: bad arguments"); return S3O_ERR_INVALID; }
-    if (p->kind != S3O_KIND_SIM3 && world > 1) { /* every kind works; kept general */ }
+    if (p->kind == S3O_KIND_BA && world > 1) {
+        set_error("s3o_set_comm: bundle adjustment has no partitioned path (replicas only, SURVEY.md 8e)");
+        return S3O_ERR_UNSUPPORTED;
+    }
     cudaSetDevice(p->device);
     free_structure(p);
     comm_destroy(p->comm);
@@ -700,6 +740,17 @@ int s3o_set_preconditioner(s3o_problem *p, int kind) {
     return S3O_OK;
 }
 
+int s3o_set_linear_solver(s3o_problem *p, int kind) {
+    if (!p) return S3O_ERR_INVALID;
+    if (kind != S3O_LINSOLVER_AUTO && kind != S3O_LINSOLVER_PCG && kind != S3O_LINSOLVER_DIRECT) {
+        set_error("s3o_set_linear_solver: unknown kind %d", kind);
+        return S3O_ERR_INVALID;
+    }
+    if (kind != p->linsolver) direct_destroy(p);     // the AUTO and DIRECT size limits differ: analyse again
+    p->linsolver = kind;
+    return S3O_OK;
+}
+
 int s3o_set_pcg(s3o_problem *p, double rel_tol, int max_iter) {
     if (!p) return S3O_ERR_INVALID;
     if (rel_tol > 0) p->pcg_tol = rel_tol;
@@ -845,6 +896,30 @@ int s3o_host_multilevel(int n_vertices, const uint8_t *fixed, int n_edges, const
         if (level_blocks) level_blocks[l] = (int32_t)lv[l].colidx.size();
     }
     if (aggregate0 && !lv.empty()) memcpy(aggregate0, lv[0].agg.data(), sizeof(int32_t) * S.nf);
+    return S3O_OK;
+}
+
+int s3o_host_direct_plan(int n_vertices, const uint8_t *fixed, int n_edges, const int32_t *v0, const int32_t *v1,
+                         int64_t max_pairs, int64_t *counts, int32_t *perm, int32_t *lev_ptr, int32_t *cptr,
+                         int32_t *brow, int32_t *src, int32_t *upd_ptr, int32_t *upd_a, int32_t *upd_b) {
+    if (n_vertices < 0 || n_edges < 0 || (n_edges > 0 && (!v0 || !v1)) || !counts) { set_error("s3o_host_direct_plan: bad arguments"); return S3O_ERR_INVALID; }
+    for (int k = 0; k < n_edges; ++k)
+        if (v0[k] < 0 || v0[k] >= n_vertices || v1[k] < 0 || v1[k] >= n_vertices || v0[k] == v1[k]) {
+            set_error("s3o_host_direct_plan: edge %d has invalid vertices", k);
+            return S3O_ERR_INVALID;
+        }
+    HostStructure S;
+    build_structure_host(n_vertices, fixed, n_edges, v0, v1, S);
+    s3o::DirectPlan P;
+    if (!s3o::direct_analyze(S.nf, S.rowptr, S.colidx, max_pairs > 0 ? max_pairs : (1ll << 62), P)) {
+        set_error("s3o_host_direct_plan: the factor needs more than %lld block products", (long long)max_pairs);
+        return S3O_ERR_UNSUPPORTED;
+    }
+    counts[0] = P.n; counts[1] = P.nlev; counts[2] = (int64_t)P.brow.size(); counts[3] = (int64_t)P.upd_a.size();
+    counts[4] = P.n_pairs;
+    auto put = [](int32_t *dst, const std::vector<int32_t> &v) { if (dst && !v.empty()) memcpy(dst, v.data(), sizeof(int32_t) * v.size()); };
+    put(perm, P.perm); put(lev_ptr, P.lev_ptr); put(cptr, P.cptr); put(brow, P.brow); put(src, P.src);
+    put(upd_ptr, P.upd_ptr); put(upd_a, P.upd_a); put(upd_b, P.upd_b);
     return S3O_OK;
 }
 
@@ -995,9 +1070,20 @@ int s3o_update(s3o_problem *p, const double *x) {
         p->linearized = false;
         return S3O_OK;
     }
-    const size_t bytes = (size_t)p->S.nf * p->d * sizeof(double);
+    // partitioned solve: x holds this rank's OWNED rows (the first n_own entries of the local numbering); they are
+    // all-gathered so that every rank retracts every vertex from the same global step, exactly like s3o_optimize
+    const double *xfull = p->d_x;
+    const size_t bytes = (size_t)(p->dist ? p->plan.n_own : p->S.nf) * p->d * sizeof(double);
+    if (p->dist) S3O_CUDA(cudaMemsetAsync(p->d_x, 0, (size_t)p->plan.seg * p->d * sizeof(double), p->stream));
     S3O_CUDA(cudaMemcpyAsync(p->d_x, x, bytes, cudaMemcpyHostToDevice, p->stream));
-    launch_retract(graph_view(p, p->cur), p->d_x, p->d_est[p->cur ^ 1], p->stream);
+    if (p->dist) {
+        if (comm_allgather(p->comm, p->d_x, p->d_xg, (size_t)p->plan.seg * p->d, p->stream)) {
+            set_error("%s", comm_last_error());
+            return S3O_ERR_NCCL;
+        }
+        xfull = p->d_xg;
+    }
+    launch_retract(graph_view(p, p->cur), xfull, p->d_est[p->cur ^ 1], p->stream);
     if ((rc = check_launch(p, 1))) return rc;
     S3O_CUDA(cudaStreamSynchronize(p->stream));
     p->cur ^= 1;
@@ -1013,7 +1099,9 @@ int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterat
     int rc = ensure_built(p);
     if (rc) return rc;
     if (iterations) *iterations = -1;
-    if (p->S.nf == 0 || (p->dist && p->plan.nf_global == 0)) { set_error("s3o_optimize: 0 vertices to optimize"); return S3O_ERR_INVALID; }
+    // partitioned solve: decided on the GLOBAL count, so that a rank that happens to own no row still takes part
+    // in every collective of the loop below (zero-sized local work)
+    if (p->dist ? p->plan.nf_global == 0 : p->S.nf == 0) { set_error("s3o_optimize: 0 vertices to optimize"); return S3O_ERR_INVALID; }
     const int nf = own_rows(p), d = p->d;
     const bool resume = p->lm_resume != 0 && p->lm_valid;
     double lambda = resume ? p->lm_lambda : 0, ni = resume ? p->lm_ni : 2, currentChi = resume ? p->lm_chi : 0;
@@ -1047,7 +1135,7 @@ int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterat
             cudaEventRecord(p->ev[3], p->stream);
             int status = 0, iters = 0;
             if (p->kind == S3O_KIND_BA) rc = ba_solve(p, lambda, &status, &iters, nullptr);
-            else rc = do_solve(p, lambda, &status, &iters, nullptr);
+            else rc = do_solve(p, lambda, &status, &iters, nullptr, true);
             if (rc) return rc;
             pcg_total += iters;
             cudaEventRecord(p->ev[4], p->stream);
@@ -1074,6 +1162,7 @@ int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterat
             float ms = 0;
             cudaEventElapsedTime(&ms, p->ev[3], p->ev[4]); p->stats.ms_solve += ms;
             cudaEventElapsedTime(&ms, p->ev[4], p->ev[5]); p->stats.ms_update += ms;
+            if (status == 0) status = p->h_sc->done;     // exact solve: its verdict arrived with this read-back
             double tempChi = p->h_sc->chi2;
             const bool ok2 = status != 3;
             if (!ok2) tempChi = DBL_MAX;
@@ -1171,23 +1260,42 @@ int s3o_smallest_eigenvector(s3o_problem *p, int max_iter, double tol, double *x
         p->stats.kernel_launches += 1;
     }
     // ---- smallest eigenvalue: inverse iteration (d_b holds the normalised iterate)
-    const double shift = 1e-13 * maxdiag;
+    // With the exact solver one factorisation serves every sweep; its shift stays well above the round-off of
+    // a Cholesky factor (H itself is singular: the null vector is what is being computed), which still
+    // contracts the error by shift / lambda_2 per sweep.
+    bool exact = false;
+    if (p->linsolver != S3O_LINSOLVER_PCG) {
+        if ((rc = direct_setup(p))) return rc;
+        exact = direct_available(p);
+    }
+    const double shift = (exact ? 1e-10 : 1e-13) * maxdiag;
     launch_fill_const(n, 1.0 / std::sqrt((double)n), p->d_b, p->stream);
     double theta = 0, theta_prev = -1;
     int done = 0;
+    p->reuse_factor = true;
     for (int it = 0; it < std::max(max_iter, 1); ++it) {
         int status = 0;
-        if ((rc = do_solve(p, shift, &status, nullptr, nullptr))) return rc;
+        if ((rc = do_solve(p, shift, &status, nullptr, nullptr))) { p->reuse_factor = false; return rc; }
+        if (status == 3) {
+            p->reuse_factor = false;
+            set_error("s3o_smallest_eigenvector: the linear solve of sweep %d broke down", it);
+            return S3O_ERR_INVALID;
+        }
         double yy = 0, xy = 0;
-        if ((rc = dot(p->d_x, p->d_x, &yy)) || (rc = dot(p->d_x, p->d_b, &xy))) return rc;
-        if (!(yy > 0) || !std::isfinite(yy)) { set_error("s3o_smallest_eigenvector: inverse iteration broke down"); return S3O_ERR_INVALID; }
+        if ((rc = dot(p->d_x, p->d_x, &yy)) || (rc = dot(p->d_x, p->d_b, &xy))) { p->reuse_factor = false; return rc; }
+        if (!(yy > 0) || !std::isfinite(yy)) { p->reuse_factor = false; set_error("s3o_smallest_eigenvector: inverse iteration broke down"); return S3O_ERR_INVALID; }
         theta = xy / yy - shift;
         launch_scale_vec(n, p->d_x, 1.0 / std::sqrt(yy), p->d_b, p->stream);
         p->stats.kernel_launches += 1;
         done = it + 1;
-        if (it > 0 && std::fabs(theta - theta_prev) <= tol * std::fabs(theta)) break;
+        // exact sweeps: stop on the change of the Rayleigh quotient measured against the shift (theta itself
+        // is ~0 for a null vector, so a relative test on it never settles)
+        const double ref = exact ? std::max(std::fabs(theta), shift) : std::fabs(theta);
+        if (it > 0 && std::fabs(theta - theta_prev) <= tol * ref) break;
         theta_prev = theta;
     }
+    p->reuse_factor = false;
+    direct_invalidate(p);
     S3O_CUDA(cudaMemcpyAsync(x, p->d_b, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     S3O_CUDA(cudaStreamSynchronize(p->stream));
     p->stats.d2h_bytes += (int64_t)n * 8;

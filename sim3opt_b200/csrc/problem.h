@@ -23,6 +23,7 @@ void dev_free(T *&ptr) {
 
 struct BaState;   // bundle adjustment (ba.cu)
 struct AmgState;  // multilevel preconditioner (amg.cu)
+struct DirectState;  // sparse block Cholesky (direct.cu)
 
 }  // namespace s3o
 
@@ -110,6 +111,10 @@ struct s3o_problem {
     s3o::BaState *ba = nullptr;
     // multilevel preconditioner of the pose-graph PCG (amg.cu), built on first use
     s3o::AmgState *amg = nullptr;
+    // exact solve: sparse block Cholesky on the device (direct.cu), built on first use
+    s3o::DirectState *direct = nullptr;
+    int linsolver = S3O_LINSOLVER_AUTO;     // s3o_set_linear_solver
+    bool reuse_factor = false;              // repeated solves with one matrix (inverse iteration)
 };
 
 namespace s3o {
@@ -132,8 +137,17 @@ int check_launch(s3o_problem *p, int n);
 int sync_scalars(s3o_problem *p);
 int upload_structure_arrays(s3o_problem *p, int rows_own);   // BSR / tile arrays of p->S -> device
 int alloc_linear_system(s3o_problem *p);                      // H, b, x, r, z, p, q1, T, Minv for p->S
-// Solve (H + lambda I) x = b by block-Jacobi PCG on the system held in p->d_H / p->d_b; x in p->d_x
-int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel_res);
+// Solve (H + lambda I) x = b on the system held in p->d_H / p->d_b; x in p->d_x.  Sparse block Cholesky when the
+// factor is small (s3o_set_linear_solver), PCG otherwise.  defer_sync: the exact path does not wait for the
+// device; *status stays 0 and the caller reads DevScalars::done after its own sync_scalars.
+int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel_res, bool defer_sync = false);
+
+// ---- sparse block Cholesky (direct.cu, direct_host.cpp) ---------------------------------------
+int direct_setup(s3o_problem *p);                     // symbolic analysis + upload, once per structure
+bool direct_available(const s3o_problem *p);          // false: the factor would be too large, use PCG
+int direct_solve(s3o_problem *p, double lambda, bool reuse_factor);
+void direct_invalidate(s3o_problem *p);               // H changed
+void direct_destroy(s3o_problem *p);
 
 // ---- multilevel preconditioner (amg.cu) -------------------------------------------------------
 bool wants_multilevel(const s3o_problem *p);
