@@ -255,6 +255,7 @@ typedef struct s3o_stats {
     int32_t direct_levels;     /* elimination rounds of the factorisation plan (0: PCG in use) */
     int32_t direct_blocks;     /* blocks of the factor L */
     int64_t pcg_unconverged;   /* PCG solves that ended on the iteration cap or a breakdown (inexact LM steps) */
+    double sum_ms_linearize, sum_ms_solve, sum_ms_update; /* the per-call phase times above, summed since create / reset */
 } s3o_stats;
 int s3o_get_stats(s3o_problem *p, s3o_stats *out);
 int s3o_reset_stats(s3o_problem *p);

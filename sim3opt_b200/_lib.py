@@ -27,6 +27,7 @@ class Stats(C.Structure):
         ("multilevel_levels", C.c_int32), ("p2p_halo", C.c_int32),
         ("direct_solves", C.c_int64), ("direct_levels", C.c_int32), ("direct_blocks", C.c_int32),
         ("pcg_unconverged", C.c_int64),
+        ("sum_ms_linearize", C.c_double), ("sum_ms_solve", C.c_double), ("sum_ms_update", C.c_double),
     ]
 
 

@@ -1160,8 +1160,8 @@ int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterat
             cudaEventRecord(p->ev[5], p->stream);
             if ((rc = sync_scalars(p))) return rc;
             float ms = 0;
-            cudaEventElapsedTime(&ms, p->ev[3], p->ev[4]); p->stats.ms_solve += ms;
-            cudaEventElapsedTime(&ms, p->ev[4], p->ev[5]); p->stats.ms_update += ms;
+            cudaEventElapsedTime(&ms, p->ev[3], p->ev[4]); p->stats.ms_solve += ms; p->stats.sum_ms_solve += ms;
+            cudaEventElapsedTime(&ms, p->ev[4], p->ev[5]); p->stats.ms_update += ms; p->stats.sum_ms_update += ms;
             if (status == 0) status = p->h_sc->done;     // exact solve: its verdict arrived with this read-back
             double tempChi = p->h_sc->chi2;
             const bool ok2 = status != 3;
@@ -1189,6 +1189,7 @@ int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterat
             float ms = 0;
             cudaEventElapsedTime(&ms, p->ev[1], p->ev[2]);
             p->stats.ms_linearize += ms;
+            p->stats.sum_ms_linearize += ms;
         }
         done = it + 1;
         p->stats.lm_iterations++;

@@ -86,7 +86,8 @@ def test_direct_end_to_end_tolerances(sphere_small):
         n_c, chi_c, _, hist_c = cpu.optimize(40)
     finally:
         orc.set_math_mode(orc.MATH_REFERENCE)
-    assert n_g == n_c
+    # both runs stop on g2o's Terminate (10 failed trials at the fp64 floor); which iteration that is depends on round-off
+    assert abs(n_g - n_c) <= 5
     assert abs(chi_g - chi_c) <= 1e-9 * chi_c
     vg, vc = gpu.vertices(), cpu.vertices()
     assert np.abs(vg[:, 4:7] - vc[:, 4:7]).max() <= 1e-6
