@@ -69,7 +69,8 @@ enum s3o_math_mode { S3O_MATH_REFERENCE = 0, S3O_MATH_CORRECTED = 1 };
  * scale: s_i/s_root); pose-graph kinds only, also in the partitioned solve (Sim3).  AUTO (default):
  * MULTILEVEL for graphs with >= 20000 free vertices; smaller Sim3 / scale-trans graphs start with
  * BLOCK_JACOBI, switch to MULTILEVEL once a solve has needed more than 256 PCG iterations, and back
- * when a MULTILEVEL solve finishes within 8. */
+ * when a MULTILEVEL solve finishes within 8.  Naming BLOCK_JACOBI or MULTILEVEL also selects the PCG as the linear
+ * solver (s3o_set_linear_solver) unless the caller has chosen one. */
 enum s3o_preconditioner { S3O_PRECOND_AUTO = 0, S3O_PRECOND_BLOCK_JACOBI = 1, S3O_PRECOND_MULTILEVEL = 2 };
 /* Linear solver behind BlockSolver::solve (the LinearSolverEigen slot, kitti_surf.cpp:553-557).  DIRECT: sparse
  * block Cholesky on the device -- symbolic analysis once per structure (multiple-minimum-degree order whose

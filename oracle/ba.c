@@ -409,6 +409,7 @@ void orc_ba_get_points(const orc_ba *p, double *pts) { memcpy(pts, p->pt, sizeof
 /* OptimizationAlgorithmLevenberg::solve inside SparseOptimizer::optimize */
 int orc_ba_optimize(orc_ba *p, int max_iter, double stop_rel_gain, double *hist, int hist_cap, double *final_chi2,
                     double *final_lambda) {
+    if (!p->Hpp) orc_ba_build_structure(p);      /* optimize() without initializeOptimization(): build it here */
     const int n = 6 * p->ncf + 3 * p->npf;
     double *x = (double *)calloc(n + 1, sizeof(double));
     double *cam_bk = (double *)malloc(sizeof(double) * 7 * (p->nc ? p->nc : 1));

@@ -6,6 +6,10 @@
 //                             z = D^-1 r + P0 x_1,  r.z  and the PCG scalar bookkeeping.
 // All sums run in list order (no atomics), so a solve is bitwise reproducible.
 #include <algorithm>
+#include <cstdlib>
+#include <functional>
+
+#include <cooperative_groups.h>
 
 #include "amg.h"
 #include "comm.h"
@@ -31,7 +35,11 @@ struct LevelDev {       // transfer level l -> l+1 plus operator and vectors of 
     int32_t *gal_order = nullptr;
     double *rel = nullptr;      // [13][pad_fine]: R (row-major), t, s of S_i S_root^-1 for every level-l vertex
     double *A = nullptr, *Dinv = nullptr, *r = nullptr, *x = nullptr, *x2 = nullptr, *t = nullptr;
+    double *z1 = nullptr, *q1 = nullptr, *rp = nullptr, *z2 = nullptr;      // K-cycle (two inner conjugate-gradient steps)
 };
+
+// scalars of the two-step inner conjugate-gradient iteration of one K-cycle level (device resident)
+struct KScal { double rho1, alpha1, c1, c2; };
 
 }  // namespace
 
@@ -55,6 +63,12 @@ struct AmgState {
     int32_t *d_unpad_src = nullptr; // [n_1 * 7] position in d_rpad of every entry of r_1
     int32_t *d_scal_pos = nullptr;  // [world] position in d_rpad of every rank's two partial scalars
     size_t r_seg = 0;               // doubles per rank in d_rpad: r_max + 2
+    // K-cycle: the first `kdepth` coarse levels run two inner conjugate-gradient steps preconditioned by the
+    // cycle below them (Notay's K-cycle) instead of one V-cycle visit; every level from `coop_first` down is
+    // walked by ONE cooperative kernel (grid barriers instead of kernel boundaries)
+    int kdepth = 0, coop_first = 0, coop_grid = 0;
+    KScal *d_ks = nullptr;          // [kMaxLevels]
+    double *d_cdots = nullptr;      // [3][coop_grid] partial sums of the cooperative kernel's dot products
 };
 
 namespace {
@@ -591,6 +605,301 @@ amg_tail_kernel(const __grid_constant__ TailParams P, double omega, const DevSca
     }
 }
 
+// ---- K-cycle ---------------------------------------------------------------------------------------
+// A V-cycle over plain aggregates loses a constant factor of the coarse correction at every level (the
+// Galerkin operators of piecewise-rigid transfers are too stiff), so the PCG iteration count grows with the
+// depth of the hierarchy.  On the first `kdepth` coarse levels the coarse problem  A_l x = r  is therefore solved
+// by TWO conjugate-gradient steps preconditioned with the cycle below (Notay's K-cycle), in closed form:
+//   z1 = C(r);          q1 = A z1;  rho1 = z1.q1;  alpha1 = z1.r / rho1;   r' = r - alpha1 q1
+//   z2 = C(r');         q2 = A z2;  gamma = z2.q1; beta = z2.q2;  alpha2 = z2.r'
+//   rho2 = beta - gamma^2 / rho1;   x = (alpha1 - alpha2 gamma / (rho1 rho2)) z1 + (alpha2 / rho2) z2
+// Levels with many rows run as ordinary launches (they are bandwidth-bound and want the whole machine in
+// flight); every level from `coop_first` down is latency-bound and is walked by one cooperative kernel.
+// All reductions are two-stage with a fixed order, so the preconditioner stays bitwise reproducible.
+
+__device__ __forceinline__ void kscal_first(KScal *k, double zq, double zr) {
+    const bool ok = zq > 0 && isfinite(zq);
+    k->rho1 = ok ? zq : 1.0;
+    k->alpha1 = ok ? zr / zq : 0.0;
+    k->c1 = k->alpha1;
+    k->c2 = 0.0;
+}
+__device__ __forceinline__ void kscal_second(KScal *k, double beta, double alpha2, double gamma) {
+    const double rho2 = beta - gamma * gamma / k->rho1;
+    if (rho2 > 0 && isfinite(rho2)) {
+        k->c1 = k->alpha1 - alpha2 * gamma / (k->rho1 * rho2);
+        k->c2 = alpha2 / rho2;
+    } else {        // the second direction adds nothing (or broke down): keep the one-step result
+        k->c1 = k->alpha1;
+        k->c2 = 0.0;
+    }
+}
+
+// q = A z (optional store) and the dot products z.q, z.v1, z.v2 of one K-cycle step; second = 0: first step
+// (v1 = r), second = 1: second step (v1 = r', v2 = q1).  An 8-lane group owns one block row.
+template <int D, int NT>
+__global__ void __launch_bounds__(NT) amg_kdots_kernel(int n, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+                                                       const double *__restrict__ A, const double *__restrict__ z,
+                                                       const double *__restrict__ v1, const double *__restrict__ v2,
+                                                       double *__restrict__ q, double *__restrict__ partials, KScal *ks,
+                                                       int second, DevScalars *sc, int check_done) {
+    __shared__ double sh[32];
+    if (check_done && sc->done) return;
+    const int g0 = blockIdx.x * (NT / 8) + threadIdx.x / 8, l = threadIdx.x & 7, ng = gridDim.x * (NT / 8);
+    double d0 = 0, d1 = 0, d2 = 0;
+    for (int i = g0; i < n; i += ng) {
+        if (l >= D) continue;
+        double acc = 0;
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            const double *zj = z + (size_t)colidx[k] * D;
+            const double *Ak = A + (size_t)k * DD + l * D;
+#pragma unroll
+            for (int c = 0; c < D; ++c) acc += Ak[c] * zj[c];
+        }
+        const double zi = z[(size_t)i * D + l];
+        if (q) q[(size_t)i * D + l] = acc;
+        d0 += zi * acc;
+        d1 += zi * v1[(size_t)i * D + l];
+        if (v2) d2 += zi * v2[(size_t)i * D + l];
+    }
+    const double s0 = block_sum<NT>(d0, sh);
+    const double s1 = block_sum<NT>(d1, sh);
+    const double s2 = block_sum<NT>(d2, sh);
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = s0;
+        partials[kMaxPartials + blockIdx.x] = s1;
+        partials[2 * kMaxPartials + blockIdx.x] = s2;
+    }
+    if (last_block(&sc->counters[7])) {
+        const double t0 = sum_partials<NT>(partials, gridDim.x, sh);
+        const double t1 = sum_partials<NT>(partials + kMaxPartials, gridDim.x, sh);
+        const double t2 = sum_partials<NT>(partials + 2 * kMaxPartials, gridDim.x, sh);
+        if (threadIdx.x == 0) {
+            if (!second) kscal_first(ks, t0, t1);
+            else kscal_second(ks, t0, t1, t2);
+        }
+    }
+}
+
+// out = a - alpha1 q   (mode 0: the residual after the first inner step)
+// out = c1 a + c2 q    (mode 1: the combined correction)
+__global__ void amg_kaxpy_kernel(int n, const double *__restrict__ a, const double *__restrict__ q, double *__restrict__ out,
+                                 const KScal *ks, int mode, const DevScalars *sc, int check_done) {
+    if (check_done && sc->done) return;
+    const double c1 = mode ? ks->c1 : 1.0, c2 = mode ? ks->c2 : -ks->alpha1;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) out[t] = c1 * a[t] + c2 * q[t];
+}
+
+// ---- cooperative kernel: every level from `coop_first` down, K-cycle on the first P.kdepth of them ----
+constexpr int kCoopThreads = 512, kCoopRows = 24000;
+
+struct CoopLevel {
+    int n, pad_fine;
+    const int32_t *rowptr, *colidx, *mem_ptr, *mem_idx, *agg;
+    const double *A, *Dinv, *rel;
+    double *r, *x, *x2, *t, *z1, *q1, *rp, *z2;
+};
+struct CoopParams {
+    int nlev, dense, N, kdepth;
+    const double *inv;
+    double *dots;                 // [3][gridDim.x]
+    CoopLevel lev[kMaxLevels];
+};
+
+// mode 0: out = omega Dinv rin;  1: out = rin - A x;  2: out = x + omega Dinv (rin - A x)
+template <int D, int MODE>
+__device__ __forceinline__ void coop_rows(const CoopLevel &L, const double *rin, const double *x, double *out, double omega,
+                                          int gtid, int nth) {
+    const int groups = nth / 8, g = gtid / 8, l = gtid & 7;
+    for (int base = 0; base < L.n; base += groups) {
+        const int i = base + g;
+        const bool act = i < L.n && l < D;
+        double res = act ? __ldcg(rin + (size_t)i * D + l) : 0.0;
+        if (MODE != 0 && act) {
+            double acc = 0;
+            const int kb = L.rowptr[i], ke = L.rowptr[i + 1];
+            for (int k = kb; k < ke; ++k) {
+                const double *xj = x + (size_t)L.colidx[k] * D;
+                const double *Ak = L.A + (size_t)k * DD + l * D;
+#pragma unroll
+                for (int c = 0; c < D; ++c) acc += Ak[c] * __ldcg(xj + c);
+            }
+            res -= acc;
+        }
+        if (MODE == 1) {
+            if (act) out[(size_t)i * D + l] = res;
+            continue;
+        }
+        double z = 0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            const double rc = __shfl_sync(0xffffffffu, res, c, 8);
+            if (act) z += L.Dinv[(size_t)i * sym_size<D>() + sym_off<D>(l, c)] * rc;
+        }
+        if (act) out[(size_t)i * D + l] = (MODE == 2 ? __ldcg(x + (size_t)i * D + l) : 0.0) + omega * z;
+    }
+}
+
+// dot products of one inner step over the grid: per-CTA partials -> grid barrier -> every CTA adds the
+// partials in the same fixed order (all CTAs obtain identical bits)
+template <int D>
+__device__ __forceinline__ void coop_kdots(const CoopLevel &L, const double *z, const double *v1, const double *v2, double *q,
+                                           double *dots, double out[3], int gtid, int nth, double *sh) {
+    const int groups = nth / 8, g = gtid / 8, l = gtid & 7;
+    double d0 = 0, d1 = 0, d2 = 0;
+    for (int i = g; i < L.n; i += groups) {
+        if (l >= D) continue;
+        double acc = 0;
+        for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k) {
+            const double *zj = z + (size_t)L.colidx[k] * D;
+            const double *Ak = L.A + (size_t)k * DD + l * D;
+#pragma unroll
+            for (int c = 0; c < D; ++c) acc += Ak[c] * __ldcg(zj + c);
+        }
+        const double zi = __ldcg(z + (size_t)i * D + l);
+        if (q) q[(size_t)i * D + l] = acc;
+        d0 += zi * acc;
+        d1 += zi * __ldcg(v1 + (size_t)i * D + l);
+        if (v2) d2 += zi * __ldcg(v2 + (size_t)i * D + l);
+    }
+    const double s0 = block_sum<kCoopThreads>(d0, sh);
+    const double s1 = block_sum<kCoopThreads>(d1, sh);
+    const double s2 = block_sum<kCoopThreads>(d2, sh);
+    const int G = gridDim.x;
+    if (threadIdx.x == 0) { dots[blockIdx.x] = s0; dots[G + blockIdx.x] = s1; dots[2 * G + blockIdx.x] = s2; }
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+    __shared__ double tot[3];
+    if (threadIdx.x < 32) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double v = 0;
+            for (int t = threadIdx.x; t < G; t += 32) v += __ldcg(dots + k * G + t);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+            if (threadIdx.x == 0) tot[k] = v;
+        }
+    }
+    __syncthreads();
+    out[0] = tot[0]; out[1] = tot[1]; out[2] = tot[2];
+    __syncthreads();
+}
+
+template <int D>
+__global__ void __launch_bounds__(kCoopThreads, 1)
+amg_coop_kernel(const __grid_constant__ CoopParams P, double omega, const DevScalars *sc, int check_done) {
+    if (check_done && sc->done) return;       // uniform over the grid: nobody reaches a barrier
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh[32];
+    const int nth = gridDim.x * kCoopThreads, gtid = blockIdx.x * kCoopThreads + threadIdx.x;
+    auto gsync = [&]() { __threadfence(); grid.sync(); };
+    const int last = P.nlev - 1;
+    // explicit recursion state: input residual / output of the cycle in progress at every level, inner step
+    const double *cur_r[kMaxLevels];
+    double *cur_out[kMaxLevels];
+    int step[kMaxLevels];
+    KScal ks[kMaxLevels];
+    int l = 0;
+    cur_r[0] = P.lev[0].r;
+    cur_out[0] = (P.kdepth > 0 && last > 0) ? P.lev[0].z1 : P.lev[0].x2;
+    step[0] = 0;
+    for (;;) {
+        // ---------------- descend: cycle at level l on cur_r[l] -----------------------------------
+        for (;;) {
+            const CoopLevel &L = P.lev[l];
+            if (l == last) {
+                if (P.dense) {
+                    for (int t = gtid; t < P.N; t += nth) {
+                        double acc = 0;
+                        for (int c = 0; c < P.N; ++c) acc += P.inv[(size_t)c * P.N + t] * __ldcg(cur_r[l] + c);
+                        cur_out[l][t] = acc;
+                    }
+                } else {            // no dense inverse: five damped block-Jacobi sweeps (a fixed linear operator)
+                    coop_rows<D, 0>(L, cur_r[l], nullptr, L.x, omega, gtid, nth);
+                    gsync();
+                    coop_rows<D, 2>(L, cur_r[l], L.x, L.t, omega, gtid, nth);
+                    gsync();
+                    coop_rows<D, 2>(L, cur_r[l], L.t, L.x, omega, gtid, nth);
+                    gsync();
+                    coop_rows<D, 2>(L, cur_r[l], L.x, L.t, omega, gtid, nth);
+                    gsync();
+                    coop_rows<D, 2>(L, cur_r[l], L.t, cur_out[l], omega, gtid, nth);
+                }
+                gsync();
+                break;
+            }
+            coop_rows<D, 0>(L, cur_r[l], nullptr, L.x, omega, gtid, nth);
+            gsync();
+            coop_rows<D, 1>(L, cur_r[l], L.x, L.t, omega, gtid, nth);
+            gsync();
+            const CoopLevel &C = P.lev[l + 1];
+            for (int I = gtid; I < C.n; I += nth) {        // r_{l+1} = P^T t
+                double acc[D];
+#pragma unroll
+                for (int c = 0; c < D; ++c) acc[c] = 0;
+                for (int m = C.mem_ptr[I]; m < C.mem_ptr[I + 1]; ++m) {
+                    const int i = C.mem_idx[m];
+                    const Rel S = load_rel(C.rel, C.pad_fine, i);
+                    double w[D], u[D];
+#pragma unroll
+                    for (int c = 0; c < D; ++c) w[c] = __ldcg(L.t + (size_t)i * D + c);
+                    Xf<D>::applyT(S, w, u);
+#pragma unroll
+                    for (int c = 0; c < D; ++c) acc[c] += u[c];
+                }
+#pragma unroll
+                for (int c = 0; c < D; ++c) C.r[(size_t)I * D + c] = acc[c];
+            }
+            gsync();
+            ++l;
+            cur_r[l] = P.lev[l].r;
+            cur_out[l] = (l < P.kdepth && l < last) ? P.lev[l].z1 : P.lev[l].x2;
+            step[l] = 0;
+        }
+        // ---------------- ascend: cur_out[l] holds the result of a cycle at level l ---------------
+        for (;;) {
+            const CoopLevel &L = P.lev[l];
+            if (l < P.kdepth && l < last) {
+                double d[3];
+                if (step[l] == 0) {
+                    coop_kdots<D>(L, L.z1, cur_r[l], nullptr, L.q1, P.dots, d, gtid, nth, sh);
+                    kscal_first(&ks[l], d[0], d[1]);
+                    const double a1 = ks[l].alpha1;
+                    for (int t = gtid; t < L.n * D; t += nth) L.rp[t] = __ldcg(cur_r[l] + t) - a1 * __ldcg(L.q1 + t);
+                    gsync();
+                    step[l] = 1;
+                    cur_r[l] = L.rp;
+                    cur_out[l] = L.z2;
+                    break;                      // second cycle at the same level
+                }
+                coop_kdots<D>(L, L.z2, L.rp, L.q1, nullptr, P.dots, d, gtid, nth, sh);
+                kscal_second(&ks[l], d[0], d[1], d[2]);
+                const double c1 = ks[l].c1, c2 = ks[l].c2;
+                for (int t = gtid; t < L.n * D; t += nth) L.x2[t] = c1 * __ldcg(L.z1 + t) + c2 * __ldcg(L.z2 + t);
+                gsync();
+            }
+            // the solve of level l is complete in L.x2
+            if (l == 0) return;
+            const CoopLevel &F = P.lev[l - 1];
+            for (int i = gtid; i < F.n; i += nth) {        // x_{l-1} += P x_l
+                const Rel S = load_rel(L.rel, L.pad_fine, i);
+                const int I = L.agg[i];
+                double v[D], u[D];
+#pragma unroll
+                for (int c = 0; c < D; ++c) v[c] = __ldcg(L.x2 + (size_t)I * D + c);
+                Xf<D>::apply(S, v, u);
+#pragma unroll
+                for (int c = 0; c < D; ++c) F.x[(size_t)i * D + c] = __ldcg(F.x + (size_t)i * D + c) + u[c];
+            }
+            gsync();
+            --l;
+            coop_rows<D, 2>(F, cur_r[l], F.x, cur_out[l], omega, gtid, nth);
+            gsync();
+        }
+    }
+}
+
 template <class T>
 int up(s3o_problem *p, T **dst, const std::vector<T> &src) { return upload(p, dst, src); }
 
@@ -599,6 +908,7 @@ void free_level(LevelDev &L) {
     dev_free(L.rowptr); dev_free(L.colidx); dev_free(L.blk_row); dev_free(L.dpos);
     dev_free(L.gal_ptr); dev_free(L.gal_ent); dev_free(L.gal_i); dev_free(L.gal_j); dev_free(L.gal_order); dev_free(L.gal_out); dev_free(L.gal_mirror);
     dev_free(L.rel); dev_free(L.A); dev_free(L.Dinv); dev_free(L.r); dev_free(L.x); dev_free(L.x2); dev_free(L.t);
+    dev_free(L.z1); dev_free(L.q1); dev_free(L.rp); dev_free(L.z2);
 }
 
 // Partitioned solve: rewrite level 0 of the global hierarchy in this rank's local indices.
@@ -675,6 +985,8 @@ void amg_destroy(s3o_problem *p) {
     dev_free(p->amg->d_rpad);
     dev_free(p->amg->d_unpad_src);
     dev_free(p->amg->d_scal_pos);
+    dev_free(p->amg->d_ks);
+    dev_free(p->amg->d_cdots);
     delete p->amg;
     p->amg = nullptr;
 }
@@ -736,6 +1048,10 @@ int amg_setup(s3o_problem *p) {
         rc = rc ? rc : dev_alloc(&L.x, (size_t)L.n * D);
         rc = rc ? rc : dev_alloc(&L.x2, (size_t)L.n * D);
         rc = rc ? rc : dev_alloc(&L.t, (size_t)L.n * D);
+        rc = rc ? rc : dev_alloc(&L.z1, (size_t)L.n * D);
+        rc = rc ? rc : dev_alloc(&L.q1, (size_t)L.n * D);
+        rc = rc ? rc : dev_alloc(&L.rp, (size_t)L.n * D);
+        rc = rc ? rc : dev_alloc(&L.z2, (size_t)L.n * D);
     }
     if (!rc && st->dist) {
         const int world = (int)st->r_cnt.size();
@@ -760,6 +1076,27 @@ int amg_setup(s3o_problem *p) {
         if (!rc && ea != cudaSuccess) {
             set_error("amg_setup: cannot reserve %d bytes of shared memory", smem);
             rc = S3O_ERR_CUDA;
+        }
+    }
+    if (!rc) {
+        // K-cycle on the two largest coarse levels of a deep hierarchy (large graphs); shallow ones keep the V-cycle.
+        // S3O_KCYCLE=<levels> overrides (0: V-cycle everywhere).
+        st->kdepth = (nl >= 3 && st->host[0].n_fine >= 20000) ? 2 : 0;
+        if (const char *v = getenv("S3O_KCYCLE")) st->kdepth = std::max(0, std::min(atoi(v), nl - 1));
+        st->coop_first = 0;
+        while (st->coop_first < nl - 1 && st->lev[st->coop_first].n > kCoopRows) ++st->coop_first;
+        if (st->kdepth > 0) {
+            int per_sm = 0, sms = 0;
+            cudaError_t eo = D == 7 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, amg_coop_kernel<7>, kCoopThreads, 0)
+                           : D == 4 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, amg_coop_kernel<4>, kCoopThreads, 0)
+                                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, amg_coop_kernel<1>, kCoopThreads, 0);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+            if (eo != cudaSuccess || per_sm < 1 || sms < 8) st->kdepth = 0;      // no cooperative launch: V-cycle
+            else {
+                st->coop_grid = sms;
+                rc = dev_alloc(&st->d_ks, kMaxLevels);
+                rc = rc ? rc : dev_alloc(&st->d_cdots, (size_t)3 * sms);
+            }
         }
     }
     if (!rc) { cudaError_t e = cudaStreamSynchronize(p->stream); if (e != cudaSuccess) { set_error("amg_setup: %s", cudaGetErrorString(e)); rc = S3O_ERR_CUDA; } }
@@ -866,38 +1203,104 @@ int apply_t(s3o_problem *p, int init) {
             launches += 2;
         }
     }
-    for (int l = 0; l < lt; ++l) {
-        LevelDev &L = st->lev[l];
-        LevelDev &C = st->lev[l + 1];
-        amg_row_kernel<D, 0><<<rows(L.n), 128, 0, s>>>(L.n, L.rowptr, L.colidx, L.A, L.Dinv, L.r, nullptr, L.x, kOmega, sc, chk);
-        amg_row_kernel<D, 1><<<rows(L.n), 128, 0, s>>>(L.n, L.rowptr, L.colidx, L.A, L.Dinv, L.r, L.x, L.t, kOmega, sc, chk);
-        amg_restrict_kernel<D><<<(C.n + 15) / 16, 128, 0, s>>>(C.n, C.mem_ptr, C.mem_idx, C.rel, C.pad_fine, L.t, C.r, sc, chk);
-        launches += 3;
-    }
-    {
-        TailParams P{};
-        P.nlev = nl - lt;
-        P.dense = st->dense ? 1 : 0;
-        P.N = st->lev.back().n * D;
-        P.inv = st->d_dense;
-        for (int l = lt; l < nl; ++l) {
+    if (st->kdepth > 0) {
+        // K-cycle path: levels above coop_first by ordinary launches (host-side recursion), the rest in one
+        // cooperative kernel per visit; the solve of level l leaves its result in lev[l].x2
+        const int nk = st->kdepth;
+        int rc_inner = S3O_OK;
+        auto kgrid = [](int n) { int g = (n + 15) / 16; return g > 148 * 8 ? 148 * 8 : (g < 1 ? 1 : g); };
+        std::function<void(int)> solve;
+        auto cycle = [&](int l, const double *rin, double *xout) {
             LevelDev &L = st->lev[l];
-            TailLevel &T = P.lev[l - lt];
-            T.n = L.n; T.pad_fine = L.pad_fine;
-            T.rowptr = L.rowptr; T.colidx = L.colidx; T.mem_ptr = L.mem_ptr; T.mem_idx = L.mem_idx; T.agg = L.agg;
-            T.A = L.A; T.Dinv = L.Dinv; T.rel = L.rel; T.r = L.r; T.x = L.x; T.x2 = L.x2; T.t = L.t;
+            LevelDev &C = st->lev[l + 1];
+            amg_row_kernel<D, 0><<<rows(L.n), 128, 0, s>>>(L.n, L.rowptr, L.colidx, L.A, L.Dinv, rin, nullptr, L.x, kOmega, sc, chk);
+            amg_row_kernel<D, 1><<<rows(L.n), 128, 0, s>>>(L.n, L.rowptr, L.colidx, L.A, L.Dinv, rin, L.x, L.t, kOmega, sc, chk);
+            amg_restrict_kernel<D><<<(C.n + 15) / 16, 128, 0, s>>>(C.n, C.mem_ptr, C.mem_idx, C.rel, C.pad_fine, L.t, C.r, sc, chk);
+            launches += 3;
+            solve(l + 1);
+            amg_prolong_kernel<D><<<(L.n + 127) / 128, 128, 0, s>>>(L.n, C.agg, C.rel, C.pad_fine, C.x2, L.x, sc, chk);
+            amg_row_kernel<D, 2><<<rows(L.n), 128, 0, s>>>(L.n, L.rowptr, L.colidx, L.A, L.Dinv, rin, L.x, xout, kOmega, sc, chk);
+            launches += 2;
+        };
+        solve = [&](int l) {
+            LevelDev &L = st->lev[l];
+            if (l >= st->coop_first) {
+                CoopParams P{};
+                P.nlev = nl - l;
+                P.dense = st->dense ? 1 : 0;
+                P.N = st->lev.back().n * D;
+                P.inv = st->d_dense;
+                P.kdepth = nk > l ? nk - l : 0;
+                P.dots = st->d_cdots;
+                for (int k = l; k < nl; ++k) {
+                    LevelDev &S = st->lev[k];
+                    CoopLevel &T = P.lev[k - l];
+                    T.n = S.n; T.pad_fine = S.pad_fine;
+                    T.rowptr = S.rowptr; T.colidx = S.colidx; T.mem_ptr = S.mem_ptr; T.mem_idx = S.mem_idx; T.agg = S.agg;
+                    T.A = S.A; T.Dinv = S.Dinv; T.rel = S.rel; T.r = S.r; T.x = S.x; T.x2 = S.x2; T.t = S.t;
+                    T.z1 = S.z1; T.q1 = S.q1; T.rp = S.rp; T.z2 = S.z2;
+                }
+                double omega = kOmega;
+                int chk_ = chk;
+                void *args[] = { &P, &omega, (void *)&sc, &chk_ };
+                int grid = (L.n * 8 + kCoopThreads - 1) / kCoopThreads;
+                grid = std::max(8, std::min(grid, st->coop_grid));
+                if (cudaLaunchCooperativeKernel((void *)amg_coop_kernel<D>, dim3(grid), dim3(kCoopThreads), args, 0, s) != cudaSuccess)
+                    rc_inner = S3O_ERR_CUDA;
+                ++launches;
+                return;
+            }
+            if (l < nk) {
+                KScal *ks = st->d_ks + l;
+                const int n = L.n * D;
+                cycle(l, L.r, L.z1);
+                amg_kdots_kernel<D, 128><<<kgrid(L.n), 128, 0, s>>>(L.n, L.rowptr, L.colidx, L.A, L.z1, L.r, nullptr, L.q1, p->d_partials, ks, 0, p->d_sc, chk);
+                amg_kaxpy_kernel<<<std::min((n + 255) / 256, 148 * 8), 256, 0, s>>>(n, L.r, L.q1, L.rp, ks, 0, sc, chk);
+                cycle(l, L.rp, L.z2);
+                amg_kdots_kernel<D, 128><<<kgrid(L.n), 128, 0, s>>>(L.n, L.rowptr, L.colidx, L.A, L.z2, L.rp, L.q1, nullptr, p->d_partials, ks, 1, p->d_sc, chk);
+                amg_kaxpy_kernel<<<std::min((n + 255) / 256, 148 * 8), 256, 0, s>>>(n, L.z1, L.z2, L.x2, ks, 1, sc, chk);
+                launches += 4;
+            } else {
+                cycle(l, L.r, L.x2);
+            }
+        };
+        solve(0);
+        if (rc_inner) { set_error("multilevel K-cycle: cooperative launch failed: %s", cudaGetErrorString(cudaGetLastError())); return rc_inner; }
+        std::swap(st->lev[0].x, st->lev[0].x2);
+    } else {
+        for (int l = 0; l < lt; ++l) {
+            LevelDev &L = st->lev[l];
+            LevelDev &C = st->lev[l + 1];
+            amg_row_kernel<D, 0><<<rows(L.n), 128, 0, s>>>(L.n, L.rowptr, L.colidx, L.A, L.Dinv, L.r, nullptr, L.x, kOmega, sc, chk);
+            amg_row_kernel<D, 1><<<rows(L.n), 128, 0, s>>>(L.n, L.rowptr, L.colidx, L.A, L.Dinv, L.r, L.x, L.t, kOmega, sc, chk);
+            amg_restrict_kernel<D><<<(C.n + 15) / 16, 128, 0, s>>>(C.n, C.mem_ptr, C.mem_idx, C.rel, C.pad_fine, L.t, C.r, sc, chk);
+            launches += 3;
         }
-        amg_tail_kernel<D><<<kTailCtas, kTailThreads, 0, s>>>(P, kOmega, sc, chk);
-        for (int l = lt; l < nl; ++l) std::swap(st->lev[l].x, st->lev[l].x2);
-        ++launches;
-    }
-    for (int l = lt - 1; l >= 0; --l) {
-        LevelDev &L = st->lev[l];
-        LevelDev &C = st->lev[l + 1];
-        amg_prolong_kernel<D><<<(L.n + 127) / 128, 128, 0, s>>>(L.n, C.agg, C.rel, C.pad_fine, C.x, L.x, sc, chk);
-        amg_row_kernel<D, 2><<<rows(L.n), 128, 0, s>>>(L.n, L.rowptr, L.colidx, L.A, L.Dinv, L.r, L.x, L.x2, kOmega, sc, chk);
-        std::swap(L.x, L.x2);
-        launches += 2;
+        {
+            TailParams P{};
+            P.nlev = nl - lt;
+            P.dense = st->dense ? 1 : 0;
+            P.N = st->lev.back().n * D;
+            P.inv = st->d_dense;
+            for (int l = lt; l < nl; ++l) {
+                LevelDev &L = st->lev[l];
+                TailLevel &T = P.lev[l - lt];
+                T.n = L.n; T.pad_fine = L.pad_fine;
+                T.rowptr = L.rowptr; T.colidx = L.colidx; T.mem_ptr = L.mem_ptr; T.mem_idx = L.mem_idx; T.agg = L.agg;
+                T.A = L.A; T.Dinv = L.Dinv; T.rel = L.rel; T.r = L.r; T.x = L.x; T.x2 = L.x2; T.t = L.t;
+            }
+            amg_tail_kernel<D><<<kTailCtas, kTailThreads, 0, s>>>(P, kOmega, sc, chk);
+            for (int l = lt; l < nl; ++l) std::swap(st->lev[l].x, st->lev[l].x2);
+            ++launches;
+        }
+        for (int l = lt - 1; l >= 0; --l) {
+            LevelDev &L = st->lev[l];
+            LevelDev &C = st->lev[l + 1];
+            amg_prolong_kernel<D><<<(L.n + 127) / 128, 128, 0, s>>>(L.n, C.agg, C.rel, C.pad_fine, C.x, L.x, sc, chk);
+            amg_row_kernel<D, 2><<<rows(L.n), 128, 0, s>>>(L.n, L.rowptr, L.colidx, L.A, L.Dinv, L.r, L.x, L.x2, kOmega, sc, chk);
+            std::swap(L.x, L.x2);
+            launches += 2;
+        }
     }
     {
         LevelDev &L = st->lev[0];

@@ -490,7 +490,7 @@ int s3o_create(int kind, int device, s3o_problem **out) {
     }
     for (auto &ev : p->ev) cudaEventCreate(&ev);
     for (auto &ev : p->spmv_ev) cudaEventCreate(&ev);
-    if (dev_alloc(&p->d_sc, 1) || dev_alloc(&p->d_partials, 2 * kMaxPartials) ||
+    if (dev_alloc(&p->d_sc, 1) || dev_alloc(&p->d_partials, 3 * kMaxPartials) ||
         cudaMallocHost((void **)&p->h_sc, sizeof(DevScalars)) != cudaSuccess) {
         s3o_destroy(p);
         return S3O_ERR_CUDA;
@@ -737,6 +737,8 @@ int s3o_set_preconditioner(s3o_problem *p, int kind) {
         return S3O_ERR_UNSUPPORTED;
     }
     p->precond = kind;
+    // naming a preconditioner asks for the Krylov solver (AUTO leaves the direct / PCG choice to the library)
+    if (kind != S3O_PRECOND_AUTO && p->linsolver == S3O_LINSOLVER_AUTO) p->linsolver = S3O_LINSOLVER_PCG;
     return S3O_OK;
 }
 

@@ -351,21 +351,22 @@ __device__ __forceinline__ void sim3_edge_jacobians(const Sim3 &C, const double 
         Ji[(3 + r) * 7 + 6] = L.y[r] - (L.Wi[r * 3] * C.tx + L.Wi[r * 3 + 1] * C.ty + L.Wi[r * 3 + 2] * C.tz);
     }
     Ji[48] = 1;
-    double me[7];
-#pragma unroll
-    for (int i = 0; i < 7; ++i) me[i] = -e[i];
-    sim3_jl_inv(me, L);
+    // Jj = -Jl^-1(-e).  The odd Bernoulli numbers beyond B_1 vanish, so Jl^-1(-e) = Jl^-1(e) + ad_e exactly:
+    // the second series is not needed.  ad_e = [[Om,0,0],[Up,Om+sigma I,-ups],[0,0,0]].
+    double Om[9], Up[9];
+    skew3(e[0], e[1], e[2], Om);
+    skew3(e[3], e[4], e[5], Up);
 #pragma unroll
     for (int i = 0; i < 49; ++i) Jj[i] = 0;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            Jj[r * 7 + c] = -L.Jw[r * 3 + c];
-            Jj[(3 + r) * 7 + c] = -L.X[r * 3 + c];
-            Jj[(3 + r) * 7 + 3 + c] = -L.Wi[r * 3 + c];
+            Jj[r * 7 + c] = -(L.Jw[r * 3 + c] + Om[r * 3 + c]);
+            Jj[(3 + r) * 7 + c] = -(L.X[r * 3 + c] + Up[r * 3 + c]);
+            Jj[(3 + r) * 7 + 3 + c] = -(L.Wi[r * 3 + c] + Om[r * 3 + c] + (r == c ? e[6] : 0.0));
         }
-        Jj[(3 + r) * 7 + 6] = -L.y[r];
+        Jj[(3 + r) * 7 + 6] = -(L.y[r] - e[3 + r]);
     }
     Jj[48] = -1;
 }

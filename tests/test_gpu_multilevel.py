@@ -125,6 +125,42 @@ def test_scale_null_vector_multilevel(kitti_k118):
     assert np.abs(x - ref).max() <= 1e-6 * np.abs(ref).max()
 
 
+def test_kcycle_fewer_iterations_same_solution():
+    """K-cycle (two inner CG steps on the largest coarse levels, one cooperative kernel for the small ones)
+    against the V-cycle on a 9k-pose sphere at a late-iteration damping: same solution, fewer iterations,
+    bitwise reproducible."""
+    import os
+    import sim3opt_b200 as s3
+    from sim3opt_b200 import synth
+    g = synth.sphere(n_laps=30, poses_per_lap=300, seed=42)
+    res = {}
+    for k in ("0", "1", "2"):
+        os.environ["S3O_KCYCLE"] = k
+        try:
+            gpu = make_gpu(g, jac=1, math_mode=s3.MATH_CORRECTED)
+            gpu.set_preconditioner(s3.PRECOND_MULTILEVEL)
+            gpu.set_pcg(1e-3, 20000)
+            gpu.optimize(4)                                  # a late-iteration linearisation point
+            colptr, rowidx = gpu.build_structure()
+            gpu.linearize_only()
+            lam = 1e-10 * gpu.max_diag()
+            gpu.set_pcg(1e-10, 50000)
+            rc, x, it, rel = gpu.solve(lam)
+            y = gpu.hessian_multiply(lam, x)
+            rc2, x2, it2, _ = gpu.solve(lam)
+        finally:
+            del os.environ["S3O_KCYCLE"]
+        assert rc == 0 and rel <= 1e-10
+        assert it2 == it and np.array_equal(x, x2)
+        res[k] = (x, it, y)
+    b = res["0"][2]
+    for k in ("1", "2"):
+        assert np.linalg.norm(res[k][2] - b) <= 1e-9 * np.linalg.norm(b)          # (H + lambda I) x reproduces the same b
+        assert np.abs(res[k][0] - res["0"][0]).max() <= 1e-4 * np.abs(res["0"][0]).max()
+    assert res["1"][1] < res["0"][1] and res["2"][1] < res["1"][1], {k: v[1] for k, v in res.items()}
+    assert res["2"][1] * 3 <= res["0"][1] * 2, {k: v[1] for k, v in res.items()}
+
+
 def test_multilevel_rejected_for_ba():
     import sim3opt_b200 as s3
     from sim3opt_b200 import synth
