@@ -238,6 +238,24 @@ int s3o_ba_get_system(s3o_problem *p, double *Hpp, double *Hll, double *Hpl, dou
  * order of s3o_get_structure) and bs = bp - sum Hpl (Hll + lambda I)^-1 bl */
 int s3o_ba_get_schur(s3o_problem *p, double lambda, double *blocks, double *bs);
 
+/* ---- LinearSolver-level plug-in: g2o::LinearSolver<M>::{init(), solve(A, x, b)} (the innermost slot of
+ * OptimizationAlgorithmLevenberg(BlockSolverX(LinearSolverEigen)), kitti_surf.cpp:553-557, bal_example.cpp:73-83) ----
+ * For callers that keep g2o's own LM loop and block solver and only swap the linear solver: A is g2o's
+ * SparseBlockMatrix, i.e. an upper block-CCS (colptr[n+1], rowidx[nb], rows ascending, row <= column, every column
+ * with its diagonal block) of d x d blocks, each row-major or (Eigen's default) column-major; b and x are n*d.
+ * Solves (A + lambda I) x = b on the device: sparse block Cholesky when the factor is small (see
+ * s3o_linear_solver), block-Jacobi PCG (s3o_set_pcg on the handle) otherwise.  The handle caches the pattern, the
+ * factorisation plan and all device buffers between calls (LinearSolver::init() once, solve() per LM trial).  The
+ * whole-LM entry s3o_optimize avoids the per-trial PCIe round trip of A, x, b that this cut implies.
+ * Returns S3O_OK, or S3O_RESULT_FAIL when the matrix is not positive definite / the PCG did not converge (g2o:
+ * solve() == false -> the LM raises lambda). */
+typedef struct s3o_problem s3o_linsolver;
+int s3o_linsolver_create(int device, int block_dim /* 1, 4, 6 or 7 */, s3o_linsolver **out);
+int s3o_linsolver_destroy(s3o_linsolver *s);
+int s3o_linsolver_solve(s3o_linsolver *s, int n_block_cols, const int32_t *colptr, const int32_t *rowidx,
+                        const double *blocks, int column_major, double lambda, const double *b, double *x,
+                        int *method /* out, may be NULL: s3o_linear_solver used */, int *pcg_iterations /* may be NULL */);
+
 /* ---- statistics ------------------------------------------------------------------------ */
 typedef struct s3o_stats {
     double ms_linearize, ms_solve, ms_chi2, ms_update, ms_total; /* CUDA-event time, last optimize */

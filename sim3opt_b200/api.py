@@ -297,6 +297,48 @@ def host_structure(n_vertices, fixed, v0, v1):
     return colptr[:nf.value + 1].copy(), rowidx[:nb.value].copy(), hidx[:n_vertices].copy()
 
 
+class LinearSolver:
+    """LinearSolver-level plug-in (s3o_linsolver_*): solve (A + lambda I) x = b for an upper block-CCS matrix, the
+    slot of g2o::LinearSolver<M>::solve(A, x, b) (kitti_surf.cpp:553-557)."""
+
+    def __init__(self, block_dim, device=0):
+        self.L = _lib.load()
+        self.d = int(block_dim)
+        self.h = C.c_void_p()
+        rc = self.L.s3o_linsolver_create(int(device), self.d, C.byref(self.h))
+        if rc != 0:
+            raise S3OError(f"s3o error {rc}: {self.L.s3o_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.s3o_linsolver_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def set_linear_solver(self, kind):
+        if self.L.s3o_set_linear_solver(self.h, int(kind)) != 0:
+            raise S3OError(self.L.s3o_last_error().decode())
+
+    def set_pcg(self, rel_tol=0.0, max_iter=0):
+        self.L.s3o_set_pcg(self.h, rel_tol, max_iter)
+
+    def solve(self, colptr, rowidx, blocks, b, lam=0.0, column_major=False):
+        """Returns (rc, x, method, pcg_iterations); rc 0 ok, -1 not positive definite / not converged."""
+        colptr = np.ascontiguousarray(colptr, np.int32)
+        rowidx = np.ascontiguousarray(rowidx, np.int32)
+        blocks = _f64(blocks)
+        b = _f64(b).reshape(-1)
+        n = len(colptr) - 1
+        x = np.zeros(n * self.d)
+        method, its = C.c_int(0), C.c_int(0)
+        rc = self.L.s3o_linsolver_solve(self.h, n, colptr.ctypes.data_as(_ip), rowidx.ctypes.data_as(_ip), _d(blocks),
+                                        1 if column_major else 0, float(lam), _d(b), _d(x), C.byref(method), C.byref(its))
+        if rc not in (0, -1):
+            raise S3OError(f"s3o error {rc}: {self.L.s3o_last_error().decode()}")
+        return rc, x, method.value, its.value
+
+
 def host_direct_plan(n_vertices, fixed, v0, v1, max_pairs=0):
     """Factorisation plan of the DIRECT linear solver (host only): dict with perm, lev_ptr, cptr, brow, src,
     upd_ptr, upd_a, upd_b and the counts n, rounds, n_pairs."""

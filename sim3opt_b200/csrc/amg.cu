@@ -1081,10 +1081,12 @@ int amg_setup(s3o_problem *p) {
     if (!rc) {
         // K-cycle on the two largest coarse levels of a deep hierarchy (large graphs); shallow ones keep the V-cycle.
         // S3O_KCYCLE=<levels> overrides (0: V-cycle everywhere).
-        st->kdepth = (nl >= 3 && st->host[0].n_fine >= 20000) ? 2 : 0;
+        st->kdepth = (nl >= 3 && st->host[0].n_fine >= 20000) ? 1 : 0;
         if (const char *v = getenv("S3O_KCYCLE")) st->kdepth = std::max(0, std::min(atoi(v), nl - 1));
+        int coop_rows = kCoopRows;
+        if (const char *v = getenv("S3O_COOP_ROWS")) coop_rows = atoi(v);       // experiment switch
         st->coop_first = 0;
-        while (st->coop_first < nl - 1 && st->lev[st->coop_first].n > kCoopRows) ++st->coop_first;
+        while (st->coop_first < nl - 1 && st->lev[st->coop_first].n > coop_rows) ++st->coop_first;
         if (st->kdepth > 0) {
             int per_sm = 0, sms = 0;
             cudaError_t eo = D == 7 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, amg_coop_kernel<7>, kCoopThreads, 0)

@@ -199,7 +199,7 @@ namespace s3o {
 // multilevel preconditioner: Sim3 graphs on one GPU; AUTO switches it on for large graphs
 bool wants_multilevel(const s3o_problem *p) {
     const int nf = p->dist ? p->plan.nf_global : p->S.nf;
-    return p->kind != S3O_KIND_BA &&
+    return p->kind != S3O_KIND_BA && p->kind != 100 /* solver-only handle: no poses to build the coarse space on */ &&
            (p->precond == S3O_PRECOND_MULTILEVEL || (p->precond == S3O_PRECOND_AUTO && (nf >= 20000 || p->auto_multilevel)));
 }
 
@@ -456,11 +456,15 @@ int s3o_device_count(void) {
     return n;
 }
 
-int s3o_create(int kind, int device, s3o_problem **out) {
+// kind of the handle behind s3o_linsolver_*: a block system only (no graph, no estimates)
+static constexpr int kKindLinear = 100;
+
+static int create_impl(int kind, int linear_dim, int device, s3o_problem **out) {
     if (!out) { set_error("s3o_create: out is NULL"); return S3O_ERR_INVALID; }
     *out = nullptr;
     int d, est_dim;
     switch (kind) {
+    case kKindLinear: d = linear_dim; est_dim = 0; break;
     case S3O_KIND_SIM3: d = 7; est_dim = 8; break;
     case S3O_KIND_SCALE_TRANS: d = 4; est_dim = 4; break;
     case S3O_KIND_SCALE: d = 1; est_dim = 1; break;
@@ -499,6 +503,86 @@ int s3o_create(int kind, int device, s3o_problem **out) {
     memset(p->h_sc, 0, sizeof(DevScalars));
     p->stats.dim = d;
     *out = p;
+    return S3O_OK;
+}
+
+int s3o_create(int kind, int device, s3o_problem **out) {
+    if (kind == kKindLinear) { set_error("s3o_create: unsupported kind %d", kind); return S3O_ERR_UNSUPPORTED; }
+    return create_impl(kind, 0, device, out);
+}
+
+// ---- LinearSolver-level entry (the slot of g2o::LinearSolver<M>::solve(A, x, b), kitti_surf.cpp:553-557) ----
+int s3o_linsolver_create(int device, int block_dim, s3o_linsolver **out) {
+    if (block_dim != 1 && block_dim != 4 && block_dim != 6 && block_dim != 7) {
+        set_error("s3o_linsolver_create: block dimension %d (supported: 1, 4, 6, 7)", block_dim);
+        return S3O_ERR_UNSUPPORTED;
+    }
+    return create_impl(kKindLinear, block_dim, device, out);
+}
+
+int s3o_linsolver_destroy(s3o_linsolver *p) { return s3o_destroy(p); }
+
+int s3o_linsolver_solve(s3o_linsolver *p, int n, const int32_t *colptr, const int32_t *rowidx, const double *blocks,
+                        int column_major, double lambda, const double *b, double *x, int *method, int *pcg_iterations) {
+    if (!p || p->kind != kKindLinear || n < 0 || !colptr || (n > 0 && (!rowidx || !blocks || !b || !x))) { set_error("s3o_linsolver_solve: bad arguments"); return S3O_ERR_INVALID; }
+    if (n == 0) return S3O_OK;
+    cudaSetDevice(p->device);
+    const int d = p->d, dd = d * d, nb = colptr[n];
+    // same pattern as the last call (LinearSolver::init() once, solve() per LM trial): keep structure and plan
+    bool same = p->built && p->S.nf == n && p->S.nb == nb &&
+                memcmp(p->S.ccs_colptr.data(), colptr, sizeof(int32_t) * (n + 1)) == 0 &&
+                memcmp(p->S.ccs_rowidx.data(), rowidx, sizeof(int32_t) * nb) == 0;
+    if (!same) {
+        free_structure(p);
+        std::vector<int32_t> v0, v1;
+        for (int c = 0; c < n; ++c) {
+            bool diag = false;
+            for (int k = colptr[c]; k < colptr[c + 1]; ++k) {
+                const int r = rowidx[k];
+                if (r < 0 || r > c || (k > colptr[c] && r <= rowidx[k - 1])) {
+                    set_error("s3o_linsolver_solve: column %d is not an upper block-CCS column (rows ascending, row <= column)", c);
+                    return S3O_ERR_INVALID;
+                }
+                if (r == c) diag = true;
+                else { v0.push_back(r); v1.push_back(c); }
+            }
+            if (!diag) { set_error("s3o_linsolver_solve: column %d has no diagonal block", c); return S3O_ERR_INVALID; }
+        }
+        p->nv = n;
+        p->fixed.assign(n, 0);
+        build_structure_host(n, nullptr, (int)v0.size(), v0.data(), v1.data(), p->S);
+        if (p->S.nb != nb || memcmp(p->S.ccs_rowidx.data(), rowidx, sizeof(int32_t) * nb) != 0) { set_error("s3o_linsolver_solve: pattern mismatch"); return S3O_ERR_INVALID; }
+        int rc = upload_structure_arrays(p, n);
+        rc = rc ? rc : alloc_linear_system(p);
+        if (rc) { free_structure(p); return rc; }
+        p->built = true;
+        p->stats.n_free = n; p->stats.n_blocks = nb;
+    }
+    // blocks into BSR-upper order (row-major d x d)
+    std::vector<double> H((size_t)nb * dd);
+    for (int c = 0; c < nb; ++c) {
+        double *dst = H.data() + (size_t)p->S.ccs2bsr[c] * dd;
+        const double *src = blocks + (size_t)c * dd;
+        if (!column_major) memcpy(dst, src, sizeof(double) * dd);
+        else
+            for (int r = 0; r < d; ++r)
+                for (int cc = 0; cc < d; ++cc) dst[r * d + cc] = src[cc * d + r];
+    }
+    S3O_CUDA(cudaMemcpyAsync(p->d_H, H.data(), H.size() * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    S3O_CUDA(cudaMemcpyAsync(p->d_b, b, (size_t)n * d * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    p->stats.h2d_bytes += (int64_t)((H.size() + (size_t)n * d) * sizeof(double));
+    p->linearized = true;
+    direct_invalidate(p);
+    int status = 0, iters = 0;
+    int rc = do_solve(p, lambda, &status, &iters, nullptr);
+    if (rc) return rc;
+    S3O_CUDA(cudaMemcpyAsync(x, p->d_x, (size_t)n * d * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    S3O_CUDA(cudaStreamSynchronize(p->stream));
+    p->stats.d2h_bytes += (int64_t)n * d * 8;
+    if (method) *method = direct_available(p) && p->linsolver != S3O_LINSOLVER_PCG ? S3O_LINSOLVER_DIRECT : S3O_LINSOLVER_PCG;
+    if (pcg_iterations) *pcg_iterations = iters;
+    if (status == 3) { set_error("s3o_linsolver_solve: the matrix is not positive definite (pivot / PCG breakdown)"); return S3O_RESULT_FAIL; }
+    if (status == 2) { set_error("s3o_linsolver_solve: PCG hit the iteration cap"); return S3O_RESULT_FAIL; }
     return S3O_OK;
 }
 

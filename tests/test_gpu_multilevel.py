@@ -127,22 +127,24 @@ def test_scale_null_vector_multilevel(kitti_k118):
 
 def test_kcycle_fewer_iterations_same_solution():
     """K-cycle (two inner CG steps on the largest coarse levels, one cooperative kernel for the small ones)
-    against the V-cycle on a 9k-pose sphere at a late-iteration damping: same solution, fewer iterations,
-    bitwise reproducible."""
+    against the V-cycle on a 9k-pose sphere at a late-iteration linearisation point and damping: same solution
+    (backward error against the same H and b), fewer iterations, bitwise reproducible."""
     import os
     import sim3opt_b200 as s3
     from sim3opt_b200 import synth
-    g = synth.sphere(n_laps=30, poses_per_lap=300, seed=42)
+    g = dict(synth.sphere(n_laps=30, poses_per_lap=300, seed=42))
+    warm = make_gpu(g, jac=1, math_mode=s3.MATH_CORRECTED)
+    warm.set_pcg(1e-3, 20000)
+    warm.optimize(5)                                         # a late-iteration linearisation point, shared by all runs
+    g["est"] = warm.vertices()
+    del warm
     res = {}
     for k in ("0", "1", "2"):
         os.environ["S3O_KCYCLE"] = k
         try:
             gpu = make_gpu(g, jac=1, math_mode=s3.MATH_CORRECTED)
             gpu.set_preconditioner(s3.PRECOND_MULTILEVEL)
-            gpu.set_pcg(1e-3, 20000)
-            gpu.optimize(4)                                  # a late-iteration linearisation point
-            colptr, rowidx = gpu.build_structure()
-            gpu.linearize_only()
+            H, b = gpu.linearize()
             lam = 1e-10 * gpu.max_diag()
             gpu.set_pcg(1e-10, 50000)
             rc, x, it, rel = gpu.solve(lam)
@@ -151,14 +153,15 @@ def test_kcycle_fewer_iterations_same_solution():
         finally:
             del os.environ["S3O_KCYCLE"]
         assert rc == 0 and rel <= 1e-10
+        assert np.linalg.norm(y - b) <= 1e-9 * np.linalg.norm(b)
         assert it2 == it and np.array_equal(x, x2)
-        res[k] = (x, it, y)
-    b = res["0"][2]
+        res[k] = (x, it)
+    counts = {k: v[1] for k, v in res.items()}
+    print("PCG iterations V / K1 / K2:", counts)
     for k in ("1", "2"):
-        assert np.linalg.norm(res[k][2] - b) <= 1e-9 * np.linalg.norm(b)          # (H + lambda I) x reproduces the same b
-        assert np.abs(res[k][0] - res["0"][0]).max() <= 1e-4 * np.abs(res["0"][0]).max()
-    assert res["1"][1] < res["0"][1] and res["2"][1] < res["1"][1], {k: v[1] for k, v in res.items()}
-    assert res["2"][1] * 3 <= res["0"][1] * 2, {k: v[1] for k, v in res.items()}
+        assert np.abs(res[k][0] - res["0"][0]).max() <= 1e-5 * np.abs(res["0"][0]).max()
+    assert counts["1"] < counts["0"] and counts["2"] <= counts["1"], counts
+    assert counts["2"] * 3 <= counts["0"] * 2, counts
 
 
 def test_multilevel_rejected_for_ba():
