@@ -24,6 +24,10 @@ namespace {
 #define DD (D * D)       /* D: template parameter in the kernels, p->d in the host code */
 constexpr int NREL = 13;             // doubles of transfer data per vertex: a 3x3 matrix, a 3-vector, a scalar
 constexpr int kCoarsestMax = 16;        // dense inverse held in shared memory: (16*7)^2 doubles = 98 KB
+constexpr int kCoarsestMaxBig = 128;    // large graphs: the hierarchy stops at <= 128 vertices, inverted by a cooperative
+                                        // block Gauss-Jordan in global memory (896^2 doubles = 6.4 MB); one level fewer
+                                        // to recurse through in every K-cycle visit
+constexpr int kBigGraph = 20000;        // free vertices from which the deep-hierarchy settings apply
 constexpr int kMaxLevels = 12;
 constexpr double kOmega = 0.7;          // damping of the block-Jacobi smoother on the coarse levels
 
@@ -68,6 +72,8 @@ struct AmgState {
     // walked by ONE cooperative kernel (grid barriers instead of kernel boundaries)
     int kdepth = 0, coop_first = 0, coop_grid = 0;
     KScal *d_ks = nullptr;          // [kMaxLevels]
+    bool dense_coop = false;        // coarsest level inverted by the cooperative kernel (too large for shared memory)
+    double *d_colbuf = nullptr, *d_rowbuf = nullptr;
     double *d_cdots = nullptr;      // [3][coop_grid] partial sums of the cooperative kernel's dot products
 };
 
@@ -301,6 +307,95 @@ __global__ void __launch_bounds__(256) amg_dense_inverse_kernel(const double *__
         __syncthreads();
     }
     for (int t = threadIdx.x; t < N * N; t += blockDim.x) inv[t] = a[t];
+}
+
+// Same inverse for a coarsest level that does not fit shared memory: block Gauss-Jordan on the d x d block grid
+// in global memory, one cooperative grid, two barriers per pivot block.  No pivoting (the matrix is SPD).
+//   pivot phase   P = A_kk^-1;  colbuf_i = A_ik;  rowbuf_j = P A_kj
+//   update phase  A_kj <- rowbuf_j (A_kk <- P);  A_ik <- -colbuf_i P;  A_ij <- A_ij - colbuf_i rowbuf_j
+template <int D>
+__global__ void __launch_bounds__(256) amg_dense_inverse_coop_kernel(const double *__restrict__ A, const int32_t *__restrict__ rowptr,
+                                                                     const int32_t *__restrict__ colidx, int n, double *inv,
+                                                                     double *colbuf, double *rowbuf, DevScalars *sc) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const int N = n * D, nth = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t t = gtid; t < (size_t)N * N; t += nth) inv[t] = 0;
+    __threadfence();
+    grid.sync();
+    for (int k = gtid; k < rowptr[n] * DD; k += nth) {
+        const int blk = k / DD, e = k - blk * DD;
+        // block row of blk: binary search in rowptr
+        int lo = 0, hi = n - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (rowptr[mid] <= blk) lo = mid; else hi = mid - 1; }
+        inv[(size_t)(lo * D + e / D) * N + colidx[blk] * D + e % D] = A[k];
+    }
+    __threadfence();
+    grid.sync();
+    __shared__ double Ps[DD];
+    for (int kb = 0; kb < n; ++kb) {
+        // every CTA inverts the pivot block for itself (Gauss-Jordan on d x d by one thread)
+        if (threadIdx.x == 0) {
+            double M[DD], I[DD];
+#pragma unroll
+            for (int r = 0; r < D; ++r)
+#pragma unroll
+                for (int c = 0; c < D; ++c) { M[r * D + c] = __ldcg(inv + (size_t)(kb * D + r) * N + kb * D + c); I[r * D + c] = r == c ? 1.0 : 0.0; }
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                double piv = M[c * D + c];
+                if (!(piv > 0)) { piv = 1; sc->precond_fail = 1; }
+                const double ip = 1.0 / piv;
+#pragma unroll
+                for (int j = 0; j < D; ++j) { M[c * D + j] *= ip; I[c * D + j] *= ip; }
+#pragma unroll
+                for (int r = 0; r < D; ++r) {
+                    if (r == c) continue;
+                    const double f = M[r * D + c];
+#pragma unroll
+                    for (int j = 0; j < D; ++j) { M[r * D + j] -= f * M[c * D + j]; I[r * D + j] -= f * I[c * D + j]; }
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < DD; ++e) Ps[e] = I[e];
+        }
+        __syncthreads();
+        // colbuf[i*D+r][c] = A[i*D+r][kb*D+c];  rowbuf[r][j] = sum_m P[r][m] A[kb*D+m][j]
+        for (int t = gtid; t < N * D; t += nth) {
+            const int row = t / D, c = t - row * D;
+            colbuf[t] = __ldcg(inv + (size_t)row * N + kb * D + c);
+        }
+        for (int t = gtid; t < D * N; t += nth) {
+            const int r = t / N, j = t - r * N;
+            double acc = 0;
+#pragma unroll
+            for (int m = 0; m < D; ++m) acc += Ps[r * D + m] * __ldcg(inv + (size_t)(kb * D + m) * N + j);
+            rowbuf[t] = acc;
+        }
+        __threadfence();
+        grid.sync();
+        for (size_t t = gtid; t < (size_t)N * N; t += nth) {
+            const int i = (int)(t / N), j = (int)(t - (size_t)i * N);
+            const int ib = i / D, jb = j / D;
+            double v;
+            if (ib == kb) v = (jb == kb) ? Ps[(i - kb * D) * D + (j - kb * D)] : __ldcg(rowbuf + (size_t)(i - kb * D) * N + j);
+            else {
+                double acc = 0;
+                if (jb == kb) {
+#pragma unroll
+                    for (int m = 0; m < D; ++m) acc -= __ldcg(colbuf + (size_t)i * D + m) * Ps[m * D + (j - kb * D)];
+                    v = acc;
+                } else {
+#pragma unroll
+                    for (int m = 0; m < D; ++m) acc += __ldcg(colbuf + (size_t)i * D + m) * __ldcg(rowbuf + (size_t)m * N + j);
+                    v = __ldcg(inv + t) - acc;
+                }
+            }
+            inv[t] = v;
+        }
+        __threadfence();
+        grid.sync();
+    }
 }
 
 // ---- coarse-level row kernels: an 8-lane group owns one block row, lane l one component ---------
@@ -706,7 +801,29 @@ struct CoopParams {
     CoopLevel lev[kMaxLevels];
 };
 
-// mode 0: out = omega Dinv rin;  1: out = rin - A x;  2: out = x + omega Dinv (rin - A x)
+// A residual given as  a - alpha b  (b == nullptr: a).  The second inner step of a K-cycle level works on
+// r' = r - alpha1 q1, which is formed where it is read instead of being stored.
+struct RSpec { const double *a, *b; double alpha; };
+__device__ __forceinline__ double rget(const RSpec &R, size_t t) {
+    double v = __ldcg(R.a + t);
+    if (R.b) v -= R.alpha * __ldcg(R.b + t);
+    return v;
+}
+// A coarse correction given as  c1 a + c2 b  (b == nullptr: a): the result of a K-cycle level is combined where
+// the parent prolongs it.
+struct XSpec { const double *a, *b; double c1, c2; };
+__device__ __forceinline__ double xget(const XSpec &X, size_t t) {
+    double v = __ldcg(X.a + t);
+    if (X.b) v = X.c1 * v + X.c2 * __ldcg(X.b + t);
+    return v;
+}
+
+// shuffle inside the 8-lane group of a warp (groups of one warp may run different trip counts)
+__device__ __forceinline__ double gshfl(unsigned gmask, double v, int src_in_group) {
+    return __shfl_sync(gmask, v, (threadIdx.x & 24) + src_in_group);
+}
+
+// mode 0: out = omega Dinv rin;  2: out = x + omega Dinv (rin - A x)      (coarsest level without a dense inverse)
 template <int D, int MODE>
 __device__ __forceinline__ void coop_rows(const CoopLevel &L, const double *rin, const double *x, double *out, double omega,
                                           int gtid, int nth) {
@@ -726,10 +843,6 @@ __device__ __forceinline__ void coop_rows(const CoopLevel &L, const double *rin,
             }
             res -= acc;
         }
-        if (MODE == 1) {
-            if (act) out[(size_t)i * D + l] = res;
-            continue;
-        }
         double z = 0;
 #pragma unroll
         for (int c = 0; c < D; ++c) {
@@ -740,10 +853,122 @@ __device__ __forceinline__ void coop_rows(const CoopLevel &L, const double *rin,
     }
 }
 
-// dot products of one inner step over the grid: per-CTA partials -> grid barrier -> every CTA adds the
-// partials in the same fixed order (all CTAs obtain identical bits)
+// Way down, fused: the first smoothing sweep starts from zero, x = omega Dinv r, so the residual after it is
+// t_i = r_i - sum_j A_ij (omega Dinv_j r_j) with the neighbours' sweep formed on the fly: one phase instead of two.
 template <int D>
-__device__ __forceinline__ void coop_kdots(const CoopLevel &L, const double *z, const double *v1, const double *v2, double *q,
+__device__ __forceinline__ void coop_down(const CoopLevel &L, const RSpec R, double omega, int gtid, int nth) {
+    const int groups = nth / 8, g = gtid / 8, l = gtid & 7;
+    const unsigned gmask = 0xffu << (threadIdx.x & 24);
+    const int lc = l < D ? l : 0;             // lane 7 shadows lane 0 (keeps the group's shuffles convergent)
+    for (int i = g; i < L.n; i += groups) {
+        const double ri = rget(R, (size_t)i * D + lc);
+        double xi = 0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) xi += L.Dinv[(size_t)i * sym_size<D>() + sym_off<D>(lc, c)] * gshfl(gmask, ri, c);
+        xi *= omega;
+        double acc = 0;
+        const int kb = L.rowptr[i], ke = L.rowptr[i + 1];
+        for (int k = kb; k < ke; ++k) {
+            const int j = L.colidx[k];
+            double xj;
+            if (j == i) xj = xi;
+            else {
+                const double rj = rget(R, (size_t)j * D + lc);
+                xj = 0;
+#pragma unroll
+                for (int c = 0; c < D; ++c) xj += L.Dinv[(size_t)j * sym_size<D>() + sym_off<D>(lc, c)] * gshfl(gmask, rj, c);
+                xj *= omega;
+            }
+            const double *Ak = L.A + (size_t)k * DD + lc * D;
+#pragma unroll
+            for (int c = 0; c < D; ++c) acc += Ak[c] * gshfl(gmask, xj, c);
+        }
+        if (l < D) {
+            L.x[(size_t)i * D + l] = xi;
+            L.t[(size_t)i * D + l] = ri - acc;
+        }
+    }
+}
+
+// r_{l+1} = P^T t: an 8-lane group per aggregate, lane m takes members m, m+8, ... and a fixed butterfly adds them
+template <int D>
+__device__ __forceinline__ void coop_restrict(const CoopLevel &C, const double *t, int gtid, int nth) {
+    const int groups = nth / 8, g = gtid / 8, lane = gtid & 7;
+    const unsigned gmask = 0xffu << (threadIdx.x & 24);
+    for (int I = g; I < C.n; I += groups) {
+        double acc[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) acc[c] = 0;
+        for (int m = C.mem_ptr[I] + lane; m < C.mem_ptr[I + 1]; m += 8) {
+            const int i = C.mem_idx[m];
+            const Rel S = load_rel(C.rel, C.pad_fine, i);
+            double w[D], u[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) w[c] = __ldcg(t + (size_t)i * D + c);
+            Xf<D>::applyT(S, w, u);
+#pragma unroll
+            for (int c = 0; c < D; ++c) acc[c] += u[c];
+        }
+#pragma unroll
+        for (int off = 4; off > 0; off >>= 1) {
+#pragma unroll
+            for (int c = 0; c < D; ++c) acc[c] += __shfl_xor_sync(gmask, acc[c], off, 8);
+        }
+        if (lane < D) {
+            double v = acc[0];
+#pragma unroll
+            for (int c = 1; c < D; ++c) v = (lane == c) ? acc[c] : v;
+            C.r[(size_t)I * D + lane] = v;
+        }
+    }
+}
+
+// Way up, fused: x' = x + P xc (the child's correction, combined on the fly) and the second smoothing sweep
+// out = x' + omega Dinv (r - A x'), with the neighbours' prolonged values formed where they are read.
+template <int D>
+__device__ __forceinline__ void coop_up(const CoopLevel &F, const CoopLevel &C, const XSpec X, const RSpec R, double *out,
+                                        double omega, int gtid, int nth) {
+    const int groups = nth / 8, g = gtid / 8, l = gtid & 7;
+    const unsigned gmask = 0xffu << (threadIdx.x & 24);
+    const int lc = l < D ? l : 0;
+    auto prolonged = [&](int v, double xp[D]) {
+        const Rel S = load_rel(C.rel, C.pad_fine, v);
+        const int I = C.agg[v];
+        double xc[D], u[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) xc[c] = xget(X, (size_t)I * D + c);
+        Xf<D>::apply(S, xc, u);
+#pragma unroll
+        for (int c = 0; c < D; ++c) xp[c] = __ldcg(F.x + (size_t)v * D + c) + u[c];
+    };
+    for (int i = g; i < F.n; i += groups) {
+        double acc = 0, xi_l = 0;
+        const int kb = F.rowptr[i], ke = F.rowptr[i + 1];
+        for (int k = kb; k < ke; ++k) {
+            const int j = F.colidx[k];
+            double xp[D];
+            prolonged(j, xp);
+            const double *Ak = F.A + (size_t)k * DD + lc * D;
+#pragma unroll
+            for (int c = 0; c < D; ++c) acc += Ak[c] * xp[c];
+            if (j == i) {
+#pragma unroll
+                for (int c = 0; c < D; ++c) xi_l = (c == lc) ? xp[c] : xi_l;
+            }
+        }
+        const double res = rget(R, (size_t)i * D + lc) - acc;
+        double z = 0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) z += F.Dinv[(size_t)i * sym_size<D>() + sym_off<D>(lc, c)] * gshfl(gmask, res, c);
+        if (l < D) out[(size_t)i * D + l] = xi_l + omega * z;
+    }
+}
+
+// dot products of one inner step over the grid: per-CTA partials -> grid barrier -> every CTA adds the
+// partials in the same fixed order (all CTAs obtain identical bits).  The barrier inside also orders the
+// store of q before whatever phase follows.
+template <int D>
+__device__ __forceinline__ void coop_kdots(const CoopLevel &L, const double *z, const RSpec V1, const double *v2, double *q,
                                            double *dots, double out[3], int gtid, int nth, double *sh) {
     const int groups = nth / 8, g = gtid / 8, l = gtid & 7;
     double d0 = 0, d1 = 0, d2 = 0;
@@ -759,7 +984,7 @@ __device__ __forceinline__ void coop_kdots(const CoopLevel &L, const double *z, 
         const double zi = __ldcg(z + (size_t)i * D + l);
         if (q) q[(size_t)i * D + l] = acc;
         d0 += zi * acc;
-        d1 += zi * __ldcg(v1 + (size_t)i * D + l);
+        d1 += zi * rget(V1, (size_t)i * D + l);
         if (v2) d2 += zi * __ldcg(v2 + (size_t)i * D + l);
     }
     const double s0 = block_sum<kCoopThreads>(d0, sh);
@@ -785,6 +1010,9 @@ __device__ __forceinline__ void coop_kdots(const CoopLevel &L, const double *z, 
     __syncthreads();
 }
 
+// Phases per level visit: way down 2 (fused sweep + residual, restriction), way up 1 (fused prolongation + sweep);
+// a K-cycle level adds one phase per inner step (product + dot products).  The dots buffer alternates between two
+// halves, so a step's partial sums are never overwritten while a slow CTA still reads the previous step's.
 template <int D>
 __global__ void __launch_bounds__(kCoopThreads, 1)
 amg_coop_kernel(const __grid_constant__ CoopParams P, double omega, const DevScalars *sc, int check_done) {
@@ -795,108 +1023,95 @@ amg_coop_kernel(const __grid_constant__ CoopParams P, double omega, const DevSca
     const int nth = gridDim.x * kCoopThreads, gtid = blockIdx.x * kCoopThreads + threadIdx.x;
     auto gsync = [&]() { __threadfence(); grid.sync(); };
     const int last = P.nlev - 1;
-    // explicit recursion state: input residual / output of the cycle in progress at every level, inner step
-    const double *cur_r[kMaxLevels];
+    // explicit recursion state: residual of the cycle in progress at every level, where its result goes, the
+    // inner step of a K-cycle level and its scalars
+    RSpec cur_r[kMaxLevels];
     double *cur_out[kMaxLevels];
     int step[kMaxLevels];
     KScal ks[kMaxLevels];
+    int flip = 0;
+    auto is_k = [&](int l) { return l < P.kdepth && l < last; };
     int l = 0;
-    cur_r[0] = P.lev[0].r;
-    cur_out[0] = (P.kdepth > 0 && last > 0) ? P.lev[0].z1 : P.lev[0].x2;
+    cur_r[0] = RSpec{ P.lev[0].r, nullptr, 0.0 };
+    cur_out[0] = is_k(0) ? P.lev[0].z1 : P.lev[0].x2;
     step[0] = 0;
     for (;;) {
         // ---------------- descend: cycle at level l on cur_r[l] -----------------------------------
         for (;;) {
             const CoopLevel &L = P.lev[l];
             if (l == last) {
+                // the coarsest level is never a K-cycle level: its residual is the plain vector L.r
                 if (P.dense) {
                     for (int t = gtid; t < P.N; t += nth) {
                         double acc = 0;
-                        for (int c = 0; c < P.N; ++c) acc += P.inv[(size_t)c * P.N + t] * __ldcg(cur_r[l] + c);
+                        for (int c = 0; c < P.N; ++c) acc += P.inv[(size_t)c * P.N + t] * __ldcg(L.r + c);
                         cur_out[l][t] = acc;
                     }
-                } else {            // no dense inverse: five damped block-Jacobi sweeps (a fixed linear operator)
-                    coop_rows<D, 0>(L, cur_r[l], nullptr, L.x, omega, gtid, nth);
+                } else if (l == 0) {    // a single coarse level too large for the dense inverse: five damped sweeps
+                    coop_rows<D, 0>(L, L.r, nullptr, L.x, omega, gtid, nth);
                     gsync();
-                    coop_rows<D, 2>(L, cur_r[l], L.x, L.t, omega, gtid, nth);
+                    coop_rows<D, 2>(L, L.r, L.x, L.t, omega, gtid, nth);
                     gsync();
-                    coop_rows<D, 2>(L, cur_r[l], L.t, L.x, omega, gtid, nth);
+                    coop_rows<D, 2>(L, L.r, L.t, L.x, omega, gtid, nth);
                     gsync();
-                    coop_rows<D, 2>(L, cur_r[l], L.x, L.t, omega, gtid, nth);
+                    coop_rows<D, 2>(L, L.r, L.x, L.t, omega, gtid, nth);
                     gsync();
-                    coop_rows<D, 2>(L, cur_r[l], L.t, cur_out[l], omega, gtid, nth);
+                    coop_rows<D, 2>(L, L.r, L.t, cur_out[l], omega, gtid, nth);
+                } else {
+                    coop_rows<D, 0>(L, L.r, nullptr, L.x, omega, gtid, nth);
+                    gsync();
+                    coop_rows<D, 2>(L, L.r, L.x, L.t, omega, gtid, nth);
+                    gsync();
+                    coop_rows<D, 2>(L, L.r, L.t, L.x, omega, gtid, nth);
+                    gsync();
+                    coop_rows<D, 2>(L, L.r, L.x, L.t, omega, gtid, nth);
+                    gsync();
+                    coop_rows<D, 2>(L, L.r, L.t, cur_out[l], omega, gtid, nth);
                 }
                 gsync();
                 break;
             }
-            coop_rows<D, 0>(L, cur_r[l], nullptr, L.x, omega, gtid, nth);
+            coop_down<D>(L, cur_r[l], omega, gtid, nth);
             gsync();
-            coop_rows<D, 1>(L, cur_r[l], L.x, L.t, omega, gtid, nth);
-            gsync();
-            const CoopLevel &C = P.lev[l + 1];
-            for (int I = gtid; I < C.n; I += nth) {        // r_{l+1} = P^T t
-                double acc[D];
-#pragma unroll
-                for (int c = 0; c < D; ++c) acc[c] = 0;
-                for (int m = C.mem_ptr[I]; m < C.mem_ptr[I + 1]; ++m) {
-                    const int i = C.mem_idx[m];
-                    const Rel S = load_rel(C.rel, C.pad_fine, i);
-                    double w[D], u[D];
-#pragma unroll
-                    for (int c = 0; c < D; ++c) w[c] = __ldcg(L.t + (size_t)i * D + c);
-                    Xf<D>::applyT(S, w, u);
-#pragma unroll
-                    for (int c = 0; c < D; ++c) acc[c] += u[c];
-                }
-#pragma unroll
-                for (int c = 0; c < D; ++c) C.r[(size_t)I * D + c] = acc[c];
-            }
+            coop_restrict<D>(P.lev[l + 1], L.t, gtid, nth);
             gsync();
             ++l;
-            cur_r[l] = P.lev[l].r;
-            cur_out[l] = (l < P.kdepth && l < last) ? P.lev[l].z1 : P.lev[l].x2;
+            cur_r[l] = RSpec{ P.lev[l].r, nullptr, 0.0 };
+            cur_out[l] = is_k(l) ? P.lev[l].z1 : P.lev[l].x2;
             step[l] = 0;
         }
         // ---------------- ascend: cur_out[l] holds the result of a cycle at level l ---------------
+        bool again = false;
         for (;;) {
             const CoopLevel &L = P.lev[l];
-            if (l < P.kdepth && l < last) {
+            XSpec X{ L.x2, nullptr, 1.0, 0.0 };       // how the parent reads the solution of level l
+            if (is_k(l)) {
                 double d[3];
+                double *dots = P.dots + (flip ? 3 * gridDim.x : 0);
+                flip ^= 1;
                 if (step[l] == 0) {
-                    coop_kdots<D>(L, L.z1, cur_r[l], nullptr, L.q1, P.dots, d, gtid, nth, sh);
+                    coop_kdots<D>(L, L.z1, cur_r[l], nullptr, L.q1, dots, d, gtid, nth, sh);
                     kscal_first(&ks[l], d[0], d[1]);
-                    const double a1 = ks[l].alpha1;
-                    for (int t = gtid; t < L.n * D; t += nth) L.rp[t] = __ldcg(cur_r[l] + t) - a1 * __ldcg(L.q1 + t);
-                    gsync();
                     step[l] = 1;
-                    cur_r[l] = L.rp;
+                    cur_r[l] = RSpec{ L.r, L.q1, ks[l].alpha1 };      // r' = r - alpha1 q1, formed where it is read
                     cur_out[l] = L.z2;
+                    again = true;
                     break;                      // second cycle at the same level
                 }
-                coop_kdots<D>(L, L.z2, L.rp, L.q1, nullptr, P.dots, d, gtid, nth, sh);
+                coop_kdots<D>(L, L.z2, cur_r[l], L.q1, nullptr, dots, d, gtid, nth, sh);
                 kscal_second(&ks[l], d[0], d[1], d[2]);
-                const double c1 = ks[l].c1, c2 = ks[l].c2;
-                for (int t = gtid; t < L.n * D; t += nth) L.x2[t] = c1 * __ldcg(L.z1 + t) + c2 * __ldcg(L.z2 + t);
-                gsync();
+                X = XSpec{ L.z1, L.z2, ks[l].c1, ks[l].c2 };
+                if (l == 0) {                   // the caller reads a plain vector
+                    for (int t = gtid; t < L.n * D; t += nth) L.x2[t] = xget(X, t);
+                    return;
+                }
             }
-            // the solve of level l is complete in L.x2
             if (l == 0) return;
-            const CoopLevel &F = P.lev[l - 1];
-            for (int i = gtid; i < F.n; i += nth) {        // x_{l-1} += P x_l
-                const Rel S = load_rel(L.rel, L.pad_fine, i);
-                const int I = L.agg[i];
-                double v[D], u[D];
-#pragma unroll
-                for (int c = 0; c < D; ++c) v[c] = __ldcg(L.x2 + (size_t)I * D + c);
-                Xf<D>::apply(S, v, u);
-#pragma unroll
-                for (int c = 0; c < D; ++c) F.x[(size_t)i * D + c] = __ldcg(F.x + (size_t)i * D + c) + u[c];
-            }
-            gsync();
             --l;
-            coop_rows<D, 2>(F, cur_r[l], F.x, cur_out[l], omega, gtid, nth);
+            coop_up<D>(P.lev[l], P.lev[l + 1], X, cur_r[l], cur_out[l], omega, gtid, nth);
             gsync();
         }
+        (void)again;
     }
 }
 
@@ -986,6 +1201,8 @@ void amg_destroy(s3o_problem *p) {
     dev_free(p->amg->d_unpad_src);
     dev_free(p->amg->d_scal_pos);
     dev_free(p->amg->d_ks);
+    dev_free(p->amg->d_colbuf);
+    dev_free(p->amg->d_rowbuf);
     dev_free(p->amg->d_cdots);
     delete p->amg;
     p->amg = nullptr;
@@ -1006,10 +1223,10 @@ int amg_setup(s3o_problem *p) {
         // then keeps the part of the fine transfer that touches its own rows
         HostStructure Sg;
         build_structure_host(p->nv, p->fixed.data(), (int)p->gv0.size(), p->gv0.data(), p->gv1.data(), Sg);
-        amg_build_hierarchy(Sg, kCoarsestMax, kMaxLevels, st->host, p->plan.seg);
+        amg_build_hierarchy(Sg, Sg.nf >= kBigGraph ? kCoarsestMaxBig : kCoarsestMax, kMaxLevels, st->host, p->plan.seg);
         if (!st->host.empty()) localize_fine_level(p, Sg, st);
     } else {
-        amg_build_hierarchy(p->S, kCoarsestMax, kMaxLevels, st->host);
+        amg_build_hierarchy(p->S, p->S.nf >= kBigGraph ? kCoarsestMaxBig : kCoarsestMax, kMaxLevels, st->host);
     }
     const int nl = (int)st->host.size();
     if (nl == 0) return S3O_OK;
@@ -1066,38 +1283,45 @@ int amg_setup(s3o_problem *p) {
         rc = rc ? rc : dev_alloc(&st->d_rpad, (size_t)world * st->r_seg);
     }
     const int nc = st->host.back().n;
-    st->dense = nc <= kCoarsestMax;
+    st->dense = nc <= kCoarsestMaxBig;
+    st->dense_coop = st->dense && nc > kCoarsestMax;
     if (!rc && st->dense) {
         rc = dev_alloc(&st->d_dense, (size_t)nc * D * nc * D);
-        const int smem = (nc * D * nc * D + nc * D) * (int)sizeof(double);
-        cudaError_t ea = D == 7 ? cudaFuncSetAttribute(amg_dense_inverse_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-                       : D == 4 ? cudaFuncSetAttribute(amg_dense_inverse_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-                                : cudaFuncSetAttribute(amg_dense_inverse_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (!rc && ea != cudaSuccess) {
-            set_error("amg_setup: cannot reserve %d bytes of shared memory", smem);
-            rc = S3O_ERR_CUDA;
+        if (st->dense_coop) {
+            rc = rc ? rc : dev_alloc(&st->d_colbuf, (size_t)nc * D * D);
+            rc = rc ? rc : dev_alloc(&st->d_rowbuf, (size_t)nc * D * D);
+        } else {
+            const int smem = (nc * D * nc * D + nc * D) * (int)sizeof(double);
+            cudaError_t ea = D == 7 ? cudaFuncSetAttribute(amg_dense_inverse_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                           : D == 4 ? cudaFuncSetAttribute(amg_dense_inverse_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                                    : cudaFuncSetAttribute(amg_dense_inverse_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (!rc && ea != cudaSuccess) {
+                set_error("amg_setup: cannot reserve %d bytes of shared memory", smem);
+                rc = S3O_ERR_CUDA;
+            }
         }
     }
     if (!rc) {
-        // K-cycle on the two largest coarse levels of a deep hierarchy (large graphs); shallow ones keep the V-cycle.
-        // S3O_KCYCLE=<levels> overrides (0: V-cycle everywhere).
-        st->kdepth = (nl >= 3 && st->host[0].n_fine >= 20000) ? 1 : 0;
+        // K-cycle on every level above the coarsest for large graphs (measured on the 1M-pose sphere: PCG iterations of a
+        // late LM iteration 334 with the V-cycle, 166 with one K level, 63 with three; K on some levels and V below them
+        // can be worse than either); small graphs keep the V-cycle.  S3O_KCYCLE=<levels> overrides (0: V-cycle everywhere).
+        st->kdepth = (nl >= 2 && st->host[0].n_fine >= kBigGraph) ? nl - 1 : 0;
         if (const char *v = getenv("S3O_KCYCLE")) st->kdepth = std::max(0, std::min(atoi(v), nl - 1));
         int coop_rows = kCoopRows;
         if (const char *v = getenv("S3O_COOP_ROWS")) coop_rows = atoi(v);       // experiment switch
         st->coop_first = 0;
         while (st->coop_first < nl - 1 && st->lev[st->coop_first].n > coop_rows) ++st->coop_first;
-        if (st->kdepth > 0) {
+        if (st->kdepth > 0 || st->dense_coop) {
             int per_sm = 0, sms = 0;
             cudaError_t eo = D == 7 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, amg_coop_kernel<7>, kCoopThreads, 0)
                            : D == 4 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, amg_coop_kernel<4>, kCoopThreads, 0)
                                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, amg_coop_kernel<1>, kCoopThreads, 0);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
-            if (eo != cudaSuccess || per_sm < 1 || sms < 8) st->kdepth = 0;      // no cooperative launch: V-cycle
+            if (eo != cudaSuccess || per_sm < 1 || sms < 8) { st->kdepth = 0; if (st->dense_coop) { set_error("amg_setup: cooperative launch unavailable"); rc = S3O_ERR_CUDA; } }
             else {
                 st->coop_grid = sms;
                 rc = dev_alloc(&st->d_ks, kMaxLevels);
-                rc = rc ? rc : dev_alloc(&st->d_cdots, (size_t)3 * sms);
+                rc = rc ? rc : dev_alloc(&st->d_cdots, (size_t)6 * sms);
             }
         }
     }
@@ -1164,8 +1388,18 @@ int update_values_t(s3o_problem *p, double lambda) {
     if (st->dense) {
         const LevelDev &C = st->lev.back();
         const int N = C.n * D;
-        amg_dense_inverse_kernel<D><<<1, 256, (size_t)(N * N + N) * sizeof(double), p->stream>>>(C.A, C.rowptr, C.colidx, C.n,
-                                                                                              st->d_dense, p->d_sc);
+        if (st->dense_coop) {
+            const double *Ap = C.A;
+            const int32_t *rp = C.rowptr, *ci = C.colidx;
+            int n = C.n;
+            double *inv = st->d_dense, *cb = st->d_colbuf, *rb = st->d_rowbuf;
+            DevScalars *scp = p->d_sc;
+            void *args[] = { &Ap, &rp, &ci, &n, &inv, &cb, &rb, &scp };
+            S3O_CUDA(cudaLaunchCooperativeKernel((void *)amg_dense_inverse_coop_kernel<D>, dim3(st->coop_grid), dim3(256), args, 0, p->stream));
+        } else {
+            amg_dense_inverse_kernel<D><<<1, 256, (size_t)(N * N + N) * sizeof(double), p->stream>>>(C.A, C.rowptr, C.colidx, C.n,
+                                                                                                  st->d_dense, p->d_sc);
+        }
         launches += 1;
     }
     return check_launch(p, launches);

@@ -285,6 +285,9 @@ int direct_setup(s3o_problem *p) {
     D->available = false;
     if (p->dist || p->S.nf == 0) return S3O_OK;
     const bool forced = p->linsolver == S3O_LINSOLVER_DIRECT;
+    // AUTO: a factor within kAutoMaxPairs block products cannot have more than ~kAutoMaxPairs / 3 columns (a chain
+    // costs 3 products per column), so larger graphs go to the PCG without paying for the analysis
+    if (!forced && p->S.nf > kAutoMaxPairs / 3) return S3O_OK;
     if (!direct_analyze(p->S.nf, p->S.rowptr, p->S.colidx, forced ? kForcedMaxPairs : kAutoMaxPairs, D->plan)) return S3O_OK;
     const DirectPlan &P = D->plan;
     if (!forced && P.nlev > kAutoMaxLevels) return S3O_OK;

@@ -975,7 +975,7 @@ int s3o_host_multilevel(int n_vertices, const uint8_t *fixed, int n_edges, const
     std::vector<s3o::AmgHostLevel> lv;
     // world > 1: the hierarchy of the partitioned solve (aggregates stay inside the ranks' vertex ranges)
     const int seg = world > 1 ? (S.nf + world - 1) / world : 0;
-    s3o::amg_build_hierarchy(S, 16, 12, lv, seg);
+    s3o::amg_build_hierarchy(S, S.nf >= 20000 ? 128 : 16, 12, lv, seg);      // same rule as amg_setup
     *n_levels = (int)lv.size();
     for (int l = 0; l < (int)lv.size() && l < cap; ++l) {
         if (level_vertices) level_vertices[l] = lv[l].n;
