@@ -328,6 +328,12 @@ __device__ __forceinline__ void warp_store_piece_to(double *stage, const double 
     __syncwarp();
 }
 
+// Zero pattern of the analytic Sim3 Jacobians (sim3_edge_jacobians): [[J11,0,0],[J21,J22,j23],[0,0,+-1]] on the
+// tangent [omega, upsilon, sigma].  The products below are fully unrolled, so the test folds at compile time
+// and the multiplications with structural zeros disappear (31 of 49 entries are non-zero).
+template <bool SP>
+__device__ __forceinline__ constexpr bool jnz(int k, int c) { return !SP || (k < 3 ? c < 3 : (k < 6 || c == 6)); }
+
 // The cross term of an edge that is the only one feeding its off-diagonal block goes straight into
 // the Hessian (Hdirect != null): assemble_kernel then has nothing to do for that block.
 // DIAG: the information matrices are diagonal (or absent = identity): Omega' is held as D weights, A^T O' and
@@ -340,6 +346,7 @@ __global__ void __launch_bounds__(NT) linearize_kernel(GraphDev g, double h, dou
     constexpr int D = Model<KIND>::D, EST = Model<KIND>::EST, DD = D * D;
     constexpr int NS = packed_size(D), STRIDE = scr_stride(D);
     constexpr int SMAX = DD > NS + D ? DD : NS + D;
+    constexpr bool SP = KIND == S3O_KIND_SIM3 && JAC == S3O_JAC_ANALYTIC;      // structured Jacobians
     __shared__ double stage_all[(NT / 32) * 32 * SMAX];
     __shared__ double *dptr_all[NT];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -448,10 +455,10 @@ __global__ void __launch_bounds__(NT) linearize_kernel(GraphDev g, double h, dou
 #pragma unroll
             for (int c = 0; c < D; ++c) {
                 double acc = 0;
-                if constexpr (DIAG) acc = A[c * D + r] * O[c];
+                if constexpr (DIAG) { if (jnz<SP>(c, r)) acc = A[c * D + r] * O[c]; }
                 else {
 #pragma unroll
-                    for (int k = 0; k < D; ++k) acc += A[k * D + r] * O[k * D + c];
+                    for (int k = 0; k < D; ++k) if (jnz<SP>(k, r)) acc += A[k * D + r] * O[k * D + c];
                 }
                 P[r * D + c] = acc;
             }
@@ -462,14 +469,14 @@ __global__ void __launch_bounds__(NT) linearize_kernel(GraphDev g, double h, dou
             for (int c = r; c < D; ++c) {
                 double acc = 0;
 #pragma unroll
-                for (int k = 0; k < D; ++k) acc += P[r * D + k] * A[k * D + c];
+                for (int k = 0; k < D; ++k) if ((!DIAG || jnz<SP>(k, r)) && jnz<SP>(k, c)) acc += P[r * D + k] * A[k * D + c];
                 out[f++] = acc;
             }
 #pragma unroll
         for (int r = 0; r < D; ++r) {
             double acc = 0;
 #pragma unroll
-            for (int k = 0; k < D; ++k) acc += P[r * D + k] * e[k];
+            for (int k = 0; k < D; ++k) if (!DIAG || jnz<SP>(k, r)) acc += P[r * D + k] * e[k];
             out[NS + r] = -acc;
         }
     }
@@ -489,7 +496,7 @@ __global__ void __launch_bounds__(NT) linearize_kernel(GraphDev g, double h, dou
             for (int c = 0; c < D; ++c) {
                 double acc = 0;
 #pragma unroll
-                for (int k = 0; k < D; ++k) acc += P[r * D + k] * B[k * D + c];
+                for (int k = 0; k < D; ++k) if ((!DIAG || jnz<SP>(k, r)) && jnz<SP>(k, c)) acc += P[r * D + k] * B[k * D + c];
                 out[r * D + c] = acc;
             }
         if (flip) {
@@ -507,10 +514,10 @@ __global__ void __launch_bounds__(NT) linearize_kernel(GraphDev g, double h, dou
 #pragma unroll
             for (int c = 0; c < D; ++c) {
                 double acc = 0;
-                if constexpr (DIAG) acc = B[c * D + r] * O[c];
+                if constexpr (DIAG) { if (jnz<SP>(c, r)) acc = B[c * D + r] * O[c]; }
                 else {
 #pragma unroll
-                    for (int k = 0; k < D; ++k) acc += B[k * D + r] * O[k * D + c];
+                    for (int k = 0; k < D; ++k) if (jnz<SP>(k, r)) acc += B[k * D + r] * O[k * D + c];
                 }
                 P[r * D + c] = acc;
             }
@@ -521,14 +528,14 @@ __global__ void __launch_bounds__(NT) linearize_kernel(GraphDev g, double h, dou
             for (int c = r; c < D; ++c) {
                 double acc = 0;
 #pragma unroll
-                for (int k = 0; k < D; ++k) acc += P[r * D + k] * B[k * D + c];
+                for (int k = 0; k < D; ++k) if ((!DIAG || jnz<SP>(k, r)) && jnz<SP>(k, c)) acc += P[r * D + k] * B[k * D + c];
                 out[f++] = acc;
             }
 #pragma unroll
         for (int r = 0; r < D; ++r) {
             double acc = 0;
 #pragma unroll
-            for (int k = 0; k < D; ++k) acc += P[r * D + k] * e[k];
+            for (int k = 0; k < D; ++k) if (!DIAG || jnz<SP>(k, r)) acc += P[r * D + k] * e[k];
             out[NS + r] = -acc;
         }
     }

@@ -266,7 +266,22 @@ static __device__ __noinline__ void sim3_jl_inv(const double e[7], JlInv &out) {
 #pragma unroll
     for (int i = 0; i < 9; ++i) M[i] = Om[i];
     M[0] += e[6]; M[4] += e[6]; M[8] += e[6];
-    double Omn[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
+    // Number of terms from a bound on the series tail instead of a per-term maximum over 30 entries:
+    // |ad_e^n| <= a^n with a = |omega| + |upsilon| + |sigma| (row sums of the blocks), term n carries 1/(n+1)!.
+    const double theta2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+    const double a = sqrt(theta2) + sqrt(e[3] * e[3] + e[4] * e[4] + e[5] * e[5]) + fabs(e[6]);
+    int nterms = 2;
+    {
+        double bound = a * 0.5;          // a^1 / 2!
+        while (bound * (1.0 + a) >= 1e-18 && nterms < 80) { bound *= a / (double)(nterms + 1); ++nterms; }
+    }
+    // Om^n needs no product: Om^3 = -theta^2 Om, so Om^(n+2) = -theta^2 Om^n.
+    double Om2[9];
+    mat3_mul(Om, Om, Om2);
+    double Oa[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };      // Om^(n-1), alternating buffers: even powers / odd powers
+    double Ob[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Ob[i] = Om[i];
     double Mn[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
     double Pn[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
     double vn[3] = { 0, 0, 0 };
@@ -275,10 +290,11 @@ static __device__ __noinline__ void sim3_jl_inv(const double e[7], JlInv &out) {
     double Q[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
     double w[3] = { 0, 0, 0 };
     double c = 1.0;
-    for (int n = 1; n < 80; ++n) {
+    for (int n = 1; n < nterms; ++n) {
+        // entering: Oa = Om^(n-1), Ob = Om^n, Mn = M^(n-1), Pn = P_(n-1), vn = M^(n-2) ups
         double T1[9], T2[9];
         mat3_mul(M, Pn, T1);
-        mat3_mul(Up, Omn, T2);
+        mat3_mul(Up, Oa, T2);
 #pragma unroll
         for (int i = 0; i < 9; ++i) Pn[i] = T1[i] + T2[i];
         if (n == 1) {
@@ -289,25 +305,20 @@ static __device__ __noinline__ void sim3_jl_inv(const double e[7], JlInv &out) {
             const double a2 = M[6] * vn[0] + M[7] * vn[1] + M[8] * vn[2];
             vn[0] = a0; vn[1] = a1; vn[2] = a2;
         }
-        mat3_mul(Om, Omn, T1);
         mat3_mul(M, Mn, T2);
         c /= (double)(n + 1);
-        double mx = 0;
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
-            Omn[i] = T1[i];
             Mn[i] = T2[i];
-            Jw[i] += c * Omn[i];
+            Jw[i] += c * Ob[i];              // Ob = Om^n
             W[i] += c * Mn[i];
             Q[i] += c * Pn[i];
-            mx = fmax(mx, fmax(fabs(Omn[i]), fmax(fabs(Mn[i]), fabs(Pn[i]))));
+            const double next = n == 1 ? Om2[i] : -theta2 * Oa[i];      // Om^(n+1)
+            Oa[i] = Ob[i];
+            Ob[i] = next;
         }
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            w[i] -= c * vn[i];
-            mx = fmax(mx, fabs(vn[i]));
-        }
-        if (c * mx < 1e-18) break;
+        for (int i = 0; i < 3; ++i) w[i] -= c * vn[i];
     }
     inv3(Jw, out.Jw);
     inv3(W, out.Wi);
