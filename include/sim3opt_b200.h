@@ -45,7 +45,9 @@ enum s3o_status {
     S3O_ERR_CUDA = -2,      /* CUDA runtime failure (no device, OOM, launch error) */
     S3O_ERR_NCCL = -3,
     S3O_ERR_IO = -4,
-    S3O_ERR_UNSUPPORTED = -5
+    S3O_ERR_UNSUPPORTED = -5,
+    S3O_ERR_SOLVE = -6      /* the linear solve failed: matrix not positive definite (pivot / PCG breakdown) or the PCG
+                               hit its iteration cap -- g2o's LinearSolver::solve() == false */
 };
 
 enum s3o_kind { S3O_KIND_SIM3 = 0, S3O_KIND_SCALE_TRANS = 1, S3O_KIND_SCALE = 2, S3O_KIND_BA = 3 };
@@ -170,7 +172,8 @@ int s3o_linearize(s3o_problem *p);                          /* BlockSolver::buil
 /* blocks in the g2o CCS order of s3o_get_structure, each d x d row-major; b: n_free*d */
 int s3o_get_hessian(s3o_problem *p, double *blocks, double *b);
 int s3o_max_diag(s3o_problem *p, double *max_diag);
-/* solve (H + lambda I) x = b by block-Jacobi PCG; x: n_free*d (may be NULL) */
+/* solve (H + lambda I) x = b with the configured linear solver; x: n_free*d (may be NULL).  S3O_ERR_SOLVE on a
+ * breakdown (matrix not positive definite). */
 int s3o_solve(s3o_problem *p, double lambda, double *x, int *pcg_iters, double *rel_residual);
 /* y = (H + lambda I) x on the device (x, y: n_free*d host arrays) -- for backward-error checks */
 int s3o_hessian_multiply(s3o_problem *p, double lambda, const double *x, double *y);
@@ -247,7 +250,7 @@ int s3o_ba_get_schur(s3o_problem *p, double lambda, double *blocks, double *bs);
  * s3o_linear_solver), block-Jacobi PCG (s3o_set_pcg on the handle) otherwise.  The handle caches the pattern, the
  * factorisation plan and all device buffers between calls (LinearSolver::init() once, solve() per LM trial).  The
  * whole-LM entry s3o_optimize avoids the per-trial PCIe round trip of A, x, b that this cut implies.
- * Returns S3O_OK, or S3O_RESULT_FAIL when the matrix is not positive definite / the PCG did not converge (g2o:
+ * Returns S3O_OK, or S3O_ERR_SOLVE when the matrix is not positive definite / the PCG did not converge (g2o:
  * solve() == false -> the LM raises lambda). */
 typedef struct s3o_problem s3o_linsolver;
 int s3o_linsolver_create(int device, int block_dim /* 1, 4, 6 or 7 */, s3o_linsolver **out);

@@ -154,8 +154,8 @@ class Problem:
         x = np.zeros(st["n_free"] * self.d)
         it, rel = C.c_int(0), C.c_double(0)
         rc = self.L.s3o_solve(self.h, float(lam), _d(x), C.byref(it), C.byref(rel))
-        if rc not in (0, -1) or (rc == -1 and self.L.s3o_last_error()):
-            pass
+        if rc not in (0, -6):            # -6 = S3O_ERR_SOLVE: reported to the caller like g2o's solve() == false
+            self._check(rc)
         return rc, x, it.value, rel.value
 
     def hessian_multiply(self, lam, x):
@@ -324,7 +324,7 @@ class LinearSolver:
         self.L.s3o_set_pcg(self.h, rel_tol, max_iter)
 
     def solve(self, colptr, rowidx, blocks, b, lam=0.0, column_major=False):
-        """Returns (rc, x, method, pcg_iterations); rc 0 ok, -1 not positive definite / not converged."""
+        """Returns (rc, x, method, pcg_iterations); rc 0 ok, -6 (S3O_ERR_SOLVE) not positive definite / not converged."""
         colptr = np.ascontiguousarray(colptr, np.int32)
         rowidx = np.ascontiguousarray(rowidx, np.int32)
         blocks = _f64(blocks)
@@ -334,7 +334,7 @@ class LinearSolver:
         method, its = C.c_int(0), C.c_int(0)
         rc = self.L.s3o_linsolver_solve(self.h, n, colptr.ctypes.data_as(_ip), rowidx.ctypes.data_as(_ip), _d(blocks),
                                         1 if column_major else 0, float(lam), _d(b), _d(x), C.byref(method), C.byref(its))
-        if rc not in (0, -1):
+        if rc not in (0, -6):
             raise S3OError(f"s3o error {rc}: {self.L.s3o_last_error().decode()}")
         return rc, x, method.value, its.value
 

@@ -868,20 +868,27 @@ __device__ __forceinline__ void coop_down(const CoopLevel &L, const RSpec R, dou
         xi *= omega;
         double acc = 0;
         const int kb = L.rowptr[i], ke = L.rowptr[i + 1];
-        for (int k = kb; k < ke; ++k) {
-            const int j = L.colidx[k];
-            double xj;
-            if (j == i) xj = xi;
-            else {
-                const double rj = rget(R, (size_t)j * D + lc);
-                xj = 0;
+        // blocks in chunks of U: all index loads of a chunk are issued before the dependent vector loads, all of
+        // those before the arithmetic (these levels live in L2: the phase is a chain of load latencies)
+        constexpr int U = 4;
+        for (int k0 = kb; k0 < ke; k0 += U) {
+            int j[U];
+            double rj[U];
 #pragma unroll
-                for (int c = 0; c < D; ++c) xj += L.Dinv[(size_t)j * sym_size<D>() + sym_off<D>(lc, c)] * gshfl(gmask, rj, c);
+            for (int u = 0; u < U; ++u) j[u] = k0 + u < ke ? L.colidx[k0 + u] : i;
+#pragma unroll
+            for (int u = 0; u < U; ++u) rj[u] = rget(R, (size_t)j[u] * D + lc);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (k0 + u >= ke) break;                 // uniform inside the group
+                double xj = 0;
+#pragma unroll
+                for (int c = 0; c < D; ++c) xj += L.Dinv[(size_t)j[u] * sym_size<D>() + sym_off<D>(lc, c)] * gshfl(gmask, rj[u], c);
                 xj *= omega;
-            }
-            const double *Ak = L.A + (size_t)k * DD + lc * D;
+                const double *Ak = L.A + (size_t)(k0 + u) * DD + lc * D;
 #pragma unroll
-            for (int c = 0; c < D; ++c) acc += Ak[c] * gshfl(gmask, xj, c);
+                for (int c = 0; c < D; ++c) acc += Ak[c] * gshfl(gmask, xj, c);
+            }
         }
         if (l < D) {
             L.x[(size_t)i * D + l] = xi;
@@ -931,29 +938,37 @@ __device__ __forceinline__ void coop_up(const CoopLevel &F, const CoopLevel &C, 
     const int groups = nth / 8, g = gtid / 8, l = gtid & 7;
     const unsigned gmask = 0xffu << (threadIdx.x & 24);
     const int lc = l < D ? l : 0;
-    auto prolonged = [&](int v, double xp[D]) {
-        const Rel S = load_rel(C.rel, C.pad_fine, v);
-        const int I = C.agg[v];
-        double xc[D], u[D];
-#pragma unroll
-        for (int c = 0; c < D; ++c) xc[c] = xget(X, (size_t)I * D + c);
-        Xf<D>::apply(S, xc, u);
-#pragma unroll
-        for (int c = 0; c < D; ++c) xp[c] = __ldcg(F.x + (size_t)v * D + c) + u[c];
-    };
     for (int i = g; i < F.n; i += groups) {
         double acc = 0, xi_l = 0;
         const int kb = F.rowptr[i], ke = F.rowptr[i + 1];
-        for (int k = kb; k < ke; ++k) {
-            const int j = F.colidx[k];
-            double xp[D];
-            prolonged(j, xp);
-            const double *Ak = F.A + (size_t)k * DD + lc * D;
+        constexpr int U = 4;
+        for (int k0 = kb; k0 < ke; k0 += U) {
+            int j[U], I[U];
 #pragma unroll
-            for (int c = 0; c < D; ++c) acc += Ak[c] * xp[c];
-            if (j == i) {
+            for (int u = 0; u < U; ++u) j[u] = k0 + u < ke ? F.colidx[k0 + u] : i;
 #pragma unroll
-                for (int c = 0; c < D; ++c) xi_l = (c == lc) ? xp[c] : xi_l;
+            for (int u = 0; u < U; ++u) I[u] = C.agg[j[u]];
+            double xp[U][D];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const Rel S = load_rel(C.rel, C.pad_fine, j[u]);
+                double xc[D], v[D];
+#pragma unroll
+                for (int c = 0; c < D; ++c) xc[c] = xget(X, (size_t)I[u] * D + c);
+                Xf<D>::apply(S, xc, v);
+#pragma unroll
+                for (int c = 0; c < D; ++c) xp[u][c] = __ldcg(F.x + (size_t)j[u] * D + c) + v[c];
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (k0 + u >= ke) break;
+                const double *Ak = F.A + (size_t)(k0 + u) * DD + lc * D;
+#pragma unroll
+                for (int c = 0; c < D; ++c) acc += Ak[c] * xp[u][c];
+                if (j[u] == i) {
+#pragma unroll
+                    for (int c = 0; c < D; ++c) xi_l = (c == lc) ? xp[u][c] : xi_l;
+                }
             }
         }
         const double res = rget(R, (size_t)i * D + lc) - acc;
@@ -975,6 +990,7 @@ __device__ __forceinline__ void coop_kdots(const CoopLevel &L, const double *z, 
     for (int i = g; i < L.n; i += groups) {
         if (l >= D) continue;
         double acc = 0;
+#pragma unroll 4
         for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k) {
             const double *zj = z + (size_t)L.colidx[k] * D;
             const double *Ak = L.A + (size_t)k * DD + l * D;
@@ -1042,10 +1058,16 @@ amg_coop_kernel(const __grid_constant__ CoopParams P, double omega, const DevSca
             if (l == last) {
                 // the coarsest level is never a K-cycle level: its residual is the plain vector L.r
                 if (P.dense) {
-                    for (int t = gtid; t < P.N; t += nth) {
+                    // x = A^-1 r: an 8-lane group per entry, reading a row of the (symmetric) inverse contiguously
+                    const int g8 = gtid / 8, l8 = gtid & 7;
+                    for (int t0 = 0; t0 < P.N; t0 += nth / 8) {
+                        const int t = t0 + g8;
                         double acc = 0;
-                        for (int c = 0; c < P.N; ++c) acc += P.inv[(size_t)c * P.N + t] * __ldcg(L.r + c);
-                        cur_out[l][t] = acc;
+                        if (t < P.N)
+                            for (int c = l8; c < P.N; c += 8) acc += P.inv[(size_t)t * P.N + c] * __ldcg(L.r + c);
+#pragma unroll
+                        for (int off = 4; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off, 8);
+                        if (t < P.N && l8 == 0) cur_out[l][t] = acc;
                     }
                 } else if (l == 0) {    // a single coarse level too large for the dense inverse: five damped sweeps
                     coop_rows<D, 0>(L, L.r, nullptr, L.x, omega, gtid, nth);

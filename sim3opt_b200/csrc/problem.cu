@@ -581,8 +581,8 @@ int s3o_linsolver_solve(s3o_linsolver *p, int n, const int32_t *colptr, const in
     p->stats.d2h_bytes += (int64_t)n * d * 8;
     if (method) *method = direct_available(p) && p->linsolver != S3O_LINSOLVER_PCG ? S3O_LINSOLVER_DIRECT : S3O_LINSOLVER_PCG;
     if (pcg_iterations) *pcg_iterations = iters;
-    if (status == 3) { set_error("s3o_linsolver_solve: the matrix is not positive definite (pivot / PCG breakdown)"); return S3O_RESULT_FAIL; }
-    if (status == 2) { set_error("s3o_linsolver_solve: PCG hit the iteration cap"); return S3O_RESULT_FAIL; }
+    if (status == 3) { set_error("s3o_linsolver_solve: the matrix is not positive definite (pivot / PCG breakdown)"); return S3O_ERR_SOLVE; }
+    if (status == 2) { set_error("s3o_linsolver_solve: PCG hit the iteration cap"); return S3O_ERR_SOLVE; }
     return S3O_OK;
 }
 
@@ -1114,7 +1114,8 @@ int s3o_solve(s3o_problem *p, double lambda, double *x, int *pcg_iters, double *
         int rc = ba_solve(p, lambda, &status, pcg_iters, rel_residual);
         if (rc) return rc;
         if (x && (rc = ba_download_step(p, x))) return rc;
-        return status == 3 ? S3O_RESULT_FAIL : S3O_OK;
+        if (status == 3) { set_error("s3o_solve: the Schur system is not positive definite"); return S3O_ERR_SOLVE; }
+        return S3O_OK;
     }
     int rc = do_solve(p, lambda, &status, pcg_iters, rel_residual);
     if (rc) return rc;
@@ -1123,7 +1124,8 @@ int s3o_solve(s3o_problem *p, double lambda, double *x, int *pcg_iters, double *
         S3O_CUDA(cudaStreamSynchronize(p->stream));
         p->stats.d2h_bytes += (int64_t)p->S.nf * p->d * 8;
     }
-    return status == 3 ? S3O_RESULT_FAIL : S3O_OK;
+    if (status == 3) { set_error("s3o_solve: the damped Hessian is not positive definite (pivot / PCG breakdown)"); return S3O_ERR_SOLVE; }
+    return S3O_OK;
 }
 
 int s3o_hessian_multiply(s3o_problem *p, double lambda, const double *x, double *y) {

@@ -187,7 +187,7 @@ def test_linsolver_plugin_slot(kitti_k118, sphere_small):
         assert np.linalg.norm(A @ x3 - b) <= 1e-11 * np.linalg.norm(b)
         # not positive definite: solve() fails like LinearSolverEigen does, the caller's LM raises lambda
         rc, _, _, _ = ls.solve(colptr, rowidx, -H, b, 0.0)
-        assert rc == -1
+        assert rc == -6               # S3O_ERR_SOLVE
     # malformed pattern
     ls = s3.LinearSolver(7)
     with pytest.raises(s3.S3OError):
