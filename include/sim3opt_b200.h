@@ -197,6 +197,12 @@ int s3o_smallest_eigenvector(s3o_problem *p, int max_iter, double tol, double *x
 int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterations,
                  double *final_chi2, double *final_lambda, double *hist, int hist_cap);
 int s3o_get_vertices(s3o_problem *p, double *est);
+/* Optional stop rule of s3o_optimize (pose-graph kinds; g2o's optimize() has none): stop after an accepted step that
+ * moved no tangent component (rad, m, log-scale) by more than max_abs_step; 0 switches it off.  A criterion on the
+ * step is scale-free, unlike a relative chi2 gain: the distance left to the stationary point is a fraction of the
+ * last step (the LM contracts the weakly constrained modes by lambda / (mu + lambda) per iteration).  The norm of the
+ * last accepted step is also reported in s3o_stats.last_step_inf. */
+int s3o_set_stop_step(s3o_problem *p, double max_abs_step);
 /* resume = 1: the next s3o_optimize continues the LM sequence (keeps lambda, nu and the current
  * chi2) instead of re-initialising lambda at its first iteration -- lets a caller drive the LM one
  * iteration at a time.  The LM state is dropped by s3o_set_vertices / s3o_set_estimates /
@@ -278,6 +284,7 @@ typedef struct s3o_stats {
     int32_t direct_blocks;     /* blocks of the factor L */
     int64_t pcg_unconverged;   /* PCG solves that ended on the iteration cap or a breakdown (inexact LM steps) */
     double sum_ms_linearize, sum_ms_solve, sum_ms_update; /* the per-call phase times above, summed since create / reset */
+    double last_step_inf;      /* max |x_j| of the last accepted LM step (pose-graph kinds) */
 } s3o_stats;
 int s3o_get_stats(s3o_problem *p, s3o_stats *out);
 int s3o_reset_stats(s3o_problem *p);

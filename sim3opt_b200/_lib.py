@@ -28,6 +28,7 @@ class Stats(C.Structure):
         ("direct_solves", C.c_int64), ("direct_levels", C.c_int32), ("direct_blocks", C.c_int32),
         ("pcg_unconverged", C.c_int64),
         ("sum_ms_linearize", C.c_double), ("sum_ms_solve", C.c_double), ("sum_ms_update", C.c_double),
+        ("last_step_inf", C.c_double),
     ]
 
 
@@ -49,6 +50,7 @@ SYMBOLS = {
     "s3o_set_jacobian_mode": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "s3o_set_math_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "s3o_set_lm": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int]),
+    "s3o_set_stop_step": (C.c_int, [C.c_void_p, C.c_double]),
     "s3o_set_pcg": (C.c_int, [C.c_void_p, C.c_double, C.c_int]),
     "s3o_set_preconditioner": (C.c_int, [C.c_void_p, C.c_int]),
     "s3o_set_linear_solver": (C.c_int, [C.c_void_p, C.c_int]),

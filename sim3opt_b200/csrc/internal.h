@@ -59,6 +59,10 @@ void build_structure_host(int nv, const uint8_t *fixed, int ne, const int32_t *v
 void build_structure_from_hidx(int nv, const int32_t *hidx, int nfree, int ne, const int32_t *v0, const int32_t *v1,
                                HostStructure &S);
 
+// Device twin (structure_dev.cu): the same arrays from integer kernels (stable radix sort + scans); bit-identical.
+int build_structure_device(cudaStream_t st, int nv, const uint8_t *fixed, const int32_t *hidx_in, int nfree_in, int ne,
+                           const int32_t *v0, const int32_t *v1, HostStructure &S);
+
 // Vertex-range partition of the free vertices across `world` ranks.
 // Rank r owns global Hessian indices [r*seg, min((r+1)*seg, nf)), seg = ceil(nf/world).
 struct PartitionPlan {

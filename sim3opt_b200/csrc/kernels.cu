@@ -700,16 +700,21 @@ template <int NT>
 __global__ void scale_kernel(int n, const double *__restrict__ x, const double *__restrict__ b, double lambda,
                              double *__restrict__ partials, DevScalars *sc) {
     __shared__ double sh[32];
-    double local = 0;
+    double local = 0, lmax = 0;
     for (int t = blockIdx.x * NT + threadIdx.x; t < n; t += gridDim.x * NT) {
         const double xv = x[t];
         local += xv * (lambda * xv + b[t]);
+        lmax = fmax(lmax, fabs(xv));
     }
     const double bs = block_sum<NT>(local, sh);
-    if (threadIdx.x == 0) partials[blockIdx.x] = bs;
+    const double bm = block_max<NT>(lmax, sh);
+    if (threadIdx.x == 0) { partials[blockIdx.x] = bs; partials[kMaxPartials + blockIdx.x] = bm; }
     if (last_block(&sc->counters[2])) {
         const double tot = sum_partials<NT>(partials, gridDim.x, sh);
-        if (threadIdx.x == 0) sc->scale = tot;
+        double v = 0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += NT) v = fmax(v, __ldcg(partials + kMaxPartials + i));
+        v = block_max<NT>(v, sh);
+        if (threadIdx.x == 0) { sc->scale = tot; sc->xmax = v; }
     }
 }
 

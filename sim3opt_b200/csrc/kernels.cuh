@@ -18,6 +18,7 @@ struct DevScalars {
     double chi2;      // last chi2 reduction
     double scale;     // sum x_j (lambda x_j + b_j)   (computeScale)
     double maxdiag;   // max |H_jj|                  (computeLambdaInit)
+    double xmax;      // max |x_j| of the last step  (step-size stop rule)
     int done;         // 0 running, 1 converged, 2 iteration cap, 3 breakdown
     int iters, max_iter;
     int precond_fail;

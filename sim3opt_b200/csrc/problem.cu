@@ -837,6 +837,12 @@ int s3o_set_linear_solver(s3o_problem *p, int kind) {
     return S3O_OK;
 }
 
+int s3o_set_stop_step(s3o_problem *p, double max_abs_step) {
+    if (!p || !(max_abs_step >= 0)) { set_error("s3o_set_stop_step: bad arguments"); return S3O_ERR_INVALID; }
+    p->stop_step = max_abs_step;
+    return S3O_OK;
+}
+
 int s3o_set_pcg(s3o_problem *p, double rel_tol, int max_iter) {
     if (!p) return S3O_ERR_INVALID;
     if (rel_tol > 0) p->pcg_tol = rel_tol;
@@ -859,11 +865,20 @@ int s3o_build_structure(s3o_problem *p, int *n_free, int *n_blocks) {
         if (p->ne > 0 && !p->d_meas_aos) { set_error("s3o_build_structure: edges were consumed; call s3o_set_edges again"); return S3O_ERR_INVALID; }
         free_structure(p);
         HostStructure &S = p->S;
-        if (p->dist)
-            build_structure_from_hidx(p->nv, p->plan.lhidx.data(), p->plan.n_own + p->plan.n_ghost, p->ne,
-                                      p->v0.data(), p->v1.data(), S);
-        else
-            build_structure_host(p->nv, p->fixed.data(), p->ne, p->v0.data(), p->v1.data(), S);
+        // the index build runs on the device (structure_dev.cu); S3O_STRUCTURE=host selects the host twin
+        const char *where = getenv("S3O_STRUCTURE");
+        if (where && !strcmp(where, "host")) {
+            if (p->dist)
+                build_structure_from_hidx(p->nv, p->plan.lhidx.data(), p->plan.n_own + p->plan.n_ghost, p->ne,
+                                          p->v0.data(), p->v1.data(), S);
+            else
+                build_structure_host(p->nv, p->fixed.data(), p->ne, p->v0.data(), p->v1.data(), S);
+        } else {
+            const int rcs = p->dist ? build_structure_device(p->stream, p->nv, nullptr, p->plan.lhidx.data(), p->plan.n_own + p->plan.n_ghost,
+                                                             p->ne, p->v0.data(), p->v1.data(), S)
+                                    : build_structure_device(p->stream, p->nv, p->fixed.data(), nullptr, 0, p->ne, p->v0.data(), p->v1.data(), S);
+            if (rcs) return rcs;
+        }
         const int rows_own = p->dist ? p->plan.n_own : S.nf;
         p->ne_pad = pad32(S.ne_act);
         int rc = 0;
@@ -1244,6 +1259,7 @@ int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterat
                 if ((rc = check_launch(p, 2))) return rc;
             }
             if ((rc = allreduce_sum(p, &p->d_sc->scale, 1))) return rc;
+            if (p->dist && (rc = allreduce_max(p, &p->d_sc->xmax, 1))) return rc;
             if ((rc = do_chi2(p, trial))) return rc;
             cudaEventRecord(p->ev[5], p->stream);
             if ((rc = sync_scalars(p))) return rc;
@@ -1266,6 +1282,7 @@ int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterat
                 ni = 2;
                 currentChi = tempChi;
                 p->cur = trial;            // discardTop: keep the updated estimates
+                p->stats.last_step_inf = p->kind == S3O_KIND_BA ? 0.0 : p->h_sc->xmax;
             } else {
                 lambda *= ni;              // pop: the current buffer still holds the old estimates
                 ni *= 2;
@@ -1290,6 +1307,8 @@ int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterat
             const double gain = (chi_start - currentChi) / currentChi;
             if (gain >= 0 && gain < stop_rel_gain) break;
         }
+        // step-size rule: the last accepted step moved no tangent component by more than stop_step
+        if (p->stop_step > 0 && rho > 0 && p->kind != S3O_KIND_BA && p->h_sc->xmax < p->stop_step) break;
     }
     cudaEventRecord(p->ev[1], p->stream);
     S3O_CUDA(cudaStreamSynchronize(p->stream));

@@ -20,6 +20,7 @@ class _Args:
     pcg_tol = bench.PCG_TOL
     pcg_max_iter = 20000
     stop_gain = bench.STOP_REL_GAIN
+    stop_step = bench.STOP_STEP
     precond = "auto"
     seed = 42
 
@@ -64,6 +65,7 @@ def test_bench_settings_reach_the_reference_answer():
     # the round-1 settings (1e-6 gain rule) stop an order of magnitude of metres short of it: keep that visible
     class Old(_Args):
         stop_gain = 1e-6
+        stop_step = 0.0
         pcg_tol = 1e-3
     old = bench.parity_s10k(Old, s3, synth, 0)
     assert old["max_translation_m"] > 10 * bench.TOL_TRANS
