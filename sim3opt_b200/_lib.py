@@ -28,7 +28,7 @@ class Stats(C.Structure):
         ("direct_solves", C.c_int64), ("direct_levels", C.c_int32), ("direct_blocks", C.c_int32),
         ("pcg_unconverged", C.c_int64),
         ("sum_ms_linearize", C.c_double), ("sum_ms_solve", C.c_double), ("sum_ms_update", C.c_double),
-        ("last_step_inf", C.c_double),
+        ("last_step_inf", C.c_double), ("est_distance", C.c_double),
     ]
 
 

@@ -1,11 +1,41 @@
 // amg_host.cpp -- aggregation hierarchy of the multilevel preconditioner (structure only, host).
 // See amg.h.  Deterministic: vertices are visited in index order, lists are sorted.
 #include <algorithm>
+#include <thread>
 
 #include "amg.h"
 
 namespace s3o {
 namespace {
+
+// LSD radix sort of 64-bit keys on their low `bits` bits (11 bits per pass): the coarse-pattern keys of a 1M-pose
+// graph are 12 M entries, where std::sort costs most of a second
+void radix_sort_u64(std::vector<uint64_t> &a, int bits) {
+    if (a.size() < 4096) { std::sort(a.begin(), a.end()); return; }
+    constexpr int R = 11, B = 1 << R;
+    std::vector<uint64_t> tmp(a.size());
+    std::vector<size_t> cnt(B);
+    uint64_t *src = a.data(), *dst = tmp.data();
+    for (int shift = 0; shift < bits; shift += R) {
+        std::fill(cnt.begin(), cnt.end(), 0);
+        for (size_t t = 0; t < a.size(); ++t) cnt[(src[t] >> shift) & (B - 1)]++;
+        size_t run = 0;
+        for (int b = 0; b < B; ++b) { const size_t c = cnt[b]; cnt[b] = run; run += c; }
+        for (size_t t = 0; t < a.size(); ++t) dst[cnt[(src[t] >> shift) & (B - 1)]++] = src[t];
+        std::swap(src, dst);
+    }
+    if (src != a.data()) std::copy(src, src + a.size(), a.data());
+}
+
+// fn(lo, hi) over [0, n) on a few host threads (disjoint index ranges: the result does not depend on the count)
+template <class F>
+void parallel_ranges(int n, F fn) {
+    const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    if (n < 100000 || hw == 1) { fn(0, n); return; }
+    std::vector<std::thread> th;
+    for (unsigned w = 0; w < hw; ++w) th.emplace_back([=]() { fn((int)((long long)n * w / hw), (int)((long long)n * (w + 1) / hw)); });
+    for (auto &t : th) t.join();
+}
 
 struct Pattern {            // blocks of one level
     int n = 0, nblk = 0;
@@ -32,7 +62,9 @@ void build_adjacency(const Pattern &F, int seg, std::vector<int32_t> &ptr, std::
         idx[fill[i]++] = j;
         if (F.upper) idx[fill[j]++] = i;
     }
-    for (int i = 0; i < F.n; ++i) std::sort(idx.begin() + ptr[i], idx.begin() + ptr[i + 1]);
+    parallel_ranges(F.n, [&](int lo, int hi) {
+        for (int i = lo; i < hi; ++i) std::sort(idx.begin() + ptr[i], idx.begin() + ptr[i + 1]);
+    });
 }
 
 // Greedy neighbourhood aggregation: a vertex whose whole neighbourhood is still free seeds an
@@ -124,8 +156,14 @@ void amg_build_hierarchy(const HostStructure &S, int coarsest_max, int max_level
             keys.push_back(((uint64_t)I << 32) | J);
             if (F.upper && I != J) keys.push_back(((uint64_t)J << 32) | I);
         }
-        std::sort(keys.begin(), keys.end());
-        keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+        {   // keys are (I << 32) | J with I, J < L.n: compact to 2 * bits for the sort, then back
+            int bits = 1;
+            while ((1ll << bits) <= L.n) ++bits;
+            for (uint64_t &k : keys) k = ((k >> 32) << bits) | (k & 0xffffffffull);
+            radix_sort_u64(keys, 2 * bits);
+            keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+            for (uint64_t &k : keys) k = ((k >> bits) << 32) | (k & ((1ull << bits) - 1));
+        }
         const int nblk = (int)keys.size();
         L.rowptr.assign(L.n + 1, 0);
         L.colidx.resize(nblk);
@@ -166,11 +204,16 @@ void amg_build_hierarchy(const HostStructure &S, int coarsest_max, int max_level
             }
         };
         L.gal_ptr.assign(L.nub + 1, 0);
-        for (int k = 0; k < F.nblk; ++k) {
-            int ub, flag;
-            target(k, ub, flag);
-            if (ub >= 0) L.gal_ptr[ub + 1]++;
-        }
+        std::vector<int32_t> tgt(F.nblk);            // (ub << 2) | flag or -1, computed once (binary searches)
+        parallel_ranges(F.nblk, [&](int lo, int hi) {
+            for (int k = lo; k < hi; ++k) {
+                int ub, flag;
+                target(k, ub, flag);
+                tgt[k] = ub >= 0 ? (ub << 2) | flag : -1;
+            }
+        });
+        for (int k = 0; k < F.nblk; ++k)
+            if (tgt[k] >= 0) L.gal_ptr[(tgt[k] >> 2) + 1]++;
         for (int u = 0; u < L.nub; ++u) L.gal_ptr[u + 1] += L.gal_ptr[u];
         L.gal_ent.resize(L.gal_ptr[L.nub]);
         L.gal_i.resize(L.gal_ent.size());
@@ -178,9 +221,8 @@ void amg_build_hierarchy(const HostStructure &S, int coarsest_max, int max_level
         {
             std::vector<int32_t> fill(L.gal_ptr.begin(), L.gal_ptr.end() - 1);
             for (int k = 0; k < F.nblk; ++k) {
-                int ub, flag;
-                target(k, ub, flag);
-                if (ub < 0) continue;
+                if (tgt[k] < 0) continue;
+                const int ub = tgt[k] >> 2, flag = tgt[k] & 3;
                 const int pos = fill[ub]++;
                 L.gal_ent[pos] = (k << 2) | flag;
                 L.gal_i[pos] = F.brow[k];

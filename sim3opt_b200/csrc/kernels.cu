@@ -49,22 +49,24 @@ void launch_unpack_vertices(const double *soa, int n, int n_pad, int dim, double
 // gathers the caller-ordered AoS edge records into vertex-pair-sorted SoA planes; the
 // information matrix is packed to its upper triangle (row-major, r<=c).
 __global__ void pack_edges_kernel(const double *__restrict__ meas_aos, const double *__restrict__ info_aos,
-                                  const int32_t *__restrict__ perm, int ne, int ne_pad, int est_dim, int d,
+                                  const int32_t *__restrict__ perm, int ne, int ne_pad, int est_dim, int d, int info_diag,
                                   double *__restrict__ meas, double *__restrict__ info) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ne) return;
     const size_t o = (size_t)perm[t];
     for (int k = 0; k < est_dim; ++k) meas[(size_t)k * ne_pad + t] = meas_aos[o * est_dim + k];
-    if (info_aos) {
+    if (info_aos && info_diag) {         // d diagonal entries per edge in, d planes out
+        for (int r = 0; r < d; ++r) info[(size_t)r * ne_pad + t] = info_aos[o * d + r];
+    } else if (info_aos) {
         int f = 0;
         for (int r = 0; r < d; ++r)
             for (int c = r; c < d; ++c) info[(size_t)(f++) * ne_pad + t] = info_aos[o * d * d + r * d + c];
     }
 }
 void launch_pack_edges(const double *meas_aos, const double *info_aos, const int32_t *perm, int ne, int ne_pad,
-                       int est_dim, int d, double *meas, double *info, cudaStream_t st) {
+                       int est_dim, int d, int info_diag, double *meas, double *info, cudaStream_t st) {
     if (ne == 0) return;
-    pack_edges_kernel<<<(ne + 127) / 128, 128, 0, st>>>(meas_aos, info_aos, perm, ne, ne_pad, est_dim, d, meas, info);
+    pack_edges_kernel<<<(ne + 127) / 128, 128, 0, st>>>(meas_aos, info_aos, perm, ne, ne_pad, est_dim, d, info_diag, meas, info);
 }
 
 // ======================================================================================
@@ -190,11 +192,17 @@ __device__ __forceinline__ void robustify(int kind, double param, double e2, dou
 }
 
 template <int D>
-__device__ __forceinline__ double quad_form_packed(const double *__restrict__ info, int pad, int t, const double *e) {
+__device__ __forceinline__ double quad_form_packed(const double *__restrict__ info, bool info_diag, int pad, int t, const double *e) {
     if (!info) {
         double s = 0;
 #pragma unroll
         for (int i = 0; i < D; ++i) s += e[i] * e[i];
+        return s;
+    }
+    if (info_diag) {        // D planes: the diagonal only
+        double s = 0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) s += __ldg(info + (size_t)i * pad + t) * e[i] * e[i];
         return s;
     }
     double s = 0;
@@ -229,7 +237,7 @@ __global__ void __launch_bounds__(NT) chi2_kernel(GraphDev g, double *__restrict
             load_planes<4>(g.aux, g.nv_pad, vj, qj);
         }
         model_error<KIND>(m, xi, xj, qi, qj, e, g.math_corrected);
-        double c = quad_form_packed<D>(g.info, g.ne_pad, t, e);
+        double c = quad_form_packed<D>(g.info, g.info_diag, g.ne_pad, t, e);
         if (g.robust_kind != S3O_ROBUST_NONE) {
             double r0, r1;
             robustify(g.robust_kind, g.robust_param, c, r0, r1);
@@ -261,7 +269,7 @@ __global__ void edge_errors_kernel(GraphDev g, double *__restrict__ err, double 
     }
     model_error<KIND>(m, xi, xj, qi, qj, e, g.math_corrected);
     for (int k = 0; k < D; ++k) err[(size_t)t * D + k] = e[k];
-    if (chi) chi[t] = quad_form_packed<D>(g.info, g.ne_pad, t, e);
+    if (chi) chi[t] = quad_form_packed<D>(g.info, g.info_diag, g.ne_pad, t, e);
 }
 
 static int reduce_grid(int n, int nt) {
@@ -404,7 +412,7 @@ __global__ void __launch_bounds__(NT) linearize_kernel(GraphDev g, double h, dou
         if constexpr (DIAG) {
 #pragma unroll
             for (int r = 0; r < D; ++r)
-                O[r] = g.info ? __ldg(g.info + (size_t)(r * D - (r * (r - 1)) / 2) * g.ne_pad + t) : 1.0;
+                O[r] = g.info ? __ldg(g.info + (size_t)r * g.ne_pad + t) : 1.0;       // diagonal information: D planes
             if (g.robust_kind != S3O_ROBUST_NONE) {
                 double c2 = 0;
 #pragma unroll

@@ -33,7 +33,7 @@ struct GraphDev {
     const int32_t *hidx;     // [nv]
     const int32_t *sv0, *sv1; // [ne]
     const double *meas;      // [est_dim][ne_pad]
-    const double *info;      // [ninfo][ne_pad] or null (identity)
+    const double *info;      // [ninfo][ne_pad] packed upper triangles, [d][ne_pad] diagonals when info_diag, or null (identity)
     bool info_diag;          // every information matrix is diagonal (checked on the host in s3o_set_edges)
     int robust_kind;
     double robust_param;
@@ -64,7 +64,7 @@ constexpr int kMaxPartials = 4096;
 void launch_pack_vertices(const double *aos, int n, int n_pad, int dim, double *soa, cudaStream_t st);
 void launch_unpack_vertices(const double *soa, int n, int n_pad, int dim, double *aos, cudaStream_t st);
 void launch_pack_edges(const double *meas_aos, const double *info_aos, const int32_t *perm, int ne, int ne_pad,
-                       int est_dim, int d, double *meas, double *info, cudaStream_t st);
+                       int est_dim, int d, int info_diag, double *meas, double *info, cudaStream_t st);
 
 // ---- per-edge --------------------------------------------------------------------------
 void launch_chi2(const GraphDev &g, double *partials, DevScalars *sc, cudaStream_t st);

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <thread>
 #include <vector>
 
 #include "problem.h"
@@ -729,13 +730,21 @@ int s3o_set_edges(s3o_problem *p, int n, const int32_t *v0, const int32_t *v1, c
     p->user_ne = n;
     p->has_info = info != nullptr;
     p->info_diag = false;
-    if (info) {     // diagonal information matrices (the usual case) take the cheaper linearisation path
-        const int dd = p->d * p->d;
-        bool diag = true;
-        for (size_t k = 0; k < (size_t)n && diag; ++k)
-            for (int e = 0; e < dd && diag; ++e)
-                if (e / p->d != e % p->d && info[k * dd + e] != 0.0) diag = false;
-        p->info_diag = diag;
+    if (info && n > 0) {     // diagonal information matrices (the usual case) are kept as their d diagonal entries
+        const int dd = p->d * p->d, d = p->d;
+        const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        std::vector<char> nondiag(hw, 0);
+        std::vector<std::thread> th;
+        for (unsigned w = 0; w < hw; ++w)
+            th.emplace_back([&, w]() {
+                const size_t lo = (size_t)n * w / hw, hi = (size_t)n * (w + 1) / hw;
+                for (size_t k = lo; k < hi && !nondiag[w]; ++k)
+                    for (int e = 0; e < dd; ++e)
+                        if (e / d != e % d && info[k * dd + e] != 0.0) { nondiag[w] = 1; break; }
+            });
+        for (auto &t : th) t.join();
+        p->info_diag = true;
+        for (char f : nondiag) if (f) p->info_diag = false;
     }
     std::vector<double> meas_loc, info_loc;
     if (p->dist) {
@@ -764,13 +773,24 @@ int s3o_set_edges(s3o_problem *p, int n, const int32_t *v0, const int32_t *v1, c
     }
     p->ne = n;
     int rc;
-    const size_t mcount = (size_t)n * p->est_dim, icount = (size_t)n * p->d * p->d;
+    const size_t mcount = (size_t)n * p->est_dim;
     if ((rc = dev_alloc(&p->d_meas_aos, mcount))) return rc;
     if (n) S3O_CUDA(cudaMemcpyAsync(p->d_meas_aos, meas, mcount * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     p->stats.h2d_bytes += (int64_t)(mcount * sizeof(double));
+    std::vector<double> info_diag_host;
     if (info) {
+        const int d = p->d, dd = d * d;
+        const double *src = info;
+        size_t icount = (size_t)n * dd;
+        if (p->info_diag) {         // 56 B per edge over PCIe instead of 392 B
+            info_diag_host.resize((size_t)n * d);
+            for (size_t k = 0; k < (size_t)n; ++k)
+                for (int r = 0; r < d; ++r) info_diag_host[k * d + r] = info[k * dd + r * d + r];
+            src = info_diag_host.data();
+            icount = (size_t)n * d;
+        }
         if ((rc = dev_alloc(&p->d_info_aos, icount))) return rc;
-        if (n) S3O_CUDA(cudaMemcpyAsync(p->d_info_aos, info, icount * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        if (n) S3O_CUDA(cudaMemcpyAsync(p->d_info_aos, src, icount * sizeof(double), cudaMemcpyHostToDevice, p->stream));
         p->stats.h2d_bytes += (int64_t)(icount * sizeof(double));
     }
     S3O_CUDA(cudaStreamSynchronize(p->stream));
@@ -907,16 +927,17 @@ int s3o_build_structure(s3o_problem *p, int *n_free, int *n_blocks) {
         p->want_p2p_setup = p->dist;
         rc = rc ? rc : upload(p, &d_perm, S.perm);
         rc = rc ? rc : dev_alloc(&p->d_meas, (size_t)p->ne_pad * p->est_dim);
-        if (p->has_info) rc = rc ? rc : dev_alloc(&p->d_info, (size_t)p->ne_pad * p->ninfo);
+        const int info_planes = p->info_diag ? p->d : p->ninfo;
+        if (p->has_info) rc = rc ? rc : dev_alloc(&p->d_info, (size_t)p->ne_pad * info_planes);
         rc = rc ? rc : alloc_linear_system(p);
         rc = rc ? rc : dev_alloc(&p->d_scratch, (size_t)p->ne_pad * scratch_stride(p->d));
         const size_t nfd = (size_t)std::max(S.nf, p->dist ? p->plan.seg : 0) * p->d;
         if (rc) { dev_free(d_perm); free_structure(p); return rc; }
         if (S.ne_act > 0) {
             cudaMemsetAsync(p->d_meas, 0, (size_t)p->ne_pad * p->est_dim * sizeof(double), p->stream);
-            if (p->has_info) cudaMemsetAsync(p->d_info, 0, (size_t)p->ne_pad * p->ninfo * sizeof(double), p->stream);
+            if (p->has_info) cudaMemsetAsync(p->d_info, 0, (size_t)p->ne_pad * info_planes * sizeof(double), p->stream);
             launch_pack_edges(p->d_meas_aos, p->has_info ? p->d_info_aos : nullptr, d_perm, S.ne_act, p->ne_pad,
-                              p->est_dim, p->d, p->d_meas, p->d_info, p->stream);
+                              p->est_dim, p->d, p->info_diag ? 1 : 0, p->d_meas, p->d_info, p->stream);
             p->stats.kernel_launches += 1;
         }
         cudaMemsetAsync(p->d_x, 0, nfd * sizeof(double), p->stream);
@@ -1208,6 +1229,7 @@ int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterat
     const int nf = own_rows(p), d = p->d;
     const bool resume = p->lm_resume != 0 && p->lm_valid;
     double lambda = resume ? p->lm_lambda : 0, ni = resume ? p->lm_ni : 2, currentChi = resume ? p->lm_chi : 0;
+    if (!resume) { p->lm_prev_step = 0; p->lm_est_dist = 0; }
     int done = 0;
     p->stats.ms_linearize = p->stats.ms_solve = p->stats.ms_chi2 = p->stats.ms_update = p->stats.ms_total = 0;
     cudaEventRecord(p->ev[0], p->stream);
@@ -1282,7 +1304,16 @@ int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterat
                 ni = 2;
                 currentChi = tempChi;
                 p->cur = trial;            // discardTop: keep the updated estimates
-                p->stats.last_step_inf = p->kind == S3O_KIND_BA ? 0.0 : p->h_sc->xmax;
+                if (p->kind != S3O_KIND_BA) {
+                    // distance left to the stationary point, from the linear convergence of the accepted steps:
+                    // step_k * rho / (1 - rho) with rho = step_k / step_(k-1) (no estimate until the steps contract)
+                    const double step = p->h_sc->xmax, prev = p->lm_prev_step;
+                    const double ratio = prev > 0 ? step / prev : 1.0;
+                    p->lm_est_dist = ratio < 0.5 ? step * ratio / (1.0 - ratio) : step;
+                    p->lm_prev_step = step;
+                    p->stats.last_step_inf = step;
+                    p->stats.est_distance = p->lm_est_dist;
+                }
             } else {
                 lambda *= ni;              // pop: the current buffer still holds the old estimates
                 ni *= 2;
@@ -1308,7 +1339,7 @@ int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterat
             if (gain >= 0 && gain < stop_rel_gain) break;
         }
         // step-size rule: the last accepted step moved no tangent component by more than stop_step
-        if (p->stop_step > 0 && rho > 0 && p->kind != S3O_KIND_BA && p->h_sc->xmax < p->stop_step) break;
+        if (p->stop_step > 0 && rho > 0 && p->kind != S3O_KIND_BA && p->lm_est_dist < p->stop_step) break;
     }
     cudaEventRecord(p->ev[1], p->stream);
     S3O_CUDA(cudaStreamSynchronize(p->stream));
