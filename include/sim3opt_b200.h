@@ -197,13 +197,19 @@ int s3o_smallest_eigenvector(s3o_problem *p, int max_iter, double tol, double *x
 int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterations,
                  double *final_chi2, double *final_lambda, double *hist, int hist_cap);
 int s3o_get_vertices(s3o_problem *p, double *est);
-/* Optional stop rule of s3o_optimize (pose-graph kinds; g2o's optimize() has none): stop once the estimated distance
- * to the stationary point is below max_abs_step in every tangent component (rad, m, log-scale); 0 switches it off.
- * The estimate comes from the accepted steps' max-norms s_k, which contract linearly near the solution (the LM
- * damps a weakly constrained mode by lambda / (mu + lambda) per iteration): s_k r / (1 - r) with r = s_k / s_(k-1)
- * once r < 1/2, s_k itself before that.  Unlike a relative chi2 gain it does not depend on the size of the graph.
- * s3o_stats reports s_k (last_step_inf) and the estimate (est_distance). */
-int s3o_set_stop_step(s3o_problem *p, double max_abs_step);
+/* Optional stop rules of s3o_optimize (g2o's optimize() has none; 0 switches a rule off):
+ *  max_abs_step (pose-graph kinds): stop once the estimated distance to the stationary point is below it in every
+ *    tangent component (rad, m, log-scale).  The estimate comes from the accepted steps' max-norms s_k, which contract
+ *    near the solution (the LM damps a weakly constrained mode by lambda / (mu + lambda) per iteration):
+ *    s_k r / (1 - r) with r = s_k / s_(k-1) once r < 1/2, s_k itself before that.  Unlike a relative chi2 gain it does
+ *    not depend on the size of the graph.
+ *  min_rel_predicted_decrease: stop when a step's predicted decrease sum x_j (lambda x_j + b_j) falls below this
+ *    fraction of chi2 -- from there on the fp64 chi2 sums cannot resolve the step, g2o's acceptance test
+ *    rho = (chi2 - chi2_new) / predicted is decided by round-off and the LM only burns trials (1e-12 is about the
+ *    resolution of a sum over millions of edges).
+ * s3o_stats reports s_k (last_step_inf), the estimate (est_distance) and which rule ended the last call
+ * (stop_reason: 0 iteration count, 1 chi2 gain, 2 step, 3 resolution, 4 g2o Terminate). */
+int s3o_set_stop_rules(s3o_problem *p, double max_abs_step, double min_rel_predicted_decrease);
 /* resume = 1: the next s3o_optimize continues the LM sequence (keeps lambda, nu and the current
  * chi2) instead of re-initialising lambda at its first iteration -- lets a caller drive the LM one
  * iteration at a time.  The LM state is dropped by s3o_set_vertices / s3o_set_estimates /
@@ -286,7 +292,9 @@ typedef struct s3o_stats {
     int64_t pcg_unconverged;   /* PCG solves that ended on the iteration cap or a breakdown (inexact LM steps) */
     double sum_ms_linearize, sum_ms_solve, sum_ms_update; /* the per-call phase times above, summed since create / reset */
     double last_step_inf;      /* max |x_j| of the last accepted LM step (pose-graph kinds) */
-    double est_distance;       /* estimated max-norm distance to the stationary point after it (s3o_set_stop_step) */
+    double est_distance;       /* estimated max-norm distance to the stationary point after it (s3o_set_stop_rules) */
+    int32_t stop_reason;       /* why the last s3o_optimize returned (s3o_set_stop_rules) */
+    int32_t reserved0;
 } s3o_stats;
 int s3o_get_stats(s3o_problem *p, s3o_stats *out);
 int s3o_reset_stats(s3o_problem *p);

@@ -29,6 +29,7 @@ class Stats(C.Structure):
         ("pcg_unconverged", C.c_int64),
         ("sum_ms_linearize", C.c_double), ("sum_ms_solve", C.c_double), ("sum_ms_update", C.c_double),
         ("last_step_inf", C.c_double), ("est_distance", C.c_double),
+        ("stop_reason", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -50,7 +51,7 @@ SYMBOLS = {
     "s3o_set_jacobian_mode": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "s3o_set_math_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "s3o_set_lm": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int]),
-    "s3o_set_stop_step": (C.c_int, [C.c_void_p, C.c_double]),
+    "s3o_set_stop_rules": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "s3o_set_pcg": (C.c_int, [C.c_void_p, C.c_double, C.c_int]),
     "s3o_set_preconditioner": (C.c_int, [C.c_void_p, C.c_int]),
     "s3o_set_linear_solver": (C.c_int, [C.c_void_p, C.c_int]),

@@ -104,7 +104,8 @@ class Problem:
     def set_math_mode(self, mode): self._check(self.L.s3o_set_math_mode(self.h, int(mode)))
     def set_lm(self, tau=0.0, lambda_init=0.0, max_trials=0): self._check(self.L.s3o_set_lm(self.h, tau, lambda_init, max_trials))
     def set_pcg(self, rel_tol=0.0, max_iter=0): self._check(self.L.s3o_set_pcg(self.h, rel_tol, max_iter))
-    def set_stop_step(self, max_abs_step): self._check(self.L.s3o_set_stop_step(self.h, float(max_abs_step)))
+    def set_stop_rules(self, max_abs_step=0.0, min_rel_predicted_decrease=0.0):
+        self._check(self.L.s3o_set_stop_rules(self.h, float(max_abs_step), float(min_rel_predicted_decrease)))
     def set_preconditioner(self, kind): self._check(self.L.s3o_set_preconditioner(self.h, int(kind)))
     def set_linear_solver(self, kind): self._check(self.L.s3o_set_linear_solver(self.h, int(kind)))
 

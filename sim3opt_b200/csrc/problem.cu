@@ -857,9 +857,10 @@ int s3o_set_linear_solver(s3o_problem *p, int kind) {
     return S3O_OK;
 }
 
-int s3o_set_stop_step(s3o_problem *p, double max_abs_step) {
-    if (!p || !(max_abs_step >= 0)) { set_error("s3o_set_stop_step: bad arguments"); return S3O_ERR_INVALID; }
+int s3o_set_stop_rules(s3o_problem *p, double max_abs_step, double min_rel_predicted_decrease) {
+    if (!p || !(max_abs_step >= 0) || !(min_rel_predicted_decrease >= 0)) { set_error("s3o_set_stop_rules: bad arguments"); return S3O_ERR_INVALID; }
     p->stop_step = max_abs_step;
+    p->stop_pred = min_rel_predicted_decrease;
     return S3O_OK;
 }
 
@@ -1256,6 +1257,7 @@ int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterat
         const double chi_start = currentChi;
         double rho = 0;
         int qmax = 0, pcg_total = 0;
+        bool unresolved = false;
         do {
             cudaEventRecord(p->ev[3], p->stream);
             int status = 0, iters = 0;
@@ -1296,6 +1298,12 @@ int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterat
             double scale = p->h_sc->scale;
             scale += 1e-3;
             rho /= scale;
+            // s3o_set_stop_rules: the predicted decrease of this step is below what the fp64 chi2 sums resolve, so
+            // g2o's acceptance test would be decided by round-off (and so would that of every further trial).  The
+            // quadratic model is exact to that precision here: take the step if chi2 stayed inside the noise band,
+            // and stop.
+            const bool unresolved_step = p->stop_pred > 0 && ok2 && p->h_sc->scale >= 0 && p->h_sc->scale < p->stop_pred * currentChi;
+            if (unresolved_step && std::isfinite(tempChi) && tempChi - currentChi <= 10 * p->stop_pred * currentChi && !(rho > 0)) rho = 1e-300;
             if (rho > 0 && std::isfinite(tempChi)) {
                 double alpha = 1. - std::pow((2 * rho - 1), 3);
                 alpha = std::min(alpha, 2. / 3.);
@@ -1320,6 +1328,9 @@ int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterat
             }
             qmax++;
             p->stats.lm_trials++;
+            // the predicted decrease of this step is below what the chi2 sums can resolve: the acceptance test
+            // above was decided by round-off, and so would be that of every further trial
+            if (unresolved_step) { unresolved = true; break; }
         } while (rho < 0 && qmax < p->max_trials);
         {
             float ms = 0;
@@ -1333,13 +1344,15 @@ int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterat
             hist[it * 5 + 0] = currentChi; hist[it * 5 + 1] = lambda; hist[it * 5 + 2] = qmax;
             hist[it * 5 + 3] = rho; hist[it * 5 + 4] = pcg_total;
         }
-        if (qmax == p->max_trials || rho == 0) { result = S3O_RESULT_TERMINATE; break; }
+        p->stats.stop_reason = 0;
+        if (unresolved) { p->stats.stop_reason = 3; break; }
+        if (qmax == p->max_trials || rho == 0) { result = S3O_RESULT_TERMINATE; p->stats.stop_reason = 4; break; }
         if (stop_rel_gain > 0) {
             const double gain = (chi_start - currentChi) / currentChi;
-            if (gain >= 0 && gain < stop_rel_gain) break;
+            if (gain >= 0 && gain < stop_rel_gain) { p->stats.stop_reason = 1; break; }
         }
         // step-size rule: the last accepted step moved no tangent component by more than stop_step
-        if (p->stop_step > 0 && rho > 0 && p->kind != S3O_KIND_BA && p->lm_est_dist < p->stop_step) break;
+        if (p->stop_step > 0 && rho > 0 && p->kind != S3O_KIND_BA && p->lm_est_dist < p->stop_step) { p->stats.stop_reason = 2; break; }
     }
     cudaEventRecord(p->ev[1], p->stream);
     S3O_CUDA(cudaStreamSynchronize(p->stream));

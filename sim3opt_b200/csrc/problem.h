@@ -88,7 +88,7 @@ struct s3o_problem {
     double jac_h = 1e-9;
     double tau = 1e-5, user_lambda = 0;
     int max_trials = 10;
-    double stop_step = 0;                   // s3o_set_stop_step: stop when an accepted step has max |x_j| below it
+    double stop_step = 0, stop_pred = 0;    // s3o_set_stop_rules
     double pcg_tol = 1e-8;
     int pcg_max_iter = 1000;
     int precond = S3O_PRECOND_AUTO;         // s3o_set_preconditioner

@@ -63,7 +63,8 @@ def main():
             tsum += dt
             st = p.stats()
             line = (f"it {it:2d} chi2 {chi2:.9f} lambda {lam:.3e} trials {int(hist[0][2])} pcg {int(hist[0][4])} "
-                    f"ms {dt * 1e3:8.1f} (lin {st['ms_linearize']:.1f} solve {st['ms_solve']:.1f}) cum {tsum:.3f}s")
+                    f"ms {dt * 1e3:8.1f} (lin {st['ms_linearize']:.1f} solve {st['ms_solve']:.1f}) cum {tsum:.3f}s "
+                    f"step {st['last_step_inf']:.2e} est {st['est_distance']:.2e}")
             if prev is not None:
                 line += f" gain {(prev - chi2) / chi2:.2e}"
             if gold is not None:
