@@ -79,7 +79,8 @@ enum s3o_preconditioner { S3O_PRECOND_AUTO = 0, S3O_PRECOND_BLOCK_JACOBI = 1, S3
  * elimination rounds are the parallel schedule), numeric factorisation + triangular solves per LM trial in one
  * kernel; exact like the reference's LDL^T.  PCG: preconditioned conjugate gradients (s3o_set_pcg,
  * s3o_set_preconditioner).  AUTO (default): DIRECT when the factor is small and shallow (<= 400 000 block
- * products, <= 64 elimination rounds: the KITTI-size chain-dominated graphs of the reference), PCG otherwise and
+ * products, <= 128 elimination rounds: the KITTI-size chain-dominated graphs of the reference, banded BA Schur
+ * systems), PCG otherwise and
  * always in the partitioned solve. */
 enum s3o_linear_solver { S3O_LINSOLVER_AUTO = 0, S3O_LINSOLVER_PCG = 1, S3O_LINSOLVER_DIRECT = 2 };
 /* g2o OptimizationAlgorithm::SolverResult */

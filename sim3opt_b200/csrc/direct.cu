@@ -273,7 +273,7 @@ void direct_destroy(s3o_problem *p) {
 
 // Block products above which the AUTO rule stays with PCG / above which the analysis is abandoned.
 static constexpr long long kAutoMaxPairs = 400000, kForcedMaxPairs = 60000000;
-static constexpr int kAutoMaxLevels = 64;
+static constexpr int kAutoMaxLevels = 128;
 
 // Symbolic analysis + upload, once per structure.  Returns S3O_OK also when the factor is too large
 // (direct_available() then says no).

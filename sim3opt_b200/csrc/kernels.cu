@@ -347,8 +347,11 @@ __device__ __forceinline__ constexpr bool jnz(int k, int c) { return !SP || (k <
 // DIAG: the information matrices are diagonal (or absent = identity): Omega' is held as D weights, A^T O' and
 // B^T O' are column scalings -- same numbers as the dense path (its extra terms are exact zeros), 2 of the 5
 // 7x7x7 products and a 49-double array less.
+#ifndef S3O_LIN_MINB
+#define S3O_LIN_MINB 1
+#endif
 template <int KIND, int JAC, int NT, bool DIAG>
-__global__ void __launch_bounds__(NT) linearize_kernel(GraphDev g, double h, double *__restrict__ scratch,
+__global__ void __launch_bounds__(NT, S3O_LIN_MINB) linearize_kernel(GraphDev g, double h, double *__restrict__ scratch,
                                                        const int32_t *__restrict__ e_blk,
                                                        const int32_t *__restrict__ blk_src, double *__restrict__ Hdirect) {
     constexpr int D = Model<KIND>::D, EST = Model<KIND>::EST, DD = D * D;
