@@ -37,7 +37,8 @@ struct DirectState {
     int32_t *d_upd_ptr = nullptr, *d_upd_a = nullptr, *d_upd_b = nullptr, *d_row_ptr = nullptr, *d_row_blk = nullptr, *d_row_col = nullptr;
     double *d_L = nullptr, *d_Linv = nullptr, *d_y = nullptr;
     int *d_fail = nullptr;
-    int coop_grid = 0;          // 0: single CTA
+    int coop_grid = 0;          // CTAs of the cooperative launch (<= 1: single CTA)
+    int wide_levels = 0;        // leading levels wide enough for the whole grid; the rest runs on CTA 0
     bool factored = false;
 };
 
@@ -48,21 +49,186 @@ constexpr int kDirectNT = 512;
 // loads of data written earlier in the same kernel by other SMs must bypass the (non-coherent) L1
 template <bool COOP> __device__ __forceinline__ double ldw(const double *p) { return COOP ? __ldcg(p) : *p; }
 
-template <bool COOP> __device__ __forceinline__ void phase_sync() {
-    if constexpr (COOP) cg::this_grid().sync();
-    else __syncthreads();
+// ---- phases (all take the executing thread space: tid in [0, nthreads)) ---------------------------------------
+// gather: every block of the level's columns subtracts its ordered list of L[a] L[b]^T products
+template <int D, bool COOP>
+__device__ __forceinline__ void dk_gather(const DirectDev &P, int lev, int tid, int nthreads) {
+    constexpr int DD = D * D;
+    const int c0 = P.lev_ptr[lev], c1 = P.lev_ptr[lev + 1];
+    const int t0 = P.cptr[c0], t1 = P.cptr[c1];
+    for (int item = tid; item < (t1 - t0) * DD; item += nthreads) {
+        const int t = t0 + item / DD, e = item % DD;
+        const int q0 = P.upd_ptr[t], q1 = P.upd_ptr[t + 1];
+        if (q0 == q1) continue;
+        const int r = e / D, c = e - r * D;
+        double acc = ldw<COOP>(P.L + (size_t)t * DD + e);
+        for (int q = q0; q < q1; ++q) {
+            const double *La = P.L + (size_t)P.upd_a[q] * DD + r * D;
+            const double *Lb = P.L + (size_t)P.upd_b[q] * DD + c * D;
+            double s = 0;
+#pragma unroll
+            for (int m = 0; m < D; ++m) s += ldw<COOP>(La + m) * ldw<COOP>(Lb + m);
+            acc -= s;
+        }
+        P.L[(size_t)t * DD + e] = acc;
+    }
 }
 
+// pivot + scale, one warp per column: lane 0 factors the d x d pivot (lower Cholesky, inverse of the factor kept),
+// then the warp's lanes scale the rows of the column's sub-diagonal blocks by L_kk^-T (rows are independent)
+template <int D, bool COOP>
+__device__ __forceinline__ void dk_pivot_scale(const DirectDev &P, int lev, int tid, int nthreads) {
+    constexpr int DD = D * D;
+    const int c0 = P.lev_ptr[lev], c1 = P.lev_ptr[lev + 1];
+    const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
+    for (int k = c0 + warp; k < c1; k += nwarps) {
+        double *Ld = P.L + (size_t)P.cptr[k] * DD;
+        double *Lik = P.Linv + (size_t)k * DD;
+        if (lane == 0) {
+            double A[DD], Li[DD];
+#pragma unroll
+            for (int i = 0; i < DD; ++i) A[i] = ldw<COOP>(Ld + i);
+            bool ok = true;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                double djj = A[j * D + j];
+#pragma unroll
+                for (int m = 0; m < j; ++m) djj -= A[j * D + m] * A[j * D + m];
+                if (!(djj > 0) || !isfinite(djj)) { ok = false; djj = 1; }
+                const double ljj = sqrt(djj), inv = 1.0 / ljj;
+                A[j * D + j] = ljj;
+#pragma unroll
+                for (int r = j + 1; r < D; ++r) {
+                    double v = A[r * D + j];
+#pragma unroll
+                    for (int m = 0; m < j; ++m) v -= A[r * D + m] * A[j * D + m];
+                    A[r * D + j] = v * inv;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < D; ++c)
+#pragma unroll
+                for (int r = 0; r < D; ++r) {
+                    if (r < c) { Li[r * D + c] = 0; continue; }
+                    double v = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+                    for (int m = c; m < r; ++m) v -= A[r * D + m] * Li[m * D + c];
+                    Li[r * D + c] = v / A[r * D + r];
+                }
+#pragma unroll
+            for (int r = 0; r < D; ++r)
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    Ld[r * D + c] = c <= r ? A[r * D + c] : 0.0;
+                    Lik[r * D + c] = Li[r * D + c];
+                }
+            if (!ok) *P.fail = 1;
+            __threadfence_block();
+        }
+        __syncwarp();
+        const int nsub = P.cptr[k + 1] - P.cptr[k] - 1;
+        for (int item = lane; item < nsub * D; item += 32) {
+            const int t = P.cptr[k] + 1 + item / D, r = item % D;
+            double a[D];
+            double *row = P.L + (size_t)t * DD + r * D;
+#pragma unroll
+            for (int m = 0; m < D; ++m) a[m] = ldw<COOP>(row + m);
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                double sacc = 0;
+#pragma unroll
+                for (int m = 0; m <= c; ++m) sacc += a[m] * Lik[c * D + m];     // written by lane 0 of this warp
+                row[c] = sacc;
+            }
+        }
+    }
+}
+
+// forward substitution of one level: y_k = L_kk^-1 (b_perm(k) - sum_j L_kj y_j), a GL-lane group per block row
+template <int D, bool COOP>
+__device__ __forceinline__ void dk_forward(const DirectDev &P, int lev, const double *__restrict__ b, int tid, int nthreads) {
+    constexpr int DD = D * D, GL = GroupLanes<D>::value;
+    const int group = tid / GL, lane = tid % GL, ngroups = nthreads / GL;
+    const int c0 = P.lev_ptr[lev], c1 = P.lev_ptr[lev + 1];
+    for (int kb = c0; kb < c1; kb += ngroups) {       // uniform trip count: the shuffles below stay convergent
+        const int k = kb + group;
+        const bool act = k < c1 && lane < D;
+        double acc = 0;
+        if (act) {
+            acc = b[(size_t)P.perm[k] * D + lane];
+            for (int q = P.row_ptr[k]; q < P.row_ptr[k + 1]; ++q) {
+                const double *Lt = P.L + (size_t)P.row_blk[q] * DD + lane * D;
+                const double *yj = P.y + (size_t)P.row_col[q] * D;
+                double s = 0;
+#pragma unroll
+                for (int m = 0; m < D; ++m) s += ldw<COOP>(Lt + m) * ldw<COOP>(yj + m);
+                acc -= s;
+            }
+        }
+        double yl = 0;
+#pragma unroll
+        for (int m = 0; m < D; ++m) {
+            const double am = __shfl_sync(0xffffffffu, acc, m, GL);
+            if (act && m <= lane) yl += ldw<COOP>(P.Linv + (size_t)k * DD + lane * D + m) * am;
+        }
+        if (act) P.y[(size_t)k * D + lane] = yl;
+    }
+}
+
+// backward substitution of one level: x_k = L_kk^-T (y_k - sum_i L_ik^T x_i), written in Hessian order as well
+template <int D, bool COOP>
+__device__ __forceinline__ void dk_backward(const DirectDev &P, int lev, double *__restrict__ x, int tid, int nthreads) {
+    constexpr int DD = D * D, GL = GroupLanes<D>::value;
+    const int group = tid / GL, lane = tid % GL, ngroups = nthreads / GL;
+    const int c0 = P.lev_ptr[lev], c1 = P.lev_ptr[lev + 1];
+    for (int kb = c0; kb < c1; kb += ngroups) {
+        const int k = kb + group;
+        const bool act = k < c1 && lane < D;
+        double acc = 0;
+        if (act) {
+            acc = ldw<COOP>(P.y + (size_t)k * D + lane);
+            for (int t = P.cptr[k] + 1; t < P.cptr[k + 1]; ++t) {
+                const double *Lt = P.L + (size_t)t * DD + lane;
+                const double *xi = P.y + (size_t)P.brow[t] * D;
+                double s = 0;
+#pragma unroll
+                for (int m = 0; m < D; ++m) s += ldw<COOP>(Lt + m * D) * ldw<COOP>(xi + m);
+                acc -= s;
+            }
+        }
+        double xl = 0;
+#pragma unroll
+        for (int m = 0; m < D; ++m) {
+            const double am = __shfl_sync(0xffffffffu, acc, m, GL);
+            if (act && m >= lane) xl += ldw<COOP>(P.Linv + (size_t)k * DD + m * D + lane) * am;
+        }
+        if (act) {
+            P.y[(size_t)k * D + lane] = xl;
+            x[(size_t)P.perm[k] * D + lane] = xl;
+        }
+    }
+}
+
+// Schedule.  The first `wide` levels (the rounds that eliminate many columns at once) run on the whole grid with
+// grid barriers; the narrow tail -- most of the rounds, each a handful of blocks -- runs on CTA 0 alone with CTA
+// barriers while the other CTAs wait at ONE grid barrier.  Per level: [gather(l) + forward(l-1)] | pivot+scale(l);
+// the forward substitution of a level only needs that level's pivots, so it rides in the next gather phase.
+//   COOP = false: one CTA, wide = 0.
 template <int D, bool COOP>
 __global__ void __launch_bounds__(kDirectNT) direct_kernel(DirectDev P, const double *__restrict__ H, double lambda,
                                                            const double *__restrict__ b, double *__restrict__ x,
-                                                           DevScalars *sc, int do_factor) {
-    constexpr int DD = D * D, GL = GroupLanes<D>::value;
-    const int tid = blockIdx.x * kDirectNT + threadIdx.x, nthreads = gridDim.x * kDirectNT;
+                                                           DevScalars *sc, int do_factor, int wide) {
+    constexpr int DD = D * D;
+    const int ltid = threadIdx.x;
+    const int gtid = blockIdx.x * kDirectNT + threadIdx.x, gthreads = gridDim.x * kDirectNT;
+    auto gsync = [&]() {
+        if constexpr (COOP) { __threadfence(); cg::this_grid().sync(); }
+        else __syncthreads();
+    };
     if (do_factor) {
-        if (tid == 0) *P.fail = 0;
+        if (gtid == 0) *P.fail = 0;
         // ---- scatter (H + lambda I) into the factor's storage, elimination order
-        for (long long item = tid; item < (long long)P.nL * DD; item += nthreads) {
+        for (long long item = gtid; item < (long long)P.nL * DD; item += gthreads) {
             const int t = (int)(item / DD), e = (int)(item - (long long)t * DD);
             const int r = e / D, c = e - r * D;
             const int s = P.src[t];
@@ -74,153 +240,35 @@ __global__ void __launch_bounds__(kDirectNT) direct_kernel(DirectDev P, const do
             if (r == c && P.brow[t] == P.bcol[t]) v += lambda;
             P.L[item] = v;
         }
-        phase_sync<COOP>();
-        for (int lev = 0; lev < P.nlev; ++lev) {
-            const int c0 = P.lev_ptr[lev], c1 = P.lev_ptr[lev + 1];
-            const int t0 = P.cptr[c0], t1 = P.cptr[c1];
-            // ---- gather: target -= sum L[a] L[b]^T (columns of earlier levels, fixed order)
-            for (int item = tid; item < (t1 - t0) * DD; item += nthreads) {
-                const int t = t0 + item / DD, e = item % DD;
-                const int q0 = P.upd_ptr[t], q1 = P.upd_ptr[t + 1];
-                if (q0 == q1) continue;
-                const int r = e / D, c = e - r * D;
-                double acc = ldw<COOP>(P.L + (size_t)t * DD + e);
-                for (int q = q0; q < q1; ++q) {
-                    const double *La = P.L + (size_t)P.upd_a[q] * DD + r * D;
-                    const double *Lb = P.L + (size_t)P.upd_b[q] * DD + c * D;
-                    double s = 0;
-#pragma unroll
-                    for (int m = 0; m < D; ++m) s += ldw<COOP>(La + m) * ldw<COOP>(Lb + m);
-                    acc -= s;
-                }
-                P.L[(size_t)t * DD + e] = acc;
-            }
-            phase_sync<COOP>();
-            // ---- pivots: lower Cholesky of the diagonal blocks and the inverse of the factor
-            for (int k = c0 + tid; k < c1; k += nthreads) {
-                double A[DD], Li[DD];
-                double *Ld = P.L + (size_t)P.cptr[k] * DD;
-#pragma unroll
-                for (int i = 0; i < DD; ++i) A[i] = ldw<COOP>(Ld + i);
-                bool ok = true;
-#pragma unroll
-                for (int j = 0; j < D; ++j) {
-                    double djj = A[j * D + j];
-#pragma unroll
-                    for (int m = 0; m < j; ++m) djj -= A[j * D + m] * A[j * D + m];
-                    if (!(djj > 0) || !isfinite(djj)) { ok = false; djj = 1; }
-                    const double ljj = sqrt(djj), inv = 1.0 / ljj;
-                    A[j * D + j] = ljj;
-#pragma unroll
-                    for (int r = j + 1; r < D; ++r) {
-                        double v = A[r * D + j];
-#pragma unroll
-                        for (int m = 0; m < j; ++m) v -= A[r * D + m] * A[j * D + m];
-                        A[r * D + j] = v * inv;
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < D; ++c)
-#pragma unroll
-                    for (int r = 0; r < D; ++r) {
-                        if (r < c) { Li[r * D + c] = 0; continue; }
-                        double v = (r == c) ? 1.0 : 0.0;
-#pragma unroll
-                        for (int m = c; m < r; ++m) v -= A[r * D + m] * Li[m * D + c];
-                        Li[r * D + c] = v / A[r * D + r];
-                    }
-#pragma unroll
-                for (int r = 0; r < D; ++r)
-#pragma unroll
-                    for (int c = 0; c < D; ++c) {
-                        Ld[r * D + c] = c <= r ? A[r * D + c] : 0.0;
-                        P.Linv[(size_t)k * DD + r * D + c] = Li[r * D + c];
-                    }
-                if (!ok) *P.fail = 1;
-            }
-            phase_sync<COOP>();
-            // ---- scale: L_ik = A_ik L_kk^-T, one thread per block row (rows are independent)
-            for (int item = tid; item < (t1 - t0) * D; item += nthreads) {
-                const int t = t0 + item / D, r = item % D;
-                const int k = P.bcol[t];
-                if (P.brow[t] == k) continue;
-                double a[D];
-                double *row = P.L + (size_t)t * DD + r * D;
-                const double *Li = P.Linv + (size_t)k * DD;
-#pragma unroll
-                for (int m = 0; m < D; ++m) a[m] = ldw<COOP>(row + m);
-#pragma unroll
-                for (int c = 0; c < D; ++c) {
-                    double s = 0;
-#pragma unroll
-                    for (int m = 0; m <= c; ++m) s += a[m] * ldw<COOP>(Li + c * D + m);
-                    row[c] = s;
-                }
-            }
-            phase_sync<COOP>();
-        }
+        gsync();
     }
-    // ---- forward substitution  y = L^-1 P b   (GL-lane group per block row)
-    const int group = tid / GL, lane = tid % GL, ngroups = nthreads / GL;
-    for (int lev = 0; lev < P.nlev; ++lev) {
-        const int c0 = P.lev_ptr[lev], c1 = P.lev_ptr[lev + 1];
-        for (int kb = c0; kb < c1; kb += ngroups) {       // uniform trip count: the shuffles below stay convergent
-            const int k = kb + group;
-            const bool act = k < c1 && lane < D;
-            double acc = 0;
-            if (act) {
-                acc = b[(size_t)P.perm[k] * D + lane];
-                for (int q = P.row_ptr[k]; q < P.row_ptr[k + 1]; ++q) {
-                    const double *Lt = P.L + (size_t)P.row_blk[q] * DD + lane * D;
-                    const double *yj = P.y + (size_t)P.row_col[q] * D;
-                    double s = 0;
-#pragma unroll
-                    for (int m = 0; m < D; ++m) s += ldw<COOP>(Lt + m) * ldw<COOP>(yj + m);
-                    acc -= s;
-                }
-            }
-            double yl = 0;
-#pragma unroll
-            for (int m = 0; m < D; ++m) {
-                const double am = __shfl_sync(0xffffffffu, acc, m, GL);
-                if (act && m <= lane) yl += ldw<COOP>(P.Linv + (size_t)k * DD + lane * D + m) * am;
-            }
-            if (act) P.y[(size_t)k * D + lane] = yl;
-        }
-        phase_sync<COOP>();
+    // ---- wide levels on the whole grid
+    for (int lev = 0; lev < wide; ++lev) {
+        if (do_factor) dk_gather<D, COOP>(P, lev, gtid, gthreads);
+        if (lev > 0) dk_forward<D, COOP>(P, lev - 1, b, gtid, gthreads);
+        if (do_factor || lev > 0) gsync();
+        if (do_factor) { dk_pivot_scale<D, COOP>(P, lev, gtid, gthreads); gsync(); }
     }
-    // ---- backward substitution  x = P^T L^-T y
-    for (int lev = P.nlev - 1; lev >= 0; --lev) {
-        const int c0 = P.lev_ptr[lev], c1 = P.lev_ptr[lev + 1];
-        for (int kb = c0; kb < c1; kb += ngroups) {
-            const int k = kb + group;
-            const bool act = k < c1 && lane < D;
-            double acc = 0;
-            if (act) {
-                acc = ldw<COOP>(P.y + (size_t)k * D + lane);
-                for (int t = P.cptr[k] + 1; t < P.cptr[k + 1]; ++t) {
-                    const double *Lt = P.L + (size_t)t * DD + lane;
-                    const double *xi = P.y + (size_t)P.brow[t] * D;
-                    double s = 0;
-#pragma unroll
-                    for (int m = 0; m < D; ++m) s += ldw<COOP>(Lt + m * D) * ldw<COOP>(xi + m);
-                    acc -= s;
-                }
-            }
-            double xl = 0;
-#pragma unroll
-            for (int m = 0; m < D; ++m) {
-                const double am = __shfl_sync(0xffffffffu, acc, m, GL);
-                if (act && m >= lane) xl += ldw<COOP>(P.Linv + (size_t)k * DD + m * D + lane) * am;
-            }
-            if (act) {
-                P.y[(size_t)k * D + lane] = xl;
-                x[(size_t)P.perm[k] * D + lane] = xl;
-            }
+    // ---- narrow tail on CTA 0 (CTA barriers), then its share of the backward substitution
+    if (blockIdx.x == 0) {
+        for (int lev = wide; lev < P.nlev; ++lev) {
+            if (do_factor) dk_gather<D, COOP>(P, lev, ltid, kDirectNT);
+            if (lev > 0) dk_forward<D, COOP>(P, lev - 1, b, ltid, kDirectNT);
+            __syncthreads();
+            if (do_factor) { dk_pivot_scale<D, COOP>(P, lev, ltid, kDirectNT); __syncthreads(); }
         }
-        phase_sync<COOP>();
+        if (P.nlev > 0) {
+            if (wide == P.nlev) { /* the last level's forward step still runs on the grid below */ }
+            else { dk_forward<D, COOP>(P, P.nlev - 1, b, ltid, kDirectNT); __syncthreads(); }
+        }
+        for (int lev = P.nlev - 1; lev >= wide; --lev) { dk_backward<D, COOP>(P, lev, x, ltid, kDirectNT); __syncthreads(); }
     }
-    if (tid == 0) {     // the PCG bookkeeping the LM driver reads: an exact solve, 0 iterations
+    if (wide > 0) {
+        if (wide == P.nlev) { dk_forward<D, COOP>(P, P.nlev - 1, b, gtid, gthreads); }
+        gsync();
+        for (int lev = wide - 1; lev >= 0; --lev) { dk_backward<D, COOP>(P, lev, x, gtid, gthreads); gsync(); }
+    }
+    if (gtid == 0) {     // the PCG bookkeeping the LM driver reads: an exact solve, 0 iterations
         const int failed = *reinterpret_cast<volatile int *>(P.fail);
         sc->done = failed ? 3 : 1;
         sc->iters = 0;
@@ -241,15 +289,16 @@ void free_direct_arrays(DirectState *D) {
 template <int D>
 int launch_direct(s3o_problem *p, const DirectDev &P, double lambda, int do_factor) {
     DirectState *S = p->direct;
-    if (S->coop_grid <= 0) {
-        direct_kernel<D, false><<<1, kDirectNT, 0, p->stream>>>(P, p->d_H, lambda, p->d_b, p->d_x, p->d_sc, do_factor);
+    if (S->coop_grid <= 1) {
+        direct_kernel<D, false><<<1, kDirectNT, 0, p->stream>>>(P, p->d_H, lambda, p->d_b, p->d_x, p->d_sc, do_factor, 0);
         return S3O_OK;
     }
     const double *H = p->d_H, *b = p->d_b;
     double *x = p->d_x;
     DevScalars *sc = p->d_sc;
     DirectDev Pc = P;
-    void *args[] = { &Pc, &H, &lambda, &b, &x, &sc, &do_factor };
+    int wide = S->wide_levels;
+    void *args[] = { &Pc, &H, &lambda, &b, &x, &sc, &do_factor, &wide };
     S3O_CUDA(cudaLaunchCooperativeKernel((void *)direct_kernel<D, true>, dim3(S->coop_grid), dim3(kDirectNT), args, 0, p->stream));
     return S3O_OK;
 }
@@ -314,18 +363,30 @@ int direct_setup(s3o_problem *p) {
     rc = rc ? rc : dev_alloc(&D->d_fail, 1);
     if (rc) { free_direct_arrays(D); return rc; }
     S3O_CUDA(cudaStreamSynchronize(p->stream));
-    // one CTA while the whole factorisation is a few thousand block products (latency-bound: CTA barriers are
-    // ~10x cheaper than grid barriers); a cooperative grid beyond that
+    // Grid and schedule: a level is "wide" while its gather phase has more than 8 items per thread of one CTA;
+    // the leading wide levels run on a cooperative grid sized for the widest one, everything after the last wide
+    // level on CTA 0 alone (CTA barriers are ~10x cheaper than grid barriers, and the tail is pure latency).
     D->coop_grid = 0;
-    if (P.n_pairs > 20000) {
-        int cap = 0;
-        switch (d) {
-        case 7: cap = coop_capacity<7>(p->device); break;
-        case 6: cap = coop_capacity<6>(p->device); break;
-        case 4: cap = coop_capacity<4>(p->device); break;
-        case 1: cap = coop_capacity<1>(p->device); break;
+    D->wide_levels = 0;
+    {
+        long long widest = 0;
+        for (int l = 0; l < P.nlev; ++l) {
+            const long long items = (long long)(P.cptr[P.lev_ptr[l + 1]] - P.cptr[P.lev_ptr[l]]) * d * d;
+            if (items > 8 * kDirectNT) D->wide_levels = l + 1;
+            widest = std::max(widest, items);
         }
-        D->coop_grid = cap;
+        if (D->wide_levels > 0) {
+            int cap = 0;
+            switch (d) {
+            case 7: cap = coop_capacity<7>(p->device); break;
+            case 6: cap = coop_capacity<6>(p->device); break;
+            case 4: cap = coop_capacity<4>(p->device); break;
+            case 1: cap = coop_capacity<1>(p->device); break;
+            }
+            const long long want = (widest + 4 * kDirectNT - 1) / (4 * kDirectNT);
+            D->coop_grid = (int)std::max<long long>(1, std::min<long long>(cap, want));
+            if (D->coop_grid <= 1) D->wide_levels = 0;
+        }
     }
     D->available = true;
     D->factored = false;
