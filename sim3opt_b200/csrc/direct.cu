@@ -74,73 +74,95 @@ __device__ __forceinline__ void dk_gather(const DirectDev &P, int lev, int tid, 
     }
 }
 
-// pivot + scale, one warp per column: lane 0 factors the d x d pivot (lower Cholesky, inverse of the factor kept),
-// then the warp's lanes scale the rows of the column's sub-diagonal blocks by L_kk^-T (rows are independent)
+// lower Cholesky of one d x d pivot block and the inverse of the factor (one thread)
 template <int D, bool COOP>
-__device__ __forceinline__ void dk_pivot_scale(const DirectDev &P, int lev, int tid, int nthreads) {
+__device__ __forceinline__ void dk_pivot_one(const DirectDev &P, int k) {
+    constexpr int DD = D * D;
+    double *Ld = P.L + (size_t)P.cptr[k] * DD;
+    double *Lik = P.Linv + (size_t)k * DD;
+    double A[DD], Li[DD];
+#pragma unroll
+    for (int i = 0; i < DD; ++i) A[i] = ldw<COOP>(Ld + i);
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        double djj = A[j * D + j];
+#pragma unroll
+        for (int m = 0; m < j; ++m) djj -= A[j * D + m] * A[j * D + m];
+        if (!(djj > 0) || !isfinite(djj)) { ok = false; djj = 1; }
+        const double ljj = sqrt(djj), inv = 1.0 / ljj;
+        A[j * D + j] = ljj;
+#pragma unroll
+        for (int r = j + 1; r < D; ++r) {
+            double v = A[r * D + j];
+#pragma unroll
+            for (int m = 0; m < j; ++m) v -= A[r * D + m] * A[j * D + m];
+            A[r * D + j] = v * inv;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c)
+#pragma unroll
+        for (int r = 0; r < D; ++r) {
+            if (r < c) { Li[r * D + c] = 0; continue; }
+            double v = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+            for (int m = c; m < r; ++m) v -= A[r * D + m] * Li[m * D + c];
+            Li[r * D + c] = v / A[r * D + r];
+        }
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            Ld[r * D + c] = c <= r ? A[r * D + c] : 0.0;
+            Lik[r * D + c] = Li[r * D + c];
+        }
+    if (!ok) *P.fail = 1;
+}
+
+// scale one row of a sub-diagonal block: L_ik[r,:] = A_ik[r,:] L_kk^-T
+template <int D, bool COOP>
+__device__ __forceinline__ void dk_scale_row(const DirectDev &P, int t, int r, const double *Lik) {
+    constexpr int DD = D * D;
+    double a[D];
+    double *row = P.L + (size_t)t * DD + r * D;
+#pragma unroll
+    for (int m = 0; m < D; ++m) a[m] = ldw<COOP>(row + m);
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        double sacc = 0;
+#pragma unroll
+        for (int m = 0; m <= c; ++m) sacc += a[m] * ldw<COOP>(Lik + c * D + m);
+        row[c] = sacc;
+    }
+}
+
+// A level with many columns: one thread per pivot (32 pivots per warp instruction), barrier, then one thread per
+// block row.  A level with few columns: one warp per column, lane 0 factors, the warp scales -- no barrier between.
+template <int D, bool COOP, class Sync>
+__device__ __forceinline__ void dk_pivot_scale(const DirectDev &P, int lev, int tid, int nthreads, Sync sync) {
     constexpr int DD = D * D;
     const int c0 = P.lev_ptr[lev], c1 = P.lev_ptr[lev + 1];
-    const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
-    for (int k = c0 + warp; k < c1; k += nwarps) {
-        double *Ld = P.L + (size_t)P.cptr[k] * DD;
-        double *Lik = P.Linv + (size_t)k * DD;
-        if (lane == 0) {
-            double A[DD], Li[DD];
-#pragma unroll
-            for (int i = 0; i < DD; ++i) A[i] = ldw<COOP>(Ld + i);
-            bool ok = true;
-#pragma unroll
-            for (int j = 0; j < D; ++j) {
-                double djj = A[j * D + j];
-#pragma unroll
-                for (int m = 0; m < j; ++m) djj -= A[j * D + m] * A[j * D + m];
-                if (!(djj > 0) || !isfinite(djj)) { ok = false; djj = 1; }
-                const double ljj = sqrt(djj), inv = 1.0 / ljj;
-                A[j * D + j] = ljj;
-#pragma unroll
-                for (int r = j + 1; r < D; ++r) {
-                    double v = A[r * D + j];
-#pragma unroll
-                    for (int m = 0; m < j; ++m) v -= A[r * D + m] * A[j * D + m];
-                    A[r * D + j] = v * inv;
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < D; ++c)
-#pragma unroll
-                for (int r = 0; r < D; ++r) {
-                    if (r < c) { Li[r * D + c] = 0; continue; }
-                    double v = (r == c) ? 1.0 : 0.0;
-#pragma unroll
-                    for (int m = c; m < r; ++m) v -= A[r * D + m] * Li[m * D + c];
-                    Li[r * D + c] = v / A[r * D + r];
-                }
-#pragma unroll
-            for (int r = 0; r < D; ++r)
-#pragma unroll
-                for (int c = 0; c < D; ++c) {
-                    Ld[r * D + c] = c <= r ? A[r * D + c] : 0.0;
-                    Lik[r * D + c] = Li[r * D + c];
-                }
-            if (!ok) *P.fail = 1;
-            __threadfence_block();
+    const int nwarps = nthreads >> 5;
+    if (c1 - c0 > 2 * nwarps) {
+        for (int k = c0 + tid; k < c1; k += nthreads) dk_pivot_one<D, COOP>(P, k);
+        sync();
+        const int t0 = P.cptr[c0], t1 = P.cptr[c1];
+        for (int item = tid; item < (t1 - t0) * D; item += nthreads) {
+            const int t = t0 + item / D, r = item % D;
+            const int k = P.bcol[t];
+            if (P.brow[t] == k) continue;
+            dk_scale_row<D, COOP>(P, t, r, P.Linv + (size_t)k * DD);
         }
+        return;
+    }
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int k = c0 + warp; k < c1; k += nwarps) {
+        if (lane == 0) { dk_pivot_one<D, COOP>(P, k); __threadfence(); }
         __syncwarp();
         const int nsub = P.cptr[k + 1] - P.cptr[k] - 1;
-        for (int item = lane; item < nsub * D; item += 32) {
-            const int t = P.cptr[k] + 1 + item / D, r = item % D;
-            double a[D];
-            double *row = P.L + (size_t)t * DD + r * D;
-#pragma unroll
-            for (int m = 0; m < D; ++m) a[m] = ldw<COOP>(row + m);
-#pragma unroll
-            for (int c = 0; c < D; ++c) {
-                double sacc = 0;
-#pragma unroll
-                for (int m = 0; m <= c; ++m) sacc += a[m] * Lik[c * D + m];     // written by lane 0 of this warp
-                row[c] = sacc;
-            }
-        }
+        for (int item = lane; item < nsub * D; item += 32)
+            dk_scale_row<D, COOP>(P, P.cptr[k] + 1 + item / D, item % D, P.Linv + (size_t)k * DD);
     }
 }
 
@@ -247,7 +269,7 @@ __global__ void __launch_bounds__(kDirectNT) direct_kernel(DirectDev P, const do
         if (do_factor) dk_gather<D, COOP>(P, lev, gtid, gthreads);
         if (lev > 0) dk_forward<D, COOP>(P, lev - 1, b, gtid, gthreads);
         if (do_factor || lev > 0) gsync();
-        if (do_factor) { dk_pivot_scale<D, COOP>(P, lev, gtid, gthreads); gsync(); }
+        if (do_factor) { dk_pivot_scale<D, COOP>(P, lev, gtid, gthreads, gsync); gsync(); }
     }
     // ---- narrow tail on CTA 0 (CTA barriers), then its share of the backward substitution
     if (blockIdx.x == 0) {
@@ -255,7 +277,7 @@ __global__ void __launch_bounds__(kDirectNT) direct_kernel(DirectDev P, const do
             if (do_factor) dk_gather<D, COOP>(P, lev, ltid, kDirectNT);
             if (lev > 0) dk_forward<D, COOP>(P, lev - 1, b, ltid, kDirectNT);
             __syncthreads();
-            if (do_factor) { dk_pivot_scale<D, COOP>(P, lev, ltid, kDirectNT); __syncthreads(); }
+            if (do_factor) { dk_pivot_scale<D, COOP>(P, lev, ltid, kDirectNT, [] { __syncthreads(); }); __syncthreads(); }
         }
         if (P.nlev > 0) {
             if (wide == P.nlev) { /* the last level's forward step still runs on the grid below */ }

@@ -1086,7 +1086,9 @@ __global__ void halo_wait_kernel(long long *const *peer_flags, int n_peers, long
     const volatile long long *f = peer_flags[t];
     long long spins = 0;
     while (*f < epoch) {
-        if (++spins > (1ll << 25)) { sc->done = 3; break; }     // ~1 minute: a peer died, report a breakdown instead of hanging
+        // ~1 minute: a peer died.  Do not leave the iteration on this rank alone (the peers would hang in the next
+        // collective): flag it, the SpMV poisons p.q and the all-reduce makes every rank break down together.
+        if (++spins > (1ll << 25)) { sc->halo_fail = 1; break; }
     }
     __threadfence_system();
 }

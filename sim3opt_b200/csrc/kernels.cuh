@@ -22,6 +22,7 @@ struct DevScalars {
     int done;         // 0 running, 1 converged, 2 iteration cap, 3 breakdown
     int iters, max_iter;
     int precond_fail;
+    int halo_fail;    // partitioned solve: a neighbour's epoch flag did not arrive (peer died); see halo_wait_kernel
     unsigned counters[8];
 };
 

@@ -143,7 +143,9 @@ __global__ void __launch_bounds__(NT) spmv2_kernel(const double *__restrict__ H,
     if (last_block(&sc->counters[3])) {
         const double pq = sum_partials<NT>(partials, gridDim.x, sh);
         if (threadIdx.x == 0) {
-            sc->pq = pq;
+            // partitioned solve: a rank whose halo wait timed out poisons its p.q, the all-reduce carries the NaN to
+            // every rank and they all leave the PCG through the same breakdown exit
+            sc->pq = (dist && sc->halo_fail) ? nan("") : pq;
             if (!dist) fin_spmv(sc);
         }
     }
@@ -307,7 +309,9 @@ __global__ void __launch_bounds__(NT) spmv3_kernel(const double *__restrict__ H,
     if (last_block(&sc->counters[3])) {
         const double pq = sum_partials<NT>(partials, gridDim.x, sh);
         if (threadIdx.x == 0) {
-            sc->pq = pq;
+            // partitioned solve: a rank whose halo wait timed out poisons its p.q, the all-reduce carries the NaN to
+            // every rank and they all leave the PCG through the same breakdown exit
+            sc->pq = (dist && sc->halo_fail) ? nan("") : pq;
             if (!dist) fin_spmv(sc);
         }
     }
@@ -496,7 +500,9 @@ __global__ void __launch_bounds__(NT) spmv4_kernel(const double *__restrict__ H,
     if (last_block(&sc->counters[3])) {
         const double pq = sum_partials<NT>(partials, gridDim.x, sh);
         if (threadIdx.x == 0) {
-            sc->pq = pq;
+            // partitioned solve: a rank whose halo wait timed out poisons its p.q, the all-reduce carries the NaN to
+            // every rank and they all leave the PCG through the same breakdown exit
+            sc->pq = (dist && sc->halo_fail) ? nan("") : pq;
             if (!dist) fin_spmv(sc);
         }
     }

@@ -60,7 +60,24 @@ def main():
         print("max |vertex diff| %.3e" % dv)
         print("DIST_CHECK", "PASS" if ok else "FAIL", "world", world)
         print("P2P_HALO", pd.stats()["p2p_halo"], "MULTILEVEL_LEVELS", pd.stats()["multilevel_levels"])
-    # every rank holds the same estimates after the solve
+    # s3o_update in the partitioned solve: every rank passes its OWNED rows of one global step, the step is
+    # all-gathered inside, and all ranks must end with the estimates a single-GPU s3o_update produces
+    nf = int((np.asarray(g["fixed"]) == 0).sum())
+    seg = -(-nf // world)
+    rng = np.random.default_rng(5)
+    step = 1e-3 * rng.standard_normal((nf, 7))
+    lo, hi = min(nf, rank * seg), min(nf, (rank + 1) * seg)
+    pd.update(step[lo:hi])
+    vu = pd.vertices()
+    upd_ok = True
+    if rank == 0:
+        ps.update(step)
+        du = np.abs(vu - ps.vertices()).max()
+        upd_ok = du <= 1e-12
+        print("UPDATE_PARTITIONED max diff %.3e %s" % (du, "PASS" if upd_ok else "FAIL"))
+        ok = ok and upd_ok
+    vd = vu
+    # every rank holds the same estimates after the solve and the update
     t = torch.from_numpy(vd.copy()).cuda()
     ref = t.clone()
     dist.broadcast(ref, src=0)
