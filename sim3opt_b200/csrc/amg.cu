@@ -1327,7 +1327,8 @@ int amg_setup(s3o_problem *p) {
         // K-cycle on every level above the coarsest for large graphs (measured on the 1M-pose sphere: PCG iterations of a
         // late LM iteration 334 with the V-cycle, 166 with one K level, 63 with three; K on some levels and V below them
         // can be worse than either); small graphs keep the V-cycle.  S3O_KCYCLE=<levels> overrides (0: V-cycle everywhere).
-        st->kdepth = (nl >= 2 && st->host[0].n_fine >= kBigGraph) ? nl - 1 : 0;
+        const int n_fine_global = p->dist ? p->plan.nf_global : st->host[0].n_fine;     // host[0].n_fine is local when partitioned
+        st->kdepth = (nl >= 2 && n_fine_global >= kBigGraph) ? nl - 1 : 0;
         if (const char *v = getenv("S3O_KCYCLE")) st->kdepth = std::max(0, std::min(atoi(v), nl - 1));
         int coop_rows = kCoopRows;
         if (const char *v = getenv("S3O_COOP_ROWS")) coop_rows = atoi(v);       // experiment switch

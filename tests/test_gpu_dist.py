@@ -48,7 +48,7 @@ def test_partitioned_kcycle_large_graph():
     port = s.getsockname()[1]
     s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "dist_check.py"), "100", "300", "4", "2", "sphere"]
+           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "dist_check.py"), "100", "300", "4", "2", "sphere", "1e-6"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert "DIST_CHECK PASS" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
     assert "ESTIMATES_IDENTICAL_ACROSS_RANKS True" in out.stdout
