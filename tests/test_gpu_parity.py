@@ -360,3 +360,31 @@ def test_hub_vertex_rows_longer_than_a_tile():
     assert rc == 0
     Ad = A + 1e-3 * np.eye(len(bg))
     assert np.linalg.norm(Ad @ xs - bg) <= 1e-10 * np.linalg.norm(bg)
+
+
+def test_stop_rules(sphere_small):
+    """s3o_set_stop_rules: the step rule ends a solve at the oracle's fixed point without burning trials at the
+    fp64 floor; stop_reason reports which rule fired; without rules g2o's Terminate (10 failed trials) ends it."""
+    orc = _orc()
+    import sim3opt_b200 as s3
+    orc.set_math_mode(orc.MATH_CORRECTED)
+    try:
+        cpu = make_oracle(sphere_small, jac=orc.JAC_ANALYTIC)
+        n_c, chi_c, _, _ = cpu.optimize(60)
+        vc = cpu.vertices()
+        gpu = make_gpu(sphere_small, jac=1, math_mode=s3.MATH_CORRECTED)
+        gpu.set_pcg(1e-10, 20000)
+        gpu.set_stop_rules(1e-6, 1e-13)
+        n_g, chi_g, _, hist = gpu.optimize(60)
+        st = gpu.stats()
+        assert st["stop_reason"] in (2, 3) and n_g < 60
+        assert hist[:, 2].max() <= 2                       # no trial storm at the end
+        assert abs(chi_g - chi_c) <= 1e-9 * chi_c
+        assert np.abs(gpu.vertices()[:, 4:7] - vc[:, 4:7]).max() <= 1e-5
+        assert st["est_distance"] <= 1e-6 or st["stop_reason"] == 3
+        free = make_gpu(sphere_small, jac=1, math_mode=s3.MATH_CORRECTED)
+        free.set_pcg(1e-10, 20000)
+        n_f, _, _, hist_f = free.optimize(60)
+        assert free.stats()["stop_reason"] in (0, 4) and n_f >= n_g
+    finally:
+        orc.set_math_mode(orc.MATH_REFERENCE)
