@@ -316,13 +316,11 @@ __global__ void __launch_bounds__(256) amg_dense_inverse_kernel(const double *__
 template <int D>
 __global__ void __launch_bounds__(256) amg_dense_inverse_coop_kernel(const double *__restrict__ A, const int32_t *__restrict__ rowptr,
                                                                      const int32_t *__restrict__ colidx, int n, double *inv,
-                                                                     double *colbuf, double *rowbuf, DevScalars *sc) {
-    namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
+                                                                     double *colbuf, double *rowbuf, DevScalars *sc, const GridBarrier gb) {
+    unsigned phase = 0;
     const int N = n * D, nth = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
     for (size_t t = gtid; t < (size_t)N * N; t += nth) inv[t] = 0;
-    __threadfence();
-    grid.sync();
+    grid_barrier(gb, phase);
     for (int k = gtid; k < rowptr[n] * DD; k += nth) {
         const int blk = k / DD, e = k - blk * DD;
         // block row of blk: binary search in rowptr
@@ -330,8 +328,7 @@ __global__ void __launch_bounds__(256) amg_dense_inverse_coop_kernel(const doubl
         while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (rowptr[mid] <= blk) lo = mid; else hi = mid - 1; }
         inv[(size_t)(lo * D + e / D) * N + colidx[blk] * D + e % D] = A[k];
     }
-    __threadfence();
-    grid.sync();
+    grid_barrier(gb, phase);
     __shared__ double Ps[DD];
     for (int kb = 0; kb < n; ++kb) {
         // every CTA inverts the pivot block for itself (Gauss-Jordan on d x d by one thread)
@@ -372,8 +369,7 @@ __global__ void __launch_bounds__(256) amg_dense_inverse_coop_kernel(const doubl
             for (int m = 0; m < D; ++m) acc += Ps[r * D + m] * __ldcg(inv + (size_t)(kb * D + m) * N + j);
             rowbuf[t] = acc;
         }
-        __threadfence();
-        grid.sync();
+        grid_barrier(gb, phase);
         for (size_t t = gtid; t < (size_t)N * N; t += nth) {
             const int i = (int)(t / N), j = (int)(t - (size_t)i * N);
             const int ib = i / D, jb = j / D;
@@ -393,8 +389,7 @@ __global__ void __launch_bounds__(256) amg_dense_inverse_coop_kernel(const doubl
             }
             inv[t] = v;
         }
-        __threadfence();
-        grid.sync();
+        grid_barrier(gb, phase);
     }
 }
 
@@ -984,7 +979,8 @@ __device__ __forceinline__ void coop_up(const CoopLevel &F, const CoopLevel &C, 
 // store of q before whatever phase follows.
 template <int D>
 __device__ __forceinline__ void coop_kdots(const CoopLevel &L, const double *z, const RSpec V1, const double *v2, double *q,
-                                           double *dots, double out[3], int gtid, int nth, double *sh) {
+                                           double *dots, double out[3], int gtid, int nth, double *sh, const GridBarrier &gb,
+                                           unsigned &phase) {
     const int groups = nth / 8, g = gtid / 8, l = gtid & 7;
     double d0 = 0, d1 = 0, d2 = 0;
     for (int i = g; i < L.n; i += groups) {
@@ -1008,8 +1004,7 @@ __device__ __forceinline__ void coop_kdots(const CoopLevel &L, const double *z, 
     const double s2 = block_sum<kCoopThreads>(d2, sh);
     const int G = gridDim.x;
     if (threadIdx.x == 0) { dots[blockIdx.x] = s0; dots[G + blockIdx.x] = s1; dots[2 * G + blockIdx.x] = s2; }
-    __threadfence();
-    cooperative_groups::this_grid().sync();
+    grid_barrier(gb, phase);
     __shared__ double tot[3];
     if (threadIdx.x < 32) {
 #pragma unroll
@@ -1031,13 +1026,13 @@ __device__ __forceinline__ void coop_kdots(const CoopLevel &L, const double *z, 
 // halves, so a step's partial sums are never overwritten while a slow CTA still reads the previous step's.
 template <int D>
 __global__ void __launch_bounds__(kCoopThreads, 1)
-amg_coop_kernel(const __grid_constant__ CoopParams P, double omega, const DevScalars *sc, int check_done) {
+amg_coop_kernel(const __grid_constant__ CoopParams P, double omega, const DevScalars *sc, int check_done,
+                const GridBarrier gb) {
     if (check_done && sc->done) return;       // uniform over the grid: nobody reaches a barrier
-    namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
+    unsigned phase = 0;
     __shared__ double sh[32];
     const int nth = gridDim.x * kCoopThreads, gtid = blockIdx.x * kCoopThreads + threadIdx.x;
-    auto gsync = [&]() { __threadfence(); grid.sync(); };
+    auto gsync = [&]() { grid_barrier(gb, phase); };
     const int last = P.nlev - 1;
     // explicit recursion state: residual of the cycle in progress at every level, where its result goes, the
     // inner step of a K-cycle level and its scalars
@@ -1112,7 +1107,7 @@ amg_coop_kernel(const __grid_constant__ CoopParams P, double omega, const DevSca
                 double *dots = P.dots + (flip ? 3 * gridDim.x : 0);
                 flip ^= 1;
                 if (step[l] == 0) {
-                    coop_kdots<D>(L, L.z1, cur_r[l], nullptr, L.q1, dots, d, gtid, nth, sh);
+                    coop_kdots<D>(L, L.z1, cur_r[l], nullptr, L.q1, dots, d, gtid, nth, sh, gb, phase);
                     kscal_first(&ks[l], d[0], d[1]);
                     step[l] = 1;
                     cur_r[l] = RSpec{ L.r, L.q1, ks[l].alpha1 };      // r' = r - alpha1 q1, formed where it is read
@@ -1120,7 +1115,7 @@ amg_coop_kernel(const __grid_constant__ CoopParams P, double omega, const DevSca
                     again = true;
                     break;                      // second cycle at the same level
                 }
-                coop_kdots<D>(L, L.z2, cur_r[l], L.q1, nullptr, dots, d, gtid, nth, sh);
+                coop_kdots<D>(L, L.z2, cur_r[l], L.q1, nullptr, dots, d, gtid, nth, sh, gb, phase);
                 kscal_second(&ks[l], d[0], d[1], d[2]);
                 X = XSpec{ L.z1, L.z2, ks[l].c1, ks[l].c2 };
                 if (l == 0) {                   // the caller reads a plain vector
@@ -1417,8 +1412,10 @@ int update_values_t(s3o_problem *p, double lambda) {
             int n = C.n;
             double *inv = st->d_dense, *cb = st->d_colbuf, *rb = st->d_rowbuf;
             DevScalars *scp = p->d_sc;
-            void *args[] = { &Ap, &rp, &ci, &n, &inv, &cb, &rb, &scp };
-            S3O_CUDA(cudaLaunchCooperativeKernel((void *)amg_dense_inverse_coop_kernel<D>, dim3(st->coop_grid), dim3(256), args, 0, p->stream));
+            GridBarrier gb{};
+            void *args[] = { &Ap, &rp, &ci, &n, &inv, &cb, &rb, &scp, &gb };
+            int rcl = launch_persistent(p, (const void *)amg_dense_inverse_coop_kernel<D>, st->coop_grid, 256, args, 9);
+            if (rcl) return rcl;
         } else {
             amg_dense_inverse_kernel<D><<<1, 256, (size_t)(N * N + N) * sizeof(double), p->stream>>>(C.A, C.rowptr, C.colidx, C.n,
                                                                                                   st->d_dense, p->d_sc);
@@ -1448,6 +1445,7 @@ int apply_t(s3o_problem *p, int init) {
         LevelDev &L = st->lev[0];
         amg_restrict_kernel<D><<<(L.n + 15) / 16, 128, 0, s>>>(L.n, L.mem_ptr, L.mem_idx, L.rel, L.pad_fine, p->d_r, L.r, sc, chk);
         ++launches;
+        trace_mark(p, "fine restrict");
         if (st->dist) {
             // my segment starts at L.r + r_off[rank], followed by my partial r.zJ and |r|^2; the padded tail of
             // the send is ignored by the unpad map
@@ -1476,10 +1474,12 @@ int apply_t(s3o_problem *p, int init) {
             amg_row_kernel<D, 1><<<rows(L.n), 128, 0, s>>>(L.n, L.rowptr, L.colidx, L.A, L.Dinv, rin, L.x, L.t, kOmega, sc, chk);
             amg_restrict_kernel<D><<<(C.n + 15) / 16, 128, 0, s>>>(C.n, C.mem_ptr, C.mem_idx, C.rel, C.pad_fine, L.t, C.r, sc, chk);
             launches += 3;
+            trace_mark(p, "lev: sweep+residual+restrict");
             solve(l + 1);
             amg_prolong_kernel<D><<<(L.n + 127) / 128, 128, 0, s>>>(L.n, C.agg, C.rel, C.pad_fine, C.x2, L.x, sc, chk);
             amg_row_kernel<D, 2><<<rows(L.n), 128, 0, s>>>(L.n, L.rowptr, L.colidx, L.A, L.Dinv, rin, L.x, xout, kOmega, sc, chk);
             launches += 2;
+            trace_mark(p, "lev: prolong+sweep");
         };
         solve = [&](int l) {
             LevelDev &L = st->lev[l];
@@ -1501,12 +1501,13 @@ int apply_t(s3o_problem *p, int init) {
                 }
                 double omega = kOmega;
                 int chk_ = chk;
-                void *args[] = { &P, &omega, (void *)&sc, &chk_ };
+                GridBarrier gb{};
+                void *args[] = { &P, &omega, (void *)&sc, &chk_, &gb };
                 int grid = (L.n * 8 + kCoopThreads - 1) / kCoopThreads;
                 grid = std::max(8, std::min(grid, st->coop_grid));
-                if (cudaLaunchCooperativeKernel((void *)amg_coop_kernel<D>, dim3(grid), dim3(kCoopThreads), args, 0, s) != cudaSuccess)
-                    rc_inner = S3O_ERR_CUDA;
+                if (launch_persistent(p, (const void *)amg_coop_kernel<D>, grid, kCoopThreads, args, 5)) rc_inner = S3O_ERR_CUDA;
                 ++launches;
+                trace_mark(p, "cooperative kernel");
                 return;
             }
             if (l < nk) {
@@ -1515,16 +1516,18 @@ int apply_t(s3o_problem *p, int init) {
                 cycle(l, L.r, L.z1);
                 amg_kdots_kernel<D, 128><<<kgrid(L.n), 128, 0, s>>>(L.n, L.rowptr, L.colidx, L.A, L.z1, L.r, nullptr, L.q1, p->d_partials, ks, 0, p->d_sc, chk);
                 amg_kaxpy_kernel<<<std::min((n + 255) / 256, 148 * 8), 256, 0, s>>>(n, L.r, L.q1, L.rp, ks, 0, sc, chk);
+                trace_mark(p, "lev: kdots+axpy");
                 cycle(l, L.rp, L.z2);
                 amg_kdots_kernel<D, 128><<<kgrid(L.n), 128, 0, s>>>(L.n, L.rowptr, L.colidx, L.A, L.z2, L.rp, L.q1, nullptr, p->d_partials, ks, 1, p->d_sc, chk);
                 amg_kaxpy_kernel<<<std::min((n + 255) / 256, 148 * 8), 256, 0, s>>>(n, L.z1, L.z2, L.x2, ks, 1, sc, chk);
                 launches += 4;
+                trace_mark(p, "lev: kdots+combine");
             } else {
                 cycle(l, L.r, L.x2);
             }
         };
         solve(0);
-        if (rc_inner) { set_error("multilevel K-cycle: cooperative launch failed: %s", cudaGetErrorString(cudaGetLastError())); return rc_inner; }
+        if (rc_inner) { set_error("multilevel K-cycle: persistent-kernel launch failed: %s", s3o_last_error()); return rc_inner; }
         std::swap(st->lev[0].x, st->lev[0].x2);
     } else {
         for (int l = 0; l < lt; ++l) {
@@ -1574,6 +1577,7 @@ int apply_t(s3o_problem *p, int init) {
         amg_coarse_dot_kernel<NT><<<dgrid, NT, 0, s>>>(L.n * D, L.r, L.x, p->d_partials, p->d_sc, init, p->pcg_tol, p->pcg_max_iter);
         amg_prolong0_kernel<D, NT><<<grid, NT, 0, s>>>(rows, L.agg, L.rel, L.pad_fine, L.x, p->d_z, p->d_p, sc, init);
         launches += 2;
+        trace_mark(p, "coarse dot + fine prolong");
     }
     return check_launch(p, launches);
 }

@@ -239,12 +239,13 @@ __device__ __forceinline__ void dk_backward(const DirectDev &P, int lev, double 
 template <int D, bool COOP>
 __global__ void __launch_bounds__(kDirectNT) direct_kernel(DirectDev P, const double *__restrict__ H, double lambda,
                                                            const double *__restrict__ b, double *__restrict__ x,
-                                                           DevScalars *sc, int do_factor, int wide) {
+                                                           DevScalars *sc, int do_factor, int wide, const GridBarrier gb) {
     constexpr int DD = D * D;
+    unsigned phase = 0;
     const int ltid = threadIdx.x;
     const int gtid = blockIdx.x * kDirectNT + threadIdx.x, gthreads = gridDim.x * kDirectNT;
     auto gsync = [&]() {
-        if constexpr (COOP) { __threadfence(); cg::this_grid().sync(); }
+        if constexpr (COOP) grid_barrier(gb, phase);
         else __syncthreads();
     };
     if (do_factor) {
@@ -312,7 +313,7 @@ template <int D>
 int launch_direct(s3o_problem *p, const DirectDev &P, double lambda, int do_factor) {
     DirectState *S = p->direct;
     if (S->coop_grid <= 1) {
-        direct_kernel<D, false><<<1, kDirectNT, 0, p->stream>>>(P, p->d_H, lambda, p->d_b, p->d_x, p->d_sc, do_factor, 0);
+        direct_kernel<D, false><<<1, kDirectNT, 0, p->stream>>>(P, p->d_H, lambda, p->d_b, p->d_x, p->d_sc, do_factor, 0, GridBarrier{});
         return S3O_OK;
     }
     const double *H = p->d_H, *b = p->d_b;
@@ -320,9 +321,9 @@ int launch_direct(s3o_problem *p, const DirectDev &P, double lambda, int do_fact
     DevScalars *sc = p->d_sc;
     DirectDev Pc = P;
     int wide = S->wide_levels;
-    void *args[] = { &Pc, &H, &lambda, &b, &x, &sc, &do_factor, &wide };
-    S3O_CUDA(cudaLaunchCooperativeKernel((void *)direct_kernel<D, true>, dim3(S->coop_grid), dim3(kDirectNT), args, 0, p->stream));
-    return S3O_OK;
+    GridBarrier gb{};
+    void *args[] = { &Pc, &H, &lambda, &b, &x, &sc, &do_factor, &wide, &gb };
+    return launch_persistent(p, (const void *)direct_kernel<D, true>, S->coop_grid, kDirectNT, args, 9);
 }
 
 template <int D>

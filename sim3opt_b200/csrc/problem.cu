@@ -137,8 +137,16 @@ int allreduce_max(s3o_problem *p, double *field, int count) {
 namespace s3o {
 int sync_scalars(s3o_problem *p) {
     S3O_CUDA(cudaMemcpyAsync(p->h_sc, p->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, p->stream));
+    unsigned bar[2] = { 0, 0 };
+    S3O_CUDA(cudaMemcpyAsync(bar, p->d_gridbar, sizeof bar, cudaMemcpyDeviceToHost, p->stream));
     S3O_CUDA(cudaStreamSynchronize(p->stream));
     p->stats.d2h_bytes += sizeof(DevScalars);
+    if (bar[1]) {       // a persistent kernel's grid barrier timed out (gridbar.cuh): its result is not to be used
+        cudaMemsetAsync(p->d_gridbar, 0, sizeof bar, p->stream);
+        set_error("a persistent kernel's grid barrier timed out (are other kernels holding this GPU's SMs?); S3O_COOP_LAUNCH=1 "
+                  "selects cooperative launches");
+        return S3O_ERR_CUDA;
+    }
     return S3O_OK;
 }
 }  // namespace s3o
@@ -271,15 +279,18 @@ int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel
         p->stats.kernel_launches += 1;
     }
     int batch = 8, launched = 0;
+    if (p->trace_state == 1 && p->trace_solve > 0) --p->trace_solve;
     for (;;) {
         for (int k = 0; k < batch; ++k) {
             const bool sample = ((launched + k) & 15) == 7 && p->spmv_ev_used < s3o_problem::kSpmvEvents;
+            if (p->trace_state == 1 && p->trace_solve == 0 && launched + k == 4) { p->trace_state = 2; trace_mark(p, "start"); }
             if ((rc = halo())) return rc;
             if (sample) {
                 p->spmv_ev_iter[p->spmv_ev_used] = launched + k;
                 cudaEventRecord(p->spmv_ev[2 * p->spmv_ev_used], p->stream);
             }
             run_spmv(p, s, lambda, p->d_p, 1);
+            trace_mark(p, "spmv");
             if (sample) cudaEventRecord(p->spmv_ev[2 * p->spmv_ev_used++ + 1], p->stream);
             if (dist) {
                 if ((rc = allreduce_sum(p, &p->d_sc->pq, 1))) return rc;
@@ -287,8 +298,10 @@ int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel
             }
             launch_pcg_update(d, s, nf, p->d_q1, p->d_T, p->d_Minv, p->d_p, p->d_x, p->d_r, p->d_z, p->d_partials,
                               p->d_sc, defer, p->stream);
+            trace_mark(p, "pcg_update");
             if (amg) {      // ... r.z, beta and p = z + beta p included
                 if ((rc = amg_apply(p, 0))) return rc;
+                if (p->trace_state == 2) { trace_mark(p, "end"); p->trace_state = 3; }
                 continue;
             }
             if (dist) {
@@ -302,6 +315,19 @@ int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel
         if (rc) return rc;
         rc = sync_scalars(p);
         if (rc) return rc;
+        if (p->trace_state == 3) {
+            float tot = 0;
+            cudaEventElapsedTime(&tot, p->trace.front().second, p->trace.back().second);
+            fprintf(stderr, "S3O_TRACE one PCG iteration: %.1f us\n", tot * 1e3f);
+            for (size_t t = 1; t < p->trace.size(); ++t) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, p->trace[t - 1].second, p->trace[t].second);
+                fprintf(stderr, "  %-28s %8.1f us\n", p->trace[t].first, ms * 1e3f);
+            }
+            for (auto &t : p->trace) cudaEventDestroy(t.second);
+            p->trace.clear();
+            p->trace_state = 0;
+        }
         // a launch after convergence exits at once: keep only the samples of iterations that ran
         // (launch index < iterations executed)
         for (int e = 0; e < p->spmv_ev_used; ++e) {
@@ -486,6 +512,7 @@ static int create_impl(int kind, int linear_dim, int device, s3o_problem **out) 
     if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); delete p; return S3O_ERR_CUDA; }
     p->own_stream = true;
     if (spmv2_configure() != 0) { set_error("s3o_create: cannot configure SpMV shared memory"); delete p; return S3O_ERR_CUDA; }
+    if (const char *v = getenv("S3O_TRACE")) { p->trace_state = atoi(v) > 0 ? 1 : 0; p->trace_solve = atoi(v); }    // trace the n-th solve
     if (const char *v = getenv("S3O_SPMV_VERSION")) p->spmv_version = atoi(v);
     if (const char *v = getenv("S3O_SPMV_GRID")) p->spmv_grid_cap = atoi(v);
     if (const char *v = getenv("S3O_SPMV4_CFG")) spmv4_set_cfg(atoi(v));
@@ -495,12 +522,14 @@ static int create_impl(int kind, int linear_dim, int device, s3o_problem **out) 
     }
     for (auto &ev : p->ev) cudaEventCreate(&ev);
     for (auto &ev : p->spmv_ev) cudaEventCreate(&ev);
-    if (dev_alloc(&p->d_sc, 1) || dev_alloc(&p->d_partials, 3 * kMaxPartials) ||
+    if (const char *v = getenv("S3O_COOP_LAUNCH")) p->coop_launch = atoi(v) != 0;
+    if (dev_alloc(&p->d_sc, 1) || dev_alloc(&p->d_partials, 3 * kMaxPartials) || dev_alloc(&p->d_gridbar, 2) ||
         cudaMallocHost((void **)&p->h_sc, sizeof(DevScalars)) != cudaSuccess) {
         s3o_destroy(p);
         return S3O_ERR_CUDA;
     }
     cudaMemsetAsync(p->d_sc, 0, sizeof(DevScalars), p->stream);
+    cudaMemsetAsync(p->d_gridbar, 0, 2 * sizeof(unsigned), p->stream);
     memset(p->h_sc, 0, sizeof(DevScalars));
     p->stats.dim = d;
     *out = p;
@@ -595,7 +624,7 @@ int s3o_destroy(s3o_problem *p) {
     ba_destroy(p);
     dev_free(p->d_meas_aos); dev_free(p->d_info_aos);
     dev_free(p->d_est[0]); dev_free(p->d_est[1]); dev_free(p->d_aux);
-    dev_free(p->d_sc); dev_free(p->d_partials);
+    dev_free(p->d_sc); dev_free(p->d_partials); dev_free(p->d_gridbar);
     comm_destroy(p->comm);
     if (p->h_sc) cudaFreeHost(p->h_sc);
     for (auto &ev : p->ev) if (ev) cudaEventDestroy(ev);

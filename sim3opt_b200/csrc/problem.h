@@ -5,6 +5,7 @@
 #include "comm.h"
 #include "internal.h"
 #include "kernels.cuh"
+#include "gridbar.cuh"
 
 namespace s3o {
 
@@ -80,6 +81,8 @@ struct s3o_problem {
     double *d_H = nullptr, *d_b = nullptr, *d_x = nullptr, *d_r = nullptr, *d_z = nullptr, *d_p = nullptr;
     double *d_q1 = nullptr, *d_T = nullptr, *d_Minv = nullptr, *d_scratch = nullptr, *d_partials = nullptr;
     DevScalars *d_sc = nullptr, *h_sc = nullptr;
+    unsigned *d_gridbar = nullptr;          // [0] arrival counter of the persistent kernels' grid barrier, [1] abort flag
+    bool coop_launch = false;               // S3O_COOP_LAUNCH=1: cudaLaunchCooperativeKernel instead of the counter barrier
     // parameters
     int robust_kind = S3O_ROBUST_NONE;
     double robust_param = 0;
@@ -117,6 +120,9 @@ struct s3o_problem {
     s3o::DirectState *direct = nullptr;
     int linsolver = S3O_LINSOLVER_AUTO;     // s3o_set_linear_solver
     bool reuse_factor = false;              // repeated solves with one matrix (inverse iteration)
+    // S3O_TRACE=1: CUDA-event timeline of ONE PCG iteration (the 5th of a solve), printed to stderr
+    std::vector<std::pair<const char *, cudaEvent_t>> trace;
+    int trace_state = 0, trace_solve = 0;   // 0 off, 1 armed, 2 recording, 3 done; solves left before recording
 };
 
 namespace s3o {
@@ -150,6 +156,28 @@ bool direct_available(const s3o_problem *p);          // false: the factor would
 int direct_solve(s3o_problem *p, double lambda, bool reuse_factor);
 void direct_invalidate(s3o_problem *p);               // H changed
 void direct_destroy(s3o_problem *p);
+// Launches a persistent kernel whose CTAs synchronise through grid_barrier (gridbar.cuh).  The kernel's LAST argument
+// is a GridBarrier; args[nargs - 1] must point to a GridBarrier that this call fills.
+inline int launch_persistent(s3o_problem *p, const void *func, int grid, int block, void **args, int nargs) {
+    GridBarrier *gb = (GridBarrier *)args[nargs - 1];
+    gb->counter = p->d_gridbar;
+    gb->abort = (int *)(p->d_gridbar + 1);
+    gb->cooperative = p->coop_launch ? 1 : 0;
+    if (p->coop_launch) {
+        S3O_CUDA(cudaLaunchCooperativeKernel(func, dim3(grid), dim3(block), args, 0, p->stream));
+        return S3O_OK;
+    }
+    S3O_CUDA(cudaMemsetAsync(p->d_gridbar, 0, sizeof(unsigned), p->stream));
+    S3O_CUDA(cudaLaunchKernel(func, dim3(grid), dim3(block), args, 0, p->stream));
+    return S3O_OK;
+}
+inline void trace_mark(s3o_problem *p, const char *what) {
+    if (p->trace_state != 2) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, p->stream);
+    p->trace.push_back({ what, e });
+}
 
 // ---- multilevel preconditioner (amg.cu) -------------------------------------------------------
 bool wants_multilevel(const s3o_problem *p);
