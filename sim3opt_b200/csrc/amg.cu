@@ -40,6 +40,7 @@ struct LevelDev {       // transfer level l -> l+1 plus operator and vectors of 
     double *rel = nullptr;      // [13][pad_fine]: R (row-major), t, s of S_i S_root^-1 for every level-l vertex
     double *A = nullptr, *Dinv = nullptr, *r = nullptr, *x = nullptr, *x2 = nullptr, *t = nullptr;
     double *z1 = nullptr, *q1 = nullptr, *rp = nullptr, *z2 = nullptr;      // K-cycle (two inner conjugate-gradient steps)
+    int32_t *acol = nullptr;    // [nblk] aggregate (in the transfer to the next level) of every block's column vertex
 };
 
 // scalars of the two-step inner conjugate-gradient iteration of one K-cycle level (device resident)
@@ -785,7 +786,7 @@ constexpr int kCoopThreads = 512, kCoopRows = 24000;
 
 struct CoopLevel {
     int n, pad_fine;
-    const int32_t *rowptr, *colidx, *mem_ptr, *mem_idx, *agg;
+    const int32_t *rowptr, *colidx, *mem_ptr, *mem_idx, *agg, *acol;
     const double *A, *Dinv, *rel;
     double *r, *x, *x2, *t, *z1, *q1, *rp, *z2;
 };
@@ -865,7 +866,7 @@ __device__ __forceinline__ void coop_down(const CoopLevel &L, const RSpec R, dou
         const int kb = L.rowptr[i], ke = L.rowptr[i + 1];
         // blocks in chunks of U: all index loads of a chunk are issued before the dependent vector loads, all of
         // those before the arithmetic (these levels live in L2: the phase is a chain of load latencies)
-        constexpr int U = 4;
+        constexpr int U = 8;
         for (int k0 = kb; k0 < ke; k0 += U) {
             int j[U];
             double rj[U];
@@ -936,34 +937,35 @@ __device__ __forceinline__ void coop_up(const CoopLevel &F, const CoopLevel &C, 
     for (int i = g; i < F.n; i += groups) {
         double acc = 0, xi_l = 0;
         const int kb = F.rowptr[i], ke = F.rowptr[i + 1];
-        constexpr int U = 4;
+        // all index loads of a chunk first (column vertex and its aggregate come from two parallel arrays, so the
+        // dependent chain is rowptr -> {colidx, acol} -> {frame, x, correction}), then the unrolled block loop whose
+        // loads do not depend on the running sum
+        constexpr int U = 12;
         for (int k0 = kb; k0 < ke; k0 += U) {
             int j[U], I[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) j[u] = k0 + u < ke ? F.colidx[k0 + u] : i;
-#pragma unroll
-            for (int u = 0; u < U; ++u) I[u] = C.agg[j[u]];
-            double xp[U][D];
+            for (int u = 0; u < U; ++u) {
+                const bool in = k0 + u < ke;
+                j[u] = in ? F.colidx[k0 + u] : i;
+                I[u] = in ? F.acol[k0 + u] : 0;
+            }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
+                if (k0 + u >= ke) break;
                 const Rel S = load_rel(C.rel, C.pad_fine, j[u]);
                 double xc[D], v[D];
 #pragma unroll
                 for (int c = 0; c < D; ++c) xc[c] = xget(X, (size_t)I[u] * D + c);
                 Xf<D>::apply(S, xc, v);
-#pragma unroll
-                for (int c = 0; c < D; ++c) xp[u][c] = __ldcg(F.x + (size_t)j[u] * D + c) + v[c];
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (k0 + u >= ke) break;
                 const double *Ak = F.A + (size_t)(k0 + u) * DD + lc * D;
+                double own = 0;
 #pragma unroll
-                for (int c = 0; c < D; ++c) acc += Ak[c] * xp[u][c];
-                if (j[u] == i) {
-#pragma unroll
-                    for (int c = 0; c < D; ++c) xi_l = (c == lc) ? xp[u][c] : xi_l;
+                for (int c = 0; c < D; ++c) {
+                    const double xpc = __ldcg(F.x + (size_t)j[u] * D + c) + v[c];
+                    acc += Ak[c] * xpc;
+                    own = (c == lc) ? xpc : own;
                 }
+                if (j[u] == i) xi_l = own;
             }
         }
         const double res = rget(R, (size_t)i * D + lc) - acc;
@@ -1140,7 +1142,7 @@ void free_level(LevelDev &L) {
     dev_free(L.rowptr); dev_free(L.colidx); dev_free(L.blk_row); dev_free(L.dpos);
     dev_free(L.gal_ptr); dev_free(L.gal_ent); dev_free(L.gal_i); dev_free(L.gal_j); dev_free(L.gal_order); dev_free(L.gal_out); dev_free(L.gal_mirror);
     dev_free(L.rel); dev_free(L.A); dev_free(L.Dinv); dev_free(L.r); dev_free(L.x); dev_free(L.x2); dev_free(L.t);
-    dev_free(L.z1); dev_free(L.q1); dev_free(L.rp); dev_free(L.z2);
+    dev_free(L.z1); dev_free(L.q1); dev_free(L.rp); dev_free(L.z2); dev_free(L.acol);
 }
 
 // Partitioned solve: rewrite level 0 of the global hierarchy in this rank's local indices.
@@ -1286,6 +1288,12 @@ int amg_setup(s3o_problem *p) {
         rc = rc ? rc : dev_alloc(&L.q1, (size_t)L.n * D);
         rc = rc ? rc : dev_alloc(&L.rp, (size_t)L.n * D);
         rc = rc ? rc : dev_alloc(&L.z2, (size_t)L.n * D);
+        if (l + 1 < nl) {       // aggregate of every block's column vertex in the transfer to the next level
+            const AmgHostLevel &N = st->host[l + 1];
+            std::vector<int32_t> acol(H.colidx.size());
+            for (size_t k = 0; k < H.colidx.size(); ++k) acol[k] = N.agg[H.colidx[k]];
+            rc = rc ? rc : up(p, &L.acol, acol);
+        }
     }
     if (!rc && st->dist) {
         const int world = (int)st->r_cnt.size();
@@ -1497,7 +1505,7 @@ int apply_t(s3o_problem *p, int init) {
                     T.n = S.n; T.pad_fine = S.pad_fine;
                     T.rowptr = S.rowptr; T.colidx = S.colidx; T.mem_ptr = S.mem_ptr; T.mem_idx = S.mem_idx; T.agg = S.agg;
                     T.A = S.A; T.Dinv = S.Dinv; T.rel = S.rel; T.r = S.r; T.x = S.x; T.x2 = S.x2; T.t = S.t;
-                    T.z1 = S.z1; T.q1 = S.q1; T.rp = S.rp; T.z2 = S.z2;
+                    T.z1 = S.z1; T.q1 = S.q1; T.rp = S.rp; T.z2 = S.z2; T.acol = S.acol;
                 }
                 double omega = kOmega;
                 int chk_ = chk;
