@@ -103,6 +103,7 @@ void free_structure(s3o_problem *p) {
     close_p2p(p);
     amg_destroy(p);
     direct_destroy(p);
+    p->last_pcg_iters = 0;
     p->auto_multilevel = false;
     p->built = false;
     p->linearized = false;
@@ -278,7 +279,10 @@ int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel
         launch_pcg_fin_init(p->d_sc, p->pcg_tol, p->pcg_max_iter, p->stream);
         p->stats.kernel_launches += 1;
     }
-    int batch = 8, launched = 0;
+    // Iterations are launched in batches between host checks of the convergence flag; an iteration launched after
+    // convergence exits at once but still costs ~30 launches (~120 us).  The first batch is sized by what the
+    // previous solve needed (consecutive LM iterations need similar counts), later ones grow geometrically.
+    int batch = p->last_pcg_iters > 0 ? std::max(2, std::min(64, p->last_pcg_iters - 1)) : 8, launched = 0;
     if (p->trace_state == 1 && p->trace_solve > 0) --p->trace_solve;
     for (;;) {
         for (int k = 0; k < batch; ++k) {
@@ -340,9 +344,10 @@ int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel
         }
         p->spmv_ev_used = 0;
         if (p->h_sc->done || launched >= p->pcg_max_iter + batch) break;
-        if (batch < 64) batch *= 2;
+        batch = launched < 16 ? std::max(2, launched / 2) : std::min(64, launched);
     }
     p->stats.pcg_iterations += p->h_sc->iters;
+    p->last_pcg_iters = p->h_sc->iters;
     if (p->h_sc->done != 1) p->stats.pcg_unconverged += 1;      // iteration cap or breakdown: the step is inexact
     // AUTO on a small graph: block-Jacobi until a solve turns out to be ill-conditioned (small lambda on
     // a long chain), the multilevel correction from the next solve on

@@ -94,6 +94,7 @@ struct s3o_problem {
     double stop_step = 0, stop_pred = 0;    // s3o_set_stop_rules
     double pcg_tol = 1e-8;
     int pcg_max_iter = 1000;
+    int last_pcg_iters = 0;                 // iterations of the previous PCG solve (sizes the first launch batch)
     int precond = S3O_PRECOND_AUTO;         // s3o_set_preconditioner
     bool auto_multilevel = false;           // AUTO: a block-Jacobi solve needed > 256 iterations
     bool linearized = false;
