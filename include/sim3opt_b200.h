@@ -64,6 +64,14 @@ enum s3o_robust { S3O_ROBUST_NONE = 0, S3O_ROBUST_HUBER = 1, S3O_ROBUST_PTAM_TUK
  * rotation drops below 4.5e-3 rad while sigma != 0; graphs that must converge to a minimum
  * (the synthetic configs) are run in CORRECTED mode on both the CPU and the GPU side. */
 enum s3o_math_mode { S3O_MATH_REFERENCE = 0, S3O_MATH_CORRECTED = 1 };
+/* [EXT vio_g2o] G2oEdgeScale / G2oEdgeScaleTrans (kitti_surf.cpp:827-847, :865-884) are not in the reference tree, and
+ * vio_g2o is cloned unpinned (build.sh:92), so their error form and the vertices' oplus are restated from the
+ * reference's call sites.  Both plausible readings are implemented and selectable:
+ *   DIFFERENCE (default): e_s = s_ji s_i - s_j (the rows of the reference's own linear system, :897-906), s <- s + d
+ *   LOGRATIO:             e_s = log(s_ji s_i / s_j),                                                      s <- s exp(d)
+ * The translation rows t_j - (s_j/s_i) R_j R_i^T t_i - t_ji (:969-985) and t <- t + d are common to both.  The
+ * scale null-vector stage (s3o_smallest_eigenvector) is defined on the DIFFERENCE rows. */
+enum s3o_scale_model { S3O_SCALE_MODEL_DIFFERENCE = 0, S3O_SCALE_MODEL_LOGRATIO = 1 };
 /* Preconditioner of the PCG that stands in for LinearSolverEigen::solve [EXT g2o] (the plug-in slot
  * filled at kitti_surf.cpp:553-558).  BLOCK_JACOBI: (H_ii + lambda I)^-1 per vertex.  MULTILEVEL:
  * block-Jacobi plus an aggregation coarse-space correction on the gauge near-null space
@@ -127,6 +135,7 @@ int s3o_set_estimates(s3o_problem *p, const double *est);
 int s3o_set_robust(s3o_problem *p, int kind, double param);
 int s3o_set_jacobian_mode(s3o_problem *p, int mode, double h /* numeric step, g2o: 1e-9 */);
 int s3o_set_math_mode(s3o_problem *p, int mode);
+int s3o_set_scale_model(s3o_problem *p, int model /* s3o_scale_model; S3O_KIND_SCALE / S3O_KIND_SCALE_TRANS */);
 /* tau (g2o 1e-5), user lambda init (<=0: tau*max diag), maxTrialsAfterFailure (g2o 10) */
 int s3o_set_lm(s3o_problem *p, double tau, double user_lambda_init, int max_trials);
 /* block-Jacobi PCG: relative residual tolerance |r|/|b| and iteration cap */

@@ -64,6 +64,7 @@ struct orc_problem {
     double robust_param;
     int jac_mode;
     double jac_h;
+    int scale_model;     /* 0 difference / additive, 1 log-ratio / multiplicative (row a18: both readings) */
     double tau, user_lambda;
     int max_trials;
     /* structure */
@@ -152,6 +153,7 @@ int orc_set_edges(orc_problem *p, int n, const int *v0, const int *v1, const dou
     return 0;
 }
 
+void orc_set_scale_model(orc_problem *p, int model) { p->scale_model = model ? 1 : 0; }
 void orc_set_robust(orc_problem *p, int kind, double param) { p->robust_kind = kind; p->robust_param = param; }
 void orc_set_jacobian_mode(orc_problem *p, int mode, double h) { p->jac_mode = mode; if (h > 0) p->jac_h = h; }
 void orc_set_lm(orc_problem *p, double tau, double user_lambda_init, int max_trials) {
@@ -263,12 +265,12 @@ static void edge_error(const orc_problem *p, int k, const double *xi, const doub
         quat_rot(qic, xi + 1, a);      /* R_i^T t_i */
         quat_rot(qj, a, b);            /* R_j R_i^T t_i */
         const double sr = xj[0] / xi[0];
-        e[0] = m[0] * xi[0] - xj[0];
+        e[0] = p->scale_model ? log(m[0] * xi[0] / xj[0]) : m[0] * xi[0] - xj[0];
         for (int c = 0; c < 3; ++c) e[1 + c] = xj[1 + c] - sr * b[c] - m[1 + c];
         break;
     }
     case ORC_KIND_SCALE:
-        e[0] = m[0] * xi[0] - xj[0];
+        e[0] = p->scale_model ? log(m[0] * xi[0] / xj[0]) : m[0] * xi[0] - xj[0];
         break;
     }
 }
@@ -281,6 +283,7 @@ static void oplus(const orc_problem *p, double *x, const double *delta) {
         memcpy(x, R, sizeof R);
     } else {
         for (int c = 0; c < p->d; ++c) x[c] += delta[c];
+        if (p->scale_model) x[0] = (x[0] - delta[0]) * exp(delta[0]);   /* s <- s exp(d_sigma) */
     }
 }
 
@@ -329,18 +332,18 @@ static void edge_jacobians(const orc_problem *p, int k, const double *xi, const 
         const double si = xi[0], sj = xj[0];
         memset(Ji, 0, sizeof(double) * 16);
         memset(Jj, 0, sizeof(double) * 16);
-        Ji[0] = m[0];
+        Ji[0] = p->scale_model ? 1.0 : m[0];
         Jj[0] = -1;
         for (int r = 0; r < 3; ++r) {
-            Ji[(1 + r) * 4] = sj / (si * si) * b[r];
-            Jj[(1 + r) * 4] = -b[r] / si;
+            Ji[(1 + r) * 4] = p->scale_model ? sj / si * b[r] : sj / (si * si) * b[r];
+            Jj[(1 + r) * 4] = p->scale_model ? -(sj / si) * b[r] : -b[r] / si;
             for (int c = 0; c < 3; ++c) Ji[(1 + r) * 4 + 1 + c] = -(sj / si) * Q[r * 3 + c];
             Jj[(1 + r) * 4 + 1 + r] = 1;
         }
         break;
     }
     case ORC_KIND_SCALE:
-        Ji[0] = p->meas[k];
+        Ji[0] = p->scale_model ? 1.0 : p->meas[k];
         Jj[0] = -1;
         break;
     }

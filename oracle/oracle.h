@@ -86,6 +86,8 @@ int orc_set_vertices(orc_problem *p, int n, const double *est, const unsigned ch
 /* meas is n x est_dim; info is n x d x d row-major or NULL (= identity) */
 int orc_set_edges(orc_problem *p, int n, const int *v0, const int *v1, const double *meas, const double *info);
 void orc_set_robust(orc_problem *p, int kind, double param);
+/* scale / scale-trans kinds: 0 = difference error + additive scale update (default), 1 = log-ratio + multiplicative */
+void orc_set_scale_model(orc_problem *p, int model);
 void orc_set_jacobian_mode(orc_problem *p, int mode, double h);
 void orc_set_lm(orc_problem *p, double tau, double user_lambda_init, int max_trials);
 

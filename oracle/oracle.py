@@ -51,6 +51,7 @@ def _declare(L):
     L.orc_set_vertices.argtypes = [C.c_void_p, C.c_int, _dp, _up, _dp]
     L.orc_set_edges.argtypes = [C.c_void_p, C.c_int, _ip, _ip, _dp, _dp]
     L.orc_set_robust.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    L.orc_set_scale_model.argtypes = [C.c_void_p, C.c_int]
     L.orc_set_jacobian_mode.argtypes = [C.c_void_p, C.c_int, C.c_double]
     L.orc_set_lm.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int]
     L.orc_build_structure.argtypes = [C.c_void_p]
@@ -244,6 +245,7 @@ class Problem:
             raise ValueError("orc_set_edges: bad vertex index")
 
     def set_robust(self, kind, param): self.L.orc_set_robust(self.h, kind, float(param))
+    def set_scale_model(self, model): self.L.orc_set_scale_model(self.h, int(model))
     def set_jacobian_mode(self, mode, h=0.0): self.L.orc_set_jacobian_mode(self.h, mode, float(h))
     def set_lm(self, tau=0.0, lambda_init=0.0, max_trials=0): self.L.orc_set_lm(self.h, tau, lambda_init, max_trials)
 

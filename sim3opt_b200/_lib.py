@@ -50,6 +50,7 @@ SYMBOLS = {
     "s3o_set_robust": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "s3o_set_jacobian_mode": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "s3o_set_math_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "s3o_set_scale_model": (C.c_int, [C.c_void_p, C.c_int]),
     "s3o_set_lm": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int]),
     "s3o_set_stop_rules": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "s3o_set_pcg": (C.c_int, [C.c_void_p, C.c_double, C.c_int]),

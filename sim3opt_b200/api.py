@@ -14,6 +14,7 @@ JAC_NUMERIC, JAC_ANALYTIC = 0, 1
 MATH_REFERENCE, MATH_CORRECTED = 0, 1
 PRECOND_AUTO, PRECOND_BLOCK_JACOBI, PRECOND_MULTILEVEL = 0, 1, 2
 LINSOLVER_AUTO, LINSOLVER_PCG, LINSOLVER_DIRECT = 0, 1, 2
+SCALE_MODEL_DIFFERENCE, SCALE_MODEL_LOGRATIO = 0, 1
 ROBUST_NONE, ROBUST_HUBER, ROBUST_PTAM_TUKEY, ROBUST_PTAM_CAUCHY, ROBUST_PTAM_HUBER, ROBUST_PTAM_LS = range(6)
 
 _EST_DIM = {KIND_SIM3: 8, KIND_SCALE_TRANS: 4, KIND_SCALE: 1, KIND_BA: 7}
@@ -102,6 +103,7 @@ class Problem:
     def set_robust(self, kind, param=0.0): self._check(self.L.s3o_set_robust(self.h, kind, float(param)))
     def set_jacobian_mode(self, mode, h=0.0): self._check(self.L.s3o_set_jacobian_mode(self.h, mode, float(h)))
     def set_math_mode(self, mode): self._check(self.L.s3o_set_math_mode(self.h, int(mode)))
+    def set_scale_model(self, model): self._check(self.L.s3o_set_scale_model(self.h, int(model)))
     def set_lm(self, tau=0.0, lambda_init=0.0, max_trials=0): self._check(self.L.s3o_set_lm(self.h, tau, lambda_init, max_trials))
     def set_pcg(self, rel_tol=0.0, max_iter=0): self._check(self.L.s3o_set_pcg(self.h, rel_tol, max_iter))
     def set_stop_rules(self, max_abs_step=0.0, min_rel_predicted_decrease=0.0):

@@ -95,11 +95,12 @@ __device__ __forceinline__ void from_sim3(const Sim3 &S, double x[8]) {
 }
 
 // e = error(measurement m, vertex(0)=xi, vertex(1)=xj); qi/qj: fixed rotations (scale-trans only)
+// flags: bit 0 = S3O_MATH_CORRECTED (Sim3 coefficients), bit 1 = S3O_SCALE_MODEL_LOGRATIO (scale / scale-trans kinds)
 template <int KIND>
 __device__ __noinline__ void model_error(const double *m, const double *xi, const double *xj, const double *qi,
-                                         const double *qj, double *e, bool corrected) {
+                                         const double *qj, double *e, int flags) {
     if constexpr (KIND == S3O_KIND_SIM3) {
-        sim3_edge_error(to_sim3(m), to_sim3(xi), to_sim3(xj), e, corrected);
+        sim3_edge_error(to_sim3(m), to_sim3(xi), to_sim3(xj), e, (flags & 1) != 0);
     } else if constexpr (KIND == S3O_KIND_SCALE_TRANS) {
         // [EXT vio_g2o] G2oEdgeScaleTrans model restated from kitti_surf.cpp:897-906 (scale rows
         // s_ji*s_i - s_j) and :969-985 (translation rows t_j - (s_j/s_i) R_j R_i^T t_i - t_ji)
@@ -107,30 +108,31 @@ __device__ __noinline__ void model_error(const double *m, const double *xi, cons
         quat_rotate(-qi[0], -qi[1], -qi[2], qi[3], xi[1], xi[2], xi[3], ax, ay, az);
         quat_rotate(qj[0], qj[1], qj[2], qj[3], ax, ay, az, bx, by, bz);
         const double sr = xj[0] / xi[0];
-        e[0] = m[0] * xi[0] - xj[0];
+        e[0] = (flags & 2) ? log(m[0] * xi[0] / xj[0]) : m[0] * xi[0] - xj[0];
         e[1] = xj[1] - sr * bx - m[1];
         e[2] = xj[2] - sr * by - m[2];
         e[3] = xj[3] - sr * bz - m[3];
     } else {
-        e[0] = m[0] * xi[0] - xj[0];
+        e[0] = (flags & 2) ? log(m[0] * xi[0] / xj[0]) : m[0] * xi[0] - xj[0];
     }
 }
 
 template <int KIND>
-__device__ __forceinline__ void model_oplus(double *x, const double *delta, bool corrected) {
+__device__ __forceinline__ void model_oplus(double *x, const double *delta, int flags) {
     if constexpr (KIND == S3O_KIND_SIM3) {
-        const Sim3 U = sim3_exp(delta, corrected);
+        const Sim3 U = sim3_exp(delta, (flags & 1) != 0);
         from_sim3(sim3_mul(U, to_sim3(x)), x);
     } else {
 #pragma unroll
         for (int c = 0; c < Model<KIND>::D; ++c) x[c] += delta[c];
+        if (flags & 2) x[0] = (x[0] - delta[0]) * exp(delta[0]);       // multiplicative scale update s <- s exp(d_sigma)
     }
 }
 
 template <int KIND>
 __device__ __forceinline__ void model_jac_analytic(const double *m, const double *xi, const double *xj,
                                                    const double *qi, const double *qj, const double *e, double *A,
-                                                   double *B) {
+                                                   double *B, int flags) {
     if constexpr (KIND == S3O_KIND_SIM3) {
         sim3_edge_jacobians(to_sim3(m), e, A, B);
     } else if constexpr (KIND == S3O_KIND_SCALE_TRANS) {
@@ -148,18 +150,19 @@ __device__ __forceinline__ void model_jac_analytic(const double *m, const double
         for (int r = 0; r < 3; ++r) b[r] = Q[r * 3] * xi[1] + Q[r * 3 + 1] * xi[2] + Q[r * 3 + 2] * xi[3];
 #pragma unroll
         for (int k = 0; k < 16; ++k) { A[k] = 0; B[k] = 0; }
-        A[0] = m[0];
+        const bool lr = (flags & 2) != 0;      // log-ratio error, multiplicative scale update: d s = s d sigma
+        A[0] = lr ? 1.0 : m[0];
         B[0] = -1;
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            A[(1 + r) * 4] = sj / (si * si) * b[r];
-            B[(1 + r) * 4] = -b[r] / si;
+            A[(1 + r) * 4] = lr ? sj / si * b[r] : sj / (si * si) * b[r];
+            B[(1 + r) * 4] = lr ? -(sj / si) * b[r] : -b[r] / si;
 #pragma unroll
             for (int c = 0; c < 3; ++c) A[(1 + r) * 4 + 1 + c] = -(sj / si) * Q[r * 3 + c];
             B[(1 + r) * 4 + 1 + r] = 1;
         }
     } else {
-        A[0] = m[0];
+        A[0] = (flags & 2) ? 1.0 : m[0];
         B[0] = -1;
     }
 }
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(NT) chi2_kernel(GraphDev g, double *__restrict
             load_planes<4>(g.aux, g.nv_pad, vi, qi);
             load_planes<4>(g.aux, g.nv_pad, vj, qj);
         }
-        model_error<KIND>(m, xi, xj, qi, qj, e, g.math_corrected);
+        model_error<KIND>(m, xi, xj, qi, qj, e, g.model_flags);
         double c = quad_form_packed<D>(g.info, g.info_diag, g.ne_pad, t, e);
         if (g.robust_kind != S3O_ROBUST_NONE) {
             double r0, r1;
@@ -267,7 +270,7 @@ __global__ void edge_errors_kernel(GraphDev g, double *__restrict__ err, double 
         load_planes<4>(g.aux, g.nv_pad, vi, qi);
         load_planes<4>(g.aux, g.nv_pad, vj, qj);
     }
-    model_error<KIND>(m, xi, xj, qi, qj, e, g.math_corrected);
+    model_error<KIND>(m, xi, xj, qi, qj, e, g.model_flags);
     for (int k = 0; k < D; ++k) err[(size_t)t * D + k] = e[k];
     if (chi) chi[t] = quad_form_packed<D>(g.info, g.info_diag, g.ne_pad, t, e);
 }
@@ -384,9 +387,9 @@ __global__ void __launch_bounds__(NT, S3O_LIN_MINB) linearize_kernel(GraphDev g,
             load_planes<4>(g.aux, g.nv_pad, vi, qi);
             load_planes<4>(g.aux, g.nv_pad, vj, qj);
         }
-        model_error<KIND>(m, xi, xj, qi, qj, e, g.math_corrected);
+        model_error<KIND>(m, xi, xj, qi, qj, e, g.model_flags);
         if constexpr (JAC == S3O_JAC_ANALYTIC) {
-            model_jac_analytic<KIND>(m, xi, xj, qi, qj, e, A, B);
+            model_jac_analytic<KIND>(m, xi, xj, qi, qj, e, A, B, g.model_flags);
         } else {
             // g2o BaseBinaryEdge::linearizeOplus: central differences through oplus, +h then -h
             const double scalar = 1.0 / (2 * h);
@@ -401,12 +404,12 @@ __global__ void __launch_bounds__(NT, S3O_LIN_MINB) linearize_kernel(GraphDev g,
                     for (int k = 0; k < D; ++k) add[k] = 0;
                     add[c] = h;
                     for (int k = 0; k < EST; ++k) xp[k] = side == 0 ? xi[k] : xj[k];
-                    model_oplus<KIND>(xp, add, g.math_corrected);
-                    model_error<KIND>(m, side == 0 ? xp : xi, side == 0 ? xj : xp, qi, qj, e1, g.math_corrected);
+                    model_oplus<KIND>(xp, add, g.model_flags);
+                    model_error<KIND>(m, side == 0 ? xp : xi, side == 0 ? xj : xp, qi, qj, e1, g.model_flags);
                     add[c] = -h;
                     for (int k = 0; k < EST; ++k) xp[k] = side == 0 ? xi[k] : xj[k];
-                    model_oplus<KIND>(xp, add, g.math_corrected);
-                    model_error<KIND>(m, side == 0 ? xp : xi, side == 0 ? xj : xp, qi, qj, e2, g.math_corrected);
+                    model_oplus<KIND>(xp, add, g.model_flags);
+                    model_error<KIND>(m, side == 0 ? xp : xi, side == 0 ? xj : xp, qi, qj, e2, g.model_flags);
                     for (int r = 0; r < D; ++r) J[r * D + c] = scalar * (e1[r] - e2[r]);
                 }
             }
@@ -657,7 +660,7 @@ __global__ void retract_kernel(GraphDev g, const double *__restrict__ x, double 
         double delta[D];
 #pragma unroll
         for (int k = 0; k < D; ++k) delta[k] = x[(size_t)hcol * D + k];
-        model_oplus<KIND>(xs, delta, g.math_corrected);
+        model_oplus<KIND>(xs, delta, g.model_flags);
     }
 #pragma unroll
     for (int k = 0; k < EST; ++k) est_out[(size_t)k * g.nv_pad + v] = xs[k];

@@ -39,6 +39,7 @@ struct GraphDev {
     int robust_kind;
     double robust_param;
     bool math_corrected;     // s3o_set_math_mode
+    int model_flags;         // bit 0: math_corrected, bit 1: log-ratio scale model (s3o_set_scale_model)
     const uint8_t *primary;  // [ne] partitioned solve: 1 if this rank counts the edge's chi2 (null: all)
     const int32_t *ghidx;    // [nv] partitioned solve: global Hessian index addressing the gathered step
 };

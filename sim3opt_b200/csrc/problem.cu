@@ -48,6 +48,7 @@ GraphDev graph_view(const s3o_problem *p, int which) {
     g.meas = p->d_meas; g.info = p->has_info ? p->d_info : nullptr; g.info_diag = p->info_diag;
     g.robust_kind = p->robust_kind; g.robust_param = p->robust_param;
     g.math_corrected = p->math_mode == S3O_MATH_CORRECTED;
+    g.model_flags = (g.math_corrected ? 1 : 0) | (p->scale_model == S3O_SCALE_MODEL_LOGRATIO ? 2 : 0);
     g.primary = p->dist ? p->d_primary : nullptr;
     g.ghidx = p->dist ? p->d_ghidx : nullptr;
     return g;
@@ -209,7 +210,9 @@ namespace s3o {
 // multilevel preconditioner: Sim3 graphs on one GPU; AUTO switches it on for large graphs
 bool wants_multilevel(const s3o_problem *p) {
     const int nf = p->dist ? p->plan.nf_global : p->S.nf;
+    // (the coarse space of the scale kinds is built on the additive scale update: not with the log-ratio model)
     return p->kind != S3O_KIND_BA && p->kind != 100 /* solver-only handle: no poses to build the coarse space on */ &&
+           p->scale_model == S3O_SCALE_MODEL_DIFFERENCE &&
            (p->precond == S3O_PRECOND_MULTILEVEL || (p->precond == S3O_PRECOND_AUTO && (nf >= 20000 || p->auto_multilevel)));
 }
 
@@ -856,6 +859,14 @@ int s3o_set_math_mode(s3o_problem *p, int mode) {
     return S3O_OK;
 }
 
+int s3o_set_scale_model(s3o_problem *p, int model) {
+    if (!p || (model != S3O_SCALE_MODEL_DIFFERENCE && model != S3O_SCALE_MODEL_LOGRATIO)) { set_error("s3o_set_scale_model: bad model"); return S3O_ERR_INVALID; }
+    if (p->kind != S3O_KIND_SCALE && p->kind != S3O_KIND_SCALE_TRANS) { set_error("s3o_set_scale_model: scale / scale-trans problems only"); return S3O_ERR_UNSUPPORTED; }
+    p->scale_model = model;
+    p->linearized = false;
+    return S3O_OK;
+}
+
 int s3o_set_lm(s3o_problem *p, double tau, double user_lambda_init, int max_trials) {
     if (!p) return S3O_ERR_INVALID;
     if (tau > 0) p->tau = tau;
@@ -1414,6 +1425,10 @@ int s3o_smallest_eigenvector(s3o_problem *p, int max_iter, double tol, double *x
                              double *lambda_max, int *iterations) {
     if (!p || !x) { set_error("s3o_smallest_eigenvector: bad arguments"); return S3O_ERR_INVALID; }
     if (p->dist || p->kind == S3O_KIND_BA) { set_error("s3o_smallest_eigenvector: not available for this problem"); return S3O_ERR_UNSUPPORTED; }
+    if (p->scale_model != S3O_SCALE_MODEL_DIFFERENCE) {   // the reference's linear system (kitti_surf.cpp:897-906) is the DIFFERENCE rows
+        set_error("s3o_smallest_eigenvector: defined on the S3O_SCALE_MODEL_DIFFERENCE rows");
+        return S3O_ERR_UNSUPPORTED;
+    }
     cudaSetDevice(p->device);
     int rc = ensure_built(p);
     if (rc) return rc;

@@ -87,6 +87,7 @@ struct s3o_problem {
     int robust_kind = S3O_ROBUST_NONE;
     double robust_param = 0;
     int math_mode = S3O_MATH_REFERENCE;
+    int scale_model = S3O_SCALE_MODEL_DIFFERENCE;      // s3o_set_scale_model
     int jac_mode = S3O_JAC_ANALYTIC;
     double jac_h = 1e-9;
     double tau = 1e-5, user_lambda = 0;

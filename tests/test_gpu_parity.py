@@ -228,6 +228,45 @@ def test_scale_trans_lockstep(kitti_k1):
     assert abs(chi_g - chi_c) <= 1e-6 * max(chi_c, 1e-12)
 
 
+@pytest.mark.parametrize("kind_name", ["SCALE_TRANS", "SCALE"])
+def test_scale_model_logratio_lockstep(kitti_k1, kind_name):
+    """Row a18: log-ratio scale error + multiplicative scale update (s3o_set_scale_model), device vs oracle:
+    chi2, H, b at a perturbed estimate and three LM iterations in lock step."""
+    orc = _orc()
+    import sim3opt_b200 as s3
+    from oracle import kitti_io
+    st = kitti_io.to_scale_trans_graph(kitti_k1)
+    g = dict(st)
+    if kind_name == "SCALE":
+        g = dict(est=st["est"][:, :1].copy(), fixed=st["fixed"], v0=st["v0"], v1=st["v1"], meas=st["meas"][:, :1].copy())
+    rng = np.random.default_rng(11)
+    g["est"] = g["est"].copy()
+    g["est"][:, 0] *= np.exp(0.05 * rng.standard_normal(len(g["est"])))
+    for jac in (0, 1):
+        gpu = make_gpu(g, kind=getattr(s3, "KIND_" + kind_name), jac=jac)
+        cpu = make_oracle(g, kind=getattr(orc, "KIND_" + kind_name), jac=jac)
+        gpu.set_scale_model(s3.SCALE_MODEL_LOGRATIO)
+        cpu.set_scale_model(1)
+        assert abs(gpu.chi2() - cpu.chi2()) <= 1e-12 * cpu.chi2()
+        Hg, bg = gpu.linearize()
+        Hc, bc = cpu.linearize()
+        assert np.abs(Hg - Hc).max() <= 1e-9 * np.abs(Hc).max()
+        assert np.abs(bg - bc).max() <= 1e-9 * np.abs(bc).max()
+        gpu.set_pcg(1e-13, 100000)
+        for it in range(3):
+            n_g, chi_g, lam_g, _ = gpu.optimize(1)
+            n_c, chi_c, lam_c, _ = cpu.optimize(1)
+            assert abs(chi_g - chi_c) <= 1e-7 * max(chi_c, 1e-12), (it, chi_g, chi_c)
+        assert np.abs(gpu.vertices() - cpu.vertices()).max() <= 1e-6
+    # the null-vector stage is defined on the DIFFERENCE rows only
+    if kind_name == "SCALE":
+        with pytest.raises(s3.S3OError):
+            gpu.smallest_eigenvector()
+    # Sim3 problems have no scale model to switch
+    with pytest.raises(s3.S3OError):
+        s3.Problem(s3.KIND_SIM3).set_scale_model(1)
+
+
 def test_edge_cases():
     import sim3opt_b200 as s3
     p = s3.Problem(s3.KIND_SIM3)
