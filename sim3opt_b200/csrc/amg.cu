@@ -1249,6 +1249,7 @@ int amg_setup(s3o_problem *p) {
     }
     const int nl = (int)st->host.size();
     if (nl == 0) return S3O_OK;
+    setup_mark("  hierarchy: host build");
     int rc = up(p, &st->d_vid0, p->S.free2v);
     st->lev.resize(nl);
     for (int l = 0; l < nl && !rc; ++l) {
@@ -1295,6 +1296,7 @@ int amg_setup(s3o_problem *p) {
             rc = rc ? rc : up(p, &L.acol, acol);
         }
     }
+    setup_mark("  hierarchy: uploads");
     if (!rc && st->dist) {
         const int world = (int)st->r_cnt.size();
         st->r_seg = st->r_max + 2;

@@ -132,9 +132,11 @@ void amg_build_hierarchy(const HostStructure &S, int coarsest_max, int max_level
     while (F.n > coarsest_max && (int)levels.size() < max_levels) {
         std::vector<int32_t> aptr, aidx;
         build_adjacency(F, levels.empty() ? seg : 0, aptr, aidx);
+        setup_mark("    adjacency");
         AmgHostLevel L;
         L.n_fine = F.n;
         aggregate(F.n, aptr, aidx, L.agg, L.root);
+        setup_mark("    aggregate");
         L.n = (int)L.root.size();
         if (L.n * 10 > F.n * 9) break;          // aggregation stalled (isolated vertices): stop here
         L.vid.resize(L.n);
@@ -164,6 +166,7 @@ void amg_build_hierarchy(const HostStructure &S, int coarsest_max, int max_level
             keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
             for (uint64_t &k : keys) k = ((k >> bits) << 32) | (k & ((1ull << bits) - 1));
         }
+        setup_mark("    coarse keys sort");
         const int nblk = (int)keys.size();
         L.rowptr.assign(L.n + 1, 0);
         L.colidx.resize(nblk);
@@ -203,6 +206,7 @@ void amg_build_hierarchy(const HostStructure &S, int coarsest_max, int max_level
                 else { ub = ubidx[find_col(L, I, J)]; flag = 0; }
             }
         };
+        setup_mark("    coarse pattern");
         L.gal_ptr.assign(L.nub + 1, 0);
         std::vector<int32_t> tgt(F.nblk);            // (ub << 2) | flag or -1, computed once (binary searches)
         parallel_ranges(F.nblk, [&](int lo, int hi) {
@@ -212,6 +216,7 @@ void amg_build_hierarchy(const HostStructure &S, int coarsest_max, int max_level
                 tgt[k] = ub >= 0 ? (ub << 2) | flag : -1;
             }
         });
+        setup_mark("    targets");
         for (int k = 0; k < F.nblk; ++k)
             if (tgt[k] >= 0) L.gal_ptr[(tgt[k] >> 2) + 1]++;
         for (int u = 0; u < L.nub; ++u) L.gal_ptr[u + 1] += L.gal_ptr[u];
@@ -229,6 +234,7 @@ void amg_build_hierarchy(const HostStructure &S, int coarsest_max, int max_level
                 L.gal_j[pos] = F.bcol[k];
             }
         }
+        setup_mark("    contributor lists");
         levels.push_back(std::move(L));
         const AmgHostLevel &B = levels.back();
         F.n = B.n; F.nblk = (int)B.colidx.size(); F.brow = B.blk_row.data(); F.bcol = B.colidx.data(); F.upper = false;

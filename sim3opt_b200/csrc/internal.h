@@ -2,6 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -22,6 +25,17 @@ void set_error(const char *fmt, ...);
     } while (0)
 
 inline int pad32(int n) { return (n + 31) & ~31; }
+
+// S3O_SETUP_TRACE=1: wall-clock of the set-up stages on stderr (diagnostic)
+inline void setup_mark(const char *what) {
+    static const bool on = getenv("S3O_SETUP_TRACE") != nullptr;
+    static std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    if (what) fprintf(stderr, "[s3o setup] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
+    last = now;
+}
+
 
 // Host-side result of the structure build.
 struct HostStructure {

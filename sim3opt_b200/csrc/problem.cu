@@ -762,6 +762,7 @@ int s3o_set_edges(s3o_problem *p, int n, const int32_t *v0, const int32_t *v1, c
             return S3O_ERR_INVALID;
         }
     cudaSetDevice(p->device);
+    setup_mark(nullptr);
     free_structure(p);
     dev_free(p->d_meas_aos); dev_free(p->d_info_aos);
     p->user_ne = n;
@@ -783,6 +784,7 @@ int s3o_set_edges(s3o_problem *p, int n, const int32_t *v0, const int32_t *v1, c
         p->info_diag = true;
         for (char f : nondiag) if (f) p->info_diag = false;
     }
+    setup_mark("set_edges: info scan");
     std::vector<double> meas_loc, info_loc;
     if (p->dist) {
         // keep only the edges that touch a vertex this rank owns (cut edges live on both sides)
@@ -809,6 +811,7 @@ int s3o_set_edges(s3o_problem *p, int n, const int32_t *v0, const int32_t *v1, c
         p->v1.assign(v1, v1 + n);
     }
     p->ne = n;
+    setup_mark("set_edges: index copy");
     int rc;
     const size_t mcount = (size_t)n * p->est_dim;
     if ((rc = dev_alloc(&p->d_meas_aos, mcount))) return rc;
@@ -825,12 +828,14 @@ int s3o_set_edges(s3o_problem *p, int n, const int32_t *v0, const int32_t *v1, c
                 for (int r = 0; r < d; ++r) info_diag_host[k * d + r] = info[k * dd + r * d + r];
             src = info_diag_host.data();
             icount = (size_t)n * d;
+            setup_mark("set_edges: diag extract");
         }
         if ((rc = dev_alloc(&p->d_info_aos, icount))) return rc;
         if (n) S3O_CUDA(cudaMemcpyAsync(p->d_info_aos, src, icount * sizeof(double), cudaMemcpyHostToDevice, p->stream));
         p->stats.h2d_bytes += (int64_t)(icount * sizeof(double));
     }
     S3O_CUDA(cudaStreamSynchronize(p->stream));
+    setup_mark("set_edges: upload");
     p->stats.n_edges = p->user_ne;
     return S3O_OK;
 }
@@ -929,6 +934,7 @@ int s3o_build_structure(s3o_problem *p, int *n_free, int *n_blocks) {
     cudaSetDevice(p->device);
     if (!p->built) {
         if (p->ne > 0 && !p->d_meas_aos) { set_error("s3o_build_structure: edges were consumed; call s3o_set_edges again"); return S3O_ERR_INVALID; }
+        setup_mark(nullptr);
         free_structure(p);
         HostStructure &S = p->S;
         // the index build runs on the device (structure_dev.cu); S3O_STRUCTURE=host selects the host twin
@@ -945,6 +951,7 @@ int s3o_build_structure(s3o_problem *p, int *n_free, int *n_blocks) {
                                     : build_structure_device(p->stream, p->nv, p->fixed.data(), nullptr, 0, p->ne, p->v0.data(), p->v1.data(), S);
             if (rcs) return rcs;
         }
+        setup_mark("structure: index build");
         const int rows_own = p->dist ? p->plan.n_own : S.nf;
         p->ne_pad = pad32(S.ne_act);
         int rc = 0;
@@ -996,11 +1003,13 @@ int s3o_build_structure(s3o_problem *p, int *n_free, int *n_blocks) {
         }
         dev_free(p->d_meas_aos);
         dev_free(p->d_info_aos);
+        setup_mark("structure: uploads + pack");
         p->built = true;
         p->stats.n_free = S.nf; p->stats.n_blocks = S.nb;
         if (p->want_p2p_setup && (rc = setup_p2p(p))) return rc;
         // the aggregation hierarchy is structure work too: build it here rather than inside the first solve
         if (wants_multilevel(p) && (rc = amg_setup(p))) return rc;
+        setup_mark("structure: hierarchy total");
     }
     if (n_free) *n_free = p->S.nf;
     if (n_blocks) *n_blocks = p->S.nb;

@@ -1,5 +1,8 @@
 // problem.h -- the s3o_problem object and the host-side helpers shared by problem.cu and ba.cu.
 #pragma once
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "comm.h"
