@@ -305,6 +305,8 @@ typedef struct s3o_stats {
     double est_distance;       /* estimated max-norm distance to the stationary point after it (s3o_set_stop_rules) */
     int32_t stop_reason;       /* why the last s3o_optimize returned (s3o_set_stop_rules) */
     int32_t reserved0;
+    int64_t multilevel_rebuilds; /* solves that rebuilt the coarse operators P^T H P of the multilevel preconditioner ... */
+    int64_t multilevel_reuses;   /* ... and solves that kept them (LM retry: same linearisation point, new lambda) */
 } s3o_stats;
 int s3o_get_stats(s3o_problem *p, s3o_stats *out);
 int s3o_reset_stats(s3o_problem *p);

@@ -30,6 +30,7 @@ class Stats(C.Structure):
         ("sum_ms_linearize", C.c_double), ("sum_ms_solve", C.c_double), ("sum_ms_update", C.c_double),
         ("last_step_inf", C.c_double), ("est_distance", C.c_double),
         ("stop_reason", C.c_int32), ("reserved0", C.c_int32),
+        ("multilevel_rebuilds", C.c_int64), ("multilevel_reuses", C.c_int64),
     ]
 
 

@@ -41,6 +41,9 @@ struct LevelDev {       // transfer level l -> l+1 plus operator and vectors of 
     double *A = nullptr, *Dinv = nullptr, *r = nullptr, *x = nullptr, *x2 = nullptr, *t = nullptr;
     double *z1 = nullptr, *q1 = nullptr, *rp = nullptr, *z2 = nullptr;      // K-cycle (two inner conjugate-gradient steps)
     int32_t *acol = nullptr;    // [nblk] aggregate (in the transfer to the next level) of every block's column vertex
+    // A = K + lambda M with K = P^T H P (Galerkin product of the undamped Hessian) and M = P^T P, which is block
+    // diagonal on every level (one nonzero block per row of P): a new lambda only rewrites the diagonal blocks
+    double *Kd = nullptr, *M = nullptr;     // [n][D*D] diagonal blocks of K, blocks of M
 };
 
 // scalars of the two-step inner conjugate-gradient iteration of one K-cycle level (device resident)
@@ -55,6 +58,13 @@ struct AmgState {
     double *d_dense = nullptr;      // inverse of the coarsest operator, [N][N]
     bool dense = false;
     bool frames_valid = false;
+    // K = P^T H P is rebuilt when the linearisation point has moved; a new lambda at the same point (LM retry) only
+    // shifts the diagonal blocks.  (Keeping K across linearisations does NOT work, measured on the 1M-pose sphere: with
+    // a Hessian whose diagonal blocks had moved by < 2 % the PCG no longer converged in 20 000 iterations -- the coarse
+    // energy of the near-null gauge modes must be the current Hessian's, else the coarse solve over-corrects them.)
+    bool k_valid = false, lin_changed = true;
+    std::vector<size_t> m_off, m_cnt;   // partitioned solve: all-gather segments of M_1
+    int64_t rebuilds = 0, reuses = 0;
     // partitioned solve: the fine level is local (owned + ghost rows), level 1 and below are replicated.
     // Rank q computes the level-1 rows [crow[q], crow[q+1]) (its own aggregates); the segments are
     // exchanged with in-place all-gathers: the residual r_1 every PCG iteration, the operator A_1 every trial.
@@ -72,6 +82,7 @@ struct AmgState {
     // cycle below them (Notay's K-cycle) instead of one V-cycle visit; every level from `coop_first` down is
     // walked by ONE cooperative kernel (grid barriers instead of kernel boundaries)
     int kdepth = 0, coop_first = 0, coop_grid = 0;
+    unsigned kmask = 0;         // bit l: level l is a K-cycle level (default: the first kdepth levels; S3O_KMASK overrides)
     KScal *d_ks = nullptr;          // [kMaxLevels]
     bool dense_coop = false;        // coarsest level inverted by the cooperative kernel (too large for shared memory)
     double *d_colbuf = nullptr, *d_rowbuf = nullptr;
@@ -189,69 +200,82 @@ __global__ void amg_rel_kernel(const double *__restrict__ est, const double *__r
     rel[(size_t)12 * pad + i] = sc;
 }
 
-// ---- Galerkin product: one 8-lane group per upper coarse block, lane c holds column c --------
-// Entry lists carry (block | flag, row vertex, column vertex) so the only dependent loads per
-// entry are the frames and the block itself; the next entry's indices are fetched one step ahead.
+// ---- Galerkin product: one 8-lane group per upper coarse block ---------------------------------
+// Entry lists carry (block | flag, row vertex, column vertex) so the only dependent loads per entry are the frames
+// and the block itself; the next entry's indices are fetched one step ahead.  Per entry X = P_l^T A P_r is formed in
+// two structured applications with a transposition in between: lane r reads ROW r of A (7 loads instead of the whole
+// block) and turns it into row r of A P_r; the group transposes through shared memory; lane c turns column c of
+// A P_r into column c of X.  flag 0: X = P_i^T A P_j;  1: X = P_j^T A^T P_i (block stored on the other side);
+// 2: both (an off-diagonal fine block inside one aggregate) -- the second is the transpose of the first, so those X
+// are also summed separately and their transpose is added once at the end.
 template <int D, bool FINE_UPPER>
 __global__ void __launch_bounds__(128, 4) amg_galerkin_kernel(const double *__restrict__ Af, const int32_t *__restrict__ gal_i,
                                                               const int32_t *__restrict__ gal_j, const double *__restrict__ rel,
-                                                              int pad, double lambda, int nub,
+                                                              int pad, int nub,
                                                               const int32_t *__restrict__ gal_ptr, const int32_t *__restrict__ gal_ent,
                                                               const int32_t *__restrict__ gal_out,
                                                               const int32_t *__restrict__ gal_mirror, double *__restrict__ Ac,
                                                               int write_mirror, const int32_t *__restrict__ gal_order) {
-    const int slot = blockIdx.x * (blockDim.x / 8) + threadIdx.x / 8;
+    __shared__ double tr[16][D * D + 1];
+    const int grp = threadIdx.x / 8;
+    const int slot = blockIdx.x * (blockDim.x / 8) + grp;
     const int c = threadIdx.x & 7;
-    if (slot >= nub || c >= D) return;
+    if (slot >= nub) return;              // the whole group leaves
+    const unsigned gmask = 0xffu << (threadIdx.x & 24);
+    const bool act = c < D;
+    const int cc = act ? c : 0;           // lane 7 shadows lane 0 (keeps the group convergent), stores nothing
     const int ub = gal_order[slot];       // lists of equal length share a warp
-    double acc[D];
+    double acc[D], accS[D];
 #pragma unroll
-    for (int r = 0; r < D; ++r) acc[r] = 0;
-    double ec[D];
-#pragma unroll
-    for (int r = 0; r < D; ++r) ec[r] = (r == c) ? 1.0 : 0.0;
+    for (int r = 0; r < D; ++r) { acc[r] = 0; accS[r] = 0; }
+    bool any2 = false;
     const int ebeg = gal_ptr[ub], eend = gal_ptr[ub + 1];
     int ent = 0, i = 0, j = 0;
     if (ebeg < eend) { ent = __ldg(gal_ent + ebeg); i = __ldg(gal_i + ebeg); j = __ldg(gal_j + ebeg); }
     for (int e = ebeg; e < eend; ++e) {
         const int k = ent >> 2, flag = ent & 3;
-        const int ci = i, cj = j;
+        const int vl = flag == 1 ? j : i, vr = flag == 1 ? i : j;      // left and right factor of X
         if (e + 1 < eend) { ent = __ldg(gal_ent + e + 1); i = __ldg(gal_i + e + 1); j = __ldg(gal_j + e + 1); }
-        const Rel ri = load_rel(rel, pad, ci);
-        const Rel rj = (ci == cj) ? ri : load_rel(rel, pad, cj);
+        const Rel rl = load_rel(rel, pad, vl);
+        const Rel rr = (vl == vr) ? rl : load_rel(rel, pad, vr);
         const double *A = Af + (size_t)k * DD;
-        double v[D], w[D], u[D];
-        if (flag != 1) {        // column c of P_i^T A P_j
-            Xf<D>::apply(rj, ec, v);
+        double a[D], b[D], w[D], u[D];
+        if (flag != 1) {
 #pragma unroll
-            for (int r = 0; r < D; ++r) {
-                double a = 0;
+            for (int q = 0; q < D; ++q) a[q] = __ldg(A + cc * D + q);
+        } else {
 #pragma unroll
-                for (int q = 0; q < D; ++q) a += __ldg(A + r * D + q) * v[q];
-                w[r] = a;
-            }
-            if (FINE_UPPER && ci == cj) {
-#pragma unroll
-                for (int r = 0; r < D; ++r) w[r] += lambda * v[r];
-            }
-            Xf<D>::applyT(ri, w, u);
-#pragma unroll
-            for (int r = 0; r < D; ++r) acc[r] += u[r];
+            for (int q = 0; q < D; ++q) a[q] = __ldg(A + q * D + cc);
         }
-        if (flag != 0) {        // column c of P_j^T A^T P_i
-            Xf<D>::apply(ri, ec, v);
+        Xf<D>::applyT(rr, a, b);          // row cc of (A P_r)
+        __syncwarp(gmask);
+        if (act) {
 #pragma unroll
-            for (int r = 0; r < D; ++r) {
-                double a = 0;
+            for (int q = 0; q < D; ++q) tr[grp][cc * D + q] = b[q];
+        }
+        __syncwarp(gmask);
 #pragma unroll
-                for (int q = 0; q < D; ++q) a += __ldg(A + q * D + r) * v[q];
-                w[r] = a;
-            }
-            Xf<D>::applyT(rj, w, u);
+        for (int r = 0; r < D; ++r) w[r] = tr[grp][r * D + cc];
+        Xf<D>::applyT(rl, w, u);          // column cc of P_l^T (A P_r)
 #pragma unroll
-            for (int r = 0; r < D; ++r) acc[r] += u[r];
+        for (int r = 0; r < D; ++r) acc[r] += u[r];
+        if (flag == 2) {
+            any2 = true;
+#pragma unroll
+            for (int r = 0; r < D; ++r) accS[r] += u[r];
         }
     }
+    if (any2) {                            // uniform over the group: T += S^T
+        __syncwarp(gmask);
+        if (act) {
+#pragma unroll
+            for (int r = 0; r < D; ++r) tr[grp][r * D + cc] = accS[r];
+        }
+        __syncwarp(gmask);
+#pragma unroll
+        for (int r = 0; r < D; ++r) acc[r] += tr[grp][cc * D + r];
+    }
+    if (!act) return;
     double *out = Ac + (size_t)gal_out[ub] * DD;
 #pragma unroll
     for (int r = 0; r < D; ++r) out[r * D + c] = acc[r];
@@ -261,6 +285,61 @@ __global__ void __launch_bounds__(128, 4) amg_galerkin_kernel(const double *__re
 #pragma unroll
         for (int r = 0; r < D; ++r) om[c * D + r] = acc[r];
     }
+}
+
+// M_I = sum_{i in I} P_i^T Mf_i P_i  (Mf == nullptr: identity): an 8-lane group per aggregate, lane c holds column c
+template <int D>
+__global__ void amg_mass_kernel(int n, const int32_t *__restrict__ mem_ptr, const int32_t *__restrict__ mem_idx,
+                                const double *__restrict__ rel, int pad, const double *__restrict__ Mf, double *__restrict__ M) {
+    const int I = blockIdx.x * (blockDim.x / 8) + threadIdx.x / 8;
+    const int c = threadIdx.x & 7;
+    if (I >= n || c >= D) return;
+    double acc[D], ec[D];
+#pragma unroll
+    for (int r = 0; r < D; ++r) { acc[r] = 0; ec[r] = (r == c) ? 1.0 : 0.0; }
+    for (int m = mem_ptr[I]; m < mem_ptr[I + 1]; ++m) {
+        const int i = mem_idx[m];
+        const Rel S = load_rel(rel, pad, i);
+        double v[D], w[D], u[D];
+        Xf<D>::apply(S, ec, v);
+        if (Mf) {
+            const double *B = Mf + (size_t)i * DD;
+#pragma unroll
+            for (int r = 0; r < D; ++r) {
+                double a = 0;
+#pragma unroll
+                for (int q = 0; q < D; ++q) a += __ldg(B + r * D + q) * v[q];
+                w[r] = a;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < D; ++r) w[r] = v[r];
+        }
+        Xf<D>::applyT(S, w, u);
+#pragma unroll
+        for (int r = 0; r < D; ++r) acc[r] += u[r];
+    }
+#pragma unroll
+    for (int r = 0; r < D; ++r) M[(size_t)I * DD + r * D + c] = acc[r];
+}
+
+// Kd_I = diagonal block of A (called while A still holds K)
+template <int D>
+__global__ void amg_save_diag_kernel(int n, const int32_t *__restrict__ dpos, const double *__restrict__ A, double *__restrict__ Kd) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * DD) return;
+    const int I = t / DD, e = t - I * DD;
+    Kd[t] = A[(size_t)dpos[I] * DD + e];
+}
+
+// diagonal block of A = Kd + lambda M
+template <int D>
+__global__ void amg_shift_diag_kernel(int n, const int32_t *__restrict__ dpos, const double *__restrict__ Kd,
+                                      const double *__restrict__ M, double lambda, double *__restrict__ A) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * DD) return;
+    const int I = t / DD, e = t - I * DD;
+    A[(size_t)dpos[I] * DD + e] = Kd[t] + lambda * M[t];
 }
 
 // lower blocks of a level from its upper blocks (partitioned solve: after the all-gather of A_1)
@@ -371,24 +450,53 @@ __global__ void __launch_bounds__(256) amg_dense_inverse_coop_kernel(const doubl
             rowbuf[t] = acc;
         }
         grid_barrier(gb, phase);
-        for (size_t t = gtid; t < (size_t)N * N; t += nth) {
-            const int i = (int)(t / N), j = (int)(t - (size_t)i * N);
-            const int ib = i / D, jb = j / D;
-            double v;
-            if (ib == kb) v = (jb == kb) ? Ps[(i - kb * D) * D + (j - kb * D)] : __ldcg(rowbuf + (size_t)(i - kb * D) * N + j);
-            else {
-                double acc = 0;
-                if (jb == kb) {
+        // one thread per d x d block: colbuf_i and rowbuf_j are read once per block (98 loads for 49 results); warps
+        // are dealt round-robin over the CTAs so that the n^2 blocks (fewer than threads) spread over all SMs
+        for (int t = (((int)threadIdx.x >> 5) * (int)gridDim.x + (int)blockIdx.x) * 32 + ((int)threadIdx.x & 31); t < n * n; t += nth) {
+            const int ib = t / n, jb = t - ib * n;
+            double *out = inv + (size_t)(ib * D) * N + jb * D;
+            if (ib == kb) {
 #pragma unroll
-                    for (int m = 0; m < D; ++m) acc -= __ldcg(colbuf + (size_t)i * D + m) * Ps[m * D + (j - kb * D)];
-                    v = acc;
-                } else {
+                for (int r = 0; r < D; ++r)
 #pragma unroll
-                    for (int m = 0; m < D; ++m) acc += __ldcg(colbuf + (size_t)i * D + m) * __ldcg(rowbuf + (size_t)m * N + j);
-                    v = __ldcg(inv + t) - acc;
-                }
+                    for (int c = 0; c < D; ++c)
+                        out[(size_t)r * N + c] = (jb == kb) ? Ps[r * D + c] : __ldcg(rowbuf + (size_t)r * N + jb * D + c);
+                continue;
             }
-            inv[t] = v;
+            double cb[DD];
+#pragma unroll
+            for (int e = 0; e < DD; ++e) cb[e] = __ldcg(colbuf + (size_t)ib * DD + e);
+            if (jb == kb) {
+#pragma unroll
+                for (int r = 0; r < D; ++r)
+#pragma unroll
+                    for (int c = 0; c < D; ++c) {
+                        double acc = 0;
+#pragma unroll
+                        for (int m = 0; m < D; ++m) acc -= cb[r * D + m] * Ps[m * D + c];
+                        out[(size_t)r * N + c] = acc;
+                    }
+                continue;
+            }
+            double acc[DD];
+#pragma unroll
+            for (int r = 0; r < D; ++r)
+#pragma unroll
+                for (int c = 0; c < D; ++c) acc[r * D + c] = __ldcg(out + (size_t)r * N + c);
+#pragma unroll
+            for (int m = 0; m < D; ++m) {
+                double rb[D];
+#pragma unroll
+                for (int c = 0; c < D; ++c) rb[c] = __ldcg(rowbuf + (size_t)m * N + jb * D + c);
+#pragma unroll
+                for (int r = 0; r < D; ++r)
+#pragma unroll
+                    for (int c = 0; c < D; ++c) acc[r * D + c] -= cb[r * D + m] * rb[c];
+            }
+#pragma unroll
+            for (int r = 0; r < D; ++r)
+#pragma unroll
+                for (int c = 0; c < D; ++c) out[(size_t)r * N + c] = acc[r * D + c];
         }
         grid_barrier(gb, phase);
     }
@@ -792,6 +900,7 @@ struct CoopLevel {
 };
 struct CoopParams {
     int nlev, dense, N, kdepth;
+    unsigned kmask;
     const double *inv;
     double *dots;                 // [3][gridDim.x]
     CoopLevel lev[kMaxLevels];
@@ -1043,7 +1152,7 @@ amg_coop_kernel(const __grid_constant__ CoopParams P, double omega, const DevSca
     int step[kMaxLevels];
     KScal ks[kMaxLevels];
     int flip = 0;
-    auto is_k = [&](int l) { return l < P.kdepth && l < last; };
+    auto is_k = [&](int l) { return ((P.kmask >> l) & 1u) && l < last; };
     int l = 0;
     cur_r[0] = RSpec{ P.lev[0].r, nullptr, 0.0 };
     cur_out[0] = is_k(0) ? P.lev[0].z1 : P.lev[0].x2;
@@ -1143,6 +1252,7 @@ void free_level(LevelDev &L) {
     dev_free(L.gal_ptr); dev_free(L.gal_ent); dev_free(L.gal_i); dev_free(L.gal_j); dev_free(L.gal_order); dev_free(L.gal_out); dev_free(L.gal_mirror);
     dev_free(L.rel); dev_free(L.A); dev_free(L.Dinv); dev_free(L.r); dev_free(L.x); dev_free(L.x2); dev_free(L.t);
     dev_free(L.z1); dev_free(L.q1); dev_free(L.rp); dev_free(L.z2); dev_free(L.acol);
+    dev_free(L.Kd); dev_free(L.M);
 }
 
 // Partitioned solve: rewrite level 0 of the global hierarchy in this rank's local indices.
@@ -1269,6 +1379,7 @@ int amg_setup(s3o_problem *p) {
         rc = rc ? rc : up(p, &L.gal_i, H.gal_i);
         rc = rc ? rc : up(p, &L.gal_j, H.gal_j);
         rc = rc ? rc : up(p, &L.gal_out, H.gal_out);
+        setup_mark("    level: list uploads");
         {   // the lists may have been localised (partitioned solve): order by their final lengths
             std::vector<int32_t> order(H.nub);
             for (int u = 0; u < H.nub; ++u) order[u] = u;
@@ -1278,9 +1389,12 @@ int amg_setup(s3o_problem *p) {
             rc = rc ? rc : up(p, &L.gal_order, order);
         }
         rc = rc ? rc : up(p, &L.gal_mirror, H.gal_mirror);
+        setup_mark("    level: order sort");
         rc = rc ? rc : dev_alloc(&L.rel, (size_t)NREL * L.pad_fine);
         rc = rc ? rc : dev_alloc(&L.A, (size_t)L.nblk * DD);
         rc = rc ? rc : dev_alloc(&L.Dinv, (size_t)L.n * DD);
+        rc = rc ? rc : dev_alloc(&L.Kd, (size_t)L.n * DD);
+        rc = rc ? rc : dev_alloc(&L.M, (size_t)L.n * DD);
         rc = rc ? rc : dev_alloc(&L.r, (size_t)L.n * D + (l == 0 ? st->r_max + 2 : 0));
         rc = rc ? rc : dev_alloc(&L.x, (size_t)L.n * D);
         rc = rc ? rc : dev_alloc(&L.x2, (size_t)L.n * D);
@@ -1289,6 +1403,7 @@ int amg_setup(s3o_problem *p) {
         rc = rc ? rc : dev_alloc(&L.q1, (size_t)L.n * D);
         rc = rc ? rc : dev_alloc(&L.rp, (size_t)L.n * D);
         rc = rc ? rc : dev_alloc(&L.z2, (size_t)L.n * D);
+        setup_mark("    level: allocations");
         if (l + 1 < nl) {       // aggregate of every block's column vertex in the transfer to the next level
             const AmgHostLevel &N = st->host[l + 1];
             std::vector<int32_t> acol(H.colidx.size());
@@ -1308,6 +1423,8 @@ int amg_setup(s3o_problem *p) {
         rc = up(p, &st->d_unpad_src, src);
         rc = rc ? rc : up(p, &st->d_scal_pos, spos);
         rc = rc ? rc : dev_alloc(&st->d_rpad, (size_t)world * st->r_seg);
+        st->m_off.resize(world); st->m_cnt.resize(world);
+        for (int q = 0; q < world; ++q) { st->m_off[q] = st->r_off[q] / D * DD; st->m_cnt[q] = st->r_cnt[q] / D * DD; }
     }
     const int nc = st->host.back().n;
     st->dense = nc <= kCoarsestMaxBig;
@@ -1334,7 +1451,21 @@ int amg_setup(s3o_problem *p) {
         // can be worse than either); small graphs keep the V-cycle.  S3O_KCYCLE=<levels> overrides (0: V-cycle everywhere).
         const int n_fine_global = p->dist ? p->plan.nf_global : st->host[0].n_fine;     // host[0].n_fine is local when partitioned
         st->kdepth = (nl >= 2 && n_fine_global >= kBigGraph) ? nl - 1 : 0;
-        if (const char *v = getenv("S3O_KCYCLE")) st->kdepth = std::max(0, std::min(atoi(v), nl - 1));
+        st->kmask = (1u << st->kdepth) - 1u;
+        // ... except the first coarse level when there are K levels below it: two inner steps there double the work of
+        // the largest coarse level and of everything under it for ~1.35x fewer PCG iterations (1M-pose sphere, complete
+        // solve: 175 iterations / 0.455 s with K everywhere, 239 / 0.424 s with V on level 1; 100k: 0.183 -> 0.155 s)
+        if (st->kdepth >= 2) st->kmask &= ~1u;
+        if (const char *v = getenv("S3O_KCYCLE")) {     // experiment switch: K on the first <levels> levels exactly
+            st->kdepth = std::max(0, std::min(atoi(v), nl - 1));
+            st->kmask = (1u << st->kdepth) - 1u;
+        }
+        if (const char *v = getenv("S3O_KMASK")) {      // experiment switch: any subset of levels
+            st->kmask = (unsigned)strtoul(v, nullptr, 0) & ((1u << (nl - 1)) - 1u);
+            st->kdepth = 0;
+            for (int l = 0; l < nl - 1; ++l) if ((st->kmask >> l) & 1u) st->kdepth = l + 1;
+            if (st->kdepth == 0 && n_fine_global >= kBigGraph) { st->kdepth = 1; }      // keep the K-cycle code path (all V)
+        }
         int coop_rows = kCoopRows;
         if (const char *v = getenv("S3O_COOP_ROWS")) coop_rows = atoi(v);       // experiment switch
         st->coop_first = 0;
@@ -1386,30 +1517,46 @@ int update_values_t(s3o_problem *p, double lambda) {
     AmgState *st = p->amg;
     if (!st || st->lev.empty()) return S3O_OK;
     int rc;
-    if (!st->frames_valid && (rc = update_frames_t<D, KIND>(p))) return rc;
     int launches = 0;
+    // K = P^T H P has to be rebuilt for a new linearisation point, not for a new lambda at the same one (LM retry)
+    const bool rebuild = !st->k_valid || st->lin_changed;
+    st->lin_changed = false;
+    if (rebuild) {
+        ++st->rebuilds;
+        if ((rc = update_frames_t<D, KIND>(p))) return rc;
+        for (size_t l = 0; l < st->lev.size(); ++l) {
+            LevelDev &L = st->lev[l];
+            const int grid = (L.nub + 15) / 16;
+            if (l == 0) {
+                amg_galerkin_kernel<D, true><<<grid, 128, 0, p->stream>>>(p->d_H, L.gal_i, L.gal_j, L.rel, L.pad_fine,
+                                                                        L.nub, L.gal_ptr, L.gal_ent, L.gal_out, L.gal_mirror, L.A,
+                                                                        st->dist ? 0 : 1, L.gal_order);
+                amg_mass_kernel<D><<<(L.n + 15) / 16, 128, 0, p->stream>>>(L.n, L.mem_ptr, L.mem_idx, L.rel, L.pad_fine, nullptr, L.M);
+                if (st->dist) {     // every rank computed the upper blocks of its own coarse rows and the mass blocks of its aggregates
+                    if (comm_allgatherv(p->comm, L.A, st->a_off.data(), st->a_cnt.data(), p->stream) ||
+                        comm_allgatherv(p->comm, L.M, st->m_off.data(), st->m_cnt.data(), p->stream)) {
+                        set_error("%s", comm_last_error());
+                        return S3O_ERR_NCCL;
+                    }
+                    amg_mirror_kernel<D><<<(L.nub * DD + 255) / 256, 256, 0, p->stream>>>(L.nub, L.gal_out, L.gal_mirror, L.A);
+                    ++launches;
+                }
+            } else {
+                const LevelDev &F = st->lev[l - 1];      // F.A still holds K of the level above: the shifts come last
+                amg_galerkin_kernel<D, false><<<grid, 128, 0, p->stream>>>(F.A, L.gal_i, L.gal_j, L.rel, L.pad_fine, L.nub,
+                                                                         L.gal_ptr, L.gal_ent, L.gal_out, L.gal_mirror, L.A, 1, L.gal_order);
+                amg_mass_kernel<D><<<(L.n + 15) / 16, 128, 0, p->stream>>>(L.n, L.mem_ptr, L.mem_idx, L.rel, L.pad_fine, F.M, L.M);
+            }
+            amg_save_diag_kernel<D><<<(L.n * DD + 255) / 256, 256, 0, p->stream>>>(L.n, L.dpos, L.A, L.Kd);
+            launches += 3;
+        }
+        st->k_valid = true;
+    } else {
+        ++st->reuses;
+    }
     for (size_t l = 0; l < st->lev.size(); ++l) {
         LevelDev &L = st->lev[l];
-        const int grid = (L.nub + 15) / 16;
-        if (l == 0)
-        {
-            amg_galerkin_kernel<D, true><<<grid, 128, 0, p->stream>>>(p->d_H, L.gal_i, L.gal_j, L.rel, L.pad_fine, lambda,
-                                                                    L.nub, L.gal_ptr, L.gal_ent, L.gal_out, L.gal_mirror, L.A,
-                                                                    st->dist ? 0 : 1, L.gal_order);
-            if (st->dist) {     // every rank computed the upper blocks of its own coarse rows
-                if (comm_allgatherv(p->comm, L.A, st->a_off.data(), st->a_cnt.data(), p->stream)) {
-                    set_error("%s", comm_last_error());
-                    return S3O_ERR_NCCL;
-                }
-                amg_mirror_kernel<D><<<(L.nub * DD + 255) / 256, 256, 0, p->stream>>>(L.nub, L.gal_out, L.gal_mirror, L.A);
-                ++launches;
-            }
-        }
-        else {
-            const LevelDev &F = st->lev[l - 1];
-            amg_galerkin_kernel<D, false><<<grid, 128, 0, p->stream>>>(F.A, L.gal_i, L.gal_j, L.rel, L.pad_fine, 0.0, L.nub,
-                                                                     L.gal_ptr, L.gal_ent, L.gal_out, L.gal_mirror, L.A, 1, L.gal_order);
-        }
+        amg_shift_diag_kernel<D><<<(L.n * DD + 255) / 256, 256, 0, p->stream>>>(L.n, L.dpos, L.Kd, L.M, lambda, L.A);
         launch_precond(D, L.A, L.dpos, L.n, 0.0, L.Dinv, p->d_sc, p->stream);
         launches += 2;
     }
@@ -1500,6 +1647,7 @@ int apply_t(s3o_problem *p, int init) {
                 P.N = st->lev.back().n * D;
                 P.inv = st->d_dense;
                 P.kdepth = nk > l ? nk - l : 0;
+                P.kmask = st->kmask >> l;
                 P.dots = st->d_cdots;
                 for (int k = l; k < nl; ++k) {
                     LevelDev &S = st->lev[k];
@@ -1520,7 +1668,7 @@ int apply_t(s3o_problem *p, int init) {
                 trace_mark(p, "cooperative kernel");
                 return;
             }
-            if (l < nk) {
+            if ((st->kmask >> l) & 1u) {
                 KScal *ks = st->d_ks + l;
                 const int n = L.n * D;
                 cycle(l, L.r, L.z1);
@@ -1614,6 +1762,11 @@ int amg_apply(s3o_problem *p, int init) {
 }
 #undef S3O_AMG_DISPATCH
 
-void amg_invalidate_frames(s3o_problem *p) { if (p->amg) p->amg->frames_valid = false; }
+void amg_counts(const s3o_problem *p, int64_t *rebuilds, int64_t *reuses) {
+    if (!rebuilds || !reuses) { if (p->amg) p->amg->rebuilds = p->amg->reuses = 0; return; }
+    *rebuilds = p->amg ? p->amg->rebuilds : 0;
+    *reuses = p->amg ? p->amg->reuses : 0;
+}
+void amg_invalidate_frames(s3o_problem *p) { if (p->amg) { p->amg->frames_valid = false; p->amg->lin_changed = true; } }
 
 }  // namespace s3o

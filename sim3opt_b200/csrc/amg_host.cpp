@@ -150,20 +150,43 @@ void amg_build_hierarchy(const HostStructure &S, int coarsest_max, int max_level
             std::vector<int32_t> fill(L.mem_ptr.begin(), L.mem_ptr.end() - 1);
             for (int i = 0; i < F.n; ++i) L.mem_idx[fill[L.agg[i]]++] = i;
         }
-        // coarse pattern
+        // coarse pattern: keys (I << bits) | J of every fine block (both orientations for an upper-only level), sorted and
+        // de-duplicated.  Fine blocks of neighbouring rows fall into the same few coarse blocks, so each host thread first
+        // sorts and de-duplicates its own contiguous range (12 M keys shrink to ~1 M), then one sort merges the ranges;
+        // the result is the sorted set of distinct keys whatever the thread count.
         std::vector<uint64_t> keys;
-        keys.reserve((size_t)F.nblk * (F.upper ? 2 : 1));
-        for (int k = 0; k < F.nblk; ++k) {
-            const uint32_t I = (uint32_t)L.agg[F.brow[k]], J = (uint32_t)L.agg[F.bcol[k]];
-            keys.push_back(((uint64_t)I << 32) | J);
-            if (F.upper && I != J) keys.push_back(((uint64_t)J << 32) | I);
-        }
-        {   // keys are (I << 32) | J with I, J < L.n: compact to 2 * bits for the sort, then back
+        {
             int bits = 1;
             while ((1ll << bits) <= L.n) ++bits;
-            for (uint64_t &k : keys) k = ((k >> 32) << bits) | (k & 0xffffffffull);
-            radix_sort_u64(keys, 2 * bits);
-            keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+            const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+            const unsigned parts = F.nblk < 100000 ? 1u : hw;
+            std::vector<std::vector<uint64_t>> part(parts);
+            auto work = [&](unsigned w) {
+                const int lo = (int)((long long)F.nblk * w / parts), hi = (int)((long long)F.nblk * (w + 1) / parts);
+                std::vector<uint64_t> &K = part[w];
+                K.reserve((size_t)(hi - lo) * (F.upper ? 2 : 1));
+                for (int k = lo; k < hi; ++k) {
+                    const uint64_t I = (uint32_t)L.agg[F.brow[k]], J = (uint32_t)L.agg[F.bcol[k]];
+                    K.push_back((I << bits) | J);
+                    if (F.upper && I != J) K.push_back((J << bits) | I);
+                }
+                radix_sort_u64(K, 2 * bits);
+                K.erase(std::unique(K.begin(), K.end()), K.end());
+            };
+            if (parts == 1) work(0);
+            else {
+                std::vector<std::thread> th;
+                for (unsigned w = 0; w < parts; ++w) th.emplace_back(work, w);
+                for (auto &t : th) t.join();
+            }
+            size_t total = 0;
+            for (auto &K : part) total += K.size();
+            keys.reserve(total);
+            for (auto &K : part) keys.insert(keys.end(), K.begin(), K.end());
+            if (parts > 1) {
+                radix_sort_u64(keys, 2 * bits);
+                keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+            }
             for (uint64_t &k : keys) k = ((k >> bits) << 32) | (k & ((1ull << bits) - 1));
         }
         setup_mark("    coarse keys sort");

@@ -824,8 +824,16 @@ int s3o_set_edges(s3o_problem *p, int n, const int32_t *v0, const int32_t *v1, c
         size_t icount = (size_t)n * dd;
         if (p->info_diag) {         // 56 B per edge over PCIe instead of 392 B
             info_diag_host.resize((size_t)n * d);
-            for (size_t k = 0; k < (size_t)n; ++k)
-                for (int r = 0; r < d; ++r) info_diag_host[k * d + r] = info[k * dd + r * d + r];
+            const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+            std::vector<std::thread> th;
+            double *dst = info_diag_host.data();
+            for (unsigned w = 0; w < hw; ++w)
+                th.emplace_back([=]() {
+                    const size_t lo = (size_t)n * w / hw, hi = (size_t)n * (w + 1) / hw;
+                    for (size_t k = lo; k < hi; ++k)
+                        for (int r = 0; r < d; ++r) dst[k * d + r] = info[k * dd + r * d + r];
+                });
+            for (auto &t : th) t.join();
             src = info_diag_host.data();
             icount = (size_t)n * d;
             setup_mark("set_edges: diag extract");
@@ -966,7 +974,9 @@ int s3o_build_structure(s3o_problem *p, int *n_free, int *n_blocks) {
         rc = rc ? rc : upload(p, &p->d_inc_ptr, S.inc_ptr);
         rc = rc ? rc : upload(p, &p->d_inc_ent, S.inc_ent);
         rc = rc ? rc : upload(p, &p->d_e_blk, S.e_blk);
+        setup_mark("  structure: edge-array uploads");
         rc = rc ? rc : upload_structure_arrays(p, rows_own);
+        setup_mark("  structure: BSR/tile uploads");
         if (p->dist) {
             const PartitionPlan &P = p->plan;
             std::vector<uint8_t> prim(S.ne_act);
@@ -984,6 +994,7 @@ int s3o_build_structure(s3o_problem *p, int *n_free, int *n_blocks) {
         if (p->has_info) rc = rc ? rc : dev_alloc(&p->d_info, (size_t)p->ne_pad * info_planes);
         rc = rc ? rc : alloc_linear_system(p);
         rc = rc ? rc : dev_alloc(&p->d_scratch, (size_t)p->ne_pad * scratch_stride(p->d));
+        setup_mark("  structure: allocations");
         const size_t nfd = (size_t)std::max(S.nf, p->dist ? p->plan.seg : 0) * p->d;
         if (rc) { dev_free(d_perm); free_structure(p); return rc; }
         if (S.ne_act > 0) {
@@ -1574,6 +1585,7 @@ int s3o_get_stats(s3o_problem *p, s3o_stats *out) {
     p->stats.n_free = p->built ? p->S.nf : 0;
     p->stats.n_blocks = p->built ? p->S.nb : 0;
     p->stats.multilevel_levels = amg_levels(p);
+    amg_counts(p, &p->stats.multilevel_rebuilds, &p->stats.multilevel_reuses);
     p->stats.p2p_halo = p->p2p ? 1 : 0;
     *out = p->stats;
     return S3O_OK;
@@ -1582,6 +1594,7 @@ int s3o_get_stats(s3o_problem *p, s3o_stats *out) {
 int s3o_reset_stats(s3o_problem *p) {
     if (!p) return S3O_ERR_INVALID;
     p->stats = s3o_stats{};
+    amg_counts(p, nullptr, nullptr);        // zeroes them
     return S3O_OK;
 }
 

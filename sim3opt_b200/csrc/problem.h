@@ -189,6 +189,7 @@ bool wants_multilevel(const s3o_problem *p);
 int amg_setup(s3o_problem *p);                        // hierarchy for p->S (host build + upload)
 void amg_destroy(s3o_problem *p);
 int amg_levels(const s3o_problem *p);                 // coarse levels (0: graph too small, block-Jacobi only)
+void amg_counts(const s3o_problem *p, int64_t *rebuilds, int64_t *reuses);
 void amg_invalidate_frames(s3o_problem *p);           // the linearisation point moved
 int amg_update_frames(s3o_problem *p);
 int amg_update_values(s3o_problem *p, double lambda); // Galerkin operators for (H + lambda I)

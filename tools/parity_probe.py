@@ -72,7 +72,9 @@ def main():
                 line += f" | vs oracle100: chi2 rel {(chi2 - gold[0]) / gold[0]:+.2e} trans {dtm:.2e} m rot {dr:.2e} rad scale {ds:.2e}"
             print(line, flush=True)
             prev = chi2
-        print("unconverged PCG solves:", p.stats()["pcg_unconverged"], flush=True)
+        st = p.stats()
+        print("unconverged PCG solves:", st["pcg_unconverged"], "| coarse operators rebuilt", st["multilevel_rebuilds"],
+              "kept", st["multilevel_reuses"], flush=True)
 
 
 if __name__ == "__main__":
