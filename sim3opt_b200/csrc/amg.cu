@@ -85,7 +85,7 @@ struct AmgState {
     unsigned kmask = 0;         // bit l: level l is a K-cycle level (default: the first kdepth levels; S3O_KMASK overrides)
     KScal *d_ks = nullptr;          // [kMaxLevels]
     bool dense_coop = false;        // coarsest level inverted by the cooperative kernel (too large for shared memory)
-    double *d_colbuf = nullptr, *d_rowbuf = nullptr;
+    double *d_rowbuf = nullptr;     // [2][d*N + d*d]: scaled pivot row + pivot inverse of the dense inversion, double-buffered
     double *d_cdots = nullptr;      // [3][coop_grid] partial sums of the cooperative kernel's dot products
 };
 
@@ -389,117 +389,114 @@ __global__ void __launch_bounds__(256) amg_dense_inverse_kernel(const double *__
     for (int t = threadIdx.x; t < N * N; t += blockDim.x) inv[t] = a[t];
 }
 
-// Same inverse for a coarsest level that does not fit shared memory: block Gauss-Jordan on the d x d block grid
-// in global memory, one cooperative grid, two barriers per pivot block.  No pivoting (the matrix is SPD).
-//   pivot phase   P = A_kk^-1;  colbuf_i = A_ik;  rowbuf_j = P A_kj
-//   update phase  A_kj <- rowbuf_j (A_kk <- P);  A_ik <- -colbuf_i P;  A_ij <- A_ij - colbuf_i rowbuf_j
+// dynamic shared memory of amg_dense_inverse_coop_kernel: block row, pivot row, P, C, inversion work space
+inline size_t dense_coop_smem(int n, int d) { return ((size_t)2 * d * n * d + 2 * d * d + 2 * d * d) * sizeof(double); }
+
+// Same inverse for a coarsest level that does not fit one CTA's shared memory: block Gauss-Jordan on the d x d block
+// grid, CTA i keeps block row i (d x N) in shared memory for the whole elimination.  Step k needs the pivot block's
+// inverse P = A_kk^-1 and the scaled pivot row  rowbuf = P A_k,:  from CTA k; everything else is local:
+//   row k:   A_kj <- rowbuf_j, A_kk <- P          other rows:  C = A_ik;  A_ik <- -C P;  A_ij <- A_ij - C rowbuf_j
+// CTA k+1 prepares P and rowbuf of the next step right after its own update, so there is ONE grid barrier per pivot
+// block.  No pivoting (the matrix is SPD).  pub: [2][d*N + d*d] double-buffered rowbuf + P in global memory.
 template <int D>
 __global__ void __launch_bounds__(256) amg_dense_inverse_coop_kernel(const double *__restrict__ A, const int32_t *__restrict__ rowptr,
                                                                      const int32_t *__restrict__ colidx, int n, double *inv,
-                                                                     double *colbuf, double *rowbuf, DevScalars *sc, const GridBarrier gb) {
+                                                                     double *pub, DevScalars *sc, const GridBarrier gb) {
+    extern __shared__ double smem[];
     unsigned phase = 0;
-    const int N = n * D, nth = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    for (size_t t = gtid; t < (size_t)N * N; t += nth) inv[t] = 0;
-    grid_barrier(gb, phase);
-    for (int k = gtid; k < rowptr[n] * DD; k += nth) {
+    const int N = n * D, ib = blockIdx.x, NT = blockDim.x;
+    double *row = smem;                 // [D][N]   this CTA's block row
+    double *rb = row + (size_t)D * N;   // [D][N]   scaled pivot row of the current step
+    double *Ps = rb + (size_t)D * N;    // [D][D]   inverse of the pivot block
+    double *Cb = Ps + DD;               // [D][D]   this row's pivot-column block before the update
+    double *Ms = Cb + DD;               // [D][2D]  work space of the d x d inversion
+    const size_t pub_stride = (size_t)D * N + DD;
+    for (int t = threadIdx.x; t < D * N; t += NT) row[t] = 0;
+    __syncthreads();
+    for (int k = rowptr[ib] * DD + threadIdx.x; k < rowptr[ib + 1] * DD; k += NT) {
         const int blk = k / DD, e = k - blk * DD;
-        // block row of blk: binary search in rowptr
-        int lo = 0, hi = n - 1;
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (rowptr[mid] <= blk) lo = mid; else hi = mid - 1; }
-        inv[(size_t)(lo * D + e / D) * N + colidx[blk] * D + e % D] = A[k];
+        row[(e / D) * N + colidx[blk] * D + e % D] = A[k];
     }
-    grid_barrier(gb, phase);
-    __shared__ double Ps[DD];
-    for (int kb = 0; kb < n; ++kb) {
-        // every CTA inverts the pivot block for itself (Gauss-Jordan on d x d by one thread)
-        if (threadIdx.x == 0) {
-            double M[DD], I[DD];
-#pragma unroll
-            for (int r = 0; r < D; ++r)
-#pragma unroll
-                for (int c = 0; c < D; ++c) { M[r * D + c] = __ldcg(inv + (size_t)(kb * D + r) * N + kb * D + c); I[r * D + c] = r == c ? 1.0 : 0.0; }
-#pragma unroll
-            for (int c = 0; c < D; ++c) {
-                double piv = M[c * D + c];
-                if (!(piv > 0)) { piv = 1; sc->precond_fail = 1; }
-                const double ip = 1.0 / piv;
-#pragma unroll
-                for (int j = 0; j < D; ++j) { M[c * D + j] *= ip; I[c * D + j] *= ip; }
-#pragma unroll
-                for (int r = 0; r < D; ++r) {
-                    if (r == c) continue;
-                    const double f = M[r * D + c];
-#pragma unroll
-                    for (int j = 0; j < D; ++j) { M[r * D + j] -= f * M[c * D + j]; I[r * D + j] -= f * I[c * D + j]; }
-                }
+    __syncthreads();
+    // P = (row[:, kb block])^-1 and rowbuf = P row -> pub[slot]; called by all threads of the CTA that owns block row kb
+    auto publish = [&](int kb, int slot) {
+        if (threadIdx.x < 32) {         // Gauss-Jordan on [M | I] (d x 2d) by one warp
+            const int lane = threadIdx.x;
+            for (int e = lane; e < D * 2 * D; e += 32) {
+                const int r = e / (2 * D), c = e - r * 2 * D;
+                Ms[e] = c < D ? row[r * N + kb * D + c] : (c - D == r ? 1.0 : 0.0);
             }
+            __syncwarp();
+            for (int c = 0; c < D; ++c) {
+                double piv = Ms[c * 2 * D + c];
+                if (!(piv > 0)) { piv = 1; if (lane == 0) sc->precond_fail = 1; }
+                const double ip = 1.0 / piv;
+                double f[(D * 2 * D + 31) / 32];
 #pragma unroll
-            for (int e = 0; e < DD; ++e) Ps[e] = I[e];
+                for (int q = 0; q < (D * 2 * D + 31) / 32; ++q) {
+                    const int e = lane + 32 * q, r = e / (2 * D);
+                    f[q] = (e < D * 2 * D && r != c) ? Ms[r * 2 * D + c] : 0.0;
+                }
+                __syncwarp();
+                if (lane < 2 * D) Ms[c * 2 * D + lane] *= ip;
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < (D * 2 * D + 31) / 32; ++q) {
+                    const int e = lane + 32 * q, r = e / (2 * D), cc = e - r * 2 * D;
+                    if (e < D * 2 * D && r != c) Ms[e] -= f[q] * Ms[c * 2 * D + cc];
+                }
+                __syncwarp();
+            }
+            for (int e = lane; e < DD; e += 32) Ps[e] = Ms[(e / D) * 2 * D + D + e % D];
         }
         __syncthreads();
-        // colbuf[i*D+r][c] = A[i*D+r][kb*D+c];  rowbuf[r][j] = sum_m P[r][m] A[kb*D+m][j]
-        for (int t = gtid; t < N * D; t += nth) {
-            const int row = t / D, c = t - row * D;
-            colbuf[t] = __ldcg(inv + (size_t)row * N + kb * D + c);
-        }
-        for (int t = gtid; t < D * N; t += nth) {
+        double *out = pub + (size_t)slot * pub_stride;
+        for (int t = threadIdx.x; t < D * N; t += NT) {
             const int r = t / N, j = t - r * N;
             double acc = 0;
 #pragma unroll
-            for (int m = 0; m < D; ++m) acc += Ps[r * D + m] * __ldcg(inv + (size_t)(kb * D + m) * N + j);
-            rowbuf[t] = acc;
+            for (int m = 0; m < D; ++m) acc += Ps[r * D + m] * row[m * N + j];
+            out[t] = acc;
         }
-        grid_barrier(gb, phase);
-        // one thread per d x d block: colbuf_i and rowbuf_j are read once per block (98 loads for 49 results); warps
-        // are dealt round-robin over the CTAs so that the n^2 blocks (fewer than threads) spread over all SMs
-        for (int t = (((int)threadIdx.x >> 5) * (int)gridDim.x + (int)blockIdx.x) * 32 + ((int)threadIdx.x & 31); t < n * n; t += nth) {
-            const int ib = t / n, jb = t - ib * n;
-            double *out = inv + (size_t)(ib * D) * N + jb * D;
-            if (ib == kb) {
-#pragma unroll
-                for (int r = 0; r < D; ++r)
-#pragma unroll
-                    for (int c = 0; c < D; ++c)
-                        out[(size_t)r * N + c] = (jb == kb) ? Ps[r * D + c] : __ldcg(rowbuf + (size_t)r * N + jb * D + c);
-                continue;
-            }
-            double cb[DD];
-#pragma unroll
-            for (int e = 0; e < DD; ++e) cb[e] = __ldcg(colbuf + (size_t)ib * DD + e);
-            if (jb == kb) {
-#pragma unroll
-                for (int r = 0; r < D; ++r)
-#pragma unroll
-                    for (int c = 0; c < D; ++c) {
-                        double acc = 0;
-#pragma unroll
-                        for (int m = 0; m < D; ++m) acc -= cb[r * D + m] * Ps[m * D + c];
-                        out[(size_t)r * N + c] = acc;
-                    }
-                continue;
-            }
-            double acc[DD];
-#pragma unroll
-            for (int r = 0; r < D; ++r)
-#pragma unroll
-                for (int c = 0; c < D; ++c) acc[r * D + c] = __ldcg(out + (size_t)r * N + c);
-#pragma unroll
-            for (int m = 0; m < D; ++m) {
-                double rb[D];
-#pragma unroll
-                for (int c = 0; c < D; ++c) rb[c] = __ldcg(rowbuf + (size_t)m * N + jb * D + c);
-#pragma unroll
-                for (int r = 0; r < D; ++r)
-#pragma unroll
-                    for (int c = 0; c < D; ++c) acc[r * D + c] -= cb[r * D + m] * rb[c];
-            }
-#pragma unroll
-            for (int r = 0; r < D; ++r)
-#pragma unroll
-                for (int c = 0; c < D; ++c) out[(size_t)r * N + c] = acc[r * D + c];
+        for (int e = threadIdx.x; e < DD; e += NT) out[(size_t)D * N + e] = Ps[e];
+    };
+    if (ib == 0) publish(0, 0);
+    grid_barrier(gb, phase);
+    for (int kb = 0; kb < n; ++kb) {
+        const double *in = pub + (size_t)(kb & 1) * pub_stride;
+        for (int t = threadIdx.x; t < D * N; t += NT) rb[t] = __ldcg(in + t);
+        for (int e = threadIdx.x; e < DD; e += NT) {
+            Ps[e] = __ldcg(in + (size_t)D * N + e);
+            Cb[e] = row[(e / D) * N + kb * D + e % D];
         }
-        grid_barrier(gb, phase);
+        __syncthreads();
+        if (ib == kb) {
+            for (int t = threadIdx.x; t < D * N; t += NT) {
+                const int r = t / N, j = t - r * N, jb = j / D;
+                row[t] = (jb == kb) ? Ps[r * D + (j - kb * D)] : rb[t];
+            }
+        } else {
+            for (int t = threadIdx.x; t < D * N; t += NT) {
+                const int r = t / N, j = t - r * N, jb = j / D;
+                double acc = 0;
+                if (jb == kb) {
+#pragma unroll
+                    for (int m = 0; m < D; ++m) acc -= Cb[r * D + m] * Ps[m * D + (j - kb * D)];
+                    row[t] = acc;
+                } else {
+#pragma unroll
+                    for (int m = 0; m < D; ++m) acc += Cb[r * D + m] * rb[m * N + j];
+                    row[t] -= acc;
+                }
+            }
+        }
+        __syncthreads();
+        if (kb + 1 < n) {
+            if (ib == kb + 1) publish(kb + 1, (kb + 1) & 1);
+            grid_barrier(gb, phase);
+        }
     }
+    for (int t = threadIdx.x; t < D * N; t += NT) inv[(size_t)(ib * D) * N + t] = row[t];
 }
 
 // ---- coarse-level row kernels: an 8-lane group owns one block row, lane l one component ---------
@@ -1330,7 +1327,6 @@ void amg_destroy(s3o_problem *p) {
     dev_free(p->amg->d_unpad_src);
     dev_free(p->amg->d_scal_pos);
     dev_free(p->amg->d_ks);
-    dev_free(p->amg->d_colbuf);
     dev_free(p->amg->d_rowbuf);
     dev_free(p->amg->d_cdots);
     delete p->amg;
@@ -1432,8 +1428,15 @@ int amg_setup(s3o_problem *p) {
     if (!rc && st->dense) {
         rc = dev_alloc(&st->d_dense, (size_t)nc * D * nc * D);
         if (st->dense_coop) {
-            rc = rc ? rc : dev_alloc(&st->d_colbuf, (size_t)nc * D * D);
-            rc = rc ? rc : dev_alloc(&st->d_rowbuf, (size_t)nc * D * D);
+            rc = rc ? rc : dev_alloc(&st->d_rowbuf, (size_t)2 * (nc * D * D + D * D));
+            const int smem = (int)dense_coop_smem(nc, D);
+            cudaError_t ea = D == 7 ? cudaFuncSetAttribute(amg_dense_inverse_coop_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                           : D == 4 ? cudaFuncSetAttribute(amg_dense_inverse_coop_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                                    : cudaFuncSetAttribute(amg_dense_inverse_coop_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (!rc && ea != cudaSuccess) {
+                set_error("amg_setup: cannot reserve %d bytes of shared memory", smem);
+                rc = S3O_ERR_CUDA;
+            }
         } else {
             const int smem = (nc * D * nc * D + nc * D) * (int)sizeof(double);
             cudaError_t ea = D == 7 ? cudaFuncSetAttribute(amg_dense_inverse_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
@@ -1567,11 +1570,11 @@ int update_values_t(s3o_problem *p, double lambda) {
             const double *Ap = C.A;
             const int32_t *rp = C.rowptr, *ci = C.colidx;
             int n = C.n;
-            double *inv = st->d_dense, *cb = st->d_colbuf, *rb = st->d_rowbuf;
+            double *inv = st->d_dense, *pub = st->d_rowbuf;
             DevScalars *scp = p->d_sc;
             GridBarrier gb{};
-            void *args[] = { &Ap, &rp, &ci, &n, &inv, &cb, &rb, &scp, &gb };
-            int rcl = launch_persistent(p, (const void *)amg_dense_inverse_coop_kernel<D>, st->coop_grid, 256, args, 9);
+            void *args[] = { &Ap, &rp, &ci, &n, &inv, &pub, &scp, &gb };
+            int rcl = launch_persistent(p, (const void *)amg_dense_inverse_coop_kernel<D>, n, 256, args, 8, dense_coop_smem(n, D));
             if (rcl) return rcl;
         } else {
             amg_dense_inverse_kernel<D><<<1, 256, (size_t)(N * N + N) * sizeof(double), p->stream>>>(C.A, C.rowptr, C.colidx, C.n,

@@ -163,17 +163,17 @@ void direct_invalidate(s3o_problem *p);               // H changed
 void direct_destroy(s3o_problem *p);
 // Launches a persistent kernel whose CTAs synchronise through grid_barrier (gridbar.cuh).  The kernel's LAST argument
 // is a GridBarrier; args[nargs - 1] must point to a GridBarrier that this call fills.
-inline int launch_persistent(s3o_problem *p, const void *func, int grid, int block, void **args, int nargs) {
+inline int launch_persistent(s3o_problem *p, const void *func, int grid, int block, void **args, int nargs, size_t smem = 0) {
     GridBarrier *gb = (GridBarrier *)args[nargs - 1];
     gb->counter = p->d_gridbar;
     gb->abort = (int *)(p->d_gridbar + 1);
     gb->cooperative = p->coop_launch ? 1 : 0;
     if (p->coop_launch) {
-        S3O_CUDA(cudaLaunchCooperativeKernel(func, dim3(grid), dim3(block), args, 0, p->stream));
+        S3O_CUDA(cudaLaunchCooperativeKernel(func, dim3(grid), dim3(block), args, smem, p->stream));
         return S3O_OK;
     }
     S3O_CUDA(cudaMemsetAsync(p->d_gridbar, 0, sizeof(unsigned), p->stream));
-    S3O_CUDA(cudaLaunchKernel(func, dim3(grid), dim3(block), args, 0, p->stream));
+    S3O_CUDA(cudaLaunchKernel(func, dim3(grid), dim3(block), args, smem, p->stream));
     return S3O_OK;
 }
 inline void trace_mark(s3o_problem *p, const char *what) {

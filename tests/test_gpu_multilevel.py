@@ -164,6 +164,39 @@ def test_kcycle_fewer_iterations_same_solution():
     assert counts["2"] * 3 <= counts["0"] * 2, counts
 
 
+def test_large_graph_kcycle_with_dense_coarsest_level():
+    """Graphs of >= 20 000 free vertices take the production path of the 1M-pose benchmark: K-cycle levels inside the
+    persistent kernel and a coarsest level of up to 128 vertices inverted by the row-resident block Gauss-Jordan.
+    A wrong coarse inverse or Galerkin operator shows as a stalled PCG; the solution is checked against H itself."""
+    import sim3opt_b200 as s3
+    from sim3opt_b200 import synth
+    g = dict(synth.sphere(n_laps=30, poses_per_lap=1000, seed=7))
+    warm = make_gpu(g, jac=1, math_mode=s3.MATH_CORRECTED)
+    warm.set_pcg(0.1, 20000)
+    warm.optimize(4)
+    g["est"] = warm.vertices()
+    del warm
+    gpu = make_gpu(g, jac=1, math_mode=s3.MATH_CORRECTED)
+    H, b = gpu.linearize()
+    gpu.set_pcg(1e-10, 5000)
+    out = []
+    for lam_rel in (1e-4, 1e-9):
+        lam = lam_rel * gpu.max_diag()
+        rc, x, it, rel = gpu.solve(lam)
+        assert rc == 0 and rel <= 1e-10, (lam_rel, rc, it, rel)
+        y = gpu.hessian_multiply(lam, x)
+        assert np.linalg.norm(y - b) <= 1e-9 * np.linalg.norm(b)
+        assert it <= 150, (lam_rel, it)
+        out.append((x, it))
+    st = gpu.stats()
+    assert st["multilevel_levels"] >= 2
+    # same lambda again: the coarse operators are kept (only the diagonal shift is redone) and the solve is bitwise equal
+    before = st["multilevel_reuses"]
+    rc, x2, it2, _ = gpu.solve(1e-9 * gpu.max_diag())
+    assert it2 == out[1][1] and np.array_equal(x2, out[1][0])
+    assert gpu.stats()["multilevel_reuses"] == before + 1
+
+
 def test_multilevel_rejected_for_ba():
     import sim3opt_b200 as s3
     from sim3opt_b200 import synth
