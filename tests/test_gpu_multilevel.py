@@ -186,7 +186,7 @@ def test_large_graph_kcycle_with_dense_coarsest_level():
         assert rc == 0 and rel <= 1e-10, (lam_rel, rc, it, rel)
         y = gpu.hessian_multiply(lam, x)
         assert np.linalg.norm(y - b) <= 1e-9 * np.linalg.norm(b)
-        assert it <= 150, (lam_rel, it)
+        assert it <= 600, (lam_rel, it)
         out.append((x, it))
     st = gpu.stats()
     assert st["multilevel_levels"] >= 2
