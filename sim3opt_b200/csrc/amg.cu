@@ -891,6 +891,7 @@ constexpr int kCoopThreads = 512, kCoopRows = 24000;
 
 struct CoopLevel {
     int n, pad_fine;
+    int G;                      // 8-lane groups that share one block row in the cooperative kernel (1, 2 or 4)
     const int32_t *rowptr, *colidx, *mem_ptr, *mem_idx, *agg, *acol;
     const double *A, *Dinv, *rel;
     double *r, *x, *x2, *t, *z1, *q1, *rp, *z2;
@@ -900,6 +901,7 @@ struct CoopParams {
     unsigned kmask;
     const double *inv;
     double *dots;                 // [3][gridDim.x]
+    long long *dbg;               // S3O_COOP_DBG: clock64() of CTA 0 after every barrier (diagnostic), else null
     CoopLevel lev[kMaxLevels];
 };
 
@@ -955,14 +957,30 @@ __device__ __forceinline__ void coop_rows(const CoopLevel &L, const double *rin,
     }
 }
 
+// ---- row phases of the cooperative kernel -------------------------------------------------------
+// These levels live in L2 and a phase is a chain of load latencies, so (1) a block row is shared by G 8-lane groups
+// (G = 4: a whole warp) when the level has fewer rows than the grid has groups -- group g takes the blocks
+// g*U.., (g+G)*U.. and the partial sums meet in a fixed butterfly -- and (2) every batch of U blocks issues ALL its loads
+// (indices, then vectors / inverses / block rows, spread over the lanes and completed by shuffles) before any arithmetic.
+template <int G> __device__ __forceinline__ unsigned row_mask() {
+    const int lane = threadIdx.x & 31;
+    return G == 4 ? 0xffffffffu : (G == 2 ? 0xffffu << (lane & 16) : 0xffu << (lane & 24));
+}
+template <int G> __device__ __forceinline__ double row_sum(unsigned rmask, double v) {
+    if (G >= 2) v += __shfl_xor_sync(rmask, v, 8);
+    if (G == 4) v += __shfl_xor_sync(rmask, v, 16);
+    return v;
+}
+
 // Way down, fused: the first smoothing sweep starts from zero, x = omega Dinv r, so the residual after it is
 // t_i = r_i - sum_j A_ij (omega Dinv_j r_j) with the neighbours' sweep formed on the fly: one phase instead of two.
-template <int D>
+template <int D, int G>
 __device__ __forceinline__ void coop_down(const CoopLevel &L, const RSpec R, double omega, int gtid, int nth) {
-    const int groups = nth / 8, g = gtid / 8, l = gtid & 7;
-    const unsigned gmask = 0xffu << (threadIdx.x & 24);
+    constexpr int U = 3, LPR = 8 * G;
+    const int lane = threadIdx.x & 31, sub = lane & (LPR - 1), g = sub >> 3, l = sub & 7;
+    const unsigned gmask = 0xffu << (lane & 24), rmask = row_mask<G>();
     const int lc = l < D ? l : 0;             // lane 7 shadows lane 0 (keeps the group's shuffles convergent)
-    for (int i = g; i < L.n; i += groups) {
+    for (int i = gtid / LPR; i < L.n; i += nth / LPR) {
         const double ri = rget(R, (size_t)i * D + lc);
         double xi = 0;
 #pragma unroll
@@ -970,29 +988,35 @@ __device__ __forceinline__ void coop_down(const CoopLevel &L, const RSpec R, dou
         xi *= omega;
         double acc = 0;
         const int kb = L.rowptr[i], ke = L.rowptr[i + 1];
-        // blocks in chunks of U: all index loads of a chunk are issued before the dependent vector loads, all of
-        // those before the arithmetic (these levels live in L2: the phase is a chain of load latencies)
-        constexpr int U = 8;
-        for (int k0 = kb; k0 < ke; k0 += U) {
+        for (int k0 = kb + g * U; k0 < ke; k0 += G * U) {
             int j[U];
-            double rj[U];
+            double rj[U], dv[U][D], av[U][D];
 #pragma unroll
-            for (int u = 0; u < U; ++u) j[u] = k0 + u < ke ? L.colidx[k0 + u] : i;
+            for (int u = 0; u < U; ++u) j[u] = L.colidx[min(k0 + u, ke - 1)];
 #pragma unroll
             for (int u = 0; u < U; ++u) rj[u] = rget(R, (size_t)j[u] * D + lc);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double *Ak = L.A + (size_t)min(k0 + u, ke - 1) * DD + lc * D;
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    dv[u][c] = L.Dinv[(size_t)j[u] * sym_size<D>() + sym_off<D>(lc, c)];
+                    av[u][c] = Ak[c];
+                }
+            }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (k0 + u >= ke) break;                 // uniform inside the group
                 double xj = 0;
 #pragma unroll
-                for (int c = 0; c < D; ++c) xj += L.Dinv[(size_t)j[u] * sym_size<D>() + sym_off<D>(lc, c)] * gshfl(gmask, rj[u], c);
+                for (int c = 0; c < D; ++c) xj += dv[u][c] * gshfl(gmask, rj[u], c);
                 xj *= omega;
-                const double *Ak = L.A + (size_t)(k0 + u) * DD + lc * D;
 #pragma unroll
-                for (int c = 0; c < D; ++c) acc += Ak[c] * gshfl(gmask, xj, c);
+                for (int c = 0; c < D; ++c) acc += av[u][c] * gshfl(gmask, xj, c);
             }
         }
-        if (l < D) {
+        acc = row_sum<G>(rmask, acc);
+        if (g == 0 && l < D) {
             L.x[(size_t)i * D + l] = xi;
             L.t[(size_t)i * D + l] = ri - acc;
         }
@@ -1033,92 +1057,126 @@ __device__ __forceinline__ void coop_restrict(const CoopLevel &C, const double *
 }
 
 // Way up, fused: x' = x + P xc (the child's correction, combined on the fly) and the second smoothing sweep
-// out = x' + omega Dinv (r - A x'), with the neighbours' prolonged values formed where they are read.
-template <int D>
+// out = x' + omega Dinv (r - A x'), with the neighbours' prolonged values formed where they are read.  Per block a lane
+// loads two of the 13 frame entries, one entry of the correction and of x, and its row of the block.
+template <int D, int G>
 __device__ __forceinline__ void coop_up(const CoopLevel &F, const CoopLevel &C, const XSpec X, const RSpec R, double *out,
                                         double omega, int gtid, int nth) {
-    const int groups = nth / 8, g = gtid / 8, l = gtid & 7;
-    const unsigned gmask = 0xffu << (threadIdx.x & 24);
+    constexpr int U = 2, LPR = 8 * G;
+    const int lane = threadIdx.x & 31, sub = lane & (LPR - 1), g = sub >> 3, l = sub & 7;
+    const unsigned gmask = 0xffu << (lane & 24), rmask = row_mask<G>();
     const int lc = l < D ? l : 0;
-    for (int i = g; i < F.n; i += groups) {
+    const size_t pad = (size_t)C.pad_fine;
+    for (int i = gtid / LPR; i < F.n; i += nth / LPR) {
         double acc = 0, xi_l = 0;
         const int kb = F.rowptr[i], ke = F.rowptr[i + 1];
-        // all index loads of a chunk first (column vertex and its aggregate come from two parallel arrays, so the
-        // dependent chain is rowptr -> {colidx, acol} -> {frame, x, correction}), then the unrolled block loop whose
-        // loads do not depend on the running sum
-        constexpr int U = 12;
-        for (int k0 = kb; k0 < ke; k0 += U) {
+        for (int k0 = kb + g * U; k0 < ke; k0 += G * U) {
             int j[U], I[U];
+            double f0[U], f1[U], xcv[U], xv[U], av[U][D];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const bool in = k0 + u < ke;
-                j[u] = in ? F.colidx[k0 + u] : i;
-                I[u] = in ? F.acol[k0 + u] : 0;
+                const int k = min(k0 + u, ke - 1);
+                j[u] = F.colidx[k];
+                I[u] = F.acol[k];
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                f0[u] = __ldg(C.rel + (size_t)l * pad + j[u]);                       // frame entries 0..7
+                f1[u] = __ldg(C.rel + (size_t)(8 + (l < 5 ? l : 4)) * pad + j[u]);   // frame entries 8..12
+                xcv[u] = xget(X, (size_t)I[u] * D + lc);
+                xv[u] = __ldcg(F.x + (size_t)j[u] * D + lc);
+                const double *Ak = F.A + (size_t)min(k0 + u, ke - 1) * DD + lc * D;
+#pragma unroll
+                for (int c = 0; c < D; ++c) av[u][c] = Ak[c];
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (k0 + u >= ke) break;
-                const Rel S = load_rel(C.rel, C.pad_fine, j[u]);
+                Rel S;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) S.R[q] = gshfl(gmask, f0[u], q);
+                S.R[8] = gshfl(gmask, f1[u], 0);
+                S.t[0] = gshfl(gmask, f1[u], 1); S.t[1] = gshfl(gmask, f1[u], 2); S.t[2] = gshfl(gmask, f1[u], 3);
+                S.s = gshfl(gmask, f1[u], 4);
                 double xc[D], v[D];
 #pragma unroll
-                for (int c = 0; c < D; ++c) xc[c] = xget(X, (size_t)I[u] * D + c);
+                for (int c = 0; c < D; ++c) xc[c] = gshfl(gmask, xcv[u], c);
                 Xf<D>::apply(S, xc, v);
-                const double *Ak = F.A + (size_t)(k0 + u) * DD + lc * D;
                 double own = 0;
 #pragma unroll
                 for (int c = 0; c < D; ++c) {
-                    const double xpc = __ldcg(F.x + (size_t)j[u] * D + c) + v[c];
-                    acc += Ak[c] * xpc;
+                    const double xpc = gshfl(gmask, xv[u], c) + v[c];
+                    acc += av[u][c] * xpc;
                     own = (c == lc) ? xpc : own;
                 }
                 if (j[u] == i) xi_l = own;
             }
         }
+        acc = row_sum<G>(rmask, acc);
+        xi_l = row_sum<G>(rmask, xi_l);         // the diagonal block sits in exactly one group
         const double res = rget(R, (size_t)i * D + lc) - acc;
         double z = 0;
 #pragma unroll
         for (int c = 0; c < D; ++c) z += F.Dinv[(size_t)i * sym_size<D>() + sym_off<D>(lc, c)] * gshfl(gmask, res, c);
-        if (l < D) out[(size_t)i * D + l] = xi_l + omega * z;
+        if (g == 0 && l < D) out[(size_t)i * D + l] = xi_l + omega * z;
     }
 }
 
 // dot products of one inner step over the grid: per-CTA partials -> grid barrier -> every CTA adds the
 // partials in the same fixed order (all CTAs obtain identical bits).  The barrier inside also orders the
 // store of q before whatever phase follows.
-template <int D>
+template <int D, int G>
 __device__ __forceinline__ void coop_kdots(const CoopLevel &L, const double *z, const RSpec V1, const double *v2, double *q,
                                            double *dots, double out[3], int gtid, int nth, double *sh, const GridBarrier &gb,
                                            unsigned &phase) {
-    const int groups = nth / 8, g = gtid / 8, l = gtid & 7;
+    constexpr int U = 6, LPR = 8 * G;
+    const int lane = threadIdx.x & 31, sub = lane & (LPR - 1), g = sub >> 3, l = sub & 7;
+    const unsigned gmask = 0xffu << (lane & 24), rmask = row_mask<G>();
+    const int lc = l < D ? l : 0;
     double d0 = 0, d1 = 0, d2 = 0;
-    for (int i = g; i < L.n; i += groups) {
-        if (l >= D) continue;
+    for (int i = gtid / LPR; i < L.n; i += nth / LPR) {
         double acc = 0;
-#pragma unroll 4
-        for (int k = L.rowptr[i]; k < L.rowptr[i + 1]; ++k) {
-            const double *zj = z + (size_t)L.colidx[k] * D;
-            const double *Ak = L.A + (size_t)k * DD + l * D;
+        const int kb = L.rowptr[i], ke = L.rowptr[i + 1];
+        for (int k0 = kb + g * U; k0 < ke; k0 += G * U) {
+            int j[U];
+            double zv[U], av[U][D];
 #pragma unroll
-            for (int c = 0; c < D; ++c) acc += Ak[c] * __ldcg(zj + c);
+            for (int u = 0; u < U; ++u) j[u] = L.colidx[min(k0 + u, ke - 1)];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                zv[u] = __ldcg(z + (size_t)j[u] * D + lc);
+                const double *Ak = L.A + (size_t)min(k0 + u, ke - 1) * DD + lc * D;
+#pragma unroll
+                for (int c = 0; c < D; ++c) av[u][c] = Ak[c];
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (k0 + u >= ke) break;
+#pragma unroll
+                for (int c = 0; c < D; ++c) acc += av[u][c] * gshfl(gmask, zv[u], c);
+            }
         }
-        const double zi = __ldcg(z + (size_t)i * D + l);
-        if (q) q[(size_t)i * D + l] = acc;
-        d0 += zi * acc;
-        d1 += zi * rget(V1, (size_t)i * D + l);
-        if (v2) d2 += zi * __ldcg(v2 + (size_t)i * D + l);
+        acc = row_sum<G>(rmask, acc);
+        if (g == 0 && l < D) {
+            const double zi = __ldcg(z + (size_t)i * D + l);
+            if (q) q[(size_t)i * D + l] = acc;
+            d0 += zi * acc;
+            d1 += zi * rget(V1, (size_t)i * D + l);
+            if (v2) d2 += zi * __ldcg(v2 + (size_t)i * D + l);
+        }
     }
     const double s0 = block_sum<kCoopThreads>(d0, sh);
     const double s1 = block_sum<kCoopThreads>(d1, sh);
     const double s2 = block_sum<kCoopThreads>(d2, sh);
-    const int G = gridDim.x;
-    if (threadIdx.x == 0) { dots[blockIdx.x] = s0; dots[G + blockIdx.x] = s1; dots[2 * G + blockIdx.x] = s2; }
+    const int Gd = gridDim.x;
+    if (threadIdx.x == 0) { dots[blockIdx.x] = s0; dots[Gd + blockIdx.x] = s1; dots[2 * Gd + blockIdx.x] = s2; }
     grid_barrier(gb, phase);
     __shared__ double tot[3];
     if (threadIdx.x < 32) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             double v = 0;
-            for (int t = threadIdx.x; t < G; t += 32) v += __ldcg(dots + k * G + t);
+            for (int t = threadIdx.x; t < Gd; t += 32) v += __ldcg(dots + k * Gd + t);
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
             if (threadIdx.x == 0) tot[k] = v;
@@ -1140,7 +1198,9 @@ amg_coop_kernel(const __grid_constant__ CoopParams P, double omega, const DevSca
     unsigned phase = 0;
     __shared__ double sh[32];
     const int nth = gridDim.x * kCoopThreads, gtid = blockIdx.x * kCoopThreads + threadIdx.x;
-    auto gsync = [&]() { grid_barrier(gb, phase); };
+    auto stamp = [&]() { if (P.dbg && gtid == 0 && phase < 120) P.dbg[phase] = clock64(); };
+    auto gsync = [&]() { grid_barrier(gb, phase); stamp(); };
+    stamp();
     const int last = P.nlev - 1;
     // explicit recursion state: residual of the cycle in progress at every level, where its result goes, the
     // inner step of a K-cycle level and its scalars
@@ -1161,16 +1221,15 @@ amg_coop_kernel(const __grid_constant__ CoopParams P, double omega, const DevSca
             if (l == last) {
                 // the coarsest level is never a K-cycle level: its residual is the plain vector L.r
                 if (P.dense) {
-                    // x = A^-1 r: an 8-lane group per entry, reading a row of the (symmetric) inverse contiguously
-                    const int g8 = gtid / 8, l8 = gtid & 7;
-                    for (int t0 = 0; t0 < P.N; t0 += nth / 8) {
-                        const int t = t0 + g8;
+                    // x = A^-1 r: a warp per entry, reading a row of the (symmetric) inverse contiguously
+                    const int lane = threadIdx.x & 31;
+                    for (int t = gtid >> 5; t < P.N; t += nth >> 5) {
                         double acc = 0;
-                        if (t < P.N)
-                            for (int c = l8; c < P.N; c += 8) acc += P.inv[(size_t)t * P.N + c] * __ldcg(L.r + c);
+#pragma unroll 8
+                        for (int c = lane; c < P.N; c += 32) acc += P.inv[(size_t)t * P.N + c] * __ldcg(L.r + c);
 #pragma unroll
-                        for (int off = 4; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off, 8);
-                        if (t < P.N && l8 == 0) cur_out[l][t] = acc;
+                        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+                        if (lane == 0) cur_out[l][t] = acc;
                     }
                 } else if (l == 0) {    // a single coarse level too large for the dense inverse: five damped sweeps
                     coop_rows<D, 0>(L, L.r, nullptr, L.x, omega, gtid, nth);
@@ -1196,7 +1255,9 @@ amg_coop_kernel(const __grid_constant__ CoopParams P, double omega, const DevSca
                 gsync();
                 break;
             }
-            coop_down<D>(L, cur_r[l], omega, gtid, nth);
+            if (L.G == 4) coop_down<D, 4>(L, cur_r[l], omega, gtid, nth);
+            else if (L.G == 2) coop_down<D, 2>(L, cur_r[l], omega, gtid, nth);
+            else coop_down<D, 1>(L, cur_r[l], omega, gtid, nth);
             gsync();
             coop_restrict<D>(P.lev[l + 1], L.t, gtid, nth);
             gsync();
@@ -1215,7 +1276,10 @@ amg_coop_kernel(const __grid_constant__ CoopParams P, double omega, const DevSca
                 double *dots = P.dots + (flip ? 3 * gridDim.x : 0);
                 flip ^= 1;
                 if (step[l] == 0) {
-                    coop_kdots<D>(L, L.z1, cur_r[l], nullptr, L.q1, dots, d, gtid, nth, sh, gb, phase);
+                    if (L.G == 4) coop_kdots<D, 4>(L, L.z1, cur_r[l], nullptr, L.q1, dots, d, gtid, nth, sh, gb, phase);
+                    else if (L.G == 2) coop_kdots<D, 2>(L, L.z1, cur_r[l], nullptr, L.q1, dots, d, gtid, nth, sh, gb, phase);
+                    else coop_kdots<D, 1>(L, L.z1, cur_r[l], nullptr, L.q1, dots, d, gtid, nth, sh, gb, phase);
+                    stamp();
                     kscal_first(&ks[l], d[0], d[1]);
                     step[l] = 1;
                     cur_r[l] = RSpec{ L.r, L.q1, ks[l].alpha1 };      // r' = r - alpha1 q1, formed where it is read
@@ -1223,7 +1287,10 @@ amg_coop_kernel(const __grid_constant__ CoopParams P, double omega, const DevSca
                     again = true;
                     break;                      // second cycle at the same level
                 }
-                coop_kdots<D>(L, L.z2, cur_r[l], L.q1, nullptr, dots, d, gtid, nth, sh, gb, phase);
+                if (L.G == 4) coop_kdots<D, 4>(L, L.z2, cur_r[l], L.q1, nullptr, dots, d, gtid, nth, sh, gb, phase);
+                else if (L.G == 2) coop_kdots<D, 2>(L, L.z2, cur_r[l], L.q1, nullptr, dots, d, gtid, nth, sh, gb, phase);
+                else coop_kdots<D, 1>(L, L.z2, cur_r[l], L.q1, nullptr, dots, d, gtid, nth, sh, gb, phase);
+                stamp();
                 kscal_second(&ks[l], d[0], d[1], d[2]);
                 X = XSpec{ L.z1, L.z2, ks[l].c1, ks[l].c2 };
                 if (l == 0) {                   // the caller reads a plain vector
@@ -1233,7 +1300,9 @@ amg_coop_kernel(const __grid_constant__ CoopParams P, double omega, const DevSca
             }
             if (l == 0) return;
             --l;
-            coop_up<D>(P.lev[l], P.lev[l + 1], X, cur_r[l], cur_out[l], omega, gtid, nth);
+            if (P.lev[l].G == 4) coop_up<D, 4>(P.lev[l], P.lev[l + 1], X, cur_r[l], cur_out[l], omega, gtid, nth);
+            else if (P.lev[l].G == 2) coop_up<D, 2>(P.lev[l], P.lev[l + 1], X, cur_r[l], cur_out[l], omega, gtid, nth);
+            else coop_up<D, 1>(P.lev[l], P.lev[l + 1], X, cur_r[l], cur_out[l], omega, gtid, nth);
             gsync();
         }
         (void)again;
@@ -1652,6 +1721,12 @@ int apply_t(s3o_problem *p, int init) {
                 P.kdepth = nk > l ? nk - l : 0;
                 P.kmask = st->kmask >> l;
                 P.dots = st->d_cdots;
+                static long long *d_dbg = nullptr;
+                static int dbg_calls = 0;
+                static const bool dbg_on = getenv("S3O_COOP_DBG") != nullptr;
+                if (dbg_on && !d_dbg) { cudaMalloc(&d_dbg, 128 * sizeof(long long)); }
+                const bool dbg_now = dbg_on && ++dbg_calls == 200;
+                if (dbg_now) { cudaMemsetAsync(d_dbg, 0, 128 * sizeof(long long), s); P.dbg = d_dbg; }
                 for (int k = l; k < nl; ++k) {
                     LevelDev &S = st->lev[k];
                     CoopLevel &T = P.lev[k - l];
@@ -1666,9 +1741,22 @@ int apply_t(s3o_problem *p, int init) {
                 void *args[] = { &P, &omega, (void *)&sc, &chk_, &gb };
                 int grid = (L.n * 8 + kCoopThreads - 1) / kCoopThreads;
                 grid = std::max(8, std::min(grid, st->coop_grid));
+                for (int k = 0; k < P.nlev; ++k) {      // a block row is shared by as many 8-lane groups as the grid has to spare
+                    const long long lanes = (long long)grid * kCoopThreads, n = P.lev[k].n;
+                    P.lev[k].G = n * 32 <= lanes ? 4 : (n * 16 <= lanes ? 2 : 1);
+                }
                 if (launch_persistent(p, (const void *)amg_coop_kernel<D>, grid, kCoopThreads, args, 5)) rc_inner = S3O_ERR_CUDA;
                 ++launches;
                 trace_mark(p, "cooperative kernel");
+                if (dbg_now) {
+                    long long h[128];
+                    cudaStreamSynchronize(s);
+                    cudaMemcpy(h, d_dbg, sizeof h, cudaMemcpyDeviceToHost);
+                    int khz = 1; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, p->device);
+                    fprintf(stderr, "S3O_COOP_DBG: phase times of one cooperative-kernel call (us, SM clock %d kHz)\n ", khz);
+                    for (int q = 1; q < 120 && h[q]; ++q) fprintf(stderr, " %d:%.1f", q, (double)(h[q] - h[q - 1]) / khz * 1e3);
+                    fprintf(stderr, "\n");
+                }
                 return;
             }
             if ((st->kmask >> l) & 1u) {
