@@ -74,8 +74,16 @@ void build_structure_from_hidx(int nv, const int32_t *hidx, int nfree, int ne, c
                                HostStructure &S);
 
 // Device twin (structure_dev.cu): the same arrays from integer kernels (stable radix sort + scans); bit-identical.
+// Device copies of the index arrays that build_structure_device leaves alive for the caller (ownership passes:
+// cudaFree them).  The arrays no host code reads are not copied back at all.
+struct DeviceStructure {
+    int32_t *hidx = nullptr, *sv0 = nullptr, *sv1 = nullptr, *blk_ebeg = nullptr, *blk_eend = nullptr, *blk_src = nullptr,
+            *multi_blk = nullptr, *inc_ptr = nullptr, *inc_ent = nullptr, *e_blk = nullptr, *rowptr = nullptr, *colidx = nullptr,
+            *blk_row = nullptr, *colT_ptr = nullptr, *colT_blk = nullptr, *perm = nullptr;
+    bool valid = false;
+};
 int build_structure_device(cudaStream_t st, int nv, const uint8_t *fixed, const int32_t *hidx_in, int nfree_in, int ne,
-                           const int32_t *v0, const int32_t *v1, HostStructure &S);
+                           const int32_t *v0, const int32_t *v1, HostStructure &S, DeviceStructure *keep = nullptr);
 
 // Vertex-range partition of the free vertices across `world` ranks.
 // Rank r owns global Hessian indices [r*seg, min((r+1)*seg, nf)), seg = ceil(nf/world).

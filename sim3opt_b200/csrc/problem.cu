@@ -369,17 +369,19 @@ int do_solve(s3o_problem *p, double lambda, int *status, int *iters, double *rel
 namespace s3o {
 
 // BSR-upper arrays of p->S (rows, columns, block->row, column view, SpMV tiles) -> device
-int upload_structure_arrays(s3o_problem *p, int rows_own) {
+int upload_structure_arrays(s3o_problem *p, int rows_own, bool on_device) {
     HostStructure &S = p->S;
-    std::vector<int32_t> blk_row(S.nb);
-    for (int r = 0; r < S.nf; ++r)
-        for (int k = S.rowptr[r]; k < S.rowptr[r + 1]; ++k) blk_row[k] = r;
     int rc = 0;
-    rc = rc ? rc : upload(p, &p->d_rowptr, S.rowptr);
-    rc = rc ? rc : upload(p, &p->d_colidx, S.colidx);
-    rc = rc ? rc : upload(p, &p->d_blk_row, blk_row);
-    rc = rc ? rc : upload(p, &p->d_colT_ptr, S.colT_ptr);
-    rc = rc ? rc : upload(p, &p->d_colT_blk, S.colT_blk);
+    if (!on_device) {       // (the device build hands its own copies over)
+        std::vector<int32_t> blk_row(S.nb);
+        for (int r = 0; r < S.nf; ++r)
+            for (int k = S.rowptr[r]; k < S.rowptr[r + 1]; ++k) blk_row[k] = r;
+        rc = rc ? rc : upload(p, &p->d_rowptr, S.rowptr);
+        rc = rc ? rc : upload(p, &p->d_colidx, S.colidx);
+        rc = rc ? rc : upload(p, &p->d_blk_row, blk_row);
+        rc = rc ? rc : upload(p, &p->d_colT_ptr, S.colT_ptr);
+        rc = rc ? rc : upload(p, &p->d_colT_blk, S.colT_blk);
+    }
     S.max_row_blocks = 0;
     for (int r = 0; r < rows_own; ++r) S.max_row_blocks = std::max(S.max_row_blocks, S.rowptr[r + 1] - S.rowptr[r]);
     S.tile_blocks = (p->spmv_version == 4 && p->d == 7) ? spmv4_tile_blocks()
@@ -945,6 +947,7 @@ int s3o_build_structure(s3o_problem *p, int *n_free, int *n_blocks) {
         setup_mark(nullptr);
         free_structure(p);
         HostStructure &S = p->S;
+        DeviceStructure dev;
         // the index build runs on the device (structure_dev.cu); S3O_STRUCTURE=host selects the host twin
         const char *where = getenv("S3O_STRUCTURE");
         if (where && !strcmp(where, "host")) {
@@ -955,8 +958,8 @@ int s3o_build_structure(s3o_problem *p, int *n_free, int *n_blocks) {
                 build_structure_host(p->nv, p->fixed.data(), p->ne, p->v0.data(), p->v1.data(), S);
         } else {
             const int rcs = p->dist ? build_structure_device(p->stream, p->nv, nullptr, p->plan.lhidx.data(), p->plan.n_own + p->plan.n_ghost,
-                                                             p->ne, p->v0.data(), p->v1.data(), S)
-                                    : build_structure_device(p->stream, p->nv, p->fixed.data(), nullptr, 0, p->ne, p->v0.data(), p->v1.data(), S);
+                                                             p->ne, p->v0.data(), p->v1.data(), S, &dev)
+                                    : build_structure_device(p->stream, p->nv, p->fixed.data(), nullptr, 0, p->ne, p->v0.data(), p->v1.data(), S, &dev);
             if (rcs) return rcs;
         }
         setup_mark("structure: index build");
@@ -964,18 +967,26 @@ int s3o_build_structure(s3o_problem *p, int *n_free, int *n_blocks) {
         p->ne_pad = pad32(S.ne_act);
         int rc = 0;
         int32_t *d_perm = nullptr;
-        rc = rc ? rc : upload(p, &p->d_hidx, S.hidx);
-        rc = rc ? rc : upload(p, &p->d_sv0, S.sv0);
-        rc = rc ? rc : upload(p, &p->d_sv1, S.sv1);
-        rc = rc ? rc : upload(p, &p->d_blk_ebeg, S.blk_ebeg);
-        rc = rc ? rc : upload(p, &p->d_blk_eend, S.blk_eend);
-        rc = rc ? rc : upload(p, &p->d_blk_src, S.blk_src);
-        rc = rc ? rc : upload(p, &p->d_multi_blk, S.multi_blk);
-        rc = rc ? rc : upload(p, &p->d_inc_ptr, S.inc_ptr);
-        rc = rc ? rc : upload(p, &p->d_inc_ent, S.inc_ent);
-        rc = rc ? rc : upload(p, &p->d_e_blk, S.e_blk);
+        if (dev.valid) {        // built on the device: the arrays are already where they are needed
+            p->d_hidx = dev.hidx; p->d_sv0 = dev.sv0; p->d_sv1 = dev.sv1; p->d_blk_ebeg = dev.blk_ebeg; p->d_blk_eend = dev.blk_eend;
+            p->d_blk_src = dev.blk_src; p->d_multi_blk = dev.multi_blk; p->d_inc_ptr = dev.inc_ptr; p->d_inc_ent = dev.inc_ent;
+            p->d_e_blk = dev.e_blk; p->d_rowptr = dev.rowptr; p->d_colidx = dev.colidx; p->d_blk_row = dev.blk_row;
+            p->d_colT_ptr = dev.colT_ptr; p->d_colT_blk = dev.colT_blk;
+            d_perm = dev.perm;
+        } else {
+            rc = rc ? rc : upload(p, &p->d_hidx, S.hidx);
+            rc = rc ? rc : upload(p, &p->d_sv0, S.sv0);
+            rc = rc ? rc : upload(p, &p->d_sv1, S.sv1);
+            rc = rc ? rc : upload(p, &p->d_blk_ebeg, S.blk_ebeg);
+            rc = rc ? rc : upload(p, &p->d_blk_eend, S.blk_eend);
+            rc = rc ? rc : upload(p, &p->d_blk_src, S.blk_src);
+            rc = rc ? rc : upload(p, &p->d_multi_blk, S.multi_blk);
+            rc = rc ? rc : upload(p, &p->d_inc_ptr, S.inc_ptr);
+            rc = rc ? rc : upload(p, &p->d_inc_ent, S.inc_ent);
+            rc = rc ? rc : upload(p, &p->d_e_blk, S.e_blk);
+        }
         setup_mark("  structure: edge-array uploads");
-        rc = rc ? rc : upload_structure_arrays(p, rows_own);
+        rc = rc ? rc : upload_structure_arrays(p, rows_own, dev.valid);
         setup_mark("  structure: BSR/tile uploads");
         if (p->dist) {
             const PartitionPlan &P = p->plan;
@@ -988,7 +999,7 @@ int s3o_build_structure(s3o_problem *p, int *n_free, int *n_blocks) {
             rc = rc ? rc : dev_alloc(&p->d_xg, (size_t)P.world * P.seg * p->d);
         }
         p->want_p2p_setup = p->dist;
-        rc = rc ? rc : upload(p, &d_perm, S.perm);
+        if (!dev.valid) rc = rc ? rc : upload(p, &d_perm, S.perm);
         rc = rc ? rc : dev_alloc(&p->d_meas, (size_t)p->ne_pad * p->est_dim);
         const int info_planes = p->info_diag ? p->d : p->ninfo;
         if (p->has_info) rc = rc ? rc : dev_alloc(&p->d_info, (size_t)p->ne_pad * info_planes);

@@ -148,7 +148,7 @@ void free_structure(s3o_problem *p);
 void close_p2p(s3o_problem *p);
 int check_launch(s3o_problem *p, int n);
 int sync_scalars(s3o_problem *p);
-int upload_structure_arrays(s3o_problem *p, int rows_own);   // BSR / tile arrays of p->S -> device
+int upload_structure_arrays(s3o_problem *p, int rows_own, bool on_device = false);   // BSR / tile arrays of p->S -> device
 int alloc_linear_system(s3o_problem *p);                      // H, b, x, r, z, p, q1, T, Minv for p->S
 // Solve (H + lambda I) x = b on the system held in p->d_H / p->d_b; x in p->d_x.  Sparse block Cholesky when the
 // factor is small (s3o_set_linear_solver), PCG otherwise.  defer_sync: the exact path does not wait for the

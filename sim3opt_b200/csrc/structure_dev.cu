@@ -362,7 +362,7 @@ inline int grid_for(long long n) { return (int)std::max<long long>(1, (n + 255) 
 // completely (all arrays are copied back: the hierarchy builder, the factorisation plan and the getters read them
 // on the host).
 int build_structure_device(cudaStream_t st, int nv, const uint8_t *fixed, const int32_t *hidx_in, int nfree_in, int ne,
-                           const int32_t *v0, const int32_t *v1, HostStructure &S) {
+                           const int32_t *v0, const int32_t *v1, HostStructure &S, DeviceStructure *keep) {
     S = HostStructure();
     S.nv = nv;
     S.ne = ne;
@@ -501,29 +501,53 @@ int build_structure_device(cudaStream_t st, int nv, const uint8_t *fixed, const 
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("build_structure_device: %s", cudaGetErrorString(e)); cleanup(); return S3O_ERR_CUDA; }
 
-    // ---- everything back to the host structure
+    // ---- back to the host structure: everything when the caller keeps no device copies, else only what host code
+    // reads (hierarchy builder, factorisation plan, getters); the edge-side arrays stay on the device
     SD_CHECK(to_host(st, S.hidx, d_hidx, (size_t)nv));
     SD_CHECK(to_host(st, S.free2v, d_free2v, (size_t)nf));
     SD_CHECK(to_host(st, S.perm, d_perm, (size_t)na));
-    SD_CHECK(to_host(st, S.sv0, d_sv0, (size_t)na));
-    SD_CHECK(to_host(st, S.sv1, d_sv1, (size_t)na));
-    SD_CHECK(to_host(st, S.e_blk, d_e_blk, (size_t)na));
     SD_CHECK(to_host(st, S.rowptr, d_rowptr, (size_t)nf + 1));
     SD_CHECK(to_host(st, S.colidx, d_colidx, (size_t)nb));
-    SD_CHECK(to_host(st, S.blk_ebeg, d_ebeg, (size_t)nb));
-    SD_CHECK(to_host(st, S.blk_eend, d_eend, (size_t)nb));
-    SD_CHECK(to_host(st, S.blk_src, d_blk_src, (size_t)nb));
     SD_CHECK(to_host(st, S.multi_blk, d_multi, (size_t)n_multi));
-    SD_CHECK(to_host(st, S.inc_ptr, d_inc_ptr, (size_t)nf + 1));
-    SD_CHECK(to_host(st, S.inc_ent, d_inc_ent, (size_t)n_inc));
-    SD_CHECK(to_host(st, S.colT_ptr, d_colT_ptr, (size_t)nf + 1));
-    SD_CHECK(to_host(st, S.colT_blk, d_colT_blk, (size_t)n_off2));
     SD_CHECK(to_host(st, S.ccs_colptr, d_ccs_colptr, (size_t)nf + 1));
     SD_CHECK(to_host(st, S.ccs_rowidx, d_ccs_rowidx, (size_t)nb));
     SD_CHECK(to_host(st, S.ccs2bsr, d_ccs2bsr, (size_t)nb));
+    if (!keep) {
+        SD_CHECK(to_host(st, S.sv0, d_sv0, (size_t)na));
+        SD_CHECK(to_host(st, S.sv1, d_sv1, (size_t)na));
+        SD_CHECK(to_host(st, S.e_blk, d_e_blk, (size_t)na));
+        SD_CHECK(to_host(st, S.blk_ebeg, d_ebeg, (size_t)nb));
+        SD_CHECK(to_host(st, S.blk_eend, d_eend, (size_t)nb));
+        SD_CHECK(to_host(st, S.blk_src, d_blk_src, (size_t)nb));
+        SD_CHECK(to_host(st, S.inc_ptr, d_inc_ptr, (size_t)nf + 1));
+        SD_CHECK(to_host(st, S.inc_ent, d_inc_ent, (size_t)n_inc));
+        SD_CHECK(to_host(st, S.colT_ptr, d_colT_ptr, (size_t)nf + 1));
+        SD_CHECK(to_host(st, S.colT_blk, d_colT_blk, (size_t)n_off2));
+    } else {
+        auto take = [&](int32_t *ptr) {         // out of the scratch list: the caller frees it
+            tmp.erase(std::find(tmp.begin(), tmp.end(), (void *)ptr));
+            return ptr;
+        };
+        keep->hidx = take(d_hidx); keep->sv0 = take(d_sv0); keep->sv1 = take(d_sv1);
+        keep->blk_ebeg = take(d_ebeg); keep->blk_eend = take(d_eend); keep->blk_src = take(d_blk_src);
+        keep->multi_blk = take(d_multi); keep->inc_ptr = take(d_inc_ptr); keep->inc_ent = take(d_inc_ent);
+        keep->e_blk = take(d_e_blk); keep->rowptr = take(d_rowptr); keep->colidx = take(d_colidx);
+        keep->blk_row = take(d_blk_row); keep->colT_ptr = take(d_colT_ptr); keep->colT_blk = take(d_colT_blk);
+        keep->perm = take(d_perm);
+        keep->valid = true;
+    }
     e = cudaStreamSynchronize(st);
     cleanup();
-    if (e != cudaSuccess) { set_error("build_structure_device: %s", cudaGetErrorString(e)); return S3O_ERR_CUDA; }
+    if (e != cudaSuccess) {
+        set_error("build_structure_device: %s", cudaGetErrorString(e));
+        if (keep && keep->valid) {
+            for (int32_t *q : { keep->hidx, keep->sv0, keep->sv1, keep->blk_ebeg, keep->blk_eend, keep->blk_src, keep->multi_blk,
+                                keep->inc_ptr, keep->inc_ent, keep->e_blk, keep->rowptr, keep->colidx, keep->blk_row,
+                                keep->colT_ptr, keep->colT_blk, keep->perm }) cudaFree(q);
+            *keep = DeviceStructure();
+        }
+        return S3O_ERR_CUDA;
+    }
 #undef SD_CHECK
 #undef SD_ALLOC
     return S3O_OK;
