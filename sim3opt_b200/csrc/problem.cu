@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -770,21 +771,33 @@ int s3o_set_edges(s3o_problem *p, int n, const int32_t *v0, const int32_t *v1, c
     p->user_ne = n;
     p->has_info = info != nullptr;
     p->info_diag = false;
-    if (info && n > 0) {     // diagonal information matrices (the usual case) are kept as their d diagonal entries
+    // Diagonal information matrices (the usual case) are kept as their d diagonal entries.  One threaded pass over
+    // the caller's matrices checks the off-diagonal entries and extracts the diagonals at the same time (the buffer
+    // is left uninitialised so that its pages are first touched by the threads that fill them).
+    std::unique_ptr<double[]> info_diag_host;
+    if (info && n > 0) {
         const int dd = p->d * p->d, d = p->d;
         const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        info_diag_host.reset(new double[(size_t)n * d]);
+        double *dst = info_diag_host.get();
         std::vector<char> nondiag(hw, 0);
         std::vector<std::thread> th;
         for (unsigned w = 0; w < hw; ++w)
             th.emplace_back([&, w]() {
                 const size_t lo = (size_t)n * w / hw, hi = (size_t)n * (w + 1) / hw;
-                for (size_t k = lo; k < hi && !nondiag[w]; ++k)
-                    for (int e = 0; e < dd; ++e)
-                        if (e / d != e % d && info[k * dd + e] != 0.0) { nondiag[w] = 1; break; }
+                for (size_t k = lo; k < hi && !nondiag[w]; ++k) {
+                    const double *M = info + k * dd;
+                    for (int e = 0; e < dd; ++e) {
+                        const int r = e / d, c = e - r * d;
+                        if (r == c) dst[k * d + r] = M[e];
+                        else if (M[e] != 0.0) { nondiag[w] = 1; break; }
+                    }
+                }
             });
         for (auto &t : th) t.join();
         p->info_diag = true;
         for (char f : nondiag) if (f) p->info_diag = false;
+        if (!p->info_diag) info_diag_host.reset();
     }
     setup_mark("set_edges: info scan");
     std::vector<double> meas_loc, info_loc;
@@ -798,16 +811,19 @@ int s3o_set_edges(s3o_problem *p, int n, const int32_t *v0, const int32_t *v1, c
         const int ed = p->est_dim, dd = p->d * p->d;
         p->v0.resize(nl); p->v1.resize(nl);
         meas_loc.resize((size_t)nl * ed);
-        if (info) info_loc.resize((size_t)nl * dd);
+        // the information matrices of the local edges: their diagonals when all are diagonal, else the full matrices
+        const int iw = p->info_diag ? p->d : dd;
+        const double *isrc = p->info_diag ? info_diag_host.get() : info;
+        if (info) info_loc.resize((size_t)nl * iw);
         for (int t = 0; t < nl; ++t) {
             const size_t k = (size_t)P.local_edges[t];
             p->v0[t] = v0[k]; p->v1[t] = v1[k];
             memcpy(&meas_loc[(size_t)t * ed], meas + k * ed, sizeof(double) * ed);
-            if (info) memcpy(&info_loc[(size_t)t * dd], info + k * dd, sizeof(double) * dd);
+            if (info) memcpy(&info_loc[(size_t)t * iw], isrc + k * iw, sizeof(double) * iw);
         }
         n = nl;
         meas = meas_loc.data();
-        if (info) info = info_loc.data();
+        if (info) info = info_loc.data();       // (diagonals only when info_diag)
     } else {
         p->v0.assign(v0, v0 + n);
         p->v1.assign(v1, v1 + n);
@@ -819,26 +835,13 @@ int s3o_set_edges(s3o_problem *p, int n, const int32_t *v0, const int32_t *v1, c
     if ((rc = dev_alloc(&p->d_meas_aos, mcount))) return rc;
     if (n) S3O_CUDA(cudaMemcpyAsync(p->d_meas_aos, meas, mcount * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     p->stats.h2d_bytes += (int64_t)(mcount * sizeof(double));
-    std::vector<double> info_diag_host;
     if (info) {
         const int d = p->d, dd = d * d;
         const double *src = info;
         size_t icount = (size_t)n * dd;
         if (p->info_diag) {         // 56 B per edge over PCIe instead of 392 B
-            info_diag_host.resize((size_t)n * d);
-            const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-            std::vector<std::thread> th;
-            double *dst = info_diag_host.data();
-            for (unsigned w = 0; w < hw; ++w)
-                th.emplace_back([=]() {
-                    const size_t lo = (size_t)n * w / hw, hi = (size_t)n * (w + 1) / hw;
-                    for (size_t k = lo; k < hi; ++k)
-                        for (int r = 0; r < d; ++r) dst[k * d + r] = info[k * dd + r * d + r];
-                });
-            for (auto &t : th) t.join();
-            src = info_diag_host.data();
+            src = p->dist ? info : info_diag_host.get();
             icount = (size_t)n * d;
-            setup_mark("set_edges: diag extract");
         }
         if ((rc = dev_alloc(&p->d_info_aos, icount))) return rc;
         if (n) S3O_CUDA(cudaMemcpyAsync(p->d_info_aos, src, icount * sizeof(double), cudaMemcpyHostToDevice, p->stream));
