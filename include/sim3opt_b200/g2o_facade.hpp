@@ -455,7 +455,7 @@ public:
             v1[k] = dense_[e->vertex(1)->id()];
             e->packMeasurement(&meas[(size_t)k * est_dim_]);
             if (!identity) e->packInformation(&info[(size_t)k * dim_ * dim_]);
-            if (e->robustKernel()) rk = e->robustKernel();
+            if (!robustConsistent(e, k, rk)) return fail("initializeOptimization: the library applies ONE robust kernel to all edges; set the same kernel (kind and delta) on every edge or on none");
         }
         if (s3o_set_edges(problem_, ne, v0.data(), v1.data(), meas.data(), identity ? nullptr : info.data()) != S3O_OK)
             return fail(s3o_last_error());
@@ -533,6 +533,13 @@ public:
     }
 
 private:
+    // s3o_set_robust is per problem: every edge must carry the same kernel (kind, delta) or none (edge k of the scan)
+    static bool robustConsistent(const Edge *e, int k, const RobustKernel *&rk) {
+        const RobustKernel *r = e->robustKernel();
+        if (k == 0) { rk = r; return true; }
+        if ((r == nullptr) != (rk == nullptr)) return false;
+        return !r || (r->s3oKind() == rk->s3oKind() && r->delta() == rk->delta());
+    }
     bool fail(const char *msg) { error_ = msg ? msg : "unknown error"; return false; }
     // BA graph (bal_example.cpp:98-198): cameras and points in id order, observations in insertion order
     bool initializeBA() {
@@ -563,7 +570,7 @@ private:
             oc[k] = dense_[e->vertex(1)->id()];
             e->packMeasurement(&uv[(size_t)k * 2]);
             if (!identity) { double m[4]; e->packInformation(m); info[(size_t)k * 3] = m[0]; info[(size_t)k * 3 + 1] = m[1]; info[(size_t)k * 3 + 2] = m[3]; }
-            if (e->robustKernel()) rk = e->robustKernel();
+            if (!robustConsistent(e, k, rk)) return fail("initializeOptimization: the library applies ONE robust kernel to all edges; set the same kernel (kind and delta) on every edge or on none");
             if (auto *proj = dynamic_cast<EdgeProjectXYZ2UV *>(e)) cam = proj->cameraParameters();
         }
         if (!cam) return fail("initializeOptimization: no CameraParameters (addParameter + setParameterId)");
