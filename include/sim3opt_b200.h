@@ -212,7 +212,8 @@ int s3o_get_vertices(s3o_problem *p, double *est);
  *    tangent component (rad, m, log-scale).  The estimate comes from the accepted steps' max-norms s_k, which contract
  *    near the solution (the LM damps a weakly constrained mode by lambda / (mu + lambda) per iteration):
  *    s_k r / (1 - r) with r = s_k / s_(k-1) once r < 1/2, s_k itself before that.  Unlike a relative chi2 gain it does
- *    not depend on the size of the graph.
+ *    not depend on the size of the graph.  With inexact solves (PCG tolerance above 1e-4) the rule has to hold in two
+ *    consecutive iterations.
  *  min_rel_predicted_decrease: stop when a step's predicted decrease sum x_j (lambda x_j + b_j) falls below this
  *    fraction of chi2 -- from there on the fp64 chi2 sums cannot resolve the step, g2o's acceptance test
  *    rho = (chi2 - chi2_new) / predicted is decided by round-off and the LM only burns trials (1e-12 is about the

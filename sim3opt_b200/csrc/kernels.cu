@@ -375,14 +375,24 @@ __global__ void __launch_bounds__(NT, S3O_LIN_MINB) linearize_kernel(GraphDev g,
     double A[DD], B[DD], O[DIAG ? D : DD], e[D], P[DD];
     double out[SMAX];
     bool fi = false, fj = false;
+    int kb = -1, src = -1;      // off-diagonal block of this edge; its only source edge (or -1: summed by assemble_kernel)
     if (valid) {
+        // everything that does not depend on the vertex indices goes out with them: one round trip to DRAM
+        // covers the edge record, a second one the vertex states
         const int vi = g.sv0[t], vj = g.sv1[t];
+        if (Hdirect) kb = __ldg(e_blk + t);
+        double xi[EST], xj[EST], m[EST], qi[4], qj[4];
+        load_planes<EST>(g.meas, g.ne_pad, t, m);
+        if constexpr (DIAG) {
+#pragma unroll
+            for (int r = 0; r < D; ++r)
+                O[r] = g.info ? __ldg(g.info + (size_t)r * g.ne_pad + t) : 1.0;       // diagonal information: D planes
+        }
         fi = g.hidx[vi] >= 0;
         fj = g.hidx[vj] >= 0;
-        double xi[EST], xj[EST], m[EST], qi[4], qj[4];
         load_planes<EST>(g.est, g.nv_pad, vi, xi);
         load_planes<EST>(g.est, g.nv_pad, vj, xj);
-        load_planes<EST>(g.meas, g.ne_pad, t, m);
+        if (kb >= 0) src = __ldg(blk_src + kb);
         if constexpr (Model<KIND>::AUX) {
             load_planes<4>(g.aux, g.nv_pad, vi, qi);
             load_planes<4>(g.aux, g.nv_pad, vj, qj);
@@ -416,9 +426,6 @@ __global__ void __launch_bounds__(NT, S3O_LIN_MINB) linearize_kernel(GraphDev g,
         }
         // O' = rho1 * Omega (full symmetric, row-major; or its diagonal)
         if constexpr (DIAG) {
-#pragma unroll
-            for (int r = 0; r < D; ++r)
-                O[r] = g.info ? __ldg(g.info + (size_t)r * g.ne_pad + t) : 1.0;       // diagonal information: D planes
             if (g.robust_kind != S3O_ROBUST_NONE) {
                 double c2 = 0;
 #pragma unroll
@@ -498,11 +505,7 @@ __global__ void __launch_bounds__(NT, S3O_LIN_MINB) linearize_kernel(GraphDev g,
     // ---- cross term Hij = (A^T O') B
     double *cross_dst = rec0 + (size_t)lane * STRIDE + 2 * (NS + D);
     bool flip = false;         // stored block is (min,max): vertex(0) on the max side -> transpose
-    if (valid && Hdirect) {
-        const int kb = e_blk[t];
-        const int src = kb >= 0 ? blk_src[kb] : -1;
-        if (src >= 0) { cross_dst = Hdirect + (size_t)kb * DD; flip = (src & 1) != 0; }
-    }
+    if (src >= 0) { cross_dst = Hdirect + (size_t)kb * DD; flip = (src & 1) != 0; }
     if (valid) {
 #pragma unroll
         for (int r = 0; r < D; ++r)

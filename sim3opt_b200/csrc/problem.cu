@@ -1309,7 +1309,7 @@ int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterat
     const int nf = own_rows(p), d = p->d;
     const bool resume = p->lm_resume != 0 && p->lm_valid;
     double lambda = resume ? p->lm_lambda : 0, ni = resume ? p->lm_ni : 2, currentChi = resume ? p->lm_chi : 0;
-    if (!resume) { p->lm_prev_step = 0; p->lm_est_dist = 0; }
+    if (!resume) { p->lm_prev_step = 0; p->lm_est_dist = 0; p->lm_stop_hits = 0; }
     int done = 0;
     p->stats.ms_linearize = p->stats.ms_solve = p->stats.ms_chi2 = p->stats.ms_update = p->stats.ms_total = 0;
     cudaEventRecord(p->ev[0], p->stream);
@@ -1431,7 +1431,14 @@ int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterat
             if (gain >= 0 && gain < stop_rel_gain) { p->stats.stop_reason = 1; break; }
         }
         // step-size rule: the last accepted step moved no tangent component by more than stop_step
-        if (p->stop_step > 0 && rho > 0 && p->kind != S3O_KIND_BA && p->lm_est_dist < p->stop_step) { p->stats.stop_reason = 2; break; }
+        // After an INEXACT solve (PCG forcing tolerance) the step can fall short of the Newton step in the modes the
+        // preconditioner resolves worst, and the estimate with it (block-Jacobi at 0.2 stopped 1.3 mm early on the s10k
+        // sphere): such solves have to meet the rule in two consecutive iterations.
+        if (p->stop_step > 0 && rho > 0 && p->kind != S3O_KIND_BA) {
+            const bool exact = (p->linsolver != S3O_LINSOLVER_PCG && !p->dist && direct_available(p)) || p->pcg_tol <= 1e-4;
+            p->lm_stop_hits = p->lm_est_dist < p->stop_step ? p->lm_stop_hits + 1 : 0;
+            if (p->lm_stop_hits >= (exact ? 1 : 2)) { p->stats.stop_reason = 2; break; }
+        }
     }
     cudaEventRecord(p->ev[1], p->stream);
     S3O_CUDA(cudaStreamSynchronize(p->stream));

@@ -107,6 +107,7 @@ struct s3o_problem {
     bool lm_valid = false;
     double lm_lambda = 0, lm_ni = 2, lm_chi = 0;
     double lm_prev_step = 0, lm_est_dist = 0;   // step-size stop rule: previous accepted step, estimated distance left
+    int lm_stop_hits = 0;                       // consecutive accepted iterations that met the step-size rule
     double *d_est_snap = nullptr;
     double *d_stage = nullptr;             // AoS staging of the estimates (upload / download)
     // sampled SpMV timing

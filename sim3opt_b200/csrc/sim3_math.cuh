@@ -259,70 +259,142 @@ struct JlInv {
     double y[3];
 };
 
-static __device__ __noinline__ void sim3_jl_inv(const double e[7], JlInv &out) {
-    double Om[9], Up[9], M[9];
-    skew3(e[0], e[1], e[2], Om);
-    skew3(e[3], e[4], e[5], Up);
+// 1/(n+1)!, n = 0..79: the series coefficients (a table instead of one fp64 division per term; constant bank: the
+// loop counter is the index, so the access is uniform over the warp)
+static __constant__ double kInvFact1[80] = {
+    1.0, 0.5, 0.16666666666666666, 0.041666666666666664, 0.008333333333333333, 0.001388888888888889,
+    0.0001984126984126984, 2.48015873015873e-05, 2.7557319223985893e-06, 2.755731922398589e-07,
+    2.505210838544172e-08, 2.08767569878681e-09, 1.6059043836821613e-10, 1.1470745597729725e-11,
+    7.647163731819816e-13, 4.779477332387385e-14, 2.8114572543455206e-15, 1.5619206968586225e-16,
+    8.22063524662433e-18, 4.110317623312165e-19, 1.9572941063391263e-20, 8.896791392450574e-22,
+    3.868170170630684e-23, 1.6117375710961184e-24, 6.446950284384474e-26, 2.4795962632247976e-27,
+    9.183689863795546e-29, 3.279889237069838e-30, 1.1309962886447716e-31, 3.7699876288159054e-33,
+    1.216125041553518e-34, 3.8003907548547434e-36, 1.151633562077195e-37, 3.387157535521162e-39,
+    9.67759295863189e-41, 2.6882202662866363e-42, 7.265460179153071e-44, 1.911963205040282e-45,
+    4.902469756513544e-47, 1.2256174391283858e-48, 2.9893108271424046e-50, 7.117406731291439e-52,
+    1.6552108677421951e-53, 3.7618428812322616e-55, 8.359650847182804e-57, 1.817315401561479e-58,
+    3.866628513960594e-60, 8.055476070751236e-62, 1.643974708316579e-63, 3.287949416633158e-65,
+    6.446959640457172e-67, 1.2397999308571486e-68, 2.3392451525606576e-70, 4.331935467704922e-72,
+    7.876246304918039e-74, 1.4064725544496498e-75, 2.4674957095607893e-77, 4.254302947518602e-79,
+    7.2106829618959365e-81, 1.2017804936493226e-82, 1.9701319568021682e-84, 3.1776321883905942e-86,
+    5.043860616493007e-88, 7.881032213270323e-90, 1.2124664943492804e-91, 1.8370704459837581e-93,
+    2.74189618803546e-95, 4.0322002765227353e-97, 5.843768516699616e-99, 8.34824073814231e-101,
+    1.1758085546679308e-102, 1.633067437038793e-104, 2.2370786808750587e-106, 3.023079298479809e-108,
+    4.030772397973079e-110, 5.30364789206984e-112, 6.887854405285506e-114, 8.830582570878855e-116,
+    1.117795262136564e-117, 1.397244077670705e-119 };
+
+// out = w x (columns of A)  (= Om A, Om = skew(w))
+__device__ __forceinline__ void cross_cols(double x, double y, double z, const double A[9], double out[9]) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) M[i] = Om[i];
-    M[0] += e[6]; M[4] += e[6]; M[8] += e[6];
+    for (int j = 0; j < 3; ++j) {
+        out[j] = y * A[6 + j] - z * A[3 + j];
+        out[3 + j] = z * A[j] - x * A[6 + j];
+        out[6 + j] = x * A[3 + j] - y * A[j];
+    }
+}
+// out = (rows of A) x w  (= A Om)
+__device__ __forceinline__ void cross_rows(const double A[9], double x, double y, double z, double out[9]) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        out[i * 3] = A[i * 3 + 1] * z - A[i * 3 + 2] * y;
+        out[i * 3 + 1] = A[i * 3 + 2] * x - A[i * 3] * z;
+        out[i * 3 + 2] = A[i * 3] * y - A[i * 3 + 1] * x;
+    }
+}
+
+// The series runs on scalars: Om^3 = -theta^2 Om, so every block is a polynomial in Om --
+//   Om^n, M^n in span{I, Om, Om^2},   P_n = sum_ab p_ab(n) Om^a Up Om^b,  a, b in {0,1,2}
+// (left multiplication by M acts on the index a: (x0,x1,x2) -> (s x0, s x1 + x0 - th2 x2, s x2 + x1)).  One term
+// costs ~45 fp64 operations instead of three 3x3 products; the nine products Om^a Up Om^b are formed once.
+static __device__ __noinline__ void sim3_jl_inv(const double e[7], JlInv &out) {
+    const double sg = e[6];
     // Number of terms from a bound on the series tail instead of a per-term maximum over 30 entries:
     // |ad_e^n| <= a^n with a = |omega| + |upsilon| + |sigma| (row sums of the blocks), term n carries 1/(n+1)!.
     const double theta2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
-    const double a = sqrt(theta2) + sqrt(e[3] * e[3] + e[4] * e[4] + e[5] * e[5]) + fabs(e[6]);
+    const double a = sqrt(theta2) + sqrt(e[3] * e[3] + e[4] * e[4] + e[5] * e[5]) + fabs(sg);
     int nterms = 2;
-    {
-        double bound = a * 0.5;          // a^1 / 2!
-        while (bound * (1.0 + a) >= 1e-18 && nterms < 80) { bound *= a / (double)(nterms + 1); ++nterms; }
+    {   // (fp32 is plenty for a stopping bound; 1e-18 keeps the fp64 series exact to the last bit)
+        const float af = (float)a, lim = 1e-18f / (1.0f + af);
+        float bound = 0.5f * af;         // a^(nterms-1) / nterms!
+        while (bound >= lim && nterms < 80) { bound *= __fdividef(af, (float)(nterms + 1)); ++nterms; }
     }
-    // Om^n needs no product: Om^3 = -theta^2 Om, so Om^(n+2) = -theta^2 Om^n.
-    double Om2[9];
-    mat3_mul(Om, Om, Om2);
-    double Oa[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };      // Om^(n-1), alternating buffers: even powers / odd powers
-    double Ob[9];
+    double o0 = 1, o1 = 0, o2 = 0;       // Om^(n-1)
+    double m0 = 1, m1 = 0, m2 = 0;       // M^(n-1)
+    double p[3][3], q[3][3];             // P_(n-1), Q
 #pragma unroll
-    for (int i = 0; i < 9; ++i) Ob[i] = Om[i];
-    double Mn[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
-    double Pn[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
-    double vn[3] = { 0, 0, 0 };
-    double Jw[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
-    double W[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
-    double Q[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
-    double w[3] = { 0, 0, 0 };
-    double c = 1.0;
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { p[i][j] = 0; q[i][j] = 0; }
+    double j1 = 0, j2 = 0;               // Jw = I + j1 Om + j2 Om^2
+    double w0 = 1, w1 = 0, w2 = 0;       // W
+    double u0 = 0, u1 = 0, u2 = 0;       // sum_n c_n M^(n-1):  w = -(that) ups
     for (int n = 1; n < nterms; ++n) {
-        // entering: Oa = Om^(n-1), Ob = Om^n, Mn = M^(n-1), Pn = P_(n-1), vn = M^(n-2) ups
-        double T1[9], T2[9];
-        mat3_mul(M, Pn, T1);
-        mat3_mul(Up, Oa, T2);
+        const double c = kInvFact1[n];
+        const double ob[3] = { o0, o1, o2 };
 #pragma unroll
-        for (int i = 0; i < 9; ++i) Pn[i] = T1[i] + T2[i];
-        if (n == 1) {
-            vn[0] = e[3]; vn[1] = e[4]; vn[2] = e[5];
-        } else {
-            const double a0 = M[0] * vn[0] + M[1] * vn[1] + M[2] * vn[2];
-            const double a1 = M[3] * vn[0] + M[4] * vn[1] + M[5] * vn[2];
-            const double a2 = M[6] * vn[0] + M[7] * vn[1] + M[8] * vn[2];
-            vn[0] = a0; vn[1] = a1; vn[2] = a2;
+        for (int b = 0; b < 3; ++b) {    // P_n = M P_(n-1) + Up Om^(n-1)
+            const double t0 = sg * p[0][b] + ob[b];
+            const double t1 = sg * p[1][b] + (p[0][b] - theta2 * p[2][b]);
+            const double t2 = sg * p[2][b] + p[1][b];
+            p[0][b] = t0; p[1][b] = t1; p[2][b] = t2;
+            q[0][b] += c * t0; q[1][b] += c * t1; q[2][b] += c * t2;
         }
-        mat3_mul(M, Mn, T2);
-        c /= (double)(n + 1);
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-            Mn[i] = T2[i];
-            Jw[i] += c * Ob[i];              // Ob = Om^n
-            W[i] += c * Mn[i];
-            Q[i] += c * Pn[i];
-            const double next = n == 1 ? Om2[i] : -theta2 * Oa[i];      // Om^(n+1)
-            Oa[i] = Ob[i];
-            Ob[i] = next;
+        u0 += c * m0; u1 += c * m1; u2 += c * m2;
+        {   // M^n
+            const double t0 = sg * m0, t1 = sg * m1 + (m0 - theta2 * m2), t2 = sg * m2 + m1;
+            m0 = t0; m1 = t1; m2 = t2;
         }
+        {   // Om^n
+            const double t1 = o0 - theta2 * o2, t2 = o1;
+            o0 = 0; o1 = t1; o2 = t2;
+        }
+        j1 += c * o1; j2 += c * o2;
+        w0 += c * m0; w1 += c * m1; w2 += c * m2;
+    }
+    const double wx = e[0], wy = e[1], wz = e[2];
+    double Om[9], Om2[9], Up[9];
+    skew3(wx, wy, wz, Om);
+    skew3(e[3], e[4], e[5], Up);
+    {   // Om^2 = w w^T - theta^2 I
+        Om2[0] = wx * wx - theta2; Om2[1] = wx * wy;          Om2[2] = wx * wz;
+        Om2[3] = Om2[1];           Om2[4] = wy * wy - theta2; Om2[5] = wy * wz;
+        Om2[6] = Om2[2];           Om2[7] = Om2[5];           Om2[8] = wz * wz - theta2;
+    }
+    double Jw[9], W[9];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) w[i] -= c * vn[i];
+    for (int i = 0; i < 9; ++i) {
+        Jw[i] = j1 * Om[i] + j2 * Om2[i];
+        W[i] = w1 * Om[i] + w2 * Om2[i];
+    }
+    Jw[0] += 1; Jw[4] += 1; Jw[8] += 1;
+    W[0] += w0; W[4] += w0; W[8] += w0;
+    // Q = G0 + G1 Om + G2 Om^2,  G_b = sum_a q_ab Om^a Up
+    double U1[9], U2[9], G[9], T[9], T2[9], Q[9];
+    cross_cols(wx, wy, wz, Up, U1);
+    cross_cols(wx, wy, wz, U1, U2);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Q[i] = q[0][0] * Up[i] + q[1][0] * U1[i] + q[2][0] * U2[i];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) G[i] = q[0][1] * Up[i] + q[1][1] * U1[i] + q[2][1] * U2[i];
+    cross_rows(G, wx, wy, wz, T);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { Q[i] += T[i]; G[i] = q[0][2] * Up[i] + q[1][2] * U1[i] + q[2][2] * U2[i]; }
+    cross_rows(G, wx, wy, wz, T);
+    cross_rows(T, wx, wy, wz, T2);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Q[i] += T2[i];
+    // w = -(u0 I + u1 Om + u2 Om^2) ups
+    double w[3];
+    {
+        const double ux = e[3], uy = e[4], uz = e[5];
+        const double cx = wy * uz - wz * uy, cy = wz * ux - wx * uz, cz = wx * uy - wy * ux;     // Om ups
+        const double dx = wy * cz - wz * cy, dy = wz * cx - wx * cz, dz = wx * cy - wy * cx;     // Om^2 ups
+        w[0] = -(u0 * ux + u1 * cx + u2 * dx);
+        w[1] = -(u0 * uy + u1 * cy + u2 * dy);
+        w[2] = -(u0 * uz + u1 * cz + u2 * dz);
     }
     inv3(Jw, out.Jw);
     inv3(W, out.Wi);
-    double T[9];
     mat3_mul(out.Wi, Q, T);
     mat3_mul(T, out.Jw, out.X);
 #pragma unroll
