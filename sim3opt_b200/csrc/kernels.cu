@@ -12,6 +12,7 @@
 // Every global reduction writes one partial per CTA and lets the last CTA to arrive (integer
 // ticket) add the partials in index order, so results are bitwise reproducible run to run.
 #include <assert.h>
+#include <stdlib.h>
 
 #include "../../include/sim3opt_b200.h"
 #include "kernels.cuh"
@@ -97,7 +98,7 @@ __device__ __forceinline__ void from_sim3(const Sim3 &S, double x[8]) {
 // e = error(measurement m, vertex(0)=xi, vertex(1)=xj); qi/qj: fixed rotations (scale-trans only)
 // flags: bit 0 = S3O_MATH_CORRECTED (Sim3 coefficients), bit 1 = S3O_SCALE_MODEL_LOGRATIO (scale / scale-trans kinds)
 template <int KIND>
-__device__ __noinline__ void model_error(const double *m, const double *xi, const double *xj, const double *qi,
+__device__ S3O_ERR_INLINE void model_error(const double *m, const double *xi, const double *xj, const double *qi,
                                          const double *qj, double *e, int flags) {
     if constexpr (KIND == S3O_KIND_SIM3) {
         sim3_edge_error(to_sim3(m), to_sim3(xi), to_sim3(xj), e, (flags & 1) != 0);
@@ -311,11 +312,30 @@ __host__ __device__ constexpr int packed_size(int d) { return d * (d + 1) / 2; }
 __host__ __device__ constexpr int scr_stride(int d) { return 2 * (packed_size(d) + d) + d * d; }
 int scratch_stride(int d) { return scr_stride(d); }
 
+// The warp's staging buffer holds S values per edge (edge-major); they leave as one coalesced stream into the
+// per-edge records (stride doubles apart).  Full warps with S >= 32: round i moves the values 32 i .. 32 i + 31, which
+// belong to at most two edges -- the split point is a compile-time constant, so there is no division in the loop.
+// The warp's staging buffer holds S values per edge (edge-major); they leave as one coalesced stream into the
+// per-edge records (stride doubles apart).  The (edge, entry) pair of a lane advances by 32 entries per round: no
+// division in the loop.  The loops stay rolled on purpose: this kernel is bound by instruction fetch as soon as
+// its straight-line code grows (unrolling them cost 10 % although it saved 11 % of the instructions).
 template <int S>
-__device__ __forceinline__ void warp_store_piece(double *stage, const double *vals, double *__restrict__ dst0,
-                                                 int stride, int lane, int nvalid) {
-#pragma unroll
-    for (int f = 0; f < S; ++f) stage[lane * S + f] = vals[f];
+__device__ __forceinline__ void warp_copy_piece(const double *stage, double *__restrict__ dst0, int stride, int lane, int nvalid) {
+    static_assert(S >= 32, "one wrap per round");
+    __syncwarp();
+    int el = 0, f = lane;
+    if (f >= S) { f -= S; el = 1; }
+    const int n = nvalid * S;
+#pragma unroll 1
+    for (int idx = lane; idx < n; idx += 32) {
+        dst0[el * stride + f] = stage[idx];
+        f += 32;
+        if (f >= S) { f -= S; ++el; }
+    }
+    __syncwarp();
+}
+template <int S>
+__device__ __forceinline__ void warp_copy_piece_small(const double *stage, double *__restrict__ dst0, int stride, int lane, int nvalid) {
     __syncwarp();
     for (int idx = lane; idx < nvalid * S; idx += 32) {
         const int el = idx / S, f = idx - el * S;
@@ -326,15 +346,24 @@ __device__ __forceinline__ void warp_store_piece(double *stage, const double *va
 
 // same, but every element of the warp has its own destination (dptr[el], staged in shared memory)
 template <int S>
-__device__ __forceinline__ void warp_store_piece_to(double *stage, const double *vals, double **dptr, double *mine,
-                                                    int lane, int nvalid) {
-#pragma unroll
-    for (int f = 0; f < S; ++f) stage[lane * S + f] = vals[f];
+__device__ __forceinline__ void warp_copy_piece_to(const double *stage, double **dptr, double *mine, int lane, int nvalid) {
     dptr[lane] = mine;
     __syncwarp();
-    for (int idx = lane; idx < nvalid * S; idx += 32) {
-        const int el = idx / S, f = idx - el * S;
-        dptr[el][f] = stage[idx];
+    if constexpr (S >= 32) {
+        int el = 0, f = lane;
+        if (f >= S) { f -= S; el = 1; }
+        const int n = nvalid * S;
+#pragma unroll 1
+        for (int idx = lane; idx < n; idx += 32) {
+            dptr[el][f] = stage[idx];
+            f += 32;
+            if (f >= S) { f -= S; ++el; }
+        }
+    } else {
+        for (int idx = lane; idx < nvalid * S; idx += 32) {
+            const int el = idx / S, f = idx - el * S;
+            dptr[el][f] = stage[idx];
+        }
     }
     __syncwarp();
 }
@@ -350,8 +379,9 @@ __device__ __forceinline__ constexpr bool jnz(int k, int c) { return !SP || (k <
 // DIAG: the information matrices are diagonal (or absent = identity): Omega' is held as D weights, A^T O' and
 // B^T O' are column scalings -- same numbers as the dense path (its extra terms are exact zeros), 2 of the 5
 // 7x7x7 products and a 49-double array less.
+// 6 CTAs of 64 threads per SM: 168 registers, no spills worth the name (244 at one CTA; 128 spills 0.5 KB)
 #ifndef S3O_LIN_MINB
-#define S3O_LIN_MINB 1
+#define S3O_LIN_MINB 6
 #endif
 template <int KIND, int JAC, int NT, bool DIAG>
 __global__ void __launch_bounds__(NT, S3O_LIN_MINB) linearize_kernel(GraphDev g, double h, double *__restrict__ scratch,
@@ -372,8 +402,7 @@ __global__ void __launch_bounds__(NT, S3O_LIN_MINB) linearize_kernel(GraphDev g,
     const bool valid = t < g.ne;
     const int nvalid = min(32, g.ne - e0);
 
-    double A[DD], B[DD], O[DIAG ? D : DD], e[D], P[DD];
-    double out[SMAX];
+    double A[DD], B[DD], O[DIAG ? D : DD], e[D];
     bool fi = false, fj = false;
     int kb = -1, src = -1;      // off-diagonal block of this edge; its only source edge (or -1: summed by assemble_kernel)
     if (valid) {
@@ -469,94 +498,72 @@ __global__ void __launch_bounds__(NT, S3O_LIN_MINB) linearize_kernel(GraphDev g,
         }
     }
     double *rec0 = scratch + (size_t)e0 * STRIDE;
-    // ---- vertex(0) side: P = A^T O'
-    if (valid) {
+    // Row r of J^T O' (J = A or B) -- recomputed where it is needed (a column scaling when the information is diagonal)
+    // instead of a 49-entry array kept across the three products.
+    auto jto_row = [&](const double *J, int r, double *Pr) {
 #pragma unroll
-        for (int r = 0; r < D; ++r)
-#pragma unroll
-            for (int c = 0; c < D; ++c) {
-                double acc = 0;
-                if constexpr (DIAG) { if (jnz<SP>(c, r)) acc = A[c * D + r] * O[c]; }
-                else {
-#pragma unroll
-                    for (int k = 0; k < D; ++k) if (jnz<SP>(k, r)) acc += A[k * D + r] * O[k * D + c];
-                }
-                P[r * D + c] = acc;
-            }
-        int f = 0;
-#pragma unroll
-        for (int r = 0; r < D; ++r)
-#pragma unroll
-            for (int c = r; c < D; ++c) {
-                double acc = 0;
-#pragma unroll
-                for (int k = 0; k < D; ++k) if ((!DIAG || jnz<SP>(k, r)) && jnz<SP>(k, c)) acc += P[r * D + k] * A[k * D + c];
-                out[f++] = acc;
-            }
-#pragma unroll
-        for (int r = 0; r < D; ++r) {
+        for (int c = 0; c < D; ++c) {
             double acc = 0;
+            if constexpr (DIAG) { if (jnz<SP>(c, r)) acc = J[c * D + r] * O[c]; }
+            else {
 #pragma unroll
-            for (int k = 0; k < D; ++k) if (!DIAG || jnz<SP>(k, r)) acc += P[r * D + k] * e[k];
-            out[NS + r] = -acc;
+                for (int k = 0; k < D; ++k) if (jnz<SP>(k, r)) acc += J[k * D + r] * O[k * D + c];
+            }
+            Pr[c] = acc;
         }
-    }
-    warp_store_piece<NS + D>(stage, out, rec0, STRIDE, lane, nvalid);
+    };
+    // Every product row goes to the staging buffer as soon as it is formed: at most one row of accumulators is live.
+    // [J^T O' J packed | -J^T O' e] of one side
+    auto side_piece = [&](const double *J) {
+        if (valid) {
+            double *mine = stage + lane * (NS + D);
+            int f = 0;
+#pragma unroll
+            for (int r = 0; r < D; ++r) {
+                double Pr[D];
+                jto_row(J, r, Pr);
+#pragma unroll
+                for (int c = r; c < D; ++c) {
+                    double acc = 0;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) if ((!DIAG || jnz<SP>(k, r)) && jnz<SP>(k, c)) acc += Pr[k] * J[k * D + c];
+                    mine[f++] = acc;
+                }
+                double acc = 0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) if (!DIAG || jnz<SP>(k, r)) acc += Pr[k] * e[k];
+                mine[NS + r] = -acc;
+            }
+        }
+    };
+    // ---- vertex(0) side
+    side_piece(A);
+    if constexpr (NS + D >= 32) warp_copy_piece<NS + D>(stage, rec0, STRIDE, lane, nvalid);
+    else warp_copy_piece_small<NS + D>(stage, rec0, STRIDE, lane, nvalid);
     // ---- cross term Hij = (A^T O') B
     double *cross_dst = rec0 + (size_t)lane * STRIDE + 2 * (NS + D);
     bool flip = false;         // stored block is (min,max): vertex(0) on the max side -> transpose
     if (src >= 0) { cross_dst = Hdirect + (size_t)kb * DD; flip = (src & 1) != 0; }
     if (valid) {
-#pragma unroll
-        for (int r = 0; r < D; ++r)
-#pragma unroll
-            for (int c = 0; c < D; ++c) {
-                double acc = 0;
-#pragma unroll
-                for (int k = 0; k < D; ++k) if ((!DIAG || jnz<SP>(k, r)) && jnz<SP>(k, c)) acc += P[r * D + k] * B[k * D + c];
-                out[r * D + c] = acc;
-            }
-        if (flip) {
-#pragma unroll
-            for (int r = 0; r < D; ++r)
-#pragma unroll
-                for (int c = r + 1; c < D; ++c) { const double tmp = out[r * D + c]; out[r * D + c] = out[c * D + r]; out[c * D + r] = tmp; }
-        }
-    }
-    warp_store_piece_to<DD>(stage, out, dptr, cross_dst, lane, nvalid);
-    // ---- vertex(1) side: P = B^T O'
-    if (valid) {
-#pragma unroll
-        for (int r = 0; r < D; ++r)
-#pragma unroll
-            for (int c = 0; c < D; ++c) {
-                double acc = 0;
-                if constexpr (DIAG) { if (jnz<SP>(c, r)) acc = B[c * D + r] * O[c]; }
-                else {
-#pragma unroll
-                    for (int k = 0; k < D; ++k) if (jnz<SP>(k, r)) acc += B[k * D + r] * O[k * D + c];
-                }
-                P[r * D + c] = acc;
-            }
-        int f = 0;
-#pragma unroll
-        for (int r = 0; r < D; ++r)
-#pragma unroll
-            for (int c = r; c < D; ++c) {
-                double acc = 0;
-#pragma unroll
-                for (int k = 0; k < D; ++k) if ((!DIAG || jnz<SP>(k, r)) && jnz<SP>(k, c)) acc += P[r * D + k] * B[k * D + c];
-                out[f++] = acc;
-            }
+        double *mine = stage + lane * DD;
 #pragma unroll
         for (int r = 0; r < D; ++r) {
-            double acc = 0;
+            double Pr[D];
+            jto_row(A, r, Pr);
 #pragma unroll
-            for (int k = 0; k < D; ++k) if (!DIAG || jnz<SP>(k, r)) acc += P[r * D + k] * e[k];
-            out[NS + r] = -acc;
+            for (int c = 0; c < D; ++c) {
+                double acc = 0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) if ((!DIAG || jnz<SP>(k, r)) && jnz<SP>(k, c)) acc += Pr[k] * B[k * D + c];
+                mine[flip ? c * D + r : r * D + c] = acc;
+            }
         }
     }
-    warp_store_piece<NS + D>(stage, out, rec0 + (NS + D), STRIDE, lane, nvalid);
+    warp_copy_piece_to<DD>(stage, dptr, cross_dst, lane, nvalid);
+    // ---- vertex(1) side
+    side_piece(B);
+    if constexpr (NS + D >= 32) warp_copy_piece<NS + D>(stage, rec0 + (NS + D), STRIDE, lane, nvalid);
+    else warp_copy_piece_small<NS + D>(stage, rec0 + (NS + D), STRIDE, lane, nvalid);
 }
 
 void launch_linearize(const GraphDev &g, int jac_mode, double h, double *scratch, const int32_t *e_blk,

