@@ -306,7 +306,9 @@ void launch_edge_errors(const GraphDev &g, double *err, double *chi, cudaStream_
 // ======================================================================================
 // linearize: per-edge Jacobians and quadratic-form products
 // ======================================================================================
-// Per-edge scratch record (doubles):  [Hii packed NS | bi D | Hjj packed NS | bj D | Hij D*D]
+// Scratch (doubles): side records [ne_pad][Hii packed NS | bi D | Hjj packed NS | bj D], one contiguous stream in edge order
+// (entry e of an incidence list, 2*edge + side, is piece e), followed by the cross terms [ne_pad][Hij D*D] -- only the
+// edges of multi-edge blocks write theirs, every other cross term goes straight into the Hessian.
 // Hii = A^T O' A, bi = -A^T O' e, Hjj = B^T O' B, bj = -B^T O' e, Hij = A^T O' B, O' = rho1 * Omega.
 __host__ __device__ constexpr int packed_size(int d) { return d * (d + 1) / 2; }
 __host__ __device__ constexpr int scr_stride(int d) { return 2 * (packed_size(d) + d) + d * d; }
@@ -388,7 +390,7 @@ __global__ void __launch_bounds__(NT, S3O_LIN_MINB) linearize_kernel(GraphDev g,
                                                        const int32_t *__restrict__ e_blk,
                                                        const int32_t *__restrict__ blk_src, double *__restrict__ Hdirect) {
     constexpr int D = Model<KIND>::D, EST = Model<KIND>::EST, DD = D * D;
-    constexpr int NS = packed_size(D), STRIDE = scr_stride(D);
+    constexpr int NS = packed_size(D), STRIDE = 2 * (NS + D);       // the two side pieces of an edge are one record
     constexpr int SMAX = DD > NS + D ? DD : NS + D;
     constexpr bool SP = KIND == S3O_KIND_SIM3 && JAC == S3O_JAC_ANALYTIC;      // structured Jacobians
     __shared__ double stage_all[(NT / 32) * 32 * SMAX];
@@ -541,7 +543,7 @@ __global__ void __launch_bounds__(NT, S3O_LIN_MINB) linearize_kernel(GraphDev g,
     if constexpr (NS + D >= 32) warp_copy_piece<NS + D>(stage, rec0, STRIDE, lane, nvalid);
     else warp_copy_piece_small<NS + D>(stage, rec0, STRIDE, lane, nvalid);
     // ---- cross term Hij = (A^T O') B
-    double *cross_dst = rec0 + (size_t)lane * STRIDE + 2 * (NS + D);
+    double *cross_dst = scratch + (size_t)g.ne_pad * STRIDE + (size_t)t * DD;
     bool flip = false;         // stored block is (min,max): vertex(0) on the max side -> transpose
     if (src >= 0) { cross_dst = Hdirect + (size_t)kb * DD; flip = (src & 1) != 0; }
     if (valid) {
@@ -594,59 +596,63 @@ void launch_linearize(const GraphDev &g, int jac_mode, double h, double *scratch
 template <int D>
 __global__ void assemble_kernel(GraphDev g, StructDev s, const double *__restrict__ scratch, double *__restrict__ H,
                                 double *__restrict__ b) {
-    constexpr int DD = D * D, NS = packed_size(D), STRIDE = scr_stride(D), EL = DD + D;
-    // work items: the nf diagonal blocks (+ b), then the few off-diagonal blocks fed by more than one edge;
-    // single-edge off-diagonal blocks were written in place by linearize_kernel
+    constexpr int DD = D * D, NS = packed_size(D), SIDE = NS + D;
+    // work items: SIDE per diagonal block (one per PACKED entry of the symmetric block, which it writes to both
+    // triangles, and one per entry of b), then D*D per off-diagonal block fed by more than one edge; single-edge
+    // off-diagonal blocks were written in place by linearize_kernel
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long w64 = tid / EL;
-    if (w64 >= (long long)g.nf + s.n_multi) return;
-    const int w = (int)w64, el = (int)(tid - w64 * EL);
-    const int k = w < g.nf ? s.rowptr[w] : s.multi_blk[w - g.nf];
-    const int row = w < g.nf ? w : s.blk_row[k];
-    if (w < g.nf) {
-        int off;
-        if (el < DD) {
-            const int r = el / D, c = el - r * D;
-            const int lo = r < c ? r : c, hi = r < c ? c : r;
-            off = lo * D - (lo * (lo - 1)) / 2 + (hi - lo);
-        } else {
-            off = NS + (el - DD);
-        }
+    const long long n_diag = (long long)g.nf * SIDE;
+    if (tid < n_diag) {
+        const int row = (int)(tid / SIDE), f = (int)(tid - (long long)row * SIDE);
+        const double *src = scratch + f;
         double acc = 0;
         const int ib = s.inc_ptr[row], ie = s.inc_ptr[row + 1];
         int n = ib;
-        for (; n + 4 <= ie; n += 4) {     // four independent loads in flight, summed in list order
-            const int e0 = s.inc_ent[n], e1 = s.inc_ent[n + 1], e2 = s.inc_ent[n + 2], e3 = s.inc_ent[n + 3];
-            const double v0 = scratch[(size_t)(e0 >> 1) * STRIDE + (e0 & 1) * (NS + D) + off];
-            const double v1 = scratch[(size_t)(e1 >> 1) * STRIDE + (e1 & 1) * (NS + D) + off];
-            const double v2 = scratch[(size_t)(e2 >> 1) * STRIDE + (e2 & 1) * (NS + D) + off];
-            const double v3 = scratch[(size_t)(e3 >> 1) * STRIDE + (e3 & 1) * (NS + D) + off];
-            acc += v0; acc += v1; acc += v2; acc += v3;
+        for (; n + 8 <= ie; n += 8) {     // eight independent loads in flight, summed in list order
+            double v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = src[(size_t)s.inc_ent[n + q] * SIDE];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc += v[q];
         }
-        for (; n < ie; ++n) {
-            const int ent = s.inc_ent[n];
-            acc += scratch[(size_t)(ent >> 1) * STRIDE + (ent & 1) * (NS + D) + off];
+        for (; n + 2 <= ie; n += 2) {
+            const double v0 = src[(size_t)s.inc_ent[n] * SIDE], v1 = src[(size_t)s.inc_ent[n + 1] * SIDE];
+            acc += v0; acc += v1;
         }
-        if (el < DD) H[(size_t)k * DD + el] = acc;
-        else b[(size_t)row * D + (el - DD)] = acc;
-    } else if (el < DD) {
-        const int r = el / D, c = el - r * D;
-        double acc = 0;
-        const int eb = s.blk_ebeg[k], ee = s.blk_eend[k];
-        for (int t = eb; t < ee; ++t) {
-            // stored block is (min,max); when vertex(0) is the max side the edge's A^T O' B is its transpose
-            const bool transposed = g.hidx[g.sv0[t]] > g.hidx[g.sv1[t]];
-            acc += scratch[(size_t)t * STRIDE + 2 * (NS + D) + (transposed ? c * D + r : r * D + c)];
+        if (n < ie) acc += src[(size_t)s.inc_ent[n] * SIDE];
+        if (f < NS) {
+            int r = 0, c = f;           // packed upper triangle, row-major: row r holds D - r entries
+            while (c >= D - r) { c -= D - r; ++r; }
+            c += r;
+            double *blk = H + (size_t)s.rowptr[row] * DD;
+            blk[r * D + c] = acc;
+            if (r != c) blk[c * D + r] = acc;
+        } else {
+            b[(size_t)row * D + (f - NS)] = acc;
         }
-        H[(size_t)k * DD + el] = acc;
+        return;
     }
+    const long long m = tid - n_diag;
+    const long long w = m / DD;
+    if (w >= s.n_multi) return;
+    const int el = (int)(m - w * DD);
+    const int k = s.multi_blk[w];
+    const int r = el / D, c = el - r * D;
+    double acc = 0;
+    const int eb = s.blk_ebeg[k], ee = s.blk_eend[k];
+    const double *cross = scratch + (size_t)g.ne_pad * (2 * SIDE);
+    for (int t = eb; t < ee; ++t) {
+        // stored block is (min,max); when vertex(0) is the max side the edge's A^T O' B is its transpose
+        const bool transposed = g.hidx[g.sv0[t]] > g.hidx[g.sv1[t]];
+        acc += cross[(size_t)t * DD + (transposed ? c * D + r : r * D + c)];
+    }
+    H[(size_t)k * DD + el] = acc;
 }
 
 void launch_assemble(const GraphDev &g, const StructDev &s, const double *scratch, double *H, double *b,
                      cudaStream_t st) {
     if (g.nb == 0) return;
-    const int el = g.d * g.d + g.d;
-    const long long total = ((long long)g.nf + s.n_multi) * el;
+    const long long total = (long long)g.nf * (packed_size(g.d) + g.d) + (long long)s.n_multi * g.d * g.d;
     const int grid = (int)((total + 255) / 256);
     switch (g.d) {
     case 7: assemble_kernel<7><<<grid, 256, 0, st>>>(g, s, scratch, H, b); break;
