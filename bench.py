@@ -425,6 +425,22 @@ def config_subrecords(args, s3, synth, device, threads, peak):
                         "gpu": {"wall_s": wall, "setup_s": t_setup, "lm_iterations": n, "final_chi2": chis[-1],
                                 "pcg_iterations": int(hist[:, 4].sum()), "lm_iterations_per_s": n / wall}, "cpu": None}
         del p
+        # the same graph in the reference's AS-WRITTEN math (sim3_rv.h:165,:291; S3O_MATH_REFERENCE): the record behind
+        # DESIGN.md section 2's statement that the synthetic configs need the corrected coefficients
+        p = s3.Problem(s3.KIND_SIM3, device=device)
+        configure(p, args, s3)
+        p.set_math_mode(s3.MATH_REFERENCE)
+        p.set_vertices(g["est"], g["fixed"])
+        p.set_edges(g["v0"], g["v1"], g["meas"], g["info"])
+        p.build_structure()
+        n_r, chi_r, _, hist_r = p.optimize(len(chis) + 10, 0.0)
+        out["s100k"]["reference_math_mode"] = {
+            "lm_iterations": n_r, "final_chi2": chi_r, "chi2_history": [float(v) for v in hist_r[:n_r, 0]],
+            "lm_trials": [int(v) for v in hist_r[:n_r, 2]], "stop_reason": p.stats().get("stop_reason"),
+            "chi2_vs_corrected": chi_r / chis[-1],
+            "note": "as-written small-angle branch (B without the -1, R = I + Om + Om^2): compare chi2_history and lm_trials with the "
+                    "corrected run of the same graph; tests/test_oracle.py shows the CPU oracle behaving the same way"}
+        del p
     # ---- configs[4]: Ladybug-size synthetic BA (1000 cameras, 500k points, ~5M observations), 10 LM iterations
     gb = synth.ba_loop(1000, 500000, 10, seed=args.seed)
     b = s3.BAProblem(device=device)

@@ -381,12 +381,13 @@ __device__ __forceinline__ constexpr bool jnz(int k, int c) { return !SP || (k <
 // DIAG: the information matrices are diagonal (or absent = identity): Omega' is held as D weights, A^T O' and
 // B^T O' are column scalings -- same numbers as the dense path (its extra terms are exact zeros), 2 of the 5
 // 7x7x7 products and a 49-double array less.
-// 6 CTAs of 64 threads per SM: 168 registers, no spills worth the name (244 at one CTA; 128 spills 0.5 KB)
+// 6 CTAs of 64 threads per SM: 168 registers, no spills worth the name (244 at one CTA; 128 spills 0.5 KB).  The
+// dense-information and numeric-Jacobian instantiations keep all registers (they would spill 0.7-1.3 KB).
 #ifndef S3O_LIN_MINB
 #define S3O_LIN_MINB 6
 #endif
 template <int KIND, int JAC, int NT, bool DIAG>
-__global__ void __launch_bounds__(NT, S3O_LIN_MINB) linearize_kernel(GraphDev g, double h, double *__restrict__ scratch,
+__global__ void __launch_bounds__(NT, (DIAG && JAC == S3O_JAC_ANALYTIC) ? S3O_LIN_MINB : 1) linearize_kernel(GraphDev g, double h, double *__restrict__ scratch,
                                                        const int32_t *__restrict__ e_blk,
                                                        const int32_t *__restrict__ blk_src, double *__restrict__ Hdirect) {
     constexpr int D = Model<KIND>::D, EST = Model<KIND>::EST, DD = D * D;
