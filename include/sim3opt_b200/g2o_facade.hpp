@@ -282,7 +282,9 @@ public:
     virtual ~LinearSolver() {}
     virtual bool init() { return true; }
 };
-// The reference's choice (SimplicialLDLT).  Here: a tag -- the solve is the on-device PCG.
+// The reference's choice (SimplicialLDLT).  Here: a tag -- SparseOptimizer::optimize hands the whole LM to the device
+// library, which picks its sparse block Cholesky or the multilevel PCG (s3o_set_linear_solver).  A LinearSolver that
+// plugs into a REAL g2o block solver is in INTEGRATION.md (LinearSolverS3O over s3o_linsolver_solve).
 template <class MatrixType>
 class LinearSolverEigen : public LinearSolver<MatrixType> {};
 template <class MatrixType>
