@@ -624,11 +624,17 @@ def run_ours(args):
     # ---- end-to-end: host estimates in, host estimates out, every step ------------------------
     # Same LM-iteration sequence as the timed region above (complete solves from the initial guess), but the
     # estimates live in pinned HOST memory between steps.
-    est_host = torch.empty((nv, 8), dtype=torch.float64).pin_memory()
-    est0_host = torch.empty((nv, 8), dtype=torch.float64).pin_memory()
-    est_np, est0_np = est_host.numpy(), est0_host.numpy()
+    # Partitioned job: every rank's host moves its SLICE of the estimates (even split of the vertex ids), the slices are
+    # all-gathered over NVLink inside s3o_set_estimates_slice -- the job as a whole still moves nv * 64 bytes each way.
+    sliced = world > 1
+    s_first, s_count = prob.estimate_slice() if sliced else (0, nv)
+    est_host = torch.empty((max(s_count, 1), 8), dtype=torch.float64).pin_memory()
+    est0_host = torch.empty((max(s_count, 1), 8), dtype=torch.float64).pin_memory()
+    est_np, est0_np = est_host.numpy()[:s_count], est0_host.numpy()[:s_count]
+    put = prob.set_estimates_slice if sliced else prob.set_estimates
+    get = (lambda out: prob.vertices_slice(out)) if sliced else (lambda out: prob.vertices(out=out))
     prob.restore_estimates()
-    prob.vertices(out=est0_np)
+    get(est0_np)
     e2e_steps = args.steps
     prob.set_lm_resume(2)                   # keep lambda/nu across the host round trip of the estimates
     in_solve, last_chi = 0, None
@@ -638,11 +644,11 @@ def run_ours(args):
     for k in range(e2e_steps):
         if in_solve == 0:
             prob.restore_estimates()        # drops the LM state: lambda is re-initialised
-            prob.set_estimates(est0_np)     # H2D from pinned host memory
+            put(est0_np)                    # H2D from pinned host memory
         else:
-            prob.set_estimates(est_np)
+            put(est_np)
         n_, chi2_, lam_, _h = prob.optimize(1, 0.0)
-        prob.vertices(out=est_np)           # D2H of the step's result
+        get(est_np)                         # D2H of the step's result
         e2e_trace.append([float(v) for v in np.asarray(_h).reshape(-1)[:5]] + [time.perf_counter() - t0])
         in_solve += 1
         conv = converged(_h, chi2_, last_chi)
@@ -770,7 +776,10 @@ def run_ours(args):
                    "multilevel_levels": int(st["multilevel_levels"]), "pcg_unconverged_solves": int(st["pcg_unconverged"])},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "LM iterations/s", "h2d_bytes_per_step": nv * 64, "d2h_bytes_per_step": nv * 64 + 160,
-                "steps": e2e_steps},
+                "steps": e2e_steps,
+                "how": ("whole job: each rank's host moves its 1/%d slice of the estimates (s3o_set_estimates_slice / "
+                        "s3o_get_vertices_slice), the slices are all-gathered over NVLink" % world) if world > 1 else
+                       "s3o_set_estimates / s3o_optimize(1) / s3o_get_vertices every step, pinned host buffers"},
         "gpu_launches": int(st["kernel_launches"]),
         "roofline": roof,
         "roofline_phases": phases,

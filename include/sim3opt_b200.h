@@ -207,6 +207,14 @@ int s3o_smallest_eigenvector(s3o_problem *p, int max_iter, double tol, double *x
 int s3o_optimize(s3o_problem *p, int max_iter, double stop_rel_gain, int *iterations,
                  double *final_chi2, double *final_lambda, double *hist, int hist_cap);
 int s3o_get_vertices(s3o_problem *p, double *est);
+/* Partitioned solve (s3o_set_comm): the host round trip of the estimates, sharded over the ranks.  Every rank keeps all
+ * estimates on its device, but its host only moves the slice [first, first + count) of the vertex ids that
+ * s3o_estimate_slice reports (the even split; the whole range without a communicator).  s3o_set_estimates_slice is
+ * COLLECTIVE: the slices are all-gathered over NVLink.  s3o_get_vertices_slice is local.  Same LM-state semantics as
+ * s3o_set_estimates. */
+int s3o_estimate_slice(s3o_problem *p, int *first, int *count);
+int s3o_set_estimates_slice(s3o_problem *p, const double *est_slice);
+int s3o_get_vertices_slice(s3o_problem *p, double *est_slice);
 /* Optional stop rules of s3o_optimize (g2o's optimize() has none; 0 switches a rule off):
  *  max_abs_step (pose-graph kinds): stop once the estimated distance to the stationary point is below it in every
  *    tangent component (rad, m, log-scale).  The estimate comes from the accepted steps' max-norms s_k, which contract

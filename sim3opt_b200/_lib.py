@@ -75,6 +75,9 @@ SYMBOLS = {
     "s3o_smallest_eigenvector": (C.c_int, [C.c_void_p, C.c_int, C.c_double, _dp, _dp, _dp, C.POINTER(C.c_int)]),
     "s3o_optimize": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_int), _dp, _dp, _dp, C.c_int]),
     "s3o_get_vertices": (C.c_int, [C.c_void_p, _dp]),
+    "s3o_estimate_slice": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "s3o_set_estimates_slice": (C.c_int, [C.c_void_p, _dp]),
+    "s3o_get_vertices_slice": (C.c_int, [C.c_void_p, _dp]),
     "s3o_set_lm_resume": (C.c_int, [C.c_void_p, C.c_int]),
     "s3o_snapshot_estimates": (C.c_int, [C.c_void_p]),
     "s3o_restore_estimates": (C.c_int, [C.c_void_p]),

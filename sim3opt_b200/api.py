@@ -100,6 +100,22 @@ class Problem:
         est = _f64(est).reshape(self.nv, self.est_dim)
         self._check(self.L.s3o_set_estimates(self.h, _d(est)))
 
+    # ---- sharded host round trip of the estimates in the partitioned solve (s3o_*_slice)
+    def estimate_slice(self):
+        first, count = C.c_int(0), C.c_int(0)
+        self._check(self.L.s3o_estimate_slice(self.h, C.byref(first), C.byref(count)))
+        return first.value, count.value
+
+    def set_estimates_slice(self, est_slice):
+        """Collective: this rank's slice (estimate_slice()) of the caller-ordered estimates, C-contiguous float64."""
+        assert est_slice.dtype == np.float64 and est_slice.flags["C_CONTIGUOUS"]
+        self._check(self.L.s3o_set_estimates_slice(self.h, _d(est_slice)))
+
+    def vertices_slice(self, out):
+        assert out.dtype == np.float64 and out.flags["C_CONTIGUOUS"]
+        self._check(self.L.s3o_get_vertices_slice(self.h, _d(out)))
+        return out
+
     def set_robust(self, kind, param=0.0): self._check(self.L.s3o_set_robust(self.h, kind, float(param)))
     def set_jacobian_mode(self, mode, h=0.0): self._check(self.L.s3o_set_jacobian_mode(self.h, mode, float(h)))
     def set_math_mode(self, mode): self._check(self.L.s3o_set_math_mode(self.h, int(mode)))

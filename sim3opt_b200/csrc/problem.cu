@@ -756,6 +756,70 @@ int s3o_set_estimates(s3o_problem *p, const double *est) {
     return upload_estimates(p, est);
 }
 
+// ---- sharded host round trip of the estimates (partitioned solve) -------------------------------
+// Every rank keeps ALL estimates on its device (cut edges, retraction), but the host side of a rank only has to move
+// its share: the even split of the vertex ids.  Slices are all-gathered over NVLink into the staging buffer.
+static void estimate_slice(const s3o_problem *p, int rank, int *first, int *count) {
+    const int world = p->dist ? p->comm.world : 1;
+    const int per = (p->nv + world - 1) / world;
+    const int f = std::min(p->nv, rank * per);
+    *first = f;
+    *count = std::max(0, std::min(per, p->nv - f));
+}
+
+int s3o_estimate_slice(s3o_problem *p, int *first, int *count) {
+    if (!p || !first || !count || p->kind == S3O_KIND_BA) { set_error("s3o_estimate_slice: bad arguments"); return S3O_ERR_INVALID; }
+    estimate_slice(p, p->dist ? p->comm.rank : 0, first, count);
+    return S3O_OK;
+}
+
+int s3o_set_estimates_slice(s3o_problem *p, const double *est_slice) {
+    if (!p || p->kind == S3O_KIND_BA || !p->d_est[0]) { set_error("s3o_set_estimates_slice: call s3o_set_vertices first"); return S3O_ERR_INVALID; }
+    cudaSetDevice(p->device);
+    p->linearized = false;
+    if (p->lm_resume != 2) { p->lm_valid = false; p->auto_multilevel = false; }
+    int rc = ensure_stage(p);
+    if (rc) return rc;
+    const int world = p->dist ? p->comm.world : 1, rank = p->dist ? p->comm.rank : 0;
+    int first = 0, count = 0;
+    estimate_slice(p, rank, &first, &count);
+    if (count > 0 && !est_slice) { set_error("s3o_set_estimates_slice: null slice"); return S3O_ERR_INVALID; }
+    const size_t ed = (size_t)p->est_dim;
+    if (count > 0) S3O_CUDA(cudaMemcpyAsync(p->d_stage + first * ed, est_slice, count * ed * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    if (world > 1) {
+        std::vector<size_t> off(world), cnt(world);
+        for (int q = 0; q < world; ++q) {
+            int f = 0, c = 0;
+            estimate_slice(p, q, &f, &c);
+            off[q] = f * ed;
+            cnt[q] = c * ed;
+        }
+        if (comm_allgatherv(p->comm, p->d_stage, off.data(), cnt.data(), p->stream)) { set_error("%s", comm_last_error()); return S3O_ERR_NCCL; }
+    }
+    launch_pack_vertices(p->d_stage, p->nv, p->nv_pad, p->est_dim, p->d_est[p->cur], p->stream);
+    S3O_CUDA(cudaStreamSynchronize(p->stream));
+    p->stats.h2d_bytes += (int64_t)(count * ed * sizeof(double));
+    p->stats.kernel_launches += 1;
+    return S3O_OK;
+}
+
+int s3o_get_vertices_slice(s3o_problem *p, double *est_slice) {
+    if (!p || p->kind == S3O_KIND_BA || !p->d_est[0]) { set_error("s3o_get_vertices_slice: no vertices"); return S3O_ERR_INVALID; }
+    cudaSetDevice(p->device);
+    int rc = ensure_stage(p);
+    if (rc) return rc;
+    int first = 0, count = 0;
+    estimate_slice(p, p->dist ? p->comm.rank : 0, &first, &count);
+    if (count > 0 && !est_slice) { set_error("s3o_get_vertices_slice: null slice"); return S3O_ERR_INVALID; }
+    const size_t ed = (size_t)p->est_dim;
+    launch_unpack_vertices(p->d_est[p->cur], p->nv, p->nv_pad, p->est_dim, p->d_stage, p->stream);
+    if (count > 0) S3O_CUDA(cudaMemcpyAsync(est_slice, p->d_stage + first * ed, count * ed * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    S3O_CUDA(cudaStreamSynchronize(p->stream));
+    p->stats.d2h_bytes += (int64_t)(count * ed * sizeof(double));
+    p->stats.kernel_launches += 1;
+    return S3O_OK;
+}
+
 int s3o_set_edges(s3o_problem *p, int n, const int32_t *v0, const int32_t *v1, const double *meas, const double *info) {
     if (!p || n < 0 || (n > 0 && (!v0 || !v1 || !meas))) { set_error("s3o_set_edges: bad arguments"); return S3O_ERR_INVALID; }
     if (p->kind == S3O_KIND_BA) { set_error("s3o_set_edges: a BA problem takes s3o_ba_set_observations"); return S3O_ERR_INVALID; }

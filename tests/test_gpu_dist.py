@@ -27,6 +27,7 @@ def test_partitioned_solve_matches_single_gpu(precond, graph):
     assert "DIST_CHECK PASS" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
     assert "ESTIMATES_IDENTICAL_ACROSS_RANKS True" in out.stdout
     assert "UPDATE_PARTITIONED" in out.stdout and "UPDATE_PARTITIONED max diff" in out.stdout and "FAIL" not in out.stdout
+    assert "ESTIMATE_SLICES PASS" in out.stdout        # s3o_set_estimates_slice / s3o_get_vertices_slice
     # ghost columns are read over NVLink inside the SpMV (CUDA IPC mappings); a box without peer access falls back to
     # NCCL send/recv on all ranks, which is correct but not what this test is meant to exercise
     assert "P2P_HALO " in out.stdout

@@ -431,3 +431,21 @@ def test_stop_rules(sphere_small):
         assert free.stats()["stop_reason"] in (0, 4) and n_f >= n_g
     finally:
         orc.set_math_mode(orc.MATH_REFERENCE)
+
+
+@pytest.mark.gpu
+def test_estimate_slices_without_a_communicator(sphere_small):
+    """s3o_*_slice on one GPU: the slice is the whole vertex range and the calls equal s3o_set_estimates / s3o_get_vertices
+    (the 2-rank behaviour is checked by tools/dist_check.py under tests/test_gpu_dist.py)."""
+    g = sphere_small
+    p = make_gpu(g)
+    assert p.estimate_slice() == (0, len(g["est"]))
+    est = np.ascontiguousarray(g["est"] * 1.0)
+    est[:, 4:7] += 0.5
+    p.set_estimates_slice(est)
+    out = np.zeros_like(est)
+    p.vertices_slice(out)
+    assert np.array_equal(out, est) and np.array_equal(p.vertices(), est)
+    q = make_gpu(g)
+    q.set_estimates(est)
+    assert p.chi2() == q.chi2()

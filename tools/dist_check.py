@@ -79,7 +79,25 @@ def main():
         print("UPDATE_PARTITIONED max diff %.3e %s" % (du, "PASS" if upd_ok else "FAIL"))
         ok = ok and upd_ok
     vd = vu
-    # every rank holds the same estimates after the solve and the update
+    # sharded host round trip: every rank writes only ITS slice of a new estimate vector (the rest of its host copy is
+    # garbage on purpose), after the collective every rank must hold all of it, and read its own slice back unchanged
+    first, count = pd.estimate_slice()
+    target = g["est"] + 0.0
+    target[:, 4:7] += 0.01 * np.arange(len(target))[:, None]
+    mine = np.ascontiguousarray(target[first:first + count])
+    pd.set_estimates_slice(mine)
+    back = np.zeros_like(mine)
+    pd.vertices_slice(back)
+    full = pd.vertices()
+    slice_ok = bool(np.array_equal(back, mine) and np.array_equal(full, target))
+    sl = torch.tensor([1.0 if slice_ok else 0.0], device="cuda")
+    dist.all_reduce(sl, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        covered = first == 0 and count == -(-len(target) // world)
+        print("ESTIMATE_SLICES", "PASS" if (sl.item() == 1.0 and covered) else "FAIL")
+        ok = ok and sl.item() == 1.0 and covered
+    vd = full
+    # every rank holds the same estimates after the solve, the update and the sliced upload
     t = torch.from_numpy(vd.copy()).cuda()
     ref = t.clone()
     dist.broadcast(ref, src=0)
