@@ -389,6 +389,9 @@ __global__ void __launch_bounds__(256) amg_dense_inverse_kernel(const double *__
     for (int t = threadIdx.x; t < N * N; t += blockDim.x) inv[t] = a[t];
 }
 
+// most threads per CTA of amg_dense_inverse_coop_kernel (one CTA per SM; 256 by default, S3O_DENSE_THREADS overrides
+// for experiments: every pivot step is a latency chain of d*N/threads loads and updates per thread)
+constexpr int kDenseCoopThreads = 512;
 // dynamic shared memory of amg_dense_inverse_coop_kernel: block row, pivot row, P, C, inversion work space
 inline size_t dense_coop_smem(int n, int d) { return ((size_t)2 * d * n * d + 2 * d * d + 2 * d * d) * sizeof(double); }
 
@@ -399,7 +402,7 @@ inline size_t dense_coop_smem(int n, int d) { return ((size_t)2 * d * n * d + 2 
 // CTA k+1 prepares P and rowbuf of the next step right after its own update, so there is ONE grid barrier per pivot
 // block.  No pivoting (the matrix is SPD).  pub: [2][d*N + d*d] double-buffered rowbuf + P in global memory.
 template <int D>
-__global__ void __launch_bounds__(256) amg_dense_inverse_coop_kernel(const double *__restrict__ A, const int32_t *__restrict__ rowptr,
+__global__ void __launch_bounds__(kDenseCoopThreads) amg_dense_inverse_coop_kernel(const double *__restrict__ A, const int32_t *__restrict__ rowptr,
                                                                      const int32_t *__restrict__ colidx, int n, double *inv,
                                                                      double *pub, DevScalars *sc, const GridBarrier gb) {
     extern __shared__ double smem[];
@@ -1643,7 +1646,8 @@ int update_values_t(s3o_problem *p, double lambda) {
             DevScalars *scp = p->d_sc;
             GridBarrier gb{};
             void *args[] = { &Ap, &rp, &ci, &n, &inv, &pub, &scp, &gb };
-            int rcl = launch_persistent(p, (const void *)amg_dense_inverse_coop_kernel<D>, n, 256, args, 8, dense_coop_smem(n, D));
+            static const int dense_threads = getenv("S3O_DENSE_THREADS") ? std::max(64, std::min(kDenseCoopThreads, atoi(getenv("S3O_DENSE_THREADS")))) : 256;
+            int rcl = launch_persistent(p, (const void *)amg_dense_inverse_coop_kernel<D>, n, dense_threads, args, 8, dense_coop_smem(n, D));
             if (rcl) return rcl;
         } else {
             amg_dense_inverse_kernel<D><<<1, 256, (size_t)(N * N + N) * sizeof(double), p->stream>>>(C.A, C.rowptr, C.colidx, C.n,
