@@ -389,9 +389,10 @@ __global__ void __launch_bounds__(256) amg_dense_inverse_kernel(const double *__
     for (int t = threadIdx.x; t < N * N; t += blockDim.x) inv[t] = a[t];
 }
 
-// most threads per CTA of amg_dense_inverse_coop_kernel (one CTA per SM; 256 by default, S3O_DENSE_THREADS overrides
-// for experiments: every pivot step is a latency chain of d*N/threads loads and updates per thread)
-constexpr int kDenseCoopThreads = 512;
+// most threads per CTA of amg_dense_inverse_coop_kernel (one CTA per SM).  Every pivot step is a latency chain of
+// d*N/threads loads and updates per thread (S1M, 96 pivots: 1.09 ms with 256 threads, 0.89 with 512, 0.84 with 1024);
+// S3O_DENSE_THREADS overrides for experiments.
+constexpr int kDenseCoopThreads = 1024;
 // dynamic shared memory of amg_dense_inverse_coop_kernel: block row, pivot row, P, C, inversion work space
 inline size_t dense_coop_smem(int n, int d) { return ((size_t)2 * d * n * d + 2 * d * d + 2 * d * d) * sizeof(double); }
 
@@ -1646,7 +1647,7 @@ int update_values_t(s3o_problem *p, double lambda) {
             DevScalars *scp = p->d_sc;
             GridBarrier gb{};
             void *args[] = { &Ap, &rp, &ci, &n, &inv, &pub, &scp, &gb };
-            static const int dense_threads = getenv("S3O_DENSE_THREADS") ? std::max(64, std::min(kDenseCoopThreads, atoi(getenv("S3O_DENSE_THREADS")))) : 256;
+            static const int dense_threads = getenv("S3O_DENSE_THREADS") ? std::max(64, std::min(kDenseCoopThreads, atoi(getenv("S3O_DENSE_THREADS")))) : kDenseCoopThreads;
             int rcl = launch_persistent(p, (const void *)amg_dense_inverse_coop_kernel<D>, n, dense_threads, args, 8, dense_coop_smem(n, D));
             if (rcl) return rcl;
         } else {
