@@ -143,3 +143,43 @@ def test_fixed_vertices_are_excluded(ba_small):
     p.optimize(3)
     assert np.array_equal(p.cameras()[0], cams0[0]) and np.array_equal(p.points()[:5], pts0[:5])
     assert not np.array_equal(p.cameras()[1], cams0[1])
+
+
+def test_ba_lm_fixed_point_against_scipy_least_squares():
+    """Independent pin of the BA oracle's LM (Jacobians, Schur complement, LDL^T, LM rules): scipy's trust-region
+    least squares with finite-difference Jacobians, over the same residuals on a chart around the initial guess
+    (cameras: exp(delta) * cam, points: additive), reaches the same stationary point."""
+    from scipy.optimize import least_squares
+    g = synth.ba_loop(6, 40, 4, seed=3)
+    nc, npt = len(g["cams"]), len(g["points"])
+    cam_fixed = np.zeros(nc, np.uint8)
+    cam_fixed[:2] = 1                                   # gauge: two cameras pin the similarity
+    p = make(g, robust=False, cam_fixed=cam_fixed)
+    p.build_structure()
+    n, chi2, _, _ = p.optimize(60)
+    cams_lm, pts_lm = p.cameras(), p.points()
+    free_c = np.flatnonzero(cam_fixed == 0)
+    q = make(g, robust=False, cam_fixed=cam_fixed)
+
+    def state(x):
+        cams = g["cams"].copy()
+        for k, c in enumerate(free_c):
+            cams[c] = orc.se3_mul(orc.se3_exp(x[6 * k:6 * k + 6]), g["cams"][c])
+        pts = g["points"] + x[6 * len(free_c):].reshape(npt, 3)
+        return cams, pts
+
+    def residuals(x):
+        cams, pts = state(x)
+        q.set(cams, pts, g["obs_cam"], g["obs_pt"], g["uv"], g["focal"], g["cx"], g["cy"], cam_fixed=cam_fixed)
+        q.build_structure()
+        return q.edge_errors().ravel()
+
+    sol = least_squares(residuals, np.zeros(6 * len(free_c) + 3 * npt), method="trf", xtol=1e-15, ftol=1e-15, gtol=1e-10,
+                        x_scale="jac", max_nfev=300)
+    chi2_sp = float((sol.fun ** 2).sum())
+    cams_sp, pts_sp = state(sol.x)
+    assert abs(chi2 - chi2_sp) <= 1e-8 * chi2_sp, (chi2, chi2_sp, n)
+    sgn = np.sign((cams_lm[:, :4] * cams_sp[:, :4]).sum(1))[:, None]
+    assert np.abs(cams_lm[:, :4] - sgn * cams_sp[:, :4]).max() <= 1e-5
+    assert np.abs(cams_lm[:, 4:] - cams_sp[:, 4:]).max() <= 1e-4
+    assert np.abs(pts_lm - pts_sp).max() <= 1e-3
